@@ -1,0 +1,432 @@
+/* zz_oracle.c -- CPU oracle for the factorised local-ZigZag event loop.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product path: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
+ *
+ * PARITY UNPINNED: the reference (ZigZagBoomerang.jl @ 691afe2) is pure Julia, Julia is not
+ * installed in this image, and the reference's tests hold no golden vector for this path
+ * (SURVEY.md 8(c)): every sampler test is a law-of-large-numbers check with an unpinned seed.
+ * This file is therefore a line-by-line RESTATEMENT of the algorithm, pinned only by the
+ * reference's property tests (test/poisson.jl) and statistical tests (test/maintest.jl), which
+ * tests/ re-runs against it.
+ *
+ * What is restated (file:line in /root/reference):
+ *   spdmp setup + outer loop          src/sfact.jl:162-212   (zzo_spdmp)
+ *   spdmp_inner!                      src/sfact.jl:73-145    (inner_event)
+ *   smove_forward! (ZigZag)           src/sfact.jl:6-28      (move_nbhd, move_all)
+ *   lambda / lambda-bar               src/fact_samplers.jl:28-30, src/sfact.jl:69-70
+ *   ab (ZigZag)                       src/fact_samplers.jl:41,50-54   (ab_zigzag)
+ *   adapt!                            src/fact_samplers.jl:67-70
+ *   idot                              src/common.jl:16-24    (idot)
+ *   poisson_time                      src/poissontime.jl:8-30 (o_poisson_time)
+ *   SPriorityQueue                    src/priorityqueue.jl:44-117 (heap_*)
+ *   reflect! (scalar)                 src/dynamics.jl:46-49
+ *   event / Trace push                src/sfact.jl:50-52, src/trace.jl:38,73
+ *   mean(::Trace)                     src/trace.jl:182-200   (zzo_moments, first moment)
+ *   RNG                               src/ZigZagBoomerang.jl:6-10 -> RandomNumbers.jl 1.5.3
+ *                                     Xorshifts.Xoroshiro128Plus (third-party, absent from
+ *                                     /root/reference; restated from the published
+ *                                     xoroshiro128+ algorithm, 2016 constants 55/14/36)
+ *
+ * Two independent switches (mode bits):
+ *   RNG    0 = "seq": ONE xoroshiro128+ stream consumed in global event order exactly where the
+ *              reference calls rand(rng) (sfact.jl:121,134,139,186).
+ *          1 = "ctr": per-coordinate counter streams u(j,k) (zz_math.h): coordinate j consumes
+ *              one draw every time IT is (re)scheduled and one every time IT proposes.  Same
+ *              roles as the reference, but schedule-independent -- the GPU parity contract.
+ *   ARITH  0 = "inplace": neighbours are advanced in place at every proposal like the reference.
+ *          2 = "lazy": positions are anchored at the coordinate's own last flip,
+ *              x_j(s) = xf_j + th_j (s - tf_j); only the owner ever rewrites them.
+ *   GRAPH  4 = All() neighbourhood (pdmp, sfact.jl:236) instead of Matched().
+ * GPU results must equal mode ctr|lazy bit for bit.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#include "../zigzagboomerang.jl_b200/csrc/zz_math.h" /* zz_log, zz_u01 only (shared primitives) */
+
+#define ZZO_RNG_CTR 1
+#define ZZO_ARITH_LAZY 2
+#define ZZO_GRAPH_ALL 4
+
+#define ZZO_OK 0
+#define ZZO_E_BOUND 3 /* "Tuning parameter `c` too small." sfact.jl:124 */
+#define ZZO_E_GRAPH 4
+#define ZZO_E_ARG 1
+
+typedef struct { double t; int64_t i; double x; double th; } zzo_event; /* trace.jl:38 */
+
+typedef struct {
+    int64_t d;
+    int mode;
+    /* results */
+    zzo_event *ev; int64_t nev, cap;
+    int64_t *acc; int64_t num;
+    double *t, *x, *th; /* final state */
+    double *c;
+    double *x0; double t0;
+    int status; int64_t err_i; double err_t, err_l, err_lb;
+} zzo_run;
+
+/* ---- poisson_time, src/poissontime.jl:8-30 ------------------------------------------------ */
+static double o_poisson_time(double a, double b, double u)
+{
+    if (b > 0) {
+        if (a < 0)
+            return sqrt(-zz_log(u) * 2.0 / b) - a / b;
+        else
+            return sqrt((a / b) * (a / b) - zz_log(u) * 2.0 / b) - a / b;
+    } else if (b == 0) {
+        if (a > 0)
+            return -zz_log(u) / a;
+        else
+            return INFINITY;
+    } else {
+        if (a <= 0)
+            return INFINITY;
+        else if (-zz_log(u) <= -(a * a) / b + (a * a) / (2 * b))
+            return -sqrt((a / b) * (a / b) - zz_log(u) * 2.0 / b) - a / b;
+        else
+            return INFINITY;
+    }
+}
+double zzo_poisson_time(double a, double b, double u) { return o_poisson_time(a, b, u); }
+
+/* three-parameter form c + (a+bt)^+, src/poissontime.jl:39-65 */
+double zzo_poisson_time3(double a, double b, double c, double u)
+{
+    if (b > 0) {
+        if (a < 0) {
+            if (-c * a / b + zz_log(u) < 0.0)
+                return sqrt(-2 * b * zz_log(u) + c * c + 2 * a * c) / b - (a + c) / b;
+            else
+                return -zz_log(u) / c;
+        } else
+            return sqrt(-zz_log(u) * 2.0 * b + (a + c) * (a + c)) / b - (a + c) / b;
+    } else if (b == 0) {
+        if (a > 0)
+            return -zz_log(u) / (a + c);
+        else
+            return -zz_log(u) / c;
+    } else {
+        if (a <= 0.0)
+            return -zz_log(u) / c;
+        else if (-c * a / b - (a * a) / (2 * b) + zz_log(u) > 0.0)
+            return +sqrt((a + c) * (a + c) - 2.0 * zz_log(u) * b) / b - (a + c) / b;
+        else
+            return (-zz_log(u) + (a * a) / (2 * b)) / c;
+    }
+}
+double zzo_log(double x) { return zz_log(x); }
+double zzo_u01(uint64_t s0, uint64_t s1, uint64_t i, uint64_t k) { return zz_u01(s0, s1, i, k); }
+
+/* ---- xoroshiro128+ (RandomNumbers.jl Xorshifts.Xoroshiro128Plus; restated, unpinned) ------- */
+typedef struct { uint64_t x, y; } xoro;
+static inline uint64_t rotl64(uint64_t v, int k) { return (v << k) | (v >> (64 - k)); }
+static inline uint64_t xoro_next(xoro *r)
+{
+    uint64_t s0 = r->x, s1 = r->y, p = s0 + s1;
+    s1 ^= s0;
+    r->x = rotl64(s0, 55) ^ s1 ^ (s1 << 14);
+    r->y = rotl64(s1, 36);
+    return p;
+}
+static inline double xoro_rand(xoro *r)
+{ /* 52 high bits into the mantissa of [1,2), minus one -> [0,1) */
+    uint64_t v = (xoro_next(r) >> 12) | 0x3ff0000000000000ULL;
+    double d; memcpy(&d, &v, 8);
+    return d - 1.0;
+}
+
+/* ---- SPriorityQueue, src/priorityqueue.jl ------------------------------------------------- */
+typedef struct { int64_t n; int64_t *key; double *val; int64_t *index; int lex; } heapq; /* 1-based */
+static inline int h_lt(const heapq *q, double va, int64_t ka, double vb, int64_t kb)
+{ /* lt(o, a, b) on the priorities (:44-75); with lex set, ties are broken by key so that the
+     ctr-mode event order is a strict total order (DESIGN.md "ties"). */
+    if (va < vb) return 1;
+    if (q->lex && va == vb) return ka < kb;
+    return 0;
+}
+static void h_down(heapq *q, int64_t i)
+{ /* percolate_down! :44-59 */
+    int64_t xk = q->key[i]; double xv = q->val[i];
+    int64_t l;
+    while ((l = 2 * i) <= q->n) {
+        int64_t r = 2 * i + 1;
+        int64_t j = (r > q->n || h_lt(q, q->val[l], q->key[l], q->val[r], q->key[r])) ? l : r;
+        if (h_lt(q, q->val[j], q->key[j], xv, xk)) {
+            q->index[q->key[j]] = i; q->key[i] = q->key[j]; q->val[i] = q->val[j];
+            i = j;
+        } else break;
+    }
+    q->index[xk] = i; q->key[i] = xk; q->val[i] = xv;
+}
+static void h_up(heapq *q, int64_t i)
+{ /* percolate_up! :61-75 */
+    int64_t xk = q->key[i]; double xv = q->val[i];
+    while (i > 1) {
+        int64_t j = i / 2;
+        if (h_lt(q, xv, xk, q->val[j], q->key[j])) {
+            q->index[q->key[j]] = i; q->key[i] = q->key[j]; q->val[i] = q->val[j];
+            i = j;
+        } else break;
+    }
+    q->index[xk] = i; q->key[i] = xk; q->val[i] = xv;
+}
+static void h_enqueue(heapq *q, int64_t key, double v)
+{ /* enqueue! :105-115 (keys arrive in order 1..n) */
+    q->n += 1; q->key[q->n] = key; q->val[q->n] = v; q->index[key] = q->n;
+    h_up(q, q->n);
+}
+static void h_set(heapq *q, int64_t key, double v)
+{ /* setindex! :93-103 */
+    int64_t i = q->index[key];
+    double old = q->val[i];
+    q->val[i] = v;
+    if (h_lt(q, old, key, v, key)) h_down(q, i); else h_up(q, i);
+}
+
+/* ---- sparse helpers ------------------------------------------------------------------------ */
+typedef struct { const int64_t *colptr, *rowval; const double *nzval; } csc; /* 1-based, Julia layout */
+
+static double idot(const csc *A, int64_t j, const double *x)
+{ /* src/common.jl:16-24; j and rowval 1-based, x 0-based storage */
+    double s = 0.0;
+    for (int64_t p = A->colptr[j - 1]; p < A->colptr[j]; ++p)
+        s += A->nzval[p - 1] * x[A->rowval[p - 1] - 1];
+    return s;
+}
+
+typedef struct {
+    int64_t d; int mode;
+    csc tg, bd; const double *h, *mu;
+    double *t, *x, *th, *t_old, *ba, *bb, *c;
+    double *tf, *xf;           /* lazy anchors */
+    uint32_t *kctr;            /* ctr-mode per-coordinate draw counters */
+    uint64_t s0, s1; xoro rng;
+    int64_t *g2ptr, *g2idx;    /* G2 neighbourhoods (sfact.jl:178), 1-based ids */
+    double *scratch;           /* lazy mode: positions/velocities gathered for idot */
+} ctx;
+
+static inline double draw(ctx *z, int64_t j /*1-based coordinate consuming the draw*/)
+{
+    if (z->mode & ZZO_RNG_CTR) return zz_u01(z->s0, z->s1, (uint64_t)(j - 1), z->kctr[j - 1]++);
+    return xoro_rand(&z->rng);
+}
+
+/* position of coordinate k (1-based) at time s */
+static inline double pos_at(const ctx *z, int64_t k, double s)
+{
+    if (z->mode & ZZO_ARITH_LAZY) return z->xf[k - 1] + z->th[k - 1] * (s - z->tf[k - 1]);
+    return z->x[k - 1]; /* inplace: caller has moved it to s already */
+}
+
+/* idot over positions at time s (lazy: evaluate on the fly in storage order) */
+static double idot_x(const ctx *z, const csc *A, int64_t j, double s)
+{
+    if (!(z->mode & ZZO_ARITH_LAZY)) return idot(A, j, z->x);
+    double acc = 0.0;
+    for (int64_t p = A->colptr[j - 1]; p < A->colptr[j]; ++p)
+        acc += A->nzval[p - 1] * pos_at(z, A->rowval[p - 1], s);
+    return acc;
+}
+
+/* ab(G,i,x,th,c,Z::ZigZag), src/fact_samplers.jl:50-54 with loosen(c,x) = c + x (:41) */
+static void ab_zigzag(ctx *z, int64_t i, double s)
+{
+    double a = z->c[i - 1] + (idot_x(z, &z->bd, i, s) - idot(&z->bd, i, z->mu)) * z->th[i - 1];
+    double b = z->c[i - 1] / 100 + z->th[i - 1] * idot(&z->bd, i, z->th);
+    z->ba[i - 1] = a; z->bb[i - 1] = b;
+}
+
+/* smove_forward!(G,i,...) over column i of the bound matrix (G = G1, Matched), sfact.jl:6-12 */
+static void move_nbhd(ctx *z, const int64_t *idx, int64_t n, double tp)
+{
+    for (int64_t q = 0; q < n; ++q) {
+        int64_t k = idx[q] - 1;
+        z->x[k] = z->x[k] + z->th[k] * (tp - z->t[k]);
+        z->t[k] = tp;
+    }
+}
+static void move_all(ctx *z, double tp)
+{ /* sfact.jl:23-28 */
+    for (int64_t k = 0; k < z->d; ++k) {
+        z->x[k] = z->x[k] + z->th[k] * (tp - z->t[k]);
+        z->t[k] = tp;
+    }
+}
+
+static void push_event(zzo_run *r, double t, int64_t i, double x, double th)
+{
+    if (r->nev == r->cap) {
+        r->cap = r->cap ? 2 * r->cap : 1024;
+        r->ev = (zzo_event *)realloc(r->ev, (size_t)r->cap * sizeof(zzo_event));
+    }
+    zzo_event e = { t, i, x, th };
+    r->ev[r->nev++] = e;
+}
+
+/* Build G2[i] = setdiff(union(G1[j] for j in G1[i]), G[i]) with G = G1 (sfact.jl:178). */
+static void build_g2(ctx *z)
+{
+    int64_t d = z->d;
+    z->g2ptr = (int64_t *)calloc((size_t)d + 1, sizeof(int64_t));
+    int64_t *mark = (int64_t *)calloc((size_t)d + 1, sizeof(int64_t));
+    int64_t cap = 16, n = 0;
+    z->g2idx = (int64_t *)malloc((size_t)cap * sizeof(int64_t));
+    for (int64_t i = 1; i <= d; ++i) {
+        z->g2ptr[i - 1] = n;
+        for (int64_t p = z->bd.colptr[i - 1]; p < z->bd.colptr[i]; ++p) mark[z->bd.rowval[p - 1]] = -i; /* in G[i] */
+        for (int64_t p = z->bd.colptr[i - 1]; p < z->bd.colptr[i]; ++p) {
+            int64_t j = z->bd.rowval[p - 1];
+            for (int64_t q = z->bd.colptr[j - 1]; q < z->bd.colptr[j]; ++q) {
+                int64_t k = z->bd.rowval[q - 1];
+                if (mark[k] == -i || mark[k] == i) continue;
+                mark[k] = i;
+                if (n == cap) { cap *= 2; z->g2idx = (int64_t *)realloc(z->g2idx, (size_t)cap * sizeof(int64_t)); }
+                z->g2idx[n++] = k;
+            }
+        }
+    }
+    z->g2ptr[d] = n;
+    free(mark);
+}
+
+zzo_run *zzo_spdmp(int64_t d,
+                   const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
+                   const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
+                   double t0, const double *x0, const double *th0, double T, const double *c_in,
+                   const uint64_t *seed, int adapt, double factor, int mode)
+{
+    zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run));
+    ctx zs; ctx *z = &zs; memset(z, 0, sizeof(ctx));
+    r->d = d; r->mode = mode; r->t0 = t0;
+    z->d = d; z->mode = mode;
+    z->tg.colptr = tg_colptr; z->tg.rowval = tg_rowval; z->tg.nzval = tg_nzval;
+    z->bd.colptr = bd_colptr; z->bd.rowval = bd_rowval; z->bd.nzval = bd_nzval;
+    z->h = h; z->mu = mu;
+    size_t nb = (size_t)d * sizeof(double);
+    z->t = (double *)malloc(nb); z->x = (double *)malloc(nb); z->th = (double *)malloc(nb);
+    z->t_old = (double *)malloc(nb); z->ba = (double *)malloc(nb); z->bb = (double *)malloc(nb);
+    z->c = (double *)malloc(nb); z->tf = (double *)malloc(nb); z->xf = (double *)malloc(nb);
+    z->kctr = (uint32_t *)calloc((size_t)d, sizeof(uint32_t));
+    r->acc = (int64_t *)calloc((size_t)d, sizeof(int64_t));
+    r->x0 = (double *)malloc(nb); memcpy(r->x0, x0, nb);
+    z->s0 = seed[0]; z->s1 = seed[1]; z->rng.x = seed[0]; z->rng.y = seed[1];
+    const int lazy = (mode & ZZO_ARITH_LAZY) != 0, all = (mode & ZZO_GRAPH_ALL) != 0;
+
+    /* sfact.jl:167-169,180 */
+    double tp = t0;
+    for (int64_t k = 0; k < d; ++k) {
+        z->t[k] = t0; z->t_old[k] = t0; z->x[k] = x0[k]; z->th[k] = th0[k]; z->c[k] = c_in[k];
+        z->tf[k] = t0; z->xf[k] = x0[k];
+    }
+    if (!all && !lazy) build_g2(z); /* sfact.jl:171-179 (lazy arithmetic needs no moves at all) */
+
+    heapq Q; Q.n = 0; Q.lex = (mode & ZZO_RNG_CTR) != 0;
+    Q.key = (int64_t *)malloc(((size_t)d + 2) * sizeof(int64_t));
+    Q.val = (double *)malloc(((size_t)d + 2) * sizeof(double));
+    Q.index = (int64_t *)malloc(((size_t)d + 2) * sizeof(int64_t));
+    /* sfact.jl:184-187: bounds, then the queue is filled in coordinate order, NO "+ t0" */
+    for (int64_t i = 1; i <= d; ++i) ab_zigzag(z, i, t0);
+    for (int64_t i = 1; i <= d; ++i) h_enqueue(&Q, i, o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i)));
+
+    int64_t num = 0;
+    /* sfact.jl:199 outer loop; body = spdmp_inner! (:73-145), refresh branch omitted (lambda_ref == 0,
+       fact_samplers.jl:19) */
+    while (tp < T && r->status == ZZO_OK) {
+        for (;;) {
+            int64_t i = Q.key[1]; tp = Q.val[1]; /* peek :77 */
+            const int64_t *nb = &z->bd.rowval[z->bd.colptr[i - 1] - 1];
+            int64_t nnb = z->bd.colptr[i] - z->bd.colptr[i - 1];
+            if (!lazy) { if (all) move_all(z, tp); else move_nbhd(z, nb, nnb, tp); } /* :82 */
+            double gi = idot_x(z, &z->tg, i, tp);           /* :118, user closure = idot(Gamma,i,x) */
+            if (h) gi = gi - h[i - 1];
+            double ti = lazy ? tp : z->t[i - 1];
+            double l = zz_pos(gi * z->th[i - 1]);                                   /* :119, fact_samplers.jl:28-30 */
+            double lb = zz_pos(z->ba[i - 1] + z->bb[i - 1] * (ti - z->t_old[i - 1])); /* sfact.jl:70 */
+            num += 1;                                                               /* :120 */
+            if (draw(z, i) * lb < l) {                                              /* :121 */
+                r->acc[i - 1] += 1;
+                if (l >= lb) {                                                      /* :123-128 */
+                    if (!adapt) {
+                        r->status = ZZO_E_BOUND; r->err_i = i; r->err_t = tp; r->err_l = l; r->err_lb = lb;
+                        break;
+                    }
+                    z->c[i - 1] *= factor;
+                }
+                if (!lazy && !all)                                                  /* :129 */
+                    move_nbhd(z, &z->g2idx[z->g2ptr[i - 1]], z->g2ptr[i] - z->g2ptr[i - 1], tp);
+                if (lazy) { z->xf[i - 1] = pos_at(z, i, tp); z->tf[i - 1] = tp; }
+                z->th[i - 1] = -z->th[i - 1];                                       /* :130, dynamics.jl:46-49 */
+                for (int64_t q = 0; q < nnb; ++q) {                                 /* :131-135 */
+                    int64_t j = nb[q];
+                    ab_zigzag(z, j, tp);
+                    double tj = lazy ? tp : z->t[j - 1];
+                    z->t_old[j - 1] = tj;
+                    h_set(&Q, j, tj + o_poisson_time(z->ba[j - 1], z->bb[j - 1], draw(z, j)));
+                }
+                push_event(r, ti, i, lazy ? z->xf[i - 1] : z->x[i - 1], z->th[i - 1]); /* :143, :50-52 */
+                break;
+            } else {                                                                /* :137-140 */
+                ab_zigzag(z, i, tp);
+                z->t_old[i - 1] = ti;
+                h_set(&Q, i, ti + o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i)));
+            }
+        }
+    }
+    r->num = num;
+    r->t = lazy ? z->tf : z->t; r->x = lazy ? z->xf : z->x; r->th = z->th; r->c = z->c;
+    if (lazy) { free(z->t); free(z->x); } else { free(z->tf); free(z->xf); }
+    free(z->t_old); free(z->ba); free(z->bb); free(z->kctr);
+    free(Q.key); free(Q.val); free(Q.index);
+    free(z->g2ptr); free(z->g2idx);
+    return r;
+}
+
+int zzo_status(const zzo_run *r) { return r->status; }
+void zzo_error_info(const zzo_run *r, int64_t *i, double *t, double *l, double *lb)
+{ *i = r->err_i; *t = r->err_t; *l = r->err_l; *lb = r->err_lb; }
+int64_t zzo_trace_len(const zzo_run *r) { return r->nev; }
+void zzo_trace_copy(const zzo_run *r, zzo_event *dst, int64_t first, int64_t count)
+{ memcpy(dst, r->ev + first, (size_t)count * sizeof(zzo_event)); }
+void zzo_counts(const zzo_run *r, int64_t *acc, int64_t *num)
+{ memcpy(acc, r->acc, (size_t)r->d * sizeof(int64_t)); *num = r->num; }
+void zzo_final_state(const zzo_run *r, double *t, double *x, double *th, double *c)
+{
+    size_t nb = (size_t)r->d * sizeof(double);
+    memcpy(t, r->t, nb); memcpy(x, r->x, nb); memcpy(th, r->th, nb); memcpy(c, r->c, nb);
+}
+
+/* First moment exactly as Statistics.mean(::Trace), src/trace.jl:182-200 (m1), and the matching
+ * exact second moment of the piecewise-linear path (m2; ours -- the reference has no event-based
+ * second moment, its tests discretise).  s1/s2 are the unscaled per-coordinate sums the GPU
+ * accumulates: s1 = sum (x+xi)(t2-t), s2 = sum (t2-t)(x*x + x*xi + xi*xi). */
+void zzo_moments(const zzo_run *r, double *m1, double *m2, double *s1, double *s2)
+{
+    int64_t d = r->d;
+    double *x = (double *)malloc((size_t)d * sizeof(double));
+    double *t = (double *)malloc((size_t)d * sizeof(double));
+    for (int64_t k = 0; k < d; ++k) { x[k] = r->x0[k]; t[k] = r->t0; m1[k] = 0.0; m2[k] = 0.0; s1[k] = 0.0; s2[k] = 0.0; }
+    if (r->nev == 0) { free(x); free(t); return; }
+    double T = r->ev[r->nev - 1].t;
+    double scale = 1 / (2 * T);
+    for (int64_t k = 0; k < r->nev; ++k) {
+        double t2 = r->ev[k].t, xi = r->ev[k].x; int64_t i = r->ev[k].i - 1;
+        m1[i] += (x[i] + xi) * (t2 - t[i]) * scale;
+        s1[i] += (x[i] + xi) * (t2 - t[i]);
+        s2[i] += (t2 - t[i]) * (x[i] * x[i] + x[i] * xi + xi * xi);
+        t[i] = t2; x[i] = xi;
+    }
+    for (int64_t k = 0; k < d; ++k) m2[k] = s2[k] / (3 * T);
+    free(x); free(t);
+}
+
+void zzo_free(zzo_run *r)
+{
+    if (!r) return;
+    free(r->ev); free(r->acc); free(r->t); free(r->x); free(r->th); free(r->c); free(r->x0);
+    free(r);
+}

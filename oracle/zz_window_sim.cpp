@@ -1,0 +1,195 @@
+// zz_window_sim.cpp -- single-threaded HOST EMULATION of the windowed relaxation schedule the sm_100a
+// kernel runs (zigzagboomerang.jl_b200/csrc/zz_kernels.cu), built on the very same per-coordinate code
+// (zz_core.h, zz_ctl.h, zz_host_graph.h).
+//
+// TEST INFRASTRUCTURE ONLY (lives under oracle/ for that reason): it exists so the scheme can be checked
+// against the sequential oracle (zz_oracle.c, mode ctr|lazy) on a machine without a GPU.  It is not a
+// fallback: the product library (csrc/zzb200.cpp) never links or calls it and fails loudly without CUDA.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "../zigzagboomerang.jl_b200/csrc/zz_core.h"
+#include "../zigzagboomerang.jl_b200/csrc/zz_ctl.h"
+#include "../zigzagboomerang.jl_b200/csrc/zz_host_graph.h"
+
+struct zzw_event { double t; int64_t i; double x; double th; };
+
+struct zzw_run {
+    int64_t d = 0;
+    std::vector<zzw_event> ev;
+    std::vector<int64_t> acc;
+    int64_t num = 0;
+    std::vector<double> t, x, th, c, s1, s2;
+    int status = 0; int64_t err_i = 0; double err_t = 0, err_l = 0, err_lb = 0;
+    // schedule statistics
+    int64_t windows = 0, retries = 0, iters = 0, node_evals = 0, max_iters = 0;
+    std::string msg;
+};
+
+extern "C" {
+
+zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const double* tnz, const double* h,
+                   const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
+                   const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
+                   int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit)
+{
+    zzw_run* r = new zzw_run();
+    r->d = d;
+    ZzHostGraph G;
+    std::string e = zz_build_graph(G, d, tcp, trv, tnz, h, bcp, brv, bnz, mu);
+    if (!e.empty()) { r->status = 4; r->msg = e; return r; }
+    std::vector<ZzKin> kin(d);
+    std::vector<double> flips((size_t)d * 2 * ZZ_MAXFLIP, 0.0);
+    std::vector<ZzPriv> priv(d);
+    std::vector<double> tau(d);
+    std::vector<uint32_t> kctr(d), dstamp(d, 0);
+    std::vector<ZzSpec> spec(d);
+    std::vector<double> vt(d), vl(d), vlb(d);
+    r->acc.assign(d, 0); r->s1.assign(d, 0.0); r->s2.assign(d, 0.0);
+
+    ZzGraph g; g.nptr = G.nptr.data(); g.nidx = G.nidx.data(); g.nwt = G.nwt.data(); g.nwb = G.nwb.data();
+    g.nfl = G.nfl.data(); g.gmu = G.gmu.data(); g.h = G.has_h ? G.h.data() : nullptr; g.same = G.same;
+    ZzView v; v.d = (int32_t)d; v.kin = kin.data(); v.flips = flips.data(); v.priv = priv.data();
+    v.tau = tau.data(); v.kctr = kctr.data(); v.seed0 = seed[0]; v.seed1 = seed[1]; v.adapt = adapt; v.factor = factor;
+
+    for (int64_t j = 0; j < d; ++j) {
+        kin[j].theta = th0[j]; kin[j].tf = t0; kin[j].xf = x0[j]; kin[j].hdr[0] = kin[j].hdr[1] = 0;
+        priv[j].c = c_in[j];
+    }
+    double F0 = ZZ_INF;
+    for (int64_t j = 0; j < d; ++j) { zz_init_node(g, v, (int32_t)j, t0); F0 = std::min(F0, tau[j]); }
+    if (!(t0 < T)) goto finish;  // while t' < T never entered (sfact.jl:199)
+    {
+        ZzCtl ctl;
+        double target = std::max(target_frac * (double)d, 4.0);
+        zz_ctl_init(ctl, std::min(F0, T), T, delta0, target);
+        uint32_t cur = 0;
+        std::vector<int32_t> wl, next, touched;
+        auto handle = [&](int32_t j, const ZzNodeOut& o, uint32_t w0, uint32_t curtag) {
+            int slot;
+            uint32_t cnt = zz_pick_slot(kin[j].hdr[0], kin[j].hdr[1], w0, curtag, slot);
+            bool same = (cnt == o.nflip);
+            if (same && cnt) {
+                const double* fl = &flips[((size_t)j * 2 + slot) * ZZ_MAXFLIP];
+                for (uint32_t m = 0; m < cnt && same; ++m) same = (zz_d2u(fl[m]) == zz_d2u(o.fl[m]));
+            }
+            if (!same) {
+                int ws = (slot == 0) ? 1 : 0;
+                double* fl = &flips[((size_t)j * 2 + ws) * ZZ_MAXFLIP];
+                for (uint32_t m = 0; m < o.nflip; ++m) fl[m] = o.fl[m];
+                kin[j].hdr[ws] = (curtag << 4) | o.nflip;
+                for (int32_t q = G.dptr[j]; q < G.dptr[j + 1]; ++q) {
+                    int32_t k = G.didx[q];
+                    uint32_t old = dstamp[k];
+                    if (old != curtag + 1) {
+                        dstamp[k] = curtag + 1;
+                        next.push_back(k);
+                        if (old < w0) touched.push_back(k);
+                    }
+                }
+            }
+            ZzSpec& s = spec[j];
+            s.a = o.a; s.b = o.b; s.told = o.told; s.tau = o.tau; s.c = o.c; s.k = o.k;
+            s.nprop = (uint16_t)o.nprop; s.nflip = (uint8_t)o.nflip; s.flags = (uint8_t)o.flags;
+            vt[j] = o.viol_t; vl[j] = o.viol_l; vlb[j] = o.viol_lb;
+            r->node_evals++;
+        };
+        while (ctl.phase != ZZ_PH_DONE && ctl.phase != ZZ_PH_FAIL) {
+            if (cur > tag_limit) {  // tag rebase
+                for (int64_t j = 0; j < d; ++j) { kin[j].hdr[0] = kin[j].hdr[1] = 0; dstamp[j] = 0; }
+                cur = 0;
+            }
+            zz_ctl_begin(ctl);
+            const uint32_t w0 = cur + 1;
+            cur = w0;
+            wl.clear(); next.clear(); touched.clear();
+            ZzNodeOut o;
+            int64_t it = 1;
+            for (int64_t j = 0; j < d; ++j) {
+                double tj = tau[j];
+                if (tj < ctl.H || (ctl.incl && tj == ctl.H)) {
+                    // dirtied already by an earlier node of this pass? then it is in `next` as well; fine.
+                    if (dstamp[j] < w0) { dstamp[j] = cur; touched.push_back((int32_t)j); }
+                    zz_process_node(g, v, (int32_t)j, ctl.H, ctl.incl, w0, cur, true, o);
+                    handle((int32_t)j, o, w0, cur);
+                }
+            }
+            for (;;) {
+                cur++;
+                wl.swap(next); next.clear();
+                if (wl.empty()) break;
+                ++it;
+                for (int32_t j : wl) {
+                    zz_process_node(g, v, j, ctl.H, ctl.incl, w0, cur, false, o);
+                    handle(j, o, w0, cur);
+                }
+            }
+            r->iters += it; r->max_iters = std::max(r->max_iters, it);
+            bool overflow = false; double smin = ZZ_INF; unsigned long long nprop = 0;
+            for (int32_t j : touched) {
+                const ZzSpec& s = spec[j];
+                if (s.flags & ZZ_F_OVERFLOW) overflow = true;
+                nprop += s.nprop;
+                if (s.nflip) {
+                    int slot; zz_pick_slot(kin[j].hdr[0], kin[j].hdr[1], w0, cur, slot);
+                    smin = std::min(smin, flips[((size_t)j * 2 + slot) * ZZ_MAXFLIP]);
+                }
+            }
+            int act = zz_ctl_end(ctl, overflow, smin, nprop);
+            if (act != ZZ_ACT_COMMIT) { r->retries++; continue; }
+            r->windows++;
+            size_t seg0 = r->ev.size();
+            for (int32_t j : touched) {
+                const ZzSpec& s = spec[j];
+                if ((s.flags & ZZ_F_VIOL) && r->status == 0) {
+                    r->status = 3; r->err_i = j + 1; r->err_t = vt[j]; r->err_l = vl[j]; r->err_lb = vlb[j];
+                }
+                priv[j].a = s.a; priv[j].b = s.b; priv[j].told = s.told; priv[j].c = s.c;
+                tau[j] = s.tau; kctr[j] = s.k;
+                r->num += s.nprop;
+                if (s.nflip) {
+                    int slot; zz_pick_slot(kin[j].hdr[0], kin[j].hdr[1], w0, cur, slot);
+                    const double* fl = &flips[((size_t)j * 2 + slot) * ZZ_MAXFLIP];
+                    double th = kin[j].theta, tf = kin[j].tf, xf = kin[j].xf;
+                    for (uint32_t m = 0; m < s.nflip; ++m) {
+                        double fs = fl[m];
+                        double xs = xf + th * (fs - tf);
+                        r->s1[j] += (xf + xs) * (fs - tf);                        // trace.jl:194 (unscaled)
+                        r->s2[j] += (fs - tf) * (xf * xf + xf * xs + xs * xs);
+                        th = -th; tf = fs; xf = xs;
+                        r->ev.push_back(zzw_event{ fs, j + 1, xs, th });          // sfact.jl:50-52
+                        r->acc[j] += 1;
+                    }
+                    kin[j].theta = th; kin[j].tf = tf; kin[j].xf = xf;
+                }
+            }
+            std::sort(r->ev.begin() + seg0, r->ev.end(), [](const zzw_event& a, const zzw_event& b) {
+                return a.t < b.t || (a.t == b.t && a.i < b.i);
+            });
+            if (r->status) break;
+        }
+        if (ctl.phase == ZZ_PH_FAIL) { r->status = 9; r->msg = "window controller failed"; }
+    }
+finish:
+    r->t.resize(d); r->x.resize(d); r->th.resize(d); r->c.resize(d);
+    for (int64_t j = 0; j < d; ++j) { r->t[j] = kin[j].tf; r->x[j] = kin[j].xf; r->th[j] = kin[j].theta; r->c[j] = priv[j].c; }
+    return r;
+}
+
+int zzw_status(const zzw_run* r) { return r->status; }
+void zzw_error_info(const zzw_run* r, int64_t* i, double* t, double* l, double* lb) { *i = r->err_i; *t = r->err_t; *l = r->err_l; *lb = r->err_lb; }
+int64_t zzw_trace_len(const zzw_run* r) { return (int64_t)r->ev.size(); }
+void zzw_trace_copy(const zzw_run* r, zzw_event* dst, int64_t first, int64_t count) { memcpy(dst, r->ev.data() + first, (size_t)count * sizeof(zzw_event)); }
+void zzw_counts(const zzw_run* r, int64_t* acc, int64_t* num) { memcpy(acc, r->acc.data(), (size_t)r->d * 8); *num = r->num; }
+void zzw_final_state(const zzw_run* r, double* t, double* x, double* th, double* c)
+{
+    size_t nb = (size_t)r->d * 8;
+    memcpy(t, r->t.data(), nb); memcpy(x, r->x.data(), nb); memcpy(th, r->th.data(), nb); memcpy(c, r->c.data(), nb);
+}
+void zzw_sums(const zzw_run* r, double* s1, double* s2) { memcpy(s1, r->s1.data(), (size_t)r->d * 8); memcpy(s2, r->s2.data(), (size_t)r->d * 8); }
+void zzw_stats(const zzw_run* r, int64_t* out) { out[0] = r->windows; out[1] = r->retries; out[2] = r->iters; out[3] = r->node_evals; out[4] = r->max_iters; }
+void zzw_free(zzw_run* r) { delete r; }
+}

@@ -1,0 +1,191 @@
+"""ctypes binding of oracle/libzzoracle.so (TEST INFRASTRUCTURE: the checker, never the product)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+RNG_SEQ, RNG_CTR = 0, 1
+ARITH_INPLACE, ARITH_LAZY = 0, 2
+GRAPH_ALL = 4
+PARITY_MODE = RNG_CTR | ARITH_LAZY  # what the GPU must reproduce bit for bit
+
+EVENT_DTYPE = np.dtype([("t", "<f8"), ("i", "<i8"), ("x", "<f8"), ("theta", "<f8")])  # trace.jl:38
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(ORACLE_DIR, "libzzoracle.so")
+        src = os.path.join(ORACLE_DIR, "zz_oracle.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            build()
+        L = C.CDLL(so)
+        L.zzo_spdmp.restype = C.c_void_p
+        L.zzo_spdmp.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
+                                C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
+        L.zzo_status.argtypes = [C.c_void_p]
+        L.zzo_trace_len.restype = C.c_int64
+        L.zzo_trace_len.argtypes = [C.c_void_p]
+        L.zzo_trace_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        L.zzo_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.zzo_final_state.argtypes = [C.c_void_p] * 5
+        L.zzo_moments.argtypes = [C.c_void_p] * 5
+        L.zzo_error_info.argtypes = [C.c_void_p] * 5
+        L.zzo_free.argtypes = [C.c_void_p]
+        for f in (L.zzo_poisson_time, L.zzo_poisson_time3, L.zzo_log, L.zzo_u01):
+            f.restype = C.c_double
+        L.zzo_poisson_time.argtypes = [C.c_double] * 3
+        L.zzo_poisson_time3.argtypes = [C.c_double] * 4
+        L.zzo_log.argtypes = [C.c_double]
+        L.zzo_u01.argtypes = [C.c_uint64] * 4
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OracleResult:
+    pass
+
+
+class BoundError(RuntimeError):
+    pass
+
+
+def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
+          mode=PARITY_MODE):
+    """Run the oracle.  ``target`` / ``bound`` are problems.CSC (target precision and the sampler's Z.Gamma)."""
+    L = lib()
+    d = target.n
+    f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    x0, theta0, c = f8(x0), f8(theta0), f8(c)
+    mu = np.zeros(d) if mu is None else f8(mu)
+    h = None if h is None else f8(h)
+    sd = np.array(seed, dtype=np.uint64)
+    r = L.zzo_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
+                    _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
+                    float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor), int(mode))
+    try:
+        st = L.zzo_status(r)
+        if st == 3:
+            i = C.c_int64(); t = C.c_double(); l = C.c_double(); lb = C.c_double()
+            L.zzo_error_info(r, C.byref(i), C.byref(t), C.byref(l), C.byref(lb))
+            raise BoundError("Tuning parameter `c` too small. (i=%d t=%g l=%g lb=%g)" % (i.value, t.value, l.value, lb.value))
+        out = OracleResult()
+        n = L.zzo_trace_len(r)
+        out.events = np.empty(n, dtype=EVENT_DTYPE)
+        L.zzo_trace_copy(r, _p(out.events), 0, n)
+        out.acc = np.empty(d, np.int64)
+        num = C.c_int64()
+        L.zzo_counts(r, _p(out.acc), C.byref(num))
+        out.num = num.value
+        out.t, out.x, out.theta, out.c = (np.empty(d) for _ in range(4))
+        L.zzo_final_state(r, _p(out.t), _p(out.x), _p(out.theta), _p(out.c))
+        out.m1, out.m2, out.s1, out.s2 = (np.empty(d) for _ in range(4))
+        L.zzo_moments(r, _p(out.m1), _p(out.m2), _p(out.s1), _p(out.s2))
+        out.t0, out.x0, out.theta0 = t0, x0.copy(), theta0.copy()
+        return out
+    finally:
+        L.zzo_free(r)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Host emulation of the GPU schedule (oracle/zz_window_sim.cpp) -- test-only, see its header.
+_wlib = None
+
+
+def wlib():
+    global _wlib
+    if _wlib is None:
+        so = os.path.join(ORACLE_DIR, "libzzwindowsim.so")
+        srcs = [os.path.join(ORACLE_DIR, "zz_window_sim.cpp")] + [
+            os.path.join(ROOT, "zigzagboomerang.jl_b200", "csrc", f) for f in ("zz_core.h", "zz_ctl.h", "zz_host_graph.h", "zz_math.h")]
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+            build()
+        L = C.CDLL(so)
+        L.zzw_spdmp.restype = C.c_void_p
+        L.zzw_spdmp.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
+                                C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint32]
+        L.zzw_status.argtypes = [C.c_void_p]
+        L.zzw_trace_len.restype = C.c_int64
+        L.zzw_trace_len.argtypes = [C.c_void_p]
+        L.zzw_trace_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+        L.zzw_counts.argtypes = [C.c_void_p] * 3
+        L.zzw_final_state.argtypes = [C.c_void_p] * 5
+        L.zzw_sums.argtypes = [C.c_void_p] * 3
+        L.zzw_stats.argtypes = [C.c_void_p] * 2
+        L.zzw_error_info.argtypes = [C.c_void_p] * 5
+        L.zzw_free.argtypes = [C.c_void_p]
+        _wlib = L
+    return _wlib
+
+
+def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
+               delta0=0.01, target_frac=0.4, tag_limit=0x0F000000):
+    L = wlib()
+    d = target.n
+    f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    x0, theta0, c = f8(x0), f8(theta0), f8(c)
+    mu = np.zeros(d) if mu is None else f8(mu)
+    h = None if h is None else f8(h)
+    sd = np.array(seed, dtype=np.uint64)
+    r = L.zzw_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
+                    _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
+                    float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor),
+                    float(delta0), float(target_frac), int(tag_limit))
+    try:
+        st = L.zzw_status(r)
+        if st == 3:
+            i = C.c_int64(); t = C.c_double(); l = C.c_double(); lb = C.c_double()
+            L.zzw_error_info(r, C.byref(i), C.byref(t), C.byref(l), C.byref(lb))
+            raise BoundError("Tuning parameter `c` too small. (i=%d t=%g l=%g lb=%g)" % (i.value, t.value, l.value, lb.value))
+        if st != 0:
+            raise RuntimeError("window sim failed with status %d" % st)
+        out = OracleResult()
+        n = L.zzw_trace_len(r)
+        out.events = np.empty(n, dtype=EVENT_DTYPE)
+        L.zzw_trace_copy(r, _p(out.events), 0, n)
+        out.acc = np.empty(d, np.int64)
+        num = C.c_int64()
+        L.zzw_counts(r, _p(out.acc), C.byref(num))
+        out.num = num.value
+        out.t, out.x, out.theta, out.c = (np.empty(d) for _ in range(4))
+        L.zzw_final_state(r, _p(out.t), _p(out.x), _p(out.theta), _p(out.c))
+        out.s1, out.s2 = np.empty(d), np.empty(d)
+        L.zzw_sums(r, _p(out.s1), _p(out.s2))
+        st = np.zeros(5, np.int64)
+        L.zzw_stats(r, _p(st))
+        out.stats = dict(windows=int(st[0]), retries=int(st[1]), iters=int(st[2]), node_evals=int(st[3]), max_iters=int(st[4]))
+        return out
+    finally:
+        L.zzw_free(r)
+
+
+def assert_same_run(a, b, check_state=True):
+    """Bit-exact comparison of two runs (events, counters, final state, moment sums)."""
+    assert len(a.events) == len(b.events), (len(a.events), len(b.events))
+    assert np.array_equal(a.events["i"], b.events["i"])
+    for f in ("t", "x", "theta"):
+        assert np.array_equal(a.events[f].view(np.uint64), b.events[f].view(np.uint64)), f
+    assert a.num == b.num, (a.num, b.num)
+    assert np.array_equal(a.acc, b.acc)
+    if check_state:
+        for f in ("t", "x", "theta", "c"):
+            assert np.array_equal(getattr(a, f).view(np.uint64), getattr(b, f).view(np.uint64)), f
+    if hasattr(a, "s1") and hasattr(b, "s1"):
+        assert np.array_equal(a.s1.view(np.uint64), b.s1.view(np.uint64))
+        assert np.array_equal(a.s2.view(np.uint64), b.s2.view(np.uint64))

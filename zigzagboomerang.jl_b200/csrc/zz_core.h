@@ -1,0 +1,279 @@
+// zz_core.h -- per-coordinate timeline evaluation of the windowed local-ZigZag scheme.
+//
+// Compiles for the device (zz_kernels.cu) and for the host (oracle/zz_window_sim.cpp, a TEST-ONLY
+// emulation of the schedule used to debug the scheme without a GPU).  DESIGN.md explains the scheme;
+// in short, for one time window [F, H):
+//   * every coordinate j owns a "timeline": its own proposals (src/sfact.jl:77-140, restricted to i == j)
+//     interleaved with the reschedules imposed by accepted flips of its neighbours (sfact.jl:131-135,
+//     seen from the receiving side j instead of the firing side i);
+//   * the timeline of j is a pure function of j's frontier state and of the flip lists of its neighbours,
+//     so all timelines are relaxed Jacobi-style until no flip list changes; the fixed point is exactly the
+//     sequential event history (causality is strictly forward in (time, coordinate) order);
+//   * positions are flip-anchored ("lazy"): x_k(s) = xf_k + theta_k (s - tf_k), rewritten only by the owner.
+#ifndef ZZ_CORE_H
+#define ZZ_CORE_H
+
+#include "zz_math.h"
+
+#define ZZ_MAXFLIP 6     // accepted flips one coordinate may record per window (4-bit count field)
+#define ZZ_MAXITEMS 48   // timeline items (proposals + reschedules) per coordinate per window
+#define ZZ_TAG_LIMIT 0x0f000000u  // iteration tags are rebased before they reach 2^28
+
+// neighbour entry flags
+#define ZZ_NB_TGT 1u   // entry of the target precision column (enters grad phi_j)
+#define ZZ_NB_BND 2u   // entry of the sampler's Z.Gamma column (enters the bound a_j, b_j)
+#define ZZ_NB_TRIG 4u  // a flip of this neighbour reschedules j (j in G1[k], sfact.jl:131)
+
+// per-node result flags
+#define ZZ_F_OVERFLOW 1u  // more than ZZ_MAXFLIP flips / ZZ_MAXITEMS items: the window must be shortened
+#define ZZ_F_VIOL 2u      // accepted with l >= lb and adapt == false  (sfact.jl:123-124)
+
+// Kinematic record of one coordinate, read by its neighbours: 32 B = one DRAM/L2 sector.
+// hdr[s] = (tag << 4) | count describes flip-list slot s: `count` flips recorded by the relaxation
+// iteration `tag`.  A reader running iteration `cur` of a window whose first tag is `w0` uses the slot
+// with the largest tag in [w0, cur) -- never the slot the owner may be rewriting during `cur`.
+struct __attribute__((aligned(32))) ZzKin {
+    double theta, tf, xf;
+    uint32_t hdr[2];
+};
+
+// Private bound record of one coordinate (only its owner reads or writes it).
+struct __attribute__((aligned(32))) ZzPriv {
+    double a, b, told, c;
+};
+
+// Speculative end-of-window state written by every relaxation pass, folded into the frontier at commit.
+struct __attribute__((aligned(16))) ZzSpec {
+    double a, b, told, tau, c;
+    uint32_t k;       // draw counter after the window
+    uint16_t nprop;   // proposals inside the window
+    uint8_t nflip;    // accepted ones
+    uint8_t flags;
+};
+
+struct ZzGraph {
+    const int32_t* nptr;   // [d+1] neighbour list offsets
+    const int32_t* nidx;   // neighbour ids (0-based), ascending, self included (storage order of column j)
+    const double* nwt;     // target weight Gamma_t[k,j]
+    const double* nwb;     // bound weight  Gamma_b[k,j]
+    const uint8_t* nfl;    // ZZ_NB_* flags
+    const double* gmu;     // idot(Z.Gamma, j, Z.mu)   (fact_samplers.jl:51)
+    const double* h;       // linear term of the target, may be null
+    int32_t same;          // target and bound matrices are the same object and h == 0, mu == 0
+};
+
+struct ZzView {
+    int32_t d;
+    ZzKin* kin;
+    double* flips;   // [d][2][ZZ_MAXFLIP]
+    ZzPriv* priv;
+    double* tau;
+    uint32_t* kctr;
+    uint64_t seed0, seed1;
+    int32_t adapt;
+    double factor;
+};
+
+struct ZzNodeOut {
+    double a, b, told, tau, c;
+    uint32_t k, nprop, nflip, flags;
+    double fl[ZZ_MAXFLIP];
+    double viol_t, viol_l, viol_lb;
+};
+
+#if defined(__CUDA_ARCH__)
+// data that other SMs rewrite between grid barriers is always read through L2
+ZZ_HD double zz_ld(const double* p) { return __ldcg(p); }
+ZZ_HD void zz_ld_kin(const ZzKin* p, double& th, double& tf, double& xf, uint32_t& h0, uint32_t& h1)
+{
+    double2 u = __ldcg(reinterpret_cast<const double2*>(p));
+    double2 w = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    th = u.x; tf = u.y; xf = w.x;
+    unsigned long long hh = (unsigned long long)__double_as_longlong(w.y);
+    h0 = (uint32_t)hh; h1 = (uint32_t)(hh >> 32);
+}
+#else
+ZZ_HD double zz_ld(const double* p) { return *p; }
+ZZ_HD void zz_ld_kin(const ZzKin* p, double& th, double& tf, double& xf, uint32_t& h0, uint32_t& h1)
+{
+    th = p->theta; tf = p->tf; xf = p->xf; h0 = p->hdr[0]; h1 = p->hdr[1];
+}
+#endif
+
+// Which flip-list slot is valid for a reader at iteration `cur` of a window starting at tag w0?
+// Returns the slot in `slot` and its count; count 0 when neither slot belongs to this window.
+ZZ_HD uint32_t zz_pick_slot(uint32_t h0, uint32_t h1, uint32_t w0, uint32_t cur, int& slot)
+{
+    uint32_t t0 = h0 >> 4, t1 = h1 >> 4;
+    bool v0 = (t0 >= w0) && (t0 < cur), v1 = (t1 >= w0) && (t1 < cur);
+    if (v0 && (!v1 || t0 > t1)) { slot = 0; return h0 & 15u; }
+    if (v1) { slot = 1; return h1 & 15u; }
+    slot = -1;
+    return 0;
+}
+
+// Position and velocity of neighbour k at event key (s, key_idx): frontier anchor advanced through those
+// of k's recorded flips that precede the key in (time, coordinate) order.
+ZZ_HD void zz_nb_state(const ZzView& v, int32_t k, double s, int32_t key_idx, uint32_t w0, uint32_t cur,
+                       double& x, double& th)
+{
+    double tf, xf; uint32_t h0, h1;
+    zz_ld_kin(v.kin + k, th, tf, xf, h0, h1);
+    int slot;
+    uint32_t cnt = zz_pick_slot(h0, h1, w0, cur, slot);
+    if (cnt) {
+        const double* fl = v.flips + ((size_t)k * 2 + slot) * ZZ_MAXFLIP;
+        for (uint32_t m = 0; m < cnt; ++m) {
+            double fs = zz_ld(fl + m);
+            if (fs < s || (fs == s && k <= key_idx)) {
+                xf = xf + th * (fs - tf);
+                tf = fs;
+                th = -th;
+            } else break;
+        }
+    }
+    x = xf + th * (s - tf);
+}
+
+// One pass over column j at event key (s, key_idx).  Own state is passed in (it lives in registers).
+//   gt  = idot(Gamma_t, j, x(s)) [- h_j]                  (target partial derivative, common.jl:16-24)
+//   gx  = idot(Z.Gamma, j, x(s))
+//   gp/gm = idot(Z.Gamma, j, theta) with +own / -own velocity (the caller picks after thinning)
+ZZ_HD void zz_eval(const ZzGraph& g, const ZzView& v, int32_t j, double s, int32_t key_idx, double xown,
+                   double thown, uint32_t w0, uint32_t cur, double& gt, double& gx, double& gp, double& gm)
+{
+    double at = 0.0, ax = 0.0, ap = 0.0, am = 0.0;
+    const int32_t e1 = g.nptr[j + 1];
+    for (int32_t e = g.nptr[j]; e < e1; ++e) {
+        int32_t k = g.nidx[e];
+        uint32_t fl = g.nfl[e];
+        double x, th;
+        if (k == j) {
+            x = xown; th = thown;
+            if (fl & ZZ_NB_BND) {
+                double wb = g.nwb[e];
+                ax += wb * x; ap += wb * th; am += wb * (-th);
+            }
+            if (!g.same && (fl & ZZ_NB_TGT)) at += g.nwt[e] * x;
+        } else {
+            if (!(fl & (ZZ_NB_TGT | ZZ_NB_BND))) continue;
+            zz_nb_state(v, k, s, key_idx, w0, cur, x, th);
+            if (fl & ZZ_NB_BND) {
+                double wb = g.nwb[e];
+                ax += wb * x; ap += wb * th; am += wb * th;
+            }
+            if (!g.same && (fl & ZZ_NB_TGT)) at += g.nwt[e] * x;
+        }
+    }
+    if (g.same) at = ax;
+    else if (g.h) at = at - g.h[j];
+    gt = at; gx = ax; gp = ap; gm = am;
+}
+
+// First flip of a trigger neighbour strictly after key (last_t, last_i); (+inf, INT_MAX) if none.
+ZZ_HD void zz_next_trigger(const ZzGraph& g, const ZzView& v, int32_t j, double last_t, int32_t last_i,
+                           uint32_t w0, uint32_t cur, double& nt, int32_t& ni)
+{
+    nt = ZZ_INF; ni = 0x7fffffff;
+    const int32_t e1 = g.nptr[j + 1];
+    for (int32_t e = g.nptr[j]; e < e1; ++e) {
+        if (!(g.nfl[e] & ZZ_NB_TRIG)) continue;
+        int32_t k = g.nidx[e];
+        if (k == j) continue;
+        const ZzKin* p = v.kin + k;
+#if defined(__CUDA_ARCH__)
+        unsigned long long hh = (unsigned long long)__double_as_longlong(__ldcg(reinterpret_cast<const double*>(p) + 3));
+        uint32_t h0 = (uint32_t)hh, h1 = (uint32_t)(hh >> 32);
+#else
+        uint32_t h0 = p->hdr[0], h1 = p->hdr[1];
+#endif
+        int slot;
+        uint32_t cnt = zz_pick_slot(h0, h1, w0, cur, slot);
+        if (!cnt) continue;
+        const double* fl = v.flips + ((size_t)k * 2 + slot) * ZZ_MAXFLIP;
+        for (uint32_t m = 0; m < cnt; ++m) {
+            double fs = zz_ld(fl + m);
+            if (fs > last_t || (fs == last_t && k > last_i)) {
+                if (fs < nt || (fs == nt && k < ni)) { nt = fs; ni = k; }
+                break;
+            }
+        }
+    }
+}
+
+// The timeline of coordinate j inside the window ending at H (exclusive, or inclusive when incl != 0),
+// starting from its frontier state.  See the file header; per item this is exactly the arithmetic of
+// spdmp_inner! (sfact.jl:118-139) and ab (fact_samplers.jl:50-54) for coordinate j.
+ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
+                           uint32_t cur, bool first_iter, ZzNodeOut& o)
+{
+    double th, tf, xf; uint32_t hh0, hh1;
+    zz_ld_kin(v.kin + j, th, tf, xf, hh0, hh1);
+    const ZzPriv pr = v.priv[j];
+    double a = pr.a, b = pr.b, told = pr.told, c = pr.c;
+    double tau = v.tau[j];
+    uint32_t k = v.kctr[j];
+    const double gmu = g.gmu[j];
+    uint32_t nprop = 0, nflip = 0, flags = 0;
+    double last_t = -ZZ_INF; int32_t last_i = -1;
+    o.viol_t = 0.0; o.viol_l = 0.0; o.viol_lb = 0.0;
+
+    for (int item = 0;; ++item) {
+        double nt = ZZ_INF; int32_t ni = 0x7fffffff;
+        if (!first_iter) zz_next_trigger(g, v, j, last_t, last_i, w0, cur, nt, ni);
+        const bool own = (tau < nt) || (tau == nt && j < ni);
+        const double s = own ? tau : nt;
+        if (!(s < H || (incl && s == H))) break;
+        if (item >= ZZ_MAXITEMS) { flags |= ZZ_F_OVERFLOW; break; }
+        const double xs = xf + th * (s - tf);
+        double gt, gx, gp, gm, gth;
+        if (own) {
+            zz_eval(g, v, j, s, j, xs, th, w0, cur, gt, gx, gp, gm);
+            const double l = zz_pos(gt * th);                 // fact_samplers.jl:28-30
+            const double lb = zz_pos(a + b * (s - told));     // sfact.jl:70
+            const double u = zz_u01(v.seed0, v.seed1, (uint64_t)j, k++);
+            nprop++;
+            if (u * lb < l) {                                 // sfact.jl:121
+                if (l >= lb) {                                // sfact.jl:123-128
+                    if (v.adapt) c *= v.factor;
+                    else if (!(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
+                }
+                if (nflip == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+                o.fl[nflip++] = s;
+                xf = xs; tf = s; th = -th;                    // dynamics.jl:46-49
+                gth = gm;
+            } else {
+                gth = gp;
+            }
+        } else {
+            last_t = nt; last_i = ni;
+            zz_eval(g, v, j, s, ni, xs, th, w0, cur, gt, gx, gp, gm);
+            gth = gp;
+        }
+        a = c + (gx - gmu) * th;                              // fact_samplers.jl:51
+        b = c / 100 + th * gth;                               // fact_samplers.jl:52
+        told = s;
+        tau = s + zz_poisson_time(a, b, zz_u01(v.seed0, v.seed1, (uint64_t)j, k++));  // sfact.jl:134,139
+    }
+    o.a = a; o.b = b; o.told = told; o.tau = tau; o.c = c;
+    o.k = k; o.nprop = nprop; o.nflip = nflip; o.flags = flags;
+}
+
+// Initial bound and first proposal time of coordinate j (sfact.jl:184-187; note: no "+ t0").
+ZZ_HD void zz_init_node(const ZzGraph& g, const ZzView& v, int32_t j, double t0)
+{
+    double th, tf, xf; uint32_t h0, h1;
+    zz_ld_kin(v.kin + j, th, tf, xf, h0, h1);
+    double gt, gx, gp, gm;
+    zz_eval(g, v, j, t0, j, xf + th * (t0 - tf), th, 1u, 1u, gt, gx, gp, gm);
+    ZzPriv pr;
+    pr.c = v.priv[j].c;
+    pr.a = pr.c + (gx - g.gmu[j]) * th;
+    pr.b = pr.c / 100 + th * gp;
+    pr.told = t0;
+    v.priv[j] = pr;
+    v.tau[j] = zz_poisson_time(pr.a, pr.b, zz_u01(v.seed0, v.seed1, (uint64_t)j, 0));
+    v.kctr[j] = 1;
+}
+
+#endif  // ZZ_CORE_H

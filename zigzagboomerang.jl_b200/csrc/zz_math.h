@@ -1,0 +1,162 @@
+// zz_math.h -- scalar primitives shared by the sm_100a kernels, the host library and
+// (for zz_log / zz_u01 only) the CPU oracle, so that "same seed => same bits" holds by
+// construction on both sides of the PCIe bus.
+//
+// Rules that make host and device agree bit for bit:
+//   * only + - * / sqrt and integer ops (all IEEE-754 correctly rounded on x86-64 SSE2 and sm_100a);
+//   * no fused multiply-add: device code is compiled with -fmad=false, host code with
+//     -ffp-contract=off;
+//   * the logarithm is OUR routine (zz_log), never libm's / libdevice's.
+//
+// Reference semantics restated here:
+//   pos            src/common.jl:8
+//   poisson_time   src/poissontime.jl:8-30 (two-parameter form), :39-65 (three-parameter form)
+#ifndef ZZ_MATH_H
+#define ZZ_MATH_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ZZ_HD __host__ __device__ __forceinline__
+#else
+#define ZZ_HD static inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define ZZ_INF __longlong_as_double(0x7ff0000000000000LL)
+ZZ_HD double zz_sqrt(double x) { return __dsqrt_rn(x); }
+ZZ_HD uint64_t zz_d2u(double x) { return (uint64_t)__double_as_longlong(x); }
+ZZ_HD double zz_u2d(uint64_t u) { return __longlong_as_double((long long)u); }
+#else
+#include <math.h>
+#include <string.h>
+#define ZZ_INF ((double)INFINITY)
+ZZ_HD double zz_sqrt(double x) { return sqrt(x); }
+ZZ_HD uint64_t zz_d2u(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
+ZZ_HD double zz_u2d(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
+#endif
+
+ZZ_HD double zz_pos(double x) { return x > 0.0 ? x : 0.0; }  // max(0,x); NaN -> 0 never reached on this path
+
+// Natural logarithm for finite normal x > 0 (the uniforms below are in [2^-54, 1)).
+// Classic argument reduction x = 2^k (1+f), s = f/(2+f), log(1+f) = 2s + s*R(s^2) with a
+// degree-14 minimax polynomial (the well-known Sun/fdlibm scheme, error < 1 ulp); written
+// out with explicit operation order so every compiler produces the same roundings.
+ZZ_HD double zz_log(double x)
+{
+    const double ln2_hi = 6.93147180369123816490e-01;
+    const double ln2_lo = 1.90821492927058770002e-10;
+    const double Lg1 = 6.666666666666735130e-01;
+    const double Lg2 = 3.999999999940941908e-01;
+    const double Lg3 = 2.857142874366239149e-01;
+    const double Lg4 = 2.222219843214978396e-01;
+    const double Lg5 = 1.818357216161805012e-01;
+    const double Lg6 = 1.531383769920937332e-01;
+    const double Lg7 = 1.479819860511658591e-01;
+
+    uint64_t ux = zz_d2u(x);
+    int32_t hx = (int32_t)(ux >> 32);
+    uint32_t lx = (uint32_t)ux;
+    int32_t k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    int32_t i = (hx + 0x95f64) & 0x100000;
+    // normalise x into [sqrt(2)/2, sqrt(2))
+    ux = ((uint64_t)(uint32_t)(hx | (i ^ 0x3ff00000)) << 32) | lx;
+    x = zz_u2d(ux);
+    k += (i >> 20);
+    double f = x - 1.0;
+    double dk = (double)k;
+    if ((0x000fffff & (2 + hx)) < 3) {  // |f| < 2^-20
+        if (f == 0.0) {
+            if (k == 0) return 0.0;
+            return dk * ln2_hi + dk * ln2_lo;
+        }
+        double R = f * f * (0.5 - 0.33333333333333333 * f);
+        if (k == 0) return f - R;
+        return dk * ln2_hi - ((R - dk * ln2_lo) - f);
+    }
+    double s = f / (2.0 + f);
+    double z = s * s;
+    i = hx - 0x6147a;
+    double w = z * z;
+    int32_t j = 0x6b851 - hx;
+    double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+    double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+    i |= j;
+    double R = t2 + t1;
+    if (i > 0) {
+        double hfsq = 0.5 * f * f;
+        if (k == 0) return f - (hfsq - s * (hfsq + R));
+        return dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f);
+    }
+    if (k == 0) return f - s * (f - R);
+    return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Counter-based uniforms.  u(i,k) is the k-th draw of coordinate i's private stream:
+// two rounds of the splitmix64 finaliser over (seed, coordinate, counter).  The value is
+// strictly inside (0,1) so log(u) is always finite.  (The reference draws from one
+// sequential Xoroshiro128Plus stream in global event order, src/sfact.jl:121,134,139,186,
+// which no parallel schedule can reproduce; see DESIGN.md "RNG contract".)
+ZZ_HD uint64_t zz_mix64(uint64_t z)
+{
+    z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ULL;
+    z ^= z >> 27; z *= 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return z;
+}
+
+ZZ_HD double zz_u01(uint64_t seed0, uint64_t seed1, uint64_t coord, uint64_t ctr)
+{
+    uint64_t z = zz_mix64(seed0 + (coord + 1ULL) * 0x9E3779B97F4A7C15ULL);
+    z = zz_mix64(z ^ (seed1 + ctr * 0xD1342543DE82EF95ULL));
+    // 53 random bits, centred in their cell: (n + 1/2) * 2^-53, n in [0, 2^53)
+    return ((double)(z >> 11) + 0.5) * 1.1102230246251565404e-16;
+}
+
+// First arrival time of an inhomogeneous Poisson process with rate (a + b t)^+ given u ~ U(0,1).
+// Expression shapes follow src/poissontime.jl:8-30 term by term ((a/b)^2 is (a/b)*(a/b)).
+ZZ_HD double zz_poisson_time(double a, double b, double u)
+{
+    if (b > 0.0) {
+        if (a < 0.0) return zz_sqrt(-zz_log(u) * 2.0 / b) - a / b;
+        double q = a / b;
+        return zz_sqrt(q * q - zz_log(u) * 2.0 / b) - a / b;
+    } else if (b == 0.0) {
+        if (a > 0.0) return -zz_log(u) / a;
+        return ZZ_INF;
+    } else {
+        if (a <= 0.0) return ZZ_INF;
+        double nl = -zz_log(u);
+        if (nl <= -(a * a) / b + (a * a) / (2.0 * b)) {
+            double q = a / b;
+            return -zz_sqrt(q * q - zz_log(u) * 2.0 / b) - a / b;
+        }
+        return ZZ_INF;
+    }
+}
+
+// Rate c + (a + b t)^+, c > 0 (src/poissontime.jl:39-65); used by the sticky variants.
+ZZ_HD double zz_poisson_time3(double a, double b, double c, double u)
+{
+    double lu = zz_log(u);
+    if (b > 0.0) {
+        if (a < 0.0) {
+            if (-c * a / b + lu < 0.0)
+                return zz_sqrt(-2.0 * b * lu + c * c + 2.0 * a * c) / b - (a + c) / b;
+            return -lu / c;
+        }
+        return zz_sqrt(-lu * 2.0 * b + (a + c) * (a + c)) / b - (a + c) / b;
+    } else if (b == 0.0) {
+        if (a > 0.0) return -lu / (a + c);
+        return -lu / c;
+    } else {
+        if (a <= 0.0) return -lu / c;
+        if (-c * a / b - (a * a) / (2.0 * b) + lu > 0.0)
+            return zz_sqrt((a + c) * (a + c) - 2.0 * lu * b) / b - (a + c) / b;
+        return (-lu + (a * a) / (2.0 * b)) / c;
+    }
+}
+
+#endif  // ZZ_MATH_H
