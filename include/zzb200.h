@@ -1,0 +1,95 @@
+/* zzb200.h -- C-ABI of libzzb200.so: the B200-native drop-in for the factorised local-ZigZag event loop
+ * of mschauer/ZigZagBoomerang.jl (reference @ 691afe2).  All entry points are extern "C", take plain
+ * pointers and sizes, return an int32 status (0 = ok) and never let an exception cross the boundary.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *   zzb_problem_create_gaussian   the (grad-phi closure, Z::ZigZag) pair a caller hands to spdmp: the closure
+ *                                 `(x,i,G) -> idot(G,i,x)` (src/common.jl:16-24, scripts/gaussianrandomfield.jl:25)
+ *                                 becomes the CSC arrays of the target precision (+ optional linear term h);
+ *                                 `ZigZag(G, mu)` (src/types.jl:19-27) becomes the CSC arrays of Z.Gamma and Z.mu;
+ *                                 also performs the neighbourhood setup of src/sfact.jl:170-178
+ *   zzb_spdmp_run                 spdmp(grad, t0, x0, th0, T, c, Z, args...; factor, adapt, seed)  src/sfact.jl:162-214
+ *                                 and pdmp(...) src/sfact.jl:236 (same event law; the All() graph only changes which
+ *                                 coordinates the CPU code moves eagerly)
+ *   zzb_run_counts                the returned (acc, num)                                        src/sfact.jl:181-182,211
+ *   zzb_run_final_state           the returned (t, x, theta) and the adapted c                   src/sfact.jl:211
+ *   zzb_trace_len / _copy         the returned FactTrace's `events` vector                       src/trace.jl:7-13,38
+ *   zzb_trace_moments             Statistics.mean(::Trace) (src/trace.jl:182-200) + matching exact second moment
+ *   status ZZB_E_BOUND            error("Tuning parameter `c` too small.")                       src/sfact.jl:124
+ *
+ * Ownership: the caller owns every host array and keeps it alive for the duration of the call; the library owns all
+ * device memory behind the opaque handles.  Threading: one host thread at a time per handle; calls block until the
+ * work is complete.  Indices are Julia's: 1-based Int64 `colptr` / `rowval`, rows ascending inside a column, so
+ * `pointer(G.colptr)`, `pointer(G.rowval)`, `pointer(G.nzval)` can be passed as they are.
+ * There is NO CPU fallback: every compute entry point fails with ZZB_E_CUDA when no CUDA driver / device / cubin is found.
+ */
+#ifndef ZZB200_H
+#define ZZB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZZB_OK 0
+#define ZZB_E_ARG 1       /* bad argument / handle */
+#define ZZB_E_CUDA 2      /* driver, device or cubin problem; see zzb_last_error */
+#define ZZB_E_BOUND 3     /* "Tuning parameter `c` too small." (accepted with l >= lb and adapt == 0) */
+#define ZZB_E_GRAPH 4     /* malformed sparse matrix */
+#define ZZB_E_NOMEM 5
+#define ZZB_E_TRACE 6     /* trace buffer too small for a single window */
+#define ZZB_E_INTERNAL 9
+
+/* flags of zzb_spdmp_run / zzb_run_create */
+#define ZZB_FLAG_NO_TRACE 1u   /* do not record events; counters, final state and moment sums are still produced */
+
+typedef struct zzb_problem_s* zzb_problem_t;
+typedef struct zzb_run_s* zzb_run_t;
+
+/* Trace record: the memory layout of Julia's Tuple{Float64,Int64,Float64,Float64} (src/trace.jl:38):
+ * (event time, 1-based coordinate, position of that coordinate, its velocity AFTER the flip). */
+typedef struct { double t; int64_t i; double x; double theta; } zzb_event;
+
+/* Library / device lifetime.  dev_ids may be NULL (device 0).  cubin_path may be NULL: the kernels are then loaded from
+ * $ZZB200_CUBIN or from zzb200_kernels.cubin next to the shared library. */
+int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path);
+int32_t zzb_shutdown(void);
+int32_t zzb_last_error(char* buf, int64_t len);
+int32_t zzb_device_info(int32_t* sm_count, int64_t* total_mem, char* name, int64_t name_len);
+
+/* Problem = target potential + sampler matrices (two CSC matrices of order d; hvec / bnd_mu may be NULL = zeros).
+ * grad phi_i(x) = sum_k tgt[k,i] x_k - hvec[i];  bound uses bnd (Z.Gamma) and bnd_mu (Z.mu), fact_samplers.jl:50-54. */
+int32_t zzb_problem_create_gaussian(zzb_problem_t* out, int64_t d,
+                                    const int64_t* colptr, const int64_t* rowval, const double* nzval, const double* hvec,
+                                    const int64_t* bnd_colptr, const int64_t* bnd_rowval, const double* bnd_nzval,
+                                    const double* bnd_mu);
+int32_t zzb_problem_free(zzb_problem_t p);
+
+/* One-call form, host buffers in and out: runs the sampler from t0 until the first accepted event at or after T.
+ * c is in/out (adapted when adapt != 0).  seed[2] keys the counter-based uniform streams. */
+int32_t zzb_spdmp_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, double* c,
+                      const uint64_t* seed, int32_t adapt, double factor, uint32_t flags, zzb_run_t* out);
+
+/* Staged form (what zzb_spdmp_run is made of); lets a caller keep inputs resident in HBM and time the kernel alone. */
+int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_events, zzb_run_t* out);
+int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* theta0, const double* c,
+                       const uint64_t* seed, int32_t adapt, double factor);
+int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms);   /* device_ms: CUDA-event time of the kernel(s) */
+int32_t zzb_run_set(zzb_run_t r, const char* key, double value);    /* "delta0", "target_frac", "tag_limit", "max_windows" */
+int32_t zzb_run_stats(zzb_run_t r, int64_t* out, int32_t n);        /* windows, retries, passes, node evaluations, rebases,
+                                                                       kernel launches, grid size, block size */
+
+int32_t zzb_run_counts(zzb_run_t r, int64_t* acc, int64_t* num);
+int32_t zzb_run_final_state(zzb_run_t r, double* t, double* x, double* theta, double* c);
+int32_t zzb_trace_len(zzb_run_t r, int64_t* n);
+int32_t zzb_trace_copy(zzb_run_t r, zzb_event* dst, int64_t first, int64_t count);
+int32_t zzb_trace_moments(zzb_run_t r, double* m1, double* m2);     /* time averages of x and x^2 over [t0, last event] */
+int32_t zzb_trace_sums(zzb_run_t r, double* s1, double* s2);        /* the unscaled device accumulators */
+int32_t zzb_run_error_info(zzb_run_t r, int64_t* i, double* t, double* l, double* lb);  /* after ZZB_E_BOUND */
+int32_t zzb_run_free(zzb_run_t r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZZB200_H */

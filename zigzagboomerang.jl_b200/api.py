@@ -1,0 +1,322 @@
+"""Host-side mirror of the reference's interface for the factorised local-ZigZag path, on top of the C-ABI.
+
+Names, argument order and return shapes follow mschauer/ZigZagBoomerang.jl (paths relative to /root/reference):
+
+    ZigZag(Gamma, mu, sigma; lambdaref, rho)          src/types.jl:19-27
+    spdmp(grad, t0, x0, theta0, T, c, [G,] F, args...; factor=1.8, adapt=false, seed)
+        -> Xi, (t, x, theta), (acc, num), c           src/sfact.jl:162-214
+    pdmp(grad, t0, x0, theta0, T, c, F, args...)      src/sfact.jl:236
+    Trace / FactTrace, discretize, mean, cummean, subtrace    src/trace.jl
+
+A device kernel cannot call a host closure, so `grad` must be a :class:`GaussianPotential` descriptor (it is still
+callable as ``grad(x, i)`` like the reference's ``grad(x, i, Gamma) = idot(Gamma, i, x)``).  Julia is not available in
+this image; ``julia/ZigZagBoomerangB200.jl`` is the same wrapper written against the same C-ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import secrets
+
+import numpy as np
+
+from . import _capi
+from ._capi import EVENT_DTYPE, ZZB_E_BOUND, BoundError, ZZBError, check, f8, ptr
+from .problems import CSC
+
+
+class All:
+    """`All()` neighbourhood marker (src/sfact.jl:1-2)."""
+
+
+class Matched:
+    """`Matched()` neighbourhood marker (src/sfact.jl:3-4)."""
+
+
+class ZigZag:
+    """``ZigZag(Gamma, mu, sigma=diag(Gamma).^(-0.5); lambdaref=0.0, rho=0.0)`` (src/types.jl:19-27)."""
+
+    def __init__(self, Gamma: CSC, mu, sigma=None, *, lambdaref: float = 0.0, rho: float = 0.0):
+        self.Gamma = Gamma if isinstance(Gamma, CSC) else CSC.from_scipy(Gamma)
+        self.mu = f8(mu)
+        if sigma is None:
+            G = self.Gamma
+            cols = np.repeat(np.arange(G.n), np.diff(G.colptr))
+            on = (G.rowval - 1) == cols
+            diag = np.zeros(G.n)
+            diag[cols[on]] = G.nzval[on]
+            with np.errstate(divide="ignore"):
+                sigma = diag ** -0.5
+        self.sigma = sigma
+        self.lambdaref = float(lambdaref)
+        self.rho = float(rho)
+        self.rhobar = float(np.sqrt(1 - rho * rho))
+
+
+class GaussianPotential:
+    """Target descriptor: ``grad phi_i(x) = idot(Gamma, i, x) - h[i]`` (src/common.jl:16-24)."""
+
+    def __init__(self, Gamma: CSC, h=None):
+        self.Gamma = Gamma if isinstance(Gamma, CSC) else CSC.from_scipy(Gamma)
+        self.h = None if h is None else f8(h)
+
+    def __call__(self, x, i, *args):  # 1-based i, like the reference closure
+        G = self.Gamma
+        s = 0.0
+        for p in range(G.colptr[i - 1] - 1, G.colptr[i] - 1):
+            s += G.nzval[p] * x[G.rowval[p] - 1]
+        return s - (0.0 if self.h is None else self.h[i - 1])
+
+
+class FactTrace:
+    """``FactTrace`` (src/trace.jl:7-13): initial triple plus the event list
+    ``(t, i, x_i, theta_i)``; ``events`` is a structured array with Julia's tuple layout."""
+
+    def __init__(self, F, t0, x0, theta0, events):
+        self.F, self.t0, self.x0, self.theta0, self.events = F, float(t0), f8(x0), f8(theta0), events
+
+    def __len__(self):  # Base.length(FT) = 1 + length(events), trace.jl:42
+        return 1 + len(self.events)
+
+    def __iter__(self):
+        """Iterate ``(t, x)`` like src/trace.jl:44-63 (x is a fresh copy each step; the last event is not applied,
+        exactly like the reference's `k == length(FT.events)` branch)."""
+        t, x, th = self.t0, self.x0.copy(), self.theta0.copy()
+        yield t, x.copy()
+        n = len(self.events)
+        for k in range(n):
+            if k == n - 1:
+                yield t, x.copy()
+                return
+            t2, i, xi, thi = self.events[k]
+            x += th * (t2 - t)
+            t = t2
+            x[i - 1] = xi
+            th[i - 1] = thi
+            yield t, x.copy()
+
+
+Trace = FactTrace
+
+
+def discretize(trace: FactTrace, dt: float):
+    """``collect(discretize(trace, dt))`` (src/trace.jl:94-125) as ``(ts, xs)`` arrays."""
+    t, x, th = trace.t0, trace.x0.copy(), trace.theta0.copy()
+    ts, xs = [t], [x.copy()]
+    ev = trace.events
+    k, n = 0, len(ev)
+    while True:
+        step = dt
+        done = False
+        while True:
+            if k >= n:
+                done = True
+                break
+            ti, i, xi, thi = ev[k]
+            if t + step < ti:
+                x += th * step
+                t += step
+                break
+            d = ti - t
+            step -= d
+            x += th * d
+            t = ti
+            x[i - 1] = xi
+            th[i - 1] = thi
+            k += 1
+        if done:
+            break
+        ts.append(t)
+        xs.append(x.copy())
+    return np.array(ts), np.array(xs)
+
+
+def mean(trace: FactTrace):
+    """``Statistics.mean(::Trace)`` (src/trace.jl:182-200)."""
+    x = trace.x0.copy()
+    y = np.zeros_like(x)
+    T = trace.events["t"][-1]
+    t = np.full(len(x), trace.t0)
+    scale = 1 / (2 * T)
+    for t2, i, xi, _ in trace.events:
+        y[i - 1] += (x[i - 1] + xi) * (t2 - t[i - 1]) * scale
+        t[i - 1] = t2
+        x[i - 1] = xi
+    return y
+
+
+def subtrace(tr: FactTrace, J):
+    """``subtrace(tr, J)`` (src/trace.jl:275-290); J sorted, 1-based."""
+    J = np.asarray(J, dtype=np.int64)
+    assert np.all(np.diff(J) > 0)
+    pos = np.searchsorted(J, tr.events["i"])
+    ok = (pos < len(J)) & (J[np.minimum(pos, len(J) - 1)] == tr.events["i"])
+    ev = tr.events[ok].copy()
+    ev["i"] = pos[ok] + 1
+    return FactTrace(tr.F, tr.t0, tr.x0[J - 1], tr.theta0[J - 1], ev)
+
+
+class Problem:
+    """Device-resident problem: target potential + sampler matrices (``zzb_problem_create_gaussian``)."""
+
+    def __init__(self, target: GaussianPotential, Z: ZigZag):
+        _capi.init()
+        self.target, self.Z = target, Z
+        if target.Gamma.n != Z.Gamma.n:
+            raise ValueError("target and sampler dimensions differ")
+        self.d = target.Gamma.n
+        self._h = C.c_void_p()
+        Gt, Gb = target.Gamma, Z.Gamma
+        check(_capi.lib().zzb_problem_create_gaussian(
+            C.byref(self._h), self.d, ptr(Gt.colptr), ptr(Gt.rowval), ptr(Gt.nzval), ptr(target.h),
+            ptr(Gb.colptr), ptr(Gb.rowval), ptr(Gb.nzval), ptr(Z.mu)))
+
+    def close(self):
+        if self._h:
+            _capi.lib().zzb_problem_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Run:
+    """One sampler run on the device (staged form of the C-ABI)."""
+
+    def __init__(self, problem: Problem, *, record_trace: bool = True, trace_capacity: int = 0):
+        self.problem = problem
+        self.d = problem.d
+        self._h = C.c_void_p()
+        flags = 0 if record_trace else _capi.ZZB_FLAG_NO_TRACE
+        self.record_trace = record_trace
+        check(_capi.lib().zzb_run_create(problem._h, flags, int(trace_capacity), C.byref(self._h)))
+
+    def set(self, **kw):
+        for k, v in kw.items():
+            check(_capi.lib().zzb_run_set(self._h, k.encode(), float(v)))
+        return self
+
+    def upload(self, t0, x0, theta0, c, seed=(1, 2), adapt=False, factor=1.8):
+        self._x0, self._th0, self._c = f8(x0), f8(theta0), f8(c)
+        sd = np.array(seed, dtype=np.uint64)
+        check(_capi.lib().zzb_run_upload(self._h, float(t0), ptr(self._x0), ptr(self._th0), ptr(self._c), ptr(sd),
+                                         int(bool(adapt)), float(factor)))
+        self.t0 = float(t0)
+        return self
+
+    def execute(self, T) -> float:
+        """Run to T; returns the CUDA-event time of the event-loop kernel(s) in milliseconds."""
+        ms = C.c_float()
+        st = _capi.lib().zzb_run_execute(self._h, float(T), C.byref(ms))
+        self.device_ms = ms.value
+        check(st)
+        return ms.value
+
+    def counts(self):
+        acc = np.empty(self.d, np.int64)
+        num = C.c_int64()
+        check(_capi.lib().zzb_run_counts(self._h, ptr(acc), C.byref(num)))
+        return acc, num.value
+
+    def final_state(self):
+        t, x, th, c = (np.empty(self.d) for _ in range(4))
+        check(_capi.lib().zzb_run_final_state(self._h, ptr(t), ptr(x), ptr(th), ptr(c)))
+        return t, x, th, c
+
+    def events(self):
+        n = C.c_int64()
+        check(_capi.lib().zzb_trace_len(self._h, C.byref(n)))
+        ev = np.empty(n.value, dtype=EVENT_DTYPE)
+        if n.value:
+            check(_capi.lib().zzb_trace_copy(self._h, ptr(ev), 0, n.value))
+        return ev
+
+    def n_events(self) -> int:
+        n = C.c_int64()
+        check(_capi.lib().zzb_trace_len(self._h, C.byref(n)))
+        return n.value
+
+    def moments(self):
+        m1, m2 = np.empty(self.d), np.empty(self.d)
+        check(_capi.lib().zzb_trace_moments(self._h, ptr(m1), ptr(m2)))
+        return m1, m2
+
+    def sums(self):
+        s1, s2 = np.empty(self.d), np.empty(self.d)
+        check(_capi.lib().zzb_trace_sums(self._h, ptr(s1), ptr(s2)))
+        return s1, s2
+
+    def stats(self):
+        out = np.zeros(8, np.int64)
+        check(_capi.lib().zzb_run_stats(self._h, ptr(out), 8))
+        keys = ("windows", "retries", "passes", "node_evals", "rebases", "launches", "grid", "block")
+        return dict(zip(keys, (int(v) for v in out)))
+
+    def close(self):
+        if self._h:
+            _capi.lib().zzb_run_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _as_problem(grad, F):
+    if isinstance(grad, Problem):
+        return grad, False
+    if not isinstance(grad, GaussianPotential):
+        raise TypeError("the B200 path needs a target descriptor (GaussianPotential), not a closure: "
+                        "a device kernel cannot call back into the host")
+    if not isinstance(F, ZigZag):
+        raise TypeError("only ZigZag dynamics are implemented on the device path")
+    if F.lambdaref != 0.0:
+        raise NotImplementedError("refreshments (lambdaref > 0) are not implemented on the device path")
+    return Problem(grad, F), True
+
+
+def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None, record_trace=True, tune=None):
+    """``spdmp(grad, t0, x0, theta0, T, c, [G,] F, args...; factor=1.8, adapt=false, seed=Seed())``
+    = ``Xi, (t, x, theta), (acc, num), c`` (src/sfact.jl:162-214).
+
+    `G` may be ``Matched()`` / ``All()``; both give the same event law (the reference only moves different
+    coordinate sets eagerly), so they share one kernel.  Trailing `args` (the reference forwards them to the
+    closure) are accepted and ignored.  Raises :class:`BoundError` with the reference's message when a proposal is
+    accepted with ``l >= lb`` and ``adapt`` is false (src/sfact.jl:124).
+    """
+    rest = list(rest)
+    if rest and isinstance(rest[0], (All, Matched)):
+        rest.pop(0)
+    if not rest:
+        raise TypeError("spdmp: missing sampler F")
+    F = rest.pop(0)
+    prob, own = _as_problem(grad, F)
+    if seed is None:  # Seed() = fresh entropy (src/ZigZagBoomerang.jl:10)
+        seed = (secrets.randbits(64), secrets.randbits(64))
+    run = Run(prob, record_trace=record_trace)
+    try:
+        if tune:
+            run.set(**tune)
+        run.upload(t0, x0, theta0, c, seed=seed, adapt=adapt, factor=factor)
+        run.execute(T)
+        t, x, th, cc = run.final_state()
+        acc, num = run.counts()
+        ev = run.events() if record_trace else np.empty(0, dtype=EVENT_DTYPE)
+        Xi = FactTrace(F, t0, x0, theta0, ev)
+        Xi.moments = run.moments() if num else None
+        Xi.stats = run.stats()
+        Xi.device_ms = run.device_ms
+        return Xi, (t, x, th), (acc, num), cc
+    finally:
+        run.close()
+        if own:
+            prob.close()
+
+
+def pdmp(grad, t0, x0, theta0, T, c, F, *args, **kw):
+    """``pdmp(grad, t0, x0, theta0, T, c, F::ZigZag, args...)`` = ``spdmp(..., All(), F, ...)`` (src/sfact.jl:236)."""
+    return spdmp(grad, t0, x0, theta0, T, c, All(), F, *args, **kw)

@@ -79,6 +79,7 @@ struct ZzNodeOut {
     uint32_t k, nprop, nflip, flags;
     double fl[ZZ_MAXFLIP];
     double viol_t, viol_l, viol_lb;
+    uint32_t hdr0, hdr1;   // own flip-list headers as read at entry
 };
 
 #if defined(__CUDA_ARCH__)
@@ -92,8 +93,18 @@ ZZ_HD void zz_ld_kin(const ZzKin* p, double& th, double& tf, double& xf, uint32_
     unsigned long long hh = (unsigned long long)__double_as_longlong(w.y);
     h0 = (uint32_t)hh; h1 = (uint32_t)(hh >> 32);
 }
+ZZ_HD uint32_t zz_ld32(const uint32_t* p) { return __ldcg(p); }
+ZZ_HD ZzPriv zz_ld_priv(const ZzPriv* p)
+{
+    double2 u = __ldcg(reinterpret_cast<const double2*>(p));
+    double2 w = __ldcg(reinterpret_cast<const double2*>(p) + 1);
+    ZzPriv r; r.a = u.x; r.b = u.y; r.told = w.x; r.c = w.y;
+    return r;
+}
 #else
 ZZ_HD double zz_ld(const double* p) { return *p; }
+ZZ_HD uint32_t zz_ld32(const uint32_t* p) { return *p; }
+ZZ_HD ZzPriv zz_ld_priv(const ZzPriv* p) { return *p; }
 ZZ_HD void zz_ld_kin(const ZzKin* p, double& th, double& tf, double& xf, uint32_t& h0, uint32_t& h1)
 {
     th = p->theta; tf = p->tf; xf = p->xf; h0 = p->hdr[0]; h1 = p->hdr[1];
@@ -209,10 +220,10 @@ ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double 
 {
     double th, tf, xf; uint32_t hh0, hh1;
     zz_ld_kin(v.kin + j, th, tf, xf, hh0, hh1);
-    const ZzPriv pr = v.priv[j];
+    const ZzPriv pr = zz_ld_priv(v.priv + j);
     double a = pr.a, b = pr.b, told = pr.told, c = pr.c;
-    double tau = v.tau[j];
-    uint32_t k = v.kctr[j];
+    double tau = zz_ld(v.tau + j);
+    uint32_t k = zz_ld32(v.kctr + j);
     const double gmu = g.gmu[j];
     uint32_t nprop = 0, nflip = 0, flags = 0;
     double last_t = -ZZ_INF; int32_t last_i = -1;
@@ -239,7 +250,14 @@ ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double 
                     else if (!(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
                 }
                 if (nflip == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+                for (int m = 0; m < ZZ_MAXFLIP; ++m)  // keeps o.fl in registers (no dynamic indexing)
+                    if (m == (int)nflip) o.fl[m] = s;
+                nflip++;
+#else
                 o.fl[nflip++] = s;
+#endif
                 xf = xs; tf = s; th = -th;                    // dynamics.jl:46-49
                 gth = gm;
             } else {
@@ -257,6 +275,7 @@ ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double 
     }
     o.a = a; o.b = b; o.told = told; o.tau = tau; o.c = c;
     o.k = k; o.nprop = nprop; o.nflip = nflip; o.flags = flags;
+    o.hdr0 = hh0; o.hdr1 = hh1;
 }
 
 // Initial bound and first proposal time of coordinate j (sfact.jl:184-187; note: no "+ t0").
@@ -267,7 +286,7 @@ ZZ_HD void zz_init_node(const ZzGraph& g, const ZzView& v, int32_t j, double t0)
     double gt, gx, gp, gm;
     zz_eval(g, v, j, t0, j, xf + th * (t0 - tf), th, 1u, 1u, gt, gx, gp, gm);
     ZzPriv pr;
-    pr.c = v.priv[j].c;
+    pr.c = zz_ld_priv(v.priv + j).c;
     pr.a = pr.c + (gx - g.gmu[j]) * th;
     pr.b = pr.c / 100 + th * gp;
     pr.told = t0;

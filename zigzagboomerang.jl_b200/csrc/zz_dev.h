@@ -1,0 +1,73 @@
+// zz_dev.h -- launch-parameter and device control-block layouts shared by zz_kernels.cu (device) and
+// zzb200.cpp (host, driver API).  Plain PODs; identical layout under nvcc and g++ on x86-64.
+#ifndef ZZ_DEV_H
+#define ZZ_DEV_H
+
+#include "zz_core.h"
+#include "zz_ctl.h"
+
+struct ZzEvent {  // memory layout of Tuple{Float64,Int64,Float64,Float64}, src/trace.jl:38
+    double t; long long i; double x; double theta;
+};
+
+// Counters and persistent controller state; lives in device memory, zeroed by the host before the first launch.
+struct ZzDevCtl {
+    unsigned long long bar;          // grid barrier arrival counter (monotone; zeroed by the host before each launch)
+    unsigned int wl_cnt[3];          // relaxation work lists, rotated per pass; top bit = "a coordinate overflowed"
+    unsigned int viol;               // bound violation seen (adapt == false), sfact.jl:124
+    unsigned int touched_cnt[3];     // per window attempt (attempt number mod 3)
+    int viol_i;
+    unsigned long long smin_key[3];  // order-preserving key of the earliest flip (phase B)
+    unsigned long long nprop_win[3]; // proposals committed by the window of that attempt slot
+    unsigned long long num;          // total proposals (sfact.jl:120)
+    unsigned long long nacc;         // total accepted flips
+    unsigned long long trace_len;    // records appended to the trace buffer (events + window-end markers)
+    unsigned long long f0_key;       // min over initial proposal times (init kernel)
+    double viol_t, viol_l, viol_lb;
+    unsigned int trace_full;         // (defensive) an event did not fit; cannot happen with the drain protocol
+    unsigned int need_drain;         // kernel returned because the next window might not fit into the trace buffer
+    unsigned int started;            // controller below is valid (resumed launch)
+    unsigned int cur;                // last iteration tag used
+    unsigned int itg;                // index of the work list consumed last
+    unsigned int wattempt;           // window attempts so far
+    // persisted across launches
+    ZzCtl ctl;
+    // statistics
+    unsigned long long windows, retries, iters, node_evals, rebases;
+};
+
+struct ZzParams {
+    ZzGraph g;
+    ZzView v;
+    const int32_t* dptr;     // dependents: who reads coordinate j
+    const int32_t* didx;
+    ZzSpec* spec;
+    double* viol_info;       // [d][3] (t, l, lb) of a recorded violation
+    unsigned int* dstamp;    // iteration tag for which the coordinate is (already) queued
+    unsigned int* acc;       // accepted flips per coordinate (sfact.jl:122)
+    double* s1;              // sum (x_prev + x_new)(t_new - t_prev)               (trace.jl:194, unscaled)
+    double* s2;              // sum (t_new - t_prev)(x_prev^2 + x_prev x_new + x_new^2)
+    int32_t* wl[3];
+    int32_t* touched[1];
+    ZzEvent* trace;
+    unsigned long long trace_cap;
+    ZzDevCtl* ctl;
+    double t0, T, delta0, target;
+    unsigned int tag_limit;
+    unsigned int max_windows;   // return to the host after this many committed windows (0 = run to the end)
+    int32_t record_trace;
+    int32_t pad;
+};
+
+// order-preserving map double -> uint64 (so atomicMin works for any sign)
+ZZ_HD unsigned long long zz_key(double x)
+{
+    unsigned long long u = zz_d2u(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+ZZ_HD double zz_unkey(unsigned long long k)
+{
+    return zz_u2d((k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k);
+}
+
+#endif  // ZZ_DEV_H

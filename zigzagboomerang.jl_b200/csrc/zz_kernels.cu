@@ -1,0 +1,392 @@
+// zz_kernels.cu -- sm_100a kernels of the windowed local-ZigZag event loop (compiled to a .cubin and
+// loaded by zzb200.cpp through the driver API).
+//
+//   zz_setup_kernel   pack (x0, theta0, c) into the per-coordinate records
+//   zz_init_kernel    initial bounds and first proposal times   (src/sfact.jl:184-187)
+//   zz_run_kernel     PERSISTENT COOPERATIVE kernel: the whole event loop (sfact.jl:199-208 with
+//                     spdmp_inner! :73-145 inside), one grid barrier per relaxation pass
+//   zz_export_kernel  unpack the final (t, x, theta, c) for the host
+//
+// Schedule: time is cut into windows [F, H).  Pass 1 of a window scans the proposal times,
+// compacts the coordinates with tau < H per warp and evaluates their timelines (zz_process_node); every
+// coordinate whose list of accepted flips changed marks the coordinates that read it; the following passes
+// re-evaluate exactly those, until no list changes.  The fixed point is the sequential event history, so
+// the converged window is committed: frontier state, trace records, counters, moment sums.
+#include <cooperative_groups.h>
+#include <cooperative_groups/scan.h>
+#include <cooperative_groups/reduce.h>
+
+#include "zz_dev.h"
+
+namespace cg = cooperative_groups;
+
+#define ZZ_BLOCK 256
+#define ZZ_SCAN_U 8
+#define ZZ_OVF_BIT 0x80000000u
+
+__device__ __forceinline__ unsigned long long zz_ld_acq(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All CTAs are co-resident (cooperative launch): arrive on a monotone counter, spin until everyone has.
+__device__ __forceinline__ void zz_grid_barrier(ZzDevCtl* C, unsigned long long& epoch)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();
+        atomicAdd(&C->bar, 1ULL);
+        while (zz_ld_acq(&C->bar) < epoch) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Append `val` to a global list; the active lanes of the warp share one atomic.
+__device__ __forceinline__ void zz_append(int32_t* list, unsigned int* cnt, int32_t val)
+{
+    cg::coalesced_group cgp = cg::coalesced_threads();
+    unsigned int base = 0;
+    if (cgp.thread_rank() == 0) base = atomicAdd(cnt, cgp.size());
+    base = cgp.shfl(base, 0);
+    list[(base & ~ZZ_OVF_BIT) + cgp.thread_rank()] = val;
+}
+
+__device__ __forceinline__ void zz_store_spec(ZzSpec* p, const ZzNodeOut& o)
+{
+    double2* q = reinterpret_cast<double2*>(p);
+    q[0] = make_double2(o.a, o.b);
+    q[1] = make_double2(o.told, o.tau);
+    unsigned long long w = (unsigned long long)o.k | ((unsigned long long)(o.nprop & 0xffffu) << 32) |
+                           ((unsigned long long)(o.nflip & 0xffu) << 48) | ((unsigned long long)(o.flags & 0xffu) << 56);
+    q[2] = make_double2(o.c, __longlong_as_double((long long)w));
+}
+
+struct ZzSpecR { double a, b, told, tau, c; unsigned int k, nprop, nflip, flags; };
+__device__ __forceinline__ ZzSpecR zz_load_spec(const ZzSpec* p)
+{
+    const double2* q = reinterpret_cast<const double2*>(p);
+    double2 u0 = __ldcg(q), u1 = __ldcg(q + 1), u2 = __ldcg(q + 2);
+    unsigned long long w = (unsigned long long)__double_as_longlong(u2.y);
+    ZzSpecR r;
+    r.a = u0.x; r.b = u0.y; r.told = u1.x; r.tau = u1.y; r.c = u2.x;
+    r.k = (unsigned int)w; r.nprop = (unsigned int)(w >> 32) & 0xffffu;
+    r.nflip = (unsigned int)(w >> 48) & 0xffu; r.flags = (unsigned int)(w >> 56) & 0xffu;
+    return r;
+}
+
+// Publish the result of one timeline evaluation: if the list of accepted flips differs from the one the
+// readers of this pass see, write it into the other slot and queue every coordinate that reads j.
+__device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const ZzNodeOut& o, uint32_t w0,
+                                           uint32_t cur, int nxt, int ws)
+{
+    ZzDevCtl* C = P.ctl;
+    int slot;
+    const uint32_t cnt = zz_pick_slot(o.hdr0, o.hdr1, w0, cur, slot);
+    bool same = (cnt == o.nflip);
+    if (same && cnt) {
+        const double* fl = P.v.flips + ((size_t)j * 2 + slot) * ZZ_MAXFLIP;
+#pragma unroll
+        for (int m = 0; m < ZZ_MAXFLIP; ++m)
+            if (m < (int)cnt) same = same && (zz_d2u(__ldcg(fl + m)) == zz_d2u(o.fl[m]));
+    }
+    if (!same) {
+        const int wsl = (slot == 0) ? 1 : 0;
+        double* fl = P.v.flips + ((size_t)j * 2 + wsl) * ZZ_MAXFLIP;
+#pragma unroll
+        for (int m = 0; m < ZZ_MAXFLIP; ++m)
+            if (m < (int)o.nflip) fl[m] = o.fl[m];
+        reinterpret_cast<uint32_t*>(P.v.kin + j)[6 + wsl] = (cur << 4) | o.nflip;
+        const uint32_t tagn = cur + 1;
+        const int32_t q1 = P.dptr[j + 1];
+        for (int32_t q = P.dptr[j]; q < q1; ++q) {
+            const int32_t k = P.didx[q];
+            const uint32_t old = atomicMax(P.dstamp + k, tagn);
+            if (old < tagn) {
+                zz_append(P.wl[nxt], &C->wl_cnt[nxt], k);
+                if (old < w0) zz_append(P.touched[0], &C->touched_cnt[ws], k);
+            }
+        }
+    }
+    zz_store_spec(P.spec + j, o);
+    if (o.flags & ZZ_F_VIOL) {
+        double* vi = P.viol_info + (size_t)j * 3;
+        vi[0] = o.viol_t; vi[1] = o.viol_l; vi[2] = o.viol_lb;
+    }
+    if (o.flags & ZZ_F_OVERFLOW) atomicOr(&C->wl_cnt[nxt], ZZ_OVF_BIT);
+}
+
+// Fold the converged end-of-window state of coordinate j into the frontier.
+__device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uint32_t w0, uint32_t cur,
+                                               unsigned int& nprop_acc, unsigned int& nflip_acc)
+{
+    ZzDevCtl* C = P.ctl;
+    const ZzSpecR s = zz_load_spec(P.spec + j);
+    if (s.flags & ZZ_F_VIOL) {
+        if (atomicExch(&C->viol, 1u) == 0u) {
+            const double* vi = P.viol_info + (size_t)j * 3;
+            C->viol_i = j + 1; C->viol_t = __ldcg(vi); C->viol_l = __ldcg(vi + 1); C->viol_lb = __ldcg(vi + 2);
+        }
+    }
+    double2* pq = reinterpret_cast<double2*>(P.v.priv + j);
+    pq[0] = make_double2(s.a, s.b);
+    pq[1] = make_double2(s.told, s.c);
+    P.v.tau[j] = s.tau;
+    P.v.kctr[j] = s.k;
+    nprop_acc += s.nprop;
+    if (s.nflip) {
+        nflip_acc += s.nflip;
+        double th, tf, xf; uint32_t h0, h1;
+        zz_ld_kin(P.v.kin + j, th, tf, xf, h0, h1);
+        int slot;
+        zz_pick_slot(h0, h1, w0, cur, slot);
+        const double* fl = P.v.flips + ((size_t)j * 2 + slot) * ZZ_MAXFLIP;
+        unsigned long long pos = 0;
+        if (P.record_trace) {
+            cg::coalesced_group cgp = cg::coalesced_threads();
+            const unsigned int mine = s.nflip;
+            const unsigned int pre = cg::exclusive_scan(cgp, mine, cg::plus<unsigned int>());
+            unsigned long long base = 0;
+            if (cgp.thread_rank() == cgp.size() - 1) base = atomicAdd(&C->trace_len, (unsigned long long)(pre + mine));
+            base = cgp.shfl(base, cgp.size() - 1);
+            pos = base + pre;
+        }
+        double a1 = __ldcg(P.s1 + j), a2 = __ldcg(P.s2 + j);
+        for (unsigned int m = 0; m < s.nflip; ++m) {
+            const double fs = __ldcg(fl + m);
+            const double xs = xf + th * (fs - tf);
+            a1 += (xf + xs) * (fs - tf);                          // trace.jl:194 (scaled by 1/(2T) on the host)
+            a2 += (fs - tf) * (xf * xf + xf * xs + xs * xs);
+            th = -th; tf = fs; xf = xs;
+            if (P.record_trace) {
+                if (pos + m < P.trace_cap) {
+                    double2* e = reinterpret_cast<double2*>(P.trace + pos + m);   // sfact.jl:50-52
+                    e[0] = make_double2(fs, __longlong_as_double((long long)j + 1));
+                    e[1] = make_double2(xs, th);
+                } else {
+                    C->trace_full = 1u;
+                }
+            }
+        }
+        P.s1[j] = a1; P.s2[j] = a2;
+        P.acc[j] = __ldcg(P.acc + j) + s.nflip;
+        double2* kq = reinterpret_cast<double2*>(P.v.kin + j);
+        kq[0] = make_double2(th, tf);
+        reinterpret_cast<double*>(P.v.kin + j)[2] = xf;
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK)
+zz_setup_kernel(const ZzParams P, const double* __restrict__ x0, const double* __restrict__ th0,
+                const double* __restrict__ c0)
+{
+    for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < P.v.d; j += gridDim.x * blockDim.x) {
+        ZzKin k; k.theta = th0[j]; k.tf = P.t0; k.xf = x0[j]; k.hdr[0] = 0; k.hdr[1] = 0;
+        P.v.kin[j] = k;
+        ZzPriv p; p.a = 0.0; p.b = 0.0; p.told = P.t0; p.c = c0[j];
+        P.v.priv[j] = p;
+        P.dstamp[j] = 0; P.acc[j] = 0; P.s1[j] = 0.0; P.s2[j] = 0.0;
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel(const ZzParams P)
+{
+    unsigned long long kmin = ~0ULL;
+    for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < P.v.d; j += gridDim.x * blockDim.x) {
+        zz_init_node(P.g, P.v, j, P.t0);
+        const unsigned long long k = zz_key(P.v.tau[j]);
+        kmin = k < kmin ? k : kmin;
+    }
+    cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
+    kmin = cg::reduce(w, kmin, cg::less<unsigned long long>());
+    if (w.thread_rank() == 0 && kmin != ~0ULL) atomicMin(&P.ctl->f0_key, kmin);
+}
+
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK)
+zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ x, double* __restrict__ th,
+                 double* __restrict__ c, long long* __restrict__ acc)
+{
+    for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < P.v.d; j += gridDim.x * blockDim.x) {
+        const ZzKin k = P.v.kin[j];
+        t[j] = k.tf; x[j] = k.xf; th[j] = k.theta; c[j] = P.v.priv[j].c; acc[j] = (long long)P.acc[j];
+    }
+}
+
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzParams P)
+{
+    ZzDevCtl* C = P.ctl;
+    __shared__ int32_t sq[ZZ_BLOCK / 32][32 * ZZ_SCAN_U];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int nthreads = gridDim.x * blockDim.x;
+    const unsigned int gwarp = gtid >> 5, nwarps = nthreads >> 5;
+    const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
+    const int32_t d = P.v.d;
+    unsigned long long epoch = 0;
+
+    // every thread keeps an identical copy of the controller; decisions only depend on values that are
+    // stable between two grid barriers
+    ZzCtl ctl; uint32_t cur, li, wat;
+    if (__ldcg(&C->started)) {
+        ctl = C->ctl; cur = C->cur; li = C->itg; wat = C->wattempt;
+    } else {
+        double F0 = zz_unkey(__ldcg(&C->f0_key));
+        zz_ctl_init(ctl, F0 < P.T ? F0 : P.T, P.T, P.delta0, P.target);
+        cur = 0; li = 0; wat = 0;
+    }
+    unsigned long long nprop_prev = (unsigned long long)P.target;
+    unsigned int windows_done = 0;
+    unsigned long long st_iters = 0, st_retries = 0, st_evals = 0, st_rebases = 0;
+    bool stop = false;
+
+    while (ctl.phase < ZZ_PH_DONE && !stop) {
+        if (cur > P.tag_limit) {  // iteration tags are about to run out of bits: forget all of them
+            for (int32_t j = gtid; j < d; j += nthreads) {
+                reinterpret_cast<unsigned long long*>(P.v.kin + j)[3] = 0ULL;
+                P.dstamp[j] = 0;
+            }
+            zz_grid_barrier(C, epoch);
+            cur = 0; st_rebases++;
+        }
+        const ZzCtl saved = ctl;
+        zz_ctl_begin(ctl);
+        const uint32_t w0 = cur + 1;
+        cur = w0;
+        const int ws = (int)(wat % 3u);
+        wat++;
+        const double H = ctl.H; const int incl = ctl.incl;
+
+        // ---------------- pass 1: scan + evaluate every coordinate with a proposal inside the window
+        int nxt = (int)((li + 1) % 3u);
+        if (leader) {
+            C->wl_cnt[(li + 2) % 3u] = 0;
+            const int wz = (int)(wat % 3u);  // slot of the NEXT attempt
+            C->touched_cnt[wz] = 0; C->smin_key[wz] = ~0ULL; C->nprop_win[wz] = 0;
+        }
+        for (int32_t base = gwarp * (32 * ZZ_SCAN_U); base < d; base += nwarps * (32 * ZZ_SCAN_U)) {
+            int qn = 0;
+#pragma unroll
+            for (int u = 0; u < ZZ_SCAN_U; ++u) {
+                const int32_t j = base + u * 32 + lane;
+                bool act = false;
+                if (j < d) { const double tj = __ldcg(P.v.tau + j); act = (tj < H) || (incl && tj == H); }
+                const unsigned int m = __ballot_sync(0xffffffffu, act);
+                if (act) sq[warp][qn + __popc(m & ((1u << lane) - 1u))] = j;
+                qn += __popc(m);
+            }
+            __syncwarp();
+            for (int q = lane; q < qn; q += 32) {
+                const int32_t j = sq[warp][q];
+                const uint32_t old = atomicMax(P.dstamp + j, cur);
+                if (old < w0) zz_append(P.touched[0], &C->touched_cnt[ws], j);
+                ZzNodeOut o;
+                zz_process_node(P.g, P.v, j, H, incl, w0, cur, true, o);
+                zz_publish(P, j, o, w0, cur, nxt, ws);
+                st_evals++;
+            }
+            __syncwarp();
+        }
+        zz_grid_barrier(C, epoch);
+        st_iters++;
+
+        // ---------------- relaxation passes
+        bool overflow = false;
+        for (;;) {
+            const unsigned int cw = __ldcg(&C->wl_cnt[nxt]);
+            if (cw & ZZ_OVF_BIT) { overflow = true; li = (li + 1) % 3u; break; }
+            if (cw == 0) break;
+            li = (li + 1) % 3u;
+            nxt = (int)((li + 1) % 3u);
+            cur++;
+            if (leader) C->wl_cnt[(li + 2) % 3u] = 0;
+            const int32_t* wl = P.wl[li];
+            for (unsigned int e = gtid; e < cw; e += nthreads) {
+                const int32_t j = __ldcg(wl + e);
+                ZzNodeOut o;
+                zz_process_node(P.g, P.v, j, H, incl, w0, cur, false, o);
+                zz_publish(P, j, o, w0, cur, nxt, ws);
+                st_evals++;
+            }
+            zz_grid_barrier(C, epoch);
+            st_iters++;
+        }
+        cur++;  // tag of the commit pass: every list written in this window is visible to it
+
+        // ---------------- phase B: time of the earliest accepted flip in the (trial) window
+        double smin = ZZ_INF;
+        if (!overflow && ctl.phase == ZZ_PH_B) {
+            const unsigned int nt = __ldcg(&C->touched_cnt[ws]);
+            unsigned long long kmin = ~0ULL;
+            for (unsigned int e = gtid; e < nt; e += nthreads) {
+                const int32_t j = __ldcg(P.touched[0] + e);
+                const ZzSpecR s = zz_load_spec(P.spec + j);
+                if (s.nflip) {
+                    double th, tf, xf; uint32_t h0, h1;
+                    zz_ld_kin(P.v.kin + j, th, tf, xf, h0, h1);
+                    int slot;
+                    zz_pick_slot(h0, h1, w0, cur, slot);
+                    const unsigned long long k = zz_key(__ldcg(P.v.flips + ((size_t)j * 2 + slot) * ZZ_MAXFLIP));
+                    kmin = k < kmin ? k : kmin;
+                }
+            }
+            if (kmin != ~0ULL) atomicMin(&C->smin_key[ws], kmin);
+            zz_grid_barrier(C, epoch);
+            const unsigned long long kk = __ldcg(&C->smin_key[ws]);
+            if (kk != ~0ULL) smin = zz_unkey(kk);
+        }
+
+        ZzCtl trial = ctl;
+        const int act = zz_ctl_end(trial, overflow, smin, nprop_prev);
+        if (act == ZZ_ACT_COMMIT && P.record_trace) {
+            // every event of this window (plus its end marker) must fit; otherwise hand the buffer to the host first
+            const unsigned long long tl = __ldcg(&C->trace_len);
+            const unsigned long long need = (unsigned long long)__ldcg(&C->touched_cnt[ws]) * ZZ_MAXFLIP + 1ULL;
+            if (tl + need > P.trace_cap) {
+                ctl = saved;
+                if (leader) C->need_drain = 1u;
+                break;
+            }
+        }
+        ctl = trial;
+        if (act == ZZ_ACT_COMMIT) {
+            const unsigned int nt = __ldcg(&C->touched_cnt[ws]);
+            unsigned int np = 0, nf = 0;
+            for (unsigned int e = gtid; e < nt; e += nthreads) {
+                const int32_t j = __ldcg(P.touched[0] + e);
+                zz_commit_node(P, j, w0, cur, np, nf);
+            }
+            cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
+            np = cg::reduce(w, np, cg::plus<unsigned int>());
+            nf = cg::reduce(w, nf, cg::plus<unsigned int>());
+            if (lane == 0 && (np | nf)) {
+                atomicAdd(&C->nprop_win[ws], (unsigned long long)np);
+                atomicAdd(&C->num, (unsigned long long)np);
+                atomicAdd(&C->nacc, (unsigned long long)nf);
+            }
+            zz_grid_barrier(C, epoch);
+            if (leader && P.record_trace) {  // window-end marker (i = 0): lets the host sort window by window
+                const unsigned long long pos = atomicAdd(&C->trace_len, 1ULL);
+                double2* e = reinterpret_cast<double2*>(P.trace + pos);
+                e[0] = make_double2(H, __longlong_as_double(0LL));
+                e[1] = make_double2(0.0, 0.0);
+            }
+            nprop_prev = __ldcg(&C->nprop_win[ws]);
+            windows_done++;
+            if (__ldcg(&C->viol) || __ldcg(&C->trace_full)) stop = true;
+            if (P.max_windows && windows_done >= P.max_windows) stop = true;
+        } else {
+            st_retries++;
+        }
+    }
+
+    if (leader) {
+        C->ctl = ctl; C->cur = cur; C->itg = li; C->wattempt = wat; C->started = 1u;
+        C->windows += windows_done; C->retries += st_retries; C->iters += st_iters; C->rebases += st_rebases;
+    }
+    cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
+    st_evals = cg::reduce(w, st_evals, cg::plus<unsigned long long>());
+    if (lane == 0 && st_evals) atomicAdd(&C->node_evals, st_evals);
+}

@@ -1,0 +1,607 @@
+// zzb200.cpp -- host side of libzzb200.so: the C-ABI declared in include/zzb200.h on top of the CUDA DRIVER
+// API.  libcuda is dlopen'ed on first use, so the library itself loads (and exports its symbols) on a machine
+// without a GPU; every compute entry point then fails with ZZB_E_CUDA -- there is no CPU fallback.
+//
+// The kernels live in zzb200_kernels.cubin (sm_100a), loaded with cuModuleLoadData; the event loop is one
+// persistent cooperative kernel (zz_run_kernel) launched with cuLaunchCooperativeKernel, re-launched only
+// when the trace buffer has to be drained to the host.
+#include <cuda.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/zzb200.h"
+#include "zz_dev.h"
+#include "zz_host_graph.h"
+
+#define ZZ_BLOCK 256
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------- driver loader
+#define ZZ_STR2(x) #x
+#define ZZ_STR(x) ZZ_STR2(x)
+#define ZZ_DRV_FUNCS(X) \
+    X(cuInit) X(cuDeviceGet) X(cuDeviceGetCount) X(cuDeviceGetName) X(cuDeviceGetAttribute) X(cuDeviceTotalMem) \
+    X(cuDevicePrimaryCtxRetain) X(cuDevicePrimaryCtxRelease) X(cuCtxPushCurrent) X(cuCtxPopCurrent) \
+    X(cuModuleLoadData) X(cuModuleUnload) X(cuModuleGetFunction) X(cuMemAlloc) X(cuMemFree) X(cuMemcpyHtoD) \
+    X(cuMemcpyDtoH) X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuMemsetD8) X(cuMemsetD8Async) X(cuStreamCreate) \
+    X(cuStreamDestroy) X(cuStreamSynchronize) X(cuLaunchKernel) X(cuLaunchCooperativeKernel) X(cuEventCreate) \
+    X(cuEventDestroy) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) X(cuGetErrorString) \
+    X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemFreeHost)
+
+struct Drv {
+#define X(name) decltype(&name) p_##name = nullptr;
+    ZZ_DRV_FUNCS(X)
+#undef X
+    void* handle = nullptr;
+};
+static Drv g_drv;
+
+static int32_t load_driver()
+{
+    if (g_drv.handle) return ZZB_OK;
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libcuda.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(ZZB_E_CUDA, "CUDA driver library (libcuda.so.1) not found: %s -- zzb200 has no CPU fallback", dlerror());
+#define X(name)                                                                                     \
+    g_drv.p_##name = (decltype(&name))dlsym(h, ZZ_STR(name));                                       \
+    if (!g_drv.p_##name) return fail(ZZB_E_CUDA, "symbol %s missing from the CUDA driver", ZZ_STR(name));
+    ZZ_DRV_FUNCS(X)
+#undef X
+    g_drv.handle = h;
+    return ZZB_OK;
+}
+
+static int32_t cu_fail(CUresult r, const char* what)
+{
+    const char* s = nullptr;
+    if (g_drv.p_cuGetErrorString) g_drv.p_cuGetErrorString(r, &s);
+    return fail(ZZB_E_CUDA, "%s failed: %s (CUresult %d)", what, s ? s : "?", (int)r);
+}
+#define CU(call)                                                     \
+    do {                                                             \
+        CUresult _r = g_drv.p_##call;                                \
+        if (_r != CUDA_SUCCESS) return cu_fail(_r, #call);           \
+    } while (0)
+
+// --------------------------------------------------------------------------------------------- global state
+struct Global {
+    bool ready = false;
+    CUdevice dev = 0; int dev_id = 0;
+    CUcontext ctx = nullptr;
+    CUmodule mod = nullptr;
+    CUfunction f_setup = nullptr, f_init = nullptr, f_run = nullptr, f_export = nullptr;
+    CUstream stream = nullptr;
+    CUevent ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0; int blocks_per_sm = 0;
+    size_t total_mem = 0; char name[128] = { 0 };
+};
+static Global G;
+static std::mutex g_mu;
+
+struct CtxGuard {
+    bool pushed = false;
+    CtxGuard() { if (G.ctx && g_drv.p_cuCtxPushCurrent(G.ctx) == CUDA_SUCCESS) pushed = true; }
+    ~CtxGuard() { if (pushed) { CUcontext c; g_drv.p_cuCtxPopCurrent(&c); } }
+};
+
+struct DevBuf {
+    CUdeviceptr p = 0; size_t n = 0;
+    int32_t alloc(size_t bytes)
+    {
+        release();
+        if (!bytes) bytes = 16;
+        CUresult r = g_drv.p_cuMemAlloc(&p, bytes);
+        if (r != CUDA_SUCCESS) { p = 0; return cu_fail(r, "cuMemAlloc"); }
+        n = bytes;
+        return ZZB_OK;
+    }
+    void release() { if (p) { g_drv.p_cuMemFree(p); p = 0; n = 0; } }
+    ~DevBuf() { release(); }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static int32_t upload(DevBuf& b, const void* src, size_t bytes)
+{
+    int32_t st = b.alloc(bytes);
+    if (st) return st;
+    if (bytes) CU(cuMemcpyHtoD(b.p, src, bytes));
+    return ZZB_OK;
+}
+
+static std::string default_cubin_path()
+{
+    const char* env = getenv("ZZB200_CUBIN");
+    if (env && *env) return env;
+    Dl_info info;
+    if (dladdr((void*)&default_cubin_path, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t k = p.find_last_of('/');
+        p = (k == std::string::npos) ? std::string(".") : p.substr(0, k);
+        return p + "/zzb200_kernels.cubin";
+    }
+    return "zzb200_kernels.cubin";
+}
+
+// ----------------------------------------------------------------------------------------------- handles
+struct zzb_problem_s {
+    ZzHostGraph hg;
+    DevBuf nptr, nidx, nwt, nwb, nfl, gmu, h, dptr, didx;
+    ZzGraph g;
+};
+
+struct zzb_run_s {
+    zzb_problem_s* prob = nullptr;
+    int32_t d = 0;
+    uint32_t flags = 0;
+    DevBuf kin, flips, priv, tau, kctr, spec, viol, dstamp, acc, s1, s2, wl[3], touched, trace, ctl;
+    DevBuf in_x, in_th, in_c;          // staging of the inputs / outputs
+    DevBuf out_t, out_x, out_th, out_c, out_acc;
+    unsigned long long trace_cap = 0;
+    ZzParams P;
+    double t0 = 0, T = 0;
+    double delta0 = 0, target_frac = 0.4; unsigned int tag_limit = ZZ_TAG_LIMIT; unsigned int max_windows = 0;
+    bool uploaded = false, executed = false;
+    // results
+    std::vector<zzb_event> events;     // sorted, markers removed
+    std::vector<double> x0;
+    ZzDevCtl hc;                       // last copy of the device control block
+    int64_t launches = 0;
+    int grid = 0;
+    bool fetched = false;
+    std::vector<double> ft, fx, fth, fc; std::vector<long long> facc; std::vector<double> hs1, hs2;
+};
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int32_t zzb_last_error(char* buf, int64_t len)
+{
+    if (!buf || len <= 0) return ZZB_E_ARG;
+    snprintf(buf, (size_t)len, "%s", g_err.c_str());
+    return ZZB_OK;
+}
+
+int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (G.ready) return ZZB_OK;
+    if (ndev > 1) return fail(ZZB_E_ARG, "one device per process: shard coordinates across processes (see DESIGN.md, multi-GPU)");
+    int32_t st = load_driver();
+    if (st) return st;
+    CU(cuInit(0));
+    int count = 0;
+    CU(cuDeviceGetCount(&count));
+    if (count <= 0) return fail(ZZB_E_CUDA, "no CUDA device visible -- zzb200 has no CPU fallback");
+    G.dev_id = (ndev >= 1 && dev_ids) ? dev_ids[0] : 0;
+    if (G.dev_id < 0 || G.dev_id >= count) return fail(ZZB_E_ARG, "device id %d out of range (0..%d)", G.dev_id, count - 1);
+    CU(cuDeviceGet(&G.dev, G.dev_id));
+    CU(cuDeviceGetName(G.name, sizeof G.name, G.dev));
+    CU(cuDeviceTotalMem(&G.total_mem, G.dev));
+    int major = 0, minor = 0, coop = 0;
+    CU(cuDeviceGetAttribute(&major, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MAJOR, G.dev));
+    CU(cuDeviceGetAttribute(&minor, CU_DEVICE_ATTRIBUTE_COMPUTE_CAPABILITY_MINOR, G.dev));
+    CU(cuDeviceGetAttribute(&G.sm_count, CU_DEVICE_ATTRIBUTE_MULTIPROCESSOR_COUNT, G.dev));
+    CU(cuDeviceGetAttribute(&coop, CU_DEVICE_ATTRIBUTE_COOPERATIVE_LAUNCH, G.dev));
+    if (major != 10) return fail(ZZB_E_CUDA, "device %s is sm_%d%d; the kernels are built for sm_100a only", G.name, major, minor);
+    if (!coop) return fail(ZZB_E_CUDA, "device does not support cooperative launch");
+    CU(cuDevicePrimaryCtxRetain(&G.ctx, G.dev));  // shared with the CUDA runtime (torch) of this process
+    CtxGuard cg;
+    std::string path = cubin_path && *cubin_path ? std::string(cubin_path) : default_cubin_path();
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return fail(ZZB_E_CUDA, "cannot open kernel image %s (build with __graft_entry__.build())", path.c_str());
+    std::vector<char> img;
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    img.resize((size_t)sz + 1);
+    if (fread(img.data(), 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return fail(ZZB_E_CUDA, "short read on %s", path.c_str()); }
+    fclose(f);
+    CU(cuModuleLoadData(&G.mod, img.data()));
+    CU(cuModuleGetFunction(&G.f_setup, G.mod, "zz_setup_kernel"));
+    CU(cuModuleGetFunction(&G.f_init, G.mod, "zz_init_kernel"));
+    CU(cuModuleGetFunction(&G.f_run, G.mod, "zz_run_kernel"));
+    CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
+    CU(cuStreamCreate(&G.stream, CU_STREAM_NON_BLOCKING));
+    CU(cuEventCreate(&G.ev0, CU_EVENT_DEFAULT));
+    CU(cuEventCreate(&G.ev1, CU_EVENT_DEFAULT));
+    CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm, G.f_run, ZZ_BLOCK, 0));
+    if (G.blocks_per_sm < 1) return fail(ZZB_E_CUDA, "zz_run_kernel does not fit on an SM");
+    G.ready = true;
+    return ZZB_OK;
+}
+
+int32_t zzb_shutdown(void)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!G.ready) return ZZB_OK;
+    {
+        CtxGuard cg;
+        if (G.ev0) g_drv.p_cuEventDestroy(G.ev0);
+        if (G.ev1) g_drv.p_cuEventDestroy(G.ev1);
+        if (G.stream) g_drv.p_cuStreamDestroy(G.stream);
+        if (G.mod) g_drv.p_cuModuleUnload(G.mod);
+    }
+    g_drv.p_cuDevicePrimaryCtxRelease(G.dev);
+    G = Global();
+    return ZZB_OK;
+}
+
+int32_t zzb_device_info(int32_t* sm_count, int64_t* total_mem, char* name, int64_t name_len)
+{
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (sm_count) *sm_count = G.sm_count;
+    if (total_mem) *total_mem = (int64_t)G.total_mem;
+    if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", G.name);
+    return ZZB_OK;
+}
+
+int32_t zzb_problem_create_gaussian(zzb_problem_t* out, int64_t d, const int64_t* colptr, const int64_t* rowval,
+                                    const double* nzval, const double* hvec, const int64_t* bnd_colptr,
+                                    const int64_t* bnd_rowval, const double* bnd_nzval, const double* bnd_mu)
+{
+    if (!out || !colptr || !rowval || !nzval) return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded -- zzb200 has no CPU fallback");
+    if (!bnd_colptr) { bnd_colptr = colptr; bnd_rowval = rowval; bnd_nzval = nzval; }
+    std::vector<double> zeros;
+    if (!bnd_mu) { zeros.assign((size_t)std::max<int64_t>(d, 1), 0.0); bnd_mu = zeros.data(); }
+    zzb_problem_s* p = new zzb_problem_s();
+    std::string e = zz_build_graph(p->hg, d, colptr, rowval, nzval, hvec, bnd_colptr, bnd_rowval, bnd_nzval, bnd_mu);
+    if (!e.empty()) { delete p; return fail(ZZB_E_GRAPH, "%s", e.c_str()); }
+    CtxGuard cg;
+    const ZzHostGraph& hg = p->hg;
+    int32_t st = 0;
+#define UP(buf, vec) if (!st) st = upload(p->buf, hg.vec.data(), hg.vec.size() * sizeof(hg.vec[0]))
+    UP(nptr, nptr); UP(nidx, nidx); UP(nwt, nwt); UP(nwb, nwb); UP(nfl, nfl); UP(gmu, gmu); UP(dptr, dptr); UP(didx, didx);
+    if (hg.has_h) UP(h, h);
+#undef UP
+    if (st) { delete p; return st; }
+    p->g.nptr = p->nptr.as<int32_t>(); p->g.nidx = p->nidx.as<int32_t>(); p->g.nwt = p->nwt.as<double>();
+    p->g.nwb = p->nwb.as<double>(); p->g.nfl = p->nfl.as<uint8_t>(); p->g.gmu = p->gmu.as<double>();
+    p->g.h = hg.has_h ? p->h.as<double>() : nullptr; p->g.same = hg.same;
+    *out = p;
+    return ZZB_OK;
+}
+
+int32_t zzb_problem_free(zzb_problem_t p)
+{
+    if (!p) return ZZB_OK;
+    CtxGuard cg;
+    delete p;
+    return ZZB_OK;
+}
+
+int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_events, zzb_run_t* out)
+{
+    if (!p || !out) return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    CtxGuard cg;
+    zzb_run_s* r = new zzb_run_s();
+    r->prob = p; r->d = p->hg.d; r->flags = flags;
+    const size_t d = (size_t)r->d;
+    int32_t st = 0;
+#define AL(buf, bytes) if (!st) st = r->buf.alloc(bytes)
+    AL(kin, d * sizeof(ZzKin)); AL(flips, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(priv, d * sizeof(ZzPriv));
+    AL(tau, d * 8); AL(kctr, d * 4); AL(spec, d * sizeof(ZzSpec)); AL(viol, d * 24); AL(dstamp, d * 4);
+    AL(acc, d * 4); AL(s1, d * 8); AL(s2, d * 8); AL(wl[0], d * 4); AL(wl[1], d * 4); AL(wl[2], d * 4);
+    AL(touched, d * 4); AL(ctl, sizeof(ZzDevCtl));
+    AL(in_x, d * 8); AL(in_th, d * 8); AL(in_c, d * 8);
+    AL(out_t, d * 8); AL(out_x, d * 8); AL(out_th, d * 8); AL(out_c, d * 8); AL(out_acc, d * 8);
+    if (!(flags & ZZB_FLAG_NO_TRACE)) {
+        unsigned long long cap = (unsigned long long)std::max<int64_t>(trace_capacity_events, 0);
+        const unsigned long long need = (unsigned long long)d * ZZ_MAXFLIP + 2ULL;
+        if (cap == 0) {
+            size_t fr = 0, tot = 0;
+            if (!st && g_drv.p_cuMemGetInfo(&fr, &tot) != CUDA_SUCCESS) fr = (size_t)1 << 30;
+            cap = std::max<unsigned long long>(need * 4, 1ULL << 22);
+            cap = std::min<unsigned long long>(cap, std::max<unsigned long long>(need, (fr / 4) / sizeof(ZzEvent)));
+        }
+        if (cap < need) cap = need;
+        r->trace_cap = cap;
+        AL(trace, (size_t)cap * sizeof(ZzEvent));
+    }
+#undef AL
+    if (st) { delete r; return st == ZZB_E_CUDA ? ZZB_E_NOMEM : st; }
+    r->grid = G.sm_count * G.blocks_per_sm;
+    *out = r;
+    return ZZB_OK;
+}
+
+static void fill_params(zzb_run_s* r)
+{
+    ZzParams& P = r->P;
+    memset(&P, 0, sizeof P);
+    P.g = r->prob->g;
+    P.v.d = r->d; P.v.kin = r->kin.as<ZzKin>(); P.v.flips = r->flips.as<double>(); P.v.priv = r->priv.as<ZzPriv>();
+    P.v.tau = r->tau.as<double>(); P.v.kctr = r->kctr.as<uint32_t>();
+    P.dptr = r->prob->dptr.as<int32_t>(); P.didx = r->prob->didx.as<int32_t>();
+    P.spec = r->spec.as<ZzSpec>(); P.viol_info = r->viol.as<double>(); P.dstamp = r->dstamp.as<unsigned int>();
+    P.acc = r->acc.as<unsigned int>(); P.s1 = r->s1.as<double>(); P.s2 = r->s2.as<double>();
+    for (int k = 0; k < 3; ++k) P.wl[k] = r->wl[k].as<int32_t>();
+    P.touched[0] = r->touched.as<int32_t>();
+    P.trace = r->trace.as<ZzEvent>(); P.trace_cap = r->trace_cap;
+    P.ctl = r->ctl.as<ZzDevCtl>();
+    P.record_trace = (r->flags & ZZB_FLAG_NO_TRACE) ? 0 : 1;
+}
+
+int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
+{
+    if (!r || !key) return fail(ZZB_E_ARG, "null argument");
+    if (!strcmp(key, "delta0")) r->delta0 = value;
+    else if (!strcmp(key, "target_frac")) r->target_frac = value;
+    else if (!strcmp(key, "tag_limit")) r->tag_limit = (unsigned int)value;
+    else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
+    else if (!strcmp(key, "grid")) r->grid = std::max(1, std::min((int)value, G.sm_count * G.blocks_per_sm));
+    else return fail(ZZB_E_ARG, "unknown tuning key %s", key);
+    return ZZB_OK;
+}
+
+int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* theta0, const double* c,
+                       const uint64_t* seed, int32_t adapt, double factor)
+{
+    if (!r || !x0 || !theta0 || !c || !seed) return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    CtxGuard cg;
+    const size_t nb = (size_t)r->d * 8;
+    fill_params(r);
+    ZzParams& P = r->P;
+    P.v.seed0 = seed[0]; P.v.seed1 = seed[1]; P.v.adapt = adapt; P.v.factor = factor; P.t0 = t0;
+    r->t0 = t0;
+    r->x0.assign(x0, x0 + r->d);
+    CU(cuMemcpyHtoDAsync(r->in_x.p, x0, nb, G.stream));
+    CU(cuMemcpyHtoDAsync(r->in_th.p, theta0, nb, G.stream));
+    CU(cuMemcpyHtoDAsync(r->in_c.p, c, nb, G.stream));
+    ZzDevCtl hc; memset(&hc, 0, sizeof hc);
+    hc.f0_key = ~0ULL; for (int k = 0; k < 3; ++k) hc.smin_key[k] = ~0ULL;
+    CU(cuMemcpyHtoDAsync(r->ctl.p, &hc, sizeof hc, G.stream));
+    const unsigned grid = (unsigned)std::min<size_t>(((size_t)r->d + ZZ_BLOCK - 1) / ZZ_BLOCK, (size_t)G.sm_count * 8);
+    CUdeviceptr px = r->in_x.p, pth = r->in_th.p, pc = r->in_c.p;
+    void* a1[] = { &P, &px, &pth, &pc };
+    CU(cuLaunchKernel(G.f_setup, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a1, nullptr));
+    void* a2[] = { &P };
+    CU(cuLaunchKernel(G.f_init, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a2, nullptr));
+    CU(cuStreamSynchronize(G.stream));
+    r->launches += 2;
+    r->uploaded = true; r->executed = false; r->fetched = false;
+    r->events.clear();
+    return ZZB_OK;
+}
+
+// sort every window segment (records between two i == 0 markers) by (time, coordinate) and drop the markers
+static void absorb_trace_chunk(zzb_run_s* r, std::vector<zzb_event>& chunk)
+{
+    size_t seg = 0;
+    std::vector<std::pair<size_t, size_t>> segs;
+    for (size_t k = 0; k < chunk.size(); ++k)
+        if (chunk[k].i == 0) { if (k > seg) segs.emplace_back(seg, k); seg = k + 1; }
+    if (seg < chunk.size()) segs.emplace_back(seg, chunk.size());
+    auto cmp = [](const zzb_event& a, const zzb_event& b) { return a.t < b.t || (a.t == b.t && a.i < b.i); };
+    unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (chunk.size() < (1u << 16)) nthr = 1;
+    std::vector<std::thread> th;
+    for (unsigned w = 0; w < nthr; ++w)
+        th.emplace_back([&, w]() { for (size_t s = w; s < segs.size(); s += nthr) std::sort(chunk.begin() + segs[s].first, chunk.begin() + segs[s].second, cmp); });
+    for (auto& t : th) t.join();
+    size_t total = 0;
+    for (auto& s : segs) total += s.second - s.first;
+    r->events.reserve(r->events.size() + total);
+    for (auto& s : segs) r->events.insert(r->events.end(), chunk.begin() + s.first, chunk.begin() + s.second);
+}
+
+int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
+{
+    if (!r) return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (!r->uploaded) return fail(ZZB_E_ARG, "zzb_run_upload must precede zzb_run_execute");
+    CtxGuard cg;
+    ZzParams& P = r->P;
+    r->T = T;
+    P.T = T;
+    double span = T - r->t0;
+    P.delta0 = r->delta0 > 0 ? r->delta0 : std::max(1e-12, 1e-2 * std::min(1.0, span > 0 ? span : 1.0));
+    P.target = std::max(r->target_frac * (double)r->d, 4.0);
+    P.tag_limit = r->tag_limit; P.max_windows = r->max_windows;
+    float total_ms = 0.f;
+    if (device_ms) *device_ms = 0.f;
+    if (!(r->t0 < T)) { r->executed = true; return ZZB_OK; }  // `while t' < T` never entered (sfact.jl:199)
+    for (;;) {
+        CU(cuMemsetD8Async(r->ctl.p, 0, 8, G.stream));  // barrier counter
+        void* args[] = { &P };
+        CU(cuEventRecord(G.ev0, G.stream));
+        CU(cuLaunchCooperativeKernel(G.f_run, (unsigned)r->grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, args));
+        CU(cuEventRecord(G.ev1, G.stream));
+        CU(cuStreamSynchronize(G.stream));
+        r->launches++;
+        float ms = 0.f;
+        CU(cuEventElapsedTime(&ms, G.ev0, G.ev1));
+        total_ms += ms;
+        CU(cuMemcpyDtoH(&r->hc, r->ctl.p, sizeof(ZzDevCtl)));
+        const ZzDevCtl& hc = r->hc;
+        if (hc.trace_full) return fail(ZZB_E_INTERNAL, "trace record dropped (internal protocol error)");
+        if (hc.viol) break;
+        if (hc.ctl.phase == ZZ_PH_FAIL) return fail(ZZB_E_INTERNAL, "window controller failed");
+        if (P.record_trace && (hc.need_drain || hc.ctl.phase == ZZ_PH_DONE || r->max_windows)) {
+            if (hc.need_drain && hc.trace_len == 0) return fail(ZZB_E_TRACE, "trace buffer (%llu records) too small for one window", r->trace_cap);
+            std::vector<zzb_event> chunk((size_t)hc.trace_len);
+            if (hc.trace_len) CU(cuMemcpyDtoH(chunk.data(), r->trace.p, (size_t)hc.trace_len * sizeof(zzb_event)));
+            absorb_trace_chunk(r, chunk);
+            // reset trace_len and need_drain on the device
+            ZzDevCtl z = hc; z.trace_len = 0; z.need_drain = 0;
+            CU(cuMemcpyHtoD(r->ctl.p, &z, sizeof z));
+        }
+        if (hc.ctl.phase == ZZ_PH_DONE) break;
+        if (r->max_windows && !hc.need_drain) break;  // caller asked for a bounded slice
+    }
+    if (device_ms) *device_ms = total_ms;
+    r->executed = true; r->fetched = false;
+    if (r->hc.viol) {
+        if (P.record_trace && r->hc.trace_len) {
+            std::vector<zzb_event> chunk((size_t)r->hc.trace_len);
+            CU(cuMemcpyDtoH(chunk.data(), r->trace.p, chunk.size() * sizeof(zzb_event)));
+            absorb_trace_chunk(r, chunk);
+        }
+        return fail(ZZB_E_BOUND, "Tuning parameter `c` too small. (coordinate %d, t = %.17g, l = %.17g, lb = %.17g)",
+                    r->hc.viol_i, r->hc.viol_t, r->hc.viol_l, r->hc.viol_lb);
+    }
+    return ZZB_OK;
+}
+
+static int32_t fetch_state(zzb_run_s* r)
+{
+    if (r->fetched) return ZZB_OK;
+    if (!r->uploaded) return fail(ZZB_E_ARG, "run has no state yet");
+    CtxGuard cg;
+    const size_t d = (size_t)r->d;
+    const unsigned grid = (unsigned)std::min<size_t>((d + ZZ_BLOCK - 1) / ZZ_BLOCK, (size_t)G.sm_count * 8);
+    CUdeviceptr pt = r->out_t.p, px = r->out_x.p, pth = r->out_th.p, pc = r->out_c.p, pa = r->out_acc.p;
+    void* a[] = { &r->P, &pt, &px, &pth, &pc, &pa };
+    CU(cuLaunchKernel(G.f_export, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a, nullptr));
+    r->launches++;
+    r->ft.resize(d); r->fx.resize(d); r->fth.resize(d); r->fc.resize(d); r->facc.resize(d); r->hs1.resize(d); r->hs2.resize(d);
+    CU(cuMemcpyDtoHAsync(r->ft.data(), pt, d * 8, G.stream));
+    CU(cuMemcpyDtoHAsync(r->fx.data(), px, d * 8, G.stream));
+    CU(cuMemcpyDtoHAsync(r->fth.data(), pth, d * 8, G.stream));
+    CU(cuMemcpyDtoHAsync(r->fc.data(), pc, d * 8, G.stream));
+    CU(cuMemcpyDtoHAsync(r->facc.data(), pa, d * 8, G.stream));
+    CU(cuMemcpyDtoHAsync(r->hs1.data(), r->s1.p, d * 8, G.stream));
+    CU(cuMemcpyDtoHAsync(r->hs2.data(), r->s2.p, d * 8, G.stream));
+    CU(cuMemcpyDtoHAsync(&r->hc, r->ctl.p, sizeof(ZzDevCtl), G.stream));
+    CU(cuStreamSynchronize(G.stream));
+    r->fetched = true;
+    return ZZB_OK;
+}
+
+int32_t zzb_spdmp_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, double* c,
+                      const uint64_t* seed, int32_t adapt, double factor, uint32_t flags, zzb_run_t* out)
+{
+    if (!out || !c) return fail(ZZB_E_ARG, "null argument");
+    zzb_run_t r = nullptr;
+    int32_t st = zzb_run_create(p, flags, 0, &r);
+    if (st) return st;
+    st = zzb_run_upload(r, t0, x0, theta0, c, seed, adapt, factor);
+    if (!st) st = zzb_run_execute(r, T, nullptr);
+    if (st && st != ZZB_E_BOUND) { zzb_run_free(r); return st; }
+    int32_t st2 = fetch_state(r);
+    if (st2) { zzb_run_free(r); return st2; }
+    memcpy(c, r->fc.data(), (size_t)r->d * 8);  // adapted bounds (sfact.jl:211)
+    *out = r;
+    if (st == ZZB_E_BOUND)
+        fail(ZZB_E_BOUND, "Tuning parameter `c` too small. (coordinate %d, t = %.17g, l = %.17g, lb = %.17g)", r->hc.viol_i,
+             r->hc.viol_t, r->hc.viol_l, r->hc.viol_lb);
+    return st;
+}
+
+int32_t zzb_run_stats(zzb_run_t r, int64_t* out, int32_t n)
+{
+    if (!r || !out) return fail(ZZB_E_ARG, "null argument");
+    int32_t st = fetch_state(r);
+    if (st) return st;
+    const int64_t v[8] = { (int64_t)r->hc.windows, (int64_t)r->hc.retries, (int64_t)r->hc.iters, (int64_t)r->hc.node_evals,
+                           (int64_t)r->hc.rebases, r->launches, (int64_t)r->grid, (int64_t)ZZ_BLOCK };
+    for (int32_t k = 0; k < n && k < 8; ++k) out[k] = v[k];
+    return ZZB_OK;
+}
+
+int32_t zzb_run_counts(zzb_run_t r, int64_t* acc, int64_t* num)
+{
+    if (!r) return fail(ZZB_E_ARG, "null argument");
+    int32_t st = fetch_state(r);
+    if (st) return st;
+    if (acc) for (int32_t j = 0; j < r->d; ++j) acc[j] = r->facc[j];
+    if (num) *num = (int64_t)r->hc.num;
+    return ZZB_OK;
+}
+
+int32_t zzb_run_final_state(zzb_run_t r, double* t, double* x, double* theta, double* c)
+{
+    if (!r) return fail(ZZB_E_ARG, "null argument");
+    int32_t st = fetch_state(r);
+    if (st) return st;
+    const size_t nb = (size_t)r->d * 8;
+    if (t) memcpy(t, r->ft.data(), nb);
+    if (x) memcpy(x, r->fx.data(), nb);
+    if (theta) memcpy(theta, r->fth.data(), nb);
+    if (c) memcpy(c, r->fc.data(), nb);
+    return ZZB_OK;
+}
+
+int32_t zzb_trace_len(zzb_run_t r, int64_t* n)
+{
+    if (!r || !n) return fail(ZZB_E_ARG, "null argument");
+    if (r->flags & ZZB_FLAG_NO_TRACE) {  // events were counted, not stored
+        int32_t st = fetch_state(r);
+        if (st) return st;
+        *n = (int64_t)r->hc.nacc;
+        return ZZB_OK;
+    }
+    *n = (int64_t)r->events.size();
+    return ZZB_OK;
+}
+
+int32_t zzb_trace_copy(zzb_run_t r, zzb_event* dst, int64_t first, int64_t count)
+{
+    if (!r || !dst) return fail(ZZB_E_ARG, "null argument");
+    if (r->flags & ZZB_FLAG_NO_TRACE) return fail(ZZB_E_ARG, "run was created with ZZB_FLAG_NO_TRACE");
+    if (first < 0 || count < 0 || (size_t)(first + count) > r->events.size()) return fail(ZZB_E_ARG, "trace range out of bounds");
+    memcpy(dst, r->events.data() + first, (size_t)count * sizeof(zzb_event));
+    return ZZB_OK;
+}
+
+int32_t zzb_trace_sums(zzb_run_t r, double* s1, double* s2)
+{
+    if (!r) return fail(ZZB_E_ARG, "null argument");
+    int32_t st = fetch_state(r);
+    if (st) return st;
+    if (s1) memcpy(s1, r->hs1.data(), (size_t)r->d * 8);
+    if (s2) memcpy(s2, r->hs2.data(), (size_t)r->d * 8);
+    return ZZB_OK;
+}
+
+int32_t zzb_trace_moments(zzb_run_t r, double* m1, double* m2)
+{
+    if (!r) return fail(ZZB_E_ARG, "null argument");
+    int32_t st = fetch_state(r);
+    if (st) return st;
+    // T = time of the last event (trace.jl:186) = the window end of phase C = the frontier when done
+    const double Tl = r->hc.ctl.F;
+    for (int32_t j = 0; j < r->d; ++j) {
+        if (m1) m1[j] = r->hs1[j] * (1 / (2 * Tl));   // scale = 1/(2T), trace.jl:190
+        if (m2) m2[j] = r->hs2[j] / (3 * Tl);
+    }
+    return ZZB_OK;
+}
+
+int32_t zzb_run_error_info(zzb_run_t r, int64_t* i, double* t, double* l, double* lb)
+{
+    if (!r) return fail(ZZB_E_ARG, "null argument");
+    if (i) *i = r->hc.viol_i;
+    if (t) *t = r->hc.viol_t;
+    if (l) *l = r->hc.viol_l;
+    if (lb) *lb = r->hc.viol_lb;
+    return ZZB_OK;
+}
+
+int32_t zzb_run_free(zzb_run_t r)
+{
+    if (!r) return ZZB_OK;
+    CtxGuard cg;
+    delete r;
+    return ZZB_OK;
+}
+
+}  // extern "C"
