@@ -57,6 +57,9 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path);
 int32_t zzb_shutdown(void);
 int32_t zzb_last_error(char* buf, int64_t len);
 int32_t zzb_device_info(int32_t* sm_count, int64_t* total_mem, char* name, int64_t name_len);
+/* CUDA events on the library's launching stream (which = 0 start, 1 stop) for device-side timing of a region. */
+int32_t zzb_event_record(int32_t which);
+int32_t zzb_event_elapsed_ms(float* ms);
 
 /* Problem = target potential + sampler matrices (two CSC matrices of order d; hvec / bnd_mu may be NULL = zeros).
  * grad phi_i(x) = sum_k tgt[k,i] x_k - hvec[i];  bound uses bnd (Z.Gamma) and bnd_mu (Z.mu), fact_samplers.jl:50-54. */
@@ -75,6 +78,7 @@ int32_t zzb_spdmp_run(zzb_problem_t p, double t0, const double* x0, const double
 int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_events, zzb_run_t* out);
 int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* theta0, const double* c,
                        const uint64_t* seed, int32_t adapt, double factor);
+int32_t zzb_run_reset(zzb_run_t r);                                  /* re-initialise from the inputs resident in HBM */
 int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms);   /* device_ms: CUDA-event time of the kernel(s) */
 int32_t zzb_run_set(zzb_run_t r, const char* key, double value);    /* "delta0", "target_frac", "tag_limit", "max_windows" */
 int32_t zzb_run_stats(zzb_run_t r, int64_t* out, int32_t n);        /* windows, retries, passes, node evaluations, rebases,

@@ -26,6 +26,7 @@ struct zzw_run {
     int status = 0; int64_t err_i = 0; double err_t = 0, err_l = 0, err_lb = 0;
     // schedule statistics
     int64_t windows = 0, retries = 0, iters = 0, node_evals = 0, max_iters = 0;
+    std::vector<int64_t> pass_hist = std::vector<int64_t>(64, 0);  // work-list size summed per pass index
     std::string msg;
 };
 
@@ -52,6 +53,9 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
 
     ZzGraph g; g.nptr = G.nptr.data(); g.nidx = G.nidx.data(); g.nwt = G.nwt.data(); g.nwb = G.nwb.data();
     g.nfl = G.nfl.data(); g.gmu = G.gmu.data(); g.h = G.has_h ? G.h.data() : nullptr; g.same = G.same;
+    g.grid_m = (tag_limit & 0x80000000u) ? 0 : G.grid_m; g.grid_n = G.grid_n;  // top bit of tag_limit: force the CSR path
+    tag_limit &= 0x7fffffffu;
+    for (int q = 0; q < 5; ++q) g.grid_diag[q] = G.grid_diag[q];
     ZzView v; v.d = (int32_t)d; v.kin = kin.data(); v.flips = flips.data(); v.priv = priv.data();
     v.tau = tau.data(); v.kctr = kctr.data(); v.seed0 = seed[0]; v.seed1 = seed[1]; v.adapt = adapt; v.factor = factor;
 
@@ -122,6 +126,7 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
                 wl.swap(next); next.clear();
                 if (wl.empty()) break;
                 ++it;
+                r->pass_hist[std::min<int64_t>(it, 63)] += (int64_t)wl.size();
                 for (int32_t j : wl) {
                     zz_process_node(g, v, j, ctl.H, ctl.incl, w0, cur, false, o);
                     handle(j, o, w0, cur);
@@ -191,5 +196,6 @@ void zzw_final_state(const zzw_run* r, double* t, double* x, double* th, double*
 }
 void zzw_sums(const zzw_run* r, double* s1, double* s2) { memcpy(s1, r->s1.data(), (size_t)r->d * 8); memcpy(s2, r->s2.data(), (size_t)r->d * 8); }
 void zzw_stats(const zzw_run* r, int64_t* out) { out[0] = r->windows; out[1] = r->retries; out[2] = r->iters; out[3] = r->node_evals; out[4] = r->max_iters; }
+void zzw_pass_hist(const zzw_run* r, int64_t* out) { memcpy(out, r->pass_hist.data(), 64 * 8); }
 void zzw_free(zzw_run* r) { delete r; }
 }

@@ -128,6 +128,7 @@ def wlib():
         L.zzw_final_state.argtypes = [C.c_void_p] * 5
         L.zzw_sums.argtypes = [C.c_void_p] * 3
         L.zzw_stats.argtypes = [C.c_void_p] * 2
+        L.zzw_pass_hist.argtypes = [C.c_void_p] * 2
         L.zzw_error_info.argtypes = [C.c_void_p] * 5
         L.zzw_free.argtypes = [C.c_void_p]
         _wlib = L
@@ -169,6 +170,9 @@ def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1,
         L.zzw_sums(r, _p(out.s1), _p(out.s2))
         st = np.zeros(5, np.int64)
         L.zzw_stats(r, _p(st))
+        ph = np.zeros(64, np.int64)
+        L.zzw_pass_hist(r, _p(ph))
+        out.pass_hist = ph
         out.stats = dict(windows=int(st[0]), retries=int(st[1]), iters=int(st[2]), node_evals=int(st[3]), max_iters=int(st[4]))
         return out
     finally:

@@ -38,3 +38,121 @@ def test_window_length_does_not_change_results(gpu, delta0, frac):
     ref = O.spdmp(G, G, 0.0, x0, th0, 4.0, c)
     got, _ = run_gpu(gpu, G, G, 0.0, x0, th0, 4.0, c, tune=dict(delta0=delta0, target_frac=frac))
     O.assert_same_run(ref, got)
+
+
+def test_rectangular_grid_tight_bound(gpu):
+    G = gpu.grid_precision(5, 9)
+    rng = np.random.default_rng(3)
+    x0, th0 = rng.standard_normal(45), rng.choice(np.array([-1.0, 1.0]), 45)
+    c = np.full(45, np.sqrt(np.finfo(float).eps))
+    ref = O.spdmp(G, G, 0.0, x0, th0, 8.0, c)
+    got, _ = run_gpu(gpu, G, G, 0.0, x0, th0, 8.0, c)
+    O.assert_same_run(ref, got)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_sparse_with_mu_h_adapt(gpu, seed):
+    """General sparse columns (CSR kernel), target != sampler matrix, Z.mu != 0, linear term, adaptation of c."""
+    d = 60
+    Gt = gpu.random_sparse_spd(d, deg=2 + seed % 3, seed=seed)
+    Gb = Gt.scaled(0.9)
+    rng = np.random.default_rng(seed)
+    x0, th0 = rng.standard_normal(d), rng.choice(np.array([-1.0, -0.5, 0.5, 1.0]), d)
+    mu, h = 0.1 * rng.standard_normal(d), 0.3 * rng.standard_normal(d)
+    c = 0.2 * Gt.colnorms()
+    ref = O.spdmp(Gt, Gb, 0.0, x0, th0, 20.0, c, h=h, mu=mu, adapt=True)
+    got, _ = run_gpu(gpu, Gt, Gb, 0.0, x0, th0, 20.0, c, h=h, mu=mu, adapt=True)
+    O.assert_same_run(ref, got)
+    assert (got.c != c).any()
+
+
+def test_dense_columns_slow_path_and_pdmp(gpu):
+    G = gpu.random_spd(12, density=0.5)
+    rng = np.random.default_rng(0)
+    x0, th0 = rng.random(12), rng.choice(np.array([-1.0, 1.0]), 12)
+    c = 2.0 * G.colnorms()
+    ref = O.spdmp(G, G, 0.0, x0, th0, 50.0, c, adapt=True)
+    Xi, (t, x, th), (acc, num), cc = gpu.pdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 50.0, c, gpu.ZigZag(G, np.zeros(12)),
+                                              seed=(1, 2), adapt=True)
+    assert num == ref.num and np.array_equal(acc, ref.acc)
+    assert np.array_equal(Xi.events["t"].view(np.uint64), ref.events["t"].view(np.uint64))
+
+
+def test_bound_violation_error(gpu):
+    """error("Tuning parameter `c` too small.") of sfact.jl:124 through the C-ABI (ZZB_E_BOUND)."""
+    G, x0, th0, c = gpu.gmrf_config(8)
+    with pytest.raises(gpu.BoundError, match="Tuning parameter `c` too small"):
+        run_gpu(gpu, G, G.scaled(0.5), 0.0, x0, th0, 5.0, np.full(G.n, 1e-9))
+
+
+def test_empty_horizon(gpu):
+    G, x0, th0, c = gpu.gmrf_config(8)
+    got, _ = run_gpu(gpu, G, G, 0.0, x0, th0, 0.0, c)
+    assert len(got.events) == 0 and got.num == 0 and np.array_equal(got.x, x0)
+
+
+def test_tag_rebase_and_trace_draining(gpu):
+    """Tiny iteration-tag budget (forces rebases) and a trace buffer that only holds a few windows (forces the
+    drain-and-relaunch protocol): results must not change."""
+    G, x0, th0, c = gpu.gmrf_config(16)
+    ref = O.spdmp(G, G, 0.0, x0, th0, 6.0, c)
+    prob = gpu.Problem(gpu.GaussianPotential(G), gpu.ZigZag(G, np.zeros(G.n)))
+    run = gpu.Run(prob, record_trace=True, trace_capacity=1)  # clamped to the minimum: d * MAXFLIP + 2 records
+    run.set(tag_limit=40)
+    run.upload(0.0, x0, th0, c, seed=(1, 2))
+    run.execute(6.0)
+    ev = run.events()
+    st = run.stats()
+    assert st["rebases"] > 0 and st["launches"] > 4
+    assert np.array_equal(ev["i"], ref.events["i"]) and np.array_equal(ev["t"].view(np.uint64), ref.events["t"].view(np.uint64))
+    acc, num = run.counts()
+    assert num == ref.num
+
+
+def test_maintest_moments_on_gpu(gpu):
+    """test/maintest.jl:37-61 statistical acceptance test run on the device path (d = 8, T = 1000)."""
+    import math
+    d, T = 8, 1000.0
+    G = gpu.random_spd(d, seed=2)
+    rng = np.random.default_rng(5)
+    x0, th0 = rng.random(d), rng.choice(np.array([-1.0, 1.0]), d)
+    c = 0.7 * G.colnorms()
+    Z = gpu.ZigZag(G.scaled(0.9), np.zeros(d))
+    Xi, _, (acc, num), _ = gpu.spdmp(gpu.GaussianPotential(G), 0.0, x0, th0, T, c, Z, seed=(11, 12))
+    ts, xs = gpu.discretize(Xi, 0.5)
+    Sigma = np.linalg.inv(G.to_scipy().toarray())
+    assert np.mean(np.abs(xs.mean(axis=0))) < 2 / math.sqrt(T)
+    assert np.mean(np.abs(np.cov(xs.T) - Sigma)) < 2.5 / math.sqrt(T)
+    ref = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, T, c, seed=(11, 12))
+    assert num == ref.num and np.array_equal(Xi.events["t"].view(np.uint64), ref.events["t"].view(np.uint64))
+
+
+def test_full_size_properties(gpu):
+    """d = 10^6 (BASELINE configs[4] on one GPU): size-independent properties -- the result does not depend on the
+    window length, the trace is time-sorted, counters agree with the trace, moment sums agree with the trace."""
+    G, x0, th0, c = gpu.gmrf_config(1000)
+    prob = gpu.Problem(gpu.GaussianPotential(G), gpu.ZigZag(G, np.zeros(G.n)))
+    T = 0.25
+    res = []
+    for frac, rec in ((0.05, True), (0.2, False)):
+        run = gpu.Run(prob, record_trace=rec)
+        run.set(target_frac=frac)
+        run.upload(0.0, x0, th0, c, seed=(3, 4))
+        run.execute(T)
+        acc, num = run.counts()
+        res.append((acc, num, run.final_state(), run.sums(), run.events() if rec else None))
+        run.close()
+    (a0, n0, f0, s0, ev), (a1, n1, f1, s1, _) = res
+    assert n0 == n1 and np.array_equal(a0, a1)
+    for u, v in zip(f0 + s0, f1 + s1):
+        assert np.array_equal(u.view(np.uint64), v.view(np.uint64))
+    assert len(ev) == a0.sum() and np.all(np.diff(ev["t"]) >= 0) and ev["t"][-1] >= T and np.all(ev["t"][:-1] < T)
+    assert np.array_equal(np.bincount(ev["i"] - 1, minlength=G.n), a0)
+    # first-moment sums recomputed from the trace (trace.jl:182-200, unscaled) for a sample of coordinates
+    xs, ts, s1chk = x0.copy(), np.zeros(G.n), np.zeros(G.n)
+    sel = ev[ev["i"] <= 2000]
+    for t2, i, xi, _ in sel:
+        s1chk[i - 1] += (xs[i - 1] + xi) * (t2 - ts[i - 1])
+        ts[i - 1], xs[i - 1] = t2, xi
+    assert np.array_equal(s1chk[:2000].view(np.uint64), s0[0][:2000].view(np.uint64))
+    assert 0.05 < a0.sum() / n0 < 0.5  # acceptance rate in the plausible range (SURVEY.md 6: ~0.18 at stationarity)

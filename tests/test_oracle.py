@@ -1,0 +1,194 @@
+"""CPU tests of the oracle: the reference's own property / statistical tests re-run against the restatement
+(test/poisson.jl, test/maintest.jl, test/priority.jl semantics), plus consistency between the oracle's modes."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+
+@pytest.fixture(scope="module")
+def L():
+    return O.lib()
+
+
+def rate_integral(a, b, c, s):
+    """int_0^s (max(a + b t, 0) + c) dt -- helper F of test/poisson.jl:9-19."""
+    if a <= 0 and a + s * b <= 0:
+        return s * c
+    if a > 0 and a + s * b < 0:
+        return s * c - a * a / (2 * b)
+    if a > 0 and a + s * b >= 0:
+        return 0.5 * s * (2 * a + s * b + 2 * c)
+    return a * a / (2 * b) + s * a + s * s * b / 2 + s * c
+
+
+def test_poisson_time_integral_identity(L):
+    """test/poisson.jl:20-33: the integrated rate up to the returned time equals -log(u) (or stays below it when the
+    answer is Inf)."""
+    rng = np.random.default_rng(1)
+    for _ in range(2000):
+        a, b = 2 * rng.random(2) - 1
+        u = rng.random()
+        s = L.zzo_poisson_time(a, b, u)
+        if math.isinf(s):
+            big = 1e6
+            assert rate_integral(a, b, 0.0, big) < -math.log(u) or (b <= 0 and a <= 0)
+        else:
+            assert rate_integral(a, b, 0.0, s) == pytest.approx(-math.log(u), rel=1e-7, abs=1e-9)
+
+
+def test_poisson_time3_integral_identity(L):
+    """test/poisson.jl:35-50 for the three-parameter form c + (a + b t)^+."""
+    rng = np.random.default_rng(2)
+    for _ in range(2000):
+        a, b = 2 * rng.random(2) - 1
+        c, u = rng.random(), rng.random()
+        s = L.zzo_poisson_time3(a, b, c, u)
+        assert math.isfinite(s)
+        assert rate_integral(a, b, c, s) == pytest.approx(-math.log(u), rel=1e-7, abs=1e-9)
+
+
+@pytest.mark.parametrize("a,b,pt", [(1.1, 0.0, None), (1.1, 0.3, None), (0.0, 0.3, None), (1.1, -0.5, None),
+                                    (-0.5, 1.0, "shift"), (-1.0, -2.0, 0.0)])
+def test_poisson_time_distribution(L, a, b, pt):
+    """test/poisson.jl:54-70: P(tau < 0.7) against the closed form, tolerance 2/sqrt(n)."""
+    n, T = 5000, 0.7
+    rng = np.random.default_rng(3)
+    Lam = lambda a, b, T: a * T + b * T * T / 2
+    P = lambda a, b, T: 1 - math.exp(-Lam(a, b, T))
+    p = np.mean([L.zzo_poisson_time(a, b, float(u)) < T for u in rng.random(n)])
+    expect = P(0, 1, T - 0.5) if pt == "shift" else (P(a, b, T) if pt is None else pt)
+    assert abs(p - expect) < 2 / math.sqrt(n)
+
+
+def test_log_is_within_one_ulp_of_libm(L):
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.random(50000), np.logspace(-16, 0, 2000), 1 - np.logspace(-16, -1, 500)])
+    mine = np.array([L.zzo_log(float(x)) for x in xs])
+    ref = np.log(xs)
+    err = np.abs(mine - ref) / np.spacing(np.abs(ref) + 1e-300)
+    assert err.max() <= 1.0
+
+
+def test_counter_uniforms_are_uniform_and_keyed(L):
+    u = np.array([L.zzo_u01(1, 2, i, k) for i in range(200) for k in range(100)])
+    assert 0 < u.min() and u.max() < 1
+    assert abs(u.mean() - 0.5) < 0.01 and abs(u.var() - 1 / 12) < 0.005
+    # different coordinates / counters / seeds give different streams; same key gives the same draw
+    assert L.zzo_u01(1, 2, 3, 4) == L.zzo_u01(1, 2, 3, 4)
+    assert len({L.zzo_u01(1, 2, 3, 4), L.zzo_u01(1, 2, 4, 3), L.zzo_u01(2, 1, 3, 4), L.zzo_u01(1, 3, 3, 4)}) == 4
+    # lag-1 correlation along a stream and across neighbouring coordinates
+    a = np.array([L.zzo_u01(7, 9, 5, k) for k in range(20000)])
+    assert abs(np.corrcoef(a[:-1], a[1:])[0, 1]) < 0.03
+    b = np.array([L.zzo_u01(7, 9, i, 11) for i in range(20000)])
+    assert abs(np.corrcoef(b[:-1], b[1:])[0, 1]) < 0.03
+
+
+def test_lazy_and_inplace_arithmetic_agree(zzb):
+    """SURVEY.md 7 hard part 4: flip-anchored positions give the same event sequence as the reference's in-place
+    moves (same coordinate order, times equal to rounding)."""
+    G, x0, th0, c = zzb.gmrf_config(24)
+    a = O.spdmp(G, G, 0.0, x0, th0, 6.0, c, mode=O.RNG_CTR | O.ARITH_INPLACE)
+    b = O.spdmp(G, G, 0.0, x0, th0, 6.0, c, mode=O.RNG_CTR | O.ARITH_LAZY)
+    assert a.num == b.num and np.array_equal(a.events["i"], b.events["i"])
+    assert np.allclose(a.events["t"], b.events["t"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(a.events["x"], b.events["x"], rtol=0, atol=1e-11)
+    assert np.allclose(a.m1, b.m1, atol=1e-11)
+    # also for the single-stream (reference draw order) RNG
+    a = O.spdmp(G, G, 0.0, x0, th0, 6.0, c, mode=O.RNG_SEQ | O.ARITH_INPLACE)
+    b = O.spdmp(G, G, 0.0, x0, th0, 6.0, c, mode=O.RNG_SEQ | O.ARITH_LAZY)
+    assert a.num == b.num and np.array_equal(a.events["i"], b.events["i"])
+
+
+def test_termination_rule(zzb):
+    """sfact.jl:199-202: exactly one event at or after T, and it is the last one; num counts every proposal."""
+    G, x0, th0, c = zzb.gmrf_config(8)
+    for mode in (0, 1, 2, 3):
+        r = O.spdmp(G, G, 0.0, x0, th0, 3.0, c, mode=mode)
+        t = r.events["t"]
+        assert np.all(np.diff(t) >= 0) and t[-1] >= 3.0 and np.all(t[:-1] < 3.0)
+        assert r.acc.sum() == len(t) and r.num >= len(t)
+    r = O.spdmp(G, G, 1.0, x0, th0, 0.5, c)  # T <= t0: loop never entered
+    assert len(r.events) == 0 and r.num == 0
+
+
+def test_bound_violation_raises_like_the_reference(zzb):
+    """sfact.jl:124: accepted with l >= lb and adapt == false -> error; with adapt the bound is multiplied."""
+    G, x0, th0, c = zzb.gmrf_config(8)
+    tiny = np.full(G.n, 1e-9)
+    Gb = G.scaled(0.5)  # bound matrix underestimates the target -> the affine bound is violated
+    with pytest.raises(O.BoundError, match="Tuning parameter `c` too small"):
+        O.spdmp(G, Gb, 0.0, x0, th0, 5.0, tiny)
+    r = O.spdmp(G, Gb, 0.0, x0, th0, 5.0, tiny, adapt=True, factor=1.8)
+    assert (r.c > tiny).any()
+    ratio = r.c / tiny
+    k = np.round(np.log(ratio) / np.log(1.8))
+    assert np.allclose(ratio, 1.8 ** k, rtol=1e-12)
+
+
+def _cov_check(ev_run, zzb, Gt, x0, th0, T, tol_mean, tol_cov, F=None):
+    tr = zzb.FactTrace(F, 0.0, x0, th0, ev_run.events)
+    ts, xs = zzb.discretize(tr, 0.5)
+    Sigma = np.linalg.inv(Gt.to_scipy().toarray())
+    assert np.mean(np.abs(xs.mean(axis=0))) < tol_mean / math.sqrt(T)
+    assert np.mean(np.abs(np.cov(xs.T) - Sigma)) < tol_cov / math.sqrt(T)
+
+
+@pytest.mark.parametrize("mode", [O.RNG_SEQ | O.ARITH_INPLACE | O.GRAPH_ALL, O.RNG_SEQ | O.ARITH_INPLACE, O.PARITY_MODE])
+def test_maintest_moments(zzb, mode):
+    """test/maintest.jl:14-61 (ZigZag via pdmp, SZigZag via spdmp): d = 8, Gamma = S S', Z = ZigZag(0.9 Gamma),
+    c = 0.7 ||Gamma[:, i]||, T = 1000; mean and covariance of the path discretised at dt = 0.5."""
+    d, T = 8, 1000.0
+    G = zzb.random_spd(d, seed=2)
+    rng = np.random.default_rng(5)
+    x0 = rng.random(d)
+    th0 = rng.choice(np.array([-1.0, 1.0]), d)
+    c = 0.7 * G.colnorms()
+    r = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, T, c, seed=(11, 12), mode=mode)
+    _cov_check(r, zzb, G, x0, th0, T, 2.0, 2.5)
+
+
+def test_trace_mean_matches_discretisation(zzb):
+    """Statistics.mean(::Trace) (trace.jl:182-200) as restated in the oracle vs the host mirror and a fine discretisation."""
+    d, T = 8, 400.0
+    G = zzb.random_spd(d, seed=2)
+    rng = np.random.default_rng(6)
+    x0, th0 = rng.random(d), rng.choice(np.array([-1.0, 1.0]), d)
+    r = O.spdmp(G, G, 0.0, x0, th0, T, 0.7 * G.colnorms())
+    tr = zzb.FactTrace(None, 0.0, x0, th0, r.events)
+    assert np.allclose(zzb.mean(tr), r.m1, rtol=1e-13, atol=1e-15)
+    ts, xs = zzb.discretize(tr, 0.01)
+    assert np.allclose(xs.mean(axis=0), r.m1, atol=0.02)
+    assert np.allclose((xs * xs).mean(axis=0), r.m2, atol=0.03)
+
+
+def test_subtrace(zzb):
+    """test/maintest.jl:53-58."""
+    d = 8
+    G = zzb.random_spd(d, seed=2)
+    rng = np.random.default_rng(7)
+    x0, th0 = rng.random(d), rng.choice(np.array([-1.0, -0.5, 0.5, 1.0]), d)
+    r = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, 100.0, 0.7 * G.colnorms())
+    tr = zzb.FactTrace(None, 0.0, x0, th0, r.events)
+    J = np.arange(1, d + 1, 2)
+    ts, xs = zzb.discretize(tr, 0.5)
+    ts2, xs2 = zzb.discretize(zzb.subtrace(tr, J), 0.5)
+    assert np.allclose(ts2, ts[: len(ts2)])
+    assert np.allclose(xs2, xs[: len(ts2)][:, J - 1])
+
+
+def test_golden_fixture(zzb):
+    """Regression fixture written by tests/golden/make_golden.py from the oracle itself (NOT a reference vector:
+    the reference has none for this path, see the oracle header)."""
+    import json, os
+    path = os.path.join(os.path.dirname(__file__), "golden", "gmrf16_T3.json")
+    g = json.load(open(path))
+    G, x0, th0, c = zzb.gmrf_config(g["n"])
+    r = O.spdmp(G, G, 0.0, x0, th0, g["T"], c, seed=tuple(g["seed"]))
+    assert r.num == g["num"] and len(r.events) == g["n_events"]
+    assert r.events["i"][:32].tolist() == g["first_i"]
+    assert [float(t).hex() for t in r.events["t"][:8]] == g["first_t_hex"]
+    assert float(r.events["t"][-1]).hex() == g["last_t_hex"]
+    assert int(np.bitwise_xor.reduce(r.events["t"].view(np.uint64))) == g["xor_t"]

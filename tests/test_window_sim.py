@@ -1,0 +1,67 @@
+"""The windowed relaxation schedule (host emulation built on the kernel's own per-coordinate code, zz_core.h /
+zz_fast.h / zz_ctl.h) against the sequential oracle: bit-exact for every graph kind the kernels specialise on."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+FORCE_CSR = 0x80000000  # top bit of tag_limit: disable the lattice fast path in the emulation
+
+
+@pytest.mark.parametrize("n,T", [(3, 10.0), (9, 5.0), (32, 3.0)])
+@pytest.mark.parametrize("tag_limit", [0x0F000000, 0x0F000000 | FORCE_CSR, 40])
+def test_grid(zzb, n, T, tag_limit):
+    G, x0, th0, c = zzb.gmrf_config(n)
+    ref = O.spdmp(G, G, 0.0, x0, th0, T, c)
+    got = O.window_sim(G, G, 0.0, x0, th0, T, c, tag_limit=tag_limit)
+    O.assert_same_run(ref, got)
+    assert np.allclose(got.s1, ref.s1, rtol=0, atol=0) and got.stats["windows"] > 1
+
+
+@pytest.mark.parametrize("delta0,frac", [(1e-4, 0.02), (0.01, 0.4), (2.0, 5.0)])
+def test_window_length_is_irrelevant(zzb, delta0, frac):
+    G, x0, th0, c = zzb.gmrf_config(20)
+    ref = O.spdmp(G, G, 0.0, x0, th0, 4.0, c)
+    got = O.window_sim(G, G, 0.0, x0, th0, 4.0, c, delta0=delta0, target_frac=frac)
+    O.assert_same_run(ref, got)
+
+
+def test_rectangular_grid_and_tight_bound(zzb):
+    G = zzb.grid_precision(5, 9)
+    rng = np.random.default_rng(3)
+    x0, th0 = rng.standard_normal(45), rng.choice(np.array([-1.0, 1.0]), 45)
+    for c in (G.colnorms(), np.full(45, np.sqrt(np.finfo(float).eps))):
+        ref = O.spdmp(G, G, 0.0, x0, th0, 8.0, c)
+        O.assert_same_run(ref, O.window_sim(G, G, 0.0, x0, th0, 8.0, c))
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_random_sparse_with_mu_h_adapt(zzb, seed):
+    d = 40
+    Gt = zzb.random_sparse_spd(d, deg=2 + seed % 3, seed=seed)
+    Gb = Gt.scaled(0.9)
+    rng = np.random.default_rng(seed)
+    x0, th0 = rng.standard_normal(d), rng.choice(np.array([-1.0, -0.5, 0.5, 1.0]), d)
+    mu, h = 0.1 * rng.standard_normal(d), 0.3 * rng.standard_normal(d)
+    c = 0.2 * Gt.colnorms()
+    ref = O.spdmp(Gt, Gb, 0.0, x0, th0, 20.0, c, h=h, mu=mu, adapt=True)
+    got = O.window_sim(Gt, Gb, 0.0, x0, th0, 20.0, c, h=h, mu=mu, adapt=True)
+    O.assert_same_run(ref, got)
+
+
+def test_dense_columns_take_the_slow_path(zzb):
+    G = zzb.random_spd(12, density=0.5)
+    assert np.diff(G.colptr).max() > 8
+    rng = np.random.default_rng(0)
+    x0, th0 = rng.random(12), rng.choice(np.array([-1.0, 1.0]), 12)
+    ref = O.spdmp(G, G, 0.0, x0, th0, 50.0, 2.0 * G.colnorms(), adapt=True)
+    O.assert_same_run(ref, O.window_sim(G, G, 0.0, x0, th0, 50.0, 2.0 * G.colnorms(), adapt=True))
+
+
+def test_bound_violation_and_t0(zzb):
+    G, x0, th0, c = zzb.gmrf_config(8)
+    with pytest.raises(O.BoundError):
+        O.window_sim(G, G.scaled(0.5), 0.0, x0, th0, 5.0, np.full(G.n, 1e-9))
+    ref = O.spdmp(G, G, 0.0, x0, th0, 0.0, c)     # T <= t0
+    got = O.window_sim(G, G, 0.0, x0, th0, 0.0, c)
+    assert len(got.events) == 0 and got.num == ref.num == 0

@@ -10,7 +10,7 @@ import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG_DIR, "libzzb200.so")
-CUBIN_PATH = os.path.join(PKG_DIR, "zzb200_kernels.cubin")
+CUBIN_PATH = os.environ.get("ZZB200_CUBIN") or os.path.join(PKG_DIR, "zzb200_kernels.cubin")
 
 ZZB_OK, ZZB_E_ARG, ZZB_E_CUDA, ZZB_E_BOUND, ZZB_E_GRAPH, ZZB_E_NOMEM, ZZB_E_TRACE, ZZB_E_INTERNAL = 0, 1, 2, 3, 4, 5, 6, 9
 ZZB_FLAG_NO_TRACE = 1
@@ -19,8 +19,8 @@ EVENT_DTYPE = np.dtype([("t", "<f8"), ("i", "<i8"), ("x", "<f8"), ("theta", "<f8
 
 # every symbol include/zzb200.h declares
 SYMBOLS = [
-    "zzb_init", "zzb_shutdown", "zzb_last_error", "zzb_device_info", "zzb_problem_create_gaussian", "zzb_problem_free",
-    "zzb_spdmp_run", "zzb_run_create", "zzb_run_upload", "zzb_run_execute", "zzb_run_set", "zzb_run_stats",
+    "zzb_init", "zzb_shutdown", "zzb_last_error", "zzb_device_info", "zzb_event_record", "zzb_event_elapsed_ms", "zzb_problem_create_gaussian", "zzb_problem_free",
+    "zzb_spdmp_run", "zzb_run_create", "zzb_run_upload", "zzb_run_reset", "zzb_run_execute", "zzb_run_set", "zzb_run_stats",
     "zzb_run_counts", "zzb_run_final_state", "zzb_trace_len", "zzb_trace_copy", "zzb_trace_moments", "zzb_trace_sums",
     "zzb_run_error_info", "zzb_run_free",
 ]
@@ -52,11 +52,14 @@ def lib():
             "zzb_shutdown": [],
             "zzb_last_error": [C.c_char_p, i64],
             "zzb_device_info": [vp, vp, C.c_char_p, i64],
+            "zzb_event_record": [i32],
+            "zzb_event_elapsed_ms": [vp],
             "zzb_problem_create_gaussian": [vp, i64] + [vp] * 8,
             "zzb_problem_free": [vp],
             "zzb_spdmp_run": [vp, f64, vp, vp, f64, vp, vp, i32, f64, u32, vp],
             "zzb_run_create": [vp, u32, i64, vp],
             "zzb_run_upload": [vp, f64, vp, vp, vp, vp, i32, f64],
+            "zzb_run_reset": [vp],
             "zzb_run_execute": [vp, f64, vp],
             "zzb_run_set": [vp, C.c_char_p, f64],
             "zzb_run_stats": [vp, vp, i32],
@@ -126,3 +129,13 @@ def ptr(a):
 
 def f8(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def event_record(which: int):
+    check(lib().zzb_event_record(int(which)))
+
+
+def event_elapsed_ms() -> float:
+    ms = C.c_float()
+    check(lib().zzb_event_elapsed_ms(C.byref(ms)))
+    return ms.value

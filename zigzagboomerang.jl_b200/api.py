@@ -206,6 +206,11 @@ class Run:
         self.t0 = float(t0)
         return self
 
+    def reset(self):
+        """Re-initialise the device state from the inputs already resident in HBM (no host traffic)."""
+        check(_capi.lib().zzb_run_reset(self._h))
+        return self
+
     def execute(self, T) -> float:
         """Run to T; returns the CUDA-event time of the event-loop kernel(s) in milliseconds."""
         ms = C.c_float()
@@ -249,9 +254,10 @@ class Run:
         return s1, s2
 
     def stats(self):
-        out = np.zeros(8, np.int64)
-        check(_capi.lib().zzb_run_stats(self._h, ptr(out), 8))
-        keys = ("windows", "retries", "passes", "node_evals", "rebases", "launches", "grid", "block")
+        out = np.zeros(24, np.int64)
+        check(_capi.lib().zzb_run_stats(self._h, ptr(out), 24))
+        keys = ("windows", "retries", "passes", "node_evals", "rebases", "launches", "grid", "block",
+                "ns_scan", "ns_relax", "ns_tail", "ns_commit", "ns_barrier", "ns_phaseb", "n_barriers", "n_tail_passes") + tuple("dbg%d" % q for q in range(8))
         return dict(zip(keys, (int(v) for v in out)))
 
     def close(self):

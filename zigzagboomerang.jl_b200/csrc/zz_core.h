@@ -60,6 +60,10 @@ struct ZzGraph {
     const double* gmu;     // idot(Z.Gamma, j, Z.mu)   (fact_samplers.jl:51)
     const double* h;       // linear term of the target, may be null
     int32_t same;          // target and bound matrices are the same object and h == 0, mu == 0
+    // 5-point lattice fast path (0.01 I + gridlaplacian(m, n), scripts/gridlaplace.jl): neighbours and weights
+    // follow from index arithmetic, no index/weight loads.  grid_m == 0 -> general CSR lists above.
+    int32_t grid_m, grid_n;
+    double grid_diag[5];   // diagonal entry by node degree (2, 3, 4), exactly as stored in the matrix
 };
 
 struct ZzView {
@@ -215,13 +219,14 @@ ZZ_HD void zz_next_trigger(const ZzGraph& g, const ZzView& v, int32_t j, double 
 // The timeline of coordinate j inside the window ending at H (exclusive, or inclusive when incl != 0),
 // starting from its frontier state.  See the file header; per item this is exactly the arithmetic of
 // spdmp_inner! (sfact.jl:118-139) and ab (fact_samplers.jl:50-54) for coordinate j.
-ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
+ZZ_HD void zz_process_node_slow(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                            uint32_t cur, bool first_iter, ZzNodeOut& o)
 {
     double th, tf, xf; uint32_t hh0, hh1;
     zz_ld_kin(v.kin + j, th, tf, xf, hh0, hh1);
     const ZzPriv pr = zz_ld_priv(v.priv + j);
     double a = pr.a, b = pr.b, told = pr.told, c = pr.c;
+    double c100 = c / 100;
     double tau = zz_ld(v.tau + j);
     uint32_t k = zz_ld32(v.kctr + j);
     const double gmu = g.gmu[j];
@@ -246,7 +251,7 @@ ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double 
             nprop++;
             if (u * lb < l) {                                 // sfact.jl:121
                 if (l >= lb) {                                // sfact.jl:123-128
-                    if (v.adapt) c *= v.factor;
+                    if (v.adapt) { c *= v.factor; c100 = c / 100; }
                     else if (!(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
                 }
                 if (nflip == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
@@ -269,7 +274,7 @@ ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double 
             gth = gp;
         }
         a = c + (gx - gmu) * th;                              // fact_samplers.jl:51
-        b = c / 100 + th * gth;                               // fact_samplers.jl:52
+        b = c100 + th * gth;                                  // fact_samplers.jl:52 (c100 = c / 100)
         told = s;
         tau = s + zz_poisson_time(a, b, zz_u01(v.seed0, v.seed1, (uint64_t)j, k++));  // sfact.jl:134,139
     }
@@ -277,6 +282,8 @@ ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double 
     o.k = k; o.nprop = nprop; o.nflip = nflip; o.flags = flags;
     o.hdr0 = hh0; o.hdr1 = hh1;
 }
+
+#include "zz_fast.h"
 
 // Initial bound and first proposal time of coordinate j (sfact.jl:184-187; note: no "+ t0").
 ZZ_HD void zz_init_node(const ZzGraph& g, const ZzView& v, int32_t j, double t0)

@@ -30,10 +30,15 @@ struct ZzDevCtl {
     unsigned int cur;                // last iteration tag used
     unsigned int itg;                // index of the work list consumed last
     unsigned int wattempt;           // window attempts so far
+    unsigned int tail_li, tail_cur;  // pass counters published by CTA 0 after a run of block-local tail passes
     // persisted across launches
     ZzCtl ctl;
     // statistics
     unsigned long long windows, retries, iters, node_evals, rebases;
+    // wall time (ns, %globaltimer) CTA 0 spent in: 0 scan pass work, 1 relaxation pass work, 2 tail passes, 3 commit work,
+    // 4 waiting at grid barriers, 5 phase-B scans, 6 number of grid barriers, 7 number of tail passes
+    unsigned long long tprof[8];
+    unsigned long long dbg[8];       // development counters (ZZ_PROF_NODE builds)
 };
 
 struct ZzParams {

@@ -1,0 +1,264 @@
+// zz_fast.h -- gather-first evaluation of one coordinate's timeline (included by zz_core.h).
+//
+// zz_process_node_slow walks the neighbour lists in global memory once per timeline item: a chain of ~100
+// dependent L2 round trips (tens of microseconds per coordinate on a B200).  Here the whole neighbourhood
+// (kinematic records + recorded flips) is fetched FIRST with independent loads -- four round trips in total --
+// and the timeline then runs out of registers: neighbour flips are merged into one time-ordered pool and applied
+// incrementally, so every evaluation sees exactly the neighbour state the slow path would compute, bit for bit.
+#ifndef ZZ_FAST_H
+#define ZZ_FAST_H
+
+#if defined(ZZ_PROF_NODE) && defined(__CUDA_ARCH__)
+__device__ unsigned long long* zz_dbg_ptr;   // set by the kernel; segment k accumulates cycles since segment k-1
+__device__ long long zz_dbg_last;
+#define ZZ_SEG(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long _c = clock64(); if (k) zz_dbg_ptr[k] += (unsigned long long)(_c - zz_dbg_last); zz_dbg_last = _c; } } while (0)
+#define ZZ_SEGCOUNT() do { if (blockIdx.x == 0 && threadIdx.x == 0) zz_dbg_ptr[6] += 1; } while (0)
+#else
+#define ZZ_SEG(k) do { } while (0)
+#define ZZ_SEGCOUNT() do { } while (0)
+#endif
+
+#define ZZ_NB 8     // neighbourhood capacity of the gathered path (entries of column j, j included)
+#define ZZ_POOL 16  // neighbour flips merged per coordinate and window
+
+template <int NB>
+struct ZzHood {
+    int n;        // entries in storage order
+    int self;     // position of j itself
+    double wb[NB], wt[NB];
+    uint32_t fl[NB];
+    double th[NB], tf[NB], xf[NB];
+};
+
+struct ZzPool {
+    int n;
+    double t[ZZ_POOL];
+    int m[ZZ_POOL];  // neighbourhood position of the flipping coordinate
+};
+
+// merge the recorded flips of neighbour position m into the pool, ordered by (time, position)
+ZZ_HD void zz_pool_add(ZzPool& pool, double fs, int m, uint32_t& flags)
+{
+    int p = pool.n;
+    if (p == ZZ_POOL) { flags |= ZZ_F_OVERFLOW; return; }
+    while (p > 0 && (pool.t[p - 1] > fs || (pool.t[p - 1] == fs && pool.m[p - 1] > m))) {
+        pool.t[p] = pool.t[p - 1]; pool.m[p] = pool.m[p - 1]; --p;
+    }
+    pool.t[p] = fs; pool.m[p] = m; pool.n++;
+}
+
+template <int NB>
+ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint32_t (&h0)[NB], const uint32_t (&h1)[NB],
+                           int n, int self, uint32_t w0, uint32_t cur, ZzPool& pool, uint32_t& flags)
+{
+    pool.n = 0;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        if (m < n && m != self) {
+            int slot;
+            const uint32_t cnt = zz_pick_slot(h0[m], h1[m], w0, cur, slot);
+            if (cnt) {
+                const double* fl = v.flips + ((size_t)idx[m] * 2 + slot) * ZZ_MAXFLIP;
+                for (uint32_t q = 0; q < cnt; ++q) zz_pool_add(pool, zz_ld(fl + q), m, flags);
+            }
+        }
+    }
+}
+
+// General sparse column (<= NB entries).  Returns false when the column is longer (caller uses the slow path).
+template <int NB>
+ZZ_HD bool zz_gather_csr(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t w0, uint32_t cur, bool first_iter,
+                         ZzHood<NB>& hd, ZzPool& pool, uint32_t& flags)
+{
+    const int32_t e0 = g.nptr[j];
+    const int n = g.nptr[j + 1] - e0;
+    if (n > NB) return false;
+    hd.n = n; hd.self = 0;
+    int32_t idx[NB]; uint32_t h0[NB], h1[NB];
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        if (m < n) {
+            idx[m] = g.nidx[e0 + m]; hd.fl[m] = g.nfl[e0 + m]; hd.wb[m] = g.nwb[e0 + m];
+            hd.wt[m] = g.same ? 0.0 : g.nwt[e0 + m];
+        } else { idx[m] = -1; hd.fl[m] = 0; hd.wb[m] = 0.0; hd.wt[m] = 0.0; }
+    }
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        h0[m] = 0; h1[m] = 0; hd.th[m] = 0.0; hd.tf[m] = 0.0; hd.xf[m] = 0.0;
+        if (m < n) {
+            if (idx[m] == j) hd.self = m;
+            else zz_ld_kin(v.kin + idx[m], hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
+        }
+    }
+    pool.n = 0;
+    if (!first_iter) zz_gather_flips<NB>(v, idx, h0, h1, n, hd.self, w0, cur, pool, flags);
+    return true;
+}
+
+// 5-point lattice: column j = {j-M, j-1, j, j+1, j+M} (those that exist), weights -1 and shift + degree.
+ZZ_HD void zz_gather_grid(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t w0, uint32_t cur, bool first_iter,
+                          ZzHood<5>& hd, ZzPool& pool, uint32_t& flags)
+{
+    const int32_t M = g.grid_m, N = g.grid_n;
+    const int32_t col = j / M, row = j - col * M;
+    int32_t idx[5]; uint32_t h0[5], h1[5];
+    int n = 0;
+    if (col > 0) idx[n++] = j - M;
+    if (row > 0) idx[n++] = j - 1;
+    const int self = n;
+    idx[n++] = j;
+    if (row < M - 1) idx[n++] = j + 1;
+    if (col < N - 1) idx[n++] = j + M;
+    hd.n = n; hd.self = self;
+    const double diag = g.grid_diag[n - 1];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        if (m >= n) idx[m] = -1;
+        hd.wb[m] = (m == self) ? diag : -1.0; hd.wt[m] = 0.0;
+        hd.fl[m] = (m < n) ? ((m == self) ? (ZZ_NB_TGT | ZZ_NB_BND) : (ZZ_NB_TGT | ZZ_NB_BND | ZZ_NB_TRIG)) : 0u;
+        h0[m] = 0; h1[m] = 0; hd.th[m] = 0.0; hd.tf[m] = 0.0; hd.xf[m] = 0.0;
+    }
+#pragma unroll
+    for (int m = 0; m < 5; ++m)
+        if (m < n && m != self) zz_ld_kin(v.kin + idx[m], hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
+    pool.n = 0;
+    ZZ_SEG(1);
+    if (!first_iter) zz_gather_flips<5>(v, idx, h0, h1, n, self, w0, cur, pool, flags);
+}
+
+// idot's over the gathered column at time s, storage order (common.jl:16-24)
+template <int NB>
+ZZ_HD void zz_eval_hood(const ZzHood<NB>& hd, bool same, double s, double xown, double thown, double& gt,
+                        double& gx, double& gp, double& gm)
+{
+    double at = 0.0, ax = 0.0, ap = 0.0, am = 0.0;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        if (m < hd.n) {
+            const bool self = (m == hd.self);
+            const double th = self ? thown : hd.th[m];
+            const double x = self ? xown : (hd.xf[m] + hd.th[m] * (s - hd.tf[m]));
+            if (hd.fl[m] & ZZ_NB_BND) {
+                const double wb = hd.wb[m];
+                ax += wb * x; ap += wb * th; am += wb * (self ? -th : th);
+            }
+            if (!same && (hd.fl[m] & ZZ_NB_TGT)) at += hd.wt[m] * x;
+        }
+    }
+    gt = same ? ax : at; gx = ax; gp = ap; gm = am;
+}
+
+// Timeline of coordinate j from gathered data; identical arithmetic to zz_process_node_slow.
+template <int NB>
+ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzGraph& g, const ZzView& v, int32_t j,
+                       double H, int incl, uint32_t flags0, ZzNodeOut& o)
+{
+    double th, tf, xf; uint32_t hh0, hh1;
+    zz_ld_kin(v.kin + j, th, tf, xf, hh0, hh1);
+    const ZzPriv pr = zz_ld_priv(v.priv + j);
+    double a = pr.a, b = pr.b, told = pr.told, c = pr.c;
+    double c100 = c / 100;
+    double tau = zz_ld(v.tau + j);
+    uint32_t k = zz_ld32(v.kctr + j);
+    const double gmu = g.grid_m ? 0.0 : g.gmu[j];
+    const double hj = (!g.same && g.h) ? g.h[j] : 0.0;
+    const bool has_h = (!g.same && g.h);
+    uint32_t nprop = 0, nflip = 0, flags = flags0;
+    o.viol_t = 0.0; o.viol_l = 0.0; o.viol_lb = 0.0;
+    int p = 0;
+    ZZ_SEG(3);
+
+    for (int item = 0;; ++item) {
+        ZZ_SEGCOUNT();
+        const double nt = p < pool.n ? pool.t[p] : ZZ_INF;
+        const int nm = p < pool.n ? pool.m[p] : 0x7fffffff;
+        const bool own = (tau < nt) || (tau == nt && hd.self < nm);
+        const double s = own ? tau : nt;
+        if (!(s < H || (incl && s == H))) break;
+        if (item >= ZZ_MAXITEMS) { flags |= ZZ_F_OVERFLOW; break; }
+        double gt, gx, gp, gm, gth;
+        if (own) {
+            const double xs = xf + th * (s - tf);
+            zz_eval_hood<NB>(hd, g.same != 0, s, xs, th, gt, gx, gp, gm);
+            if (has_h) gt = gt - hj;
+            const double l = zz_pos(gt * th);                 // fact_samplers.jl:28-30
+            const double lb = zz_pos(a + b * (s - told));     // sfact.jl:70
+            const double u = zz_u01(v.seed0, v.seed1, (uint64_t)j, k++);
+            nprop++;
+            if (u * lb < l) {                                 // sfact.jl:121
+                if (l >= lb) {                                // sfact.jl:123-128
+                    if (v.adapt) { c *= v.factor; c100 = c / 100; }
+                    else if (!(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
+                }
+                if (nflip == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#pragma unroll
+                for (int m = 0; m < ZZ_MAXFLIP; ++m)
+                    if (m == (int)nflip) o.fl[m] = s;
+                nflip++;
+                xf = xs; tf = s; th = -th;                    // dynamics.jl:46-49
+                gth = gm;
+            } else {
+                gth = gp;
+            }
+        } else {
+            // neighbour at position nm flips at s: advance its anchor, then (if it triggers us) reschedule
+            bool trig = false;
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+                if (m == nm) {
+                    hd.xf[m] = hd.xf[m] + hd.th[m] * (s - hd.tf[m]);
+                    hd.tf[m] = s;
+                    hd.th[m] = -hd.th[m];
+                    trig = (hd.fl[m] & ZZ_NB_TRIG) != 0;
+                }
+            }
+            ++p;
+            if (!trig) continue;
+            const double xs = xf + th * (s - tf);
+            zz_eval_hood<NB>(hd, g.same != 0, s, xs, th, gt, gx, gp, gm);
+            gth = gp;
+        }
+        a = c + (gx - gmu) * th;                              // fact_samplers.jl:51
+        b = c100 + th * gth;                                  // fact_samplers.jl:52 (c100 = c / 100)
+        told = s;
+        tau = s + zz_poisson_time(a, b, zz_u01(v.seed0, v.seed1, (uint64_t)j, k++));  // sfact.jl:134,139
+    }
+    o.a = a; o.b = b; o.told = told; o.tau = tau; o.c = c;
+    o.k = k; o.nprop = nprop; o.nflip = nflip; o.flags = flags;
+    o.hdr0 = hh0; o.hdr1 = hh1;
+}
+
+// Entry points.  KIND 0: 5-point lattice (index arithmetic); KIND 1: general sparse columns.
+#define ZZ_KIND_GRID 0
+#define ZZ_KIND_CSR 1
+template <int KIND>
+ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
+                             uint32_t cur, bool first_iter, ZzNodeOut& o)
+{
+    ZzPool pool; uint32_t flags = 0;
+    if (KIND == ZZ_KIND_GRID) {
+        ZzHood<5> hd;
+        ZZ_SEG(0);
+        zz_gather_grid(g, v, j, w0, cur, first_iter, hd, pool, flags);
+        ZZ_SEG(2);
+        zz_timeline<5>(hd, pool, g, v, j, H, incl, flags, o);
+        ZZ_SEG(5);
+        return;
+    }
+    ZzHood<ZZ_NB> hd;
+    if (zz_gather_csr<ZZ_NB>(g, v, j, w0, cur, first_iter, hd, pool, flags)) {
+        zz_timeline<ZZ_NB>(hd, pool, g, v, j, H, incl, flags, o);
+        return;
+    }
+    zz_process_node_slow(g, v, j, H, incl, w0, cur, first_iter, o);
+}
+
+// used by the host-side schedule emulation
+ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
+                           uint32_t cur, bool first_iter, ZzNodeOut& o)
+{
+    if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID>(g, v, j, H, incl, w0, cur, first_iter, o);
+    else zz_process_node_k<ZZ_KIND_CSR>(g, v, j, H, incl, w0, cur, first_iter, o);
+}
+
+#endif  // ZZ_FAST_H

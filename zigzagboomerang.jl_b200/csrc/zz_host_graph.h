@@ -28,7 +28,43 @@ struct ZzHostGraph {
     int32_t maxdeg = 0;
     // 5-point lattice detection (m x n, column-major numbering): lets the kernels use index arithmetic
     int32_t grid_m = 0, grid_n = 0;
+    double grid_diag[5] = { 0, 0, 0, 0, 0 };
 };
+
+// Is the (single) matrix a 5-point lattice operator  shift*I + gridlaplacian(m, n)  (scripts/gridlaplace.jl:4-21)
+// with column-major node numbering?  Then the kernels can replace every index/weight load by arithmetic.
+static inline void zz_detect_grid(ZzHostGraph& G, int64_t d, const int64_t* cp, const int64_t* rv, const double* nz)
+{
+    G.grid_m = G.grid_n = 0;
+    if (!G.same || d < 4) return;
+    // column 1 of an m x n lattice (m, n >= 2) holds rows {1, 2, 1+m}
+    if (cp[1] - cp[0] != 3) return;
+    const int64_t m = rv[2] - 1;
+    if (m < 2 || d % m != 0 || d / m < 2) return;
+    const int64_t n = d / m;
+    double diag[5] = { 0, 0, 0, 0, 0 }; bool have[5] = { false, false, false, false, false };
+    for (int64_t j = 0; j < d; ++j) {
+        const int64_t col = j / m, row = j % m;
+        int64_t exp_idx[5]; int cnt = 0, self = 0;
+        if (col > 0) exp_idx[cnt++] = j - m;
+        if (row > 0) exp_idx[cnt++] = j - 1;
+        self = cnt; exp_idx[cnt++] = j;
+        if (row < m - 1) exp_idx[cnt++] = j + 1;
+        if (col < n - 1) exp_idx[cnt++] = j + m;
+        if (cp[j + 1] - cp[j] != cnt) return;
+        const int64_t p0 = cp[j] - 1;
+        for (int q = 0; q < cnt; ++q) {
+            if (rv[p0 + q] - 1 != exp_idx[q]) return;
+            if (q == self) {
+                const int deg = cnt - 1;
+                if (!have[deg]) { have[deg] = true; diag[deg] = nz[p0 + q]; }
+                else if (zz_d2u(diag[deg]) != zz_d2u(nz[p0 + q])) return;
+            } else if (nz[p0 + q] != -1.0) return;
+        }
+    }
+    G.grid_m = (int32_t)m; G.grid_n = (int32_t)n;
+    for (int q = 0; q < 5; ++q) G.grid_diag[q] = diag[q];
+}
 
 // Returns "" on success, else an error message (ZZB_E_GRAPH / ZZB_E_ARG material).
 static inline std::string zz_build_graph(ZzHostGraph& G, int64_t d, const int64_t* tcp, const int64_t* trv,
@@ -66,6 +102,7 @@ static inline std::string zz_build_graph(ZzHostGraph& G, int64_t d, const int64_
     for (int64_t j = 0; j < d && mu0; ++j) mu0 = (zz_d2u(mu[j]) == 0);
     G.same = (same && !has_h && mu0) ? 1 : 0;
     G.has_h = has_h;
+    zz_detect_grid(G, d, bcp, brv, bnz);
     if (has_h) G.h.assign(hvec, hvec + d);
 
     // transpose pattern of the bound matrix: trig[j] = { k : j in rows(col k) }

@@ -22,7 +22,11 @@ namespace cg = cooperative_groups;
 
 #define ZZ_BLOCK 256
 #define ZZ_SCAN_U 8
+#ifndef ZZ_MINB
+#define ZZ_MINB 1
+#endif
 #define ZZ_OVF_BIT 0x80000000u
+#define ZZ_TAIL 256u   // work lists this short are relaxed by one CTA with block-level barriers
 
 __device__ __forceinline__ unsigned long long zz_ld_acq(const unsigned long long* p)
 {
@@ -31,16 +35,26 @@ __device__ __forceinline__ unsigned long long zz_ld_acq(const unsigned long long
     return v;
 }
 
+__device__ __forceinline__ unsigned long long zz_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 // All CTAs are co-resident (cooperative launch): arrive on a monotone counter, spin until everyone has.
-__device__ __forceinline__ void zz_grid_barrier(ZzDevCtl* C, unsigned long long& epoch)
+// `prof` (CTA 0, thread 0 only) accumulates the time spent waiting and the number of barriers.
+__device__ __forceinline__ void zz_grid_barrier(ZzDevCtl* C, unsigned long long& epoch, unsigned long long* prof)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
+        const unsigned long long t0 = prof ? zz_now() : 0ULL;
         epoch += gridDim.x;
         __threadfence();
         atomicAdd(&C->bar, 1ULL);
         while (zz_ld_acq(&C->bar) < epoch) { }
         __threadfence();
+        if (prof) { prof[4] += zz_now() - t0; prof[6] += 1; }
     }
     __syncthreads();
 }
@@ -53,6 +67,32 @@ __device__ __forceinline__ void zz_append(int32_t* list, unsigned int* cnt, int3
     if (cgp.thread_rank() == 0) base = atomicAdd(cnt, cgp.size());
     base = cgp.shfl(base, 0);
     list[(base & ~ZZ_OVF_BIT) + cgp.thread_rank()] = val;
+}
+
+// Up to four candidates per lane: those whose stamp was older than `tagn` go to the next work list, those older
+// than `w0` (first touch in this window) also to the touched list.  One atomicAdd per list for the active lanes.
+__device__ __forceinline__ void zz_append4(int32_t* wl, unsigned int* wl_cnt, int32_t* tl, unsigned int* tl_cnt,
+                                           const int32_t (&kk)[4], const uint32_t (&old)[4], uint32_t tagn, uint32_t w0)
+{
+    unsigned int na = 0, nt = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { na += (old[q] < tagn) ? 1u : 0u; nt += (old[q] < w0) ? 1u : 0u; }
+    cg::coalesced_group cgp = cg::coalesced_threads();
+    const unsigned int pa = cg::exclusive_scan(cgp, na, cg::plus<unsigned int>());
+    const unsigned int pt = cg::exclusive_scan(cgp, nt, cg::plus<unsigned int>());
+    unsigned int ba = 0, bt = 0;
+    const unsigned int last = cgp.size() - 1;
+    if (cgp.thread_rank() == last) {
+        if (pa + na) ba = atomicAdd(wl_cnt, pa + na);
+        if (pt + nt) bt = atomicAdd(tl_cnt, pt + nt);
+    }
+    ba = (cgp.shfl(ba, last) & ~ZZ_OVF_BIT) + pa;
+    bt = cgp.shfl(bt, last) + pt;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (old[q] < tagn) wl[ba++] = kk[q];
+        if (old[q] < w0) tl[bt++] = kk[q];
+    }
 }
 
 __device__ __forceinline__ void zz_store_spec(ZzSpec* p, const ZzNodeOut& o)
@@ -80,6 +120,7 @@ __device__ __forceinline__ ZzSpecR zz_load_spec(const ZzSpec* p)
 
 // Publish the result of one timeline evaluation: if the list of accepted flips differs from the one the
 // readers of this pass see, write it into the other slot and queue every coordinate that reads j.
+template <int KIND>
 __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const ZzNodeOut& o, uint32_t w0,
                                            uint32_t cur, int nxt, int ws)
 {
@@ -101,13 +142,29 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
             if (m < (int)o.nflip) fl[m] = o.fl[m];
         reinterpret_cast<uint32_t*>(P.v.kin + j)[6 + wsl] = (cur << 4) | o.nflip;
         const uint32_t tagn = cur + 1;
-        const int32_t q1 = P.dptr[j + 1];
-        for (int32_t q = P.dptr[j]; q < q1; ++q) {
-            const int32_t k = P.didx[q];
-            const uint32_t old = atomicMax(P.dstamp + k, tagn);
-            if (old < tagn) {
-                zz_append(P.wl[nxt], &C->wl_cnt[nxt], k);
-                if (old < w0) zz_append(P.touched[0], &C->touched_cnt[ws], k);
+        // queue the readers of j: all stamp updates are issued back to back (independent atomics in flight), then
+        // the appends of the whole warp share one atomicAdd per list (zz_append2)
+        if (KIND == ZZ_KIND_GRID) {
+            const int32_t M = P.g.grid_m, N = P.g.grid_n;
+            const int32_t col = j / M, row = j - col * M;
+            int32_t kk[4]; uint32_t old[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool ok = (q == 0) ? (col > 0) : (q == 1) ? (row > 0) : (q == 2) ? (row < M - 1) : (col < N - 1);
+                kk[q] = ok ? j + ((q == 0) ? -M : (q == 1) ? -1 : (q == 2) ? 1 : M) : -1;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) old[q] = (kk[q] >= 0) ? atomicMax(P.dstamp + kk[q], tagn) : 0xffffffffu;
+            zz_append4(P.wl[nxt], &C->wl_cnt[nxt], P.touched[0], &C->touched_cnt[ws], kk, old, tagn, w0);
+        } else {
+            const int32_t q1 = P.dptr[j + 1];
+            for (int32_t q0 = P.dptr[j]; q0 < q1; q0 += 4) {
+                int32_t kk[4]; uint32_t old[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) kk[q] = (q0 + q < q1) ? P.didx[q0 + q] : -1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) old[q] = (kk[q] >= 0) ? atomicMax(P.dstamp + kk[q], tagn) : 0xffffffffu;
+                zz_append4(P.wl[nxt], &C->wl_cnt[nxt], P.touched[0], &C->touched_cnt[ws], kk, old, tagn, w0);
             }
         }
     }
@@ -117,6 +174,29 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
         vi[0] = o.viol_t; vi[1] = o.viol_l; vi[2] = o.viol_lb;
     }
     if (o.flags & ZZ_F_OVERFLOW) atomicOr(&C->wl_cnt[nxt], ZZ_OVF_BIT);
+}
+
+// One timeline evaluation + publication; kept out of line so the three call sites (scan pass, relaxation pass,
+// tail pass) share one copy of the code and its register allocation.
+template <int KIND>
+__device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, double H, int incl, uint32_t w0,
+                                             uint32_t cur, bool first, int nxt, int ws)
+{
+    ZzNodeOut o;
+#ifdef ZZ_PROF_NODE
+    const long long c0 = clock64();
+    zz_process_node_k<KIND>(P.g, P.v, j, H, incl, w0, cur, first, o);
+    const long long c1 = clock64();
+    zz_publish<KIND>(P, j, o, w0, cur, nxt, ws);
+    const long long c2 = clock64();
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        P.ctl->dbg[0] += (unsigned long long)(c2 - c1);   // cycles in publication
+        P.ctl->dbg[7] += 1ULL;
+    }
+#else
+    zz_process_node_k<KIND>(P.g, P.v, j, H, incl, w0, cur, first, o);
+    zz_publish<KIND>(P, j, o, w0, cur, nxt, ws);
+#endif
 }
 
 // Fold the converged end-of-window state of coordinate j into the frontier.
@@ -215,9 +295,14 @@ zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ 
     }
 }
 
-extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzParams P)
+template <int KIND>
+__device__ __forceinline__ void zz_run_body(const ZzParams& P)
 {
     ZzDevCtl* C = P.ctl;
+#ifdef ZZ_PROF_NODE
+    if (blockIdx.x == 0 && threadIdx.x == 0) zz_dbg_ptr = C->dbg;
+    __syncthreads();
+#endif
     __shared__ int32_t sq[ZZ_BLOCK / 32][32 * ZZ_SCAN_U];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -241,6 +326,11 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzPar
     unsigned int windows_done = 0;
     unsigned long long st_iters = 0, st_retries = 0, st_evals = 0, st_rebases = 0;
     bool stop = false;
+    unsigned long long profbuf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    unsigned long long* prof = leader ? profbuf : nullptr;
+    unsigned long long tmark = 0;
+#define ZZ_TIC() do { if (prof) tmark = zz_now(); } while (0)
+#define ZZ_TOC(k) do { if (prof) prof[k] += zz_now() - tmark; } while (0)
 
     while (ctl.phase < ZZ_PH_DONE && !stop) {
         if (cur > P.tag_limit) {  // iteration tags are about to run out of bits: forget all of them
@@ -248,7 +338,7 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzPar
                 reinterpret_cast<unsigned long long*>(P.v.kin + j)[3] = 0ULL;
                 P.dstamp[j] = 0;
             }
-            zz_grid_barrier(C, epoch);
+            zz_grid_barrier(C, epoch, prof);
             cur = 0; st_rebases++;
         }
         const ZzCtl saved = ctl;
@@ -261,6 +351,7 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzPar
 
         // ---------------- pass 1: scan + evaluate every coordinate with a proposal inside the window
         int nxt = (int)((li + 1) % 3u);
+        ZZ_TIC();
         if (leader) {
             C->wl_cnt[(li + 2) % 3u] = 0;
             const int wz = (int)(wat % 3u);  // slot of the NEXT attempt
@@ -282,14 +373,13 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzPar
                 const int32_t j = sq[warp][q];
                 const uint32_t old = atomicMax(P.dstamp + j, cur);
                 if (old < w0) zz_append(P.touched[0], &C->touched_cnt[ws], j);
-                ZzNodeOut o;
-                zz_process_node(P.g, P.v, j, H, incl, w0, cur, true, o);
-                zz_publish(P, j, o, w0, cur, nxt, ws);
+                zz_eval_publish<KIND>(P, j, H, incl, w0, cur, true, nxt, ws);
                 st_evals++;
             }
             __syncwarp();
         }
-        zz_grid_barrier(C, epoch);
+        ZZ_TOC(0);
+        zz_grid_barrier(C, epoch, prof);
         st_iters++;
 
         // ---------------- relaxation passes
@@ -298,19 +388,51 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzPar
             const unsigned int cw = __ldcg(&C->wl_cnt[nxt]);
             if (cw & ZZ_OVF_BIT) { overflow = true; li = (li + 1) % 3u; break; }
             if (cw == 0) break;
+            if (cw <= ZZ_TAIL) {
+                // Few coordinates left (typically a couple of hot neighbours resolving a long causal chain one
+                // event per pass): CTA 0 runs these passes alone with block barriers; the others wait once.
+                if (blockIdx.x == 0) {
+                    ZZ_TIC();
+                    unsigned int n = cw;
+                    for (;;) {
+                        li = (li + 1) % 3u;
+                        nxt = (int)((li + 1) % 3u);
+                        cur++;
+                        if (threadIdx.x == 0) C->wl_cnt[(li + 2) % 3u] = 0;
+                        const int32_t* wlt = P.wl[li];
+                        for (unsigned int e = threadIdx.x; e < n; e += blockDim.x) {
+                            const int32_t j = __ldcg(wlt + e);
+                            zz_eval_publish<KIND>(P, j, H, incl, w0, cur, false, nxt, ws);
+                            st_evals++;
+                        }
+                        __threadfence();
+                        __syncthreads();
+                        st_iters++;
+                        if (prof) prof[7] += 1;
+                        n = __ldcg(&C->wl_cnt[nxt]);
+                        if (n == 0 || n > ZZ_TAIL) break;  // (an overflow bit makes n > ZZ_TAIL)
+                    }
+                    if (threadIdx.x == 0) { C->tail_li = li; C->tail_cur = cur; }
+                    ZZ_TOC(2);
+                }
+                zz_grid_barrier(C, epoch, prof);
+                li = __ldcg(&C->tail_li); cur = __ldcg(&C->tail_cur);
+                nxt = (int)((li + 1) % 3u);
+                continue;
+            }
             li = (li + 1) % 3u;
             nxt = (int)((li + 1) % 3u);
             cur++;
+            ZZ_TIC();
             if (leader) C->wl_cnt[(li + 2) % 3u] = 0;
             const int32_t* wl = P.wl[li];
             for (unsigned int e = gtid; e < cw; e += nthreads) {
                 const int32_t j = __ldcg(wl + e);
-                ZzNodeOut o;
-                zz_process_node(P.g, P.v, j, H, incl, w0, cur, false, o);
-                zz_publish(P, j, o, w0, cur, nxt, ws);
+                zz_eval_publish<KIND>(P, j, H, incl, w0, cur, false, nxt, ws);
                 st_evals++;
             }
-            zz_grid_barrier(C, epoch);
+            ZZ_TOC(1);
+            zz_grid_barrier(C, epoch, prof);
             st_iters++;
         }
         cur++;  // tag of the commit pass: every list written in this window is visible to it
@@ -318,6 +440,7 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzPar
         // ---------------- phase B: time of the earliest accepted flip in the (trial) window
         double smin = ZZ_INF;
         if (!overflow && ctl.phase == ZZ_PH_B) {
+            ZZ_TIC();
             const unsigned int nt = __ldcg(&C->touched_cnt[ws]);
             unsigned long long kmin = ~0ULL;
             for (unsigned int e = gtid; e < nt; e += nthreads) {
@@ -333,7 +456,8 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzPar
                 }
             }
             if (kmin != ~0ULL) atomicMin(&C->smin_key[ws], kmin);
-            zz_grid_barrier(C, epoch);
+            ZZ_TOC(5);
+            zz_grid_barrier(C, epoch, prof);
             const unsigned long long kk = __ldcg(&C->smin_key[ws]);
             if (kk != ~0ULL) smin = zz_unkey(kk);
         }
@@ -352,6 +476,7 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzPar
         }
         ctl = trial;
         if (act == ZZ_ACT_COMMIT) {
+            ZZ_TIC();
             const unsigned int nt = __ldcg(&C->touched_cnt[ws]);
             unsigned int np = 0, nf = 0;
             for (unsigned int e = gtid; e < nt; e += nthreads) {
@@ -366,7 +491,8 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzPar
                 atomicAdd(&C->num, (unsigned long long)np);
                 atomicAdd(&C->nacc, (unsigned long long)nf);
             }
-            zz_grid_barrier(C, epoch);
+            ZZ_TOC(3);
+            zz_grid_barrier(C, epoch, prof);
             if (leader && P.record_trace) {  // window-end marker (i = 0): lets the host sort window by window
                 const unsigned long long pos = atomicAdd(&C->trace_len, 1ULL);
                 double2* e = reinterpret_cast<double2*>(P.trace + pos);
@@ -384,9 +510,13 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_run_kernel(const ZzPar
 
     if (leader) {
         C->ctl = ctl; C->cur = cur; C->itg = li; C->wattempt = wat; C->started = 1u;
+        for (int q = 0; q < 8; ++q) C->tprof[q] += profbuf[q];
         C->windows += windows_done; C->retries += st_retries; C->iters += st_iters; C->rebases += st_rebases;
     }
     cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
     st_evals = cg::reduce(w, st_evals, cg::plus<unsigned long long>());
     if (lane == 0 && st_evals) atomicAdd(&C->node_evals, st_evals);
 }
+
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_grid(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_GRID>(P); }
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_csr(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_CSR>(P); }

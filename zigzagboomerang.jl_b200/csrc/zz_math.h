@@ -119,22 +119,19 @@ ZZ_HD double zz_u01(uint64_t seed0, uint64_t seed1, uint64_t coord, uint64_t ctr
 // Expression shapes follow src/poissontime.jl:8-30 term by term ((a/b)^2 is (a/b)*(a/b)).
 ZZ_HD double zz_poisson_time(double a, double b, double u)
 {
-    if (b > 0.0) {
-        if (a < 0.0) return zz_sqrt(-zz_log(u) * 2.0 / b) - a / b;
-        double q = a / b;
-        return zz_sqrt(q * q - zz_log(u) * 2.0 / b) - a / b;
-    } else if (b == 0.0) {
-        if (a > 0.0) return -zz_log(u) / a;
-        return ZZ_INF;
-    } else {
-        if (a <= 0.0) return ZZ_INF;
-        double nl = -zz_log(u);
-        if (nl <= -(a * a) / b + (a * a) / (2.0 * b)) {
-            double q = a / b;
-            return -zz_sqrt(q * q - zz_log(u) * 2.0 / b) - a / b;
-        }
-        return ZZ_INF;
-    }
+    // One logarithm, one square root and the two quotients shared by all branches (SIMT lanes that take different
+    // branches of the reference formula then diverge only in cheap selects).  Bit-identical to evaluating the
+    // reference expressions branch by branch: (-L)*2/b == -(L*2/b) exactly, negation commutes with rounding.
+    const double L = zz_log(u);  // < 0
+    if (b == 0.0) return a > 0.0 ? -L / a : ZZ_INF;
+    const double q = a / b;
+    const double t2 = L * 2.0 / b;
+    int ok = b > 0.0;
+    if (!ok && a > 0.0) ok = (-L <= -(a * a) / b + (a * a) / (2.0 * b));
+    if (!ok) return ZZ_INF;
+    const double arg = (b > 0.0 && a < 0.0) ? -t2 : q * q - t2;
+    const double root = zz_sqrt(arg);
+    return (b > 0.0 ? root : -root) - q;
 }
 
 // Rate c + (a + b t)^+, c > 0 (src/poissontime.jl:39-65); used by the sticky variants.

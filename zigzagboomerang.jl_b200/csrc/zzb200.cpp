@@ -87,10 +87,10 @@ struct Global {
     CUdevice dev = 0; int dev_id = 0;
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
-    CUfunction f_setup = nullptr, f_init = nullptr, f_run = nullptr, f_export = nullptr;
+    CUfunction f_setup = nullptr, f_init = nullptr, f_run[2] = { nullptr, nullptr }, f_export = nullptr;
     CUstream stream = nullptr;
-    CUevent ev0 = nullptr, ev1 = nullptr;
-    int sm_count = 0; int blocks_per_sm = 0;
+    CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
+    int sm_count = 0; int blocks_per_sm[2] = { 0, 0 };
     size_t total_mem = 0; char name[128] = { 0 };
 };
 static Global G;
@@ -158,13 +158,12 @@ struct zzb_run_s {
     ZzParams P;
     double t0 = 0, T = 0;
     double delta0 = 0, target_frac = 0.4; unsigned int tag_limit = ZZ_TAG_LIMIT; unsigned int max_windows = 0;
-    bool uploaded = false, executed = false;
+    bool uploaded = false, executed = false, have_inputs = false;
     // results
     std::vector<zzb_event> events;     // sorted, markers removed
-    std::vector<double> x0;
     ZzDevCtl hc;                       // last copy of the device control block
     int64_t launches = 0;
-    int grid = 0;
+    int grid = 0; int kind = 1;
     bool fetched = false;
     std::vector<double> ft, fx, fth, fc; std::vector<long long> facc; std::vector<double> hs1, hs2;
 };
@@ -215,13 +214,18 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     CU(cuModuleLoadData(&G.mod, img.data()));
     CU(cuModuleGetFunction(&G.f_setup, G.mod, "zz_setup_kernel"));
     CU(cuModuleGetFunction(&G.f_init, G.mod, "zz_init_kernel"));
-    CU(cuModuleGetFunction(&G.f_run, G.mod, "zz_run_kernel"));
+    CU(cuModuleGetFunction(&G.f_run[0], G.mod, "zz_run_kernel_grid"));
+    CU(cuModuleGetFunction(&G.f_run[1], G.mod, "zz_run_kernel_csr"));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuStreamCreate(&G.stream, CU_STREAM_NON_BLOCKING));
     CU(cuEventCreate(&G.ev0, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.ev1, CU_EVENT_DEFAULT));
-    CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm, G.f_run, ZZ_BLOCK, 0));
-    if (G.blocks_per_sm < 1) return fail(ZZB_E_CUDA, "zz_run_kernel does not fit on an SM");
+    CU(cuEventCreate(&G.tev0, CU_EVENT_DEFAULT));
+    CU(cuEventCreate(&G.tev1, CU_EVENT_DEFAULT));
+    for (int k = 0; k < 2; ++k) {
+        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm[k], G.f_run[k], ZZ_BLOCK, 0));
+        if (G.blocks_per_sm[k] < 1) return fail(ZZB_E_CUDA, "zz_run_kernel does not fit on an SM");
+    }
     G.ready = true;
     return ZZB_OK;
 }
@@ -251,6 +255,24 @@ int32_t zzb_device_info(int32_t* sm_count, int64_t* total_mem, char* name, int64
     return ZZB_OK;
 }
 
+// CUDA events on the library's launching stream: which = 0 marks the start, 1 the end of a timed region.
+int32_t zzb_event_record(int32_t which)
+{
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    CtxGuard cg;
+    CU(cuEventRecord(which ? G.tev1 : G.tev0, G.stream));
+    return ZZB_OK;
+}
+
+int32_t zzb_event_elapsed_ms(float* ms)
+{
+    if (!G.ready || !ms) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    CtxGuard cg;
+    CU(cuEventSynchronize(G.tev1));
+    CU(cuEventElapsedTime(ms, G.tev0, G.tev1));
+    return ZZB_OK;
+}
+
 int32_t zzb_problem_create_gaussian(zzb_problem_t* out, int64_t d, const int64_t* colptr, const int64_t* rowval,
                                     const double* nzval, const double* hvec, const int64_t* bnd_colptr,
                                     const int64_t* bnd_rowval, const double* bnd_nzval, const double* bnd_mu)
@@ -274,6 +296,8 @@ int32_t zzb_problem_create_gaussian(zzb_problem_t* out, int64_t d, const int64_t
     p->g.nptr = p->nptr.as<int32_t>(); p->g.nidx = p->nidx.as<int32_t>(); p->g.nwt = p->nwt.as<double>();
     p->g.nwb = p->nwb.as<double>(); p->g.nfl = p->nfl.as<uint8_t>(); p->g.gmu = p->gmu.as<double>();
     p->g.h = hg.has_h ? p->h.as<double>() : nullptr; p->g.same = hg.same;
+    p->g.grid_m = getenv("ZZB200_NO_GRID") ? 0 : hg.grid_m; p->g.grid_n = hg.grid_n;
+    for (int q = 0; q < 5; ++q) p->g.grid_diag[q] = hg.grid_diag[q];
     *out = p;
     return ZZB_OK;
 }
@@ -317,7 +341,8 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     }
 #undef AL
     if (st) { delete r; return st == ZZB_E_CUDA ? ZZB_E_NOMEM : st; }
-    r->grid = G.sm_count * G.blocks_per_sm;
+    r->kind = p->g.grid_m ? 0 : 1;
+    r->grid = G.sm_count * G.blocks_per_sm[r->kind];
     *out = r;
     return ZZB_OK;
 }
@@ -346,26 +371,20 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     else if (!strcmp(key, "target_frac")) r->target_frac = value;
     else if (!strcmp(key, "tag_limit")) r->tag_limit = (unsigned int)value;
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
-    else if (!strcmp(key, "grid")) r->grid = std::max(1, std::min((int)value, G.sm_count * G.blocks_per_sm));
+    else if (!strcmp(key, "grid")) r->grid = std::max(1, std::min((int)value, G.sm_count * G.blocks_per_sm[r->kind]));
     else return fail(ZZB_E_ARG, "unknown tuning key %s", key);
     return ZZB_OK;
 }
 
-int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* theta0, const double* c,
-                       const uint64_t* seed, int32_t adapt, double factor)
+// (Re)initialise the device state from the inputs already resident in HBM: per-coordinate records, initial
+// bounds and first proposal times (sfact.jl:167-187).  No host<->device traffic except the 200-byte control block.
+int32_t zzb_run_reset(zzb_run_t r)
 {
-    if (!r || !x0 || !theta0 || !c || !seed) return fail(ZZB_E_ARG, "null argument");
+    if (!r) return fail(ZZB_E_ARG, "null argument");
     if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (!r->have_inputs) return fail(ZZB_E_ARG, "zzb_run_upload must precede zzb_run_reset");
     CtxGuard cg;
-    const size_t nb = (size_t)r->d * 8;
-    fill_params(r);
     ZzParams& P = r->P;
-    P.v.seed0 = seed[0]; P.v.seed1 = seed[1]; P.v.adapt = adapt; P.v.factor = factor; P.t0 = t0;
-    r->t0 = t0;
-    r->x0.assign(x0, x0 + r->d);
-    CU(cuMemcpyHtoDAsync(r->in_x.p, x0, nb, G.stream));
-    CU(cuMemcpyHtoDAsync(r->in_th.p, theta0, nb, G.stream));
-    CU(cuMemcpyHtoDAsync(r->in_c.p, c, nb, G.stream));
     ZzDevCtl hc; memset(&hc, 0, sizeof hc);
     hc.f0_key = ~0ULL; for (int k = 0; k < 3; ++k) hc.smin_key[k] = ~0ULL;
     CU(cuMemcpyHtoDAsync(r->ctl.p, &hc, sizeof hc, G.stream));
@@ -380,6 +399,26 @@ int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* t
     r->uploaded = true; r->executed = false; r->fetched = false;
     r->events.clear();
     return ZZB_OK;
+}
+
+int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* theta0, const double* c,
+                       const uint64_t* seed, int32_t adapt, double factor)
+{
+    if (!r || !x0 || !theta0 || !c || !seed) return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    {
+        CtxGuard cg;
+        const size_t nb = (size_t)r->d * 8;
+        fill_params(r);
+        ZzParams& P = r->P;
+        P.v.seed0 = seed[0]; P.v.seed1 = seed[1]; P.v.adapt = adapt; P.v.factor = factor; P.t0 = t0;
+        r->t0 = t0;
+        CU(cuMemcpyHtoDAsync(r->in_x.p, x0, nb, G.stream));
+        CU(cuMemcpyHtoDAsync(r->in_th.p, theta0, nb, G.stream));
+        CU(cuMemcpyHtoDAsync(r->in_c.p, c, nb, G.stream));
+        r->have_inputs = true;
+    }
+    return zzb_run_reset(r);
 }
 
 // sort every window segment (records between two i == 0 markers) by (time, coordinate) and drop the markers
@@ -423,7 +462,7 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
         CU(cuMemsetD8Async(r->ctl.p, 0, 8, G.stream));  // barrier counter
         void* args[] = { &P };
         CU(cuEventRecord(G.ev0, G.stream));
-        CU(cuLaunchCooperativeKernel(G.f_run, (unsigned)r->grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, args));
+        CU(cuLaunchCooperativeKernel(G.f_run[r->kind], (unsigned)r->grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, args));
         CU(cuEventRecord(G.ev1, G.stream));
         CU(cuStreamSynchronize(G.stream));
         r->launches++;
@@ -511,9 +550,10 @@ int32_t zzb_run_stats(zzb_run_t r, int64_t* out, int32_t n)
     if (!r || !out) return fail(ZZB_E_ARG, "null argument");
     int32_t st = fetch_state(r);
     if (st) return st;
-    const int64_t v[8] = { (int64_t)r->hc.windows, (int64_t)r->hc.retries, (int64_t)r->hc.iters, (int64_t)r->hc.node_evals,
-                           (int64_t)r->hc.rebases, r->launches, (int64_t)r->grid, (int64_t)ZZ_BLOCK };
-    for (int32_t k = 0; k < n && k < 8; ++k) out[k] = v[k];
+    int64_t v[24] = { (int64_t)r->hc.windows, (int64_t)r->hc.retries, (int64_t)r->hc.iters, (int64_t)r->hc.node_evals,
+                      (int64_t)r->hc.rebases, r->launches, (int64_t)r->grid, (int64_t)ZZ_BLOCK };
+    for (int k = 0; k < 8; ++k) { v[8 + k] = (int64_t)r->hc.tprof[k]; v[16 + k] = (int64_t)r->hc.dbg[k]; }
+    for (int32_t k = 0; k < n && k < 24; ++k) out[k] = v[k];
     return ZZB_OK;
 }
 
