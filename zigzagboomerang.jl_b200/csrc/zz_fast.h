@@ -21,6 +21,21 @@ __device__ long long zz_dbg_last;
 #define ZZ_NB 8     // neighbourhood capacity of the gathered path (entries of column j, j included)
 #define ZZ_POOL 16  // neighbour flips merged per coordinate and window
 
+// frontier state of the coordinate being evaluated (loaded before the neighbourhood so that all loads overlap)
+struct ZzOwn {
+    double th, tf, xf, a, b, told, c, tau;
+    uint32_t k, hdr0, hdr1;
+};
+
+ZZ_HD void zz_load_own(const ZzView& v, int32_t j, ZzOwn& w)
+{
+    zz_ld_kin(v.kin + j, w.th, w.tf, w.xf, w.hdr0, w.hdr1);
+    const ZzPriv pr = zz_ld_priv(v.priv + j);
+    w.a = pr.a; w.b = pr.b; w.told = pr.told; w.c = pr.c;
+    w.tau = zz_ld(v.tau + j);
+    w.k = zz_ld32(v.kctr + j);
+}
+
 template <int NB>
 struct ZzHood {
     int n;        // entries in storage order
@@ -150,23 +165,21 @@ ZZ_HD void zz_eval_hood(const ZzHood<NB>& hd, bool same, double s, double xown, 
 
 // Timeline of coordinate j from gathered data; identical arithmetic to zz_process_node_slow.
 template <int NB>
-ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzGraph& g, const ZzView& v, int32_t j,
-                       double H, int incl, uint32_t flags0, ZzNodeOut& o)
+ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w, const ZzGraph& g, const ZzView& v,
+                       int32_t j, double H, int incl, uint32_t flags0, ZzNodeOut& o)
 {
-    double th, tf, xf; uint32_t hh0, hh1;
-    zz_ld_kin(v.kin + j, th, tf, xf, hh0, hh1);
-    const ZzPriv pr = zz_ld_priv(v.priv + j);
-    double a = pr.a, b = pr.b, told = pr.told, c = pr.c;
+    double th = w.th, tf = w.tf, xf = w.xf;
+    const uint32_t hh0 = w.hdr0, hh1 = w.hdr1;
+    double a = w.a, b = w.b, told = w.told, c = w.c;
     double c100 = c / 100;
-    double tau = zz_ld(v.tau + j);
-    uint32_t k = zz_ld32(v.kctr + j);
+    double tau = w.tau;
+    uint32_t k = w.k;
     const double gmu = g.grid_m ? 0.0 : g.gmu[j];
     const double hj = (!g.same && g.h) ? g.h[j] : 0.0;
     const bool has_h = (!g.same && g.h);
     uint32_t nprop = 0, nflip = 0, flags = flags0;
     o.viol_t = 0.0; o.viol_l = 0.0; o.viol_lb = 0.0;
     int p = 0;
-    ZZ_SEG(3);
 
     for (int item = 0;; ++item) {
         ZZ_SEGCOUNT();
@@ -176,32 +189,8 @@ ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzGraph& g, con
         const double s = own ? tau : nt;
         if (!(s < H || (incl && s == H))) break;
         if (item >= ZZ_MAXITEMS) { flags |= ZZ_F_OVERFLOW; break; }
-        double gt, gx, gp, gm, gth;
-        if (own) {
-            const double xs = xf + th * (s - tf);
-            zz_eval_hood<NB>(hd, g.same != 0, s, xs, th, gt, gx, gp, gm);
-            if (has_h) gt = gt - hj;
-            const double l = zz_pos(gt * th);                 // fact_samplers.jl:28-30
-            const double lb = zz_pos(a + b * (s - told));     // sfact.jl:70
-            const double u = zz_u01(v.seed0, v.seed1, (uint64_t)j, k++);
-            nprop++;
-            if (u * lb < l) {                                 // sfact.jl:121
-                if (l >= lb) {                                // sfact.jl:123-128
-                    if (v.adapt) { c *= v.factor; c100 = c / 100; }
-                    else if (!(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
-                }
-                if (nflip == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
-#pragma unroll
-                for (int m = 0; m < ZZ_MAXFLIP; ++m)
-                    if (m == (int)nflip) o.fl[m] = s;
-                nflip++;
-                xf = xs; tf = s; th = -th;                    // dynamics.jl:46-49
-                gth = gm;
-            } else {
-                gth = gp;
-            }
-        } else {
-            // neighbour at position nm flips at s: advance its anchor, then (if it triggers us) reschedule
+        if (!own) {
+            // neighbour at position nm flips at s: advance its anchor; reschedule j only if it triggers us
             bool trig = false;
 #pragma unroll
             for (int m = 0; m < NB; ++m) {
@@ -214,14 +203,41 @@ ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzGraph& g, con
             }
             ++p;
             if (!trig) continue;
-            const double xs = xf + th * (s - tf);
-            zz_eval_hood<NB>(hd, g.same != 0, s, xs, th, gt, gx, gp, gm);
-            gth = gp;
+        }
+        // the draws of this item depend only on the counter: start them (and the logarithm of the rescheduling draw)
+        // before the neighbourhood evaluation so that the two dependency chains overlap
+        const uint32_t kr = own ? k + 1u : k;
+        const double L2 = zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, kr));
+        const double u1 = own ? zz_u01(v.seed0, v.seed1, (uint64_t)j, k) : 0.0;
+        k = kr + 1u;
+        // one evaluation of the column at s shared by both kinds of item (keeps diverged lanes on the same code)
+        const double xs = xf + th * (s - tf);
+        double gt, gx, gp, gm;
+        zz_eval_hood<NB>(hd, g.same != 0, s, xs, th, gt, gx, gp, gm);
+        double gth = gp;
+        if (own) {
+            if (has_h) gt = gt - hj;
+            const double l = zz_pos(gt * th);                 // fact_samplers.jl:28-30
+            const double lb = zz_pos(a + b * (s - told));     // sfact.jl:70
+            nprop++;
+            if (u1 * lb < l) {                                // sfact.jl:121
+                if (l >= lb) {                                // sfact.jl:123-128
+                    if (v.adapt) { c *= v.factor; c100 = c / 100; }
+                    else if (!(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
+                }
+                if (nflip == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#pragma unroll
+                for (int m = 0; m < ZZ_MAXFLIP; ++m)
+                    if (m == (int)nflip) o.fl[m] = s;
+                nflip++;
+                xf = xs; tf = s; th = -th;                    // dynamics.jl:46-49
+                gth = gm;
+            }
         }
         a = c + (gx - gmu) * th;                              // fact_samplers.jl:51
         b = c100 + th * gth;                                  // fact_samplers.jl:52 (c100 = c / 100)
         told = s;
-        tau = s + zz_poisson_time(a, b, zz_u01(v.seed0, v.seed1, (uint64_t)j, k++));  // sfact.jl:134,139
+        tau = s + zz_poisson_time_L(a, b, L2);                // sfact.jl:134,139
     }
     o.a = a; o.b = b; o.told = told; o.tau = tau; o.c = c;
     o.k = k; o.nprop = nprop; o.nflip = nflip; o.flags = flags;
@@ -236,18 +252,22 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
                              uint32_t cur, bool first_iter, ZzNodeOut& o)
 {
     ZzPool pool; uint32_t flags = 0;
+    ZzOwn w;
     if (KIND == ZZ_KIND_GRID) {
         ZzHood<5> hd;
         ZZ_SEG(0);
+        zz_load_own(v, j, w);
         zz_gather_grid(g, v, j, w0, cur, first_iter, hd, pool, flags);
         ZZ_SEG(2);
-        zz_timeline<5>(hd, pool, g, v, j, H, incl, flags, o);
+        zz_timeline<5>(hd, pool, w, g, v, j, H, incl, flags, o);
         ZZ_SEG(5);
         return;
     }
     ZzHood<ZZ_NB> hd;
-    if (zz_gather_csr<ZZ_NB>(g, v, j, w0, cur, first_iter, hd, pool, flags)) {
-        zz_timeline<ZZ_NB>(hd, pool, g, v, j, H, incl, flags, o);
+    if (g.nptr[j + 1] - g.nptr[j] <= ZZ_NB) {
+        zz_load_own(v, j, w);
+        zz_gather_csr<ZZ_NB>(g, v, j, w0, cur, first_iter, hd, pool, flags);
+        zz_timeline<ZZ_NB>(hd, pool, w, g, v, j, H, incl, flags, o);
         return;
     }
     zz_process_node_slow(g, v, j, H, incl, w0, cur, first_iter, o);

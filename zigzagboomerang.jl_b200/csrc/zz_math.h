@@ -96,7 +96,7 @@ ZZ_HD double zz_log(double x)
 // ---------------------------------------------------------------------------------------------
 // Counter-based uniforms.  u(i,k) is the k-th draw of coordinate i's private stream:
 // two rounds of the splitmix64 finaliser over (seed, coordinate, counter).  The value is
-// strictly inside (0,1) so log(u) is always finite.  (The reference draws from one
+// strictly inside (0,1) -- in [2^-53, 1 - 2^-53] -- so log(u) is always finite.  (The reference draws from one
 // sequential Xoroshiro128Plus stream in global event order, src/sfact.jl:121,134,139,186,
 // which no parallel schedule can reproduce; see DESIGN.md "RNG contract".)
 ZZ_HD uint64_t zz_mix64(uint64_t z)
@@ -111,18 +111,20 @@ ZZ_HD double zz_u01(uint64_t seed0, uint64_t seed1, uint64_t coord, uint64_t ctr
 {
     uint64_t z = zz_mix64(seed0 + (coord + 1ULL) * 0x9E3779B97F4A7C15ULL);
     z = zz_mix64(z ^ (seed1 + ctr * 0xD1342543DE82EF95ULL));
-    // 53 random bits, centred in their cell: (n + 1/2) * 2^-53, n in [0, 2^53)
-    return ((double)(z >> 11) + 0.5) * 1.1102230246251565404e-16;
+    // 52 random bits as the mantissa of a double in [1,2), shifted to (0,1): u = m 2^-52 + 2^-53 (exact arithmetic;
+    // two integer and two floating-point instructions instead of a 64-bit integer-to-double conversion)
+    return (zz_u2d((z >> 12) | 0x3FF0000000000000ULL) - 1.0) + 1.1102230246251565404e-16;
 }
 
 // First arrival time of an inhomogeneous Poisson process with rate (a + b t)^+ given u ~ U(0,1).
 // Expression shapes follow src/poissontime.jl:8-30 term by term ((a/b)^2 is (a/b)*(a/b)).
-ZZ_HD double zz_poisson_time(double a, double b, double u)
+// zz_poisson_time_L takes L = log(u) so that callers can compute the logarithm early (it does not depend on a, b)
+// and overlap its latency with the evaluation of the rates.
+ZZ_HD double zz_poisson_time_L(double a, double b, double L)
 {
-    // One logarithm, one square root and the two quotients shared by all branches (SIMT lanes that take different
-    // branches of the reference formula then diverge only in cheap selects).  Bit-identical to evaluating the
-    // reference expressions branch by branch: (-L)*2/b == -(L*2/b) exactly, negation commutes with rounding.
-    const double L = zz_log(u);  // < 0
+    // One square root and the two quotients shared by all branches (SIMT lanes that take different branches of the
+    // reference formula then diverge only in cheap selects).  Bit-identical to evaluating the reference expressions
+    // branch by branch: (-L)*2/b == -(L*2/b) exactly, negation commutes with rounding.  L = log(u) < 0.
     if (b == 0.0) return a > 0.0 ? -L / a : ZZ_INF;
     const double q = a / b;
     const double t2 = L * 2.0 / b;
@@ -133,6 +135,8 @@ ZZ_HD double zz_poisson_time(double a, double b, double u)
     const double root = zz_sqrt(arg);
     return (b > 0.0 ? root : -root) - q;
 }
+
+ZZ_HD double zz_poisson_time(double a, double b, double u) { return zz_poisson_time_L(a, b, zz_log(u)); }
 
 // Rate c + (a + b t)^+, c > 0 (src/poissontime.jl:39-65); used by the sticky variants.
 ZZ_HD double zz_poisson_time3(double a, double b, double c, double u)

@@ -1,0 +1,106 @@
+# ZigZagBoomerangB200.jl -- thin Julia wrapper over libzzb200.so (include/zzb200.h).
+#
+# Adds GPU methods to the reference's own `spdmp` / `pdmp` generic functions: they are selected by dispatch when
+# the "gradient" argument is a `GaussianPotential` descriptor instead of a closure, and return exactly what the
+# reference returns: `Ξ::FactTrace, (t, x, θ), (acc, num), c` (src/sfact.jl:211).
+#
+# NOTE: Julia is not installed in the build image, so this file is UNTESTED there; it is kept in lock-step with the
+# ctypes binding zigzagboomerang.jl_b200/_capi.py, which exercises the same entry points in the test-suite.
+module ZigZagBoomerangB200
+
+using ZigZagBoomerang
+using ZigZagBoomerang: ZigZag, FactTrace, Trace, Seed
+using SparseArrays
+import ZigZagBoomerang: spdmp, pdmp
+
+const libzzb200 = get(ENV, "ZZB200_LIB", joinpath(@__DIR__, "..", "libzzb200.so"))
+const cubin = get(ENV, "ZZB200_CUBIN", joinpath(@__DIR__, "..", "zzb200_kernels.cubin"))
+
+const ZZB_E_BOUND = Int32(3)
+const ZZB_FLAG_NO_TRACE = UInt32(1)
+
+"""
+    GaussianPotential(Γ, h = nothing)
+
+Target descriptor standing in for the closure `∇ϕ(x, i) = idot(Γ, i, x) - h[i]`; also callable like it, so the same
+object works with the reference's CPU `spdmp`.
+"""
+struct GaussianPotential{T<:SparseMatrixCSC{Float64,Int}, H}
+    Γ::T
+    h::H
+end
+GaussianPotential(Γ) = GaussianPotential(Γ, nothing)
+(g::GaussianPotential)(x, i, args...) = ZigZagBoomerang.idot(g.Γ, i, x) - (g.h === nothing ? 0.0 : g.h[i])
+
+function lasterror()
+    buf = Vector{UInt8}(undef, 1024)
+    ccall((:zzb_last_error, libzzb200), Int32, (Ptr{UInt8}, Int64), buf, 1024)
+    unsafe_string(pointer(buf))
+end
+
+function check(st::Int32)
+    st == 0 && return
+    st == ZZB_E_BOUND && error("Tuning parameter `c` too small.")   # same message as src/sfact.jl:124
+    error("zzb200 error $st: " * lasterror())
+end
+
+const initialised = Ref(false)
+function init(device::Integer = 0)
+    initialised[] && return
+    ids = Int32[device]
+    check(ccall((:zzb_init, libzzb200), Int32, (Int32, Ptr{Int32}, Cstring), 1, ids, cubin))
+    initialised[] = true
+end
+
+function spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G::Union{ZigZagBoomerang.All,ZigZagBoomerang.Matched}, F::ZigZag, args...;
+               factor = 1.8, adapt = false, adaptscale = false, progress = false, progress_stops = 20, seed = Seed())
+    F.λref == 0 || error("refreshments (λref > 0) are not implemented on the device path")
+    init()
+    d = length(x0)
+    Γt, Γb = ∇ϕ.Γ, F.Γ
+    μ = Vector{Float64}(F.μ)
+    x0v, θ0v, cv = Vector{Float64}(x0), Vector{Float64}(θ0), Vector{Float64}(c)
+    prob = Ref{Ptr{Cvoid}}(C_NULL)
+    run = Ref{Ptr{Cvoid}}(C_NULL)
+    h = ∇ϕ.h === nothing ? Ptr{Float64}(C_NULL) : pointer(∇ϕ.h)
+    sd = UInt64[seed[1], seed[2]]
+    GC.@preserve Γt Γb μ x0v θ0v cv sd ∇ϕ begin
+        check(ccall((:zzb_problem_create_gaussian, libzzb200), Int32,
+                    (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+                    prob, d, Γt.colptr, Γt.rowval, Γt.nzval, h, Γb.colptr, Γb.rowval, Γb.nzval, μ))
+        st = ccall((:zzb_spdmp_run, libzzb200), Int32,
+                   (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{UInt64}, Int32, Float64,
+                    UInt32, Ref{Ptr{Cvoid}}),
+                   prob[], t0, x0v, θ0v, T, cv, sd, adapt, factor, UInt32(0), run)
+        if st != 0
+            ccall((:zzb_problem_free, libzzb200), Int32, (Ptr{Cvoid},), prob[])
+            check(st)
+        end
+    end
+    try
+        n = Ref{Int64}(0)
+        check(ccall((:zzb_trace_len, libzzb200), Int32, (Ptr{Cvoid}, Ref{Int64}), run[], n))
+        Ξ = Trace(t0, x0, θ0, F)                       # FactTrace with Tuple{Float64,Int,Float64,Float64}[] events
+        resize!(Ξ.events, n[])
+        check(ccall((:zzb_trace_copy, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64), run[], Ξ.events, 0, n[]))
+        t, x, θ = similar(x0v), similar(x0v), similar(x0v)
+        check(ccall((:zzb_run_final_state, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    run[], t, x, θ, cv))
+        acc = Vector{Int}(undef, d); num = Ref{Int64}(0)
+        check(ccall((:zzb_run_counts, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ref{Int64}), run[], acc, num))
+        c .= cv                                        # adapted bounds, like the in-place `adapt!` of the reference
+        return Ξ, (t, x, θ), (acc, num[]), c
+    finally
+        ccall((:zzb_run_free, libzzb200), Int32, (Ptr{Cvoid},), run[])
+        ccall((:zzb_problem_free, libzzb200), Int32, (Ptr{Cvoid},), prob[])
+    end
+end
+
+spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F::ZigZag, args...; kargs...) =
+    spdmp(∇ϕ, t0, x0, θ0, T, c, ZigZagBoomerang.Matched(), F, args...; kargs...)
+pdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F::ZigZag, args...; kargs...) =
+    spdmp(∇ϕ, t0, x0, θ0, T, c, ZigZagBoomerang.All(), F, args...; kargs...)
+
+export GaussianPotential
+end # module
