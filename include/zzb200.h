@@ -78,6 +78,14 @@ int32_t zzb_spdmp_run(zzb_problem_t p, double t0, const double* x0, const double
 int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_events, zzb_run_t* out);
 int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* theta0, const double* c,
                        const uint64_t* seed, int32_t adapt, double factor);
+/* Coordinate sharding over the GPUs of one node (one process per GPU): rank r owns a contiguous block of coordinates;
+ * halo records are read, and remote coordinates queued, through CUDA-IPC peer mappings over NVLink.  Order: zzb_run_create,
+ * zzb_run_shard, exchange zzb_run_ipc_export blobs (e.g. torch.distributed all_gather), zzb_run_ipc_import for every peer,
+ * zzb_run_upload on every rank, a host barrier, zzb_run_execute on every rank.  Results cover the owned range. */
+int32_t zzb_run_shard(zzb_run_t r, int32_t rank, int32_t nranks);
+int32_t zzb_run_ipc_export(zzb_run_t r, void* buf, int64_t cap, int64_t* len);
+int32_t zzb_run_ipc_import(zzb_run_t r, int32_t peer_rank, const void* buf, int64_t len);
+int32_t zzb_run_range(zzb_run_t r, int64_t* lo, int64_t* hi);       /* owned coordinates [lo, hi), 0-based */
 int32_t zzb_run_reset(zzb_run_t r);                                  /* re-initialise from the inputs resident in HBM */
 int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms);   /* device_ms: CUDA-event time of the kernel(s) */
 int32_t zzb_run_set(zzb_run_t r, const char* key, double value);    /* "delta0", "target_frac", "tag_limit", "max_windows" */

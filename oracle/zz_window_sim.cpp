@@ -56,7 +56,7 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
     g.grid_m = (tag_limit & 0x80000000u) ? 0 : G.grid_m; g.grid_n = G.grid_n;  // top bit of tag_limit: force the CSR path
     tag_limit &= 0x7fffffffu;
     for (int q = 0; q < 5; ++q) g.grid_diag[q] = G.grid_diag[q];
-    ZzView v; v.d = (int32_t)d; v.kin = kin.data(); v.flips = flips.data(); v.priv = priv.data();
+    ZzView v; memset(&v, 0, sizeof v); v.nranks = 1; v.hi = (int32_t)d; v.shard = (int32_t)d; v.d = (int32_t)d; v.kin = kin.data(); v.flips = flips.data(); v.priv = priv.data();
     v.tau = tau.data(); v.kctr = kctr.data(); v.seed0 = seed[0]; v.seed1 = seed[1]; v.adapt = adapt; v.factor = factor;
 
     for (int64_t j = 0; j < d; ++j) {

@@ -8,3 +8,5 @@ from ._capi import BoundError, ZZBError, device_info, init, shutdown  # noqa: F4
 from .api import (All, FactTrace, GaussianPotential, Matched, Problem, Run, Trace, ZigZag, discretize, mean, pdmp,  # noqa: F401
                   spdmp, subtrace)
 from .problems import CSC, gmrf_config, grid_precision, random_sparse_spd, random_spd  # noqa: F401
+from . import multigpu  # noqa: F401,E402
+from .multigpu import merge_shards, shard_bounds, spdmp_sharded  # noqa: F401,E402

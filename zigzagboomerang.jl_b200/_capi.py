@@ -20,7 +20,7 @@ EVENT_DTYPE = np.dtype([("t", "<f8"), ("i", "<i8"), ("x", "<f8"), ("theta", "<f8
 # every symbol include/zzb200.h declares
 SYMBOLS = [
     "zzb_init", "zzb_shutdown", "zzb_last_error", "zzb_device_info", "zzb_event_record", "zzb_event_elapsed_ms", "zzb_problem_create_gaussian", "zzb_problem_free",
-    "zzb_spdmp_run", "zzb_run_create", "zzb_run_upload", "zzb_run_reset", "zzb_run_execute", "zzb_run_set", "zzb_run_stats",
+    "zzb_spdmp_run", "zzb_run_create", "zzb_run_shard", "zzb_run_ipc_export", "zzb_run_ipc_import", "zzb_run_range", "zzb_run_upload", "zzb_run_reset", "zzb_run_execute", "zzb_run_set", "zzb_run_stats",
     "zzb_run_counts", "zzb_run_final_state", "zzb_trace_len", "zzb_trace_copy", "zzb_trace_moments", "zzb_trace_sums",
     "zzb_run_error_info", "zzb_run_free",
 ]
@@ -59,6 +59,10 @@ def lib():
             "zzb_spdmp_run": [vp, f64, vp, vp, f64, vp, vp, i32, f64, u32, vp],
             "zzb_run_create": [vp, u32, i64, vp],
             "zzb_run_upload": [vp, f64, vp, vp, vp, vp, i32, f64],
+            "zzb_run_shard": [vp, i32, i32],
+            "zzb_run_ipc_export": [vp, vp, i64, vp],
+            "zzb_run_ipc_import": [vp, i32, vp, i64],
+            "zzb_run_range": [vp, vp, vp],
             "zzb_run_reset": [vp],
             "zzb_run_execute": [vp, f64, vp],
             "zzb_run_set": [vp, C.c_char_p, f64],

@@ -206,6 +206,25 @@ class Run:
         self.t0 = float(t0)
         return self
 
+    # ---- sharding over the GPUs of one node (see multigpu.py) -------------------------------------------------
+    def shard(self, rank: int, nranks: int):
+        check(_capi.lib().zzb_run_shard(self._h, int(rank), int(nranks)))
+        return self
+
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(8 * 64)
+        n = C.c_int64()
+        check(_capi.lib().zzb_run_ipc_export(self._h, buf, len(buf), C.byref(n)))
+        return buf.raw[: n.value]
+
+    def ipc_import(self, peer_rank: int, blob: bytes):
+        check(_capi.lib().zzb_run_ipc_import(self._h, int(peer_rank), blob, len(blob)))
+
+    def owned_range(self):
+        lo, hi = C.c_int64(), C.c_int64()
+        check(_capi.lib().zzb_run_range(self._h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
     def reset(self):
         """Re-initialise the device state from the inputs already resident in HBM (no host traffic)."""
         check(_capi.lib().zzb_run_reset(self._h))

@@ -17,6 +17,7 @@
 
 #define ZZ_MAXFLIP 6     // accepted flips one coordinate may record per window (4-bit count field)
 #define ZZ_MAXITEMS 48   // timeline items (proposals + reschedules) per coordinate per window
+#define ZZ_MAXRANKS 8     // GPUs of one node
 #define ZZ_TAG_LIMIT 0x0f000000u  // iteration tags are rebased before they reach 2^28
 
 // neighbour entry flags
@@ -76,7 +77,26 @@ struct ZzView {
     uint64_t seed0, seed1;
     int32_t adapt;
     double factor;
+    // coordinate sharding across GPUs (one process per GPU): rank r owns the global ids [r*shard, (r+1)*shard).
+    // Every rank allocates full-length arrays and indexes them globally; a record is valid only in its owner's
+    // copy, reached through the peer mappings below (NVLink loads).  nranks == 1: the plain pointers above.
+    int32_t nranks, rank, shard;
+    int32_t lo, hi;                 // owned range
+    ZzKin* kin_peer[ZZ_MAXRANKS];
+    double* flips_peer[ZZ_MAXRANKS];
 };
+
+// where the authoritative record / flip lists of coordinate k live
+ZZ_HD const ZzKin* zz_kin_at(const ZzView& v, int32_t k)
+{
+    if (v.nranks > 1) return v.kin_peer[k / v.shard] + k;
+    return v.kin + k;
+}
+ZZ_HD const double* zz_flips_at(const ZzView& v, int32_t k)
+{
+    if (v.nranks > 1) return v.flips_peer[k / v.shard] + (size_t)k * 2 * ZZ_MAXFLIP;
+    return v.flips + (size_t)k * 2 * ZZ_MAXFLIP;
+}
 
 struct ZzNodeOut {
     double a, b, told, tau, c;
@@ -133,11 +153,11 @@ ZZ_HD void zz_nb_state(const ZzView& v, int32_t k, double s, int32_t key_idx, ui
                        double& x, double& th)
 {
     double tf, xf; uint32_t h0, h1;
-    zz_ld_kin(v.kin + k, th, tf, xf, h0, h1);
+    zz_ld_kin(zz_kin_at(v, k), th, tf, xf, h0, h1);
     int slot;
     uint32_t cnt = zz_pick_slot(h0, h1, w0, cur, slot);
     if (cnt) {
-        const double* fl = v.flips + ((size_t)k * 2 + slot) * ZZ_MAXFLIP;
+        const double* fl = zz_flips_at(v, k) + slot * ZZ_MAXFLIP;
         for (uint32_t m = 0; m < cnt; ++m) {
             double fs = zz_ld(fl + m);
             if (fs < s || (fs == s && k <= key_idx)) {
@@ -195,7 +215,7 @@ ZZ_HD void zz_next_trigger(const ZzGraph& g, const ZzView& v, int32_t j, double 
         if (!(g.nfl[e] & ZZ_NB_TRIG)) continue;
         int32_t k = g.nidx[e];
         if (k == j) continue;
-        const ZzKin* p = v.kin + k;
+        const ZzKin* p = zz_kin_at(v, k);
 #if defined(__CUDA_ARCH__)
         unsigned long long hh = (unsigned long long)__double_as_longlong(__ldcg(reinterpret_cast<const double*>(p) + 3));
         uint32_t h0 = (uint32_t)hh, h1 = (uint32_t)(hh >> 32);
@@ -205,7 +225,7 @@ ZZ_HD void zz_next_trigger(const ZzGraph& g, const ZzView& v, int32_t j, double 
         int slot;
         uint32_t cnt = zz_pick_slot(h0, h1, w0, cur, slot);
         if (!cnt) continue;
-        const double* fl = v.flips + ((size_t)k * 2 + slot) * ZZ_MAXFLIP;
+        const double* fl = zz_flips_at(v, k) + slot * ZZ_MAXFLIP;
         for (uint32_t m = 0; m < cnt; ++m) {
             double fs = zz_ld(fl + m);
             if (fs > last_t || (fs == last_t && k > last_i)) {

@@ -10,6 +10,17 @@ struct ZzEvent {  // memory layout of Tuple{Float64,Int64,Float64,Float64}, src/
     double t; long long i; double x; double theta;
 };
 
+// Message one GPU leaves in a peer's mailbox at every pass boundary (all-reduce by all-to-all stores over NVLink).
+struct ZzMsg {
+    unsigned long long sum;      // work-list appends issued / proposals committed (summed over ranks)
+    unsigned long long minkey;   // earliest-flip key (min over ranks)
+    unsigned int flags;          // ZZ_X_* (or-ed over ranks)
+    unsigned int pad;
+    unsigned long long epoch;    // written last; the receiver polls it
+};
+#define ZZ_X_OVERFLOW 1u
+#define ZZ_X_STOP 2u
+
 // Counters and persistent controller state; lives in device memory, zeroed by the host before the first launch.
 struct ZzDevCtl {
     unsigned long long bar;          // grid barrier arrival counter (monotone; zeroed by the host before each launch)
@@ -39,6 +50,11 @@ struct ZzDevCtl {
     // 4 waiting at grid barriers, 5 phase-B scans, 6 number of grid barriers, 7 number of tail passes
     unsigned long long tprof[8];
     unsigned long long dbg[8];       // development counters (ZZ_PROF_NODE builds)
+    // multi-GPU pass-boundary exchange
+    unsigned long long issued[3];    // appends issued by this rank into ANY rank's next work list, per list slot
+    unsigned long long xrelease;     // bumped by CTA 0 once the exchange of the current boundary is complete
+    ZzMsg xres[2];                   // reduced result of the exchange, by boundary parity
+    ZzMsg mbox[2][ZZ_MAXRANKS];      // incoming messages, by boundary parity and sender
 };
 
 struct ZzParams {
@@ -62,6 +78,11 @@ struct ZzParams {
     unsigned int max_windows;   // return to the host after this many committed windows (0 = run to the end)
     int32_t record_trace;
     int32_t pad;
+    // peer mappings (nranks > 1): who owns coordinate k also owns its stamp, its work-list slots and its counters
+    unsigned int* dstamp_peer[ZZ_MAXRANKS];
+    int32_t* wl_peer[3][ZZ_MAXRANKS];
+    int32_t* touched_peer[ZZ_MAXRANKS];
+    ZzDevCtl* ctl_peer[ZZ_MAXRANKS];
 };
 
 // order-preserving map double -> uint64 (so atomicMin works for any sign)

@@ -73,7 +73,7 @@ ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint
             int slot;
             const uint32_t cnt = zz_pick_slot(h0[m], h1[m], w0, cur, slot);
             if (cnt) {
-                const double* fl = v.flips + ((size_t)idx[m] * 2 + slot) * ZZ_MAXFLIP;
+                const double* fl = zz_flips_at(v, idx[m]) + slot * ZZ_MAXFLIP;
                 for (uint32_t q = 0; q < cnt; ++q) zz_pool_add(pool, zz_ld(fl + q), m, flags);
             }
         }
@@ -102,7 +102,7 @@ ZZ_HD bool zz_gather_csr(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t 
         h0[m] = 0; h1[m] = 0; hd.th[m] = 0.0; hd.tf[m] = 0.0; hd.xf[m] = 0.0;
         if (m < n) {
             if (idx[m] == j) hd.self = m;
-            else zz_ld_kin(v.kin + idx[m], hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
+            else zz_ld_kin(zz_kin_at(v, idx[m]), hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
         }
     }
     pool.n = 0;
@@ -135,7 +135,7 @@ ZZ_HD void zz_gather_grid(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t
     }
 #pragma unroll
     for (int m = 0; m < 5; ++m)
-        if (m < n && m != self) zz_ld_kin(v.kin + idx[m], hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
+        if (m < n && m != self) zz_ld_kin(zz_kin_at(v, idx[m]), hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
     pool.n = 0;
     ZZ_SEG(1);
     if (!first_iter) zz_gather_flips<5>(v, idx, h0, h1, n, self, w0, cur, pool, flags);

@@ -59,18 +59,89 @@ __device__ __forceinline__ void zz_grid_barrier(ZzDevCtl* C, unsigned long long&
     __syncthreads();
 }
 
+__device__ __forceinline__ unsigned long long zz_ld_acq_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void zz_st_rel_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+struct ZzXres { unsigned long long sum, minkey; unsigned int flags; };
+
+// Pass boundary: local grid barrier, then (MULTI) an all-reduce of (sum, min, or) across the GPUs of the node done by
+// CTA 0 with plain stores into the peers' mailboxes over NVLink; the other CTAs are released once the result is known.
+// The caller passes this rank's contributions as addresses inside the control block; they are read by CTA 0 after
+// every local CTA has arrived (so they are final).
+template <bool MULTI>
+__device__ __forceinline__ ZzXres zz_boundary(const ZzParams& P, unsigned long long& epoch, unsigned long long& xep,
+                                              unsigned long long* prof, const unsigned long long* psum,
+                                              const unsigned long long* pmin, const unsigned int* pflag_word,
+                                              unsigned int flag_mask, unsigned int flag_value)
+{
+    ZzDevCtl* C = P.ctl;
+    zz_grid_barrier(C, epoch, prof);
+    ZzXres r;
+    if (!MULTI) {
+        r.sum = psum ? __ldcg(psum) : 0ULL;
+        r.minkey = pmin ? __ldcg(pmin) : ~0ULL;
+        r.flags = (pflag_word && (__ldcg(pflag_word) & flag_mask)) ? flag_value : 0u;
+        return r;
+    }
+    xep += 1;
+    const int par = (int)(xep & 1ULL);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long t0 = prof ? zz_now() : 0ULL;
+        const unsigned long long ms = psum ? __ldcg(psum) : 0ULL;
+        const unsigned long long mk = pmin ? __ldcg(pmin) : ~0ULL;
+        const unsigned int mf = (pflag_word && (__ldcg(pflag_word) & flag_mask)) ? flag_value : 0u;
+        __threadfence_system();
+        for (int p = 0; p < P.v.nranks; ++p) {
+            ZzMsg* dst = &P.ctl_peer[p]->mbox[par][P.v.rank];
+            dst->sum = ms; dst->minkey = mk; dst->flags = mf;
+        }
+        __threadfence_system();
+        for (int p = 0; p < P.v.nranks; ++p) zz_st_rel_sys(&P.ctl_peer[p]->mbox[par][P.v.rank].epoch, xep);
+        unsigned long long s = 0ULL, k = ~0ULL; unsigned int f = 0u;
+        for (int p = 0; p < P.v.nranks; ++p) {
+            const ZzMsg* src = &C->mbox[par][p];
+            while (zz_ld_acq_sys(&src->epoch) < xep) { }
+            s += *(volatile const unsigned long long*)&src->sum;
+            const unsigned long long kk = *(volatile const unsigned long long*)&src->minkey;
+            k = kk < k ? kk : k;
+            f |= *(volatile const unsigned int*)&src->flags;
+        }
+        C->xres[par].sum = s; C->xres[par].minkey = k; C->xres[par].flags = f;
+        __threadfence();
+        atomicExch(&C->xrelease, xep);
+        if (prof) prof[5] += zz_now() - t0;
+    }
+    if (threadIdx.x == 0) {
+        while (zz_ld_acq(&C->xrelease) < xep) { }
+        __threadfence();
+    }
+    __syncthreads();
+    r.sum = __ldcg(&C->xres[par].sum); r.minkey = __ldcg(&C->xres[par].minkey); r.flags = __ldcg(&C->xres[par].flags);
+    return r;
+}
+
 // Append `val` to a global list; the active lanes of the warp share one atomic.
+template <bool MULTI>
 __device__ __forceinline__ void zz_append(int32_t* list, unsigned int* cnt, int32_t val)
 {
     cg::coalesced_group cgp = cg::coalesced_threads();
     unsigned int base = 0;
-    if (cgp.thread_rank() == 0) base = atomicAdd(cnt, cgp.size());
+    if (cgp.thread_rank() == 0) base = MULTI ? atomicAdd_system(cnt, cgp.size()) : atomicAdd(cnt, cgp.size());
     base = cgp.shfl(base, 0);
     list[(base & ~ZZ_OVF_BIT) + cgp.thread_rank()] = val;
 }
 
 // Up to four candidates per lane: those whose stamp was older than `tagn` go to the next work list, those older
 // than `w0` (first touch in this window) also to the touched list.  One atomicAdd per list for the active lanes.
+template <bool MULTI>
 __device__ __forceinline__ void zz_append4(int32_t* wl, unsigned int* wl_cnt, int32_t* tl, unsigned int* tl_cnt,
                                            const int32_t (&kk)[4], const uint32_t (&old)[4], uint32_t tagn, uint32_t w0)
 {
@@ -83,8 +154,8 @@ __device__ __forceinline__ void zz_append4(int32_t* wl, unsigned int* wl_cnt, in
     unsigned int ba = 0, bt = 0;
     const unsigned int last = cgp.size() - 1;
     if (cgp.thread_rank() == last) {
-        if (pa + na) ba = atomicAdd(wl_cnt, pa + na);
-        if (pt + nt) bt = atomicAdd(tl_cnt, pt + nt);
+        if (pa + na) ba = MULTI ? atomicAdd_system(wl_cnt, pa + na) : atomicAdd(wl_cnt, pa + na);
+        if (pt + nt) bt = MULTI ? atomicAdd_system(tl_cnt, pt + nt) : atomicAdd(tl_cnt, pt + nt);
     }
     ba = (cgp.shfl(ba, last) & ~ZZ_OVF_BIT) + pa;
     bt = cgp.shfl(bt, last) + pt;
@@ -120,7 +191,48 @@ __device__ __forceinline__ ZzSpecR zz_load_spec(const ZzSpec* p)
 
 // Publish the result of one timeline evaluation: if the list of accepted flips differs from the one the
 // readers of this pass see, write it into the other slot and queue every coordinate that reads j.
-template <int KIND>
+// Stamp up to four readers of a changed coordinate and queue those that were not queued yet.  MULTI: a reader owned
+// by another GPU is stamped and queued in its owner's memory with system-scope atomics over NVLink.
+template <bool MULTI>
+__device__ __forceinline__ void zz_mark4(const ZzParams& P, const int32_t (&kk)[4], uint32_t tagn, uint32_t w0, int nxt, int ws)
+{
+    ZzDevCtl* C = P.ctl;
+    uint32_t old[4];
+    if (!MULTI) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) old[q] = (kk[q] >= 0) ? atomicMax(P.dstamp + kk[q], tagn) : 0xffffffffu;
+        zz_append4<false>(P.wl[nxt], &C->wl_cnt[nxt], P.touched[0], &C->touched_cnt[ws], kk, old, tagn, w0);
+        return;
+    }
+    int32_t kl[4]; uint32_t ol[4];
+    unsigned int issued = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        kl[q] = -1; ol[q] = 0xffffffffu;
+        if (kk[q] < 0) continue;
+        const int o = kk[q] / P.v.shard;
+        if (o == P.v.rank) {
+            kl[q] = kk[q];
+            ol[q] = atomicMax_system(P.dstamp + kk[q], tagn);
+            issued += (ol[q] < tagn) ? 1u : 0u;
+        } else {
+            const uint32_t od = atomicMax_system(P.dstamp_peer[o] + kk[q], tagn);
+            if (od < tagn) {
+                const unsigned int pos = atomicAdd_system(&P.ctl_peer[o]->wl_cnt[nxt], 1u) & ~ZZ_OVF_BIT;
+                P.wl_peer[nxt][o][pos] = kk[q];
+                issued += 1u;
+                if (od < w0) {
+                    const unsigned int pt = atomicAdd_system(&P.ctl_peer[o]->touched_cnt[ws], 1u);
+                    P.touched_peer[o][pt] = kk[q];
+                }
+            }
+        }
+    }
+    zz_append4<true>(P.wl[nxt], &C->wl_cnt[nxt], P.touched[0], &C->touched_cnt[ws], kl, ol, tagn, w0);
+    if (issued) atomicAdd(&C->issued[nxt], (unsigned long long)issued);
+}
+
+template <int KIND, bool MULTI>
 __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const ZzNodeOut& o, uint32_t w0,
                                            uint32_t cur, int nxt, int ws)
 {
@@ -143,28 +255,24 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
         reinterpret_cast<uint32_t*>(P.v.kin + j)[6 + wsl] = (cur << 4) | o.nflip;
         const uint32_t tagn = cur + 1;
         // queue the readers of j: all stamp updates are issued back to back (independent atomics in flight), then
-        // the appends of the whole warp share one atomicAdd per list (zz_append2)
+        // the appends of the whole warp share one atomicAdd per list (zz_append4)
         if (KIND == ZZ_KIND_GRID) {
             const int32_t M = P.g.grid_m, N = P.g.grid_n;
             const int32_t col = j / M, row = j - col * M;
-            int32_t kk[4]; uint32_t old[4];
+            int32_t kk[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const bool ok = (q == 0) ? (col > 0) : (q == 1) ? (row > 0) : (q == 2) ? (row < M - 1) : (col < N - 1);
                 kk[q] = ok ? j + ((q == 0) ? -M : (q == 1) ? -1 : (q == 2) ? 1 : M) : -1;
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) old[q] = (kk[q] >= 0) ? atomicMax(P.dstamp + kk[q], tagn) : 0xffffffffu;
-            zz_append4(P.wl[nxt], &C->wl_cnt[nxt], P.touched[0], &C->touched_cnt[ws], kk, old, tagn, w0);
+            zz_mark4<MULTI>(P, kk, tagn, w0, nxt, ws);
         } else {
             const int32_t q1 = P.dptr[j + 1];
             for (int32_t q0 = P.dptr[j]; q0 < q1; q0 += 4) {
-                int32_t kk[4]; uint32_t old[4];
+                int32_t kk[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) kk[q] = (q0 + q < q1) ? P.didx[q0 + q] : -1;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) old[q] = (kk[q] >= 0) ? atomicMax(P.dstamp + kk[q], tagn) : 0xffffffffu;
-                zz_append4(P.wl[nxt], &C->wl_cnt[nxt], P.touched[0], &C->touched_cnt[ws], kk, old, tagn, w0);
+                zz_mark4<MULTI>(P, kk, tagn, w0, nxt, ws);
             }
         }
     }
@@ -178,7 +286,7 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
 
 // One timeline evaluation + publication; kept out of line so the three call sites (scan pass, relaxation pass,
 // tail pass) share one copy of the code and its register allocation.
-template <int KIND>
+template <int KIND, bool MULTI>
 __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, double H, int incl, uint32_t w0,
                                              uint32_t cur, bool first, int nxt, int ws)
 {
@@ -187,7 +295,7 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
     const long long c0 = clock64();
     zz_process_node_k<KIND>(P.g, P.v, j, H, incl, w0, cur, first, o);
     const long long c1 = clock64();
-    zz_publish<KIND>(P, j, o, w0, cur, nxt, ws);
+    zz_publish<KIND, MULTI>(P, j, o, w0, cur, nxt, ws);
     const long long c2 = clock64();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.ctl->dbg[0] += (unsigned long long)(c2 - c1);   // cycles in publication
@@ -195,7 +303,7 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
     }
 #else
     zz_process_node_k<KIND>(P.g, P.v, j, H, incl, w0, cur, first, o);
-    zz_publish<KIND>(P, j, o, w0, cur, nxt, ws);
+    zz_publish<KIND, MULTI>(P, j, o, w0, cur, nxt, ws);
 #endif
 }
 
@@ -274,10 +382,11 @@ zz_setup_kernel(const ZzParams P, const double* __restrict__ x0, const double* _
 
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel(const ZzParams P)
 {
+    ZzView vloc = P.v; vloc.nranks = 1;   // every rank initialises all coordinates from its own (identical) copies
     unsigned long long kmin = ~0ULL;
     for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < P.v.d; j += gridDim.x * blockDim.x) {
-        zz_init_node(P.g, P.v, j, P.t0);
-        const unsigned long long k = zz_key(P.v.tau[j]);
+        zz_init_node(P.g, vloc, j, P.t0);
+        const unsigned long long k = zz_key(vloc.tau[j]);
         kmin = k < kmin ? k : kmin;
     }
     cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
@@ -295,7 +404,7 @@ zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ 
     }
 }
 
-template <int KIND>
+template <int KIND, bool MULTI>
 __device__ __forceinline__ void zz_run_body(const ZzParams& P)
 {
     ZzDevCtl* C = P.ctl;
@@ -309,11 +418,12 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
     const unsigned int nthreads = gridDim.x * blockDim.x;
     const unsigned int gwarp = gtid >> 5, nwarps = nthreads >> 5;
     const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
-    const int32_t d = P.v.d;
+    const int32_t lo = MULTI ? P.v.lo : 0, hi = MULTI ? P.v.hi : P.v.d;   // owned coordinates
     unsigned long long epoch = 0;
+    unsigned long long xep = MULTI ? __ldcg(&C->xrelease) : 0ULL;        // cross-GPU boundary counter (persists)
 
-    // every thread keeps an identical copy of the controller; decisions only depend on values that are
-    // stable between two grid barriers
+    // every thread of every GPU keeps an identical copy of the controller; decisions only depend on values that are
+    // stable between two boundaries (and, MULTI, reduced over all GPUs)
     ZzCtl ctl; uint32_t cur, li, wat;
     if (__ldcg(&C->started)) {
         ctl = C->ctl; cur = C->cur; li = C->itg; wat = C->wattempt;
@@ -334,11 +444,11 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
 
     while (ctl.phase < ZZ_PH_DONE && !stop) {
         if (cur > P.tag_limit) {  // iteration tags are about to run out of bits: forget all of them
-            for (int32_t j = gtid; j < d; j += nthreads) {
+            for (int32_t j = lo + (int32_t)gtid; j < hi; j += nthreads) {
                 reinterpret_cast<unsigned long long*>(P.v.kin + j)[3] = 0ULL;
                 P.dstamp[j] = 0;
             }
-            zz_grid_barrier(C, epoch, prof);
+            zz_boundary<MULTI>(P, epoch, xep, prof, nullptr, nullptr, nullptr, 0u, 0u);
             cur = 0; st_rebases++;
         }
         const ZzCtl saved = ctl;
@@ -349,21 +459,21 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
         wat++;
         const double H = ctl.H; const int incl = ctl.incl;
 
-        // ---------------- pass 1: scan + evaluate every coordinate with a proposal inside the window
+        // ---------------- pass 1: scan + evaluate every owned coordinate with a proposal inside the window
         int nxt = (int)((li + 1) % 3u);
         ZZ_TIC();
         if (leader) {
-            C->wl_cnt[(li + 2) % 3u] = 0;
+            C->wl_cnt[(li + 2) % 3u] = 0; C->issued[(li + 2) % 3u] = 0;
             const int wz = (int)(wat % 3u);  // slot of the NEXT attempt
             C->touched_cnt[wz] = 0; C->smin_key[wz] = ~0ULL; C->nprop_win[wz] = 0;
         }
-        for (int32_t base = gwarp * (32 * ZZ_SCAN_U); base < d; base += nwarps * (32 * ZZ_SCAN_U)) {
+        for (int32_t base = lo + (int32_t)gwarp * (32 * ZZ_SCAN_U); base < hi; base += nwarps * (32 * ZZ_SCAN_U)) {
             int qn = 0;
 #pragma unroll
             for (int u = 0; u < ZZ_SCAN_U; ++u) {
                 const int32_t j = base + u * 32 + lane;
                 bool act = false;
-                if (j < d) { const double tj = __ldcg(P.v.tau + j); act = (tj < H) || (incl && tj == H); }
+                if (j < hi) { const double tj = __ldcg(P.v.tau + j); act = (tj < H) || (incl && tj == H); }
                 const unsigned int m = __ballot_sync(0xffffffffu, act);
                 if (act) sq[warp][qn + __popc(m & ((1u << lane) - 1u))] = j;
                 qn += __popc(m);
@@ -371,24 +481,27 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             __syncwarp();
             for (int q = lane; q < qn; q += 32) {
                 const int32_t j = sq[warp][q];
-                const uint32_t old = atomicMax(P.dstamp + j, cur);
-                if (old < w0) zz_append(P.touched[0], &C->touched_cnt[ws], j);
-                zz_eval_publish<KIND>(P, j, H, incl, w0, cur, true, nxt, ws);
+                const uint32_t old = MULTI ? atomicMax_system(P.dstamp + j, cur) : atomicMax(P.dstamp + j, cur);
+                if (old < w0) zz_append<MULTI>(P.touched[0], &C->touched_cnt[ws], j);
+                zz_eval_publish<KIND, MULTI>(P, j, H, incl, w0, cur, true, nxt, ws);
                 st_evals++;
             }
             __syncwarp();
         }
         ZZ_TOC(0);
-        zz_grid_barrier(C, epoch, prof);
+        ZzXres xr = zz_boundary<MULTI>(P, epoch, xep, prof, MULTI ? &C->issued[nxt] : nullptr, nullptr, &C->wl_cnt[nxt],
+                                       ZZ_OVF_BIT, ZZ_X_OVERFLOW);
         st_iters++;
 
         // ---------------- relaxation passes
         bool overflow = false;
         for (;;) {
-            const unsigned int cw = __ldcg(&C->wl_cnt[nxt]);
-            if (cw & ZZ_OVF_BIT) { overflow = true; li = (li + 1) % 3u; break; }
-            if (cw == 0) break;
-            if (cw <= ZZ_TAIL) {
+            const unsigned int cwl = __ldcg(&C->wl_cnt[nxt]);            // this GPU's share of the next list
+            const unsigned int cw = cwl & ~ZZ_OVF_BIT;
+            const unsigned long long total = MULTI ? xr.sum : (unsigned long long)cw;
+            if (xr.flags & ZZ_X_OVERFLOW) { overflow = true; li = (li + 1) % 3u; break; }
+            if (total == 0) break;
+            if (!MULTI && cw <= ZZ_TAIL) {
                 // Few coordinates left (typically a couple of hot neighbours resolving a long causal chain one
                 // event per pass): CTA 0 runs these passes alone with block barriers; the others wait once.
                 if (blockIdx.x == 0) {
@@ -402,7 +515,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                         const int32_t* wlt = P.wl[li];
                         for (unsigned int e = threadIdx.x; e < n; e += blockDim.x) {
                             const int32_t j = __ldcg(wlt + e);
-                            zz_eval_publish<KIND>(P, j, H, incl, w0, cur, false, nxt, ws);
+                            zz_eval_publish<KIND, MULTI>(P, j, H, incl, w0, cur, false, nxt, ws);
                             st_evals++;
                         }
                         __threadfence();
@@ -418,21 +531,23 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                 zz_grid_barrier(C, epoch, prof);
                 li = __ldcg(&C->tail_li); cur = __ldcg(&C->tail_cur);
                 nxt = (int)((li + 1) % 3u);
+                xr.flags = (__ldcg(&C->wl_cnt[nxt]) & ZZ_OVF_BIT) ? ZZ_X_OVERFLOW : 0u;
                 continue;
             }
             li = (li + 1) % 3u;
             nxt = (int)((li + 1) % 3u);
             cur++;
             ZZ_TIC();
-            if (leader) C->wl_cnt[(li + 2) % 3u] = 0;
+            if (leader) { C->wl_cnt[(li + 2) % 3u] = 0; C->issued[(li + 2) % 3u] = 0; }
             const int32_t* wl = P.wl[li];
             for (unsigned int e = gtid; e < cw; e += nthreads) {
                 const int32_t j = __ldcg(wl + e);
-                zz_eval_publish<KIND>(P, j, H, incl, w0, cur, false, nxt, ws);
+                zz_eval_publish<KIND, MULTI>(P, j, H, incl, w0, cur, false, nxt, ws);
                 st_evals++;
             }
             ZZ_TOC(1);
-            zz_grid_barrier(C, epoch, prof);
+            xr = zz_boundary<MULTI>(P, epoch, xep, prof, MULTI ? &C->issued[nxt] : nullptr, nullptr, &C->wl_cnt[nxt],
+                                    ZZ_OVF_BIT, ZZ_X_OVERFLOW);
             st_iters++;
         }
         cur++;  // tag of the commit pass: every list written in this window is visible to it
@@ -457,14 +572,13 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             }
             if (kmin != ~0ULL) atomicMin(&C->smin_key[ws], kmin);
             ZZ_TOC(5);
-            zz_grid_barrier(C, epoch, prof);
-            const unsigned long long kk = __ldcg(&C->smin_key[ws]);
-            if (kk != ~0ULL) smin = zz_unkey(kk);
+            const ZzXres xb = zz_boundary<MULTI>(P, epoch, xep, prof, nullptr, &C->smin_key[ws], nullptr, 0u, 0u);
+            if (xb.minkey != ~0ULL) smin = zz_unkey(xb.minkey);
         }
 
         ZzCtl trial = ctl;
         const int act = zz_ctl_end(trial, overflow, smin, nprop_prev);
-        if (act == ZZ_ACT_COMMIT && P.record_trace) {
+        if (!MULTI && act == ZZ_ACT_COMMIT && P.record_trace) {
             // every event of this window (plus its end marker) must fit; otherwise hand the buffer to the host first
             const unsigned long long tl = __ldcg(&C->trace_len);
             const unsigned long long need = (unsigned long long)__ldcg(&C->touched_cnt[ws]) * ZZ_MAXFLIP + 1ULL;
@@ -492,16 +606,21 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                 atomicAdd(&C->nacc, (unsigned long long)nf);
             }
             ZZ_TOC(3);
-            zz_grid_barrier(C, epoch, prof);
+            // stop word: bound violation or (defensive) dropped trace record on ANY GPU stops all of them
+            const ZzXres xc = zz_boundary<MULTI>(P, epoch, xep, prof, &C->nprop_win[ws], nullptr, &C->viol, 0xffffffffu, ZZ_X_STOP);
             if (leader && P.record_trace) {  // window-end marker (i = 0): lets the host sort window by window
                 const unsigned long long pos = atomicAdd(&C->trace_len, 1ULL);
-                double2* e = reinterpret_cast<double2*>(P.trace + pos);
-                e[0] = make_double2(H, __longlong_as_double(0LL));
-                e[1] = make_double2(0.0, 0.0);
+                if (pos < P.trace_cap) {
+                    double2* e = reinterpret_cast<double2*>(P.trace + pos);
+                    e[0] = make_double2(H, __longlong_as_double(0LL));
+                    e[1] = make_double2(0.0, 0.0);
+                } else {
+                    C->trace_full = 1u;
+                }
             }
-            nprop_prev = __ldcg(&C->nprop_win[ws]);
+            nprop_prev = xc.sum;
             windows_done++;
-            if (__ldcg(&C->viol) || __ldcg(&C->trace_full)) stop = true;
+            if (xc.flags & ZZ_X_STOP) stop = true;
             if (P.max_windows && windows_done >= P.max_windows) stop = true;
         } else {
             st_retries++;
@@ -518,5 +637,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
     if (lane == 0 && st_evals) atomicAdd(&C->node_evals, st_evals);
 }
 
-extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_grid(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_GRID>(P); }
-extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_csr(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_CSR>(P); }
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_grid(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_GRID, false>(P); }
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_csr(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_CSR, false>(P); }
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_grid_multi(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_GRID, true>(P); }
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_csr_multi(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_CSR, true>(P); }

@@ -44,7 +44,8 @@ static int32_t fail(int32_t code, const char* fmt, ...)
     X(cuMemcpyDtoH) X(cuMemcpyHtoDAsync) X(cuMemcpyDtoHAsync) X(cuMemsetD8) X(cuMemsetD8Async) X(cuStreamCreate) \
     X(cuStreamDestroy) X(cuStreamSynchronize) X(cuLaunchKernel) X(cuLaunchCooperativeKernel) X(cuEventCreate) \
     X(cuEventDestroy) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) X(cuGetErrorString) \
-    X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemFreeHost)
+    X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemFreeHost) \
+    X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle)
 
 struct Drv {
 #define X(name) decltype(&name) p_##name = nullptr;
@@ -87,10 +88,10 @@ struct Global {
     CUdevice dev = 0; int dev_id = 0;
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
-    CUfunction f_setup = nullptr, f_init = nullptr, f_run[2] = { nullptr, nullptr }, f_export = nullptr;
+    CUfunction f_setup = nullptr, f_init = nullptr, f_run[4] = { nullptr, nullptr, nullptr, nullptr }, f_export = nullptr;
     CUstream stream = nullptr;
     CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
-    int sm_count = 0; int blocks_per_sm[2] = { 0, 0 };
+    int sm_count = 0; int blocks_per_sm[4] = { 0, 0, 0, 0 };
     size_t total_mem = 0; char name[128] = { 0 };
 };
 static Global G;
@@ -157,6 +158,7 @@ struct zzb_run_s {
     unsigned long long trace_cap = 0;
     ZzParams P;
     double t0 = 0, T = 0;
+    uint64_t seed[2] = { 0, 0 }; int32_t adapt = 0; double factor = 1.8;
     double delta0 = 0, target_frac = 0.4; unsigned int tag_limit = ZZ_TAG_LIMIT; unsigned int max_windows = 0;
     bool uploaded = false, executed = false, have_inputs = false;
     // results
@@ -164,6 +166,9 @@ struct zzb_run_s {
     ZzDevCtl hc;                       // last copy of the device control block
     int64_t launches = 0;
     int grid = 0; int kind = 1;
+    int rank = 0, nranks = 1, shard = 0, lo = 0, hi = 0;
+    CUdeviceptr peer[ZZ_MAXRANKS][8] = {};   // imported mappings: kin, flips, dstamp, wl0, wl1, wl2, touched, ctl
+    bool peer_open[ZZ_MAXRANKS] = {};
     bool fetched = false;
     std::vector<double> ft, fx, fth, fc; std::vector<long long> facc; std::vector<double> hs1, hs2;
 };
@@ -216,13 +221,15 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     CU(cuModuleGetFunction(&G.f_init, G.mod, "zz_init_kernel"));
     CU(cuModuleGetFunction(&G.f_run[0], G.mod, "zz_run_kernel_grid"));
     CU(cuModuleGetFunction(&G.f_run[1], G.mod, "zz_run_kernel_csr"));
+    CU(cuModuleGetFunction(&G.f_run[2], G.mod, "zz_run_kernel_grid_multi"));
+    CU(cuModuleGetFunction(&G.f_run[3], G.mod, "zz_run_kernel_csr_multi"));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuStreamCreate(&G.stream, CU_STREAM_NON_BLOCKING));
     CU(cuEventCreate(&G.ev0, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.ev1, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.tev0, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.tev1, CU_EVENT_DEFAULT));
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 4; ++k) {
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm[k], G.f_run[k], ZZ_BLOCK, 0));
         if (G.blocks_per_sm[k] < 1) return fail(ZZB_E_CUDA, "zz_run_kernel does not fit on an SM");
     }
@@ -343,6 +350,7 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     if (st) { delete r; return st == ZZB_E_CUDA ? ZZB_E_NOMEM : st; }
     r->kind = p->g.grid_m ? 0 : 1;
     r->grid = G.sm_count * G.blocks_per_sm[r->kind];
+    r->shard = r->d; r->hi = r->d;
     *out = r;
     return ZZB_OK;
 }
@@ -362,6 +370,79 @@ static void fill_params(zzb_run_s* r)
     P.trace = r->trace.as<ZzEvent>(); P.trace_cap = r->trace_cap;
     P.ctl = r->ctl.as<ZzDevCtl>();
     P.record_trace = (r->flags & ZZB_FLAG_NO_TRACE) ? 0 : 1;
+    P.v.nranks = r->nranks; P.v.rank = r->rank; P.v.shard = r->shard; P.v.lo = r->lo; P.v.hi = r->hi;
+    if (r->nranks > 1) {
+        for (int q = 0; q < r->nranks; ++q) {
+            const bool me = (q == r->rank);
+            P.v.kin_peer[q] = me ? P.v.kin : reinterpret_cast<ZzKin*>(r->peer[q][0]);
+            P.v.flips_peer[q] = me ? P.v.flips : reinterpret_cast<double*>(r->peer[q][1]);
+            P.dstamp_peer[q] = me ? P.dstamp : reinterpret_cast<unsigned int*>(r->peer[q][2]);
+            for (int k = 0; k < 3; ++k) P.wl_peer[k][q] = me ? P.wl[k] : reinterpret_cast<int32_t*>(r->peer[q][3 + k]);
+            P.touched_peer[q] = me ? P.touched[0] : reinterpret_cast<int32_t*>(r->peer[q][6]);
+            P.ctl_peer[q] = me ? P.ctl : reinterpret_cast<ZzDevCtl*>(r->peer[q][7]);
+        }
+    }
+}
+
+static CUdeviceptr shared_buf(zzb_run_s* r, int k)
+{
+    switch (k) {
+    case 0: return r->kin.p; case 1: return r->flips.p; case 2: return r->dstamp.p;
+    case 3: return r->wl[0].p; case 4: return r->wl[1].p; case 5: return r->wl[2].p;
+    case 6: return r->touched.p; default: return r->ctl.p;
+    }
+}
+
+// ---- coordinate sharding across the GPUs of one node (one process per GPU) ----------------
+// Rank `rank` of `nranks` owns the global coordinates [rank*shard, (rank+1)*shard); on the lattice the shard is a
+// whole number of lattice columns.  Call before zzb_run_upload.
+int32_t zzb_run_shard(zzb_run_t r, int32_t rank, int32_t nranks)
+{
+    if (!r) return fail(ZZB_E_ARG, "null argument");
+    if (nranks < 1 || nranks > ZZ_MAXRANKS || rank < 0 || rank >= nranks) return fail(ZZB_E_ARG, "bad rank %d of %d", rank, nranks);
+    const int64_t d = r->d;
+    int64_t shard = (d + nranks - 1) / nranks;
+    const int64_t m = r->prob->g.grid_m;
+    if (m) shard = ((shard + m - 1) / m) * m;
+    r->rank = rank; r->nranks = nranks; r->shard = (int)shard;
+    r->lo = (int)std::min<int64_t>(d, shard * rank);
+    r->hi = (int)std::min<int64_t>(d, shard * (rank + 1));
+    r->grid = G.sm_count * G.blocks_per_sm[r->kind + (nranks > 1 ? 2 : 0)];
+    return ZZB_OK;
+}
+
+// 8 IPC handles (kin, flips, dstamp, three work lists, touched list, control block) of this rank's allocations.
+int32_t zzb_run_ipc_export(zzb_run_t r, void* buf, int64_t cap, int64_t* len)
+{
+    if (!r || !buf || !len) return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    const int64_t need = 8 * (int64_t)sizeof(CUipcMemHandle);
+    if (cap < need) return fail(ZZB_E_ARG, "buffer too small (%lld < %lld)", (long long)cap, (long long)need);
+    CtxGuard cg;
+    CUipcMemHandle* h = reinterpret_cast<CUipcMemHandle*>(buf);
+    for (int k = 0; k < 8; ++k) CU(cuIpcGetMemHandle(&h[k], shared_buf(r, k)));
+    *len = need;
+    return ZZB_OK;
+}
+
+int32_t zzb_run_ipc_import(zzb_run_t r, int32_t peer_rank, const void* buf, int64_t len)
+{
+    if (!r || !buf) return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (peer_rank < 0 || peer_rank >= r->nranks || peer_rank == r->rank) return fail(ZZB_E_ARG, "bad peer rank %d", peer_rank);
+    if (len < 8 * (int64_t)sizeof(CUipcMemHandle)) return fail(ZZB_E_ARG, "short handle buffer");
+    CtxGuard cg;
+    const CUipcMemHandle* h = reinterpret_cast<const CUipcMemHandle*>(buf);
+    for (int k = 0; k < 8; ++k) CU(cuIpcOpenMemHandle(&r->peer[peer_rank][k], h[k], CU_IPC_MEM_LAZY_ENABLE_PEER_ACCESS));
+    r->peer_open[peer_rank] = true;
+    return ZZB_OK;
+}
+
+int32_t zzb_run_range(zzb_run_t r, int64_t* lo, int64_t* hi)
+{
+    if (!r || !lo || !hi) return fail(ZZB_E_ARG, "null argument");
+    *lo = r->lo; *hi = r->hi;
+    return ZZB_OK;
 }
 
 int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
@@ -371,7 +452,7 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     else if (!strcmp(key, "target_frac")) r->target_frac = value;
     else if (!strcmp(key, "tag_limit")) r->tag_limit = (unsigned int)value;
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
-    else if (!strcmp(key, "grid")) r->grid = std::max(1, std::min((int)value, G.sm_count * G.blocks_per_sm[r->kind]));
+    else if (!strcmp(key, "grid")) r->grid = std::max(1, std::min((int)value, G.sm_count * G.blocks_per_sm[r->kind + (r->nranks > 1 ? 2 : 0)]));
     else return fail(ZZB_E_ARG, "unknown tuning key %s", key);
     return ZZB_OK;
 }
@@ -383,6 +464,10 @@ int32_t zzb_run_reset(zzb_run_t r)
     if (!r) return fail(ZZB_E_ARG, "null argument");
     if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
     if (!r->have_inputs) return fail(ZZB_E_ARG, "zzb_run_upload must precede zzb_run_reset");
+    for (int q = 0; q < r->nranks; ++q)
+        if (q != r->rank && !r->peer_open[q]) return fail(ZZB_E_ARG, "peer %d of a sharded run has not been imported", q);
+    fill_params(r);
+    r->P.v.seed0 = r->seed[0]; r->P.v.seed1 = r->seed[1]; r->P.v.adapt = r->adapt; r->P.v.factor = r->factor; r->P.t0 = r->t0;
     CtxGuard cg;
     ZzParams& P = r->P;
     ZzDevCtl hc; memset(&hc, 0, sizeof hc);
@@ -409,9 +494,7 @@ int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* t
     {
         CtxGuard cg;
         const size_t nb = (size_t)r->d * 8;
-        fill_params(r);
-        ZzParams& P = r->P;
-        P.v.seed0 = seed[0]; P.v.seed1 = seed[1]; P.v.adapt = adapt; P.v.factor = factor; P.t0 = t0;
+        r->seed[0] = seed[0]; r->seed[1] = seed[1]; r->adapt = adapt; r->factor = factor;
         r->t0 = t0;
         CU(cuMemcpyHtoDAsync(r->in_x.p, x0, nb, G.stream));
         CU(cuMemcpyHtoDAsync(r->in_th.p, theta0, nb, G.stream));
@@ -462,7 +545,7 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
         CU(cuMemsetD8Async(r->ctl.p, 0, 8, G.stream));  // barrier counter
         void* args[] = { &P };
         CU(cuEventRecord(G.ev0, G.stream));
-        CU(cuLaunchCooperativeKernel(G.f_run[r->kind], (unsigned)r->grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, args));
+        CU(cuLaunchCooperativeKernel(G.f_run[r->kind + (r->nranks > 1 ? 2 : 0)], (unsigned)r->grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, args));
         CU(cuEventRecord(G.ev1, G.stream));
         CU(cuStreamSynchronize(G.stream));
         r->launches++;
@@ -640,6 +723,8 @@ int32_t zzb_run_free(zzb_run_t r)
 {
     if (!r) return ZZB_OK;
     CtxGuard cg;
+    for (int q = 0; q < ZZ_MAXRANKS; ++q)
+        if (r->peer_open[q]) for (int k = 0; k < 8; ++k) if (r->peer[q][k]) g_drv.p_cuIpcCloseMemHandle(r->peer[q][k]);
     delete r;
     return ZZB_OK;
 }
