@@ -15,6 +15,8 @@
  *   zzb_run_final_state           the returned (t, x, theta) and the adapted c                   src/sfact.jl:211
  *   zzb_trace_len / _copy         the returned FactTrace's `events` vector                       src/trace.jl:7-13,38
  *   zzb_trace_moments             Statistics.mean(::Trace) (src/trace.jl:182-200) + matching exact second moment
+ *   flag ZZB_FLAG_LOCAL_BOUND     the LocalBound methods: ab src/local.jl:2-6, spdmp_inner! :10-78, spdmp/pdmp :95-149,
+ *                                 next_time src/not_fact_samplers.jl:43-50
  *   status ZZB_E_BOUND            error("Tuning parameter `c` too small.")                       src/sfact.jl:124
  *
  * Ownership: the caller owns every host array and keeps it alive for the duration of the call; the library owns all
@@ -43,6 +45,8 @@ extern "C" {
 
 /* flags of zzb_spdmp_run / zzb_run_create */
 #define ZZB_FLAG_NO_TRACE 1u   /* do not record events; counters, final state and moment sums are still produced */
+#define ZZB_FLAG_LOCAL_BOUND 2u /* spdmp(..., C::LocalBound, ...) of src/local.jl:95-149: bounds from the target's own first and
+                                   second directional derivatives, valid for 2/c/|theta|, then renewed (problem: bnd_* = NULL) */
 
 typedef struct zzb_problem_s* zzb_problem_t;
 typedef struct zzb_run_s* zzb_run_t;

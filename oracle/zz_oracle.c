@@ -38,7 +38,11 @@
  *          2 = "lazy": positions are anchored at the coordinate's own last flip,
  *              x_j(s) = xf_j + th_j (s - tf_j); only the owner ever rewrites them.
  *   GRAPH  4 = All() neighbourhood (pdmp, sfact.jl:236) instead of Matched().
- * GPU results must equal mode ctr|lazy bit for bit.
+ *   BOUND  8 = LocalBound variant (src/local.jl:2-6,10-78,95-149; next_time: src/not_fact_samplers.jl:43-50): the
+ *              bound comes from the target's own first and second directional derivatives, expires after
+ *              Delta = 2/c/|theta| and is then renewed.  The target descriptor plays the role of the extended-form
+ *              closure: (grad phi_i, v_i) = (idot(G,i,x) - h_i, theta_i idot(G,i,theta)) (local.jl:7).
+ * GPU results must equal mode ctr|lazy (|8) bit for bit.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -50,6 +54,7 @@
 #define ZZO_RNG_CTR 1
 #define ZZO_ARITH_LAZY 2
 #define ZZO_GRAPH_ALL 4
+#define ZZO_LOCAL_BOUND 8 /* spdmp(..., C::LocalBound, ...) of src/local.jl:95-149 */
 
 #define ZZO_OK 0
 #define ZZO_E_BOUND 3 /* "Tuning parameter `c` too small." sfact.jl:124 */
@@ -294,6 +299,26 @@ static void build_g2(ctx *z)
     free(mark);
 }
 
+/* ab(G,i,x,th,C::LocalBound,grad_i,v_i,Z::ZigZag), src/local.jl:2-6; returns Delta */
+static double ab_local(ctx *z, int64_t i, double s)
+{
+    double gi = idot_x(z, &z->tg, i, s);
+    if (z->h) gi = gi - z->h[i - 1];
+    double vi = idot(&z->tg, i, z->th) * z->th[i - 1];
+    z->ba[i - 1] = z->c[i - 1] + gi * z->th[i - 1];
+    z->bb[i - 1] = z->c[i - 1] / 100 + vi;
+    return 2.0 / z->c[i - 1] / fabs(z->th[i - 1]);
+}
+
+/* next_time(t, abc, z), src/not_fact_samplers.jl:43-50 */
+static double next_time(double t, double a, double b, double Delta, double u, char *renew)
+{
+    double dt = o_poisson_time(a, b, u);
+    if (dt > Delta) { *renew = 1; return t + Delta; }
+    *renew = 0;
+    return t + dt;
+}
+
 zzo_run *zzo_spdmp(int64_t d,
                    const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
                    const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
@@ -329,9 +354,19 @@ zzo_run *zzo_spdmp(int64_t d,
     Q.key = (int64_t *)malloc(((size_t)d + 2) * sizeof(int64_t));
     Q.val = (double *)malloc(((size_t)d + 2) * sizeof(double));
     Q.index = (int64_t *)malloc(((size_t)d + 2) * sizeof(int64_t));
-    /* sfact.jl:184-187: bounds, then the queue is filled in coordinate order, NO "+ t0" */
-    for (int64_t i = 1; i <= d; ++i) ab_zigzag(z, i, t0);
-    for (int64_t i = 1; i <= d; ++i) h_enqueue(&Q, i, o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i)));
+    const int lbnd = (mode & ZZO_LOCAL_BOUND) != 0;
+    char *renew = (char *)calloc((size_t)d, 1);
+    if (lbnd) {
+        /* local.jl:118-123: bound and first time per coordinate, t[i] + ... (here t0 IS added) */
+        for (int64_t i = 1; i <= d; ++i) {
+            double Delta = ab_local(z, i, t0);
+            h_enqueue(&Q, i, next_time(t0, z->ba[i - 1], z->bb[i - 1], Delta, draw(z, i), &renew[i - 1]));
+        }
+    } else {
+        /* sfact.jl:184-187: bounds, then the queue is filled in coordinate order, NO "+ t0" */
+        for (int64_t i = 1; i <= d; ++i) ab_zigzag(z, i, t0);
+        for (int64_t i = 1; i <= d; ++i) h_enqueue(&Q, i, o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i)));
+    }
 
     int64_t num = 0;
     /* sfact.jl:199 outer loop; body = spdmp_inner! (:73-145), refresh branch omitted (lambda_ref == 0,
@@ -342,6 +377,13 @@ zzo_run *zzo_spdmp(int64_t d,
             const int64_t *nb = &z->bd.rowval[z->bd.colptr[i - 1] - 1];
             int64_t nnb = z->bd.colptr[i] - z->bd.colptr[i - 1];
             if (!lazy) { if (all) move_all(z, tp); else move_nbhd(z, nb, nnb, tp); } /* :82 */
+            if (lbnd && renew[i - 1]) { /* local.jl:34-41: the bound expired, renew it */
+                double Delta = ab_local(z, i, tp);
+                double tr = lazy ? tp : z->t[i - 1];
+                z->t_old[i - 1] = tr;
+                h_set(&Q, i, next_time(tr, z->ba[i - 1], z->bb[i - 1], Delta, draw(z, i), &renew[i - 1]));
+                continue;
+            }
             double gi = idot_x(z, &z->tg, i, tp);           /* :118, user closure = idot(Gamma,i,x) */
             if (h) gi = gi - h[i - 1];
             double ti = lazy ? tp : z->t[i - 1];
@@ -361,19 +403,29 @@ zzo_run *zzo_spdmp(int64_t d,
                     move_nbhd(z, &z->g2idx[z->g2ptr[i - 1]], z->g2ptr[i] - z->g2ptr[i - 1], tp);
                 if (lazy) { z->xf[i - 1] = pos_at(z, i, tp); z->tf[i - 1] = tp; }
                 z->th[i - 1] = -z->th[i - 1];                                       /* :130, dynamics.jl:46-49 */
-                for (int64_t q = 0; q < nnb; ++q) {                                 /* :131-135 */
+                for (int64_t q = 0; q < nnb; ++q) {                                 /* :131-135, local.jl:60-66 */
                     int64_t j = nb[q];
-                    ab_zigzag(z, j, tp);
                     double tj = lazy ? tp : z->t[j - 1];
                     z->t_old[j - 1] = tj;
-                    h_set(&Q, j, tj + o_poisson_time(z->ba[j - 1], z->bb[j - 1], draw(z, j)));
+                    if (lbnd) {
+                        double Delta = ab_local(z, j, tp);
+                        h_set(&Q, j, next_time(tj, z->ba[j - 1], z->bb[j - 1], Delta, draw(z, j), &renew[j - 1]));
+                    } else {
+                        ab_zigzag(z, j, tp);
+                        h_set(&Q, j, tj + o_poisson_time(z->ba[j - 1], z->bb[j - 1], draw(z, j)));
+                    }
                 }
                 push_event(r, ti, i, lazy ? z->xf[i - 1] : z->x[i - 1], z->th[i - 1]); /* :143, :50-52 */
                 break;
-            } else {                                                                /* :137-140 */
-                ab_zigzag(z, i, tp);
+            } else {                                                                /* :137-140, local.jl:68-73 */
                 z->t_old[i - 1] = ti;
-                h_set(&Q, i, ti + o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i)));
+                if (lbnd) {
+                    double Delta = ab_local(z, i, tp);
+                    h_set(&Q, i, next_time(ti, z->ba[i - 1], z->bb[i - 1], Delta, draw(z, i), &renew[i - 1]));
+                } else {
+                    ab_zigzag(z, i, tp);
+                    h_set(&Q, i, ti + o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i)));
+                }
             }
         }
     }
@@ -382,7 +434,7 @@ zzo_run *zzo_spdmp(int64_t d,
     if (lazy) { free(z->t); free(z->x); } else { free(z->tf); free(z->xf); }
     free(z->t_old); free(z->ba); free(z->bb); free(z->kctr);
     free(Q.key); free(Q.val); free(Q.index);
-    free(z->g2ptr); free(z->g2idx);
+    free(z->g2ptr); free(z->g2idx); free(renew);
     return r;
 }
 

@@ -35,12 +35,15 @@ extern "C" {
 zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const double* tnz, const double* h,
                    const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
                    const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
-                   int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit)
+                   int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound)
 {
     zzw_run* r = new zzw_run();
     r->d = d;
     ZzHostGraph G;
-    std::string e = zz_build_graph(G, d, tcp, trv, tnz, h, bcp, brv, bnz, mu);
+    std::vector<double> zero_mu((size_t)d, 0.0);
+    // LocalBound (src/local.jl): the bound is built from the TARGET's derivatives; the sampler matrix is not used
+    std::string e = local_bound ? zz_build_graph(G, d, tcp, trv, tnz, h, tcp, trv, tnz, zero_mu.data())
+                                : zz_build_graph(G, d, tcp, trv, tnz, h, bcp, brv, bnz, mu);
     if (!e.empty()) { r->status = 4; r->msg = e; return r; }
     std::vector<ZzKin> kin(d);
     std::vector<double> flips((size_t)d * 2 * ZZ_MAXFLIP, 0.0);
@@ -57,7 +60,7 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
     tag_limit &= 0x7fffffffu;
     for (int q = 0; q < 5; ++q) g.grid_diag[q] = G.grid_diag[q];
     ZzView v; memset(&v, 0, sizeof v); v.nranks = 1; v.hi = (int32_t)d; v.shard = (int32_t)d; v.d = (int32_t)d; v.kin = kin.data(); v.flips = flips.data(); v.priv = priv.data();
-    v.tau = tau.data(); v.kctr = kctr.data(); v.seed0 = seed[0]; v.seed1 = seed[1]; v.adapt = adapt; v.factor = factor;
+    v.tau = tau.data(); v.kctr = kctr.data(); v.seed0 = seed[0]; v.seed1 = seed[1]; v.adapt = adapt; v.factor = factor; v.local_bound = local_bound;
 
     for (int64_t j = 0; j < d; ++j) {
         kin[j].theta = th0[j]; kin[j].tf = t0; kin[j].xf = x0[j]; kin[j].hdr[0] = kin[j].hdr[1] = 0;

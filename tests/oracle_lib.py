@@ -13,6 +13,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 RNG_SEQ, RNG_CTR = 0, 1
 ARITH_INPLACE, ARITH_LAZY = 0, 2
 GRAPH_ALL = 4
+LOCAL_BOUND = 8
 PARITY_MODE = RNG_CTR | ARITH_LAZY  # what the GPU must reproduce bit for bit
 
 EVENT_DTYPE = np.dtype([("t", "<f8"), ("i", "<i8"), ("x", "<f8"), ("theta", "<f8")])  # trace.jl:38
@@ -119,7 +120,7 @@ def wlib():
         L = C.CDLL(so)
         L.zzw_spdmp.restype = C.c_void_p
         L.zzw_spdmp.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
-                                C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint32]
+                                C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_int]
         L.zzw_status.argtypes = [C.c_void_p]
         L.zzw_trace_len.restype = C.c_int64
         L.zzw_trace_len.argtypes = [C.c_void_p]
@@ -136,7 +137,7 @@ def wlib():
 
 
 def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
-               delta0=0.01, target_frac=0.4, tag_limit=0x0F000000):
+               delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False):
     L = wlib()
     d = target.n
     f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -147,7 +148,7 @@ def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1,
     r = L.zzw_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
                     _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
                     float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor),
-                    float(delta0), float(target_frac), int(tag_limit))
+                    float(delta0), float(target_frac), int(tag_limit), int(bool(local_bound)))
     try:
         st = L.zzw_status(r)
         if st == 3:

@@ -156,3 +156,28 @@ def test_full_size_properties(gpu):
         ts[i - 1], xs[i - 1] = t2, xi
     assert np.array_equal(s1chk[:2000].view(np.uint64), s0[0][:2000].view(np.uint64))
     assert 0.05 < a0.sum() / n0 < 0.5  # acceptance rate in the plausible range (~0.18 at stationarity)
+
+
+@pytest.mark.parametrize("cval", [1.0, 0.05])
+def test_local_bound_variant(gpu, cval):
+    """spdmp(grad, t0, x0, th0, T, LocalBound(c), Z) (src/local.jl:95-149) through the C-ABI flag ZZB_FLAG_LOCAL_BOUND."""
+    LB = O.PARITY_MODE | O.LOCAL_BOUND
+    G, x0, th0, _ = gpu.gmrf_config(24)
+    c = np.full(G.n, cval)
+    ref = O.spdmp(G, G, 0.0, x0, th0, 5.0, c, mode=LB, adapt=True)
+    Xi, (t, x, th), (acc, num), C = gpu.spdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 5.0, gpu.LocalBound(c),
+                                               gpu.ZigZag(G, np.zeros(G.n)), seed=(1, 2), adapt=True)
+    got = R()
+    got.events, got.t, got.x, got.theta, got.c, got.acc, got.num = Xi.events, t, x, th, C.c, acc, num
+    O.assert_same_run(ref, got)
+    # general sparse target with a linear term
+    d = 60
+    Gt = gpu.random_sparse_spd(d, deg=3, seed=4)
+    rng = np.random.default_rng(4)
+    x0, th0, h = rng.standard_normal(d), rng.choice(np.array([-1.0, 1.0]), d), 0.3 * rng.standard_normal(d)
+    ref = O.spdmp(Gt, Gt, 0.0, x0, th0, 15.0, np.full(d, 0.3), h=h, mode=LB, adapt=True)
+    Xi, (t, x, th), (acc, num), C = gpu.spdmp(gpu.GaussianPotential(Gt, h), 0.0, x0, th0, 15.0, gpu.LocalBound(np.full(d, 0.3)),
+                                               gpu.ZigZag(Gt, np.zeros(d)), seed=(1, 2), adapt=True)
+    got = R()
+    got.events, got.t, got.x, got.theta, got.c, got.acc, got.num = Xi.events, t, x, th, C.c, acc, num
+    O.assert_same_run(ref, got)

@@ -192,3 +192,21 @@ def test_golden_fixture(zzb):
     assert [float(t).hex() for t in r.events["t"][:8]] == g["first_t_hex"]
     assert float(r.events["t"][-1]).hex() == g["last_t_hex"]
     assert int(np.bitwise_xor.reduce(r.events["t"].view(np.uint64))) == g["xor_t"]
+
+
+def test_local_bound_moments_and_modes(zzb):
+    """LocalBound variant (src/local.jl): law-of-large-numbers check in the style of test/maintest.jl (the reference
+    itself only exercises LocalBound through performance/smartbound.jl), and agreement of the oracle's arithmetic modes."""
+    d, T = 8, 1000.0
+    G = zzb.random_spd(d, seed=2)
+    rng = np.random.default_rng(5)
+    x0, th0 = rng.random(d), rng.choice(np.array([-1.0, 1.0]), d)
+    c = np.full(d, 0.5)
+    for mode in (O.RNG_SEQ | O.ARITH_INPLACE | O.LOCAL_BOUND, O.PARITY_MODE | O.LOCAL_BOUND):
+        r = O.spdmp(G, G, 0.0, x0, th0, T, c, seed=(11, 12), mode=mode)
+        _cov_check(r, zzb, G, x0, th0, T, 2.0, 2.5)
+        assert r.acc.sum() / r.num > 0.5          # Hessian-informed bound: far fewer rejections than c = 0.7 ||Gamma_i||
+    a = O.spdmp(G, G, 0.0, x0, th0, 50.0, c, mode=O.RNG_CTR | O.ARITH_INPLACE | O.LOCAL_BOUND)
+    b = O.spdmp(G, G, 0.0, x0, th0, 50.0, c, mode=O.PARITY_MODE | O.LOCAL_BOUND)
+    assert a.num == b.num and np.array_equal(a.events["i"], b.events["i"])
+    assert np.allclose(a.events["t"], b.events["t"], rtol=1e-12, atol=1e-12)

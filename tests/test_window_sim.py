@@ -65,3 +65,20 @@ def test_bound_violation_and_t0(zzb):
     ref = O.spdmp(G, G, 0.0, x0, th0, 0.0, c)     # T <= t0
     got = O.window_sim(G, G, 0.0, x0, th0, 0.0, c)
     assert len(got.events) == 0 and got.num == ref.num == 0
+
+
+@pytest.mark.parametrize("cval", [1.0, 0.05])
+def test_local_bound(zzb, cval):
+    """spdmp(..., C::LocalBound, ...) (src/local.jl): bound expiry / renew items in the timelines."""
+    LB = O.PARITY_MODE | O.LOCAL_BOUND
+    G, x0, th0, _ = zzb.gmrf_config(16)
+    c = np.full(G.n, cval)
+    ref = O.spdmp(G, G, 0.0, x0, th0, 5.0, c, mode=LB, adapt=True)
+    for tl in (0x0F000000, 0x0F000000 | FORCE_CSR):
+        O.assert_same_run(ref, O.window_sim(G, G, 0.0, x0, th0, 5.0, c, tag_limit=tl, local_bound=True, adapt=True))
+    d = 40
+    Gt = zzb.random_sparse_spd(d, deg=4, seed=2)
+    rng = np.random.default_rng(2)
+    x0, th0, h = rng.standard_normal(d), rng.choice(np.array([-1.0, -0.5, 0.5, 1.0]), d), 0.3 * rng.standard_normal(d)
+    ref = O.spdmp(Gt, Gt, 0.0, x0, th0, 15.0, np.full(d, 0.3), h=h, mode=LB, adapt=True)
+    O.assert_same_run(ref, O.window_sim(Gt, Gt, 0.0, x0, th0, 15.0, np.full(d, 0.3), h=h, local_bound=True, adapt=True))

@@ -1,0 +1,5 @@
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
+python bench.py --steps 5 --warmup 3 --no-cpu 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('N=1', d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'])"
+python bench.py --steps 5 --warmup 3 --no-cpu --frac 0.1 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('N=1 frac .1', d['value'], d['ms_per_step'])"
+python bench.py --steps 5 --warmup 3 --no-cpu --tight 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('N=1 tight', d['value'], d['ms_per_step'], d['config']['passes_per_step'])"
+python bench.py --steps 5 --warmup 3 --no-cpu --tight --frac 0.05 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('N=1 tight .05', d['value'], d['ms_per_step'], d['config']['passes_per_step'])"

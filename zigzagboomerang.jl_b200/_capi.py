@@ -14,6 +14,7 @@ CUBIN_PATH = os.environ.get("ZZB200_CUBIN") or os.path.join(PKG_DIR, "zzb200_ker
 
 ZZB_OK, ZZB_E_ARG, ZZB_E_CUDA, ZZB_E_BOUND, ZZB_E_GRAPH, ZZB_E_NOMEM, ZZB_E_TRACE, ZZB_E_INTERNAL = 0, 1, 2, 3, 4, 5, 6, 9
 ZZB_FLAG_NO_TRACE = 1
+ZZB_FLAG_LOCAL_BOUND = 2
 
 EVENT_DTYPE = np.dtype([("t", "<f8"), ("i", "<i8"), ("x", "<f8"), ("theta", "<f8")])  # src/trace.jl:38
 

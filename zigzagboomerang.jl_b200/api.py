@@ -52,6 +52,14 @@ class ZigZag:
         self.rhobar = float(np.sqrt(1 - rho * rho))
 
 
+class LocalBound:
+    """``LocalBound(c)`` (src/types.jl:121-123): bounds from the target's own first and second directional derivatives
+    (src/local.jl:2-6), valid for ``2/c/|theta|`` and then renewed."""
+
+    def __init__(self, c):
+        self.c = f8(c)
+
+
 class GaussianPotential:
     """Target descriptor: ``grad phi_i(x) = idot(Gamma, i, x) - h[i]`` (src/common.jl:16-24)."""
 
@@ -185,11 +193,11 @@ class Problem:
 class Run:
     """One sampler run on the device (staged form of the C-ABI)."""
 
-    def __init__(self, problem: Problem, *, record_trace: bool = True, trace_capacity: int = 0):
+    def __init__(self, problem: Problem, *, record_trace: bool = True, trace_capacity: int = 0, local_bound: bool = False):
         self.problem = problem
         self.d = problem.d
         self._h = C.c_void_p()
-        flags = 0 if record_trace else _capi.ZZB_FLAG_NO_TRACE
+        flags = (0 if record_trace else _capi.ZZB_FLAG_NO_TRACE) | (_capi.ZZB_FLAG_LOCAL_BOUND if local_bound else 0)
         self.record_trace = record_trace
         check(_capi.lib().zzb_run_create(problem._h, flags, int(trace_capacity), C.byref(self._h)))
 
@@ -319,10 +327,15 @@ def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None,
     if not rest:
         raise TypeError("spdmp: missing sampler F")
     F = rest.pop(0)
+    local_bound = isinstance(c, LocalBound)   # spdmp(grad, t0, x0, th0, T, C::LocalBound, F, ...) src/local.jl:95,148
+    if local_bound:
+        c = c.c
+        if isinstance(grad, GaussianPotential):  # the bound comes from the target: F.Gamma / F.mu are ignored (local.jl:2-6)
+            F = ZigZag(grad.Gamma, np.zeros(grad.Gamma.n), F.sigma, lambdaref=F.lambdaref, rho=F.rho)
     prob, own = _as_problem(grad, F)
     if seed is None:  # Seed() = fresh entropy (src/ZigZagBoomerang.jl:10)
         seed = (secrets.randbits(64), secrets.randbits(64))
-    run = Run(prob, record_trace=record_trace)
+    run = Run(prob, record_trace=record_trace, local_bound=local_bound)
     try:
         if tune:
             run.set(**tune)
@@ -335,7 +348,7 @@ def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None,
         Xi.moments = run.moments() if num else None
         Xi.stats = run.stats()
         Xi.device_ms = run.device_ms
-        return Xi, (t, x, th), (acc, num), cc
+        return Xi, (t, x, th), (acc, num), (LocalBound(cc) if local_bound else cc)
     finally:
         run.close()
         if own:

@@ -28,6 +28,7 @@
 // per-node result flags
 #define ZZ_F_OVERFLOW 1u  // more than ZZ_MAXFLIP flips / ZZ_MAXITEMS items: the window must be shortened
 #define ZZ_F_VIOL 2u      // accepted with l >= lb and adapt == false  (sfact.jl:123-124)
+#define ZZ_RENEW_BIT 0x80000000u  // in the draw counter: the queued time is a bound expiry, not a proposal (local.jl:34)
 
 // Kinematic record of one coordinate, read by its neighbours: 32 B = one DRAM/L2 sector.
 // hdr[s] = (tag << 4) | count describes flip-list slot s: `count` flips recorded by the relaxation
@@ -77,6 +78,10 @@ struct ZzView {
     uint64_t seed0, seed1;
     int32_t adapt;
     double factor;
+    // LocalBound variant (src/local.jl): bounds from the target's own derivatives, valid for Delta = 2/c/|theta|, then
+    // renewed; the renew flag of a coordinate travels in bit 31 of its draw counter
+    int32_t local_bound;
+    int32_t pad_lb;
     // coordinate sharding across GPUs (one process per GPU): rank r owns the global ids [r*shard, (r+1)*shard).
     // Every rank allocates full-length arrays and indexes them globally; a record is valid only in its owner's
     // copy, reached through the peer mappings below (NVLink loads).  nranks == 1: the plain pointers above.
@@ -236,6 +241,17 @@ ZZ_HD void zz_next_trigger(const ZzGraph& g, const ZzView& v, int32_t j, double 
     }
 }
 
+// next_time(t, abc, z) of src/not_fact_samplers.jl:43-50 for the LocalBound variant: the proposal is capped at the
+// validity horizon Delta = 2/c/|theta| of the bound (local.jl:5); plain `s + dt` otherwise.
+ZZ_HD double zz_next_time(double s, double dt, double c, double th, bool lbm, bool& renew)
+{
+    if (!lbm) return s + dt;
+    const double Delta = 2.0 / c / (th < 0.0 ? -th : th);
+    if (dt > Delta) { renew = true; return s + Delta; }
+    renew = false;
+    return s + dt;
+}
+
 // The timeline of coordinate j inside the window ending at H (exclusive, or inclusive when incl != 0),
 // starting from its frontier state.  See the file header; per item this is exactly the arithmetic of
 // spdmp_inner! (sfact.jl:118-139) and ab (fact_samplers.jl:50-54) for coordinate j.
@@ -249,6 +265,9 @@ ZZ_HD void zz_process_node_slow(const ZzGraph& g, const ZzView& v, int32_t j, do
     double c100 = c / 100;
     double tau = zz_ld(v.tau + j);
     uint32_t k = zz_ld32(v.kctr + j);
+    const bool lbm = v.local_bound != 0;
+    bool renew = (k & ZZ_RENEW_BIT) != 0;
+    k &= ~ZZ_RENEW_BIT;
     const double gmu = g.gmu[j];
     uint32_t nprop = 0, nflip = 0, flags = 0;
     double last_t = -ZZ_INF; int32_t last_i = -1;
@@ -263,7 +282,10 @@ ZZ_HD void zz_process_node_slow(const ZzGraph& g, const ZzView& v, int32_t j, do
         if (item >= ZZ_MAXITEMS) { flags |= ZZ_F_OVERFLOW; break; }
         const double xs = xf + th * (s - tf);
         double gt, gx, gp, gm, gth;
-        if (own) {
+        if (own && lbm && renew) {                            // local.jl:34-41: bound expired, renew it
+            zz_eval(g, v, j, s, j, xs, th, w0, cur, gt, gx, gp, gm);
+            gth = gp;
+        } else if (own) {
             zz_eval(g, v, j, s, j, xs, th, w0, cur, gt, gx, gp, gm);
             const double l = zz_pos(gt * th);                 // fact_samplers.jl:28-30
             const double lb = zz_pos(a + b * (s - told));     // sfact.jl:70
@@ -293,13 +315,14 @@ ZZ_HD void zz_process_node_slow(const ZzGraph& g, const ZzView& v, int32_t j, do
             zz_eval(g, v, j, s, ni, xs, th, w0, cur, gt, gx, gp, gm);
             gth = gp;
         }
-        a = c + (gx - gmu) * th;                              // fact_samplers.jl:51
-        b = c100 + th * gth;                                  // fact_samplers.jl:52 (c100 = c / 100)
+        a = c + (lbm ? gt : gx - gmu) * th;                   // fact_samplers.jl:51 / local.jl:3
+        b = c100 + th * gth;                                  // fact_samplers.jl:52 / local.jl:4 (c100 = c / 100)
         told = s;
-        tau = s + zz_poisson_time(a, b, zz_u01(v.seed0, v.seed1, (uint64_t)j, k++));  // sfact.jl:134,139
+        const double dt = zz_poisson_time(a, b, zz_u01(v.seed0, v.seed1, (uint64_t)j, k++));  // sfact.jl:134,139
+        tau = zz_next_time(s, dt, c, th, lbm, renew);         // not_fact_samplers.jl:43-50 when LocalBound
     }
     o.a = a; o.b = b; o.told = told; o.tau = tau; o.c = c;
-    o.k = k; o.nprop = nprop; o.nflip = nflip; o.flags = flags;
+    o.k = k | (renew ? ZZ_RENEW_BIT : 0u); o.nprop = nprop; o.nflip = nflip; o.flags = flags;
     o.hdr0 = hh0; o.hdr1 = hh1;
 }
 
@@ -314,12 +337,15 @@ ZZ_HD void zz_init_node(const ZzGraph& g, const ZzView& v, int32_t j, double t0)
     zz_eval(g, v, j, t0, j, xf + th * (t0 - tf), th, 1u, 1u, gt, gx, gp, gm);
     ZzPriv pr;
     pr.c = zz_ld_priv(v.priv + j).c;
-    pr.a = pr.c + (gx - g.gmu[j]) * th;
+    const bool lbm = v.local_bound != 0;
+    pr.a = pr.c + (lbm ? gt : gx - g.gmu[j]) * th;
     pr.b = pr.c / 100 + th * gp;
     pr.told = t0;
     v.priv[j] = pr;
-    v.tau[j] = zz_poisson_time(pr.a, pr.b, zz_u01(v.seed0, v.seed1, (uint64_t)j, 0));
-    v.kctr[j] = 1;
+    const double dt = zz_poisson_time(pr.a, pr.b, zz_u01(v.seed0, v.seed1, (uint64_t)j, 0));
+    bool renew = false;
+    v.tau[j] = lbm ? zz_next_time(t0, dt, pr.c, th, true, renew) : dt;   // sfact.jl:186 has no "+ t0"; local.jl:122 has
+    v.kctr[j] = 1u | (renew ? ZZ_RENEW_BIT : 0u);
 }
 
 #endif  // ZZ_CORE_H

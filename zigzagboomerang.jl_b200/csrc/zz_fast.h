@@ -164,7 +164,7 @@ ZZ_HD void zz_eval_hood(const ZzHood<NB>& hd, bool same, double s, double xown, 
 }
 
 // Timeline of coordinate j from gathered data; identical arithmetic to zz_process_node_slow.
-template <int NB>
+template <int NB, bool LB>
 ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w, const ZzGraph& g, const ZzView& v,
                        int32_t j, double H, int incl, uint32_t flags0, ZzNodeOut& o)
 {
@@ -173,7 +173,9 @@ ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w, const
     double a = w.a, b = w.b, told = w.told, c = w.c;
     double c100 = c / 100;
     double tau = w.tau;
-    uint32_t k = w.k;
+    const bool lbm = LB;   // compile-time: the plain ZigZag kernels carry none of the LocalBound logic
+    bool renew = LB && (w.k & ZZ_RENEW_BIT) != 0;
+    uint32_t k = w.k & ~ZZ_RENEW_BIT;
     const double gmu = g.grid_m ? 0.0 : g.gmu[j];
     const double hj = (!g.same && g.h) ? g.h[j] : 0.0;
     const bool has_h = (!g.same && g.h);
@@ -206,17 +208,18 @@ ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w, const
         }
         // the draws of this item depend only on the counter: start them (and the logarithm of the rescheduling draw)
         // before the neighbourhood evaluation so that the two dependency chains overlap
-        const uint32_t kr = own ? k + 1u : k;
+        const bool prop = own && !(lbm && renew);             // an expired LocalBound is renewed without thinning
+        const uint32_t kr = prop ? k + 1u : k;
         const double L2 = zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, kr));
-        const double u1 = own ? zz_u01(v.seed0, v.seed1, (uint64_t)j, k) : 0.0;
+        const double u1 = prop ? zz_u01(v.seed0, v.seed1, (uint64_t)j, k) : 0.0;
         k = kr + 1u;
         // one evaluation of the column at s shared by both kinds of item (keeps diverged lanes on the same code)
         const double xs = xf + th * (s - tf);
         double gt, gx, gp, gm;
         zz_eval_hood<NB>(hd, g.same != 0, s, xs, th, gt, gx, gp, gm);
         double gth = gp;
-        if (own) {
-            if (has_h) gt = gt - hj;
+        if (has_h) gt = gt - hj;
+        if (prop) {
             const double l = zz_pos(gt * th);                 // fact_samplers.jl:28-30
             const double lb = zz_pos(a + b * (s - told));     // sfact.jl:70
             nprop++;
@@ -234,20 +237,20 @@ ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w, const
                 gth = gm;
             }
         }
-        a = c + (gx - gmu) * th;                              // fact_samplers.jl:51
-        b = c100 + th * gth;                                  // fact_samplers.jl:52 (c100 = c / 100)
+        a = c + (lbm ? gt : gx - gmu) * th;                   // fact_samplers.jl:51 / local.jl:3
+        b = c100 + th * gth;                                  // fact_samplers.jl:52 / local.jl:4 (c100 = c / 100)
         told = s;
-        tau = s + zz_poisson_time_L(a, b, L2);                // sfact.jl:134,139
+        tau = zz_next_time(s, zz_poisson_time_L(a, b, L2), c, th, lbm, renew);   // sfact.jl:134,139 / local.jl:38-39
     }
     o.a = a; o.b = b; o.told = told; o.tau = tau; o.c = c;
-    o.k = k; o.nprop = nprop; o.nflip = nflip; o.flags = flags;
+    o.k = k | (renew ? ZZ_RENEW_BIT : 0u); o.nprop = nprop; o.nflip = nflip; o.flags = flags;
     o.hdr0 = hh0; o.hdr1 = hh1;
 }
 
 // Entry points.  KIND 0: 5-point lattice (index arithmetic); KIND 1: general sparse columns.
 #define ZZ_KIND_GRID 0
 #define ZZ_KIND_CSR 1
-template <int KIND>
+template <int KIND, bool LB>
 ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                              uint32_t cur, bool first_iter, ZzNodeOut& o)
 {
@@ -259,7 +262,7 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
         zz_load_own(v, j, w);
         zz_gather_grid(g, v, j, w0, cur, first_iter, hd, pool, flags);
         ZZ_SEG(2);
-        zz_timeline<5>(hd, pool, w, g, v, j, H, incl, flags, o);
+        zz_timeline<5, LB>(hd, pool, w, g, v, j, H, incl, flags, o);
         ZZ_SEG(5);
         return;
     }
@@ -267,7 +270,7 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
     if (g.nptr[j + 1] - g.nptr[j] <= ZZ_NB) {
         zz_load_own(v, j, w);
         zz_gather_csr<ZZ_NB>(g, v, j, w0, cur, first_iter, hd, pool, flags);
-        zz_timeline<ZZ_NB>(hd, pool, w, g, v, j, H, incl, flags, o);
+        zz_timeline<ZZ_NB, LB>(hd, pool, w, g, v, j, H, incl, flags, o);
         return;
     }
     zz_process_node_slow(g, v, j, H, incl, w0, cur, first_iter, o);
@@ -277,8 +280,13 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
 ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                            uint32_t cur, bool first_iter, ZzNodeOut& o)
 {
-    if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID>(g, v, j, H, incl, w0, cur, first_iter, o);
-    else zz_process_node_k<ZZ_KIND_CSR>(g, v, j, H, incl, w0, cur, first_iter, o);
+    if (v.local_bound) {
+        if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, true>(g, v, j, H, incl, w0, cur, first_iter, o);
+        else zz_process_node_k<ZZ_KIND_CSR, true>(g, v, j, H, incl, w0, cur, first_iter, o);
+    } else {
+        if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, false>(g, v, j, H, incl, w0, cur, first_iter, o);
+        else zz_process_node_k<ZZ_KIND_CSR, false>(g, v, j, H, incl, w0, cur, first_iter, o);
+    }
 }
 
 #endif  // ZZ_FAST_H

@@ -25,6 +25,7 @@ struct ZzHostGraph {
     std::vector<uint8_t> nfl;
     int32_t same = 0;
     bool has_h = false;
+    bool bnd_eq_tgt = false;   // sampler matrix identical to the target matrix and Z.mu == 0 (needed by LocalBound)
     int32_t maxdeg = 0;
     // 5-point lattice detection (m x n, column-major numbering): lets the kernels use index arithmetic
     int32_t grid_m = 0, grid_n = 0;
@@ -101,6 +102,7 @@ static inline std::string zz_build_graph(ZzHostGraph& G, int64_t d, const int64_
     bool mu0 = true;
     for (int64_t j = 0; j < d && mu0; ++j) mu0 = (zz_d2u(mu[j]) == 0);
     G.same = (same && !has_h && mu0) ? 1 : 0;
+    G.bnd_eq_tgt = same && mu0;
     G.has_h = has_h;
     zz_detect_grid(G, d, bcp, brv, bnz);
     if (has_h) G.h.assign(hvec, hvec + d);

@@ -286,14 +286,14 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
 
 // One timeline evaluation + publication; kept out of line so the three call sites (scan pass, relaxation pass,
 // tail pass) share one copy of the code and its register allocation.
-template <int KIND, bool MULTI>
+template <int KIND, bool MULTI, bool LB>
 __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, double H, int incl, uint32_t w0,
                                              uint32_t cur, bool first, int nxt, int ws)
 {
     ZzNodeOut o;
 #ifdef ZZ_PROF_NODE
     const long long c0 = clock64();
-    zz_process_node_k<KIND>(P.g, P.v, j, H, incl, w0, cur, first, o);
+    zz_process_node_k<KIND, LB>(P.g, P.v, j, H, incl, w0, cur, first, o);
     const long long c1 = clock64();
     zz_publish<KIND, MULTI>(P, j, o, w0, cur, nxt, ws);
     const long long c2 = clock64();
@@ -302,7 +302,7 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
         P.ctl->dbg[7] += 1ULL;
     }
 #else
-    zz_process_node_k<KIND>(P.g, P.v, j, H, incl, w0, cur, first, o);
+    zz_process_node_k<KIND, LB>(P.g, P.v, j, H, incl, w0, cur, first, o);
     zz_publish<KIND, MULTI>(P, j, o, w0, cur, nxt, ws);
 #endif
 }
@@ -404,7 +404,7 @@ zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ 
     }
 }
 
-template <int KIND, bool MULTI>
+template <int KIND, bool MULTI, bool LB>
 __device__ __forceinline__ void zz_run_body(const ZzParams& P)
 {
     ZzDevCtl* C = P.ctl;
@@ -483,7 +483,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                 const int32_t j = sq[warp][q];
                 const uint32_t old = MULTI ? atomicMax_system(P.dstamp + j, cur) : atomicMax(P.dstamp + j, cur);
                 if (old < w0) zz_append<MULTI>(P.touched[0], &C->touched_cnt[ws], j);
-                zz_eval_publish<KIND, MULTI>(P, j, H, incl, w0, cur, true, nxt, ws);
+                zz_eval_publish<KIND, MULTI, LB>(P, j, H, incl, w0, cur, true, nxt, ws);
                 st_evals++;
             }
             __syncwarp();
@@ -515,7 +515,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                         const int32_t* wlt = P.wl[li];
                         for (unsigned int e = threadIdx.x; e < n; e += blockDim.x) {
                             const int32_t j = __ldcg(wlt + e);
-                            zz_eval_publish<KIND, MULTI>(P, j, H, incl, w0, cur, false, nxt, ws);
+                            zz_eval_publish<KIND, MULTI, LB>(P, j, H, incl, w0, cur, false, nxt, ws);
                             st_evals++;
                         }
                         __threadfence();
@@ -542,7 +542,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             const int32_t* wl = P.wl[li];
             for (unsigned int e = gtid; e < cw; e += nthreads) {
                 const int32_t j = __ldcg(wl + e);
-                zz_eval_publish<KIND, MULTI>(P, j, H, incl, w0, cur, false, nxt, ws);
+                zz_eval_publish<KIND, MULTI, LB>(P, j, H, incl, w0, cur, false, nxt, ws);
                 st_evals++;
             }
             ZZ_TOC(1);
@@ -637,7 +637,13 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
     if (lane == 0 && st_evals) atomicAdd(&C->node_evals, st_evals);
 }
 
-extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_grid(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_GRID, false>(P); }
-extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_csr(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_CSR, false>(P); }
-extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_grid_multi(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_GRID, true>(P); }
-extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) zz_run_kernel_csr_multi(const __grid_constant__ ZzParams P) { zz_run_body<ZZ_KIND_CSR, true>(P); }
+#define ZZ_RUN_KERNEL(name, KIND, MULTI, LB) \
+    extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) name(const __grid_constant__ ZzParams P) { zz_run_body<KIND, MULTI, LB>(P); }
+ZZ_RUN_KERNEL(zz_run_kernel_grid, ZZ_KIND_GRID, false, false)
+ZZ_RUN_KERNEL(zz_run_kernel_csr, ZZ_KIND_CSR, false, false)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_multi, ZZ_KIND_GRID, true, false)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_multi, ZZ_KIND_CSR, true, false)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_lb, ZZ_KIND_GRID, false, true)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_lb, ZZ_KIND_CSR, false, true)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_multi_lb, ZZ_KIND_GRID, true, true)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_multi_lb, ZZ_KIND_CSR, true, true)

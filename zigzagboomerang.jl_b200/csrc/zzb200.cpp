@@ -88,10 +88,10 @@ struct Global {
     CUdevice dev = 0; int dev_id = 0;
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
-    CUfunction f_setup = nullptr, f_init = nullptr, f_run[4] = { nullptr, nullptr, nullptr, nullptr }, f_export = nullptr;
+    CUfunction f_setup = nullptr, f_init = nullptr, f_run[8] = {}, f_export = nullptr;
     CUstream stream = nullptr;
     CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
-    int sm_count = 0; int blocks_per_sm[4] = { 0, 0, 0, 0 };
+    int sm_count = 0; int blocks_per_sm[8] = {};
     size_t total_mem = 0; char name[128] = { 0 };
 };
 static Global G;
@@ -166,6 +166,7 @@ struct zzb_run_s {
     ZzDevCtl hc;                       // last copy of the device control block
     int64_t launches = 0;
     int grid = 0; int kind = 1;
+    int kidx() const { return kind + (nranks > 1 ? 2 : 0) + ((flags & ZZB_FLAG_LOCAL_BOUND) ? 4 : 0); }
     int rank = 0, nranks = 1, shard = 0, lo = 0, hi = 0;
     CUdeviceptr peer[ZZ_MAXRANKS][8] = {};   // imported mappings: kin, flips, dstamp, wl0, wl1, wl2, touched, ctl
     bool peer_open[ZZ_MAXRANKS] = {};
@@ -219,17 +220,17 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     CU(cuModuleLoadData(&G.mod, img.data()));
     CU(cuModuleGetFunction(&G.f_setup, G.mod, "zz_setup_kernel"));
     CU(cuModuleGetFunction(&G.f_init, G.mod, "zz_init_kernel"));
-    CU(cuModuleGetFunction(&G.f_run[0], G.mod, "zz_run_kernel_grid"));
-    CU(cuModuleGetFunction(&G.f_run[1], G.mod, "zz_run_kernel_csr"));
-    CU(cuModuleGetFunction(&G.f_run[2], G.mod, "zz_run_kernel_grid_multi"));
-    CU(cuModuleGetFunction(&G.f_run[3], G.mod, "zz_run_kernel_csr_multi"));
+    // index = kind (0 lattice, 1 general) + 2 * multi-GPU + 4 * LocalBound
+    static const char* run_names[8] = { "zz_run_kernel_grid", "zz_run_kernel_csr", "zz_run_kernel_grid_multi", "zz_run_kernel_csr_multi",
+                                        "zz_run_kernel_grid_lb", "zz_run_kernel_csr_lb", "zz_run_kernel_grid_multi_lb", "zz_run_kernel_csr_multi_lb" };
+    for (int k = 0; k < 8; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuStreamCreate(&G.stream, CU_STREAM_NON_BLOCKING));
     CU(cuEventCreate(&G.ev0, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.ev1, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.tev0, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.tev1, CU_EVENT_DEFAULT));
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 8; ++k) {
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm[k], G.f_run[k], ZZ_BLOCK, 0));
         if (G.blocks_per_sm[k] < 1) return fail(ZZB_E_CUDA, "zz_run_kernel does not fit on an SM");
     }
@@ -321,6 +322,8 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
 {
     if (!p || !out) return fail(ZZB_E_ARG, "null argument");
     if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if ((flags & ZZB_FLAG_LOCAL_BOUND) && !p->hg.bnd_eq_tgt)
+        return fail(ZZB_E_ARG, "LocalBound builds its bound from the target: create the problem with the sampler matrix equal to the target (bnd_* = NULL) and Z.mu = 0");
     CtxGuard cg;
     zzb_run_s* r = new zzb_run_s();
     r->prob = p; r->d = p->hg.d; r->flags = flags;
@@ -349,7 +352,7 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
 #undef AL
     if (st) { delete r; return st == ZZB_E_CUDA ? ZZB_E_NOMEM : st; }
     r->kind = p->g.grid_m ? 0 : 1;
-    r->grid = G.sm_count * G.blocks_per_sm[r->kind];
+    r->grid = G.sm_count * G.blocks_per_sm[r->kidx()];
     r->shard = r->d; r->hi = r->d;
     *out = r;
     return ZZB_OK;
@@ -370,6 +373,7 @@ static void fill_params(zzb_run_s* r)
     P.trace = r->trace.as<ZzEvent>(); P.trace_cap = r->trace_cap;
     P.ctl = r->ctl.as<ZzDevCtl>();
     P.record_trace = (r->flags & ZZB_FLAG_NO_TRACE) ? 0 : 1;
+    P.v.local_bound = (r->flags & ZZB_FLAG_LOCAL_BOUND) ? 1 : 0;
     P.v.nranks = r->nranks; P.v.rank = r->rank; P.v.shard = r->shard; P.v.lo = r->lo; P.v.hi = r->hi;
     if (r->nranks > 1) {
         for (int q = 0; q < r->nranks; ++q) {
@@ -407,7 +411,7 @@ int32_t zzb_run_shard(zzb_run_t r, int32_t rank, int32_t nranks)
     r->rank = rank; r->nranks = nranks; r->shard = (int)shard;
     r->lo = (int)std::min<int64_t>(d, shard * rank);
     r->hi = (int)std::min<int64_t>(d, shard * (rank + 1));
-    r->grid = G.sm_count * G.blocks_per_sm[r->kind + (nranks > 1 ? 2 : 0)];
+    r->grid = G.sm_count * G.blocks_per_sm[r->kidx()];
     return ZZB_OK;
 }
 
@@ -452,7 +456,7 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     else if (!strcmp(key, "target_frac")) r->target_frac = value;
     else if (!strcmp(key, "tag_limit")) r->tag_limit = (unsigned int)value;
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
-    else if (!strcmp(key, "grid")) r->grid = std::max(1, std::min((int)value, G.sm_count * G.blocks_per_sm[r->kind + (r->nranks > 1 ? 2 : 0)]));
+    else if (!strcmp(key, "grid")) r->grid = std::max(1, std::min((int)value, G.sm_count * G.blocks_per_sm[r->kidx()]));
     else return fail(ZZB_E_ARG, "unknown tuning key %s", key);
     return ZZB_OK;
 }
@@ -545,7 +549,7 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
         CU(cuMemsetD8Async(r->ctl.p, 0, 8, G.stream));  // barrier counter
         void* args[] = { &P };
         CU(cuEventRecord(G.ev0, G.stream));
-        CU(cuLaunchCooperativeKernel(G.f_run[r->kind + (r->nranks > 1 ? 2 : 0)], (unsigned)r->grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, args));
+        CU(cuLaunchCooperativeKernel(G.f_run[r->kidx()], (unsigned)r->grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, args));
         CU(cuEventRecord(G.ev1, G.stream));
         CU(cuStreamSynchronize(G.stream));
         r->launches++;
