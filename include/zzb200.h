@@ -92,7 +92,7 @@ int32_t zzb_run_ipc_import(zzb_run_t r, int32_t peer_rank, const void* buf, int6
 int32_t zzb_run_range(zzb_run_t r, int64_t* lo, int64_t* hi);       /* owned coordinates [lo, hi), 0-based */
 int32_t zzb_run_reset(zzb_run_t r);                                  /* re-initialise from the inputs resident in HBM */
 int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms);   /* device_ms: CUDA-event time of the kernel(s) */
-int32_t zzb_run_set(zzb_run_t r, const char* key, double value);    /* "delta0", "target_frac", "tag_limit", "max_windows" */
+int32_t zzb_run_set(zzb_run_t r, const char* key, double value);    /* "delta0", "target_frac" / "target_flip_frac" (proposals / accepted flips per window over d), "tag_limit", "max_windows", "grid" */
 int32_t zzb_run_stats(zzb_run_t r, int64_t* out, int32_t n);        /* windows, retries, passes, node evaluations, rebases,
                                                                        kernel launches, grid size, block size */
 

@@ -72,7 +72,7 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
     {
         ZzCtl ctl;
         double target = std::max(target_frac * (double)d, 4.0);
-        zz_ctl_init(ctl, std::min(F0, T), T, delta0, target);
+        zz_ctl_init(ctl, std::min(F0, T), T, delta0, target, std::max(0.25 * target, 2.0));
         uint32_t cur = 0;
         std::vector<int32_t> wl, next, touched;
         auto handle = [&](int32_t j, const ZzNodeOut& o, uint32_t w0, uint32_t curtag) {
@@ -136,11 +136,11 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
                 }
             }
             r->iters += it; r->max_iters = std::max(r->max_iters, it);
-            bool overflow = false; double smin = ZZ_INF; unsigned long long nprop = 0;
+            bool overflow = false; double smin = ZZ_INF; unsigned long long nprop = 0;  // accepted flips (length controller)
             for (int32_t j : touched) {
                 const ZzSpec& s = spec[j];
                 if (s.flags & ZZ_F_OVERFLOW) overflow = true;
-                nprop += s.nprop;
+                nprop += (unsigned long long)s.nprop | ((unsigned long long)s.nflip << 32);
                 if (s.nflip) {
                     int slot; zz_pick_slot(kin[j].hdr[0], kin[j].hdr[1], w0, cur, slot);
                     smin = std::min(smin, flips[((size_t)j * 2 + slot) * ZZ_MAXFLIP]);

@@ -6,7 +6,7 @@ z = g.load_package(); z.init(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 T = float(sys.argv[2]) if len(sys.argv) > 2 else 2.0
 tight = len(sys.argv) > 3 and sys.argv[3] == "tight"
-fracs = [float(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0.4]
+fracs = [float(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0.03]
 G, x0, th0, c = z.gmrf_config(n, tight=tight)
 prob = z.Problem(z.GaussianPotential(G), z.ZigZag(G, np.zeros(G.n)))
 # warm the clocks up

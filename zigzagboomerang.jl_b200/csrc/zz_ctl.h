@@ -24,14 +24,15 @@ struct ZzCtl {
     double H;      // end of the current window
     double T;      // user horizon
     double delta;  // current window length
-    double target; // proposals per window the length controller aims for
+    double target; // proposals per window the length controller aims for; accepted flips are capped at target_flips
+    double target_flips;
     int phase;
     int incl;      // window closed on the right (phase C only)
 };
 
-ZZ_HD void zz_ctl_init(ZzCtl& c, double F0, double T, double delta0, double target)
+ZZ_HD void zz_ctl_init(ZzCtl& c, double F0, double T, double delta0, double target, double target_flips)
 {
-    c.F = F0; c.T = T; c.delta = delta0; c.target = target; c.incl = 0; c.H = F0;
+    c.F = F0; c.T = T; c.delta = delta0; c.target = target; c.target_flips = target_flips; c.incl = 0; c.H = F0;
     c.phase = (F0 < T) ? ZZ_PH_A : ZZ_PH_B;
 }
 
@@ -47,7 +48,8 @@ ZZ_HD void zz_ctl_begin(ZzCtl& c)
 // Called once the relaxation of the current window has converged.
 //   overflow  some coordinate exceeded ZZ_MAXFLIP / ZZ_MAXITEMS
 //   smin      earliest accepted flip inside the window (+inf if none); only used in phase B
-//   nprop     proposals inside the window
+//   nprop     proposals (low 32 bits) and accepted flips (high 32 bits) of the previously committed window; they
+//             steer the window length only -- the events do not depend on it
 ZZ_HD int zz_ctl_end(ZzCtl& c, bool overflow, double smin, unsigned long long nprop)
 {
     if (overflow) {
@@ -58,7 +60,10 @@ ZZ_HD int zz_ctl_end(ZzCtl& c, bool overflow, double smin, unsigned long long np
     if (c.phase == ZZ_PH_C) { c.F = c.H; c.phase = ZZ_PH_DONE; return ZZ_ACT_COMMIT; }
     if (c.phase == ZZ_PH_B && smin < ZZ_INF) { c.H = smin; c.phase = ZZ_PH_C; return ZZ_ACT_RETRY; }
     // commit and adapt the window length (any policy gives the same events; this one only steers speed)
-    double f = c.target / (double)(nprop > 0 ? nprop : 1ULL);
+    const unsigned long long np = nprop & 0xffffffffULL, nf = nprop >> 32;
+    double f = c.target / (double)(np > 0 ? np : 1ULL);
+    const double ff = c.target_flips / (double)(nf > 0 ? nf : 1ULL);
+    f = ff < f ? ff : f;
     f = f < 0.5 ? 0.5 : (f > 2.0 ? 2.0 : f);
     const bool clipped = (c.phase == ZZ_PH_A && c.H >= c.T);
     if (!clipped) c.delta *= 0.5 * (1.0 + f);

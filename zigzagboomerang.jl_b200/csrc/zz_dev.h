@@ -29,7 +29,7 @@ struct ZzDevCtl {
     unsigned int touched_cnt[3];     // per window attempt (attempt number mod 3)
     int viol_i;
     unsigned long long smin_key[3];  // order-preserving key of the earliest flip (phase B)
-    unsigned long long nprop_win[3]; // proposals committed by the window of that attempt slot
+    unsigned long long nprop_win[3]; // proposals | accepted flips << 32 committed by the window of that attempt slot
     unsigned long long num;          // total proposals (sfact.jl:120)
     unsigned long long nacc;         // total accepted flips
     unsigned long long trace_len;    // records appended to the trace buffer (events + window-end markers)
@@ -73,7 +73,7 @@ struct ZzParams {
     ZzEvent* trace;
     unsigned long long trace_cap;
     ZzDevCtl* ctl;
-    double t0, T, delta0, target;
+    double t0, T, delta0, target, target_flips;
     unsigned int tag_limit;
     unsigned int max_windows;   // return to the host after this many committed windows (0 = run to the end)
     int32_t record_trace;

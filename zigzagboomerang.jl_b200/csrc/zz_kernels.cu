@@ -429,10 +429,10 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
         ctl = C->ctl; cur = C->cur; li = C->itg; wat = C->wattempt;
     } else {
         double F0 = zz_unkey(__ldcg(&C->f0_key));
-        zz_ctl_init(ctl, F0 < P.T ? F0 : P.T, P.T, P.delta0, P.target);
+        zz_ctl_init(ctl, F0 < P.T ? F0 : P.T, P.T, P.delta0, P.target, P.target_flips);
         cur = 0; li = 0; wat = 0;
     }
-    unsigned long long nprop_prev = (unsigned long long)P.target;
+    unsigned long long nprop_prev = (unsigned long long)P.target | ((unsigned long long)P.target_flips << 32);
     unsigned int windows_done = 0;
     unsigned long long st_iters = 0, st_retries = 0, st_evals = 0, st_rebases = 0;
     bool stop = false;
@@ -601,7 +601,8 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             np = cg::reduce(w, np, cg::plus<unsigned int>());
             nf = cg::reduce(w, nf, cg::plus<unsigned int>());
             if (lane == 0 && (np | nf)) {
-                atomicAdd(&C->nprop_win[ws], (unsigned long long)np);
+                // proposals (low half) and accepted flips (high half) of this window, for the length controller
+                atomicAdd(&C->nprop_win[ws], (unsigned long long)np | ((unsigned long long)nf << 32));
                 atomicAdd(&C->num, (unsigned long long)np);
                 atomicAdd(&C->nacc, (unsigned long long)nf);
             }

@@ -159,7 +159,7 @@ struct zzb_run_s {
     ZzParams P;
     double t0 = 0, T = 0;
     uint64_t seed[2] = { 0, 0 }; int32_t adapt = 0; double factor = 1.8;
-    double delta0 = 0, target_frac = 0.15; unsigned int tag_limit = ZZ_TAG_LIMIT; unsigned int max_windows = 0;
+    double delta0 = 0, target_frac = 0.15, target_flip_frac = 0.035; unsigned int tag_limit = ZZ_TAG_LIMIT; unsigned int max_windows = 0;
     bool uploaded = false, executed = false, have_inputs = false;
     // results
     std::vector<zzb_event> events;     // sorted, markers removed
@@ -454,6 +454,7 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     if (!r || !key) return fail(ZZB_E_ARG, "null argument");
     if (!strcmp(key, "delta0")) r->delta0 = value;
     else if (!strcmp(key, "target_frac")) r->target_frac = value;
+    else if (!strcmp(key, "target_flip_frac")) r->target_flip_frac = value;
     else if (!strcmp(key, "tag_limit")) r->tag_limit = (unsigned int)value;
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
     else if (!strcmp(key, "grid")) r->grid = std::max(1, std::min((int)value, G.sm_count * G.blocks_per_sm[r->kidx()]));
@@ -540,7 +541,8 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
     P.T = T;
     double span = T - r->t0;
     P.delta0 = r->delta0 > 0 ? r->delta0 : std::max(1e-12, 1e-2 * std::min(1.0, span > 0 ? span : 1.0));
-    P.target = std::max(r->target_frac * (double)r->d, 4.0);
+    P.target = std::max(r->target_frac * (double)r->d, 4.0);              // proposals per window
+    P.target_flips = std::max(r->target_flip_frac * (double)r->d, 2.0);   // cap on accepted flips per window
     P.tag_limit = r->tag_limit; P.max_windows = r->max_windows;
     float total_ms = 0.f;
     if (device_ms) *device_ms = 0.f;
