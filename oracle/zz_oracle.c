@@ -438,6 +438,171 @@ zzo_run *zzo_spdmp(int64_t d,
     return r;
 }
 
+/* =====================================================================================================
+ * Sticky ZigZag, sspdmp (src/ss_fact.jl:10-217): coordinates freeze when they hit 0 and thaw after an Exp(kappa_i) time.
+ *   freezing_time            ss_fact.jl:10-16      ssmove_forward!   :25-45
+ *   queue_time!              ss_fact.jl:54-66      sspdmp_inner!     :78-157     sspdmp  :159-217
+ * Options restated: reversible = false, strong_upperbounds = false; `adapt` is refused (its reset of the global
+ * counters, :134, depends on the global event order).  Every draw of the reference comes from Julia's GLOBAL RNG
+ * (:96,112,130,179 and queue_time!'s default rng): mode seq uses one xoroshiro stream in that order, mode ctr the
+ * per-coordinate streams (a coordinate draws when IT is queued, proposes, or freezes -- the thaw clock).
+ * Returned acc[] counts accepted reflections per coordinate (the reference keeps only their sum).
+ * ===================================================================================================== */
+static double freezing_time(double x, double th)
+{ /* ss_fact.jl:10-16 */
+    if (th * x >= 0) return INFINITY;
+    return -x / th;
+}
+
+typedef struct { ctx *z; heapq *Q; char *f; } sctx;
+
+static void s_queue_time(sctx *S, int64_t j, double tj, double xj)
+{ /* queue_time!(rng, Q, t, x, th, i, b, f, Z), ss_fact.jl:54-66 */
+    ctx *z = S->z;
+    double trefl = o_poisson_time(z->ba[j - 1], z->bb[j - 1], draw(z, j));
+    double tfreeze = freezing_time(xj, z->th[j - 1]);
+    if (tfreeze <= trefl) { S->f[j - 1] = 1; h_set(S->Q, j, tj + tfreeze); }
+    else { S->f[j - 1] = 0; h_set(S->Q, j, tj + trefl); }
+}
+
+static void s_move_nbhd(ctx *z, const int64_t *idx, int64_t n, double tp)
+{ /* ssmove_forward!(G, i, ...), ss_fact.jl:38-45: frozen coordinates are not moved */
+    for (int64_t q = 0; q < n; ++q) {
+        int64_t k = idx[q] - 1;
+        if (z->th[k] != 0.0) { z->x[k] = z->x[k] + z->th[k] * (tp - z->t[k]); z->t[k] = tp; }
+    }
+}
+
+zzo_run *zzo_sspdmp(int64_t d,
+                    const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
+                    const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
+                    double t0, const double *x0, const double *th0, double T, const double *c_in, const double *kappa,
+                    const uint64_t *seed, int mode)
+{
+    zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run));
+    ctx zs; ctx *z = &zs; memset(z, 0, sizeof(ctx));
+    r->d = d; r->mode = mode; r->t0 = t0;
+    z->d = d; z->mode = mode;
+    z->tg.colptr = tg_colptr; z->tg.rowval = tg_rowval; z->tg.nzval = tg_nzval;
+    z->bd.colptr = bd_colptr; z->bd.rowval = bd_rowval; z->bd.nzval = bd_nzval;
+    z->h = h; z->mu = mu;
+    size_t nb = (size_t)d * sizeof(double);
+    z->t = (double *)malloc(nb); z->x = (double *)malloc(nb); z->th = (double *)malloc(nb);
+    z->t_old = (double *)malloc(nb); z->ba = (double *)malloc(nb); z->bb = (double *)malloc(nb);
+    z->c = (double *)malloc(nb); z->tf = (double *)malloc(nb); z->xf = (double *)malloc(nb);
+    z->kctr = (uint32_t *)calloc((size_t)d, sizeof(uint32_t));
+    double *thf = (double *)calloc((size_t)d, sizeof(double));
+    char *f = (char *)calloc((size_t)d, 1);
+    r->acc = (int64_t *)calloc((size_t)d, sizeof(int64_t));
+    r->x0 = (double *)malloc(nb); memcpy(r->x0, x0, nb);
+    z->s0 = seed[0]; z->s1 = seed[1]; z->rng.x = seed[0]; z->rng.y = seed[1];
+    const int lazy = (mode & ZZO_ARITH_LAZY) != 0;
+    double tp = t0;
+    for (int64_t k = 0; k < d; ++k) {
+        z->t[k] = t0; z->t_old[k] = t0; z->x[k] = x0[k]; z->th[k] = th0[k]; z->c[k] = c_in[k];
+        z->tf[k] = t0; z->xf[k] = x0[k];
+    }
+    if (!lazy) build_g2(z);
+    heapq Q; Q.n = 0; Q.lex = (mode & ZZO_RNG_CTR) != 0;
+    Q.key = (int64_t *)malloc(((size_t)d + 2) * sizeof(int64_t));
+    Q.val = (double *)malloc(((size_t)d + 2) * sizeof(double));
+    Q.index = (int64_t *)malloc(((size_t)d + 2) * sizeof(int64_t));
+    sctx S = { z, &Q, f };
+    /* ss_fact.jl:177-188 */
+    for (int64_t i = 1; i <= d; ++i) ab_zigzag(z, i, t0);
+    for (int64_t i = 1; i <= d; ++i) {
+        double trefl = o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i));
+        double tfreez = freezing_time(x0[i - 1], th0[i - 1]);
+        if (trefl > tfreez) { f[i - 1] = 1; h_enqueue(&Q, i, t0 + tfreez); }
+        else { f[i - 1] = 0; h_enqueue(&Q, i, t0 + trefl); }
+    }
+    int64_t num = 0;
+    while (tp < T && r->status == ZZO_OK) { /* ss_fact.jl:202 */
+        for (;;) {                           /* sspdmp_inner!, :82 */
+            int64_t i = Q.key[1]; tp = Q.val[1];
+            const int64_t *nbv = &z->bd.rowval[z->bd.colptr[i - 1] - 1];
+            int64_t nnb = z->bd.colptr[i] - z->bd.colptr[i - 1];
+            const int64_t *g2 = lazy ? NULL : &z->g2idx[z->g2ptr[i - 1]];
+            int64_t ng2 = lazy ? 0 : z->g2ptr[i] - z->g2ptr[i - 1];
+            double xi_now = lazy ? pos_at(z, i, tp) : 0.0;
+            int is_event = 1;
+            if (f[i - 1]) {                                         /* case 1: freeze, :87-107 */
+                if (!lazy) { z->x[i - 1] = z->x[i - 1] + z->th[i - 1] * (tp - z->t[i - 1]); z->t[i - 1] = tp; xi_now = z->x[i - 1]; }
+                if (fabs(xi_now) > 1e-8) { r->status = 9; break; }  /* error("x[i] = ... !~ 0"), :89-91 */
+                double xz = -0.0 * z->th[i - 1];                      /* x[i] = -0*theta[i], :92 */
+                if (lazy) { z->xf[i - 1] = xz; z->tf[i - 1] = tp; } else z->x[i - 1] = xz;
+                thf[i - 1] = z->th[i - 1]; z->th[i - 1] = 0.0;      /* :93 */
+                z->t_old[i - 1] = tp; f[i - 1] = 0;
+                h_set(&Q, i, tp - zz_log(draw(z, i)) / kappa[i - 1]); /* :96 */
+                if (!lazy) { s_move_nbhd(z, nbv, nnb, tp); s_move_nbhd(z, g2, ng2, tp); }
+                for (int64_t q = 0; q < nnb; ++q) {                 /* :100-106 */
+                    int64_t j = nbv[q];
+                    if (z->th[j - 1] != 0) {
+                        ab_zigzag(z, j, tp);
+                        double tj = lazy ? tp : z->t[j - 1];
+                        z->t_old[j - 1] = tj;
+                        s_queue_time(&S, j, tj, lazy ? pos_at(z, j, tp) : z->x[j - 1]);
+                    }
+                }
+            } else if ((lazy ? z->xf[i - 1] : z->x[i - 1]) == 0 && z->th[i - 1] == 0) { /* case 2: thaw, :108-123 */
+                if (lazy) z->tf[i - 1] = tp; else z->t[i - 1] = tp;
+                z->th[i - 1] = thf[i - 1]; thf[i - 1] = 0.0;
+                z->t_old[i - 1] = tp;
+                if (!lazy) { s_move_nbhd(z, nbv, nnb, tp); s_move_nbhd(z, g2, ng2, tp); }
+                for (int64_t q = 0; q < nnb; ++q) {
+                    int64_t j = nbv[q];
+                    if (z->th[j - 1] != 0) {
+                        ab_zigzag(z, j, tp);
+                        double tj = lazy ? tp : z->t[j - 1];
+                        z->t_old[j - 1] = tj;
+                        s_queue_time(&S, j, tj, lazy ? pos_at(z, j, tp) : z->x[j - 1]);
+                    }
+                }
+            } else {                                                /* case 3: proposal, :124-152 */
+                if (!lazy) s_move_nbhd(z, nbv, nnb, tp);
+                double gi = idot_x(z, &z->tg, i, tp);
+                if (h) gi = gi - h[i - 1];
+                double ti = lazy ? tp : z->t[i - 1];
+                double l = zz_pos(gi * z->th[i - 1]);
+                double lb = zz_pos(z->ba[i - 1] + z->bb[i - 1] * (ti - z->t_old[i - 1]));
+                num += 1;
+                if (draw(z, i) * lb < l) {
+                    r->acc[i - 1] += 1;
+                    if (l > lb) { r->status = ZZO_E_BOUND; r->err_i = i; r->err_t = tp; r->err_l = l; r->err_lb = lb; break; }
+                    if (!lazy) s_move_nbhd(z, g2, ng2, tp);
+                    if (lazy) { z->xf[i - 1] = pos_at(z, i, tp); z->tf[i - 1] = tp; }
+                    z->th[i - 1] = -z->th[i - 1];
+                    for (int64_t q = 0; q < nnb; ++q) {
+                        int64_t j = nbv[q];
+                        if (z->th[j - 1] != 0) {
+                            ab_zigzag(z, j, tp);
+                            double tj = lazy ? tp : z->t[j - 1];
+                            z->t_old[j - 1] = tj;
+                            s_queue_time(&S, j, tj, lazy ? pos_at(z, j, tp) : z->x[j - 1]);
+                        }
+                    }
+                } else {
+                    ab_zigzag(z, i, tp);
+                    z->t_old[i - 1] = ti;
+                    s_queue_time(&S, i, ti, lazy ? pos_at(z, i, tp) : z->x[i - 1]);
+                    is_event = 0;
+                }
+            }
+            if (is_event) {                                         /* :154 */
+                push_event(r, tp, i, lazy ? z->xf[i - 1] : z->x[i - 1], z->th[i - 1]);
+                break;
+            }
+        }
+    }
+    r->num = num;
+    r->t = lazy ? z->tf : z->t; r->x = lazy ? z->xf : z->x; r->th = z->th; r->c = z->c;
+    if (lazy) { free(z->t); free(z->x); } else { free(z->tf); free(z->xf); }
+    free(z->t_old); free(z->ba); free(z->bb); free(z->kctr); free(thf); free(f);
+    free(Q.key); free(Q.val); free(Q.index);
+    free(z->g2ptr); free(z->g2idx);
+    return r;
+}
+
 int zzo_status(const zzo_run *r) { return r->status; }
 void zzo_error_info(const zzo_run *r, int64_t *i, double *t, double *l, double *lb)
 { *i = r->err_i; *t = r->err_t; *l = r->err_l; *lb = r->err_lb; }

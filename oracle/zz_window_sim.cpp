@@ -35,7 +35,7 @@ extern "C" {
 zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const double* tnz, const double* h,
                    const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
                    const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
-                   int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound)
+                   int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound, const double* kappa)
 {
     zzw_run* r = new zzw_run();
     r->d = d;
@@ -46,7 +46,7 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
                                 : zz_build_graph(G, d, tcp, trv, tnz, h, bcp, brv, bnz, mu);
     if (!e.empty()) { r->status = 4; r->msg = e; return r; }
     std::vector<ZzKin> kin(d);
-    std::vector<double> flips((size_t)d * 2 * ZZ_MAXFLIP, 0.0);
+    std::vector<double> flips((size_t)d * 2 * ZZ_MAXFLIP, 0.0), fth((size_t)d * 2 * ZZ_MAXFLIP, 0.0);
     std::vector<ZzPriv> priv(d);
     std::vector<double> tau(d);
     std::vector<uint32_t> kctr(d), dstamp(d, 0);
@@ -61,6 +61,7 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
     for (int q = 0; q < 5; ++q) g.grid_diag[q] = G.grid_diag[q];
     ZzView v; memset(&v, 0, sizeof v); v.nranks = 1; v.hi = (int32_t)d; v.shard = (int32_t)d; v.d = (int32_t)d; v.kin = kin.data(); v.flips = flips.data(); v.priv = priv.data();
     v.tau = tau.data(); v.kctr = kctr.data(); v.seed0 = seed[0]; v.seed1 = seed[1]; v.adapt = adapt; v.factor = factor; v.local_bound = local_bound;
+    v.sticky = kappa ? 1 : 0; v.fth = kappa ? fth.data() : nullptr; v.kappa = kappa;
 
     for (int64_t j = 0; j < d; ++j) {
         kin[j].theta = th0[j]; kin[j].tf = t0; kin[j].xf = x0[j]; kin[j].hdr[0] = kin[j].hdr[1] = 0;
@@ -82,11 +83,15 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
             if (same && cnt) {
                 const double* fl = &flips[((size_t)j * 2 + slot) * ZZ_MAXFLIP];
                 for (uint32_t m = 0; m < cnt && same; ++m) same = (zz_d2u(fl[m]) == zz_d2u(o.fl[m]));
+                const double* ft = &fth[((size_t)j * 2 + slot) * ZZ_MAXFLIP];
+                for (uint32_t m = 0; kappa && m < cnt && same; ++m) same = (zz_d2u(ft[m]) == zz_d2u(o.fth[m]));
             }
             if (!same) {
                 int ws = (slot == 0) ? 1 : 0;
                 double* fl = &flips[((size_t)j * 2 + ws) * ZZ_MAXFLIP];
                 for (uint32_t m = 0; m < o.nflip; ++m) fl[m] = o.fl[m];
+                double* ft = &fth[((size_t)j * 2 + ws) * ZZ_MAXFLIP];
+                for (uint32_t m = 0; kappa && m < o.nflip; ++m) ft[m] = o.fth[m];
                 kin[j].hdr[ws] = (curtag << 4) | o.nflip;
                 for (int32_t q = G.dptr[j]; q < G.dptr[j + 1]; ++q) {
                     int32_t k = G.didx[q];
@@ -152,6 +157,7 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
             size_t seg0 = r->ev.size();
             for (int32_t j : touched) {
                 const ZzSpec& s = spec[j];
+                if ((s.flags & ZZ_F_STICKY_ERR) && r->status == 0) r->status = 9;
                 if ((s.flags & ZZ_F_VIOL) && r->status == 0) {
                     r->status = 3; r->err_i = j + 1; r->err_t = vt[j]; r->err_l = vl[j]; r->err_lb = vlb[j];
                 }
@@ -162,14 +168,20 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
                     int slot; zz_pick_slot(kin[j].hdr[0], kin[j].hdr[1], w0, cur, slot);
                     const double* fl = &flips[((size_t)j * 2 + slot) * ZZ_MAXFLIP];
                     double th = kin[j].theta, tf = kin[j].tf, xf = kin[j].xf;
+                    const double* ft = &fth[((size_t)j * 2 + slot) * ZZ_MAXFLIP];
                     for (uint32_t m = 0; m < s.nflip; ++m) {
                         double fs = fl[m];
-                        double xs = xf + th * (fs - tf);
+                        double xs, thn;
+                        if (kappa) {   // sticky: flip / freeze / thaw (zz_commit_node)
+                            thn = ft[m];
+                            if (thn == 0.0) xs = -0.0 * th;
+                            else if (th == 0.0) xs = xf;
+                            else { xs = xf + th * (fs - tf); r->acc[j] += 1; }
+                        } else { xs = xf + th * (fs - tf); thn = -th; r->acc[j] += 1; }
                         r->s1[j] += (xf + xs) * (fs - tf);                        // trace.jl:194 (unscaled)
                         r->s2[j] += (fs - tf) * (xf * xf + xf * xs + xs * xs);
-                        th = -th; tf = fs; xf = xs;
+                        th = thn; tf = fs; xf = xs;
                         r->ev.push_back(zzw_event{ fs, j + 1, xs, th });          // sfact.jl:50-52
-                        r->acc[j] += 1;
                     }
                     kin[j].theta = th; kin[j].tf = tf; kin[j].xf = xf;
                 }

@@ -36,6 +36,9 @@ def lib():
         L.zzo_spdmp.restype = C.c_void_p
         L.zzo_spdmp.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
+        L.zzo_sspdmp.restype = C.c_void_p
+        L.zzo_sspdmp.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.zzo_status.argtypes = [C.c_void_p]
         L.zzo_trace_len.restype = C.c_int64
         L.zzo_trace_len.argtypes = [C.c_void_p]
@@ -68,8 +71,9 @@ class BoundError(RuntimeError):
 
 
 def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
-          mode=PARITY_MODE):
-    """Run the oracle.  ``target`` / ``bound`` are problems.CSC (target precision and the sampler's Z.Gamma)."""
+          mode=PARITY_MODE, kappa=None):
+    """Run the oracle.  ``target`` / ``bound`` are problems.CSC (target precision and the sampler's Z.Gamma).
+    With ``kappa`` (thaw rates) the sticky sampler sspdmp (src/ss_fact.jl) is run instead of spdmp."""
     L = lib()
     d = target.n
     f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -77,15 +81,23 @@ def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), 
     mu = np.zeros(d) if mu is None else f8(mu)
     h = None if h is None else f8(h)
     sd = np.array(seed, dtype=np.uint64)
-    r = L.zzo_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
-                    _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
-                    float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor), int(mode))
+    if kappa is not None:
+        kappa = f8(kappa)
+        r = L.zzo_sspdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
+                         _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
+                         float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(kappa), _p(sd), int(mode))
+    else:
+        r = L.zzo_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
+                        _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
+                        float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor), int(mode))
     try:
         st = L.zzo_status(r)
         if st == 3:
             i = C.c_int64(); t = C.c_double(); l = C.c_double(); lb = C.c_double()
             L.zzo_error_info(r, C.byref(i), C.byref(t), C.byref(l), C.byref(lb))
             raise BoundError("Tuning parameter `c` too small. (i=%d t=%g l=%g lb=%g)" % (i.value, t.value, l.value, lb.value))
+        if st != 0:
+            raise RuntimeError("oracle failed with status %d" % st)
         out = OracleResult()
         n = L.zzo_trace_len(r)
         out.events = np.empty(n, dtype=EVENT_DTYPE)
@@ -120,7 +132,7 @@ def wlib():
         L = C.CDLL(so)
         L.zzw_spdmp.restype = C.c_void_p
         L.zzw_spdmp.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
-                                C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_int]
+                                C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_int, C.c_void_p]
         L.zzw_status.argtypes = [C.c_void_p]
         L.zzw_trace_len.restype = C.c_int64
         L.zzw_trace_len.argtypes = [C.c_void_p]
@@ -137,7 +149,7 @@ def wlib():
 
 
 def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
-               delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False):
+               delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False, kappa=None):
     L = wlib()
     d = target.n
     f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -148,7 +160,8 @@ def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1,
     r = L.zzw_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
                     _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
                     float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor),
-                    float(delta0), float(target_frac), int(tag_limit), int(bool(local_bound)))
+                    float(delta0), float(target_frac), int(tag_limit), int(bool(local_bound)),
+                    _p(None if kappa is None else f8(kappa)))
     try:
         st = L.zzw_status(r)
         if st == 3:

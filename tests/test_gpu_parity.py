@@ -181,3 +181,36 @@ def test_local_bound_variant(gpu, cval):
     got = R()
     got.events, got.t, got.x, got.theta, got.c, got.acc, got.num = Xi.events, t, x, th, C.c, acc, num
     O.assert_same_run(ref, got)
+
+
+@pytest.mark.parametrize("n,T,kap", [(8, 8.0, 1.0), (32, 3.0, 0.5)])
+def test_sticky_zigzag(gpu, n, T, kap):
+    """sspdmp(grad, t0, x0, th0, T, c, Z, kappa) (src/ss_fact.jl:159-217) through zzb_run_upload_kappa / ZZB_FLAG_STICKY."""
+    G, x0, th0, c = gpu.gmrf_config(n)
+    kappa = np.full(G.n, kap)
+    ref = O.spdmp(G, G, 0.0, x0, th0, T, c, kappa=kappa)
+    Xi, (t, x, th), (acc, num), cc = gpu.sspdmp(gpu.GaussianPotential(G), 0.0, x0, th0, T, c, gpu.ZigZag(G, np.zeros(G.n)), kappa,
+                                                seed=(1, 2))
+    got = R()
+    got.events, got.t, got.x, got.theta, got.c, got.acc, got.num = Xi.events, t, x, th, cc, Xi.acc_per_coordinate, num
+    got.s1, got.s2 = Xi.sums
+    O.assert_same_run(ref, got)
+    assert acc == ref.acc.sum() and (Xi.events["theta"] == 0).sum() > 10
+    # freeze records carry x = -0*theta: a signed zero, bit-identical to the oracle (checked by assert_same_run above)
+    assert np.all(Xi.events["x"][Xi.events["theta"] == 0] == 0)
+
+
+def test_sticky_1d_closed_form_on_gpu(gpu):
+    """test/sticky.jl:7-36 on the device path."""
+    import math
+    sigma, mu, kap, T = math.sqrt(0.5), 0.9, 1.5, 2000.0
+    G = gpu.CSC.from_dense(np.array([[1 / sigma ** 2]]))
+    Z = gpu.ZigZag(gpu.CSC.from_dense(np.array([[1.0]])), np.zeros(1))
+    Xi, _, (acc, num), _ = gpu.sspdmp(gpu.GaussianPotential(G, np.array([mu / sigma ** 2])), 0.0, np.array([1.0]), np.array([0.8]), T,
+                                      np.array([20.0]), Z, np.array([kap]), seed=(3, 4))
+    ts, xs = gpu.discretize(Xi, 0.2)
+    xs = xs[:, 0]
+    w = math.sqrt(2 * math.pi) * sigma / (math.sqrt(2 * math.pi) * sigma + math.exp(-0.5 * mu ** 2 / sigma ** 2) / kap)
+    assert abs(np.mean(xs != 0) - w) < 2.5 / math.sqrt(T)
+    assert abs(xs.mean() - w * mu) < 5.0 / math.sqrt(T)
+    assert abs((xs ** 2).mean() - w * (sigma ** 2 + mu ** 2)) < 5.0 / math.sqrt(T)

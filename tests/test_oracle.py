@@ -210,3 +210,36 @@ def test_local_bound_moments_and_modes(zzb):
     b = O.spdmp(G, G, 0.0, x0, th0, 50.0, c, mode=O.PARITY_MODE | O.LOCAL_BOUND)
     assert a.num == b.num and np.array_equal(a.events["i"], b.events["i"])
     assert np.allclose(a.events["t"], b.events["t"], rtol=1e-12, atol=1e-12)
+
+
+def test_sticky_1d_closed_form(zzb):
+    """test/sticky.jl:7-36: 1-d sticky ZigZag on N(mu, sigma^2) with kappa = 1.5: P(X != 0) = w, E X = w mu,
+    E X^2 = w (sigma^2 + mu^2) with w = sqrt(2 pi) sigma / (sqrt(2 pi) sigma + exp(-mu^2 / 2 sigma^2) / kappa)."""
+    sigma, mu, kap, T = math.sqrt(0.5), 0.9, 1.5, 2000.0
+    G = zzb.CSC.from_dense(np.array([[1 / sigma ** 2]]))   # grad phi = (x - mu) / sigma^2 = G x - h
+    Gb = zzb.CSC.from_dense(np.array([[1.0]]))
+    w = math.sqrt(2 * math.pi) * sigma / (math.sqrt(2 * math.pi) * sigma + math.exp(-0.5 * mu ** 2 / sigma ** 2) / kap)
+    for mode, seed in ((O.RNG_SEQ | O.ARITH_INPLACE, (0x9E3779B97F4A7C15, 0xD1B54A32D192ED03)), (O.PARITY_MODE, (3, 4))):
+        r = O.spdmp(G, Gb, 0.0, np.array([1.0]), np.array([0.8]), T, np.array([20.0]), h=np.array([mu / sigma ** 2]),
+                    kappa=np.array([kap]), mode=mode, seed=seed)
+        tr = zzb.FactTrace(None, 0.0, np.array([1.0]), np.array([0.8]), r.events)
+        ts, xs = zzb.discretize(tr, 0.2)
+        xs = xs[:, 0]
+        assert abs(np.mean(xs != 0) - w) < 2.5 / math.sqrt(T)
+        assert abs(xs.mean() - w * mu) < 5.0 / math.sqrt(T)
+        assert abs((xs ** 2).mean() - w * (sigma ** 2 + mu ** 2)) < 5.0 / math.sqrt(T)
+        assert (r.events["theta"] == 0).sum() > 100          # freeze events are in the trace (x = -0*theta, theta = 0)
+
+
+def test_sticky_large_kappa_matches_plain_moments(zzb):
+    """test/sticky.jl:39-65: kappa = 1000 ("don't stop, actually") must reproduce the Gaussian moments."""
+    d, T = 8, 1000.0
+    G = zzb.random_spd(d, seed=2)
+    rng = np.random.default_rng(1)
+    x0, th0 = rng.random(d), rng.choice(np.array([-1.0, -0.5, 0.5, 1.0]), d)
+    for mode in (O.RNG_CTR | O.ARITH_INPLACE, O.PARITY_MODE):
+        r = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, T, 0.7 * G.colnorms(), kappa=np.full(d, 1000.0), mode=mode)
+        _cov_check(r, zzb, G, x0, th0, T, 2.0, 2.5)
+    a = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, 100.0, 0.7 * G.colnorms(), kappa=np.full(d, 2.0), mode=O.RNG_CTR | O.ARITH_INPLACE)
+    b = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, 100.0, 0.7 * G.colnorms(), kappa=np.full(d, 2.0), mode=O.PARITY_MODE)
+    assert a.num == b.num and np.array_equal(a.events["i"], b.events["i"]) and np.allclose(a.events["t"], b.events["t"], atol=1e-10)

@@ -82,3 +82,26 @@ def test_local_bound(zzb, cval):
     x0, th0, h = rng.standard_normal(d), rng.choice(np.array([-1.0, -0.5, 0.5, 1.0]), d), 0.3 * rng.standard_normal(d)
     ref = O.spdmp(Gt, Gt, 0.0, x0, th0, 15.0, np.full(d, 0.3), h=h, mode=LB, adapt=True)
     O.assert_same_run(ref, O.window_sim(Gt, Gt, 0.0, x0, th0, 15.0, np.full(d, 0.3), h=h, local_bound=True, adapt=True))
+
+
+@pytest.mark.parametrize("n,T,kap", [(6, 8.0, 1.0), (16, 5.0, 0.5), (24, 3.0, 5.0)])
+def test_sticky(zzb, n, T, kap):
+    """sspdmp (src/ss_fact.jl): freeze / thaw items in the timelines, (time, velocity) lists."""
+    G, x0, th0, c = zzb.gmrf_config(n)
+    kappa = np.full(G.n, kap)
+    ref = O.spdmp(G, G, 0.0, x0, th0, T, c, kappa=kappa)
+    assert (ref.events["theta"] == 0).sum() > 10
+    for tl in (0x0F000000, 0x0F000000 | FORCE_CSR, 60):
+        O.assert_same_run(ref, O.window_sim(G, G, 0.0, x0, th0, T, c, tag_limit=tl, kappa=kappa))
+
+
+def test_sticky_general_graph(zzb):
+    d = 40
+    Gt = zzb.random_sparse_spd(d, deg=2, seed=0)
+    assert np.diff(Gt.colptr).max() <= 8
+    rng = np.random.default_rng(0)
+    x0, th0 = rng.standard_normal(d), rng.choice(np.array([-1.0, -0.5, 0.5, 1.0]), d)
+    h, mu, kappa = 0.3 * rng.standard_normal(d), 0.1 * rng.standard_normal(d), rng.uniform(0.2, 3.0, d)
+    c = 2.0 * Gt.colnorms() + 1
+    ref = O.spdmp(Gt, Gt.scaled(0.9), 0.0, x0, th0, 15.0, c, h=h, mu=mu, kappa=kappa)
+    O.assert_same_run(ref, O.window_sim(Gt, Gt.scaled(0.9), 0.0, x0, th0, 15.0, c, h=h, mu=mu, kappa=kappa))

@@ -15,13 +15,14 @@ CUBIN_PATH = os.environ.get("ZZB200_CUBIN") or os.path.join(PKG_DIR, "zzb200_ker
 ZZB_OK, ZZB_E_ARG, ZZB_E_CUDA, ZZB_E_BOUND, ZZB_E_GRAPH, ZZB_E_NOMEM, ZZB_E_TRACE, ZZB_E_INTERNAL = 0, 1, 2, 3, 4, 5, 6, 9
 ZZB_FLAG_NO_TRACE = 1
 ZZB_FLAG_LOCAL_BOUND = 2
+ZZB_FLAG_STICKY = 4
 
 EVENT_DTYPE = np.dtype([("t", "<f8"), ("i", "<i8"), ("x", "<f8"), ("theta", "<f8")])  # src/trace.jl:38
 
 # every symbol include/zzb200.h declares
 SYMBOLS = [
     "zzb_init", "zzb_shutdown", "zzb_last_error", "zzb_device_info", "zzb_event_record", "zzb_event_elapsed_ms", "zzb_problem_create_gaussian", "zzb_problem_free",
-    "zzb_spdmp_run", "zzb_run_create", "zzb_run_shard", "zzb_run_ipc_export", "zzb_run_ipc_import", "zzb_run_range", "zzb_run_upload", "zzb_run_reset", "zzb_run_execute", "zzb_run_set", "zzb_run_stats",
+    "zzb_spdmp_run", "zzb_sspdmp_run", "zzb_run_create", "zzb_run_shard", "zzb_run_ipc_export", "zzb_run_ipc_import", "zzb_run_range", "zzb_run_upload", "zzb_run_upload_kappa", "zzb_run_reset", "zzb_run_execute", "zzb_run_set", "zzb_run_stats",
     "zzb_run_counts", "zzb_run_final_state", "zzb_trace_len", "zzb_trace_copy", "zzb_trace_moments", "zzb_trace_sums",
     "zzb_run_error_info", "zzb_run_free",
 ]
@@ -58,7 +59,9 @@ def lib():
             "zzb_problem_create_gaussian": [vp, i64] + [vp] * 8,
             "zzb_problem_free": [vp],
             "zzb_spdmp_run": [vp, f64, vp, vp, f64, vp, vp, i32, f64, u32, vp],
+            "zzb_sspdmp_run": [vp, f64, vp, vp, f64, vp, vp, vp, u32, vp],
             "zzb_run_create": [vp, u32, i64, vp],
+            "zzb_run_upload_kappa": [vp, vp],
             "zzb_run_upload": [vp, f64, vp, vp, vp, vp, i32, f64],
             "zzb_run_shard": [vp, i32, i32],
             "zzb_run_ipc_export": [vp, vp, i64, vp],

@@ -193,13 +193,18 @@ class Problem:
 class Run:
     """One sampler run on the device (staged form of the C-ABI)."""
 
-    def __init__(self, problem: Problem, *, record_trace: bool = True, trace_capacity: int = 0, local_bound: bool = False):
+    def __init__(self, problem: Problem, *, record_trace: bool = True, trace_capacity: int = 0, local_bound: bool = False,
+                 kappa=None):
         self.problem = problem
         self.d = problem.d
         self._h = C.c_void_p()
-        flags = (0 if record_trace else _capi.ZZB_FLAG_NO_TRACE) | (_capi.ZZB_FLAG_LOCAL_BOUND if local_bound else 0)
+        flags = (0 if record_trace else _capi.ZZB_FLAG_NO_TRACE) | (_capi.ZZB_FLAG_LOCAL_BOUND if local_bound else 0) \
+            | (_capi.ZZB_FLAG_STICKY if kappa is not None else 0)
         self.record_trace = record_trace
         check(_capi.lib().zzb_run_create(problem._h, flags, int(trace_capacity), C.byref(self._h)))
+        if kappa is not None:
+            self._kappa = f8(kappa)
+            check(_capi.lib().zzb_run_upload_kappa(self._h, ptr(self._kappa)))
 
     def set(self, **kw):
         for k, v in kw.items():
@@ -358,3 +363,38 @@ def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None,
 def pdmp(grad, t0, x0, theta0, T, c, F, *args, **kw):
     """``pdmp(grad, t0, x0, theta0, T, c, F::ZigZag, args...)`` = ``spdmp(..., All(), F, ...)`` (src/sfact.jl:236)."""
     return spdmp(grad, t0, x0, theta0, T, c, All(), F, *args, **kw)
+
+
+def sspdmp(grad, t0, x0, theta0, T, c, *rest, seed=None, record_trace=True, tune=None, **unsupported):
+    """``sspdmp(grad, t0, x0, theta0, T, c, [G,] F::ZigZag, kappa, args...)`` = ``Xi, (t, x, theta), (acc, num), c``
+    (src/ss_fact.jl:159-217): sticky ZigZag -- coordinates freeze when they hit 0 and thaw after an Exp(kappa_i) time.
+    `acc` is the number of accepted reflections (a scalar, like the reference).  Options of the reference that are
+    not available on the device path raise (``adapt``, ``reversible``, ``strong_upperbounds``)."""
+    for k, v in unsupported.items():
+        if v not in (False, None) and k in ("adapt", "reversible", "strong_upperbounds"):
+            raise NotImplementedError(f"sspdmp(...; {k}=true) is not implemented on the device path")
+    rest = list(rest)
+    if rest and (rest[0] is None or isinstance(rest[0], (All, Matched))):
+        rest.pop(0)
+    F, kappa = rest[0], rest[1]
+    prob, own = _as_problem(grad, F)
+    if seed is None:
+        seed = (secrets.randbits(64), secrets.randbits(64))
+    run = Run(prob, record_trace=record_trace, kappa=np.broadcast_to(f8(kappa), (prob.d,)).copy())
+    try:
+        if tune:
+            run.set(**tune)
+        run.upload(t0, x0, theta0, c, seed=seed)
+        run.execute(T)
+        t, x, th, cc = run.final_state()
+        acc, num = run.counts()
+        ev = run.events() if record_trace else np.empty(0, dtype=EVENT_DTYPE)
+        Xi = FactTrace(F, t0, x0, theta0, ev)
+        Xi.stats = run.stats()
+        Xi.acc_per_coordinate = acc
+        Xi.sums = run.sums()
+        return Xi, (t, x, th), (int(acc.sum()), num), cc
+    finally:
+        run.close()
+        if own:
+            prob.close()

@@ -28,6 +28,7 @@
 // per-node result flags
 #define ZZ_F_OVERFLOW 1u  // more than ZZ_MAXFLIP flips / ZZ_MAXITEMS items: the window must be shortened
 #define ZZ_F_VIOL 2u      // accepted with l >= lb and adapt == false  (sfact.jl:123-124)
+#define ZZ_F_STICKY_ERR 4u  // a freezing coordinate was not at 0 (ss_fact.jl:89-91)
 #define ZZ_RENEW_BIT 0x80000000u  // in the draw counter: the queued time is a bound expiry, not a proposal (local.jl:34)
 
 // Kinematic record of one coordinate, read by its neighbours: 32 B = one DRAM/L2 sector.
@@ -81,7 +82,13 @@ struct ZzView {
     // LocalBound variant (src/local.jl): bounds from the target's own derivatives, valid for Delta = 2/c/|theta|, then
     // renewed; the renew flag of a coordinate travels in bit 31 of its draw counter
     int32_t local_bound;
-    int32_t pad_lb;
+    // Sticky ZigZag (src/ss_fact.jl): coordinates freeze at 0 and thaw after Exp(kappa); the lists of a window then hold
+    // (time, velocity after the event) pairs -- fth is the velocity array parallel to `flips`; a frozen coordinate has
+    // theta == 0 in its record and keeps its saved velocity in priv.a; bit 31 of the draw counter = "next own event is a
+    // freeze" (the f flag of ss_fact.jl:54-66)
+    int32_t sticky;
+    double* fth;
+    const double* kappa;
     // coordinate sharding across GPUs (one process per GPU): rank r owns the global ids [r*shard, (r+1)*shard).
     // Every rank allocates full-length arrays and indexes them globally; a record is valid only in its owner's
     // copy, reached through the peer mappings below (NVLink loads).  nranks == 1: the plain pointers above.
@@ -107,6 +114,7 @@ struct ZzNodeOut {
     double a, b, told, tau, c;
     uint32_t k, nprop, nflip, flags;
     double fl[ZZ_MAXFLIP];
+    double fth[ZZ_MAXFLIP];  // sticky only: velocity after each recorded event
     double viol_t, viol_l, viol_lb;
     uint32_t hdr0, hdr1;   // own flip-list headers as read at entry
 };
@@ -344,7 +352,14 @@ ZZ_HD void zz_init_node(const ZzGraph& g, const ZzView& v, int32_t j, double t0)
     v.priv[j] = pr;
     const double dt = zz_poisson_time(pr.a, pr.b, zz_u01(v.seed0, v.seed1, (uint64_t)j, 0));
     bool renew = false;
-    v.tau[j] = lbm ? zz_next_time(t0, dt, pr.c, th, true, renew) : dt;   // sfact.jl:186 has no "+ t0"; local.jl:122 has
+    if (v.sticky) {   // ss_fact.jl:178-188: the earlier of the first proposal and the hitting time of 0, from t0
+        const double x0 = xf + th * (t0 - tf);
+        const double tfreez = (th * x0 >= 0.0) ? ZZ_INF : -x0 / th;
+        renew = dt > tfreez;
+        v.tau[j] = t0 + (renew ? tfreez : dt);
+    } else {
+        v.tau[j] = lbm ? zz_next_time(t0, dt, pr.c, th, true, renew) : dt;   // sfact.jl:186 has no "+ t0"; local.jl:122 has
+    }
     v.kctr[j] = 1u | (renew ? ZZ_RENEW_BIT : 0u);
 }
 

@@ -48,18 +48,19 @@ struct ZzHood {
 struct ZzPool {
     int n;
     double t[ZZ_POOL];
-    int m[ZZ_POOL];  // neighbourhood position of the flipping coordinate
+    int m[ZZ_POOL];      // neighbourhood position of the flipping coordinate
+    double th[ZZ_POOL];  // sticky only: its velocity after the event (0 = freeze)
 };
 
 // merge the recorded flips of neighbour position m into the pool, ordered by (time, position)
-ZZ_HD void zz_pool_add(ZzPool& pool, double fs, int m, uint32_t& flags)
+ZZ_HD void zz_pool_add(ZzPool& pool, double fs, int m, uint32_t& flags, double tha = 0.0)
 {
     int p = pool.n;
     if (p == ZZ_POOL) { flags |= ZZ_F_OVERFLOW; return; }
     while (p > 0 && (pool.t[p - 1] > fs || (pool.t[p - 1] == fs && pool.m[p - 1] > m))) {
-        pool.t[p] = pool.t[p - 1]; pool.m[p] = pool.m[p - 1]; --p;
+        pool.t[p] = pool.t[p - 1]; pool.m[p] = pool.m[p - 1]; pool.th[p] = pool.th[p - 1]; --p;
     }
-    pool.t[p] = fs; pool.m[p] = m; pool.n++;
+    pool.t[p] = fs; pool.m[p] = m; pool.th[p] = tha; pool.n++;
 }
 
 template <int NB>
@@ -74,7 +75,12 @@ ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint
             const uint32_t cnt = zz_pick_slot(h0[m], h1[m], w0, cur, slot);
             if (cnt) {
                 const double* fl = zz_flips_at(v, idx[m]) + slot * ZZ_MAXFLIP;
-                for (uint32_t q = 0; q < cnt; ++q) zz_pool_add(pool, zz_ld(fl + q), m, flags);
+                if (v.fth) {   // sticky lists carry the velocity after each event
+                    const double* ft = v.fth + ((size_t)idx[m] * 2 + slot) * ZZ_MAXFLIP;
+                    for (uint32_t q = 0; q < cnt; ++q) zz_pool_add(pool, zz_ld(fl + q), m, flags, zz_ld(ft + q));
+                } else {
+                    for (uint32_t q = 0; q < cnt; ++q) zz_pool_add(pool, zz_ld(fl + q), m, flags);
+                }
             }
         }
     }
@@ -247,10 +253,121 @@ ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w, const
     o.hdr0 = hh0; o.hdr1 = hh1;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Sticky ZigZag (sspdmp, src/ss_fact.jl:78-157) seen from coordinate j.  Own items: proposal (:124-152), freeze when the
+// coordinate reaches 0 (:87-107), thaw after its Exp(kappa_j) clock (:108-123).  Neighbour items: any velocity change
+// of a neighbour (flip / freeze / thaw) reschedules j if j is moving (:100-106,117-123,140-146).
+ZZ_HD double zz_freezing_time(double x, double th)
+{   // ss_fact.jl:10-16
+    if (th * x >= 0.0) return ZZ_INF;
+    return -x / th;
+}
+
+template <int NB>
+ZZ_HD void zz_timeline_sticky(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w, const ZzGraph& g, const ZzView& v,
+                              int32_t j, double H, int incl, uint32_t flags0, ZzNodeOut& o)
+{
+    double th = w.th, tf = w.tf, xf = w.xf;
+    double a = w.a, b = w.b, told = w.told, c = w.c;
+    const double c100 = c / 100;
+    double tau = w.tau;
+    bool fbit = (w.k & ZZ_RENEW_BIT) != 0;
+    uint32_t k = w.k & ~ZZ_RENEW_BIT;
+    bool frozen = (th == 0.0);
+    double thf = frozen ? w.a : 0.0;          // the saved velocity of a frozen coordinate travels in the `a` slot
+    const double kap = v.kappa[j];
+    const double gmu = g.grid_m ? 0.0 : g.gmu[j];
+    const bool has_h = (!g.same && g.h);
+    const double hj = has_h ? g.h[j] : 0.0;
+    uint32_t nprop = 0, nflip = 0, nev = 0, flags = flags0;
+    o.viol_t = 0.0; o.viol_l = 0.0; o.viol_lb = 0.0;
+    int p = 0;
+
+    for (int item = 0;; ++item) {
+        const double nt = p < pool.n ? pool.t[p] : ZZ_INF;
+        const int nm = p < pool.n ? pool.m[p] : 0x7fffffff;
+        const bool own = (tau < nt) || (tau == nt && hd.self < nm);
+        const double s = own ? tau : nt;
+        if (!(s < H || (incl && s == H))) break;
+        if (item >= ZZ_MAXITEMS) { flags |= ZZ_F_OVERFLOW; break; }
+        bool propose = false;
+        if (!own) {
+            const double tha = pool.th[p];
+            bool trig = false;
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+                if (m == nm) {
+                    if (tha == 0.0) { hd.xf[m] = -0.0 * hd.th[m]; }                          // freeze: x = -0*theta (:92)
+                    else if (hd.th[m] != 0.0) { hd.xf[m] = hd.xf[m] + hd.th[m] * (s - hd.tf[m]); }  // flip
+                    hd.tf[m] = s;
+                    hd.th[m] = tha;
+                    trig = (hd.fl[m] & ZZ_NB_TRIG) != 0;
+                }
+            }
+            ++p;
+            if (!trig || frozen) continue;           // frozen coordinates are not rescheduled
+        } else if (frozen) {                         // thaw (:108-116): restore the speed, then reschedule below
+            th = thf; thf = 0.0; tf = s; frozen = false;
+            if (nev == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#pragma unroll
+            for (int m = 0; m < ZZ_MAXFLIP; ++m) if (m == (int)nev) { o.fl[m] = s; o.fth[m] = th; }
+            nev++;
+        } else if (fbit) {                           // freeze (:87-96)
+            const double xs = xf + th * (s - tf);
+            if ((xs < 0.0 ? -xs : xs) > 1e-8) flags |= ZZ_F_STICKY_ERR;
+            if (nev == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#pragma unroll
+            for (int m = 0; m < ZZ_MAXFLIP; ++m) if (m == (int)nev) { o.fl[m] = s; o.fth[m] = 0.0; }
+            nev++;
+            xf = -0.0 * th; tf = s; thf = th; th = 0.0; frozen = true; fbit = false; told = s;
+            tau = s - zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, k++)) / kap;   // :96
+            continue;
+        } else {
+            propose = true;
+        }
+        const double xs = xf + th * (s - tf);
+        double gt, gx, gp, gm;
+        zz_eval_hood<NB>(hd, g.same != 0, s, xs, th, gt, gx, gp, gm);
+        double gth = gp;
+        double xnow = xs;
+        if (propose) {
+            if (has_h) gt = gt - hj;
+            const double l = zz_pos(gt * th);
+            const double lb = zz_pos(a + b * (s - told));
+            const double u1 = zz_u01(v.seed0, v.seed1, (uint64_t)j, k++);
+            nprop++;
+            if (u1 * lb < l) {                       // :130
+                if (l > lb && !(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }  // :132-133
+                if (nev == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#pragma unroll
+                for (int m = 0; m < ZZ_MAXFLIP; ++m) if (m == (int)nev) { o.fl[m] = s; o.fth[m] = -th; }
+                nev++; nflip++;
+                xf = xs; tf = s; th = -th;
+                gth = gm;
+            }
+        }
+        a = c + (gx - gmu) * th;                     // fact_samplers.jl:51
+        b = c100 + th * gth;                         // fact_samplers.jl:52
+        told = s;
+        // queue_time! (:54-66): the earlier of the proposed reflection and the hitting time of 0
+        const double trefl = zz_poisson_time(a, b, zz_u01(v.seed0, v.seed1, (uint64_t)j, k++));
+        const double tfreeze = zz_freezing_time(xnow, th);
+        if (tfreeze <= trefl) { fbit = true; tau = s + tfreeze; }
+        else { fbit = false; tau = s + trefl; }
+    }
+    o.a = frozen ? thf : a; o.b = b; o.told = told; o.tau = tau; o.c = c;
+    o.k = k | (fbit ? ZZ_RENEW_BIT : 0u); o.nprop = nprop; o.nflip = nev; o.flags = flags;
+    o.hdr0 = w.hdr0; o.hdr1 = w.hdr1;
+    (void)nflip;
+}
+
 // Entry points.  KIND 0: 5-point lattice (index arithmetic); KIND 1: general sparse columns.
 #define ZZ_KIND_GRID 0
 #define ZZ_KIND_CSR 1
-template <int KIND, bool LB>
+#define ZZ_MODE_PLAIN 0
+#define ZZ_MODE_LB 1       // LocalBound (src/local.jl)
+#define ZZ_MODE_STICKY 2   // sticky ZigZag (src/ss_fact.jl)
+template <int KIND, int MODE>
 ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                              uint32_t cur, bool first_iter, ZzNodeOut& o)
 {
@@ -262,7 +379,8 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
         zz_load_own(v, j, w);
         zz_gather_grid(g, v, j, w0, cur, first_iter, hd, pool, flags);
         ZZ_SEG(2);
-        zz_timeline<5, LB>(hd, pool, w, g, v, j, H, incl, flags, o);
+        if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<5>(hd, pool, w, g, v, j, H, incl, flags, o);
+        else zz_timeline<5, MODE == ZZ_MODE_LB>(hd, pool, w, g, v, j, H, incl, flags, o);
         ZZ_SEG(5);
         return;
     }
@@ -270,7 +388,8 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
     if (g.nptr[j + 1] - g.nptr[j] <= ZZ_NB) {
         zz_load_own(v, j, w);
         zz_gather_csr<ZZ_NB>(g, v, j, w0, cur, first_iter, hd, pool, flags);
-        zz_timeline<ZZ_NB, LB>(hd, pool, w, g, v, j, H, incl, flags, o);
+        if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<ZZ_NB>(hd, pool, w, g, v, j, H, incl, flags, o);
+        else zz_timeline<ZZ_NB, MODE == ZZ_MODE_LB>(hd, pool, w, g, v, j, H, incl, flags, o);
         return;
     }
     zz_process_node_slow(g, v, j, H, incl, w0, cur, first_iter, o);
@@ -280,12 +399,15 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
 ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                            uint32_t cur, bool first_iter, ZzNodeOut& o)
 {
-    if (v.local_bound) {
-        if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, true>(g, v, j, H, incl, w0, cur, first_iter, o);
-        else zz_process_node_k<ZZ_KIND_CSR, true>(g, v, j, H, incl, w0, cur, first_iter, o);
+    if (v.sticky) {
+        if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, ZZ_MODE_STICKY>(g, v, j, H, incl, w0, cur, first_iter, o);
+        else zz_process_node_k<ZZ_KIND_CSR, ZZ_MODE_STICKY>(g, v, j, H, incl, w0, cur, first_iter, o);
+    } else if (v.local_bound) {
+        if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, ZZ_MODE_LB>(g, v, j, H, incl, w0, cur, first_iter, o);
+        else zz_process_node_k<ZZ_KIND_CSR, ZZ_MODE_LB>(g, v, j, H, incl, w0, cur, first_iter, o);
     } else {
-        if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, false>(g, v, j, H, incl, w0, cur, first_iter, o);
-        else zz_process_node_k<ZZ_KIND_CSR, false>(g, v, j, H, incl, w0, cur, first_iter, o);
+        if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, ZZ_MODE_PLAIN>(g, v, j, H, incl, w0, cur, first_iter, o);
+        else zz_process_node_k<ZZ_KIND_CSR, ZZ_MODE_PLAIN>(g, v, j, H, incl, w0, cur, first_iter, o);
     }
 }
 

@@ -232,7 +232,7 @@ __device__ __forceinline__ void zz_mark4(const ZzParams& P, const int32_t (&kk)[
     if (issued) atomicAdd(&C->issued[nxt], (unsigned long long)issued);
 }
 
-template <int KIND, bool MULTI>
+template <int KIND, bool MULTI, int MODE>
 __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const ZzNodeOut& o, uint32_t w0,
                                            uint32_t cur, int nxt, int ws)
 {
@@ -245,6 +245,12 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
 #pragma unroll
         for (int m = 0; m < ZZ_MAXFLIP; ++m)
             if (m < (int)cnt) same = same && (zz_d2u(__ldcg(fl + m)) == zz_d2u(o.fl[m]));
+        if (MODE == ZZ_MODE_STICKY) {
+            const double* ft = P.v.fth + ((size_t)j * 2 + slot) * ZZ_MAXFLIP;
+#pragma unroll
+            for (int m = 0; m < ZZ_MAXFLIP; ++m)
+                if (m < (int)cnt) same = same && (zz_d2u(__ldcg(ft + m)) == zz_d2u(o.fth[m]));
+        }
     }
     if (!same) {
         const int wsl = (slot == 0) ? 1 : 0;
@@ -252,6 +258,12 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
 #pragma unroll
         for (int m = 0; m < ZZ_MAXFLIP; ++m)
             if (m < (int)o.nflip) fl[m] = o.fl[m];
+        if (MODE == ZZ_MODE_STICKY) {
+            double* ft = P.v.fth + ((size_t)j * 2 + wsl) * ZZ_MAXFLIP;
+#pragma unroll
+            for (int m = 0; m < ZZ_MAXFLIP; ++m)
+                if (m < (int)o.nflip) ft[m] = o.fth[m];
+        }
         reinterpret_cast<uint32_t*>(P.v.kin + j)[6 + wsl] = (cur << 4) | o.nflip;
         const uint32_t tagn = cur + 1;
         // queue the readers of j: all stamp updates are issued back to back (independent atomics in flight), then
@@ -286,24 +298,24 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
 
 // One timeline evaluation + publication; kept out of line so the three call sites (scan pass, relaxation pass,
 // tail pass) share one copy of the code and its register allocation.
-template <int KIND, bool MULTI, bool LB>
+template <int KIND, bool MULTI, int MODE>
 __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, double H, int incl, uint32_t w0,
                                              uint32_t cur, bool first, int nxt, int ws)
 {
     ZzNodeOut o;
 #ifdef ZZ_PROF_NODE
     const long long c0 = clock64();
-    zz_process_node_k<KIND, LB>(P.g, P.v, j, H, incl, w0, cur, first, o);
+    zz_process_node_k<KIND, MODE>(P.g, P.v, j, H, incl, w0, cur, first, o);
     const long long c1 = clock64();
-    zz_publish<KIND, MULTI>(P, j, o, w0, cur, nxt, ws);
+    zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws);
     const long long c2 = clock64();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.ctl->dbg[0] += (unsigned long long)(c2 - c1);   // cycles in publication
         P.ctl->dbg[7] += 1ULL;
     }
 #else
-    zz_process_node_k<KIND, LB>(P.g, P.v, j, H, incl, w0, cur, first, o);
-    zz_publish<KIND, MULTI>(P, j, o, w0, cur, nxt, ws);
+    zz_process_node_k<KIND, MODE>(P.g, P.v, j, H, incl, w0, cur, first, o);
+    zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws);
 #endif
 }
 
@@ -325,6 +337,7 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uin
     P.v.tau[j] = s.tau;
     P.v.kctr[j] = s.k;
     nprop_acc += s.nprop;
+    if (s.flags & ZZ_F_STICKY_ERR) atomicExch(&C->viol, 2u);      // error("x[i] !~ 0"), ss_fact.jl:89-91
     if (s.nflip) {
         nflip_acc += s.nflip;
         double th, tf, xf; uint32_t h0, h1;
@@ -343,12 +356,22 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uin
             pos = base + pre;
         }
         double a1 = __ldcg(P.s1 + j), a2 = __ldcg(P.s2 + j);
+        const double* ft = P.v.sticky ? P.v.fth + ((size_t)j * 2 + slot) * ZZ_MAXFLIP : nullptr;
+        unsigned int nrefl = 0;
         for (unsigned int m = 0; m < s.nflip; ++m) {
             const double fs = __ldcg(fl + m);
-            const double xs = xf + th * (fs - tf);
+            double xs, thn;
+            if (ft) {   // sticky: flip / freeze (velocity after = 0, x = -0*theta) / thaw (x stays 0), ss_fact.jl:87-123
+                thn = __ldcg(ft + m);
+                if (thn == 0.0) xs = -0.0 * th;
+                else if (th == 0.0) xs = xf;
+                else { xs = xf + th * (fs - tf); nrefl++; }
+            } else {
+                xs = xf + th * (fs - tf); thn = -th; nrefl++;
+            }
             a1 += (xf + xs) * (fs - tf);                          // trace.jl:194 (scaled by 1/(2T) on the host)
             a2 += (fs - tf) * (xf * xf + xf * xs + xs * xs);
-            th = -th; tf = fs; xf = xs;
+            th = thn; tf = fs; xf = xs;
             if (P.record_trace) {
                 if (pos + m < P.trace_cap) {
                     double2* e = reinterpret_cast<double2*>(P.trace + pos + m);   // sfact.jl:50-52
@@ -360,7 +383,7 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uin
             }
         }
         P.s1[j] = a1; P.s2[j] = a2;
-        P.acc[j] = __ldcg(P.acc + j) + s.nflip;
+        P.acc[j] = __ldcg(P.acc + j) + nrefl;            // accepted reflections (freezes and thaws are events, not acceptances)
         double2* kq = reinterpret_cast<double2*>(P.v.kin + j);
         kq[0] = make_double2(th, tf);
         reinterpret_cast<double*>(P.v.kin + j)[2] = xf;
@@ -404,7 +427,7 @@ zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ 
     }
 }
 
-template <int KIND, bool MULTI, bool LB>
+template <int KIND, bool MULTI, int MODE>
 __device__ __forceinline__ void zz_run_body(const ZzParams& P)
 {
     ZzDevCtl* C = P.ctl;
@@ -483,7 +506,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                 const int32_t j = sq[warp][q];
                 const uint32_t old = MULTI ? atomicMax_system(P.dstamp + j, cur) : atomicMax(P.dstamp + j, cur);
                 if (old < w0) zz_append<MULTI>(P.touched[0], &C->touched_cnt[ws], j);
-                zz_eval_publish<KIND, MULTI, LB>(P, j, H, incl, w0, cur, true, nxt, ws);
+                zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, true, nxt, ws);
                 st_evals++;
             }
             __syncwarp();
@@ -515,7 +538,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                         const int32_t* wlt = P.wl[li];
                         for (unsigned int e = threadIdx.x; e < n; e += blockDim.x) {
                             const int32_t j = __ldcg(wlt + e);
-                            zz_eval_publish<KIND, MULTI, LB>(P, j, H, incl, w0, cur, false, nxt, ws);
+                            zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, false, nxt, ws);
                             st_evals++;
                         }
                         __threadfence();
@@ -542,7 +565,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             const int32_t* wl = P.wl[li];
             for (unsigned int e = gtid; e < cw; e += nthreads) {
                 const int32_t j = __ldcg(wl + e);
-                zz_eval_publish<KIND, MULTI, LB>(P, j, H, incl, w0, cur, false, nxt, ws);
+                zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, false, nxt, ws);
                 st_evals++;
             }
             ZZ_TOC(1);
@@ -638,13 +661,15 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
     if (lane == 0 && st_evals) atomicAdd(&C->node_evals, st_evals);
 }
 
-#define ZZ_RUN_KERNEL(name, KIND, MULTI, LB) \
-    extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) name(const __grid_constant__ ZzParams P) { zz_run_body<KIND, MULTI, LB>(P); }
-ZZ_RUN_KERNEL(zz_run_kernel_grid, ZZ_KIND_GRID, false, false)
-ZZ_RUN_KERNEL(zz_run_kernel_csr, ZZ_KIND_CSR, false, false)
-ZZ_RUN_KERNEL(zz_run_kernel_grid_multi, ZZ_KIND_GRID, true, false)
-ZZ_RUN_KERNEL(zz_run_kernel_csr_multi, ZZ_KIND_CSR, true, false)
-ZZ_RUN_KERNEL(zz_run_kernel_grid_lb, ZZ_KIND_GRID, false, true)
-ZZ_RUN_KERNEL(zz_run_kernel_csr_lb, ZZ_KIND_CSR, false, true)
-ZZ_RUN_KERNEL(zz_run_kernel_grid_multi_lb, ZZ_KIND_GRID, true, true)
-ZZ_RUN_KERNEL(zz_run_kernel_csr_multi_lb, ZZ_KIND_CSR, true, true)
+#define ZZ_RUN_KERNEL(name, KIND, MULTI, MODE) \
+    extern "C" __global__ void __launch_bounds__(ZZ_BLOCK, ZZ_MINB) name(const __grid_constant__ ZzParams P) { zz_run_body<KIND, MULTI, MODE>(P); }
+ZZ_RUN_KERNEL(zz_run_kernel_grid, ZZ_KIND_GRID, false, ZZ_MODE_PLAIN)
+ZZ_RUN_KERNEL(zz_run_kernel_csr, ZZ_KIND_CSR, false, ZZ_MODE_PLAIN)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_multi, ZZ_KIND_GRID, true, ZZ_MODE_PLAIN)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_multi, ZZ_KIND_CSR, true, ZZ_MODE_PLAIN)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_lb, ZZ_KIND_GRID, false, ZZ_MODE_LB)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_lb, ZZ_KIND_CSR, false, ZZ_MODE_LB)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_multi_lb, ZZ_KIND_GRID, true, ZZ_MODE_LB)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_multi_lb, ZZ_KIND_CSR, true, ZZ_MODE_LB)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_sticky, ZZ_KIND_GRID, false, ZZ_MODE_STICKY)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_sticky, ZZ_KIND_CSR, false, ZZ_MODE_STICKY)

@@ -88,10 +88,10 @@ struct Global {
     CUdevice dev = 0; int dev_id = 0;
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
-    CUfunction f_setup = nullptr, f_init = nullptr, f_run[8] = {}, f_export = nullptr;
+    CUfunction f_setup = nullptr, f_init = nullptr, f_run[10] = {}, f_export = nullptr;
     CUstream stream = nullptr;
     CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
-    int sm_count = 0; int blocks_per_sm[8] = {};
+    int sm_count = 0; int blocks_per_sm[10] = {};
     size_t total_mem = 0; char name[128] = { 0 };
 };
 static Global G;
@@ -166,7 +166,12 @@ struct zzb_run_s {
     ZzDevCtl hc;                       // last copy of the device control block
     int64_t launches = 0;
     int grid = 0; int kind = 1;
-    int kidx() const { return kind + (nranks > 1 ? 2 : 0) + ((flags & ZZB_FLAG_LOCAL_BOUND) ? 4 : 0); }
+    int kidx() const
+    {
+        if (flags & ZZB_FLAG_STICKY) return 8 + kind;
+        return kind + (nranks > 1 ? 2 : 0) + ((flags & ZZB_FLAG_LOCAL_BOUND) ? 4 : 0);
+    }
+    DevBuf dfth, kappa; bool have_kappa = false;
     int rank = 0, nranks = 1, shard = 0, lo = 0, hi = 0;
     CUdeviceptr peer[ZZ_MAXRANKS][8] = {};   // imported mappings: kin, flips, dstamp, wl0, wl1, wl2, touched, ctl
     bool peer_open[ZZ_MAXRANKS] = {};
@@ -221,16 +226,18 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     CU(cuModuleGetFunction(&G.f_setup, G.mod, "zz_setup_kernel"));
     CU(cuModuleGetFunction(&G.f_init, G.mod, "zz_init_kernel"));
     // index = kind (0 lattice, 1 general) + 2 * multi-GPU + 4 * LocalBound
-    static const char* run_names[8] = { "zz_run_kernel_grid", "zz_run_kernel_csr", "zz_run_kernel_grid_multi", "zz_run_kernel_csr_multi",
-                                        "zz_run_kernel_grid_lb", "zz_run_kernel_csr_lb", "zz_run_kernel_grid_multi_lb", "zz_run_kernel_csr_multi_lb" };
-    for (int k = 0; k < 8; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
+    // 8, 9: sticky ZigZag (single GPU)
+    static const char* run_names[10] = { "zz_run_kernel_grid", "zz_run_kernel_csr", "zz_run_kernel_grid_multi", "zz_run_kernel_csr_multi",
+                                         "zz_run_kernel_grid_lb", "zz_run_kernel_csr_lb", "zz_run_kernel_grid_multi_lb", "zz_run_kernel_csr_multi_lb",
+                                         "zz_run_kernel_grid_sticky", "zz_run_kernel_csr_sticky" };
+    for (int k = 0; k < 10; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuStreamCreate(&G.stream, CU_STREAM_NON_BLOCKING));
     CU(cuEventCreate(&G.ev0, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.ev1, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.tev0, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.tev1, CU_EVENT_DEFAULT));
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < 10; ++k) {
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm[k], G.f_run[k], ZZ_BLOCK, 0));
         if (G.blocks_per_sm[k] < 1) return fail(ZZB_E_CUDA, "zz_run_kernel does not fit on an SM");
     }
@@ -322,6 +329,9 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
 {
     if (!p || !out) return fail(ZZB_E_ARG, "null argument");
     if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if ((flags & ZZB_FLAG_STICKY) && (flags & ZZB_FLAG_LOCAL_BOUND)) return fail(ZZB_E_ARG, "sticky and LocalBound cannot be combined");
+    if ((flags & ZZB_FLAG_STICKY) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB)
+        return fail(ZZB_E_ARG, "the sticky kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB, p->hg.maxdeg);
     if ((flags & ZZB_FLAG_LOCAL_BOUND) && !p->hg.bnd_eq_tgt)
         return fail(ZZB_E_ARG, "LocalBound builds its bound from the target: create the problem with the sampler matrix equal to the target (bnd_* = NULL) and Z.mu = 0");
     CtxGuard cg;
@@ -335,6 +345,7 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     AL(acc, d * 4); AL(s1, d * 8); AL(s2, d * 8); AL(wl[0], d * 4); AL(wl[1], d * 4); AL(wl[2], d * 4);
     AL(touched, d * 4); AL(ctl, sizeof(ZzDevCtl));
     AL(in_x, d * 8); AL(in_th, d * 8); AL(in_c, d * 8);
+    if (flags & ZZB_FLAG_STICKY) { AL(dfth, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(kappa, d * 8); }
     AL(out_t, d * 8); AL(out_x, d * 8); AL(out_th, d * 8); AL(out_c, d * 8); AL(out_acc, d * 8);
     if (!(flags & ZZB_FLAG_NO_TRACE)) {
         unsigned long long cap = (unsigned long long)std::max<int64_t>(trace_capacity_events, 0);
@@ -374,6 +385,9 @@ static void fill_params(zzb_run_s* r)
     P.ctl = r->ctl.as<ZzDevCtl>();
     P.record_trace = (r->flags & ZZB_FLAG_NO_TRACE) ? 0 : 1;
     P.v.local_bound = (r->flags & ZZB_FLAG_LOCAL_BOUND) ? 1 : 0;
+    P.v.sticky = (r->flags & ZZB_FLAG_STICKY) ? 1 : 0;
+    P.v.fth = P.v.sticky ? r->dfth.as<double>() : nullptr;
+    P.v.kappa = P.v.sticky ? r->kappa.as<double>() : nullptr;
     P.v.nranks = r->nranks; P.v.rank = r->rank; P.v.shard = r->shard; P.v.lo = r->lo; P.v.hi = r->hi;
     if (r->nranks > 1) {
         for (int q = 0; q < r->nranks; ++q) {
@@ -404,6 +418,7 @@ int32_t zzb_run_shard(zzb_run_t r, int32_t rank, int32_t nranks)
 {
     if (!r) return fail(ZZB_E_ARG, "null argument");
     if (nranks < 1 || nranks > ZZ_MAXRANKS || rank < 0 || rank >= nranks) return fail(ZZB_E_ARG, "bad rank %d of %d", rank, nranks);
+    if (nranks > 1 && (r->flags & ZZB_FLAG_STICKY)) return fail(ZZB_E_ARG, "the sticky sampler is not sharded yet");
     const int64_t d = r->d;
     int64_t shard = (d + nranks - 1) / nranks;
     const int64_t m = r->prob->g.grid_m;
@@ -462,6 +477,19 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     return ZZB_OK;
 }
 
+// Thaw rates kappa_i of the sticky sampler (ss_fact.jl:96); call before zzb_run_upload.
+int32_t zzb_run_upload_kappa(zzb_run_t r, const double* kappa)
+{
+    if (!r || !kappa) return fail(ZZB_E_ARG, "null argument");
+    if (!(r->flags & ZZB_FLAG_STICKY)) return fail(ZZB_E_ARG, "run was not created with ZZB_FLAG_STICKY");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    for (int32_t j = 0; j < r->d; ++j) if (!(kappa[j] > 0.0)) return fail(ZZB_E_ARG, "kappa[%d] must be positive", j + 1);
+    CtxGuard cg;
+    CU(cuMemcpyHtoD(r->kappa.p, kappa, (size_t)r->d * 8));
+    r->have_kappa = true;
+    return ZZB_OK;
+}
+
 // (Re)initialise the device state from the inputs already resident in HBM: per-coordinate records, initial
 // bounds and first proposal times (sfact.jl:167-187).  No host<->device traffic except the 200-byte control block.
 int32_t zzb_run_reset(zzb_run_t r)
@@ -469,6 +497,8 @@ int32_t zzb_run_reset(zzb_run_t r)
     if (!r) return fail(ZZB_E_ARG, "null argument");
     if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
     if (!r->have_inputs) return fail(ZZB_E_ARG, "zzb_run_upload must precede zzb_run_reset");
+    if ((r->flags & ZZB_FLAG_STICKY) && !r->have_kappa) return fail(ZZB_E_ARG, "zzb_run_upload_kappa must precede zzb_run_upload for a sticky run");
+    if ((r->flags & ZZB_FLAG_STICKY) && r->adapt) return fail(ZZB_E_ARG, "adapt is not supported by the sticky sampler on the device path");
     for (int q = 0; q < r->nranks; ++q)
         if (q != r->rank && !r->peer_open[q]) return fail(ZZB_E_ARG, "peer %d of a sharded run has not been imported", q);
     fill_params(r);
@@ -577,6 +607,7 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
     }
     if (device_ms) *device_ms = total_ms;
     r->executed = true; r->fetched = false;
+    if (r->hc.viol == 2u) return fail(ZZB_E_INTERNAL, "sticky sampler: a freezing coordinate was not at 0 (ss_fact.jl:89-91)");
     if (r->hc.viol) {
         if (P.record_trace && r->hc.trace_len) {
             std::vector<zzb_event> chunk((size_t)r->hc.trace_len);
@@ -631,6 +662,23 @@ int32_t zzb_spdmp_run(zzb_problem_t p, double t0, const double* x0, const double
     if (st == ZZB_E_BOUND)
         fail(ZZB_E_BOUND, "Tuning parameter `c` too small. (coordinate %d, t = %.17g, l = %.17g, lb = %.17g)", r->hc.viol_i,
              r->hc.viol_t, r->hc.viol_l, r->hc.viol_lb);
+    return st;
+}
+
+int32_t zzb_sspdmp_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, const double* c,
+                       const double* kappa, const uint64_t* seed, uint32_t flags, zzb_run_t* out)
+{
+    if (!out || !c || !kappa) return fail(ZZB_E_ARG, "null argument");
+    zzb_run_t r = nullptr;
+    int32_t st = zzb_run_create(p, flags | ZZB_FLAG_STICKY, 0, &r);
+    if (st) return st;
+    st = zzb_run_upload_kappa(r, kappa);
+    if (!st) st = zzb_run_upload(r, t0, x0, theta0, c, seed, 0, 1.0);
+    if (!st) st = zzb_run_execute(r, T, nullptr);
+    if (st && st != ZZB_E_BOUND) { zzb_run_free(r); return st; }
+    int32_t st2 = fetch_state(r);
+    if (st2) { zzb_run_free(r); return st2; }
+    *out = r;
     return st;
 }
 
