@@ -99,14 +99,17 @@ struct ZzView {
 };
 
 // where the authoritative record / flip lists of coordinate k live
+// (MG = false: single-GPU kernels, the test is compiled away)
+template <bool MG = true>
 ZZ_HD const ZzKin* zz_kin_at(const ZzView& v, int32_t k)
 {
-    if (v.nranks > 1) return v.kin_peer[k / v.shard] + k;
+    if (MG && v.nranks > 1) return v.kin_peer[k / v.shard] + k;
     return v.kin + k;
 }
+template <bool MG = true>
 ZZ_HD const double* zz_flips_at(const ZzView& v, int32_t k)
 {
-    if (v.nranks > 1) return v.flips_peer[k / v.shard] + (size_t)k * 2 * ZZ_MAXFLIP;
+    if (MG && v.nranks > 1) return v.flips_peer[k / v.shard] + (size_t)k * 2 * ZZ_MAXFLIP;
     return v.flips + (size_t)k * 2 * ZZ_MAXFLIP;
 }
 

@@ -63,7 +63,7 @@ ZZ_HD void zz_pool_add(ZzPool& pool, double fs, int m, uint32_t& flags, double t
     pool.t[p] = fs; pool.m[p] = m; pool.th[p] = tha; pool.n++;
 }
 
-template <int NB>
+template <int NB, bool MG>
 ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint32_t (&h0)[NB], const uint32_t (&h1)[NB],
                            int n, int self, uint32_t w0, uint32_t cur, ZzPool& pool, uint32_t& flags)
 {
@@ -74,7 +74,7 @@ ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint
             int slot;
             const uint32_t cnt = zz_pick_slot(h0[m], h1[m], w0, cur, slot);
             if (cnt) {
-                const double* fl = zz_flips_at(v, idx[m]) + slot * ZZ_MAXFLIP;
+                const double* fl = zz_flips_at<MG>(v, idx[m]) + slot * ZZ_MAXFLIP;
                 if (v.fth) {   // sticky lists carry the velocity after each event
                     const double* ft = v.fth + ((size_t)idx[m] * 2 + slot) * ZZ_MAXFLIP;
                     for (uint32_t q = 0; q < cnt; ++q) zz_pool_add(pool, zz_ld(fl + q), m, flags, zz_ld(ft + q));
@@ -87,7 +87,7 @@ ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint
 }
 
 // General sparse column (<= NB entries).  Returns false when the column is longer (caller uses the slow path).
-template <int NB>
+template <int NB, bool MG>
 ZZ_HD bool zz_gather_csr(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t w0, uint32_t cur, bool first_iter,
                          ZzHood<NB>& hd, ZzPool& pool, uint32_t& flags)
 {
@@ -108,15 +108,16 @@ ZZ_HD bool zz_gather_csr(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t 
         h0[m] = 0; h1[m] = 0; hd.th[m] = 0.0; hd.tf[m] = 0.0; hd.xf[m] = 0.0;
         if (m < n) {
             if (idx[m] == j) hd.self = m;
-            else zz_ld_kin(zz_kin_at(v, idx[m]), hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
+            else zz_ld_kin(zz_kin_at<MG>(v, idx[m]), hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
         }
     }
     pool.n = 0;
-    if (!first_iter) zz_gather_flips<NB>(v, idx, h0, h1, n, hd.self, w0, cur, pool, flags);
+    if (!first_iter) zz_gather_flips<NB, MG>(v, idx, h0, h1, n, hd.self, w0, cur, pool, flags);
     return true;
 }
 
 // 5-point lattice: column j = {j-M, j-1, j, j+1, j+M} (those that exist), weights -1 and shift + degree.
+template <bool MG>
 ZZ_HD void zz_gather_grid(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t w0, uint32_t cur, bool first_iter,
                           ZzHood<5>& hd, ZzPool& pool, uint32_t& flags)
 {
@@ -141,10 +142,10 @@ ZZ_HD void zz_gather_grid(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t
     }
 #pragma unroll
     for (int m = 0; m < 5; ++m)
-        if (m < n && m != self) zz_ld_kin(zz_kin_at(v, idx[m]), hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
+        if (m < n && m != self) zz_ld_kin(zz_kin_at<MG>(v, idx[m]), hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
     pool.n = 0;
     ZZ_SEG(1);
-    if (!first_iter) zz_gather_flips<5>(v, idx, h0, h1, n, self, w0, cur, pool, flags);
+    if (!first_iter) zz_gather_flips<5, MG>(v, idx, h0, h1, n, self, w0, cur, pool, flags);
 }
 
 // idot's over the gathered column at time s, storage order (common.jl:16-24)
@@ -367,7 +368,7 @@ ZZ_HD void zz_timeline_sticky(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w
 #define ZZ_MODE_PLAIN 0
 #define ZZ_MODE_LB 1       // LocalBound (src/local.jl)
 #define ZZ_MODE_STICKY 2   // sticky ZigZag (src/ss_fact.jl)
-template <int KIND, int MODE>
+template <int KIND, int MODE, bool MG = true>
 ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                              uint32_t cur, bool first_iter, ZzNodeOut& o)
 {
@@ -377,7 +378,7 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
         ZzHood<5> hd;
         ZZ_SEG(0);
         zz_load_own(v, j, w);
-        zz_gather_grid(g, v, j, w0, cur, first_iter, hd, pool, flags);
+        zz_gather_grid<MG>(g, v, j, w0, cur, first_iter, hd, pool, flags);
         ZZ_SEG(2);
         if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<5>(hd, pool, w, g, v, j, H, incl, flags, o);
         else zz_timeline<5, MODE == ZZ_MODE_LB>(hd, pool, w, g, v, j, H, incl, flags, o);
@@ -387,7 +388,7 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
     ZzHood<ZZ_NB> hd;
     if (g.nptr[j + 1] - g.nptr[j] <= ZZ_NB) {
         zz_load_own(v, j, w);
-        zz_gather_csr<ZZ_NB>(g, v, j, w0, cur, first_iter, hd, pool, flags);
+        zz_gather_csr<ZZ_NB, MG>(g, v, j, w0, cur, first_iter, hd, pool, flags);
         if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<ZZ_NB>(hd, pool, w, g, v, j, H, incl, flags, o);
         else zz_timeline<ZZ_NB, MODE == ZZ_MODE_LB>(hd, pool, w, g, v, j, H, incl, flags, o);
         return;

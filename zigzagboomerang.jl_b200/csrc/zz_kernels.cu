@@ -305,7 +305,7 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
     ZzNodeOut o;
 #ifdef ZZ_PROF_NODE
     const long long c0 = clock64();
-    zz_process_node_k<KIND, MODE>(P.g, P.v, j, H, incl, w0, cur, first, o);
+    zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, cur, first, o);
     const long long c1 = clock64();
     zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws);
     const long long c2 = clock64();
@@ -314,7 +314,7 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
         P.ctl->dbg[7] += 1ULL;
     }
 #else
-    zz_process_node_k<KIND, MODE>(P.g, P.v, j, H, incl, w0, cur, first, o);
+    zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, cur, first, o);
     zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws);
 #endif
 }
@@ -512,8 +512,8 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             __syncwarp();
         }
         ZZ_TOC(0);
-        ZzXres xr = zz_boundary<MULTI>(P, epoch, xep, prof, MULTI ? &C->issued[nxt] : nullptr, nullptr, &C->wl_cnt[nxt],
-                                       ZZ_OVF_BIT, ZZ_X_OVERFLOW);
+        ZzXres xr = zz_boundary<MULTI>(P, epoch, xep, prof, MULTI ? &C->issued[nxt] : nullptr, nullptr,
+                                       MULTI ? &C->wl_cnt[nxt] : nullptr, ZZ_OVF_BIT, ZZ_X_OVERFLOW);
         st_iters++;
 
         // ---------------- relaxation passes
@@ -522,7 +522,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             const unsigned int cwl = __ldcg(&C->wl_cnt[nxt]);            // this GPU's share of the next list
             const unsigned int cw = cwl & ~ZZ_OVF_BIT;
             const unsigned long long total = MULTI ? xr.sum : (unsigned long long)cw;
-            if (xr.flags & ZZ_X_OVERFLOW) { overflow = true; li = (li + 1) % 3u; break; }
+            if (MULTI ? (xr.flags & ZZ_X_OVERFLOW) != 0u : (cwl & ZZ_OVF_BIT) != 0u) { overflow = true; li = (li + 1) % 3u; break; }
             if (total == 0) break;
             if (!MULTI && cw <= ZZ_TAIL) {
                 // Few coordinates left (typically a couple of hot neighbours resolving a long causal chain one
@@ -554,7 +554,6 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                 zz_grid_barrier(C, epoch, prof);
                 li = __ldcg(&C->tail_li); cur = __ldcg(&C->tail_cur);
                 nxt = (int)((li + 1) % 3u);
-                xr.flags = (__ldcg(&C->wl_cnt[nxt]) & ZZ_OVF_BIT) ? ZZ_X_OVERFLOW : 0u;
                 continue;
             }
             li = (li + 1) % 3u;
@@ -569,8 +568,8 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                 st_evals++;
             }
             ZZ_TOC(1);
-            xr = zz_boundary<MULTI>(P, epoch, xep, prof, MULTI ? &C->issued[nxt] : nullptr, nullptr, &C->wl_cnt[nxt],
-                                    ZZ_OVF_BIT, ZZ_X_OVERFLOW);
+            xr = zz_boundary<MULTI>(P, epoch, xep, prof, MULTI ? &C->issued[nxt] : nullptr, nullptr,
+                                    MULTI ? &C->wl_cnt[nxt] : nullptr, ZZ_OVF_BIT, ZZ_X_OVERFLOW);
             st_iters++;
         }
         cur++;  // tag of the commit pass: every list written in this window is visible to it
