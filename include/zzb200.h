@@ -107,6 +107,9 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value);    /* "delta0",
 int32_t zzb_run_stats(zzb_run_t r, int64_t* out, int32_t n);        /* windows, retries, passes, node evaluations, rebases,
                                                                        kernel launches, grid size, block size */
 
+/* one-shot read-back straight into caller buffers (any may be NULL; pinned buffers copy at PCIe speed) */
+int32_t zzb_run_fetch(zzb_run_t r, double* t, double* x, double* theta, double* c, int64_t* acc, double* s1, double* s2,
+                      int64_t* num, int64_t* nacc);
 int32_t zzb_run_counts(zzb_run_t r, int64_t* acc, int64_t* num);
 int32_t zzb_run_final_state(zzb_run_t r, double* t, double* x, double* theta, double* c);
 int32_t zzb_trace_len(zzb_run_t r, int64_t* n);

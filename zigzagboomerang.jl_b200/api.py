@@ -251,6 +251,14 @@ class Run:
         check(st)
         return ms.value
 
+    def fetch_into(self, *, t=None, x=None, theta=None, c=None, acc=None, s1=None, s2=None):
+        """Read results straight into caller-provided arrays (float64 / int64 of length d; pinned memory copies at
+        PCIe speed).  Returns (num, nacc)."""
+        num, nacc = C.c_int64(), C.c_int64()
+        check(_capi.lib().zzb_run_fetch(self._h, ptr(t), ptr(x), ptr(theta), ptr(c), ptr(acc), ptr(s1), ptr(s2),
+                                        C.byref(num), C.byref(nacc)))
+        return num.value, nacc.value
+
     def counts(self):
         acc = np.empty(self.d, np.int64)
         num = C.c_int64()

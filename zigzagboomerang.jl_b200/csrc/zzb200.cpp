@@ -682,6 +682,36 @@ int32_t zzb_sspdmp_run(zzb_problem_t p, double t0, const double* x0, const doubl
     return st;
 }
 
+// Device -> caller buffers in one go (any pointer may be NULL): final (t, x, theta), adapted c, per-coordinate accepted
+// counts, moment sums, total proposals.  With pinned destination buffers the copies run at full PCIe speed; this is
+// the read-back used by the one-call path of a host wrapper that wants no intermediate copies.
+int32_t zzb_run_fetch(zzb_run_t r, double* t, double* x, double* theta, double* c, int64_t* acc, double* s1, double* s2,
+                      int64_t* num, int64_t* nacc)
+{
+    if (!r) return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (!r->uploaded) return fail(ZZB_E_ARG, "run has no state yet");
+    CtxGuard cg;
+    const size_t d = (size_t)r->d;
+    const unsigned grid = (unsigned)std::min<size_t>((d + ZZ_BLOCK - 1) / ZZ_BLOCK, (size_t)G.sm_count * 8);
+    CUdeviceptr pt = r->out_t.p, px = r->out_x.p, pth = r->out_th.p, pc = r->out_c.p, pa = r->out_acc.p;
+    void* a[] = { &r->P, &pt, &px, &pth, &pc, &pa };
+    CU(cuLaunchKernel(G.f_export, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a, nullptr));
+    r->launches++;
+    if (t) CU(cuMemcpyDtoHAsync(t, pt, d * 8, G.stream));
+    if (x) CU(cuMemcpyDtoHAsync(x, px, d * 8, G.stream));
+    if (theta) CU(cuMemcpyDtoHAsync(theta, pth, d * 8, G.stream));
+    if (c) CU(cuMemcpyDtoHAsync(c, pc, d * 8, G.stream));
+    if (acc) CU(cuMemcpyDtoHAsync(acc, pa, d * 8, G.stream));
+    if (s1) CU(cuMemcpyDtoHAsync(s1, r->s1.p, d * 8, G.stream));
+    if (s2) CU(cuMemcpyDtoHAsync(s2, r->s2.p, d * 8, G.stream));
+    CU(cuMemcpyDtoHAsync(&r->hc, r->ctl.p, sizeof(ZzDevCtl), G.stream));
+    CU(cuStreamSynchronize(G.stream));
+    if (num) *num = (int64_t)r->hc.num;
+    if (nacc) *nacc = (int64_t)r->hc.nacc;
+    return ZZB_OK;
+}
+
 int32_t zzb_run_stats(zzb_run_t r, int64_t* out, int32_t n)
 {
     if (!r || !out) return fail(ZZB_E_ARG, "null argument");
