@@ -45,7 +45,7 @@ static int32_t fail(int32_t code, const char* fmt, ...)
     X(cuStreamDestroy) X(cuStreamSynchronize) X(cuLaunchKernel) X(cuLaunchCooperativeKernel) X(cuEventCreate) \
     X(cuEventDestroy) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) X(cuGetErrorString) \
     X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemFreeHost) \
-    X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle)
+    X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle) X(cuModuleGetGlobal)
 
 struct Drv {
 #define X(name) decltype(&name) p_##name = nullptr;
@@ -91,7 +91,7 @@ struct Global {
     CUfunction f_setup = nullptr, f_init = nullptr, f_run[10] = {}, f_export = nullptr;
     CUstream stream = nullptr;
     CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
-    int sm_count = 0; int blocks_per_sm[10] = {};
+    int sm_count = 0; int blocks_per_sm[10] = {}; int run_block[2] = { 256, 256 };   // lattice / general-sparse kernels
     size_t total_mem = 0; char name[128] = { 0 };
 };
 static Global G;
@@ -237,8 +237,16 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     CU(cuEventCreate(&G.ev1, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.tev0, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.tev1, CU_EVENT_DEFAULT));
+    {   // block size the event-loop kernels were compiled for
+        static const char* names[2] = { "zz_run_block_grid", "zz_run_block_csr" };
+        for (int q = 0; q < 2; ++q) {
+            CUdeviceptr sym = 0; size_t symsz = 0;
+            if (g_drv.p_cuModuleGetGlobal(&sym, &symsz, G.mod, names[q]) == CUDA_SUCCESS && symsz == sizeof(int))
+                CU(cuMemcpyDtoH(&G.run_block[q], sym, sizeof(int)));
+        }
+    }
     for (int k = 0; k < 10; ++k) {
-        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm[k], G.f_run[k], ZZ_BLOCK, 0));
+        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm[k], G.f_run[k], G.run_block[k & 1], 0));
         if (G.blocks_per_sm[k] < 1) return fail(ZZB_E_CUDA, "zz_run_kernel does not fit on an SM");
     }
     G.ready = true;
@@ -581,7 +589,7 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
         CU(cuMemsetD8Async(r->ctl.p, 0, 8, G.stream));  // barrier counter
         void* args[] = { &P };
         CU(cuEventRecord(G.ev0, G.stream));
-        CU(cuLaunchCooperativeKernel(G.f_run[r->kidx()], (unsigned)r->grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, args));
+        CU(cuLaunchCooperativeKernel(G.f_run[r->kidx()], (unsigned)r->grid, 1, 1, (unsigned)G.run_block[r->kind], 1, 1, 0, G.stream, args));
         CU(cuEventRecord(G.ev1, G.stream));
         CU(cuStreamSynchronize(G.stream));
         r->launches++;
@@ -718,7 +726,7 @@ int32_t zzb_run_stats(zzb_run_t r, int64_t* out, int32_t n)
     int32_t st = fetch_state(r);
     if (st) return st;
     int64_t v[24] = { (int64_t)r->hc.windows, (int64_t)r->hc.retries, (int64_t)r->hc.iters, (int64_t)r->hc.node_evals,
-                      (int64_t)r->hc.rebases, r->launches, (int64_t)r->grid, (int64_t)ZZ_BLOCK };
+                      (int64_t)r->hc.rebases, r->launches, (int64_t)r->grid, (int64_t)G.run_block[r->kind] };
     for (int k = 0; k < 8; ++k) { v[8 + k] = (int64_t)r->hc.tprof[k]; v[16 + k] = (int64_t)r->hc.dbg[k]; }
     for (int32_t k = 0; k < n && k < 24; ++k) out[k] = v[k];
     return ZZB_OK;
