@@ -14,6 +14,8 @@
  *   zzb_run_counts                the returned (acc, num)                                        src/sfact.jl:181-182,211
  *   zzb_run_final_state           the returned (t, x, theta) and the adapted c                   src/sfact.jl:211
  *   zzb_trace_len / _copy         the returned FactTrace's `events` vector                       src/trace.jl:7-13,38
+ *   zzb_run_set("max_windows") + zzb_run_execute(T = Inf) + zzb_trace_copy / _clear
+ *                                 the pull-style iterator FactSampler / iterate / trace(FS, T)   src/sfactiter.jl:5-79
  *   zzb_trace_moments             Statistics.mean(::Trace) (src/trace.jl:182-200) + matching exact second moment
  *   zzb_sspdmp_run                sspdmp(...) src/ss_fact.jl:159-217 with sspdmp_inner! :78-157, queue_time! :54-66,
  *                                 freezing_time :10-16
@@ -114,6 +116,7 @@ int32_t zzb_run_counts(zzb_run_t r, int64_t* acc, int64_t* num);
 int32_t zzb_run_final_state(zzb_run_t r, double* t, double* x, double* theta, double* c);
 int32_t zzb_trace_len(zzb_run_t r, int64_t* n);
 int32_t zzb_trace_copy(zzb_run_t r, zzb_event* dst, int64_t first, int64_t count);
+int32_t zzb_trace_clear(zzb_run_t r);                                 /* streaming: drop the events already copied out */
 int32_t zzb_trace_moments(zzb_run_t r, double* m1, double* m2);     /* time averages of x and x^2 over [t0, last event] */
 int32_t zzb_trace_sums(zzb_run_t r, double* s1, double* s2);        /* the unscaled device accumulators */
 int32_t zzb_run_error_info(zzb_run_t r, int64_t* i, double* t, double* l, double* lb);  /* after ZZB_E_BOUND */

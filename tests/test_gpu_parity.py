@@ -214,3 +214,18 @@ def test_sticky_1d_closed_form_on_gpu(gpu):
     assert abs(np.mean(xs != 0) - w) < 2.5 / math.sqrt(T)
     assert abs(xs.mean() - w * mu) < 5.0 / math.sqrt(T)
     assert abs((xs ** 2).mean() - w * (sigma ** 2 + mu ** 2)) < 5.0 / math.sqrt(T)
+
+
+def test_fact_sampler_iterator(gpu):
+    """FactSampler / trace(FS, T) (src/sfactiter.jl): pulled events equal the one-shot trace (prefix), in time order."""
+    import itertools
+    G, x0, th0, c = gpu.gmrf_config(16)
+    Z = gpu.ZigZag(G, np.zeros(G.n))
+    ref = O.spdmp(G, G, 0.0, x0, th0, 6.0, c, seed=(1, 2))
+    FS = gpu.FactSampler(gpu.GaussianPotential(G), (0.0, (x0, th0)), c, Z, seed=(1, 2), windows_per_pull=3)
+    got = list(itertools.islice(iter(FS), 500))
+    assert [e[1][1] for e in got] == ref.events["i"][:500].tolist()
+    assert [e[0] for e in got] == ref.events["t"][:500].tolist()
+    tr = gpu.trace(FS, 3.0)      # drops the first event (upstream quirk) and stops at the first event with t > T
+    n = int(np.searchsorted(ref.events["t"], 3.0, side="right"))
+    assert np.array_equal(tr.events["t"], ref.events["t"][1:n]) and np.array_equal(tr.events["i"], ref.events["i"][1:n])

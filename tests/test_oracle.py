@@ -243,3 +243,16 @@ def test_sticky_large_kappa_matches_plain_moments(zzb):
     a = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, 100.0, 0.7 * G.colnorms(), kappa=np.full(d, 2.0), mode=O.RNG_CTR | O.ARITH_INPLACE)
     b = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, 100.0, 0.7 * G.colnorms(), kappa=np.full(d, 2.0), mode=O.PARITY_MODE)
     assert a.num == b.num and np.array_equal(a.events["i"], b.events["i"]) and np.allclose(a.events["t"], b.events["t"], atol=1e-10)
+
+
+def test_trace_postprocessing_mirrors(zzb):
+    """cummean / inclusion_prob mirrors of src/trace.jl:161-225 on an oracle trace."""
+    G, x0, th0, c = zzb.gmrf_config(6)
+    r = O.spdmp(G, G, 0.0, x0, th0, 30.0, c, kappa=np.full(G.n, 0.7))
+    tr = zzb.FactTrace(None, 0.0, x0, th0, r.events)
+    cm = zzb.cummean(tr)
+    last = np.array([ys[1][-1] for ys in cm])
+    tl = np.array([ys[0][-1] for ys in cm])
+    assert np.allclose(last, r.s1 / (2 * tl), rtol=1e-12)       # running mean at the coordinate's last event
+    p = zzb.inclusion_prob(tr)
+    assert np.all(p > 0) and np.all(p <= 1.0 + 1e-12) and p.mean() < 0.999   # sticky: some time is spent at 0

@@ -278,6 +278,9 @@ class Run:
             check(_capi.lib().zzb_trace_copy(self._h, ptr(ev), 0, n.value))
         return ev
 
+    def clear_events(self):
+        check(_capi.lib().zzb_trace_clear(self._h))
+
     def n_events(self) -> int:
         n = C.c_int64()
         check(_capi.lib().zzb_trace_len(self._h, C.byref(n)))
@@ -406,3 +409,82 @@ def sspdmp(grad, t0, x0, theta0, T, c, *rest, seed=None, record_trace=True, tune
         run.close()
         if own:
             prob.close()
+
+
+class FactSampler:
+    """``FactSampler(grad, u0, c, [G,] F; factor=1.8, adapt=false, seed)`` with ``u0 = (t0, (x0, theta0))`` -- the pull-style
+    interface of src/sfactiter.jl:5-64.  Iterating yields ``(t, (t, i, x_i, theta_i))`` pairs, one per accepted event, in
+    time order, for ever; the device simulates `windows_per_pull` windows ahead at a time and hands the events over."""
+
+    def __init__(self, grad, u0, c, *rest, factor=1.8, adapt=False, seed=None, windows_per_pull=16):
+        rest = list(rest)
+        if rest and (rest[0] is None or isinstance(rest[0], (All, Matched))):
+            rest.pop(0)
+        self.F = rest[0]
+        self.grad, self.u0, self.c = grad, u0, c
+        self.factor, self.adapt = factor, adapt
+        self.seed = seed if seed is not None else (secrets.randbits(64), secrets.randbits(64))
+        self.windows_per_pull = int(windows_per_pull)
+
+    def __iter__(self):
+        t0, (x0, th0) = self.u0
+        local_bound = isinstance(self.c, LocalBound)
+        prob, own = _as_problem(self.grad, self.F)
+        run = Run(prob, record_trace=True, local_bound=local_bound)
+        try:
+            run.set(max_windows=self.windows_per_pull)
+            run.upload(t0, x0, th0, self.c.c if local_bound else self.c, seed=self.seed, adapt=self.adapt, factor=self.factor)
+            while True:
+                run.execute(np.inf)          # a bounded slice of windows; the controller state persists on the device
+                ev = run.events()
+                run.clear_events()
+                for e in ev:
+                    yield float(e["t"]), (float(e["t"]), int(e["i"]), float(e["x"]), float(e["theta"]))
+        finally:
+            run.close()
+            if own:
+                prob.close()
+
+
+def trace(FS: FactSampler, T):
+    """``trace(FS, T)`` (src/sfactiter.jl:66-79), including its quirk: the first event of the iteration is consumed and
+    not stored; events with t > T end the collection."""
+    t0, (x0, th0) = FS.u0
+    it = iter(FS)
+    next(it)
+    out = []
+    for t, ev in it:
+        if t > T:
+            break
+        out.append(ev)
+    it.close()
+    return FactTrace(FS.F, t0, x0, th0, np.array(out, dtype=EVENT_DTYPE))
+
+
+def cummean(tr: FactTrace):
+    """``cummean(trace)`` (src/trace.jl:203-225): per coordinate the running time-average at each of its events."""
+    x = tr.x0.copy()
+    y = np.zeros_like(x)
+    t = np.full(len(x), tr.t0)
+    ys = [([tr.t0], [xi]) for xi in x]
+    for t2, i, xi, _ in tr.events:
+        y[i - 1] += (x[i - 1] + xi) * (t2 - t[i - 1])
+        t[i - 1] = t2
+        x[i - 1] = xi
+        ys[i - 1][0].append(t2)
+        ys[i - 1][1].append(y[i - 1] / (2 * t2))
+    return ys
+
+
+def inclusion_prob(tr: FactTrace):
+    """``inclusion_prob(trace)`` (src/trace.jl:161-178): fraction of time a coordinate is away from 0 (sticky samplers).
+    Julia parses ``x[i] != 0 | xi != 0`` as ``x[i] != (0 | xi) != 0``; the evident intent (either end non-zero) is used."""
+    x = tr.x0.copy()
+    y = np.zeros_like(x)
+    T = tr.events["t"][-1]
+    t = np.full(len(x), tr.t0)
+    for t2, i, xi, _ in tr.events:
+        y[i - 1] += float((x[i - 1] != 0) or (xi != 0)) * (t2 - t[i - 1]) / T
+        t[i - 1] = t2
+        x[i - 1] = xi
+    return y

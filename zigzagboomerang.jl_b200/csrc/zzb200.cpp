@@ -777,6 +777,14 @@ int32_t zzb_trace_copy(zzb_run_t r, zzb_event* dst, int64_t first, int64_t count
     return ZZB_OK;
 }
 
+// Forget the events handed out so far (streaming use: execute a bounded number of windows, copy, clear, repeat).
+int32_t zzb_trace_clear(zzb_run_t r)
+{
+    if (!r) return fail(ZZB_E_ARG, "null argument");
+    r->events.clear();
+    return ZZB_OK;
+}
+
 int32_t zzb_trace_sums(zzb_run_t r, double* s1, double* s2)
 {
     if (!r) return fail(ZZB_E_ARG, "null argument");
