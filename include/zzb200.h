@@ -19,6 +19,8 @@
  *   zzb_trace_moments             Statistics.mean(::Trace) (src/trace.jl:182-200) + matching exact second moment
  *   zzb_sspdmp_run                sspdmp(...) src/ss_fact.jl:159-217 with sspdmp_inner! :78-157, queue_time! :54-66,
  *                                 freezing_time :10-16
+ *   zzb_spdmp_boomerang_run       spdmp / pdmp with F::FactBoomerang: flow src/sfact.jl:29-48, rate src/fact_samplers.jl:37-39,
+ *                                 constant bound :58-65, velocity refreshment src/sfact.jl:78-114 (types.jl:62-79)
  *   flag ZZB_FLAG_LOCAL_BOUND     the LocalBound methods: ab src/local.jl:2-6, spdmp_inner! :10-78, spdmp/pdmp :95-149,
  *                                 next_time src/not_fact_samplers.jl:43-50
  *   status ZZB_E_BOUND            error("Tuning parameter `c` too small.")                       src/sfact.jl:124
@@ -53,6 +55,7 @@ extern "C" {
                                    second directional derivatives, valid for 2/c/|theta|, then renewed (problem: bnd_* = NULL) */
 
 #define ZZB_FLAG_STICKY 4u      /* sticky ZigZag sspdmp (src/ss_fact.jl): coordinates freeze at 0, thaw after Exp(kappa_i) */
+#define ZZB_FLAG_BOOMERANG 8u   /* factorised Boomerang (F::FactBoomerang): rotation around Z.mu, velocity refreshments */
 
 typedef struct zzb_problem_s* zzb_problem_t;
 typedef struct zzb_run_s* zzb_run_t;
@@ -90,6 +93,15 @@ int32_t zzb_spdmp_run(zzb_problem_t p, double t0, const double* x0, const double
 int32_t zzb_sspdmp_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, const double* c,
                        const double* kappa, const uint64_t* seed, uint32_t flags, zzb_run_t* out);
 
+/* Factorised Boomerang, spdmp(grad, t0, x0, th0, T, c, FactBoomerang(Gamma, mu, lambdaref, sigma; rho), ...) (src/sfact.jl:162-214
+ * with the FactBoomerang methods; the problem's bnd_* / bnd_mu are Z.Gamma / Z.mu).  sigma[d] scales the refreshed
+ * velocities (types.jl:79: diag(Gamma)^-1/2), lambdaref > 0 is the total refreshment rate, rho the autoregression
+ * coefficient of the refreshment.  The trace holds reflections and refreshments; zzb_run_counts the reflections.
+ * c is in/out like zzb_spdmp_run. */
+int32_t zzb_spdmp_boomerang_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, double* c,
+                                const double* sigma, double lambdaref, double rho, const uint64_t* seed, int32_t adapt,
+                                double factor, uint32_t flags, zzb_run_t* out);
+
 /* Staged form (what zzb_spdmp_run is made of); lets a caller keep inputs resident in HBM and time the kernel alone. */
 int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_events, zzb_run_t* out);
 int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* theta0, const double* c,
@@ -103,6 +115,7 @@ int32_t zzb_run_ipc_export(zzb_run_t r, void* buf, int64_t cap, int64_t* len);
 int32_t zzb_run_ipc_import(zzb_run_t r, int32_t peer_rank, const void* buf, int64_t len);
 int32_t zzb_run_range(zzb_run_t r, int64_t* lo, int64_t* hi);       /* owned coordinates [lo, hi), 0-based */
 int32_t zzb_run_upload_kappa(zzb_run_t r, const double* kappa);      /* sticky runs: before zzb_run_upload */
+int32_t zzb_run_upload_boomerang(zzb_run_t r, const double* sigma, double lambdaref, double rho);  /* Boomerang runs: before zzb_run_upload */
 int32_t zzb_run_reset(zzb_run_t r);                                  /* re-initialise from the inputs resident in HBM */
 int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms);   /* device_ms: CUDA-event time of the kernel(s) */
 int32_t zzb_run_set(zzb_run_t r, const char* key, double value);    /* "delta0", "target_frac" / "target_flip_frac" (proposals / accepted flips per window over d), "tag_limit", "max_windows", "grid" */

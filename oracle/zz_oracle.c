@@ -43,13 +43,14 @@
  *              Delta = 2/c/|theta| and is then renewed.  The target descriptor plays the role of the extended-form
  *              closure: (grad phi_i, v_i) = (idot(G,i,x) - h_i, theta_i idot(G,i,theta)) (local.jl:7).
  * GPU results must equal mode ctr|lazy (|8) bit for bit.
+ * Further entry points below: zzo_sspdmp (sticky ZigZag, src/ss_fact.jl) and zzo_spdmp_boom (FactBoomerang).
  */
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
 
-#include "../zigzagboomerang.jl_b200/csrc/zz_math.h" /* zz_log, zz_u01 only (shared primitives) */
+#include "../zigzagboomerang.jl_b200/csrc/zz_math.h" /* zz_log, zz_u01, zz_sincos / zz_boom_at (shared primitives) */
 
 #define ZZO_RNG_CTR 1
 #define ZZO_ARITH_LAZY 2
@@ -602,6 +603,194 @@ zzo_run *zzo_sspdmp(int64_t d,
     free(z->g2ptr); free(z->g2idx);
     return r;
 }
+
+/* =====================================================================================================
+ * Factorised Boomerang in spdmp / pdmp (src/sfact.jl:29-48,73-145,162-212 with F::FactBoomerang):
+ *   flow                     sfact.jl:29-38 / dynamics.jl:29-36 (rotation of (x - mu, theta), `sincos` -> zz_sincos)
+ *   lambda                   fact_samplers.jl:37-39     pos((grad_i - (x_i - mu_i) Gamma_ii) theta_i)
+ *   ab                       fact_samplers.jl:58-65     a = c_i sqrt(x_i^2 + th_i^2) z + (x_i^2 + th_i^2) Gamma_ii, b = 0
+ *   refreshment              sfact.jl:78-114, hasrefresh fact_samplers.jl:18, waiting_time_ref dynamics.jl:100-101
+ * RNG seq  : ONE stream in the reference's call order; the reference draws the refreshed coordinate TWICE from Julia's
+ *            global RNG (sfact.jl:80,84: the neighbourhood of the first pick is moved, the velocity of the second is
+ *            refreshed at ITS stale local time) -- reproduced literally with arithmetic inplace.
+ * RNG ctr  : (GPU parity contract) the single clock of rate lambda_ref picking a uniform coordinate is replaced by the
+ *            equal-in-law superposition of d independent clocks of rate lambda_ref/d, one per coordinate, each drawing
+ *            from its coordinate's counter stream; the refreshment is applied at the event time.  Draw roles per
+ *            coordinate: first proposal (k=0), first refreshment time (k=1); a proposal consumes (thinning, reschedule);
+ *            a neighbour's event consumes (reschedule); a refreshment consumes (2 for the normal, next refreshment time)
+ *            and then the reschedule of the coordinate itself.
+ * randn is Box-Muller on two uniforms (Julia: ziggurat; equal in law).
+ * ===================================================================================================== */
+typedef struct { const double *mu, *sigma; double lref, rho, rhobar; double *diag; } boomp;
+
+static void b_at(const ctx *z, const boomp *B, int64_t k, double s, double *x, double *th)
+{ /* lazy: anchor (tf, xf, th) of coordinate k (1-based) rotated to time s */
+    zz_boom_at(z->tf[k - 1], z->xf[k - 1], z->th[k - 1], B->mu[k - 1], s, x, th);
+}
+static void b_move(ctx *z, const boomp *B, const int64_t *idx, int64_t n, double tp)
+{ /* smove_forward!(G, i, ..., B), sfact.jl:29-38 (inplace) */
+    for (int64_t q = 0; q < n; ++q) {
+        int64_t k = idx[q] - 1;
+        double sn, cs; zz_sincos(tp - z->t[k], &sn, &cs);
+        double xm = z->x[k] - B->mu[k];
+        double xn = xm * cs + z->th[k] * sn + B->mu[k];
+        double tn = -xm * sn + z->th[k] * cs;
+        z->t[k] = tp; z->x[k] = xn; z->th[k] = tn;
+    }
+}
+static void b_move_all(ctx *z, const boomp *B, double tp)
+{ /* sfact.jl:40-48 */
+    for (int64_t k = 1; k <= z->d; ++k) b_move(z, B, &k, 1, tp);
+}
+/* ab(G,i,x,th,c,Z::FactBoomerang), fact_samplers.jl:58-65; positions/velocities at time s (lazy) or as stored (inplace) */
+static void ab_boom(ctx *z, const boomp *B, int64_t i, double s)
+{
+    const int lazy = (z->mode & ZZO_ARITH_LAZY) != 0;
+    double sum = 0.0, xi = 0.0, thi = 0.0; int first = 1, found = 0;
+    for (int64_t p = z->bd.colptr[i - 1]; p < z->bd.colptr[i]; ++p) {   /* sum(... for j in nhd): left fold in storage order */
+        int64_t j = z->bd.rowval[p - 1];
+        double xj, thj;
+        if (lazy) b_at(z, B, j, s, &xj, &thj); else { xj = z->x[j - 1]; thj = z->th[j - 1]; }
+        double term = (xj - B->mu[j - 1]) * (xj - B->mu[j - 1]) + thj * thj;
+        sum = first ? term : sum + term; first = 0;
+        if (j == i) { xi = xj; thi = thj; found = 1; }
+    }
+    if (!found) { if (lazy) b_at(z, B, i, s, &xi, &thi); else { xi = z->x[i - 1]; thi = z->th[i - 1]; } }
+    double zz = sqrt(sum);
+    double z2 = xi * xi + thi * thi;
+    z->ba[i - 1] = z->c[i - 1] * sqrt(z2) * zz + z2 * B->diag[i - 1];
+    z->bb[i - 1] = 0.0;
+}
+static double b_grad(ctx *z, const boomp *B, int64_t i, double s, const double *h)
+{ /* the user closure idot(Gamma, i, x) [- h_i], common.jl:16-24 */
+    double acc = 0.0;
+    if (!(z->mode & ZZO_ARITH_LAZY)) acc = idot(&z->tg, i, z->x);
+    else for (int64_t p = z->tg.colptr[i - 1]; p < z->tg.colptr[i]; ++p) {
+        double xj, thj; b_at(z, B, z->tg.rowval[p - 1], s, &xj, &thj);
+        acc += z->tg.nzval[p - 1] * xj;
+    }
+    if (h) acc = acc - h[i - 1];
+    return acc;
+}
+
+zzo_run *zzo_spdmp_boom(int64_t d,
+                        const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
+                        const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
+                        const double *sigma, double lambdaref, double rho,
+                        double t0, const double *x0, const double *th0, double T, const double *c_in,
+                        const uint64_t *seed, int adapt, double factor, int mode)
+{
+    zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run));
+    ctx zs; ctx *z = &zs; memset(z, 0, sizeof(ctx));
+    r->d = d; r->mode = mode; r->t0 = t0;
+    z->d = d; z->mode = mode;
+    z->tg.colptr = tg_colptr; z->tg.rowval = tg_rowval; z->tg.nzval = tg_nzval;
+    z->bd.colptr = bd_colptr; z->bd.rowval = bd_rowval; z->bd.nzval = bd_nzval;
+    z->h = h; z->mu = mu;
+    size_t nb = (size_t)d * sizeof(double);
+    z->t = (double *)malloc(nb); z->x = (double *)malloc(nb); z->th = (double *)malloc(nb);
+    z->t_old = (double *)malloc(nb); z->ba = (double *)malloc(nb); z->bb = (double *)malloc(nb);
+    z->c = (double *)malloc(nb); z->tf = (double *)malloc(nb); z->xf = (double *)malloc(nb);
+    z->kctr = (uint32_t *)calloc((size_t)d, sizeof(uint32_t));
+    r->acc = (int64_t *)calloc((size_t)d, sizeof(int64_t));
+    r->x0 = (double *)malloc(nb); memcpy(r->x0, x0, nb);
+    z->s0 = seed[0]; z->s1 = seed[1]; z->rng.x = seed[0]; z->rng.y = seed[1];
+    const int lazy = (mode & ZZO_ARITH_LAZY) != 0, all = (mode & ZZO_GRAPH_ALL) != 0, ctr = (mode & ZZO_RNG_CTR) != 0;
+    boomp B; B.mu = mu; B.sigma = sigma; B.lref = lambdaref; B.rho = rho; B.rhobar = sqrt(1 - rho * rho);
+    B.diag = (double *)calloc((size_t)d, sizeof(double));
+    for (int64_t i = 1; i <= d; ++i)  /* Z.Gamma[i,i] (sparse getindex: 0 when not stored) */
+        for (int64_t p = bd_colptr[i - 1]; p < bd_colptr[i]; ++p)
+            if (bd_rowval[p - 1] == i) B.diag[i - 1] = bd_nzval[p - 1];
+    double tp = t0;
+    for (int64_t k = 0; k < d; ++k) {
+        z->t[k] = t0; z->t_old[k] = t0; z->x[k] = x0[k]; z->th[k] = th0[k]; z->c[k] = c_in[k];
+        z->tf[k] = t0; z->xf[k] = x0[k];
+    }
+    if (!all && !lazy) build_g2(z);
+    /* keys 1..d: reflections; seq: key d+1 = the refreshment clock (sfact.jl:188-190); ctr: keys d+1..2d = one clock per coordinate */
+    heapq Q; Q.n = 0; Q.lex = ctr;
+    Q.key = (int64_t *)malloc((2 * (size_t)d + 2) * sizeof(int64_t));
+    Q.val = (double *)malloc((2 * (size_t)d + 2) * sizeof(double));
+    Q.index = (int64_t *)malloc((2 * (size_t)d + 2) * sizeof(int64_t));
+    const double lam1 = ctr ? lambdaref / (double)d : lambdaref;
+    for (int64_t i = 1; i <= d; ++i) ab_boom(z, &B, i, t0);
+    for (int64_t i = 1; i <= d; ++i) h_enqueue(&Q, i, o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i))); /* sfact.jl:186, no + t0 */
+    if (ctr) { for (int64_t i = 1; i <= d; ++i) h_enqueue(&Q, d + i, -zz_log(draw(z, i)) / lam1); }
+    else h_enqueue(&Q, d + 1, -zz_log(xoro_rand(&z->rng)) / lam1);   /* waiting_time_ref(rng, F), no + t0 either */
+
+    int64_t num = 0;
+    while (tp < T && r->status == ZZO_OK) {
+        for (;;) {
+            int64_t i = Q.key[1]; tp = Q.val[1];
+            const int refresh = i > d;
+            int64_t qkey = i;
+            if (refresh) i = ctr ? i - d : (int64_t)(xoro_rand(&z->rng) * (double)d) + 1;          /* :80 rand(1:n) */
+            const int64_t *nbv = &z->bd.rowval[z->bd.colptr[i - 1] - 1];
+            int64_t nnb = z->bd.colptr[i] - z->bd.colptr[i - 1];
+            if (!lazy) { if (all) b_move_all(z, &B, tp); else b_move(z, &B, nbv, nnb, tp); }       /* :82 */
+            if (refresh) {
+                if (!ctr) i = (int64_t)(xoro_rand(&z->rng) * (double)d) + 1;                       /* :84 second pick */
+                nbv = &z->bd.rowval[z->bd.colptr[i - 1] - 1]; nnb = z->bd.colptr[i] - z->bd.colptr[i - 1];
+                if (!lazy && !all) b_move(z, &B, &z->g2idx[z->g2ptr[i - 1]], z->g2ptr[i] - z->g2ptr[i - 1], tp); /* :85 */
+                double u1 = draw(z, i), u2 = draw(z, i);
+                double xi, thi;
+                if (lazy) { b_at(z, &B, i, tp, &xi, &thi); z->xf[i - 1] = xi; z->tf[i - 1] = tp; }
+                else { xi = z->x[i - 1]; thi = z->th[i - 1]; }
+                z->th[i - 1] = B.rho * thi + B.rhobar * B.sigma[i - 1] * zz_randn(u1, u2);         /* :102 */
+                h_set(&Q, qkey, tp - zz_log(ctr ? draw(z, i) : xoro_rand(&z->rng)) / lam1);        /* :108 */
+                for (int64_t q = 0; q < nnb; ++q) {                                                /* :110-114 */
+                    int64_t j = nbv[q];
+                    ab_boom(z, &B, j, tp);
+                    double tj = lazy ? tp : z->t[j - 1];
+                    z->t_old[j - 1] = tj;
+                    h_set(&Q, j, tj + o_poisson_time(z->ba[j - 1], z->bb[j - 1], draw(z, j)));
+                }
+                push_event(r, lazy ? tp : z->t[i - 1], i, lazy ? z->xf[i - 1] : z->x[i - 1], z->th[i - 1]);
+                break;
+            }
+            double xi, thi;
+            if (lazy) b_at(z, &B, i, tp, &xi, &thi); else { xi = z->x[i - 1]; thi = z->th[i - 1]; }
+            double gi = b_grad(z, &B, i, tp, h);                                                   /* :118 */
+            double ti = lazy ? tp : z->t[i - 1];
+            double l = zz_pos((gi - (xi - B.mu[i - 1]) * B.diag[i - 1]) * thi);                    /* fact_samplers.jl:37-39 */
+            double lb = zz_pos(z->ba[i - 1] + z->bb[i - 1] * (ti - z->t_old[i - 1]));
+            num += 1;
+            if (draw(z, i) * lb < l) {
+                r->acc[i - 1] += 1;
+                if (l >= lb) {
+                    if (!adapt) { r->status = ZZO_E_BOUND; r->err_i = i; r->err_t = tp; r->err_l = l; r->err_lb = lb; break; }
+                    z->c[i - 1] *= factor;
+                }
+                if (!lazy && !all) b_move(z, &B, &z->g2idx[z->g2ptr[i - 1]], z->g2ptr[i] - z->g2ptr[i - 1], tp);
+                if (lazy) { z->xf[i - 1] = xi; z->tf[i - 1] = tp; }
+                z->th[i - 1] = -thi;                                                               /* dynamics.jl:46-49 */
+                for (int64_t q = 0; q < nnb; ++q) {
+                    int64_t j = nbv[q];
+                    ab_boom(z, &B, j, tp);
+                    double tj = lazy ? tp : z->t[j - 1];
+                    z->t_old[j - 1] = tj;
+                    h_set(&Q, j, tj + o_poisson_time(z->ba[j - 1], z->bb[j - 1], draw(z, j)));
+                }
+                push_event(r, ti, i, lazy ? z->xf[i - 1] : z->x[i - 1], z->th[i - 1]);
+                break;
+            } else {
+                ab_boom(z, &B, i, tp);
+                z->t_old[i - 1] = ti;
+                h_set(&Q, i, ti + o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i)));
+            }
+        }
+    }
+    r->num = num;
+    r->t = lazy ? z->tf : z->t; r->x = lazy ? z->xf : z->x; r->th = z->th; r->c = z->c;
+    if (lazy) { free(z->t); free(z->x); } else { free(z->tf); free(z->xf); }
+    free(z->t_old); free(z->ba); free(z->bb); free(z->kctr); free(B.diag);
+    free(Q.key); free(Q.val); free(Q.index);
+    free(z->g2ptr); free(z->g2idx);
+    return r;
+}
+
+void zzo_sincos(double x, double *s, double *c) { zz_sincos(x, s, c); }
+double zzo_randn(double u1, double u2) { return zz_randn(u1, u2); }
 
 int zzo_status(const zzo_run *r) { return r->status; }
 void zzo_error_info(const zzo_run *r, int64_t *i, double *t, double *l, double *lb)

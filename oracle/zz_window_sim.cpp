@@ -8,7 +8,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "../zigzagboomerang.jl_b200/csrc/zz_core.h"
@@ -35,7 +37,8 @@ extern "C" {
 zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const double* tnz, const double* h,
                    const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
                    const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
-                   int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound, const double* kappa)
+                   int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound, const double* kappa,
+                   const double* boom_sigma, double boom_lambdaref, double boom_rho)
 {
     zzw_run* r = new zzw_run();
     r->d = d;
@@ -61,7 +64,11 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
     for (int q = 0; q < 5; ++q) g.grid_diag[q] = G.grid_diag[q];
     ZzView v; memset(&v, 0, sizeof v); v.nranks = 1; v.hi = (int32_t)d; v.shard = (int32_t)d; v.d = (int32_t)d; v.kin = kin.data(); v.flips = flips.data(); v.priv = priv.data();
     v.tau = tau.data(); v.kctr = kctr.data(); v.seed0 = seed[0]; v.seed1 = seed[1]; v.adapt = adapt; v.factor = factor; v.local_bound = local_bound;
-    v.sticky = kappa ? 1 : 0; v.fth = kappa ? fth.data() : nullptr; v.kappa = kappa;
+    v.sticky = kappa ? 1 : 0; v.fth = (kappa || boom_sigma) ? fth.data() : nullptr; v.kappa = kappa;
+    const bool vel = kappa || boom_sigma;   // lists carry the velocity after each event
+    v.boom = boom_sigma ? 1 : 0; v.bmu = mu; v.bsig = boom_sigma; v.bref_rate = boom_lambdaref / (double)d; v.brho = boom_rho;
+    v.brhobar = sqrt(1 - boom_rho * boom_rho);
+    if (boom_sigma && !g.grid_m && G.maxdeg > ZZ_NB) { r->status = 1; r->msg = "column too long"; return r; }
 
     for (int64_t j = 0; j < d; ++j) {
         kin[j].theta = th0[j]; kin[j].tf = t0; kin[j].xf = x0[j]; kin[j].hdr[0] = kin[j].hdr[1] = 0;
@@ -84,14 +91,14 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
                 const double* fl = &flips[((size_t)j * 2 + slot) * ZZ_MAXFLIP];
                 for (uint32_t m = 0; m < cnt && same; ++m) same = (zz_d2u(fl[m]) == zz_d2u(o.fl[m]));
                 const double* ft = &fth[((size_t)j * 2 + slot) * ZZ_MAXFLIP];
-                for (uint32_t m = 0; kappa && m < cnt && same; ++m) same = (zz_d2u(ft[m]) == zz_d2u(o.fth[m]));
+                for (uint32_t m = 0; vel && m < cnt && same; ++m) same = (zz_d2u(ft[m]) == zz_d2u(o.fth[m]));
             }
             if (!same) {
                 int ws = (slot == 0) ? 1 : 0;
                 double* fl = &flips[((size_t)j * 2 + ws) * ZZ_MAXFLIP];
                 for (uint32_t m = 0; m < o.nflip; ++m) fl[m] = o.fl[m];
                 double* ft = &fth[((size_t)j * 2 + ws) * ZZ_MAXFLIP];
-                for (uint32_t m = 0; kappa && m < o.nflip; ++m) ft[m] = o.fth[m];
+                for (uint32_t m = 0; vel && m < o.nflip; ++m) ft[m] = o.fth[m];
                 kin[j].hdr[ws] = (curtag << 4) | o.nflip;
                 for (int32_t q = G.dptr[j]; q < G.dptr[j + 1]; ++q) {
                     int32_t k = G.didx[q];
@@ -172,14 +179,20 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
                     for (uint32_t m = 0; m < s.nflip; ++m) {
                         double fs = fl[m];
                         double xs, thn;
-                        if (kappa) {   // sticky: flip / freeze / thaw (zz_commit_node)
+                        if (boom_sigma) {   // reflection / refreshment (zz_commit_node)
+                            double tho; zz_boom_at(tf, xf, th, mu[j], fs, &xs, &tho);
+                            thn = ft[m];
+                            if (m == 0) r->acc[j] += (s.flags >> 3) & 7u;
+                        } else if (kappa) {   // sticky: flip / freeze / thaw (zz_commit_node)
                             thn = ft[m];
                             if (thn == 0.0) xs = -0.0 * th;
                             else if (th == 0.0) xs = xf;
                             else { xs = xf + th * (fs - tf); r->acc[j] += 1; }
                         } else { xs = xf + th * (fs - tf); thn = -th; r->acc[j] += 1; }
-                        r->s1[j] += (xf + xs) * (fs - tf);                        // trace.jl:194 (unscaled)
-                        r->s2[j] += (fs - tf) * (xf * xf + xf * xs + xs * xs);
+                        if (!boom_sigma) {
+                            r->s1[j] += (xf + xs) * (fs - tf);                    // trace.jl:194 (unscaled)
+                            r->s2[j] += (fs - tf) * (xf * xf + xf * xs + xs * xs);
+                        }
                         th = thn; tf = fs; xf = xs;
                         r->ev.push_back(zzw_event{ fs, j + 1, xs, th });          // sfact.jl:50-52
                     }

@@ -39,6 +39,12 @@ def lib():
         L.zzo_sspdmp.restype = C.c_void_p
         L.zzo_sspdmp.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.zzo_spdmp_boom.restype = C.c_void_p
+        L.zzo_spdmp_boom.argtypes = [C.c_int64] + [C.c_void_p] * 9 + [C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                     C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
+        L.zzo_sincos.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
+        L.zzo_randn.restype = C.c_double
+        L.zzo_randn.argtypes = [C.c_double, C.c_double]
         L.zzo_status.argtypes = [C.c_void_p]
         L.zzo_trace_len.restype = C.c_int64
         L.zzo_trace_len.argtypes = [C.c_void_p]
@@ -71,9 +77,10 @@ class BoundError(RuntimeError):
 
 
 def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
-          mode=PARITY_MODE, kappa=None):
+          mode=PARITY_MODE, kappa=None, boom=None):
     """Run the oracle.  ``target`` / ``bound`` are problems.CSC (target precision and the sampler's Z.Gamma).
-    With ``kappa`` (thaw rates) the sticky sampler sspdmp (src/ss_fact.jl) is run instead of spdmp."""
+    With ``kappa`` (thaw rates) the sticky sampler sspdmp (src/ss_fact.jl) is run instead of spdmp; with
+    ``boom = (sigma, lambdaref, rho)`` the factorised Boomerang (F::FactBoomerang in src/sfact.jl)."""
     L = lib()
     d = target.n
     f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -81,7 +88,12 @@ def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), 
     mu = np.zeros(d) if mu is None else f8(mu)
     h = None if h is None else f8(h)
     sd = np.array(seed, dtype=np.uint64)
-    if kappa is not None:
+    if boom is not None:
+        sigma = f8(boom[0])
+        r = L.zzo_spdmp_boom(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
+                             _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu), _p(sigma), float(boom[1]), float(boom[2]),
+                             float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor), int(mode))
+    elif kappa is not None:
         kappa = f8(kappa)
         r = L.zzo_sspdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
                          _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
@@ -110,6 +122,8 @@ def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), 
         L.zzo_final_state(r, _p(out.t), _p(out.x), _p(out.theta), _p(out.c))
         out.m1, out.m2, out.s1, out.s2 = (np.empty(d) for _ in range(4))
         L.zzo_moments(r, _p(out.m1), _p(out.m2), _p(out.s1), _p(out.s2))
+        if boom is not None:   # the event-based moments assume a piecewise linear path (trace.jl:182-200)
+            del out.m1, out.m2, out.s1, out.s2
         out.t0, out.x0, out.theta0 = t0, x0.copy(), theta0.copy()
         return out
     finally:
@@ -132,7 +146,8 @@ def wlib():
         L = C.CDLL(so)
         L.zzw_spdmp.restype = C.c_void_p
         L.zzw_spdmp.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
-                                C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_int, C.c_void_p]
+                                C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_int, C.c_void_p,
+                                C.c_void_p, C.c_double, C.c_double]
         L.zzw_status.argtypes = [C.c_void_p]
         L.zzw_trace_len.restype = C.c_int64
         L.zzw_trace_len.argtypes = [C.c_void_p]
@@ -149,7 +164,7 @@ def wlib():
 
 
 def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
-               delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False, kappa=None):
+               delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False, kappa=None, boom=None):
     L = wlib()
     d = target.n
     f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -161,7 +176,8 @@ def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1,
                     _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
                     float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor),
                     float(delta0), float(target_frac), int(tag_limit), int(bool(local_bound)),
-                    _p(None if kappa is None else f8(kappa)))
+                    _p(None if kappa is None else f8(kappa)),
+                    _p(None if boom is None else f8(boom[0])), 0.0 if boom is None else float(boom[1]), 0.0 if boom is None else float(boom[2]))
     try:
         st = L.zzw_status(r)
         if st == 3:
@@ -207,3 +223,48 @@ def assert_same_run(a, b, check_state=True):
     if hasattr(a, "s1") and hasattr(b, "s1"):
         assert np.array_equal(a.s1.view(np.uint64), b.s1.view(np.uint64))
         assert np.array_equal(a.s2.view(np.uint64), b.s2.view(np.uint64))
+
+
+def sincos(x):
+    s, c = C.c_double(), C.c_double()
+    lib().zzo_sincos(float(x), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def boom_discretize(res, mu, dt):
+    """``collect(discretize(trace, dt))`` for a FactBoomerang trace (src/trace.jl:94-125 with the rotation flow of
+    src/dynamics.jl:29-36) as ``(ts, xs)``; plain numpy, vectorised over coordinates."""
+    t, x, th = float(res.t0), res.x0.copy(), res.theta0.copy()
+    mu = np.asarray(mu, dtype=np.float64)
+    ts, xs = [t], [x.copy()]
+    ev = res.events
+    k, n = 0, len(ev)
+
+    def move(x, th, tau):
+        s, c = np.sin(tau), np.cos(tau)
+        return (x - mu) * c + th * s + mu, -(x - mu) * s + th * c
+
+    while True:
+        step = dt
+        done = False
+        while True:
+            if k >= n:
+                done = True
+                break
+            ti, i, xi, thi = ev[k]
+            if t + step < ti:
+                x, th = move(x, th, step)
+                t += step
+                break
+            dd = ti - t
+            step -= dd
+            x, th = move(x, th, dd)
+            t = ti
+            x[i - 1] = xi
+            th[i - 1] = thi
+            k += 1
+        if done:
+            break
+        ts.append(t)
+        xs.append(x.copy())
+    return np.array(ts), np.array(xs)

@@ -26,7 +26,7 @@ def test_kernel_image_is_sm100a_and_uses_no_fma_contraction():
     out = subprocess.run(["cuobjdump", "-elf", cubin], capture_output=True, text=True).stdout
     assert "sm_100a" in out or "sm_100" in out
     names = subprocess.run(["cuobjdump", "-sass", cubin], capture_output=True, text=True).stdout
-    for k in ("zz_run_kernel_grid", "zz_run_kernel_csr", "zz_run_kernel_grid_multi_lb", "zz_init_kernel", "zz_setup_kernel", "zz_export_kernel"):
+    for k in ("zz_run_kernel_grid", "zz_run_kernel_csr", "zz_run_kernel_grid_multi_lb", "zz_run_kernel_grid_boom", "zz_run_kernel_csr_boom", "zz_init_kernel", "zz_setup_kernel", "zz_export_kernel"):
         assert k in names
 
 

@@ -3,6 +3,7 @@
 Names, argument order and return shapes follow mschauer/ZigZagBoomerang.jl (paths relative to /root/reference):
 
     ZigZag(Gamma, mu, sigma; lambdaref, rho)          src/types.jl:19-27
+    FactBoomerang(Gamma, mu, lambdaref, sigma; rho)   src/types.jl:62-79
     spdmp(grad, t0, x0, theta0, T, c, [G,] F, args...; factor=1.8, adapt=false, seed)
         -> Xi, (t, x, theta), (acc, num), c           src/sfact.jl:162-214
     pdmp(grad, t0, x0, theta0, T, c, F, args...)      src/sfact.jl:236
@@ -47,6 +48,22 @@ class ZigZag:
             with np.errstate(divide="ignore"):
                 sigma = diag ** -0.5
         self.sigma = sigma
+        self.lambdaref = float(lambdaref)
+        self.rho = float(rho)
+        self.rhobar = float(np.sqrt(1 - rho * rho))
+
+
+class FactBoomerang:
+    """``FactBoomerang(Gamma, mu, lambda, sigma=diag(Gamma).^(-0.5); rho=0.0)`` (src/types.jl:62-79): factorised Boomerang
+    dynamics preserving N(mu, inv(Diagonal(Gamma))), refreshment rate ``lambda`` (must be > 0: ``hasrefresh`` is always
+    true, src/fact_samplers.jl:18)."""
+
+    def __init__(self, Gamma: CSC, mu, lambdaref: float, sigma=None, *, rho: float = 0.0):
+        self.Gamma = Gamma if isinstance(Gamma, CSC) else CSC.from_scipy(Gamma)
+        self.mu = f8(mu)
+        if sigma is None:
+            sigma = ZigZag(self.Gamma, self.mu).sigma
+        self.sigma = f8(sigma)
         self.lambdaref = float(lambdaref)
         self.rho = float(rho)
         self.rhobar = float(np.sqrt(1 - rho * rho))
@@ -106,8 +123,19 @@ class FactTrace:
 Trace = FactTrace
 
 
+def _flow(F, x, th, tau):
+    """move_forward of the trace's dynamics over tau: straight lines (ZigZag, src/dynamics.jl:12-17) or the rotation
+    around F.mu (FactBoomerang, src/dynamics.jl:29-36); returns the new (x, theta)."""
+    if isinstance(F, FactBoomerang):
+        s, c = np.sin(tau), np.cos(tau)
+        return (x - F.mu) * c + th * s + F.mu, -(x - F.mu) * s + th * c
+    return x + th * tau, th
+
+
 def discretize(trace: FactTrace, dt: float):
     """``collect(discretize(trace, dt))`` (src/trace.jl:94-125) as ``(ts, xs)`` arrays."""
+    if isinstance(trace.F, FactBoomerang):
+        return _discretize_flow(trace, dt)
     t, x, th = trace.t0, trace.x0.copy(), trace.theta0.copy()
     ts, xs = [t], [x.copy()]
     ev = trace.events
@@ -127,6 +155,39 @@ def discretize(trace: FactTrace, dt: float):
             d = ti - t
             step -= d
             x += th * d
+            t = ti
+            x[i - 1] = xi
+            th[i - 1] = thi
+            k += 1
+        if done:
+            break
+        ts.append(t)
+        xs.append(x.copy())
+    return np.array(ts), np.array(xs)
+
+
+def _discretize_flow(trace: FactTrace, dt: float):
+    """The same iteration (src/trace.jl:106-125) with a general flow between events."""
+    F = trace.F
+    t, x, th = trace.t0, trace.x0.copy(), trace.theta0.copy()
+    ts, xs = [t], [x.copy()]
+    ev = trace.events
+    k, n = 0, len(ev)
+    while True:
+        step = dt
+        done = False
+        while True:
+            if k >= n:
+                done = True
+                break
+            ti, i, xi, thi = ev[k]
+            if t + step < ti:
+                x, th = _flow(F, x, th, step)
+                t += step
+                break
+            d = ti - t
+            step -= d
+            x, th = _flow(F, x, th, d)
             t = ti
             x[i - 1] = xi
             th[i - 1] = thi
@@ -194,17 +255,20 @@ class Run:
     """One sampler run on the device (staged form of the C-ABI)."""
 
     def __init__(self, problem: Problem, *, record_trace: bool = True, trace_capacity: int = 0, local_bound: bool = False,
-                 kappa=None):
+                 kappa=None, boomerang=None):
         self.problem = problem
         self.d = problem.d
         self._h = C.c_void_p()
         flags = (0 if record_trace else _capi.ZZB_FLAG_NO_TRACE) | (_capi.ZZB_FLAG_LOCAL_BOUND if local_bound else 0) \
-            | (_capi.ZZB_FLAG_STICKY if kappa is not None else 0)
+            | (_capi.ZZB_FLAG_STICKY if kappa is not None else 0) | (_capi.ZZB_FLAG_BOOMERANG if boomerang is not None else 0)
         self.record_trace = record_trace
         check(_capi.lib().zzb_run_create(problem._h, flags, int(trace_capacity), C.byref(self._h)))
         if kappa is not None:
             self._kappa = f8(kappa)
             check(_capi.lib().zzb_run_upload_kappa(self._h, ptr(self._kappa)))
+        if boomerang is not None:   # a FactBoomerang: sigma, lambdaref, rho (its Gamma / mu are the problem's sampler matrices)
+            self._sigma = f8(boomerang.sigma)
+            check(_capi.lib().zzb_run_upload_boomerang(self._h, ptr(self._sigma), boomerang.lambdaref, boomerang.rho))
 
     def set(self, **kw):
         for k, v in kw.items():
@@ -321,9 +385,9 @@ def _as_problem(grad, F):
     if not isinstance(grad, GaussianPotential):
         raise TypeError("the B200 path needs a target descriptor (GaussianPotential), not a closure: "
                         "a device kernel cannot call back into the host")
-    if not isinstance(F, ZigZag):
-        raise TypeError("only ZigZag dynamics are implemented on the device path")
-    if F.lambdaref != 0.0:
+    if not isinstance(F, (ZigZag, FactBoomerang)):
+        raise TypeError("only ZigZag and FactBoomerang dynamics are implemented on the device path")
+    if isinstance(F, ZigZag) and F.lambdaref != 0.0:
         raise NotImplementedError("refreshments (lambdaref > 0) are not implemented on the device path")
     return Problem(grad, F), True
 
@@ -351,7 +415,10 @@ def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None,
     prob, own = _as_problem(grad, F)
     if seed is None:  # Seed() = fresh entropy (src/ZigZagBoomerang.jl:10)
         seed = (secrets.randbits(64), secrets.randbits(64))
-    run = Run(prob, record_trace=record_trace, local_bound=local_bound)
+    boom = F if isinstance(F, FactBoomerang) else None
+    if boom is not None and local_bound:
+        raise NotImplementedError("LocalBound with FactBoomerang is not implemented on the device path")
+    run = Run(prob, record_trace=record_trace, local_bound=local_bound, boomerang=boom)
     try:
         if tune:
             run.set(**tune)
@@ -361,7 +428,7 @@ def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None,
         acc, num = run.counts()
         ev = run.events() if record_trace else np.empty(0, dtype=EVENT_DTYPE)
         Xi = FactTrace(F, t0, x0, theta0, ev)
-        Xi.moments = run.moments() if num else None
+        Xi.moments = run.moments() if (num and boom is None) else None   # event-based moments assume linear segments
         Xi.stats = run.stats()
         Xi.device_ms = run.device_ms
         return Xi, (t, x, th), (acc, num), (LocalBound(cc) if local_bound else cc)

@@ -45,6 +45,13 @@ struct ZzHood {
     double th[NB], tf[NB], xf[NB];
 };
 
+// FactBoomerang only: centre of the rotation of each neighbour (Z.mu).  Kept out of ZzHood so that the ZigZag kernels
+// compile exactly as before.
+template <int NB>
+struct ZzHoodMu {
+    double mu[NB];
+};
+
 struct ZzPool {
     int n;
     double t[ZZ_POOL];
@@ -89,7 +96,7 @@ ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint
 // General sparse column (<= NB entries).  Returns false when the column is longer (caller uses the slow path).
 template <int NB, bool MG>
 ZZ_HD bool zz_gather_csr(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t w0, uint32_t cur, bool first_iter,
-                         ZzHood<NB>& hd, ZzPool& pool, uint32_t& flags)
+                         ZzHood<NB>& hd, ZzPool& pool, uint32_t& flags, ZzHoodMu<NB>* hm = nullptr)
 {
     const int32_t e0 = g.nptr[j];
     const int n = g.nptr[j + 1] - e0;
@@ -111,6 +118,10 @@ ZZ_HD bool zz_gather_csr(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t 
             else zz_ld_kin(zz_kin_at<MG>(v, idx[m]), hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
         }
     }
+    if (hm) {
+#pragma unroll
+        for (int m = 0; m < NB; ++m) hm->mu[m] = (m < n) ? v.bmu[idx[m]] : 0.0;
+    }
     pool.n = 0;
     if (!first_iter) zz_gather_flips<NB, MG>(v, idx, h0, h1, n, hd.self, w0, cur, pool, flags);
     return true;
@@ -119,7 +130,7 @@ ZZ_HD bool zz_gather_csr(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t 
 // 5-point lattice: column j = {j-M, j-1, j, j+1, j+M} (those that exist), weights -1 and shift + degree.
 template <bool MG>
 ZZ_HD void zz_gather_grid(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t w0, uint32_t cur, bool first_iter,
-                          ZzHood<5>& hd, ZzPool& pool, uint32_t& flags)
+                          ZzHood<5>& hd, ZzPool& pool, uint32_t& flags, ZzHoodMu<5>* hm = nullptr)
 {
     const int32_t M = g.grid_m, N = g.grid_n;
     const int32_t col = j / M, row = j - col * M;
@@ -143,6 +154,10 @@ ZZ_HD void zz_gather_grid(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t
 #pragma unroll
     for (int m = 0; m < 5; ++m)
         if (m < n && m != self) zz_ld_kin(zz_kin_at<MG>(v, idx[m]), hd.th[m], hd.tf[m], hd.xf[m], h0[m], h1[m]);
+    if (hm) {
+#pragma unroll
+        for (int m = 0; m < 5; ++m) hm->mu[m] = (m < n) ? v.bmu[idx[m]] : 0.0;
+    }
     pool.n = 0;
     ZZ_SEG(1);
     if (!first_iter) zz_gather_flips<5, MG>(v, idx, h0, h1, n, self, w0, cur, pool, flags);
@@ -362,12 +377,162 @@ ZZ_HD void zz_timeline_sticky(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w
     (void)nflip;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Factorised Boomerang in spdmp (F::FactBoomerang, src/sfact.jl:29-48,73-145) seen from coordinate j.  Between events a
+// coordinate rotates around mu_j (zz_boom_at); its record holds the anchor (tf, xf, theta at tf).  Own items: proposal
+// (rate fact_samplers.jl:37-39, constant bound :58-65) and velocity refreshment (sfact.jl:100-108; one clock of rate
+// lambda_ref/d per coordinate -- the superposition of the reference's single clock, see oracle/zz_oracle.c).  Neighbour
+// items: any recorded event of a trigger neighbour (reflection or refreshment) reschedules j (:110-114,131-135).
+// Record layout in this mode: priv/spec = (a, next refreshment time, next proposal time, c); tau = the earlier of the two.
+template <int NB>
+ZZ_HD void zz_boom_eval(const ZzHood<NB>& hd, const ZzHoodMu<NB>& hm, bool same, double s, double xown, double thown, double& gt,
+                        double& zsum)
+{
+    double at = 0.0, zs = 0.0;
+    bool first = true;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        if (m < hd.n) {
+            double x, th;
+            if (m == hd.self) { x = xown; th = thown; }
+            else zz_boom_at(hd.tf[m], hd.xf[m], hd.th[m], hm.mu[m], s, &x, &th);
+            if (hd.fl[m] & ZZ_NB_BND) {                          // sum((x_j - mu_j)^2 + theta_j^2 for j in nhd), left fold
+                const double term = (x - hm.mu[m]) * (x - hm.mu[m]) + th * th;
+                zs = first ? term : zs + term;
+                first = false;
+            }
+            if (same) { if (hd.fl[m] & ZZ_NB_BND) at += hd.wb[m] * x; }
+            else if (hd.fl[m] & ZZ_NB_TGT) at += hd.wt[m] * x;   // idot(Gamma, j, x), common.jl:16-24
+        }
+    }
+    gt = at; zsum = zs;
+}
+
+ZZ_HD double zz_boom_a(double c, double xi, double thi, double zsum, double diag)
+{   // ab(G, i, x, theta, c, Z::FactBoomerang), fact_samplers.jl:58-65 (b = 0)
+    const double z = zz_sqrt(zsum);
+    const double z2 = xi * xi + thi * thi;
+    return c * zz_sqrt(z2) * z + z2 * diag;
+}
+
+template <int NB>
+ZZ_HD void zz_timeline_boom(ZzHood<NB>& hd, const ZzHoodMu<NB>& hm, const ZzPool& pool, const ZzOwn& w, const ZzGraph& g, const ZzView& v,
+                            int32_t j, double H, int incl, uint32_t flags0, ZzNodeOut& o)
+{
+    double th = w.th, tf = w.tf, xf = w.xf;               // own anchor
+    double a = w.a, tref = w.b, tau = w.told, c = w.c;
+    uint32_t k = w.k;
+    const double muj = v.bmu[j], sigj = v.bsig[j];
+    const bool has_h = (!g.same && g.h);
+    const double hj = has_h ? g.h[j] : 0.0;
+    double diag = 0.0;                                     // Z.Gamma[j,j] (0 when not stored)
+#pragma unroll
+    for (int m = 0; m < NB; ++m) if (m == hd.self && (hd.fl[m] & ZZ_NB_BND)) diag = hd.wb[m];
+    uint32_t nprop = 0, nev = 0, nrefl = 0, flags = flags0;
+    o.viol_t = 0.0; o.viol_l = 0.0; o.viol_lb = 0.0;
+    int p = 0;
+
+    for (int item = 0;; ++item) {
+        const double nt = p < pool.n ? pool.t[p] : ZZ_INF;
+        const int nm = p < pool.n ? pool.m[p] : 0x7fffffff;
+        const bool isprop = tau <= tref;
+        const double town = isprop ? tau : tref;
+        const bool own = (town < nt) || (town == nt && hd.self < nm);
+        const double s = own ? town : nt;
+        if (!(s < H || (incl && s == H))) break;
+        if (item >= ZZ_MAXITEMS) { flags |= ZZ_F_OVERFLOW; break; }
+        double xs, ths;
+        zz_boom_at(tf, xf, th, muj, s, &xs, &ths);
+        bool propose = false;
+        if (!own) {
+            const double tha = pool.th[p];
+            bool trig = false;
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+                if (m == nm) {                             // re-anchor the neighbour at its event
+                    double xm, tm;
+                    zz_boom_at(hd.tf[m], hd.xf[m], hd.th[m], hm.mu[m], s, &xm, &tm);
+                    hd.xf[m] = xm; hd.tf[m] = s; hd.th[m] = tha;
+                    trig = (hd.fl[m] & ZZ_NB_TRIG) != 0;
+                }
+            }
+            ++p;
+            if (!trig) continue;
+        } else if (!isprop) {                              // refreshment, sfact.jl:100-108
+            const double u1 = zz_u01(v.seed0, v.seed1, (uint64_t)j, k);
+            const double u2 = zz_u01(v.seed0, v.seed1, (uint64_t)j, k + 1u);
+            const double u3 = zz_u01(v.seed0, v.seed1, (uint64_t)j, k + 2u);
+            k += 3u;
+            const double thn = v.brho * ths + v.brhobar * sigj * zz_randn(u1, u2);
+            if (nev == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#pragma unroll
+            for (int m = 0; m < ZZ_MAXFLIP; ++m) if (m == (int)nev) { o.fl[m] = s; o.fth[m] = thn; }
+            nev++;
+            xf = xs; tf = s; th = thn; ths = thn;
+            tref = s - zz_log(u3) / v.bref_rate;
+        } else {
+            propose = true;
+        }
+        double gt, zsum;
+        zz_boom_eval<NB>(hd, hm, g.same != 0, s, xs, ths, gt, zsum);
+        if (propose) {
+            if (has_h) gt = gt - hj;
+            const double l = zz_pos((gt - (xs - muj) * diag) * ths);      // fact_samplers.jl:37-39
+            const double lb = zz_pos(a);                                   // sfact.jl:70 with b = 0
+            const double u1 = zz_u01(v.seed0, v.seed1, (uint64_t)j, k++);
+            nprop++;
+            if (u1 * lb < l) {                                             // sfact.jl:121
+                if (l >= lb) {
+                    if (v.adapt) c *= v.factor;
+                    else if (!(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
+                }
+                if (nev == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#pragma unroll
+                for (int m = 0; m < ZZ_MAXFLIP; ++m) if (m == (int)nev) { o.fl[m] = s; o.fth[m] = -ths; }
+                nev++; nrefl++;
+                xf = xs; tf = s; th = -ths; ths = -ths;                    // dynamics.jl:46-49
+            }
+        }
+        a = zz_boom_a(c, xs, ths, zsum, diag);
+        tau = s + zz_poisson_time_L(a, 0.0, zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, k++)));   // sfact.jl:134,139
+    }
+    o.a = a; o.b = tref; o.told = tau; o.tau = tau <= tref ? tau : tref; o.c = c;
+    o.k = k; o.nprop = nprop; o.nflip = nev; o.flags = flags | (nrefl << 3);
+    o.hdr0 = w.hdr0; o.hdr1 = w.hdr1;
+}
+
+// initial bound, first proposal and first refreshment time (sfact.jl:184-190: neither is offset by t0)
+template <int NB>
+ZZ_HD void zz_boom_init(ZzHood<NB>& hd, const ZzHoodMu<NB>& hm, const ZzGraph& g, const ZzView& v, int32_t j, double t0)
+{
+    double th, tf, xf; uint32_t h0, h1;
+    zz_ld_kin(v.kin + j, th, tf, xf, h0, h1);
+    double xs, ths;
+    zz_boom_at(tf, xf, th, v.bmu[j], t0, &xs, &ths);
+    double diag = 0.0;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) if (m == hd.self && (hd.fl[m] & ZZ_NB_BND)) diag = hd.wb[m];
+    double gt, zsum;
+    zz_boom_eval<NB>(hd, hm, g.same != 0, t0, xs, ths, gt, zsum);
+    ZzPriv pr;
+    pr.c = zz_ld_priv(v.priv + j).c;
+    pr.a = zz_boom_a(pr.c, xs, ths, zsum, diag);
+    const double tau = zz_poisson_time_L(pr.a, 0.0, zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, 0)));
+    const double tref = -zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, 1)) / v.bref_rate;
+    pr.b = tref; pr.told = tau;
+    v.priv[j] = pr;
+    v.tau[j] = tau <= tref ? tau : tref;
+    v.kctr[j] = 2u;
+}
+
 // Entry points.  KIND 0: 5-point lattice (index arithmetic); KIND 1: general sparse columns.
 #define ZZ_KIND_GRID 0
 #define ZZ_KIND_CSR 1
 #define ZZ_MODE_PLAIN 0
 #define ZZ_MODE_LB 1       // LocalBound (src/local.jl)
 #define ZZ_MODE_STICKY 2   // sticky ZigZag (src/ss_fact.jl)
+#define ZZ_MODE_BOOM 3     // factorised Boomerang (F::FactBoomerang in src/sfact.jl)
+#define ZZ_MODE_HAS_VEL(M) ((M) == ZZ_MODE_STICKY || (M) == ZZ_MODE_BOOM)   // flip lists carry the velocity after each event
 template <int KIND, int MODE, bool MG = true>
 ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                              uint32_t cur, bool first_iter, ZzNodeOut& o)
@@ -378,6 +543,12 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
         ZzHood<5> hd;
         ZZ_SEG(0);
         zz_load_own(v, j, w);
+        if (MODE == ZZ_MODE_BOOM) {
+            ZzHoodMu<5> hm;
+            zz_gather_grid<MG>(g, v, j, w0, cur, first_iter, hd, pool, flags, &hm);
+            zz_timeline_boom<5>(hd, hm, pool, w, g, v, j, H, incl, flags, o);
+            return;
+        }
         zz_gather_grid<MG>(g, v, j, w0, cur, first_iter, hd, pool, flags);
         ZZ_SEG(2);
         if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<5>(hd, pool, w, g, v, j, H, incl, flags, o);
@@ -388,6 +559,12 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
     ZzHood<ZZ_NB> hd;
     if (g.nptr[j + 1] - g.nptr[j] <= ZZ_NB) {
         zz_load_own(v, j, w);
+        if (MODE == ZZ_MODE_BOOM) {
+            ZzHoodMu<ZZ_NB> hm;
+            zz_gather_csr<ZZ_NB, MG>(g, v, j, w0, cur, first_iter, hd, pool, flags, &hm);
+            zz_timeline_boom<ZZ_NB>(hd, hm, pool, w, g, v, j, H, incl, flags, o);
+            return;
+        }
         zz_gather_csr<ZZ_NB, MG>(g, v, j, w0, cur, first_iter, hd, pool, flags);
         if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<ZZ_NB>(hd, pool, w, g, v, j, H, incl, flags, o);
         else zz_timeline<ZZ_NB, MODE == ZZ_MODE_LB>(hd, pool, w, g, v, j, H, incl, flags, o);
@@ -400,7 +577,10 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
 ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                            uint32_t cur, bool first_iter, ZzNodeOut& o)
 {
-    if (v.sticky) {
+    if (v.boom) {
+        if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, ZZ_MODE_BOOM>(g, v, j, H, incl, w0, cur, first_iter, o);
+        else zz_process_node_k<ZZ_KIND_CSR, ZZ_MODE_BOOM>(g, v, j, H, incl, w0, cur, first_iter, o);
+    } else if (v.sticky) {
         if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, ZZ_MODE_STICKY>(g, v, j, H, incl, w0, cur, first_iter, o);
         else zz_process_node_k<ZZ_KIND_CSR, ZZ_MODE_STICKY>(g, v, j, H, incl, w0, cur, first_iter, o);
     } else if (v.local_bound) {

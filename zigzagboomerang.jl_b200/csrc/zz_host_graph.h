@@ -21,7 +21,7 @@
 struct ZzHostGraph {
     int32_t d = 0;
     std::vector<int32_t> nptr, nidx, dptr, didx;
-    std::vector<double> nwt, nwb, gmu, h;
+    std::vector<double> nwt, nwb, gmu, h, mu;
     std::vector<uint8_t> nfl;
     int32_t same = 0;
     bool has_h = false;
@@ -106,6 +106,7 @@ static inline std::string zz_build_graph(ZzHostGraph& G, int64_t d, const int64_
     G.has_h = has_h;
     zz_detect_grid(G, d, bcp, brv, bnz);
     if (has_h) G.h.assign(hvec, hvec + d);
+    G.mu.assign(mu, mu + d);   // Z.mu itself (the Boomerang flow rotates around it)
 
     // transpose pattern of the bound matrix: trig[j] = { k : j in rows(col k) }
     std::vector<int64_t> tptr(d + 1, 0);

@@ -259,7 +259,7 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
 #pragma unroll
         for (int m = 0; m < ZZ_MAXFLIP; ++m)
             if (m < (int)cnt) same = same && (zz_d2u(__ldcg(fl + m)) == zz_d2u(o.fl[m]));
-        if (MODE == ZZ_MODE_STICKY) {
+        if (ZZ_MODE_HAS_VEL(MODE)) {
             const double* ft = P.v.fth + ((size_t)j * 2 + slot) * ZZ_MAXFLIP;
 #pragma unroll
             for (int m = 0; m < ZZ_MAXFLIP; ++m)
@@ -272,7 +272,7 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
 #pragma unroll
         for (int m = 0; m < ZZ_MAXFLIP; ++m)
             if (m < (int)o.nflip) fl[m] = o.fl[m];
-        if (MODE == ZZ_MODE_STICKY) {
+        if (ZZ_MODE_HAS_VEL(MODE)) {
             double* ft = P.v.fth + ((size_t)j * 2 + wsl) * ZZ_MAXFLIP;
 #pragma unroll
             for (int m = 0; m < ZZ_MAXFLIP; ++m)
@@ -370,12 +370,18 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uin
             pos = base + pre;
         }
         double a1 = __ldcg(P.s1 + j), a2 = __ldcg(P.s2 + j);
-        const double* ft = P.v.sticky ? P.v.fth + ((size_t)j * 2 + slot) * ZZ_MAXFLIP : nullptr;
-        unsigned int nrefl = 0;
+        const double* ft = P.v.fth ? P.v.fth + ((size_t)j * 2 + slot) * ZZ_MAXFLIP : nullptr;
+        const bool boom = P.v.boom != 0;
+        const double muj = boom ? P.v.bmu[j] : 0.0;
+        unsigned int nrefl = boom ? ((s.flags >> 3) & 7u) : 0u;   // Boomerang: reflections counted by the timeline (refreshments are events too)
         for (unsigned int m = 0; m < s.nflip; ++m) {
             const double fs = __ldcg(fl + m);
             double xs, thn;
-            if (ft) {   // sticky: flip / freeze (velocity after = 0, x = -0*theta) / thaw (x stays 0), ss_fact.jl:87-123
+            if (boom) {   // reflection or refreshment: rotate to the event, then the recorded velocity (sfact.jl:29-38,100-102,130)
+                double tho;
+                zz_boom_at(tf, xf, th, muj, fs, &xs, &tho);
+                thn = __ldcg(ft + m);
+            } else if (ft) {   // sticky: flip / freeze (velocity after = 0, x = -0*theta) / thaw (x stays 0), ss_fact.jl:87-123
                 thn = __ldcg(ft + m);
                 if (thn == 0.0) xs = -0.0 * th;
                 else if (th == 0.0) xs = xf;
@@ -383,8 +389,10 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uin
             } else {
                 xs = xf + th * (fs - tf); thn = -th; nrefl++;
             }
-            a1 += (xf + xs) * (fs - tf);                          // trace.jl:194 (scaled by 1/(2T) on the host)
-            a2 += (fs - tf) * (xf * xf + xf * xs + xs * xs);
+            if (!boom) {   // moment sums of the piecewise LINEAR path only
+                a1 += (xf + xs) * (fs - tf);                      // trace.jl:194 (scaled by 1/(2T) on the host)
+                a2 += (fs - tf) * (xf * xf + xf * xs + xs * xs);
+            }
             th = thn; tf = fs; xf = xs;
             if (P.record_trace) {
                 if (pos + m < P.trace_cap) {
@@ -686,3 +694,5 @@ ZZ_RUN_KERNEL(zz_run_kernel_grid_multi_lb, ZZ_KIND_GRID, true, ZZ_MODE_LB)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_multi_lb, ZZ_KIND_CSR, true, ZZ_MODE_LB)
 ZZ_RUN_KERNEL(zz_run_kernel_grid_sticky, ZZ_KIND_GRID, false, ZZ_MODE_STICKY)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_sticky, ZZ_KIND_CSR, false, ZZ_MODE_STICKY)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_boom, ZZ_KIND_GRID, false, ZZ_MODE_BOOM)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_boom, ZZ_KIND_CSR, false, ZZ_MODE_BOOM)

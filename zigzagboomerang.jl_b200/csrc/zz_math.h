@@ -11,6 +11,7 @@
 // Reference semantics restated here:
 //   pos            src/common.jl:8
 //   poisson_time   src/poissontime.jl:8-30 (two-parameter form), :39-65 (three-parameter form)
+//   Boomerang flow src/sfact.jl:29-38, src/dynamics.jl:29-36 (zz_boom_at, with our own zz_sincos)
 #ifndef ZZ_MATH_H
 #define ZZ_MATH_H
 
@@ -158,6 +159,70 @@ ZZ_HD double zz_poisson_time3(double a, double b, double c, double u)
             return zz_sqrt((a + c) * (a + c) - 2.0 * lu * b) / b - (a + c) / b;
         return (-lu + (a * a) / (2.0 * b)) / c;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sin and cos together (the Boomerang flow rotates (x - mu, theta), src/sfact.jl:29-38 `sincos`).  Like zz_log this is
+// OUR routine so that host and device agree bit for bit: Cody-Waite reduction by pi/2 in two 33-bit pieces (exact
+// products for |n| < 2^20, i.e. |x| < 1.6e6), then the classic Sun/fdlibm kernels on [-pi/4, pi/4] (error < 1 ulp each);
+// only + - * and one double -> integer conversion.  Beyond |x| ~ 1.6e6 the result stays deterministic but loses accuracy.
+ZZ_HD void zz_sincos(double x, double* sn, double* cs)
+{
+    const double invpio2 = 6.36619772367581382433e-01;
+    const double pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11;
+    const double pio2_2 = 6.07710050630396597660e-11, pio2_2t = 2.02226624879595063154e-21;
+    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03, S3 = -1.98412698298579493134e-04;
+    const double S4 = 2.75573137070700676789e-06, S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
+    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03, C3 = 2.48015872894767294178e-05;
+    const double C4 = -2.75573143513906633035e-07, C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
+    (void)pio2_1t;
+    const double v = x * invpio2;
+    const long long n = (long long)(v + (v < 0.0 ? -0.5 : 0.5));   // nearest integer, ties away from zero
+    const double fn = (double)n;
+    const double t = x - fn * pio2_1;
+    double w = fn * pio2_2;
+    const double r = t - w;
+    w = fn * pio2_2t - ((t - r) - w);
+    const double y0 = r - w;
+    const double y1 = (r - y0) - w;
+    const double z = y0 * y0;
+    // kernel sin
+    const double vv = z * y0;
+    const double rs = S2 + z * (S3 + z * (S4 + z * (S5 + z * S6)));
+    const double ks = y0 - ((z * (0.5 * y1 - vv * rs) - y1) - vv * S1);
+    // kernel cos
+    const double ww = z * z;
+    const double rc = z * (C1 + z * (C2 + z * C3)) + (ww * ww) * (C4 + z * (C5 + z * C6));
+    const double hz = 0.5 * z;
+    const double w1 = 1.0 - hz;
+    const double kc = w1 + (((1.0 - w1) - hz) + (z * rc - y0 * y1));
+    const int q = (int)(n & 3LL);
+    *sn = (q == 0) ? ks : (q == 1) ? kc : (q == 2) ? -ks : -kc;
+    *cs = (q == 0) ? kc : (q == 1) ? -ks : (q == 2) ? -kc : ks;
+}
+
+// Standard normal from two uniforms (Box-Muller): the velocity refreshment `randn(rng)` of src/sfact.jl:102.  (Julia
+// draws it with a ziggurat from its own stream; equal in law, and the stream is ours anyway -- DESIGN.md "RNG contract".)
+ZZ_HD double zz_randn(double u1, double u2)
+{
+    double sn, cs;
+    zz_sincos(6.283185307179586232 * u2, &sn, &cs);
+    return zz_sqrt(-2.0 * zz_log(u1)) * cs;
+}
+
+// Boomerang flow of one coordinate from its anchor (tf, xf, thf) to time s (src/sfact.jl:29-38, dynamics.jl:29-36):
+//   x = (xf - mu) cos(tau) + thf sin(tau) + mu,   theta = -(xf - mu) sin(tau) + thf cos(tau),   tau = s - tf.
+// tau == 0 returns the anchor itself (so that re-reading a coordinate at the time it was anchored is exact).
+ZZ_HD void zz_boom_at(double tf, double xf, double thf, double mu, double s, double* x, double* th)
+{
+    const double tau = s - tf;
+    double sn, cs;
+    zz_sincos(tau, &sn, &cs);
+    const double xm = xf - mu;
+    const double xr = xm * cs + thf * sn + mu;
+    const double tr = -xm * sn + thf * cs;
+    *x = (tau == 0.0) ? xf : xr;
+    *th = (tau == 0.0) ? thf : tr;
 }
 
 #endif  // ZZ_MATH_H

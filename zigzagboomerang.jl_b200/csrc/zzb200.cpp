@@ -88,10 +88,10 @@ struct Global {
     CUdevice dev = 0; int dev_id = 0;
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
-    CUfunction f_setup = nullptr, f_init = nullptr, f_run[10] = {}, f_export = nullptr;
+    CUfunction f_setup = nullptr, f_init = nullptr, f_run[12] = {}, f_export = nullptr;
     CUstream stream = nullptr;
     CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
-    int sm_count = 0; int blocks_per_sm[10] = {}; int run_block[2] = { 256, 256 };   // lattice / general-sparse kernels
+    int sm_count = 0; int blocks_per_sm[12] = {}; int run_block[2] = { 256, 256 };   // lattice / general-sparse kernels
     size_t total_mem = 0; char name[128] = { 0 };
 };
 static Global G;
@@ -168,10 +168,12 @@ struct zzb_run_s {
     int grid = 0; int kind = 1;
     int kidx() const
     {
+        if (flags & ZZB_FLAG_BOOMERANG) return 10 + kind;
         if (flags & ZZB_FLAG_STICKY) return 8 + kind;
         return kind + (nranks > 1 ? 2 : 0) + ((flags & ZZB_FLAG_LOCAL_BOUND) ? 4 : 0);
     }
     DevBuf dfth, kappa; bool have_kappa = false;
+    DevBuf bmu, bsig; bool have_boom = false; double lambdaref = 0, rho = 0;
     int rank = 0, nranks = 1, shard = 0, lo = 0, hi = 0;
     CUdeviceptr peer[ZZ_MAXRANKS][8] = {};   // imported mappings: kin, flips, dstamp, wl0, wl1, wl2, touched, ctl
     bool peer_open[ZZ_MAXRANKS] = {};
@@ -227,10 +229,11 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     CU(cuModuleGetFunction(&G.f_init, G.mod, "zz_init_kernel"));
     // index = kind (0 lattice, 1 general) + 2 * multi-GPU + 4 * LocalBound
     // 8, 9: sticky ZigZag (single GPU)
-    static const char* run_names[10] = { "zz_run_kernel_grid", "zz_run_kernel_csr", "zz_run_kernel_grid_multi", "zz_run_kernel_csr_multi",
+    // 10, 11: factorised Boomerang (single GPU)
+    static const char* run_names[12] = { "zz_run_kernel_grid", "zz_run_kernel_csr", "zz_run_kernel_grid_multi", "zz_run_kernel_csr_multi",
                                          "zz_run_kernel_grid_lb", "zz_run_kernel_csr_lb", "zz_run_kernel_grid_multi_lb", "zz_run_kernel_csr_multi_lb",
-                                         "zz_run_kernel_grid_sticky", "zz_run_kernel_csr_sticky" };
-    for (int k = 0; k < 10; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
+                                         "zz_run_kernel_grid_sticky", "zz_run_kernel_csr_sticky", "zz_run_kernel_grid_boom", "zz_run_kernel_csr_boom" };
+    for (int k = 0; k < 12; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuStreamCreate(&G.stream, CU_STREAM_NON_BLOCKING));
     CU(cuEventCreate(&G.ev0, CU_EVENT_DEFAULT));
@@ -245,7 +248,7 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
                 CU(cuMemcpyDtoH(&G.run_block[q], sym, sizeof(int)));
         }
     }
-    for (int k = 0; k < 10; ++k) {
+    for (int k = 0; k < 12; ++k) {
         CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm[k], G.f_run[k], G.run_block[k & 1], 0));
         if (G.blocks_per_sm[k] < 1) return fail(ZZB_E_CUDA, "zz_run_kernel does not fit on an SM");
     }
@@ -340,6 +343,9 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     if ((flags & ZZB_FLAG_STICKY) && (flags & ZZB_FLAG_LOCAL_BOUND)) return fail(ZZB_E_ARG, "sticky and LocalBound cannot be combined");
     if ((flags & ZZB_FLAG_STICKY) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB)
         return fail(ZZB_E_ARG, "the sticky kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB, p->hg.maxdeg);
+    if ((flags & ZZB_FLAG_BOOMERANG) && (flags & (ZZB_FLAG_STICKY | ZZB_FLAG_LOCAL_BOUND))) return fail(ZZB_E_ARG, "Boomerang cannot be combined with sticky / LocalBound");
+    if ((flags & ZZB_FLAG_BOOMERANG) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB)
+        return fail(ZZB_E_ARG, "the Boomerang kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB, p->hg.maxdeg);
     if ((flags & ZZB_FLAG_LOCAL_BOUND) && !p->hg.bnd_eq_tgt)
         return fail(ZZB_E_ARG, "LocalBound builds its bound from the target: create the problem with the sampler matrix equal to the target (bnd_* = NULL) and Z.mu = 0");
     CtxGuard cg;
@@ -354,6 +360,10 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     AL(touched, d * 4); AL(ctl, sizeof(ZzDevCtl));
     AL(in_x, d * 8); AL(in_th, d * 8); AL(in_c, d * 8);
     if (flags & ZZB_FLAG_STICKY) { AL(dfth, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(kappa, d * 8); }
+    if (flags & ZZB_FLAG_BOOMERANG) {
+        AL(dfth, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(bsig, d * 8);
+        if (!st) st = upload(r->bmu, p->hg.mu.data(), d * 8);
+    }
     AL(out_t, d * 8); AL(out_x, d * 8); AL(out_th, d * 8); AL(out_c, d * 8); AL(out_acc, d * 8);
     if (!(flags & ZZB_FLAG_NO_TRACE)) {
         unsigned long long cap = (unsigned long long)std::max<int64_t>(trace_capacity_events, 0);
@@ -394,7 +404,12 @@ static void fill_params(zzb_run_s* r)
     P.record_trace = (r->flags & ZZB_FLAG_NO_TRACE) ? 0 : 1;
     P.v.local_bound = (r->flags & ZZB_FLAG_LOCAL_BOUND) ? 1 : 0;
     P.v.sticky = (r->flags & ZZB_FLAG_STICKY) ? 1 : 0;
-    P.v.fth = P.v.sticky ? r->dfth.as<double>() : nullptr;
+    P.v.boom = (r->flags & ZZB_FLAG_BOOMERANG) ? 1 : 0;
+    P.v.fth = (P.v.sticky || P.v.boom) ? r->dfth.as<double>() : nullptr;
+    if (P.v.boom) {
+        P.v.bmu = r->bmu.as<double>(); P.v.bsig = r->bsig.as<double>();
+        P.v.bref_rate = r->lambdaref / (double)r->d; P.v.brho = r->rho; P.v.brhobar = sqrt(1 - r->rho * r->rho);
+    }
     P.v.kappa = P.v.sticky ? r->kappa.as<double>() : nullptr;
     P.v.nranks = r->nranks; P.v.rank = r->rank; P.v.shard = r->shard; P.v.lo = r->lo; P.v.hi = r->hi;
     if (r->nranks > 1) {
@@ -426,7 +441,7 @@ int32_t zzb_run_shard(zzb_run_t r, int32_t rank, int32_t nranks)
 {
     if (!r) return fail(ZZB_E_ARG, "null argument");
     if (nranks < 1 || nranks > ZZ_MAXRANKS || rank < 0 || rank >= nranks) return fail(ZZB_E_ARG, "bad rank %d of %d", rank, nranks);
-    if (nranks > 1 && (r->flags & ZZB_FLAG_STICKY)) return fail(ZZB_E_ARG, "the sticky sampler is not sharded yet");
+    if (nranks > 1 && (r->flags & (ZZB_FLAG_STICKY | ZZB_FLAG_BOOMERANG))) return fail(ZZB_E_ARG, "the sticky and Boomerang samplers are not sharded yet");
     const int64_t d = r->d;
     int64_t shard = (d + nranks - 1) / nranks;
     const int64_t m = r->prob->g.grid_m;
@@ -498,6 +513,21 @@ int32_t zzb_run_upload_kappa(zzb_run_t r, const double* kappa)
     return ZZB_OK;
 }
 
+// FactBoomerang parameters (types.jl:62-79): sigma scales refreshed velocities, lambdaref = total refreshment rate (> 0:
+// hasrefresh(::FactBoomerang) = true, fact_samplers.jl:18), rho = autoregression of the refreshment.  Before zzb_run_upload.
+int32_t zzb_run_upload_boomerang(zzb_run_t r, const double* sigma, double lambdaref, double rho)
+{
+    if (!r || !sigma) return fail(ZZB_E_ARG, "null argument");
+    if (!(r->flags & ZZB_FLAG_BOOMERANG)) return fail(ZZB_E_ARG, "run was not created with ZZB_FLAG_BOOMERANG");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (!(lambdaref > 0.0)) return fail(ZZB_E_ARG, "FactBoomerang needs a refreshment rate lambdaref > 0");
+    if (!(rho > -1.0 && rho < 1.0)) return fail(ZZB_E_ARG, "rho must lie in (-1, 1)");
+    CtxGuard cg;
+    CU(cuMemcpyHtoD(r->bsig.p, sigma, (size_t)r->d * 8));
+    r->lambdaref = lambdaref; r->rho = rho; r->have_boom = true;
+    return ZZB_OK;
+}
+
 // (Re)initialise the device state from the inputs already resident in HBM: per-coordinate records, initial
 // bounds and first proposal times (sfact.jl:167-187).  No host<->device traffic except the 200-byte control block.
 int32_t zzb_run_reset(zzb_run_t r)
@@ -506,6 +536,7 @@ int32_t zzb_run_reset(zzb_run_t r)
     if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
     if (!r->have_inputs) return fail(ZZB_E_ARG, "zzb_run_upload must precede zzb_run_reset");
     if ((r->flags & ZZB_FLAG_STICKY) && !r->have_kappa) return fail(ZZB_E_ARG, "zzb_run_upload_kappa must precede zzb_run_upload for a sticky run");
+    if ((r->flags & ZZB_FLAG_BOOMERANG) && !r->have_boom) return fail(ZZB_E_ARG, "zzb_run_upload_boomerang must precede zzb_run_upload for a Boomerang run");
     if ((r->flags & ZZB_FLAG_STICKY) && r->adapt) return fail(ZZB_E_ARG, "adapt is not supported by the sticky sampler on the device path");
     for (int q = 0; q < r->nranks; ++q)
         if (q != r->rank && !r->peer_open[q]) return fail(ZZB_E_ARG, "peer %d of a sharded run has not been imported", q);
@@ -687,6 +718,28 @@ int32_t zzb_sspdmp_run(zzb_problem_t p, double t0, const double* x0, const doubl
     int32_t st2 = fetch_state(r);
     if (st2) { zzb_run_free(r); return st2; }
     *out = r;
+    return st;
+}
+
+int32_t zzb_spdmp_boomerang_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, double* c,
+                                const double* sigma, double lambdaref, double rho, const uint64_t* seed, int32_t adapt,
+                                double factor, uint32_t flags, zzb_run_t* out)
+{
+    if (!out || !c || !sigma) return fail(ZZB_E_ARG, "null argument");
+    zzb_run_t r = nullptr;
+    int32_t st = zzb_run_create(p, flags | ZZB_FLAG_BOOMERANG, 0, &r);
+    if (st) return st;
+    st = zzb_run_upload_boomerang(r, sigma, lambdaref, rho);
+    if (!st) st = zzb_run_upload(r, t0, x0, theta0, c, seed, adapt, factor);
+    if (!st) st = zzb_run_execute(r, T, nullptr);
+    if (st && st != ZZB_E_BOUND) { zzb_run_free(r); return st; }
+    int32_t st2 = fetch_state(r);
+    if (st2) { zzb_run_free(r); return st2; }
+    memcpy(c, r->fc.data(), (size_t)r->d * 8);
+    *out = r;
+    if (st == ZZB_E_BOUND)
+        fail(ZZB_E_BOUND, "Tuning parameter `c` too small. (coordinate %d, t = %.17g, l = %.17g, lb = %.17g)", r->hc.viol_i,
+             r->hc.viol_t, r->hc.viol_l, r->hc.viol_lb);
     return st;
 }
 
