@@ -1,6 +1,7 @@
 # ZigZagBoomerangB200.jl -- thin Julia wrapper over libzzb200.so (include/zzb200.h).
 #
-# Adds GPU methods to the reference's own `spdmp` / `pdmp` generic functions: they are selected by dispatch when
+# Adds GPU methods to the reference's own `spdmp` / `pdmp` / `sspdmp` generic functions (ZigZag, LocalBound, sticky ZigZag,
+# FactBoomerang): they are selected by dispatch when
 # the "gradient" argument is a `GaussianPotential` descriptor instead of a closure, and return exactly what the
 # reference returns: `Ξ::FactTrace, (t, x, θ), (acc, num), c` (src/sfact.jl:211).
 #
@@ -9,15 +10,16 @@
 module ZigZagBoomerangB200
 
 using ZigZagBoomerang
-using ZigZagBoomerang: ZigZag, FactTrace, Trace, Seed
+using ZigZagBoomerang: ZigZag, FactBoomerang, LocalBound, FactTrace, Trace, Seed
 using SparseArrays
-import ZigZagBoomerang: spdmp, pdmp
+import ZigZagBoomerang: spdmp, pdmp, sspdmp
 
 const libzzb200 = get(ENV, "ZZB200_LIB", joinpath(@__DIR__, "..", "libzzb200.so"))
 const cubin = get(ENV, "ZZB200_CUBIN", joinpath(@__DIR__, "..", "zzb200_kernels.cubin"))
 
 const ZZB_E_BOUND = Int32(3)
 const ZZB_FLAG_NO_TRACE = UInt32(1)
+const ZZB_FLAG_LOCAL_BOUND = UInt32(2)
 
 """
     GaussianPotential(Γ, h = nothing)
@@ -52,9 +54,11 @@ function init(device::Integer = 0)
     initialised[] = true
 end
 
-function spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G::Union{ZigZagBoomerang.All,ZigZagBoomerang.Matched}, F::ZigZag, args...;
-               factor = 1.8, adapt = false, adaptscale = false, progress = false, progress_stops = 20, seed = Seed())
-    F.λref == 0 || error("refreshments (λref > 0) are not implemented on the device path")
+# One device run: problem from (∇ϕ, F), then the one-call entry point selected by `kind`, then the results in the
+# reference's return shape.  `kind`: :zigzag (zzb_spdmp_run, flags = 0 or ZZB_FLAG_LOCAL_BOUND), :sticky (zzb_sspdmp_run),
+# :boomerang (zzb_spdmp_boomerang_run).
+function device_run(kind::Symbol, ∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F; κ = nothing, flags = UInt32(0),
+                    factor = 1.8, adapt = false, seed = Seed())
     init()
     d = length(x0)
     Γt, Γb = ∇ϕ.Γ, F.Γ
@@ -64,15 +68,34 @@ function spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G::Union{ZigZagBoome
     run = Ref{Ptr{Cvoid}}(C_NULL)
     h = ∇ϕ.h === nothing ? Ptr{Float64}(C_NULL) : pointer(∇ϕ.h)
     sd = UInt64[seed[1], seed[2]]
-    GC.@preserve Γt Γb μ x0v θ0v cv sd ∇ϕ begin
-        check(ccall((:zzb_problem_create_gaussian, libzzb200), Int32,
-                    (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64},
-                     Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
-                    prob, d, Γt.colptr, Γt.rowval, Γt.nzval, h, Γb.colptr, Γb.rowval, Γb.nzval, μ))
-        st = ccall((:zzb_spdmp_run, libzzb200), Int32,
-                   (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{UInt64}, Int32, Float64,
-                    UInt32, Ref{Ptr{Cvoid}}),
-                   prob[], t0, x0v, θ0v, T, cv, sd, adapt, factor, UInt32(0), run)
+    κv = κ === nothing ? Float64[] : Vector{Float64}(κ isa Number ? fill(κ, d) : κ)
+    σv = kind === :boomerang ? Vector{Float64}(F.σ) : Float64[]
+    GC.@preserve Γt Γb μ x0v θ0v cv sd κv σv ∇ϕ begin
+        if flags & ZZB_FLAG_LOCAL_BOUND != 0     # the bound comes from the target itself (src/local.jl:2-6): bnd_* = NULL
+            check(ccall((:zzb_problem_create_gaussian, libzzb200), Int32,
+                        (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64},
+                         Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+                        prob, d, Γt.colptr, Γt.rowval, Γt.nzval, h, C_NULL, C_NULL, C_NULL, C_NULL))
+        else
+            check(ccall((:zzb_problem_create_gaussian, libzzb200), Int32,
+                        (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64},
+                         Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+                        prob, d, Γt.colptr, Γt.rowval, Γt.nzval, h, Γb.colptr, Γb.rowval, Γb.nzval, μ))
+        end
+        st = if kind === :sticky          # sspdmp, src/ss_fact.jl:159-217
+            ccall((:zzb_sspdmp_run, libzzb200), Int32,
+                  (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{UInt64}, UInt32,
+                   Ref{Ptr{Cvoid}}), prob[], t0, x0v, θ0v, T, cv, κv, sd, flags, run)
+        elseif kind === :boomerang        # spdmp with F::FactBoomerang, src/sfact.jl:29-48,73-145
+            ccall((:zzb_spdmp_boomerang_run, libzzb200), Int32,
+                  (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Float64,
+                   Ptr{UInt64}, Int32, Float64, UInt32, Ref{Ptr{Cvoid}}),
+                  prob[], t0, x0v, θ0v, T, cv, σv, F.λref, F.ρ, sd, adapt, factor, flags, run)
+        else                              # spdmp / pdmp with F::ZigZag, src/sfact.jl:162-214,236 (LocalBound: src/local.jl:95-149)
+            ccall((:zzb_spdmp_run, libzzb200), Int32,
+                  (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{UInt64}, Int32, Float64,
+                   UInt32, Ref{Ptr{Cvoid}}), prob[], t0, x0v, θ0v, T, cv, sd, adapt, factor, flags, run)
+        end
         if st != 0
             ccall((:zzb_problem_free, libzzb200), Int32, (Ptr{Cvoid},), prob[])
             check(st)
@@ -89,18 +112,57 @@ function spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G::Union{ZigZagBoome
                     run[], t, x, θ, cv))
         acc = Vector{Int}(undef, d); num = Ref{Int64}(0)
         check(ccall((:zzb_run_counts, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ref{Int64}), run[], acc, num))
-        c .= cv                                        # adapted bounds, like the in-place `adapt!` of the reference
-        return Ξ, (t, x, θ), (acc, num[]), c
+        return Ξ, (t, x, θ), (acc, num[]), cv
     finally
         ccall((:zzb_run_free, libzzb200), Int32, (Ptr{Cvoid},), run[])
         ccall((:zzb_problem_free, libzzb200), Int32, (Ptr{Cvoid},), prob[])
     end
 end
 
-spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F::ZigZag, args...; kargs...) =
-    spdmp(∇ϕ, t0, x0, θ0, T, c, ZigZagBoomerang.Matched(), F, args...; kargs...)
-pdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F::ZigZag, args...; kargs...) =
-    spdmp(∇ϕ, t0, x0, θ0, T, c, ZigZagBoomerang.All(), F, args...; kargs...)
+const Nbhd = Union{ZigZagBoomerang.All,ZigZagBoomerang.Matched}
+
+# spdmp / pdmp, F::ZigZag (src/sfact.jl:162-214,236).  Matched() and All() select the same kernel (INTEGRATION.md).
+function spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G::Nbhd, F::ZigZag, args...;
+               factor = 1.8, adapt = false, adaptscale = false, progress = false, progress_stops = 20, seed = Seed())
+    F.λref == 0 || error("ZigZag refreshments (λref > 0) are not implemented on the device path")
+    Ξ, u, an, cv = device_run(:zigzag, ∇ϕ, t0, x0, θ0, T, c, F; factor = factor, adapt = adapt, seed = seed)
+    c .= cv                                            # adapted bounds, like the in-place `adapt!` of the reference
+    Ξ, u, an, c
+end
+
+# spdmp / pdmp, F::FactBoomerang (same generic function upstream; flow src/sfact.jl:29-48, rate/bound src/fact_samplers.jl:37-39,58-65)
+function spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G::Nbhd, F::FactBoomerang, args...;
+               factor = 1.8, adapt = false, adaptscale = false, progress = false, progress_stops = 20, seed = Seed())
+    Ξ, u, an, cv = device_run(:boomerang, ∇ϕ, t0, x0, θ0, T, c, F; factor = factor, adapt = adapt, seed = seed)
+    c .= cv
+    Ξ, u, an, c
+end
+
+# spdmp(∇ϕ, t0, x0, θ0, T, C::LocalBound, F, ...) (src/local.jl:95-149)
+function spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, C::LocalBound, G::Nbhd, F::ZigZag, args...;
+               factor = 1.8, adapt = false, progress = false, progress_stops = 20, seed = Seed())
+    Ξ, u, an, cv = device_run(:zigzag, ∇ϕ, t0, x0, θ0, T, C.c, F; flags = ZZB_FLAG_LOCAL_BOUND, factor = factor, adapt = adapt, seed = seed)
+    C.c .= cv
+    Ξ, u, an, C
+end
+
+# sspdmp(∇ϕ, t0, x0, θ0, T, c, [G,] F::ZigZag, κ, ...) (src/ss_fact.jl:159-217); acc is the scalar count of reflections
+function sspdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G, F::ZigZag, κ, args...;
+                strong_upperbounds = false, factor = 1.5, adapt = false, reversible = false, seed = Seed())
+    (strong_upperbounds || adapt || reversible) && error("sspdmp options strong_upperbounds / adapt / reversible are not implemented on the device path")
+    Ξ, u, (acc, num), cv = device_run(:sticky, ∇ϕ, t0, x0, θ0, T, c, F; κ = κ, seed = seed)
+    Ξ, u, (sum(acc), num), c
+end
+sspdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F::ZigZag, κ, args...; kargs...) = sspdmp(∇ϕ, t0, x0, θ0, T, c, nothing, F, κ, args...; kargs...)
+
+for FT in (:ZigZag, :FactBoomerang)
+    @eval begin
+        spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F::$FT, args...; kargs...) =
+            spdmp(∇ϕ, t0, x0, θ0, T, c, ZigZagBoomerang.Matched(), F, args...; kargs...)
+        pdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F::$FT, args...; kargs...) =
+            spdmp(∇ϕ, t0, x0, θ0, T, c, ZigZagBoomerang.All(), F, args...; kargs...)
+    end
+end
 
 export GaussianPotential
 end # module
