@@ -96,11 +96,66 @@ def workload(args):
 
 
 def cpu_reference_step(O, G, x0, th0, c, T, seed):
-    """One step on the host: the oracle's faithful restatement of spdmp (binary heap, single xoroshiro stream,
-    in-place moves).  Returns (switches, proposals, seconds) excluding nothing but input generation."""
-    t = time.perf_counter()
+    """One step on the host, single thread: the oracle's faithful restatement of spdmp (binary heap, single xoroshiro
+    stream, in-place moves; src/sfact.jl:162-212).  Returns (switches, proposals, seconds of the event loop, setup excluded)."""
     r = O.spdmp(G, G, 0.0, x0, th0, T, c, seed=seed, mode=O.RNG_SEQ | O.ARITH_INPLACE)
-    return int(r.acc.sum()), int(r.num), time.perf_counter() - t
+    return int(r.acc.sum()), int(r.num), r.loop_seconds
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def parallel_chunks(d, cores):
+    """Chunk counts to try for parallel_spdmp: Partition(nt, n) needs nt | n (src/parallel.jl:27); one host thread runs the
+    outer task, so prefer nt <= cores - 1 but also try nt <= cores."""
+    divs = [k for k in range(1, cores + 1) if d % k == 0]
+    cand = {max(divs)}
+    lower = [k for k in divs if k <= max(1, cores - 1)]
+    if lower:
+        cand.add(max(lower))
+    return sorted(cand)
+
+
+def cpu_parallel_step(O, G, G2, K, x0, th0, c, T, seed, delta):
+    """One step on the host, K worker threads + the outer task: the restatement of the reference's multithreaded
+    parallel_spdmp (src/parallel.jl) with the bound matrix restricted to the chunks (G2)."""
+    r = O.spdmp(G, G2, 0.0, x0, th0, T, c, seed=seed, parallel=(K, delta), adapt=True)
+    return int(r.acc.sum()), int(r.num), r.loop_seconds
+
+
+def cpu_baselines(O, G, x0, th0, c, T, delta=0.02):
+    """Single-thread spdmp and multithreaded parallel_spdmp on the same workload; returns the cpu_baseline object (the better
+    of the two as `value`, both stated)."""
+    d = G.n
+    cores = host_cores()
+    a, b, s = cpu_reference_step(O, G, x0, th0, c, T, (1, 2))
+    single = dict(value=a / s, proposals_per_s=b / s, seconds=s, switches=a)
+    best = None
+    for K in parallel_chunks(d, cores):
+        if K == 1:
+            continue
+        G2 = O.block_diagonal(G, K)
+        a2, b2, s2 = cpu_parallel_step(O, G, G2, K, x0, th0, c, T, (1, 2), delta)
+        if best is None or a2 / s2 > best["value"]:
+            best = dict(value=a2 / s2, proposals_per_s=b2 / s2, seconds=s2, switches=a2, threads=K + 1, chunks=K)
+    use_par = best is not None and best["value"] > single["value"]
+    top = best if use_par else single
+    return {
+        "value": top["value"], "unit": "events/s", "cores": top.get("threads", 1), "kind": "port",
+        "sample": (f"spdmp over [0,{T}] on the same d={d} GMRF, event loop only (setup excluded): "
+                   + (f"multithreaded parallel_spdmp restatement (src/parallel.jl), {best['chunks']} chunk threads + outer task, Delta={delta}, "
+                      f"{best['switches']} switches in {best['seconds']:.2f} s; " if best else "")
+                   + f"single-thread spdmp restatement (src/sfact.jl) {single['switches']} switches in {single['seconds']:.2f} s; host has {cores} cores"),
+        "proposals_per_s": top["proposals_per_s"], "seconds": top["seconds"],
+        "single_thread_events_per_s": single["value"],
+        "multithread_events_per_s": best["value"] if best else None,
+        "multithread_threads": best["threads"] if best else None,
+        "host_cores": cores,
+    }
 
 
 def run_reference(args):
@@ -110,24 +165,20 @@ def run_reference(args):
     import oracle_lib as O
     zzb, G, x0, th0, c = workload(args)
     T = args.cpu_T if args.cpu_T else args.T
-    for _ in range(args.warmup):
-        cpu_reference_step(O, G, x0, th0, c, min(T, 0.25), (1, 2))
-    nsw = npr = 0
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        a, b, _ = cpu_reference_step(O, G, x0, th0, c, T, (1 + k, 2))
-        nsw += a
-        npr += b
-    dt = time.perf_counter() - t0
-    val = nsw / dt
-    sample = f"{args.steps} x spdmp over [0,{T}] on the same d={G.n} GMRF, single host thread (the reference loop is sequential)"
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(O, G, x0, th0, c, min(T, 0.1), (1, 2))
+    steps = max(1, min(args.steps, 3))   # every step is a bounded sample of the workload (about 10 s of CPU work)
+    runs = [cpu_baselines(O, G, x0, th0, c, T) for _ in range(steps)]
+    cb = max(runs, key=lambda r: r["value"])
+    val = cb["value"]
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "events/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "events/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * cb["seconds"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"local ZigZag spdmp, {args.n}x{args.n} grid GMRF (d={G.n}), c={'sqrt(eps)' if args.tight else '||Gamma[:,i]||'}, "
-                               f"T_step={T}", "proposals_per_s": npr / dt},
-        "cpu_baseline": {"value": val, "unit": "events/s", "cores": 1, "kind": "port", "sample": sample},
+                               f"T_step={T}", "proposals_per_s": cb["proposals_per_s"],
+                   "note": "CPU restatement of the reference (Julia is not installed): best of the single-thread spdmp and the multithreaded parallel_spdmp"},
+        "cpu_baseline": cb,
         "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -208,7 +259,7 @@ def run_ours(args):
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01b_traffic.json")) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     except Exception:
         pass
@@ -217,15 +268,26 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu:
         import oracle_lib as O
-        Tc = args.cpu_T if args.cpu_T else args.T
-        best = None
-        for k in range(2):
-            a, b, s = cpu_reference_step(O, G, x0, th0, c, Tc, (1, 2))
-            best = (a, b, s) if best is None or s < best[2] else best
-        cpu = {"value": best[0] / best[2], "unit": "events/s", "cores": 1, "kind": "port",
-               "sample": f"best of 2: spdmp over [0,{Tc}] on the same d={d} GMRF ({best[0]} switches, {best[1]} proposals, "
-                         f"{best[2]:.2f} s), oracle restatement of src/sfact.jl, single thread",
-               "proposals_per_s": best[1] / best[2]}
+        cpu = cpu_baselines(O, G, x0, th0, c, args.cpu_T if args.cpu_T else args.T)
+
+    # ---- the same step with the tight bound c = sqrt(eps) (scripts/example.jl:39; acceptance ~ 1): reported beside the headline
+    tight = None
+    if not args.tight and not args.no_tight:
+        ct = np.full(d, np.sqrt(np.finfo(np.float64).eps))
+        run3 = zzb.Run(prob, record_trace=False)
+        run3.set(target_frac=args.frac)
+        run3.upload(0.0, x0, th0, ct, seed=(1, 2))
+        for _ in range(2):
+            run3.reset(); run3.execute(args.T)
+        _capi.event_record(0)
+        for _ in range(3):
+            run3.reset(); run3.execute(args.T)
+        _capi.event_record(1)
+        t_ms = _capi.event_elapsed_ms() / 3
+        acc3, num3 = run3.counts()
+        tight = {"c": "sqrt(eps)", "events_per_s": int(acc3.sum()) / (t_ms * 1e-3), "ms_per_step": t_ms,
+                 "switches_per_step": int(acc3.sum()), "proposals_per_step": int(num3)}
+        run3.close()
 
     out = {
         "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -235,7 +297,8 @@ def run_ours(args):
                                f"T_step={args.T}, one step = full run from (x0, theta0)",
                    "l2": "device working set (state + flip lists + work lists ~ 0.4 KB/coordinate = 400 MB) exceeds the 126 MB L2",
                    "switches_per_step": nacc, "proposals_per_step": int(num), "proposals_per_s": num * args.steps / (total_ms * 1e-3),
-                   "windows_per_step": st["windows"], "passes_per_step": st["passes"], "target_frac": args.frac},
+                   "windows_per_step": st["windows"], "passes_per_step": st["passes"], "target_frac": args.frac,
+                   "tight_bound_variant": tight},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "zz_run_kernel_grid", "kernel_ms_per_launch": k_ms,
                      "algorithmic_bytes_per_launch": alg_bytes,
@@ -351,6 +414,7 @@ def main():
     ap.add_argument("--frac", type=float, default=0.15, help="window length controller: proposals per window / d")
     ap.add_argument("--tight", action="store_true", help="c = sqrt(eps) (scripts/example.jl:39) instead of column norms")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tight", action="store_true", help="skip the extra c = sqrt(eps) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -43,12 +43,14 @@
  *              Delta = 2/c/|theta| and is then renewed.  The target descriptor plays the role of the extended-form
  *              closure: (grad phi_i, v_i) = (idot(G,i,x) - h_i, theta_i idot(G,i,theta)) (local.jl:7).
  * GPU results must equal mode ctr|lazy (|8) bit for bit.
- * Further entry points below: zzo_sspdmp (sticky ZigZag, src/ss_fact.jl) and zzo_spdmp_boom (FactBoomerang).
+ * Further entry points below: zzo_sspdmp (sticky ZigZag, src/ss_fact.jl), zzo_spdmp_boom (FactBoomerang) and
+ * zzo_parallel_spdmp (the reference's multithreaded parallel_spdmp, src/parallel.jl -- CPU baseline of bench.py).
  */
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
+#include <time.h>
 
 #include "../zigzagboomerang.jl_b200/csrc/zz_math.h" /* zz_log, zz_u01, zz_sincos / zz_boom_at (shared primitives) */
 
@@ -64,6 +66,8 @@
 
 typedef struct { double t; int64_t i; double x; double th; } zzo_event; /* trace.jl:38 */
 
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec; }
+
 typedef struct {
     int64_t d;
     int mode;
@@ -74,6 +78,7 @@ typedef struct {
     double *c;
     double *x0; double t0;
     int status; int64_t err_i; double err_t, err_l, err_lb;
+    double loop_seconds;   /* wall time of the event loop alone (setup excluded), for the CPU baselines of bench.py */
 } zzo_run;
 
 /* ---- poisson_time, src/poissontime.jl:8-30 ------------------------------------------------ */
@@ -370,6 +375,7 @@ zzo_run *zzo_spdmp(int64_t d,
     }
 
     int64_t num = 0;
+    const double tl0 = now_s();
     /* sfact.jl:199 outer loop; body = spdmp_inner! (:73-145), refresh branch omitted (lambda_ref == 0,
        fact_samplers.jl:19) */
     while (tp < T && r->status == ZZO_OK) {
@@ -431,6 +437,7 @@ zzo_run *zzo_spdmp(int64_t d,
         }
     }
     r->num = num;
+    r->loop_seconds = now_s() - tl0;
     r->t = lazy ? z->tf : z->t; r->x = lazy ? z->xf : z->x; r->th = z->th; r->c = z->c;
     if (lazy) { free(z->t); free(z->x); } else { free(z->tf); free(z->xf); }
     free(z->t_old); free(z->ba); free(z->bb); free(z->kctr);
@@ -792,7 +799,285 @@ zzo_run *zzo_spdmp_boom(int64_t d,
 void zzo_sincos(double x, double *s, double *c) { zz_sincos(x, s, c); }
 double zzo_randn(double u1, double u2) { return zz_randn(u1, u2); }
 
+/* =====================================================================================================
+ * parallel_spdmp (src/parallel.jl:5-253): the reference's experimental MULTITHREADED local ZigZag -- the CPU baseline
+ * "with all the host threads it can use" of bench.py.  Restated with pthreads:
+ *   Partition                 parallel.jl:5-30       contiguous chunks of d / K coordinates, one heap per chunk
+ *   parallel_innermost!       parallel.jl:34-61      one proposal (in-place moves, thinning, reschedule inside the chunk)
+ *   parallel_spdmp_inner!     parallel.jl:63-104     worker: runs the events of its chunk while the next one is an INNER
+ *                                                    coordinate (whole neighbourhood in the chunk) and not later than
+ *                                                    t_next; otherwise reports (i, t') and sleeps
+ *   parallel_spdmp_outer!     parallel.jl:182-253    when every worker sleeps: absorb their events, process the reported
+ *                                                    events in time order if the neighbouring chunks have reached that
+ *                                                    time, wake the workers that are not waiting for a neighbour
+ *   parallel_spdmp            parallel.jl:106-151    setup; requires that the BOUND matrix Z.Gamma has no entries across
+ *                                                    chunks ("Upper bounds may not depend across chunks", :126-129) while
+ *                                                    the target's gradient and the neighbourhoods G use the full matrix
+ * Differences: Julia tasks + Threads.Condition become pthreads + spin/yield flags; every thread draws from its own
+ * xoroshiro128+ stream seeded from `seed` (upstream: Rng() with fresh entropy per task).  Like upstream, the result is not
+ * reproducible run to run in its draws; the law is that of spdmp with Z = ZigZag(Gamma2, mu).
+ * ===================================================================================================== */
+#include <pthread.h>
+#include <sched.h>
+#include <stdatomic.h>
+
+typedef struct pctx_s pctx;
+typedef struct {
+    pctx *P; int ti; pthread_t th; xoro rng;
+    heapq Q;
+    zzo_event *ev; int64_t nev, cap;
+    int64_t res_i; double res_t; int64_t res_acc, res_num;   /* ret[] = (i, t', acc, num), parallel.jl:74 */
+    atomic_int wake;                                          /* 0 sleeping, 1 run, 2 done */
+    char pad[64];
+} pworker;
+
+struct pctx_s {
+    int64_t d, K, csz; double Delta, T, t0;
+    csc G, G1, tg; const double *h, *mu;
+    int64_t *g2ptr, *g2idx;
+    double *t, *x, *th, *t_old, *ba, *bb, *c;
+    char *inner; int64_t *acc;
+    int adapt; double factor;
+    atomic_int active; atomic_int failed;
+    int64_t err_i; double err_t, err_l, err_lb;
+    pworker *W;
+};
+
+static inline void p_move(pctx *P, const int64_t *idx, int64_t n, double tp)
+{ /* smove_forward!(G, i, t, x, th, t', Z::ZigZag), sfact.jl:6-12 */
+    for (int64_t q = 0; q < n; ++q) {
+        int64_t k = idx[q] - 1;
+        P->x[k] = P->x[k] + P->th[k] * (tp - P->t[k]);
+        P->t[k] = tp;
+    }
+}
+static inline void p_ab(pctx *P, int64_t i)
+{ /* ab(G1, i, x, th, c, Z::ZigZag), fact_samplers.jl:50-54 with Z.Gamma = the block-diagonal bound matrix */
+    P->ba[i - 1] = P->c[i - 1] + (idot(&P->G1, i, P->x) - idot(&P->G1, i, P->mu)) * P->th[i - 1];
+    P->bb[i - 1] = P->c[i - 1] / 100 + P->th[i - 1] * idot(&P->G1, i, P->th);
+}
+static inline void p_resched(pctx *P, xoro *rng, int64_t j)
+{ /* Q[q1][q2] = t[j] + poisson_time(b[j], rand(rng)), parallel.jl:50-51,57-58 */
+    int64_t q1 = (j - 1) / P->csz, q2 = (j - 1) % P->csz + 1;
+    h_set(&P->W[q1].Q, q2, P->t[j - 1] + o_poisson_time(P->ba[j - 1], P->bb[j - 1], xoro_rand(rng)));
+}
+/* parallel_innermost!, parallel.jl:34-61; returns 1 when the proposal was accepted */
+static int p_innermost(pctx *P, xoro *rng, int64_t i, double tp)
+{
+    const int64_t *nbG = &P->G.rowval[P->G.colptr[i - 1] - 1]; int64_t nG = P->G.colptr[i] - P->G.colptr[i - 1];
+    p_move(P, nbG, nG, tp);
+    double gi = idot(&P->tg, i, P->x);
+    if (P->h) gi = gi - P->h[i - 1];
+    double l = zz_pos(gi * P->th[i - 1]);
+    double lb = zz_pos(P->ba[i - 1] + P->bb[i - 1] * (P->t[i - 1] - P->t_old[i - 1]));
+    if (xoro_rand(rng) * lb < l) {
+        if (l >= lb) {
+            if (!P->adapt) {
+                if (!atomic_exchange(&P->failed, 1)) { P->err_i = i; P->err_t = tp; P->err_l = l; P->err_lb = lb; }
+                return 0;
+            }
+            P->c[i - 1] *= P->factor;
+        }
+        p_move(P, &P->g2idx[P->g2ptr[i - 1]], P->g2ptr[i] - P->g2ptr[i - 1], tp);
+        P->th[i - 1] = -P->th[i - 1];
+        for (int64_t p = P->G1.colptr[i - 1]; p < P->G1.colptr[i]; ++p) {
+            int64_t j = P->G1.rowval[p - 1];
+            p_ab(P, j);
+            P->t_old[j - 1] = P->t[j - 1];
+            p_resched(P, rng, j);
+        }
+        P->acc[i - 1] += 1;
+        return 1;
+    }
+    p_ab(P, i);
+    P->t_old[i - 1] = P->t[i - 1];
+    p_resched(P, rng, i);
+    return 0;
+}
+static void p_push(pworker *w, double t, int64_t i, double x, double th)
+{
+    if (w->nev == w->cap) { w->cap = w->cap ? 2 * w->cap : 4096; w->ev = (zzo_event *)realloc(w->ev, (size_t)w->cap * sizeof(zzo_event)); }
+    zzo_event e = { t, i, x, th };
+    w->ev[w->nev++] = e;
+}
+static inline void p_spin(int *n) { if (++*n < 200) __builtin_ia32_pause(); else { sched_yield(); *n = 0; } }
+
+/* parallel_spdmp_inner!, parallel.jl:63-104 */
+static void *p_worker(void *arg)
+{
+    pworker *w = (pworker *)arg; pctx *P = w->P;
+    int64_t acc = 0, num = 0;
+    double tnext = P->t0 + P->Delta;
+    for (;;) {
+        int spin = 0;
+        while (atomic_load(&w->wake) == 0) p_spin(&spin);
+        if (atomic_load(&w->wake) == 2) return NULL;
+        for (;;) {
+            num += 1;
+            int64_t ii = w->Q.key[1]; double tp = w->Q.val[1];
+            int64_t i = (int64_t)w->ti * P->csz + ii;
+            if (!P->inner[i - 1] || tp > tnext || atomic_load_explicit(&P->failed, memory_order_relaxed)) {
+                tnext = tp + P->Delta;
+                w->res_i = i; w->res_t = tp; w->res_acc = acc; w->res_num = num;
+                acc = num = 0;
+                atomic_store(&w->wake, 0);
+                atomic_fetch_sub(&P->active, 1);   /* "last one turns the light off" */
+                break;
+            }
+            if (p_innermost(P, &w->rng, i, tp)) { acc += 1; p_push(w, P->t[i - 1], i, P->x[i - 1], P->th[i - 1]); }
+        }
+    }
+}
+
+static int ev_cmp(const void *a, const void *b)
+{
+    double ta = ((const zzo_event *)a)->t, tb = ((const zzo_event *)b)->t;
+    return (ta > tb) - (ta < tb);
+}
+
+zzo_run *zzo_parallel_spdmp(int64_t d,
+                            const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
+                            const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
+                            double t0, const double *x0, const double *th0, double T, const double *c_in,
+                            const uint64_t *seed, int adapt, double factor, int64_t K, double Delta)
+{
+    zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run));
+    r->d = d; r->t0 = t0;
+    if (K < 1 || d % K != 0) { r->status = ZZO_E_ARG; return r; }   /* Partition(nt, n) = Partition{div(n, nt)}, parallel.jl:27 */
+    pctx Ps; pctx *P = &Ps; memset(P, 0, sizeof Ps);
+    P->d = d; P->K = K; P->csz = d / K; P->Delta = Delta; P->T = T; P->t0 = t0; P->adapt = adapt; P->factor = factor;
+    P->tg.colptr = tg_colptr; P->tg.rowval = tg_rowval; P->tg.nzval = tg_nzval; P->G = P->tg;   /* G = pattern of the target */
+    P->G1.colptr = bd_colptr; P->G1.rowval = bd_rowval; P->G1.nzval = bd_nzval;
+    P->h = h; P->mu = mu;
+    size_t nb = (size_t)d * sizeof(double);
+    P->t = (double *)malloc(nb); P->x = (double *)malloc(nb); P->th = (double *)malloc(nb); P->t_old = (double *)malloc(nb);
+    P->ba = (double *)malloc(nb); P->bb = (double *)malloc(nb); P->c = (double *)malloc(nb);
+    P->inner = (char *)malloc((size_t)d); P->acc = (int64_t *)calloc((size_t)d, sizeof(int64_t));
+    r->x0 = (double *)malloc(nb); memcpy(r->x0, x0, nb);
+    for (int64_t k = 0; k < d; ++k) { P->t[k] = t0; P->t_old[k] = t0; P->x[k] = x0[k]; P->th[k] = th0[k]; P->c[k] = c_in[k]; }
+    /* inner (parallel.jl:116), the subset assertion (:120) and the chunk-locality of G1 / G2 (:124-129) */
+    int bad = 0;
+    for (int64_t i = 1; i <= d && !bad; ++i) {
+        int64_t q = (i - 1) / P->csz; char in = 1;
+        for (int64_t p = tg_colptr[i - 1]; p < tg_colptr[i]; ++p) if ((tg_rowval[p - 1] - 1) / P->csz != q) in = 0;
+        P->inner[i - 1] = in;
+        int64_t pt = tg_colptr[i - 1];
+        for (int64_t p = bd_colptr[i - 1]; p < bd_colptr[i]; ++p) {
+            if ((bd_rowval[p - 1] - 1) / P->csz != q) bad = 1;                      /* bound crosses chunks */
+            while (pt < tg_colptr[i] && tg_rowval[pt - 1] < bd_rowval[p - 1]) ++pt;
+            if (pt >= tg_colptr[i] || tg_rowval[pt - 1] != bd_rowval[p - 1]) bad = 2; /* G[i] must contain G1[i] */
+        }
+    }
+    if (bad) { r->status = ZZO_E_GRAPH; goto cleanup0; }
+    {   /* G2[i] = setdiff(union(G1[j] for j in G1[i]), G[i]), parallel.jl:122 */
+        P->g2ptr = (int64_t *)calloc((size_t)d + 1, sizeof(int64_t));
+        int64_t *mark = (int64_t *)calloc((size_t)d + 1, sizeof(int64_t));
+        int64_t cap = 16, n = 0;
+        P->g2idx = (int64_t *)malloc((size_t)cap * sizeof(int64_t));
+        for (int64_t i = 1; i <= d; ++i) {
+            P->g2ptr[i - 1] = n;
+            for (int64_t p = tg_colptr[i - 1]; p < tg_colptr[i]; ++p) mark[tg_rowval[p - 1]] = -i;
+            for (int64_t p = bd_colptr[i - 1]; p < bd_colptr[i]; ++p) {
+                int64_t j = bd_rowval[p - 1];
+                for (int64_t q = bd_colptr[j - 1]; q < bd_colptr[j]; ++q) {
+                    int64_t k = bd_rowval[q - 1];
+                    if (mark[k] == -i || mark[k] == i) continue;
+                    mark[k] = i;
+                    if (n == cap) { cap *= 2; P->g2idx = (int64_t *)realloc(P->g2idx, (size_t)cap * sizeof(int64_t)); }
+                    P->g2idx[n++] = k;
+                }
+            }
+        }
+        P->g2ptr[d] = n;
+        free(mark);
+    }
+    P->W = (pworker *)calloc((size_t)K, sizeof(pworker));
+    xoro seeder = { seed[0], seed[1] };
+    for (int64_t i = 1; i <= d; ++i) p_ab(P, i);
+    for (int64_t q = 0; q < K; ++q) {
+        pworker *w = &P->W[q];
+        w->P = P; w->ti = (int)q; w->rng.x = xoro_next(&seeder) | 1ULL; w->rng.y = xoro_next(&seeder);
+        w->Q.n = 0; w->Q.lex = 0;
+        w->Q.key = (int64_t *)malloc(((size_t)P->csz + 2) * sizeof(int64_t));
+        w->Q.val = (double *)malloc(((size_t)P->csz + 2) * sizeof(double));
+        w->Q.index = (int64_t *)malloc(((size_t)P->csz + 2) * sizeof(int64_t));
+        for (int64_t q2 = 1; q2 <= P->csz; ++q2) {   /* parallel.jl:130-133 (global rand(); no + t0) */
+            int64_t i = q * P->csz + q2;
+            h_enqueue(&w->Q, q2, o_poisson_time(P->ba[i - 1], P->bb[i - 1], xoro_rand(&seeder)));
+        }
+        atomic_store(&w->wake, 0);
+    }
+    {
+        xoro orng = { xoro_next(&seeder) | 1ULL, xoro_next(&seeder) };
+        double *tpv = (double *)malloc((size_t)K * sizeof(double));
+        double *evtime = (double *)calloc((size_t)K, sizeof(double));
+        int64_t *perm = (int64_t *)malloc((size_t)K * sizeof(int64_t));
+        int64_t *waitfor = (int64_t *)calloc((size_t)K, sizeof(int64_t));
+        pworker outer; memset(&outer, 0, sizeof outer);   /* event buffer of the outer task */
+        for (int64_t q = 0; q < K; ++q) { tpv[q] = t0; perm[q] = q; }
+        double tmin = t0;
+        int64_t acc = 0, num = 0;
+        atomic_store(&P->active, (int)K);
+        const double tl0 = now_s();
+        for (int64_t q = 0; q < K; ++q) { atomic_store(&P->W[q].wake, 1); pthread_create(&P->W[q].th, NULL, p_worker, &P->W[q]); }
+        /* parallel_spdmp_outer!, parallel.jl:182-253 */
+        while (tmin < T) {
+            int spin = 0;
+            while (atomic_load(&P->active) != 0) p_spin(&spin);
+            if (atomic_load(&P->failed)) break;
+            for (int64_t q = 0; q < K; ++q)
+                if (waitfor[q] == 0) {
+                    pworker *w = &P->W[q];
+                    for (int64_t e = 0; e < w->nev; ++e) p_push(&outer, w->ev[e].t, w->ev[e].i, w->ev[e].x, w->ev[e].th);
+                    w->nev = 0;
+                    evtime[q] = w->res_t;
+                }
+            for (int64_t a = 1; a < K; ++a) {   /* sortperm!(perm, evtime, alg = InsertionSort) */
+                int64_t v = perm[a], b2 = a;
+                while (b2 > 0 && evtime[perm[b2 - 1]] > evtime[v]) { perm[b2] = perm[b2 - 1]; --b2; }
+                perm[b2] = v;
+            }
+            for (int64_t a = 0; a < K; ++a) {
+                int64_t q = perm[a];
+                pworker *w = &P->W[q];
+                int64_t i = w->res_i; double tq = w->res_t;
+                if (waitfor[q] == 0) { num += w->res_num; acc += w->res_acc; tpv[q] = tq; }
+                waitfor[q] = 0;
+                for (int64_t p = tg_colptr[i - 1]; p < tg_colptr[i]; ++p) {
+                    int64_t j = tg_rowval[p - 1];
+                    if (j == i) continue;
+                    if (tpv[(j - 1) / P->csz] < tq) waitfor[q] = i;
+                }
+                if (waitfor[q] != 0) continue;
+                if (p_innermost(P, &orng, i, tq)) { acc += 1; p_push(&outer, P->t[i - 1], i, P->x[i - 1], P->th[i - 1]); }
+            }
+            tmin = tpv[0];
+            for (int64_t q = 1; q < K; ++q) if (tpv[q] < tmin) tmin = tpv[q];
+            if (tmin >= T || atomic_load(&P->failed)) break;
+            int nwake = 0;
+            for (int64_t q = 0; q < K; ++q) if (waitfor[q] == 0) nwake++;
+            atomic_store(&P->active, nwake);
+            for (int64_t q = 0; q < K; ++q) if (waitfor[q] == 0) atomic_store(&P->W[q].wake, 1);
+        }
+        for (int64_t q = 0; q < K; ++q) atomic_store(&P->W[q].wake, 2);
+        for (int64_t q = 0; q < K; ++q) pthread_join(P->W[q].th, NULL);
+        r->loop_seconds = now_s() - tl0;
+        if (atomic_load(&P->failed)) { r->status = ZZO_E_BOUND; r->err_i = P->err_i; r->err_t = P->err_t; r->err_l = P->err_l; r->err_lb = P->err_lb; }
+        qsort(outer.ev, (size_t)outer.nev, sizeof(zzo_event), ev_cmp);   /* sort!(Xi.events, by = ev -> ev[1]), parallel.jl:173 */
+        r->ev = outer.ev; r->nev = outer.nev; r->cap = outer.cap;
+        r->num = num; (void)acc;
+        free(tpv); free(evtime); free(perm); free(waitfor);
+    }
+    for (int64_t q = 0; q < K; ++q) { free(P->W[q].Q.key); free(P->W[q].Q.val); free(P->W[q].Q.index); free(P->W[q].ev); }
+    free(P->W); free(P->g2ptr); free(P->g2idx);
+cleanup0:
+    r->acc = P->acc; r->t = P->t; r->x = P->x; r->th = P->th; r->c = P->c;
+    free(P->t_old); free(P->ba); free(P->bb); free(P->inner);
+    return r;
+}
+
 int zzo_status(const zzo_run *r) { return r->status; }
+double zzo_loop_seconds(const zzo_run *r) { return r->loop_seconds; }
 void zzo_error_info(const zzo_run *r, int64_t *i, double *t, double *l, double *lb)
 { *i = r->err_i; *t = r->err_t; *l = r->err_l; *lb = r->err_lb; }
 int64_t zzo_trace_len(const zzo_run *r) { return r->nev; }

@@ -42,10 +42,15 @@ def lib():
         L.zzo_spdmp_boom.restype = C.c_void_p
         L.zzo_spdmp_boom.argtypes = [C.c_int64] + [C.c_void_p] * 9 + [C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                      C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
+        L.zzo_parallel_spdmp.restype = C.c_void_p
+        L.zzo_parallel_spdmp.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
+                                         C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_double]
         L.zzo_sincos.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
         L.zzo_randn.restype = C.c_double
         L.zzo_randn.argtypes = [C.c_double, C.c_double]
         L.zzo_status.argtypes = [C.c_void_p]
+        L.zzo_loop_seconds.restype = C.c_double
+        L.zzo_loop_seconds.argtypes = [C.c_void_p]
         L.zzo_trace_len.restype = C.c_int64
         L.zzo_trace_len.argtypes = [C.c_void_p]
         L.zzo_trace_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
@@ -76,9 +81,20 @@ class BoundError(RuntimeError):
     pass
 
 
+def block_diagonal(G, K):
+    """Gamma2 of test/testparallel.jl:33-42: the entries of G that couple different chunks of d/K coordinates dropped."""
+    from zzb200.problems import CSC
+    csz = G.n // K
+    cols = np.repeat(np.arange(G.n), np.diff(G.colptr))
+    keep = (cols // csz) == ((G.rowval - 1) // csz)
+    colptr = np.concatenate([[1], 1 + np.cumsum(np.bincount(cols[keep], minlength=G.n))]).astype(np.int64)
+    return CSC(G.n, colptr, np.ascontiguousarray(G.rowval[keep]), np.ascontiguousarray(G.nzval[keep]))
+
+
 def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
-          mode=PARITY_MODE, kappa=None, boom=None):
+          mode=PARITY_MODE, kappa=None, boom=None, parallel=None):
     """Run the oracle.  ``target`` / ``bound`` are problems.CSC (target precision and the sampler's Z.Gamma).
+    ``parallel = (K, Delta)`` runs the multithreaded parallel_spdmp (src/parallel.jl) on K threads.
     With ``kappa`` (thaw rates) the sticky sampler sspdmp (src/ss_fact.jl) is run instead of spdmp; with
     ``boom = (sigma, lambdaref, rho)`` the factorised Boomerang (F::FactBoomerang in src/sfact.jl)."""
     L = lib()
@@ -88,7 +104,12 @@ def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), 
     mu = np.zeros(d) if mu is None else f8(mu)
     h = None if h is None else f8(h)
     sd = np.array(seed, dtype=np.uint64)
-    if boom is not None:
+    if parallel is not None:   # (K threads, Delta): parallel_spdmp of src/parallel.jl; `bound` must be block diagonal
+        r = L.zzo_parallel_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
+                                 _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
+                                 float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor),
+                                 int(parallel[0]), float(parallel[1]))
+    elif boom is not None:
         sigma = f8(boom[0])
         r = L.zzo_spdmp_boom(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
                              _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu), _p(sigma), float(boom[1]), float(boom[2]),
@@ -125,6 +146,7 @@ def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), 
         if boom is not None:   # the event-based moments assume a piecewise linear path (trace.jl:182-200)
             del out.m1, out.m2, out.s1, out.s2
         out.t0, out.x0, out.theta0 = t0, x0.copy(), theta0.copy()
+        out.loop_seconds = L.zzo_loop_seconds(r)
         return out
     finally:
         L.zzo_free(r)
