@@ -179,19 +179,14 @@ def test_subtrace(zzb):
     assert np.allclose(xs2, xs[: len(ts2)][:, J - 1])
 
 
-def test_golden_fixture(zzb):
-    """Regression fixture written by tests/golden/make_golden.py from the oracle itself (NOT a reference vector:
+@pytest.mark.parametrize("name", __import__("golden_cases").CASES)
+def test_golden_fixture(zzb, name):
+    """Regression fixtures written by tests/golden/make_golden.py from the oracle itself (NOT reference vectors:
     the reference has none for this path, see the oracle header)."""
     import json, os
-    path = os.path.join(os.path.dirname(__file__), "golden", "gmrf16_T3.json")
-    g = json.load(open(path))
-    G, x0, th0, c = zzb.gmrf_config(g["n"])
-    r = O.spdmp(G, G, 0.0, x0, th0, g["T"], c, seed=tuple(g["seed"]))
-    assert r.num == g["num"] and len(r.events) == g["n_events"]
-    assert r.events["i"][:32].tolist() == g["first_i"]
-    assert [float(t).hex() for t in r.events["t"][:8]] == g["first_t_hex"]
-    assert float(r.events["t"][-1]).hex() == g["last_t_hex"]
-    assert int(np.bitwise_xor.reduce(r.events["t"].view(np.uint64))) == g["xor_t"]
+    import golden_cases as GC
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", name + ".json")))
+    assert GC.run_oracle(O, GC.case_inputs(zzb, name)) == g
 
 
 def test_local_bound_moments_and_modes(zzb):
