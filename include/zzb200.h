@@ -16,6 +16,8 @@
  *   zzb_trace_len / _copy         the returned FactTrace's `events` vector                       src/trace.jl:7-13,38
  *   zzb_run_set("max_windows") + zzb_run_execute(T = Inf) + zzb_trace_copy / _clear
  *                                 the pull-style iterator FactSampler / iterate / trace(FS, T)   src/sfactiter.jl:5-79
+ *   zzb_run_discretize / zzb_run_grid   collect(discretize(trace, dt)) (src/trace.jl:94-125) produced on the device while the
+ *                                 windows are committed: x(t0 + k dt) for every coordinate, without handing the trace back
  *   zzb_trace_moments             Statistics.mean(::Trace) (src/trace.jl:182-200) + matching exact second moment
  *   zzb_sspdmp_run                sspdmp(...) src/ss_fact.jl:159-217 with sspdmp_inner! :78-157, queue_time! :54-66,
  *                                 freezing_time :10-16
@@ -132,6 +134,12 @@ int32_t zzb_trace_copy(zzb_run_t r, zzb_event* dst, int64_t first, int64_t count
 int32_t zzb_trace_clear(zzb_run_t r);                                 /* streaming: drop the events already copied out */
 int32_t zzb_trace_moments(zzb_run_t r, double* m1, double* m2);     /* time averages of x and x^2 over [t0, last event] */
 int32_t zzb_trace_sums(zzb_run_t r, double* s1, double* s2);        /* the unscaled device accumulators */
+/* Device-side discretisation.  zzb_run_discretize (before zzb_run_upload) asks for the n_rows grid times t0 + k dt,
+ * k = 0 .. n_rows-1; zzb_run_grid (after zzb_run_execute) copies rows [first_row, first_row + n) of the row-major
+ * n_rows x d array (row k = x(t0 + k dt), evaluated from the anchor of the segment containing the grid time) and reports in
+ * *valid_rows how many leading rows lie at or before the simulated frontier (later rows are NaN). */
+int32_t zzb_run_discretize(zzb_run_t r, double dt, int64_t n_rows);
+int32_t zzb_run_grid(zzb_run_t r, double* xs, int64_t first_row, int64_t n, int64_t* valid_rows);
 int32_t zzb_run_error_info(zzb_run_t r, int64_t* i, double* t, double* l, double* lb);  /* after ZZB_E_BOUND */
 int32_t zzb_run_free(zzb_run_t r);
 

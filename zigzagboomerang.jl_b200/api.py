@@ -283,6 +283,22 @@ class Run:
         self.t0 = float(t0)
         return self
 
+    def discretize(self, dt: float, n_rows: int):
+        """Ask for ``x(t0 + k dt)``, ``k = 0 .. n_rows-1`` to be produced on the device while the run is committed
+        (``collect(discretize(trace, dt))``, src/trace.jl:94-125, without handing the trace back).  Before :meth:`upload`."""
+        check(_capi.lib().zzb_run_discretize(self._h, float(dt), int(n_rows)))
+        self._grid = (float(dt), int(n_rows))
+        return self
+
+    def grid(self):
+        """``(ts, xs)`` of the device-side discretisation, cut to the rows at or before the simulated frontier."""
+        dt, n = self._grid
+        xs = np.empty((n, self.d))
+        valid = C.c_int64()
+        check(_capi.lib().zzb_run_grid(self._h, ptr(xs), 0, n, C.byref(valid)))
+        k = valid.value
+        return self.t0 + dt * np.arange(k), xs[:k]
+
     # ---- sharding over the GPUs of one node (see multigpu.py) -------------------------------------------------
     def shard(self, rank: int, nranks: int):
         check(_capi.lib().zzb_run_shard(self._h, int(rank), int(nranks)))
@@ -392,13 +408,15 @@ def _as_problem(grad, F):
     return Problem(grad, F), True
 
 
-def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None, record_trace=True, tune=None):
+def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None, record_trace=True, tune=None,
+          discretize_dt=None):
     """``spdmp(grad, t0, x0, theta0, T, c, [G,] F, args...; factor=1.8, adapt=false, seed=Seed())``
     = ``Xi, (t, x, theta), (acc, num), c`` (src/sfact.jl:162-214).
 
     `G` may be ``Matched()`` / ``All()``; both give the same event law (the reference only moves different
     coordinate sets eagerly), so they share one kernel.  Trailing `args` (the reference forwards them to the
-    closure) are accepted and ignored.  Raises :class:`BoundError` with the reference's message when a proposal is
+    closure) are accepted and ignored.  ``discretize_dt=dt`` additionally produces ``collect(discretize(Xi, dt))`` on the
+    device (``Xi.grid = (ts, xs)`` up to ``T``), so that ``record_trace=False`` runs still return the thinned path.  Raises :class:`BoundError` with the reference's message when a proposal is
     accepted with ``l >= lb`` and ``adapt`` is false (src/sfact.jl:124).
     """
     rest = list(rest)
@@ -422,12 +440,15 @@ def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None,
     try:
         if tune:
             run.set(**tune)
+        if discretize_dt is not None:
+            run.discretize(discretize_dt, int(np.floor((T - t0) / discretize_dt)) + 1)
         run.upload(t0, x0, theta0, c, seed=seed, adapt=adapt, factor=factor)
         run.execute(T)
         t, x, th, cc = run.final_state()
         acc, num = run.counts()
         ev = run.events() if record_trace else np.empty(0, dtype=EVENT_DTYPE)
         Xi = FactTrace(F, t0, x0, theta0, ev)
+        Xi.grid = run.grid() if discretize_dt is not None else None
         Xi.moments = run.moments() if (num and boom is None) else None   # event-based moments assume linear segments
         Xi.stats = run.stats()
         Xi.device_ms = run.device_ms

@@ -78,6 +78,11 @@ struct ZzParams {
     unsigned int max_windows;   // return to the host after this many committed windows (0 = run to the end)
     int32_t record_trace;
     int32_t pad;
+    // device-side discretize (src/trace.jl:94-125 produced on the device): row k of `grid` holds x(t0 + k grid_dt) for every
+    // coordinate, written at commit for the grid times inside each committed segment; grid_n == 0: off
+    double* grid;
+    double grid_dt;
+    long long grid_n;
     // peer mappings (nranks > 1): who owns coordinate k also owns its stamp, its work-list slots and its counters
     unsigned int* dstamp_peer[ZZ_MAXRANKS];
     int32_t* wl_peer[3][ZZ_MAXRANKS];

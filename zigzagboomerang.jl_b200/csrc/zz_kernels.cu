@@ -333,6 +333,27 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
 #endif
 }
 
+// Device-side discretize: write x_j(t_k) for the grid times t_k = t0 + k dt in (tf, fs] of the segment that starts at the
+// anchor (tf, xf, th) and ends at fs (the position is evaluated from the anchor, x = xf + th (t_k - tf), resp. the rotation
+// of the Boomerang flow).  Row 0 (t_k = t0) is written by zz_setup_kernel.
+__device__ __forceinline__ void zz_grid_fill(const ZzParams& P, int32_t j, double tf, double xf, double th, double fs,
+                                             bool boom, double muj)
+{
+    const double dt = P.grid_dt;
+    long long k = (long long)floor((tf - P.t0) / dt);
+    if (k < 0) k = 0;
+    while (P.t0 + (double)k * dt <= tf) ++k;
+    while (k > 0 && P.t0 + (double)(k - 1) * dt > tf) --k;   // first k with t_k > tf
+    for (; k < P.grid_n; ++k) {
+        const double tk = P.t0 + (double)k * dt;
+        if (tk > fs) break;
+        double x;
+        if (boom) { double tho; zz_boom_at(tf, xf, th, muj, tk, &x, &tho); }
+        else x = xf + th * (tk - tf);
+        P.grid[(size_t)k * (size_t)P.v.d + (size_t)j] = x;
+    }
+}
+
 // Fold the converged end-of-window state of coordinate j into the frontier.
 __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uint32_t w0, uint32_t cur,
                                                unsigned int& nprop_acc, unsigned int& nflip_acc)
@@ -389,6 +410,7 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uin
             } else {
                 xs = xf + th * (fs - tf); thn = -th; nrefl++;
             }
+            if (P.grid_n) zz_grid_fill(P, j, tf, xf, th, fs, boom, muj);
             if (!boom) {   // moment sums of the piecewise LINEAR path only
                 a1 += (xf + xs) * (fs - tf);                      // trace.jl:194 (scaled by 1/(2T) on the host)
                 a2 += (fs - tf) * (xf * xf + xf * xs + xs * xs);
@@ -422,6 +444,17 @@ zz_setup_kernel(const ZzParams P, const double* __restrict__ x0, const double* _
         ZzPriv p; p.a = 0.0; p.b = 0.0; p.told = P.t0; p.c = c0[j];
         P.v.priv[j] = p;
         P.dstamp[j] = 0; P.acc[j] = 0; P.s1[j] = 0.0; P.s2[j] = 0.0;
+        if (P.grid_n) P.grid[j] = x0[j];   // row 0: x(t0)
+    }
+}
+
+// Rows of the discretisation grid between every coordinate's last committed event and the frontier `tend` (all events
+// before the frontier are final, so the current segment is valid up to it).  Idempotent; run before the grid is read.
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_grid_tail_kernel(const ZzParams P, double tend)
+{
+    for (int32_t j = P.v.lo + blockIdx.x * blockDim.x + threadIdx.x; j < P.v.hi; j += gridDim.x * blockDim.x) {
+        const ZzKin k = P.v.kin[j];
+        zz_grid_fill(P, j, k.tf, k.xf, k.theta, tend, P.v.boom != 0, P.v.boom ? P.v.bmu[j] : 0.0);
     }
 }
 

@@ -88,7 +88,7 @@ struct Global {
     CUdevice dev = 0; int dev_id = 0;
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
-    CUfunction f_setup = nullptr, f_init = nullptr, f_run[12] = {}, f_export = nullptr;
+    CUfunction f_setup = nullptr, f_init = nullptr, f_run[12] = {}, f_export = nullptr, f_grid_tail = nullptr;
     CUstream stream = nullptr;
     CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
     int sm_count = 0; int blocks_per_sm[12] = {}; int run_block[2] = { 256, 256 };   // lattice / general-sparse kernels
@@ -174,6 +174,7 @@ struct zzb_run_s {
     }
     DevBuf dfth, kappa; bool have_kappa = false;
     DevBuf bmu, bsig; bool have_boom = false; double lambdaref = 0, rho = 0;
+    DevBuf gridbuf; double grid_dt = 0; long long grid_n = 0;   // device-side discretize
     int rank = 0, nranks = 1, shard = 0, lo = 0, hi = 0;
     CUdeviceptr peer[ZZ_MAXRANKS][8] = {};   // imported mappings: kin, flips, dstamp, wl0, wl1, wl2, touched, ctl
     bool peer_open[ZZ_MAXRANKS] = {};
@@ -235,6 +236,7 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
                                          "zz_run_kernel_grid_sticky", "zz_run_kernel_csr_sticky", "zz_run_kernel_grid_boom", "zz_run_kernel_csr_boom" };
     for (int k = 0; k < 12; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
+    CU(cuModuleGetFunction(&G.f_grid_tail, G.mod, "zz_grid_tail_kernel"));
     CU(cuStreamCreate(&G.stream, CU_STREAM_NON_BLOCKING));
     CU(cuEventCreate(&G.ev0, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.ev1, CU_EVENT_DEFAULT));
@@ -402,6 +404,7 @@ static void fill_params(zzb_run_s* r)
     P.trace = r->trace.as<ZzEvent>(); P.trace_cap = r->trace_cap;
     P.ctl = r->ctl.as<ZzDevCtl>();
     P.record_trace = (r->flags & ZZB_FLAG_NO_TRACE) ? 0 : 1;
+    P.grid = r->grid_n ? r->gridbuf.as<double>() : nullptr; P.grid_dt = r->grid_dt; P.grid_n = r->grid_n;
     P.v.local_bound = (r->flags & ZZB_FLAG_LOCAL_BOUND) ? 1 : 0;
     P.v.sticky = (r->flags & ZZB_FLAG_STICKY) ? 1 : 0;
     P.v.boom = (r->flags & ZZB_FLAG_BOOMERANG) ? 1 : 0;
@@ -548,6 +551,7 @@ int32_t zzb_run_reset(zzb_run_t r)
     hc.f0_key = ~0ULL; for (int k = 0; k < 3; ++k) hc.smin_key[k] = ~0ULL;
     CU(cuMemcpyHtoDAsync(r->ctl.p, &hc, sizeof hc, G.stream));
     const unsigned grid = (unsigned)std::min<size_t>(((size_t)r->d + ZZ_BLOCK - 1) / ZZ_BLOCK, (size_t)G.sm_count * 8);
+    if (r->grid_n) CU(cuMemsetD8Async(r->gridbuf.p, 0xff, (size_t)r->grid_n * (size_t)r->d * 8, G.stream));   // all-ones = NaN
     CUdeviceptr px = r->in_x.p, pth = r->in_th.p, pc = r->in_c.p;
     void* a1[] = { &P, &px, &pth, &pc };
     CU(cuLaunchKernel(G.f_setup, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a1, nullptr));
@@ -858,6 +862,47 @@ int32_t zzb_trace_moments(zzb_run_t r, double* m1, double* m2)
     for (int32_t j = 0; j < r->d; ++j) {
         if (m1) m1[j] = r->hs1[j] * (1 / (2 * Tl));   // scale = 1/(2T), trace.jl:190
         if (m2) m2[j] = r->hs2[j] / (3 * Tl);
+    }
+    return ZZB_OK;
+}
+
+// Ask for the device-side discretisation x(t0 + k dt), k = 0 .. n_rows-1 (src/trace.jl:94-125); before zzb_run_upload.
+int32_t zzb_run_discretize(zzb_run_t r, double dt, int64_t n_rows)
+{
+    if (!r) return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (!(dt > 0.0) || n_rows < 1) return fail(ZZB_E_ARG, "discretize needs dt > 0 and n_rows >= 1");
+    if (r->flags & ZZB_FLAG_STICKY) return fail(ZZB_E_ARG, "device-side discretize is not available for the sticky sampler");
+    CtxGuard cg;
+    int32_t st = r->gridbuf.alloc((size_t)n_rows * (size_t)r->d * 8);
+    if (st) return st == ZZB_E_CUDA ? ZZB_E_NOMEM : st;
+    r->grid_dt = dt; r->grid_n = n_rows;
+    r->uploaded = false;   // the parameters change: zzb_run_upload / zzb_run_reset must follow
+    return ZZB_OK;
+}
+
+int32_t zzb_run_grid(zzb_run_t r, double* xs, int64_t first_row, int64_t n, int64_t* valid_rows)
+{
+    if (!r) return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (!r->grid_n) return fail(ZZB_E_ARG, "zzb_run_discretize was not called");
+    if (!r->uploaded) return fail(ZZB_E_ARG, "run has no state yet");
+    if (first_row < 0 || n < 0 || first_row + n > r->grid_n) return fail(ZZB_E_ARG, "row range out of bounds");
+    CtxGuard cg;
+    CU(cuMemcpyDtoH(&r->hc, r->ctl.p, sizeof(ZzDevCtl)));
+    const double tend = r->executed ? r->hc.ctl.F : r->t0;   // frontier: every event before it is final
+    const unsigned grid = (unsigned)std::min<size_t>(((size_t)r->d + ZZ_BLOCK - 1) / ZZ_BLOCK, (size_t)G.sm_count * 8);
+    double te = tend;
+    void* a[] = { &r->P, &te };
+    CU(cuLaunchKernel(G.f_grid_tail, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a, nullptr));
+    r->launches++;
+    if (xs && n) CU(cuMemcpyDtoHAsync(xs, r->gridbuf.p + (size_t)first_row * (size_t)r->d * 8, (size_t)n * (size_t)r->d * 8, G.stream));
+    CU(cuStreamSynchronize(G.stream));
+    if (valid_rows) {
+        long long k = (long long)floor((tend - r->t0) / r->grid_dt) + 2;
+        if (k > r->grid_n) k = r->grid_n;
+        while (k > 0 && r->t0 + (double)(k - 1) * r->grid_dt > tend) --k;
+        *valid_rows = k;
     }
     return ZZB_OK;
 }
