@@ -229,3 +229,20 @@ def test_fact_sampler_iterator(gpu):
     tr = gpu.trace(FS, 3.0)      # drops the first event (upstream quirk) and stops at the first event with t > T
     n = int(np.searchsorted(ref.events["t"], 3.0, side="right"))
     assert np.array_equal(tr.events["t"], ref.events["t"][1:n]) and np.array_equal(tr.events["i"], ref.events["i"][1:n])
+
+
+def test_config1_two_dimensional_pdmp_and_one_dimensional(gpu):
+    """BASELINE configs[0] (2-d Gaussian through pdmp) and the smallest possible problem (d = 1) on the device path."""
+    G = gpu.CSC.from_dense(np.array([[2.0, -1.0], [-1.0, 2.0]]))
+    x0, th0 = np.array([0.3, -0.2]), np.array([1.0, -1.0])
+    c = 0.7 * G.colnorms()
+    ref = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, 300.0, c, seed=(5, 6))
+    Xi, (t, x, th), (acc, num), cc = gpu.pdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 300.0, c, gpu.ZigZag(G.scaled(0.9), np.zeros(2)), seed=(5, 6))
+    got = R()
+    got.events, got.t, got.x, got.theta, got.c, got.acc, got.num = Xi.events, t, x, th, cc, acc, num
+    O.assert_same_run(ref, got)
+    G1 = gpu.CSC.from_dense(np.array([[1.5]]))
+    ref = O.spdmp(G1, G1, 0.0, np.array([0.4]), np.array([1.0]), 200.0, np.array([0.5]), seed=(7, 8))
+    got, _ = run_gpu(gpu, G1, G1, 0.0, np.array([0.4]), np.array([1.0]), 200.0, np.array([0.5]), seed=(7, 8))
+    O.assert_same_run(ref, got)
+    assert len(ref.events) > 50

@@ -251,3 +251,15 @@ def test_trace_postprocessing_mirrors(zzb):
     assert np.allclose(last, r.s1 / (2 * tl), rtol=1e-12)       # running mean at the coordinate's last event
     p = zzb.inclusion_prob(tr)
     assert np.all(p > 0) and np.all(p <= 1.0 + 1e-12) and p.mean() < 0.999   # sticky: some time is spent at 0
+
+
+def test_config1_two_dimensional_gaussian_pdmp(zzb):
+    """BASELINE configs[0]: 2-d Gaussian ZigZag through pdmp (All() neighbourhood), the plumbing case in the style of
+    test/maintest.jl:4-34: first and second moments of the discretised path."""
+    G = zzb.CSC.from_dense(np.array([[2.0, -1.0], [-1.0, 2.0]]))
+    T = 2000.0
+    x0, th0 = np.array([0.3, -0.2]), np.array([1.0, -1.0])
+    c = 0.7 * G.colnorms()
+    for mode in (O.RNG_SEQ | O.ARITH_INPLACE | O.GRAPH_ALL, O.PARITY_MODE):
+        r = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, T, c, seed=(5, 6), mode=mode)
+        _cov_check(r, zzb, G, x0, th0, T, 2.0, 2.5)

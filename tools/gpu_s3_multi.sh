@@ -1,0 +1,2 @@
+python -m pytest tests/test_gpu_multi.py -m gpu -x -q 2>&1 | tail -5
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 2>&1 | tail -2 | cut -c1-1500
