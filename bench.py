@@ -434,7 +434,7 @@ def main():
     ap.add_argument("--n", type=int, default=1000, help="grid side (d = n^2)")
     ap.add_argument("--T", type=float, default=2.0, help="simulated time per step")
     ap.add_argument("--cpu-T", type=float, default=0.0, help="simulated time of the CPU sample (default: T)")
-    ap.add_argument("--frac", type=float, default=0.15, help="window length controller: proposals per window / d")
+    ap.add_argument("--frac", type=float, default=0.25, help="window length controller: proposals per window / d")
     ap.add_argument("--tight", action="store_true", help="c = sqrt(eps) (scripts/example.jl:39) instead of column norms")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tight", action="store_true", help="skip the extra c = sqrt(eps) measurement")

@@ -1,0 +1,2 @@
+python tools/quick_bench.py 1000 2.0 loose 0.2,0.25,0.3 0.045,0.06,0.08 2>&1 | grep "trace=False" | sed -e "s/upload.*proposals -> //" -e "s/'node_evals.*'ns_scan'/'ns_scan'/" -e "s/'dbg0.*//"
+python tools/quick_bench.py 1000 2.0 tight 0.2,0.3 0.2,0.4 2>&1 | grep "trace=False" | sed -e "s/upload.*proposals -> //" -e "s/'node_evals.*'ns_scan'/'ns_scan'/" -e "s/'dbg0.*//"

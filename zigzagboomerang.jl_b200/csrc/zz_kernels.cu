@@ -490,11 +490,11 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
     if (blockIdx.x == 0 && threadIdx.x == 0) zz_dbg_ptr = C->dbg;
     __syncthreads();
 #endif
-    __shared__ int32_t sq[(KIND == ZZ_KIND_GRID ? ZZ_RUN_BLOCK_GRID : ZZ_RUN_BLOCK_CSR) / 32][32 * ZZ_SCAN_U];
+    __shared__ unsigned int sq_cnt;   // entries of this CTA's scan queue (pass 1)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int nthreads = gridDim.x * blockDim.x;
-    const unsigned int gwarp = gtid >> 5, nwarps = nthreads >> 5;
+    const unsigned int gwarp = gtid >> 5, nwarps = nthreads >> 5, nwc = blockDim.x >> 5;
     const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
     const int32_t lo = MULTI ? P.v.lo : 0, hi = MULTI ? P.v.hi : P.v.d;   // owned coordinates
     unsigned long long epoch = 0;
@@ -545,26 +545,44 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             const int wz = (int)(wat % 3u);  // slot of the NEXT attempt
             C->touched_cnt[wz] = 0; C->smin_key[wz] = ~0ULL; C->nprop_win[wz] = 0;
         }
-        for (int32_t base = lo + (int32_t)gwarp * (32 * ZZ_SCAN_U); base < hi; base += nwarps * (32 * ZZ_SCAN_U)) {
-            int qn = 0;
+        {
+            // Every CTA scans its contiguous share of the owned coordinates, compacts the active ones into a CTA-wide queue
+            // (the work list consumed last is free during this pass; the CTA uses the slice that mirrors its share) and then
+            // evaluates the queue with all its threads: ceil(active / threads) evaluation rounds per CTA.
+            const int32_t per = (hi - lo + (int32_t)gridDim.x - 1) / (int32_t)gridDim.x;
+            const int32_t c_lo = lo + (int32_t)blockIdx.x * per;
+            const int32_t c_hi = (c_lo + per < hi) ? c_lo + per : hi;
+            int32_t* q = P.wl[li] + c_lo;
+            if (threadIdx.x == 0) sq_cnt = 0u;
+            __syncthreads();
+            for (int32_t base = c_lo + warp * (32 * ZZ_SCAN_U); base < c_hi; base += (int32_t)nwc * (32 * ZZ_SCAN_U)) {
+                bool act[ZZ_SCAN_U];
 #pragma unroll
-            for (int u = 0; u < ZZ_SCAN_U; ++u) {
-                const int32_t j = base + u * 32 + lane;
-                bool act = false;
-                if (j < hi) { const double tj = __ldcg(P.v.tau + j); act = (tj < H) || (incl && tj == H); }
-                const unsigned int m = __ballot_sync(0xffffffffu, act);
-                if (act) sq[warp][qn + __popc(m & ((1u << lane) - 1u))] = j;
-                qn += __popc(m);
+                for (int u = 0; u < ZZ_SCAN_U; ++u) {
+                    const int32_t j = base + u * 32 + lane;
+                    act[u] = false;
+                    if (j < c_hi) { const double tj = __ldcg(P.v.tau + j); act[u] = (tj < H) || (incl && tj == H); }
+                }
+#pragma unroll
+                for (int u = 0; u < ZZ_SCAN_U; ++u) {
+                    const unsigned int m = __ballot_sync(0xffffffffu, act[u]);
+                    if (m) {
+                        unsigned int wb = 0;
+                        if (lane == 0) wb = atomicAdd(&sq_cnt, (unsigned int)__popc(m));
+                        wb = __shfl_sync(0xffffffffu, wb, 0);
+                        if (act[u]) q[wb + __popc(m & ((1u << lane) - 1u))] = base + u * 32 + lane;
+                    }
+                }
             }
-            __syncwarp();
-            for (int q = lane; q < qn; q += 32) {
-                const int32_t j = sq[warp][q];
+            __syncthreads();
+            const unsigned int qn = sq_cnt;
+            for (unsigned int e = threadIdx.x; e < qn; e += blockDim.x) {
+                const int32_t j = __ldcg(q + e);
                 const uint32_t old = MULTI ? atomicMax_system(P.dstamp + j, cur) : atomicMax(P.dstamp + j, cur);
                 if (old < w0) zz_append<MULTI>(P.touched[0], &C->touched_cnt[ws], j);
                 zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, true, nxt, ws);
                 st_evals++;
             }
-            __syncwarp();
         }
         ZZ_TOC(0);
         ZzXres xr = zz_boundary<MULTI>(P, epoch, xep, prof, MULTI ? &C->issued[nxt] : nullptr, nullptr,
@@ -591,13 +609,14 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                         cur++;
                         if (threadIdx.x == 0) C->wl_cnt[(li + 2) % 3u] = 0;
                         const int32_t* wlt = P.wl[li];
-                        for (unsigned int e = threadIdx.x; e < n; e += blockDim.x) {
+                        // entry e goes to warp e % (#warps), lane e / (#warps): few lanes per warp, so that coordinates with
+                        // different timelines do not serialise each other's branches
+                        for (unsigned int e = (unsigned int)lane * nwc + (unsigned int)warp; e < n; e += blockDim.x) {
                             const int32_t j = __ldcg(wlt + e);
                             zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, false, nxt, ws);
                             st_evals++;
                         }
-                        __threadfence();
-                        __syncthreads();
+                        __syncthreads();   // block-wide visibility is enough inside the tail; the grid barrier below fences
                         st_iters++;
                         if (prof) prof[7] += 1;
                         n = __ldcg(&C->wl_cnt[nxt]);
@@ -617,7 +636,8 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             ZZ_TIC();
             if (leader) { C->wl_cnt[(li + 2) % 3u] = 0; C->issued[(li + 2) % 3u] = 0; }
             const int32_t* wl = P.wl[li];
-            for (unsigned int e = gtid; e < cw; e += nthreads) {
+            // same spreading over all warps of the grid: a list of n entries occupies ceil(n / #warps) lanes of every warp
+            for (unsigned int e = (unsigned int)lane * nwarps + gwarp; e < cw; e += nthreads) {
                 const int32_t j = __ldcg(wl + e);
                 zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, false, nxt, ws);
                 st_evals++;

@@ -159,7 +159,7 @@ struct zzb_run_s {
     ZzParams P;
     double t0 = 0, T = 0;
     uint64_t seed[2] = { 0, 0 }; int32_t adapt = 0; double factor = 1.8;
-    double delta0 = 0, target_frac = 0.15, target_flip_frac = 0.045; unsigned int tag_limit = ZZ_TAG_LIMIT; unsigned int max_windows = 0;
+    double delta0 = 0, target_frac = 0.25, target_flip_frac = 0.045; unsigned int tag_limit = ZZ_TAG_LIMIT; unsigned int max_windows = 0;
     bool uploaded = false, executed = false, have_inputs = false;
     // results
     std::vector<zzb_event> events;     // sorted, markers removed
