@@ -161,7 +161,7 @@ __device__ __forceinline__ void zz_append4(int32_t* wl, unsigned int* wl_cnt, in
 {
     unsigned int na = 0, nt = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { na += (old[q] < tagn) ? 1u : 0u; nt += (old[q] < w0) ? 1u : 0u; }
+    for (int q = 0; q < 4; ++q) { na += (old[q] < tagn) ? 1u : 0u; nt += (tl && old[q] < w0) ? 1u : 0u; }
     cg::coalesced_group cgp = cg::coalesced_threads();
     const unsigned int pa = cg::exclusive_scan(cgp, na, cg::plus<unsigned int>());
     const unsigned int pt = cg::exclusive_scan(cgp, nt, cg::plus<unsigned int>());
@@ -176,7 +176,7 @@ __device__ __forceinline__ void zz_append4(int32_t* wl, unsigned int* wl_cnt, in
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         if (old[q] < tagn) wl[ba++] = kk[q];
-        if (old[q] < w0) tl[bt++] = kk[q];
+        if (tl && old[q] < w0) tl[bt++] = kk[q];
     }
 }
 
@@ -208,11 +208,12 @@ __device__ __forceinline__ ZzSpecR zz_load_spec(const ZzSpec* p)
 // Stamp up to four readers of a changed coordinate and queue those that were not queued yet.  MULTI: a reader owned
 // by another GPU is stamped and queued in its owner's memory with system-scope atomics over NVLink.
 template <bool MULTI>
-__device__ __forceinline__ void zz_mark4(const ZzParams& P, const int32_t (&kk)[4], uint32_t tagn, uint32_t w0, int nxt, int ws)
+__device__ __forceinline__ void zz_mark4(const ZzParams& P, const int32_t (&kk)[4], uint32_t tagn, uint32_t w0, int nxt, int ws, bool first)
 {
     ZzDevCtl* C = P.ctl;
     uint32_t old[4];
     if (!MULTI) {
+        (void)first;
 #pragma unroll
         for (int q = 0; q < 4; ++q) old[q] = (kk[q] >= 0) ? atomicMax(P.dstamp + kk[q], tagn) : 0xffffffffu;
         zz_append4<false>(P.wl[nxt], &C->wl_cnt[nxt], P.touched[0], &C->touched_cnt[ws], kk, old, tagn, w0);
@@ -248,7 +249,7 @@ __device__ __forceinline__ void zz_mark4(const ZzParams& P, const int32_t (&kk)[
 
 template <int KIND, bool MULTI, int MODE>
 __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const ZzNodeOut& o, uint32_t w0,
-                                           uint32_t cur, int nxt, int ws)
+                                           uint32_t cur, int nxt, int ws, bool first)
 {
     ZzDevCtl* C = P.ctl;
     int slot;
@@ -291,14 +292,14 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
                 const bool ok = (q == 0) ? (col > 0) : (q == 1) ? (row > 0) : (q == 2) ? (row < M - 1) : (col < N - 1);
                 kk[q] = ok ? j + ((q == 0) ? -M : (q == 1) ? -1 : (q == 2) ? 1 : M) : -1;
             }
-            zz_mark4<MULTI>(P, kk, tagn, w0, nxt, ws);
+            zz_mark4<MULTI>(P, kk, tagn, w0, nxt, ws, first);
         } else {
             const int32_t q1 = P.dptr[j + 1];
             for (int32_t q0 = P.dptr[j]; q0 < q1; q0 += 4) {
                 int32_t kk[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) kk[q] = (q0 + q < q1) ? P.didx[q0 + q] : -1;
-                zz_mark4<MULTI>(P, kk, tagn, w0, nxt, ws);
+                zz_mark4<MULTI>(P, kk, tagn, w0, nxt, ws, first);
             }
         }
     }
@@ -321,7 +322,7 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
     const long long c0 = clock64();
     zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, cur, first, o);
     const long long c1 = clock64();
-    zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws);
+    zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws, first);
     const long long c2 = clock64();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.ctl->dbg[0] += (unsigned long long)(c2 - c1);   // cycles in publication
@@ -329,7 +330,7 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
     }
 #else
     zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, cur, first, o);
-    zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws);
+    zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws, first);
 #endif
 }
 
@@ -356,9 +357,12 @@ __device__ __forceinline__ void zz_grid_fill(const ZzParams& P, int32_t j, doubl
 
 // Fold the converged end-of-window state of coordinate j into the frontier.
 __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uint32_t w0, uint32_t cur,
-                                               unsigned int& nprop_acc, unsigned int& nflip_acc)
+                                               unsigned int& nprop_acc, unsigned int& nflip_acc, bool claim)
 {
     ZzDevCtl* C = P.ctl;
+    // Single GPU: a coordinate can be listed twice (the bulk append of the pass-1 queue and a pass-1 mark of a neighbour
+    // that arrived before the coordinate's own stamp); the first visitor claims it with the commit tag.
+    if (claim && atomicMax(P.dstamp + j, cur) >= cur) return;
     const ZzSpecR s = zz_load_spec(P.spec + j);
     if (s.flags & ZZ_F_VIOL) {
         if (atomicExch(&C->viol, 1u) == 0u) {
@@ -482,6 +486,100 @@ zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ 
     }
 }
 
+// Passes whose coordinates are found by scanning: every CTA scans its contiguous share of the owned coordinates and compacts
+// the active ones into a CTA-wide queue (the work list consumed last is free during these passes; the CTA uses the slice
+// that mirrors its share); the caller then works through the queue with all its threads: ceil(active / threads) rounds.
+//   CRIT 0 (pass 1): proposal time inside the window;  CRIT 1 (pass 2, single GPU): stamped by a pass-1 mark (dstamp == cur).
+// TOUCH (single GPU): the coordinates seen for the first time in this window are appended to the touched list in bulk --
+// the whole queue of pass 1 with one atomic per CTA, in pass 2 those without a proposal in the window with one atomic per
+// scanned chunk -- so that no evaluation waits for an atomic.
+template <int CRIT, bool TOUCH>
+__device__ __forceinline__ unsigned int zz_build_queue(const ZzParams& P, unsigned int* sq_cnt, int32_t lo, int32_t hi, uint32_t li,
+                                                       double H, int incl, uint32_t cur, int ws, const int32_t*& qout)
+{
+    ZzDevCtl* C = P.ctl;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int32_t nwc = (int32_t)(blockDim.x >> 5);
+    const int32_t per = (hi - lo + (int32_t)gridDim.x - 1) / (int32_t)gridDim.x;
+    const int32_t c_lo = lo + (int32_t)blockIdx.x * per;
+    const int32_t c_hi = (c_lo + per < hi) ? c_lo + per : hi;
+    int32_t* q = P.wl[li] + c_lo;
+    __syncthreads();   // the previous user of the queue counter is done
+    if (threadIdx.x == 0) { sq_cnt[0] = 0u; sq_cnt[1] = 0u; }
+    __syncthreads();
+    for (int32_t base = c_lo + warp * (32 * ZZ_SCAN_U); base < c_hi; base += nwc * (32 * ZZ_SCAN_U)) {
+        bool act[ZZ_SCAN_U], fresh[ZZ_SCAN_U];
+        unsigned int nfresh = 0;
+#pragma unroll
+        for (int u = 0; u < ZZ_SCAN_U; ++u) {
+            const int32_t j = base + u * 32 + lane;
+            act[u] = false; fresh[u] = false;
+            if (j < c_hi) {
+                if (CRIT == 0) { const double tj = __ldcg(P.v.tau + j); act[u] = (tj < H) || (incl && tj == H); }
+                else {
+                    act[u] = (__ldcg(P.dstamp + j) == cur);
+                    if (TOUCH) { const double tj = __ldcg(P.v.tau + j); fresh[u] = act[u] && !((tj < H) || (incl && tj == H)); }
+                }
+            }
+        }
+        unsigned int mf[ZZ_SCAN_U];
+#pragma unroll
+        for (int u = 0; u < ZZ_SCAN_U; ++u) {
+            const unsigned int m = __ballot_sync(0xffffffffu, act[u]);
+            if (CRIT == 1 && TOUCH) { mf[u] = __ballot_sync(0xffffffffu, fresh[u]); nfresh += __popc(mf[u]); }
+            if (m) {
+                unsigned int wb = 0;
+                if (lane == 0) wb = atomicAdd(sq_cnt, (unsigned int)__popc(m));
+                wb = __shfl_sync(0xffffffffu, wb, 0);
+                if (act[u]) q[wb + __popc(m & ((1u << lane) - 1u))] = base + u * 32 + lane;
+            }
+        }
+        if (CRIT == 1 && TOUCH && nfresh) {   // not in the pass-1 queue: first touch
+            unsigned int tb = 0;
+            if (lane == 0) tb = atomicAdd(&C->touched_cnt[ws], nfresh);
+            tb = __shfl_sync(0xffffffffu, tb, 0);
+#pragma unroll
+            for (int u = 0; u < ZZ_SCAN_U; ++u) {
+                if (fresh[u]) P.touched[0][tb + __popc(mf[u] & ((1u << lane) - 1u))] = base + u * 32 + lane;
+                tb += __popc(mf[u]);
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned int qn = sq_cnt[0];
+    if (CRIT == 0 && TOUCH && qn) {   // every coordinate of the pass-1 queue is new to this window
+        if (threadIdx.x == 0) sq_cnt[1] = atomicAdd(&C->touched_cnt[ws], qn);
+        __syncthreads();
+        const unsigned int tb = sq_cnt[1];
+        for (unsigned int e = threadIdx.x; e < qn; e += blockDim.x) P.touched[0][tb + e] = q[e];
+    }
+    qout = q;
+    return qn;
+}
+
+template <int KIND, bool MULTI, int MODE, bool BYSTAMP>
+__device__ __forceinline__ void zz_queue_pass(const ZzParams& P, unsigned int* sq_cnt, int32_t lo, int32_t hi, uint32_t li,
+                                              double H, int incl, uint32_t w0, uint32_t cur, int nxt, int ws,
+                                              unsigned long long& st_evals)
+{
+    ZzDevCtl* C = P.ctl;
+    const int32_t* q;
+    const unsigned int qn = zz_build_queue<BYSTAMP ? 1 : 0, !MULTI>(P, sq_cnt, lo, hi, li, H, incl, cur, ws, q);
+    for (unsigned int e = threadIdx.x; e < qn; e += blockDim.x) {
+        const int32_t j = __ldcg(q + e);
+        if (!BYSTAMP) {
+            if (MULTI) {
+                const uint32_t old = atomicMax_system(P.dstamp + j, cur);
+                if (old < w0) zz_append<MULTI>(P.touched[0], &C->touched_cnt[ws], j);
+            } else {
+                atomicMax(P.dstamp + j, cur);   // result unused (RED); the queue went to the touched list in bulk
+            }
+        }
+        zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, !BYSTAMP, nxt, ws);
+        st_evals++;
+    }
+}
+
 template <int KIND, bool MULTI, int MODE>
 __device__ __forceinline__ void zz_run_body(const ZzParams& P)
 {
@@ -490,7 +588,8 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
     if (blockIdx.x == 0 && threadIdx.x == 0) zz_dbg_ptr = C->dbg;
     __syncthreads();
 #endif
-    __shared__ unsigned int sq_cnt;   // entries of this CTA's scan queue (pass 1)
+    __shared__ unsigned int sq_cnt2[2];   // entries of this CTA's scan queue / base of its bulk append
+    unsigned int* const sq_cnt_p = sq_cnt2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned int nthreads = gridDim.x * blockDim.x;
@@ -545,45 +644,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             const int wz = (int)(wat % 3u);  // slot of the NEXT attempt
             C->touched_cnt[wz] = 0; C->smin_key[wz] = ~0ULL; C->nprop_win[wz] = 0;
         }
-        {
-            // Every CTA scans its contiguous share of the owned coordinates, compacts the active ones into a CTA-wide queue
-            // (the work list consumed last is free during this pass; the CTA uses the slice that mirrors its share) and then
-            // evaluates the queue with all its threads: ceil(active / threads) evaluation rounds per CTA.
-            const int32_t per = (hi - lo + (int32_t)gridDim.x - 1) / (int32_t)gridDim.x;
-            const int32_t c_lo = lo + (int32_t)blockIdx.x * per;
-            const int32_t c_hi = (c_lo + per < hi) ? c_lo + per : hi;
-            int32_t* q = P.wl[li] + c_lo;
-            if (threadIdx.x == 0) sq_cnt = 0u;
-            __syncthreads();
-            for (int32_t base = c_lo + warp * (32 * ZZ_SCAN_U); base < c_hi; base += (int32_t)nwc * (32 * ZZ_SCAN_U)) {
-                bool act[ZZ_SCAN_U];
-#pragma unroll
-                for (int u = 0; u < ZZ_SCAN_U; ++u) {
-                    const int32_t j = base + u * 32 + lane;
-                    act[u] = false;
-                    if (j < c_hi) { const double tj = __ldcg(P.v.tau + j); act[u] = (tj < H) || (incl && tj == H); }
-                }
-#pragma unroll
-                for (int u = 0; u < ZZ_SCAN_U; ++u) {
-                    const unsigned int m = __ballot_sync(0xffffffffu, act[u]);
-                    if (m) {
-                        unsigned int wb = 0;
-                        if (lane == 0) wb = atomicAdd(&sq_cnt, (unsigned int)__popc(m));
-                        wb = __shfl_sync(0xffffffffu, wb, 0);
-                        if (act[u]) q[wb + __popc(m & ((1u << lane) - 1u))] = base + u * 32 + lane;
-                    }
-                }
-            }
-            __syncthreads();
-            const unsigned int qn = sq_cnt;
-            for (unsigned int e = threadIdx.x; e < qn; e += blockDim.x) {
-                const int32_t j = __ldcg(q + e);
-                const uint32_t old = MULTI ? atomicMax_system(P.dstamp + j, cur) : atomicMax(P.dstamp + j, cur);
-                if (old < w0) zz_append<MULTI>(P.touched[0], &C->touched_cnt[ws], j);
-                zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, true, nxt, ws);
-                st_evals++;
-            }
-        }
+        zz_queue_pass<KIND, MULTI, MODE, false>(P, sq_cnt_p, lo, hi, li, H, incl, w0, cur, nxt, ws, st_evals);
         ZZ_TOC(0);
         ZzXres xr = zz_boundary<MULTI>(P, epoch, xep, prof, MULTI ? &C->issued[nxt] : nullptr, nullptr,
                                        MULTI ? &C->wl_cnt[nxt] : nullptr, ZZ_OVF_BIT, ZZ_X_OVERFLOW);
@@ -692,7 +753,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             unsigned int np = 0, nf = 0;
             for (unsigned int e = gtid; e < nt; e += nthreads) {
                 const int32_t j = __ldcg(P.touched[0] + e);
-                zz_commit_node(P, j, w0, cur, np, nf);
+                zz_commit_node(P, j, w0, cur, np, nf, !MULTI);
             }
             cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
             np = cg::reduce(w, np, cg::plus<unsigned int>());

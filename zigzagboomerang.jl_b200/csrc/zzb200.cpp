@@ -359,7 +359,8 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     AL(kin, d * sizeof(ZzKin)); AL(flips, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(priv, d * sizeof(ZzPriv));
     AL(tau, d * 8); AL(kctr, d * 4); AL(spec, d * sizeof(ZzSpec)); AL(viol, d * 24); AL(dstamp, d * 4);
     AL(acc, d * 4); AL(s1, d * 8); AL(s2, d * 8); AL(wl[0], d * 4); AL(wl[1], d * 4); AL(wl[2], d * 4);
-    AL(touched, d * 4); AL(ctl, sizeof(ZzDevCtl));
+    AL(touched, d * 8);   // up to two entries per coordinate (see zz_commit_node)
+    AL(ctl, sizeof(ZzDevCtl));
     AL(in_x, d * 8); AL(in_th, d * 8); AL(in_c, d * 8);
     if (flags & ZZB_FLAG_STICKY) { AL(dfth, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(kappa, d * 8); }
     if (flags & ZZB_FLAG_BOOMERANG) {
