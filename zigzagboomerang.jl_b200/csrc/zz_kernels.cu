@@ -153,6 +153,14 @@ __device__ __forceinline__ void zz_append(int32_t* list, unsigned int* cnt, int3
     list[(base & ~ZZ_OVF_BIT) + cgp.thread_rank()] = val;
 }
 
+// Work list of the single-CTA tail passes, in shared memory (CTA 0 only): appends are shared-memory atomics and the next
+// pass reads its entries without a trip to L2.
+struct ZzTailList {
+    int32_t buf[2][4 * ZZ_TAIL];   // a pass of n <= ZZ_TAIL coordinates marks at most 4 n readers (lattice) / is cut off otherwise
+    unsigned int n[2];
+    unsigned int ovf;              // a coordinate overflowed, or the list did
+};
+
 // Up to four candidates per lane: those whose stamp was older than `tagn` go to the next work list, those older
 // than `w0` (first touch in this window) also to the touched list.  One atomicAdd per list for the active lanes.
 template <bool MULTI>
@@ -161,7 +169,7 @@ __device__ __forceinline__ void zz_append4(int32_t* wl, unsigned int* wl_cnt, in
 {
     unsigned int na = 0, nt = 0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) { na += (old[q] < tagn) ? 1u : 0u; nt += (tl && old[q] < w0) ? 1u : 0u; }
+    for (int q = 0; q < 4; ++q) { na += (wl && old[q] < tagn) ? 1u : 0u; nt += (tl && old[q] < w0) ? 1u : 0u; }
     cg::coalesced_group cgp = cg::coalesced_threads();
     const unsigned int pa = cg::exclusive_scan(cgp, na, cg::plus<unsigned int>());
     const unsigned int pt = cg::exclusive_scan(cgp, nt, cg::plus<unsigned int>());
@@ -175,7 +183,7 @@ __device__ __forceinline__ void zz_append4(int32_t* wl, unsigned int* wl_cnt, in
     bt = cgp.shfl(bt, last) + pt;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        if (old[q] < tagn) wl[ba++] = kk[q];
+        if (wl && old[q] < tagn) wl[ba++] = kk[q];
         if (tl && old[q] < w0) tl[bt++] = kk[q];
     }
 }
@@ -208,14 +216,29 @@ __device__ __forceinline__ ZzSpecR zz_load_spec(const ZzSpec* p)
 // Stamp up to four readers of a changed coordinate and queue those that were not queued yet.  MULTI: a reader owned
 // by another GPU is stamped and queued in its owner's memory with system-scope atomics over NVLink.
 template <bool MULTI>
-__device__ __forceinline__ void zz_mark4(const ZzParams& P, const int32_t (&kk)[4], uint32_t tagn, uint32_t w0, int nxt, int ws, bool first)
+__device__ __forceinline__ void zz_mark4(const ZzParams& P, const int32_t (&kk)[4], uint32_t tagn, uint32_t w0, int nxt, int ws,
+                                         ZzTailList* tl, int tslot)
 {
     ZzDevCtl* C = P.ctl;
     uint32_t old[4];
     if (!MULTI) {
-        (void)first;
 #pragma unroll
         for (int q = 0; q < 4; ++q) old[q] = (kk[q] >= 0) ? atomicMax(P.dstamp + kk[q], tagn) : 0xffffffffu;
+        if (tl) {   // tail pass: the next list lives in shared memory; only a first touch goes to global memory
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (old[q] < tagn) {
+                    const unsigned int pos = atomicAdd(&tl->n[tslot], 1u);
+                    if (pos < 4u * ZZ_TAIL) tl->buf[tslot][pos] = kk[q];
+                    else tl->ovf = 1u;
+                }
+            }
+            bool any = false;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) any = any || (old[q] < w0);
+            if (any) zz_append4<false>(nullptr, nullptr, P.touched[0], &C->touched_cnt[ws], kk, old, tagn, w0);
+            return;
+        }
         zz_append4<false>(P.wl[nxt], &C->wl_cnt[nxt], P.touched[0], &C->touched_cnt[ws], kk, old, tagn, w0);
         return;
     }
@@ -249,7 +272,7 @@ __device__ __forceinline__ void zz_mark4(const ZzParams& P, const int32_t (&kk)[
 
 template <int KIND, bool MULTI, int MODE>
 __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const ZzNodeOut& o, uint32_t w0,
-                                           uint32_t cur, int nxt, int ws, bool first)
+                                           uint32_t cur, int nxt, int ws, ZzTailList* tl, int tslot)
 {
     ZzDevCtl* C = P.ctl;
     int slot;
@@ -292,14 +315,14 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
                 const bool ok = (q == 0) ? (col > 0) : (q == 1) ? (row > 0) : (q == 2) ? (row < M - 1) : (col < N - 1);
                 kk[q] = ok ? j + ((q == 0) ? -M : (q == 1) ? -1 : (q == 2) ? 1 : M) : -1;
             }
-            zz_mark4<MULTI>(P, kk, tagn, w0, nxt, ws, first);
+            zz_mark4<MULTI>(P, kk, tagn, w0, nxt, ws, tl, tslot);
         } else {
             const int32_t q1 = P.dptr[j + 1];
             for (int32_t q0 = P.dptr[j]; q0 < q1; q0 += 4) {
                 int32_t kk[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) kk[q] = (q0 + q < q1) ? P.didx[q0 + q] : -1;
-                zz_mark4<MULTI>(P, kk, tagn, w0, nxt, ws, first);
+                zz_mark4<MULTI>(P, kk, tagn, w0, nxt, ws, tl, tslot);
             }
         }
     }
@@ -308,21 +331,21 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
         double* vi = P.viol_info + (size_t)j * 3;
         vi[0] = o.viol_t; vi[1] = o.viol_l; vi[2] = o.viol_lb;
     }
-    if (o.flags & ZZ_F_OVERFLOW) atomicOr(&C->wl_cnt[nxt], ZZ_OVF_BIT);
+    if (o.flags & ZZ_F_OVERFLOW) { atomicOr(&C->wl_cnt[nxt], ZZ_OVF_BIT); if (tl) tl->ovf = 1u; }
 }
 
 // One timeline evaluation + publication; kept out of line so the three call sites (scan pass, relaxation pass,
 // tail pass) share one copy of the code and its register allocation.
 template <int KIND, bool MULTI, int MODE>
 __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, double H, int incl, uint32_t w0,
-                                             uint32_t cur, bool first, int nxt, int ws)
+                                             uint32_t cur, bool first, int nxt, int ws, ZzTailList* tl = nullptr, int tslot = 0)
 {
     ZzNodeOut o;
 #ifdef ZZ_PROF_NODE
     const long long c0 = clock64();
     zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, cur, first, o);
     const long long c1 = clock64();
-    zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws, first);
+    zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws, tl, tslot);
     const long long c2 = clock64();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         P.ctl->dbg[0] += (unsigned long long)(c2 - c1);   // cycles in publication
@@ -330,7 +353,7 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
     }
 #else
     zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, cur, first, o);
-    zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws, first);
+    zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws, tl, tslot);
 #endif
 }
 
@@ -588,6 +611,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
     if (blockIdx.x == 0 && threadIdx.x == 0) zz_dbg_ptr = C->dbg;
     __syncthreads();
 #endif
+    __shared__ ZzTailList tail_list;
     __shared__ unsigned int sq_cnt2[2];   // entries of this CTA's scan queue / base of its bulk append
     unsigned int* const sq_cnt_p = sq_cnt2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -664,24 +688,40 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                 if (blockIdx.x == 0) {
                     ZZ_TIC();
                     unsigned int n = cw;
+                    // Lattice kernels keep the tail's lists in shared memory (a coordinate marks at most four readers, so
+                    // 4 * ZZ_TAIL entries always suffice); general graphs use the global lists.
+                    ZzTailList* const tl = (KIND == ZZ_KIND_GRID) ? &tail_list : nullptr;
+                    int src = -1, dst = 0;          // src < 0: the first tail pass reads the global list
+                    if (tl && threadIdx.x == 0) tl->ovf = 0u;
                     for (;;) {
                         li = (li + 1) % 3u;
                         nxt = (int)((li + 1) % 3u);
                         cur++;
-                        if (threadIdx.x == 0) C->wl_cnt[(li + 2) % 3u] = 0;
+                        if (threadIdx.x == 0) { C->wl_cnt[(li + 2) % 3u] = 0; if (tl) tl->n[dst] = 0u; }
+                        if (tl) __syncthreads();
                         const int32_t* wlt = P.wl[li];
                         // entry e goes to warp e % (#warps), lane e / (#warps): few lanes per warp, so that coordinates with
                         // different timelines do not serialise each other's branches
                         for (unsigned int e = (unsigned int)lane * nwc + (unsigned int)warp; e < n; e += blockDim.x) {
-                            const int32_t j = __ldcg(wlt + e);
-                            zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, false, nxt, ws);
+                            const int32_t j = (tl && src >= 0) ? tl->buf[src][e] : __ldcg(wlt + e);
+                            zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, false, nxt, ws, tl, dst);
                             st_evals++;
                         }
                         __syncthreads();   // block-wide visibility is enough inside the tail; the grid barrier below fences
                         st_iters++;
                         if (prof) prof[7] += 1;
-                        n = __ldcg(&C->wl_cnt[nxt]);
-                        if (n == 0 || n > ZZ_TAIL) break;  // (an overflow bit makes n > ZZ_TAIL)
+                        if (tl) {
+                            n = tl->n[dst];
+                            src = dst; dst ^= 1;
+                            if (n == 0 || n > ZZ_TAIL || tl->ovf) break;
+                        } else {
+                            n = __ldcg(&C->wl_cnt[nxt]);
+                            if (n == 0 || n > ZZ_TAIL) break;  // (an overflow bit makes n > ZZ_TAIL)
+                        }
+                    }
+                    if (tl) {   // hand the pending entries (if any) back to the global list the grid-wide passes read
+                        for (unsigned int e = threadIdx.x; e < n; e += blockDim.x) P.wl[nxt][e] = tl->buf[src][e];
+                        if (threadIdx.x == 0 && n) atomicAdd(&C->wl_cnt[nxt], n);   // keeps an overflow bit set by a publication
                     }
                     if (threadIdx.x == 0) { C->tail_li = li; C->tail_cur = cur; }
                     ZZ_TOC(2);
