@@ -29,6 +29,7 @@ struct zzw_run {
     // schedule statistics
     int64_t windows = 0, retries = 0, iters = 0, node_evals = 0, max_iters = 0;
     std::vector<int64_t> pass_hist = std::vector<int64_t>(64, 0);  // work-list size summed per pass index
+    std::vector<int64_t> item_hist = std::vector<int64_t>(64, 0);  // timeline items processed, summed per pass index
     std::string msg;
 };
 
@@ -143,7 +144,9 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
                 ++it;
                 r->pass_hist[std::min<int64_t>(it, 63)] += (int64_t)wl.size();
                 for (int32_t j : wl) {
+                    o.nitems = 0;
                     zz_process_node(g, v, j, ctl.H, ctl.incl, w0, cur, false, o);
+                    r->item_hist[std::min<int64_t>(it, 63)] += o.nitems;
                     handle(j, o, w0, cur);
                 }
             }
@@ -225,5 +228,6 @@ void zzw_final_state(const zzw_run* r, double* t, double* x, double* th, double*
 void zzw_sums(const zzw_run* r, double* s1, double* s2) { memcpy(s1, r->s1.data(), (size_t)r->d * 8); memcpy(s2, r->s2.data(), (size_t)r->d * 8); }
 void zzw_stats(const zzw_run* r, int64_t* out) { out[0] = r->windows; out[1] = r->retries; out[2] = r->iters; out[3] = r->node_evals; out[4] = r->max_iters; }
 void zzw_pass_hist(const zzw_run* r, int64_t* out) { memcpy(out, r->pass_hist.data(), 64 * 8); }
+void zzw_item_hist(const zzw_run* r, int64_t* out) { memcpy(out, r->item_hist.data(), 64 * 8); }
 void zzw_free(zzw_run* r) { delete r; }
 }

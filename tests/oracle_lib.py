@@ -179,6 +179,7 @@ def wlib():
         L.zzw_sums.argtypes = [C.c_void_p] * 3
         L.zzw_stats.argtypes = [C.c_void_p] * 2
         L.zzw_pass_hist.argtypes = [C.c_void_p] * 2
+        L.zzw_item_hist.argtypes = [C.c_void_p] * 2
         L.zzw_error_info.argtypes = [C.c_void_p] * 5
         L.zzw_free.argtypes = [C.c_void_p]
         _wlib = L
@@ -225,6 +226,9 @@ def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1,
         ph = np.zeros(64, np.int64)
         L.zzw_pass_hist(r, _p(ph))
         out.pass_hist = ph
+        ih = np.zeros(64, np.int64)
+        L.zzw_item_hist(r, _p(ih))
+        out.item_hist = ih
         out.stats = dict(windows=int(st[0]), retries=int(st[1]), iters=int(st[2]), node_evals=int(st[3]), max_iters=int(st[4]))
         return out
     finally:

@@ -127,6 +127,7 @@ struct ZzNodeOut {
     double fth[ZZ_MAXFLIP];  // sticky only: velocity after each recorded event
     double viol_t, viol_l, viol_lb;
     uint32_t hdr0, hdr1;   // own flip-list headers as read at entry
+    uint32_t nitems;       // timeline items processed by this evaluation (statistics of the host emulation)
 };
 
 #if defined(__CUDA_ARCH__)

@@ -60,14 +60,18 @@ struct ZzPool {
 };
 
 // merge the recorded flips of neighbour position m into the pool, ordered by (time, position)
+template <bool VEL = true>
 ZZ_HD void zz_pool_add(ZzPool& pool, double fs, int m, uint32_t& flags, double tha = 0.0)
 {
     int p = pool.n;
     if (p == ZZ_POOL) { flags |= ZZ_F_OVERFLOW; return; }
     while (p > 0 && (pool.t[p - 1] > fs || (pool.t[p - 1] == fs && pool.m[p - 1] > m))) {
-        pool.t[p] = pool.t[p - 1]; pool.m[p] = pool.m[p - 1]; pool.th[p] = pool.th[p - 1]; --p;
+        pool.t[p] = pool.t[p - 1]; pool.m[p] = pool.m[p - 1];
+        if (VEL) pool.th[p] = pool.th[p - 1];
+        --p;
     }
-    pool.t[p] = fs; pool.m[p] = m; pool.th[p] = tha; pool.n++;
+    pool.t[p] = fs; pool.m[p] = m; pool.n++;
+    if (VEL) pool.th[p] = tha;
 }
 
 template <int NB, bool MG>
@@ -117,9 +121,9 @@ ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint
 #pragma unroll
     for (int m = 0; m < NB; ++m) {
         if (cnt[m]) {
-            zz_pool_add(pool, f0[m], m, flags);
-            if (cnt[m] > 1) zz_pool_add(pool, f1[m], m, flags);
-            for (uint32_t q = 2; q < cnt[m]; ++q) zz_pool_add(pool, zz_ld(fl[m] + q), m, flags);
+            zz_pool_add<false>(pool, f0[m], m, flags);
+            if (cnt[m] > 1) zz_pool_add<false>(pool, f1[m], m, flags);
+            for (uint32_t q = 2; q < cnt[m]; ++q) zz_pool_add<false>(pool, zz_ld(fl[m] + q), m, flags);
         }
     }
 }
@@ -235,9 +239,11 @@ ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w, const
     uint32_t nprop = 0, nflip = 0, flags = flags0;
     o.viol_t = 0.0; o.viol_l = 0.0; o.viol_lb = 0.0;
     int p = 0;
-
-    for (int item = 0;; ++item) {
+    int item = 0;
+    uint32_t nitems = 0;
+    for (;; ++item) {
         ZZ_SEGCOUNT();
+        ++nitems;
         const double nt = p < pool.n ? pool.t[p] : ZZ_INF;
         const int nm = p < pool.n ? pool.m[p] : 0x7fffffff;
         const bool own = (tau < nt) || (tau == nt && hd.self < nm);
@@ -297,7 +303,7 @@ ZZ_HD void zz_timeline(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w, const
     }
     o.a = a; o.b = b; o.told = told; o.tau = tau; o.c = c;
     o.k = k | (renew ? ZZ_RENEW_BIT : 0u); o.nprop = nprop; o.nflip = nflip; o.flags = flags;
-    o.hdr0 = hh0; o.hdr1 = hh1;
+    o.hdr0 = hh0; o.hdr1 = hh1; o.nitems = nitems;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -161,6 +161,16 @@ struct ZzTailList {
     unsigned int ovf;              // a coordinate overflowed, or the list did
 };
 
+// Exclusive prefix sum and total of a small per-lane count (< 8) over the currently active lanes: three ballots instead
+// of a shuffle scan.
+__device__ __forceinline__ unsigned int zz_prefix3(unsigned int mask, unsigned int v, unsigned int& total)
+{
+    const unsigned int lt = (1u << (threadIdx.x & 31)) - 1u;
+    const unsigned int b0 = __ballot_sync(mask, v & 1u), b1 = __ballot_sync(mask, v & 2u), b2 = __ballot_sync(mask, v & 4u);
+    total = __popc(b0) + 2u * __popc(b1) + 4u * __popc(b2);
+    return __popc(b0 & lt) + 2u * __popc(b1 & lt) + 4u * __popc(b2 & lt);
+}
+
 // Up to four candidates per lane: those whose stamp was older than `tagn` go to the next work list, those older
 // than `w0` (first touch in this window) also to the touched list.  One atomicAdd per list for the active lanes.
 template <bool MULTI>
@@ -170,17 +180,18 @@ __device__ __forceinline__ void zz_append4(int32_t* wl, unsigned int* wl_cnt, in
     unsigned int na = 0, nt = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) { na += (wl && old[q] < tagn) ? 1u : 0u; nt += (tl && old[q] < w0) ? 1u : 0u; }
-    cg::coalesced_group cgp = cg::coalesced_threads();
-    const unsigned int pa = cg::exclusive_scan(cgp, na, cg::plus<unsigned int>());
-    const unsigned int pt = cg::exclusive_scan(cgp, nt, cg::plus<unsigned int>());
+    const unsigned int mask = __activemask();
+    unsigned int ta, tt;
+    const unsigned int pa = zz_prefix3(mask, na, ta);
+    const unsigned int pt = zz_prefix3(mask, nt, tt);
+    const int leadl = __ffs(mask) - 1;
     unsigned int ba = 0, bt = 0;
-    const unsigned int last = cgp.size() - 1;
-    if (cgp.thread_rank() == last) {
-        if (pa + na) ba = MULTI ? atomicAdd_system(wl_cnt, pa + na) : atomicAdd(wl_cnt, pa + na);
-        if (pt + nt) bt = MULTI ? atomicAdd_system(tl_cnt, pt + nt) : atomicAdd(tl_cnt, pt + nt);
+    if ((threadIdx.x & 31) == leadl) {
+        if (ta) ba = MULTI ? atomicAdd_system(wl_cnt, ta) : atomicAdd(wl_cnt, ta);
+        if (tt) bt = MULTI ? atomicAdd_system(tl_cnt, tt) : atomicAdd(tl_cnt, tt);
     }
-    ba = (cgp.shfl(ba, last) & ~ZZ_OVF_BIT) + pa;
-    bt = cgp.shfl(bt, last) + pt;
+    ba = (__shfl_sync(mask, ba, leadl) & ~ZZ_OVF_BIT) + pa;
+    bt = __shfl_sync(mask, bt, leadl) + pt;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         if (wl && old[q] < tagn) wl[ba++] = kk[q];
@@ -385,8 +396,8 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uin
     ZzDevCtl* C = P.ctl;
     // Single GPU: a coordinate can be listed twice (the bulk append of the pass-1 queue and a pass-1 mark of a neighbour
     // that arrived before the coordinate's own stamp); the first visitor claims it with the commit tag.
+    const ZzSpecR s = zz_load_spec(P.spec + j);   // (issued before the claim so that the two round trips overlap)
     if (claim && atomicMax(P.dstamp + j, cur) >= cur) return;
-    const ZzSpecR s = zz_load_spec(P.spec + j);
     if (s.flags & ZZ_F_VIOL) {
         if (atomicExch(&C->viol, 1u) == 0u) {
             const double* vi = P.viol_info + (size_t)j * 3;
@@ -409,12 +420,13 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uin
         const double* fl = P.v.flips + ((size_t)j * 2 + slot) * ZZ_MAXFLIP;
         unsigned long long pos = 0;
         if (P.record_trace) {
-            cg::coalesced_group cgp = cg::coalesced_threads();
-            const unsigned int mine = s.nflip;
-            const unsigned int pre = cg::exclusive_scan(cgp, mine, cg::plus<unsigned int>());
+            const unsigned int mask = __activemask();
+            unsigned int tot;
+            const unsigned int pre = zz_prefix3(mask, s.nflip, tot);   // nflip <= ZZ_MAXFLIP = 6
+            const int leadl = __ffs(mask) - 1;
             unsigned long long base = 0;
-            if (cgp.thread_rank() == cgp.size() - 1) base = atomicAdd(&C->trace_len, (unsigned long long)(pre + mine));
-            base = cgp.shfl(base, cgp.size() - 1);
+            if ((threadIdx.x & 31) == leadl) base = atomicAdd(&C->trace_len, (unsigned long long)tot);
+            base = __shfl_sync(mask, base, leadl);
             pos = base + pre;
         }
         double a1 = __ldcg(P.s1 + j), a2 = __ldcg(P.s2 + j);
