@@ -11,8 +11,9 @@
 #if defined(ZZ_PROF_NODE) && defined(__CUDA_ARCH__)
 __device__ unsigned long long* zz_dbg_ptr;   // set by the kernel; segment k accumulates cycles since segment k-1
 __device__ long long zz_dbg_last;
-#define ZZ_SEG(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long _c = clock64(); if (k) zz_dbg_ptr[k] += (unsigned long long)(_c - zz_dbg_last); zz_dbg_last = _c; } } while (0)
-#define ZZ_SEGCOUNT() do { if (blockIdx.x == 0 && threadIdx.x == 0) zz_dbg_ptr[6] += 1; } while (0)
+__device__ int zz_dbg_on;     // segments are accumulated only while set (ZZ_PROF_TAIL: during the single-CTA tail passes)
+#define ZZ_SEG(k) do { if (blockIdx.x == 0 && threadIdx.x == 0 && zz_dbg_on) { long long _c = clock64(); if (k) zz_dbg_ptr[k] += (unsigned long long)(_c - zz_dbg_last); zz_dbg_last = _c; } } while (0)
+#define ZZ_SEGCOUNT() do { if (blockIdx.x == 0 && threadIdx.x == 0 && zz_dbg_on) zz_dbg_ptr[6] += 1; } while (0)
 #else
 #define ZZ_SEG(k) do { } while (0)
 #define ZZ_SEGCOUNT() do { } while (0)
@@ -74,12 +75,12 @@ ZZ_HD void zz_pool_add(ZzPool& pool, double fs, int m, uint32_t& flags, double t
     if (VEL) pool.th[p] = tha;
 }
 
-template <int NB, bool MG>
+template <int NB, bool MG, bool VEL>
 ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint32_t (&h0)[NB], const uint32_t (&h1)[NB],
                            int n, int self, uint32_t w0, uint32_t cur, ZzPool& pool, uint32_t& flags)
 {
     pool.n = 0;
-    if (v.fth) {   // sticky / Boomerang lists carry the velocity after each event
+    if (VEL) {   // sticky / Boomerang lists carry the velocity after each event (compile-time: the plain kernels stay small)
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
             if (m < n && m != self) {
@@ -129,7 +130,7 @@ ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint
 }
 
 // General sparse column (<= NB entries).  Returns false when the column is longer (caller uses the slow path).
-template <int NB, bool MG>
+template <int NB, bool MG, bool VEL = false>
 ZZ_HD bool zz_gather_csr(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t w0, uint32_t cur, bool first_iter,
                          ZzHood<NB>& hd, ZzPool& pool, uint32_t& flags, ZzHoodMu<NB>* hm = nullptr)
 {
@@ -158,12 +159,12 @@ ZZ_HD bool zz_gather_csr(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t 
         for (int m = 0; m < NB; ++m) hm->mu[m] = (m < n) ? v.bmu[idx[m]] : 0.0;
     }
     pool.n = 0;
-    if (!first_iter) zz_gather_flips<NB, MG>(v, idx, h0, h1, n, hd.self, w0, cur, pool, flags);
+    if (!first_iter) zz_gather_flips<NB, MG, VEL>(v, idx, h0, h1, n, hd.self, w0, cur, pool, flags);
     return true;
 }
 
 // 5-point lattice: column j = {j-M, j-1, j, j+1, j+M} (those that exist), weights -1 and shift + degree.
-template <bool MG>
+template <bool MG, bool VEL = false>
 ZZ_HD void zz_gather_grid(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t w0, uint32_t cur, bool first_iter,
                           ZzHood<5>& hd, ZzPool& pool, uint32_t& flags, ZzHoodMu<5>* hm = nullptr)
 {
@@ -195,7 +196,7 @@ ZZ_HD void zz_gather_grid(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t
     }
     pool.n = 0;
     ZZ_SEG(1);
-    if (!first_iter) zz_gather_flips<5, MG>(v, idx, h0, h1, n, self, w0, cur, pool, flags);
+    if (!first_iter) zz_gather_flips<5, MG, VEL>(v, idx, h0, h1, n, self, w0, cur, pool, flags);
 }
 
 // idot's over the gathered column at time s, storage order (common.jl:16-24)
@@ -582,11 +583,11 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
         zz_load_own(v, j, w);
         if (MODE == ZZ_MODE_BOOM) {
             ZzHoodMu<5> hm;
-            zz_gather_grid<MG>(g, v, j, w0, cur, first_iter, hd, pool, flags, &hm);
+            zz_gather_grid<MG, true>(g, v, j, w0, cur, first_iter, hd, pool, flags, &hm);
             zz_timeline_boom<5>(hd, hm, pool, w, g, v, j, H, incl, flags, o);
             return;
         }
-        zz_gather_grid<MG>(g, v, j, w0, cur, first_iter, hd, pool, flags);
+        zz_gather_grid<MG, MODE == ZZ_MODE_STICKY>(g, v, j, w0, cur, first_iter, hd, pool, flags);
         ZZ_SEG(2);
         if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<5>(hd, pool, w, g, v, j, H, incl, flags, o);
         else zz_timeline<5, MODE == ZZ_MODE_LB>(hd, pool, w, g, v, j, H, incl, flags, o);
@@ -598,11 +599,11 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
         zz_load_own(v, j, w);
         if (MODE == ZZ_MODE_BOOM) {
             ZzHoodMu<ZZ_NB> hm;
-            zz_gather_csr<ZZ_NB, MG>(g, v, j, w0, cur, first_iter, hd, pool, flags, &hm);
+            zz_gather_csr<ZZ_NB, MG, true>(g, v, j, w0, cur, first_iter, hd, pool, flags, &hm);
             zz_timeline_boom<ZZ_NB>(hd, hm, pool, w, g, v, j, H, incl, flags, o);
             return;
         }
-        zz_gather_csr<ZZ_NB, MG>(g, v, j, w0, cur, first_iter, hd, pool, flags);
+        zz_gather_csr<ZZ_NB, MG, MODE == ZZ_MODE_STICKY>(g, v, j, w0, cur, first_iter, hd, pool, flags);
         if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<ZZ_NB>(hd, pool, w, g, v, j, H, incl, flags, o);
         else zz_timeline<ZZ_NB, MODE == ZZ_MODE_LB>(hd, pool, w, g, v, j, H, incl, flags, o);
         return;

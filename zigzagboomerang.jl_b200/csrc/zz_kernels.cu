@@ -358,9 +358,10 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
     const long long c1 = clock64();
     zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws, tl, tslot);
     const long long c2 = clock64();
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && zz_dbg_on) {
         P.ctl->dbg[0] += (unsigned long long)(c2 - c1);   // cycles in publication
         P.ctl->dbg[7] += 1ULL;
+        P.ctl->dbg[3] += (unsigned long long)(c1 - c0);   // cycles in the evaluation
     }
 #else
     zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, cur, first, o);
@@ -371,8 +372,8 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
 // Device-side discretize: write x_j(t_k) for the grid times t_k = t0 + k dt in (tf, fs] of the segment that starts at the
 // anchor (tf, xf, th) and ends at fs (the position is evaluated from the anchor, x = xf + th (t_k - tf), resp. the rotation
 // of the Boomerang flow).  Row 0 (t_k = t0) is written by zz_setup_kernel.
-__device__ __forceinline__ void zz_grid_fill(const ZzParams& P, int32_t j, double tf, double xf, double th, double fs,
-                                             bool boom, double muj)
+template <bool BOOM>
+__device__ __forceinline__ void zz_grid_fill(const ZzParams& P, int32_t j, double tf, double xf, double th, double fs, double muj)
 {
     const double dt = P.grid_dt;
     long long k = (long long)floor((tf - P.t0) / dt);
@@ -383,13 +384,14 @@ __device__ __forceinline__ void zz_grid_fill(const ZzParams& P, int32_t j, doubl
         const double tk = P.t0 + (double)k * dt;
         if (tk > fs) break;
         double x;
-        if (boom) { double tho; zz_boom_at(tf, xf, th, muj, tk, &x, &tho); }
+        if (BOOM) { double tho; zz_boom_at(tf, xf, th, muj, tk, &x, &tho); }
         else x = xf + th * (tk - tf);
         P.grid[(size_t)k * (size_t)P.v.d + (size_t)j] = x;
     }
 }
 
 // Fold the converged end-of-window state of coordinate j into the frontier.
+template <int MODE>
 __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uint32_t w0, uint32_t cur,
                                                unsigned int& nprop_acc, unsigned int& nflip_acc, bool claim)
 {
@@ -430,8 +432,8 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uin
             pos = base + pre;
         }
         double a1 = __ldcg(P.s1 + j), a2 = __ldcg(P.s2 + j);
-        const double* ft = P.v.fth ? P.v.fth + ((size_t)j * 2 + slot) * ZZ_MAXFLIP : nullptr;
-        const bool boom = P.v.boom != 0;
+        const double* ft = ZZ_MODE_HAS_VEL(MODE) ? P.v.fth + ((size_t)j * 2 + slot) * ZZ_MAXFLIP : nullptr;
+        const bool boom = (MODE == ZZ_MODE_BOOM);
         const double muj = boom ? P.v.bmu[j] : 0.0;
         unsigned int nrefl = boom ? ((s.flags >> 3) & 7u) : 0u;   // Boomerang: reflections counted by the timeline (refreshments are events too)
         for (unsigned int m = 0; m < s.nflip; ++m) {
@@ -449,7 +451,7 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uin
             } else {
                 xs = xf + th * (fs - tf); thn = -th; nrefl++;
             }
-            if (P.grid_n) zz_grid_fill(P, j, tf, xf, th, fs, boom, muj);
+            if (P.grid_n) zz_grid_fill<MODE == ZZ_MODE_BOOM>(P, j, tf, xf, th, fs, muj);
             if (!boom) {   // moment sums of the piecewise LINEAR path only
                 a1 += (xf + xs) * (fs - tf);                      // trace.jl:194 (scaled by 1/(2T) on the host)
                 a2 += (fs - tf) * (xf * xf + xf * xs + xs * xs);
@@ -493,7 +495,8 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_grid_tail_kernel(const
 {
     for (int32_t j = P.v.lo + blockIdx.x * blockDim.x + threadIdx.x; j < P.v.hi; j += gridDim.x * blockDim.x) {
         const ZzKin k = P.v.kin[j];
-        zz_grid_fill(P, j, k.tf, k.xf, k.theta, tend, P.v.boom != 0, P.v.boom ? P.v.bmu[j] : 0.0);
+        if (P.v.boom) zz_grid_fill<true>(P, j, k.tf, k.xf, k.theta, tend, P.v.bmu[j]);
+        else zz_grid_fill<false>(P, j, k.tf, k.xf, k.theta, tend, 0.0);
     }
 }
 
@@ -620,7 +623,14 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
 {
     ZzDevCtl* C = P.ctl;
 #ifdef ZZ_PROF_NODE
-    if (blockIdx.x == 0 && threadIdx.x == 0) zz_dbg_ptr = C->dbg;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        zz_dbg_ptr = C->dbg;
+#ifdef ZZ_PROF_TAIL
+        zz_dbg_on = 0;
+#else
+        zz_dbg_on = 1;
+#endif
+    }
     __syncthreads();
 #endif
     __shared__ ZzTailList tail_list;
@@ -705,6 +715,9 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                     ZzTailList* const tl = (KIND == ZZ_KIND_GRID) ? &tail_list : nullptr;
                     int src = -1, dst = 0;          // src < 0: the first tail pass reads the global list
                     if (tl && threadIdx.x == 0) tl->ovf = 0u;
+#if defined(ZZ_PROF_NODE) && defined(ZZ_PROF_TAIL)
+                    if (threadIdx.x == 0) zz_dbg_on = 1;
+#endif
                     for (;;) {
                         li = (li + 1) % 3u;
                         nxt = (int)((li + 1) % 3u);
@@ -731,6 +744,9 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                             if (n == 0 || n > ZZ_TAIL) break;  // (an overflow bit makes n > ZZ_TAIL)
                         }
                     }
+#if defined(ZZ_PROF_NODE) && defined(ZZ_PROF_TAIL)
+                    if (threadIdx.x == 0) zz_dbg_on = 0;
+#endif
                     if (tl) {   // hand the pending entries (if any) back to the global list the grid-wide passes read
                         for (unsigned int e = threadIdx.x; e < n; e += blockDim.x) P.wl[nxt][e] = tl->buf[src][e];
                         if (threadIdx.x == 0 && n) atomicAdd(&C->wl_cnt[nxt], n);   // keeps an overflow bit set by a publication
@@ -805,7 +821,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             unsigned int np = 0, nf = 0;
             for (unsigned int e = gtid; e < nt; e += nthreads) {
                 const int32_t j = __ldcg(P.touched[0] + e);
-                zz_commit_node(P, j, w0, cur, np, nf, !MULTI);
+                zz_commit_node<MODE>(P, j, w0, cur, np, nf, !MULTI);
             }
             cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
             np = cg::reduce(w, np, cg::plus<unsigned int>());
