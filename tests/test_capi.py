@@ -71,3 +71,35 @@ def test_grid_precision_matches_the_reference_construction(zzb):
     G = zzb.grid_precision(m, n)
     assert np.array_equal(G.to_scipy().toarray(), 0.01 * np.eye(m * n) + S)
     assert zzb.grid_precision(100).nnz == 49600  # scripts/gaussianrandomfield.jl:19
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/zzb200.h compiles as C99 with warnings as errors, and a C program binds every entry point of the shared
+    library the way a foreign-function interface would (no GPU needed: zzb_init fails cleanly without a driver/device)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    hdr = open(os.path.join(ROOT, "include", "zzb200.h")).read()
+    names = sorted(set(re.findall(r"\bint32_t\s+(zzb_\w+)\s*\(", hdr)))
+    body = "\n".join(f"    p[{k}] = (fn_t){n};" for k, n in enumerate(names))
+    src.write_text(f"""#include <stdio.h>
+#include "zzb200.h"
+typedef void (*fn_t)(void);
+int main(void) {{
+    fn_t p[{len(names)}];
+{body}
+    char msg[256];
+    int32_t st = zzb_init(1, NULL, NULL);
+    zzb_last_error(msg, sizeof msg);
+    zzb_event e; e.t = 0; e.i = 0; e.x = 0; e.theta = 0; (void)e;
+    printf("%d %d %zu\\n", (int)st, (int)(p[0] != (fn_t)0), sizeof(zzb_event));
+    return 0;
+}}
+""")
+    exe = tmp_path / "abi"
+    pkg = os.path.join(ROOT, "zigzagboomerang.jl_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-o", str(exe), "-L", pkg, "-lzzb200", f"-Wl,-rpath,{pkg}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert out[2] == "32"                         # sizeof(zzb_event) == sizeof(Tuple{Float64,Int64,Float64,Float64})
+    if not os.path.exists("/dev/nvidia0"):
+        assert out[0] == "2"                      # ZZB_E_CUDA: no driver / device, and no fallback

@@ -246,3 +246,43 @@ def test_config1_two_dimensional_pdmp_and_one_dimensional(gpu):
     got, _ = run_gpu(gpu, G1, G1, 0.0, np.array([0.4]), np.array([1.0]), 200.0, np.array([0.5]), seed=(7, 8))
     O.assert_same_run(ref, got)
     assert len(ref.events) > 50
+
+
+def chain_precision(zzb, p):
+    """Gamma = tridiag(-1, 2, -1) + 0.1 I with Gamma[1,1] = Gamma[p,p] = 1.1 (the chain of test/sparsesticky.jl:17-30)."""
+    import scipy.sparse as sp
+    main = np.full(p, 2.1); main[0] = main[-1] = 1.1
+    return zzb.CSC.from_scipy(sp.diags([main, -np.ones(p - 1), -np.ones(p - 1)], [0, 1, -1]).tocsc())
+
+
+def test_config4_sticky_chain_full_size_properties(gpu):
+    """BASELINE configs[3] at its full size p = 10^5 (spike-and-slab chain, everything frozen at 0 initially, kappa = 2000/p)
+    through size-independent properties: the result does not depend on the window length, the trace is time-sorted, every
+    coordinate alternates thaw / (reflections) / freeze consistently, counters agree with the trace."""
+    p, T = 100000, 3.0
+    G = chain_precision(gpu, p)
+    rng = np.random.default_rng(0)
+    x0, th0 = np.zeros(p), rng.choice(np.array([-1.0, 1.0]), p)
+    c, kappa = np.full(p, 2.5), np.full(p, 2000.0 / p)
+    out = []
+    for frac in (0.05, 0.4):
+        Xi, (t, x, th), (acc, num), _ = gpu.sspdmp(gpu.GaussianPotential(G), 0.0, x0, th0, T, c, gpu.ZigZag(G, np.zeros(p)), kappa,
+                                                    seed=(5, 6), tune=dict(target_frac=frac))
+        out.append((Xi.events, t, x, th, acc, num))
+    (ev, t, x, th, acc, num), (ev2, t2, x2, th2, acc2, num2) = out
+    assert num == num2 and acc == acc2 and np.array_equal(ev, ev2)
+    for u, v in ((t, t2), (x, x2), (th, th2)):
+        assert np.array_equal(u.view(np.uint64), v.view(np.uint64))
+    assert np.all(np.diff(ev["t"]) >= 0) and ev["t"][-1] >= T and np.all(ev["t"][:-1] < T)
+    # per coordinate: events alternate between "moving" (theta != 0) and "frozen" (theta == 0, x == 0) consistently
+    order = np.lexsort((ev["t"], ev["i"]))
+    e = ev[order]
+    first = np.r_[True, e["i"][1:] != e["i"][:-1]]
+    assert np.all(e["theta"][first] != 0)                       # everything starts frozen: the first event is a thaw
+    frozen_after = e["theta"] == 0
+    assert np.all(e["x"][frozen_after] == 0)
+    prev_frozen = np.r_[False, frozen_after[:-1]] & ~first
+    assert not np.any(prev_frozen & frozen_after)               # never two freezes in a row
+    refl = ~frozen_after & ~first & ~prev_frozen                # moving -> moving: accepted reflections
+    assert refl.sum() == acc
+    assert 0.01 < np.mean(th != 0) < 0.2                        # a few per cent of the coordinates are active at time T
