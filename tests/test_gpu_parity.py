@@ -287,3 +287,20 @@ def test_config4_sticky_chain_full_size_properties(gpu):
     refl = ~frozen_after & ~prev_frozen                         # moving -> moving: accepted reflections
     assert refl.sum() == acc
     assert 0.0 < np.mean(th != 0) < 1.0 and frozen_after.sum() > 0.2 * p   # x0 = 0 with theta0 = +-1 starts moving; most coordinates have frozen by T
+
+
+def test_testiter_fact_sampler_moments(gpu):
+    """test/testiter.jl:4-31 on the device path: tr = trace(FactSampler(grad, t0 => (x0, theta0), c, Z), T) with d = 8,
+    Z = ZigZag(0.9 Gamma, 0), T = 1000; mean(tr) and the discretised moments within the reference's tolerances."""
+    import math
+    d, T = 8, 1000.0
+    G = gpu.random_spd(d, seed=2)
+    rng = np.random.default_rng(8)
+    x0, th0 = rng.random(d), rng.choice(np.array([-1.0, 1.0]), d)
+    c = 0.7 * G.colnorms()
+    FS = gpu.FactSampler(gpu.GaussianPotential(G), (0.0, (x0, th0)), c, gpu.ZigZag(G.scaled(0.9), np.zeros(d)), seed=(21, 22))
+    tr = gpu.trace(FS, T)
+    assert 0.1 / math.sqrt(T) < np.mean(np.abs(gpu.mean(tr))) < 2 / math.sqrt(T)          # testiter.jl:26
+    ts, xs = gpu.discretize(tr, 0.5)
+    assert np.mean(np.abs(xs.mean(axis=0))) < 2 / math.sqrt(T)                            # :30
+    assert np.mean(np.abs(np.cov(xs.T) - np.linalg.inv(G.to_scipy().toarray()))) < 2.5 / math.sqrt(T)   # :31
