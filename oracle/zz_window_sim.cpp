@@ -76,7 +76,8 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
         priv[j].c = c_in[j];
     }
     double F0 = ZZ_INF;
-    for (int64_t j = 0; j < d; ++j) { zz_init_node(g, v, (int32_t)j, t0); F0 = std::min(F0, tau[j]); }
+    for (int64_t j = 0; j < d; ++j) { if (v.boom) zz_init_node_boom(g, v, (int32_t)j, t0); else zz_init_node(g, v, (int32_t)j, t0);
+        F0 = std::min(F0, tau[j]); }
     if (!(t0 < T)) goto finish;  // while t' < T never entered (sfact.jl:199)
     {
         ZzCtl ctl;

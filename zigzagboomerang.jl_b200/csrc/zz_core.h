@@ -348,18 +348,21 @@ ZZ_HD void zz_process_node_slow(const ZzGraph& g, const ZzView& v, int32_t j, do
 #include "zz_fast.h"
 
 // Initial bound and first proposal time of coordinate j (sfact.jl:184-187; note: no "+ t0").
+// FactBoomerang: every anchor is at t0 and there are no lists yet -- gather and evaluate once (kept apart from zz_init_node
+// so that the ZigZag initialisation kernel stays small)
+ZZ_HD void zz_init_node_boom(const ZzGraph& g, const ZzView& v, int32_t j, double t0)
+{
+    ZzPool pool; uint32_t fl = 0;
+    if (g.grid_m) { ZzHood<5> hd; ZzHoodMu<5> hm; zz_gather_grid<false, true>(g, v, j, 1u, 1u, true, hd, pool, fl, &hm); zz_boom_init<5>(hd, hm, g, v, j, t0); }
+    else {
+        ZzHood<ZZ_NB> hd; ZzHoodMu<ZZ_NB> hm;
+        if (!zz_gather_csr<ZZ_NB, false, true>(g, v, j, 1u, 1u, true, hd, pool, fl, &hm)) return;   // (longer columns are refused by the host)
+        zz_boom_init<ZZ_NB>(hd, hm, g, v, j, t0);
+    }
+}
+
 ZZ_HD void zz_init_node(const ZzGraph& g, const ZzView& v, int32_t j, double t0)
 {
-    if (v.boom) {   // every anchor is at t0, no lists yet: gather and evaluate once
-        ZzPool pool; uint32_t fl = 0;
-        if (g.grid_m) { ZzHood<5> hd; ZzHoodMu<5> hm; zz_gather_grid<false>(g, v, j, 1u, 1u, true, hd, pool, fl, &hm); zz_boom_init<5>(hd, hm, g, v, j, t0); }
-        else {
-            ZzHood<ZZ_NB> hd; ZzHoodMu<ZZ_NB> hm;
-            if (!zz_gather_csr<ZZ_NB, false>(g, v, j, 1u, 1u, true, hd, pool, fl, &hm)) return;   // (longer columns are refused by the host)
-            zz_boom_init<ZZ_NB>(hd, hm, g, v, j, t0);
-        }
-        return;
-    }
     double th, tf, xf; uint32_t h0, h1;
     zz_ld_kin(v.kin + j, th, tf, xf, h0, h1);
     double gt, gx, gp, gm;

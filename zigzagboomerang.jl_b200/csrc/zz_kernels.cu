@@ -392,14 +392,10 @@ __device__ __forceinline__ void zz_grid_fill(const ZzParams& P, int32_t j, doubl
 
 // Fold the converged end-of-window state of coordinate j into the frontier.
 template <int MODE>
-__device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, uint32_t w0, uint32_t cur,
-                                               unsigned int& nprop_acc, unsigned int& nflip_acc, bool claim)
+__device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, const ZzSpecR& s, uint32_t w0, uint32_t cur,
+                                               unsigned int& nprop_acc, unsigned int& nflip_acc)
 {
     ZzDevCtl* C = P.ctl;
-    // Single GPU: a coordinate can be listed twice (the bulk append of the pass-1 queue and a pass-1 mark of a neighbour
-    // that arrived before the coordinate's own stamp); the first visitor claims it with the commit tag.
-    const ZzSpecR s = zz_load_spec(P.spec + j);   // (issued before the claim so that the two round trips overlap)
-    if (claim && atomicMax(P.dstamp + j, cur) >= cur) return;
     if (s.flags & ZZ_F_VIOL) {
         if (atomicExch(&C->viol, 1u) == 0u) {
             const double* vi = P.viol_info + (size_t)j * 3;
@@ -500,12 +496,14 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_grid_tail_kernel(const
     }
 }
 
-extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel(const ZzParams P)
+template <bool BOOM>
+__device__ __forceinline__ void zz_init_body(const ZzParams& P)
 {
     ZzView vloc = P.v; vloc.nranks = 1;   // every rank initialises all coordinates from its own (identical) copies
     unsigned long long kmin = ~0ULL;
     for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < P.v.d; j += gridDim.x * blockDim.x) {
-        zz_init_node(P.g, vloc, j, P.t0);
+        if (BOOM) zz_init_node_boom(P.g, vloc, j, P.t0);
+        else zz_init_node(P.g, vloc, j, P.t0);
         const unsigned long long k = zz_key(vloc.tau[j]);
         kmin = k < kmin ? k : kmin;
     }
@@ -513,6 +511,8 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel(const ZzPa
     kmin = cg::reduce(w, kmin, cg::less<unsigned long long>());
     if (w.thread_rank() == 0 && kmin != ~0ULL) atomicMin(&P.ctl->f0_key, kmin);
 }
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel(const ZzParams P) { zz_init_body<false>(P); }
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel_boom(const ZzParams P) { zz_init_body<true>(P); }
 
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK)
 zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ x, double* __restrict__ th,
@@ -819,9 +819,13 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             ZZ_TIC();
             const unsigned int nt = __ldcg(&C->touched_cnt[ws]);
             unsigned int np = 0, nf = 0;
+            // Single GPU: a coordinate can be listed twice (the bulk append of the pass-1 queue and a pass-1 mark of a neighbour
+            // that arrived before the coordinate's own stamp); the first visitor claims it with the commit tag.
             for (unsigned int e = gtid; e < nt; e += nthreads) {
                 const int32_t j = __ldcg(P.touched[0] + e);
-                zz_commit_node<MODE>(P, j, w0, cur, np, nf, !MULTI);
+                const ZzSpecR sp = zz_load_spec(P.spec + j);   // (issued before the claim so that the two round trips overlap)
+                if (!MULTI && atomicMax(P.dstamp + j, cur) >= cur) continue;
+                zz_commit_node<MODE>(P, j, sp, w0, cur, np, nf);
             }
             cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
             np = cg::reduce(w, np, cg::plus<unsigned int>());

@@ -88,7 +88,7 @@ struct Global {
     CUdevice dev = 0; int dev_id = 0;
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
-    CUfunction f_setup = nullptr, f_init = nullptr, f_run[12] = {}, f_export = nullptr, f_grid_tail = nullptr;
+    CUfunction f_setup = nullptr, f_init = nullptr, f_init_boom = nullptr, f_run[12] = {}, f_export = nullptr, f_grid_tail = nullptr;
     CUstream stream = nullptr;
     CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
     int sm_count = 0; int blocks_per_sm[12] = {}; int run_block[2] = { 256, 256 };   // lattice / general-sparse kernels
@@ -228,6 +228,7 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     CU(cuModuleLoadData(&G.mod, img.data()));
     CU(cuModuleGetFunction(&G.f_setup, G.mod, "zz_setup_kernel"));
     CU(cuModuleGetFunction(&G.f_init, G.mod, "zz_init_kernel"));
+    CU(cuModuleGetFunction(&G.f_init_boom, G.mod, "zz_init_kernel_boom"));
     // index = kind (0 lattice, 1 general) + 2 * multi-GPU + 4 * LocalBound
     // 8, 9: sticky ZigZag (single GPU)
     // 10, 11: factorised Boomerang (single GPU)
@@ -557,7 +558,7 @@ int32_t zzb_run_reset(zzb_run_t r)
     void* a1[] = { &P, &px, &pth, &pc };
     CU(cuLaunchKernel(G.f_setup, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a1, nullptr));
     void* a2[] = { &P };
-    CU(cuLaunchKernel(G.f_init, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a2, nullptr));
+    CU(cuLaunchKernel((r->flags & ZZB_FLAG_BOOMERANG) ? G.f_init_boom : G.f_init, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a2, nullptr));
     CU(cuStreamSynchronize(G.stream));
     r->launches += 2;
     r->uploaded = true; r->executed = false; r->fetched = false;
