@@ -524,16 +524,14 @@ zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ 
     }
 }
 
-// Passes whose coordinates are found by scanning: every CTA scans its contiguous share of the owned coordinates and compacts
-// the active ones into a CTA-wide queue (the work list consumed last is free during these passes; the CTA uses the slice
-// that mirrors its share); the caller then works through the queue with all its threads: ceil(active / threads) rounds.
-//   CRIT 0 (pass 1): proposal time inside the window;  CRIT 1 (pass 2, single GPU): stamped by a pass-1 mark (dstamp == cur).
-// TOUCH (single GPU): the coordinates seen for the first time in this window are appended to the touched list in bulk --
-// the whole queue of pass 1 with one atomic per CTA, in pass 2 those without a proposal in the window with one atomic per
-// scanned chunk -- so that no evaluation waits for an atomic.
-template <int CRIT, bool TOUCH>
+// Pass 1 finds its coordinates by scanning: every CTA scans its contiguous share of the owned proposal times and compacts
+// the coordinates with a proposal inside the window into a CTA-wide queue (the work list consumed last is free during this
+// pass; the CTA uses the slice that mirrors its share); the CTA then works through the queue with all its threads:
+// ceil(active / threads) evaluation rounds.  TOUCH (single GPU): every coordinate of the queue is new to the window, so the
+// whole queue is appended to the touched list with ONE atomic per CTA and no evaluation waits for an atomic.
+template <bool TOUCH>
 __device__ __forceinline__ unsigned int zz_build_queue(const ZzParams& P, unsigned int* sq_cnt, int32_t lo, int32_t hi, uint32_t li,
-                                                       double H, int incl, uint32_t cur, int ws, const int32_t*& qout)
+                                                       double H, int incl, int ws, const int32_t*& qout)
 {
     ZzDevCtl* C = P.ctl;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -546,25 +544,16 @@ __device__ __forceinline__ unsigned int zz_build_queue(const ZzParams& P, unsign
     if (threadIdx.x == 0) { sq_cnt[0] = 0u; sq_cnt[1] = 0u; }
     __syncthreads();
     for (int32_t base = c_lo + warp * (32 * ZZ_SCAN_U); base < c_hi; base += nwc * (32 * ZZ_SCAN_U)) {
-        bool act[ZZ_SCAN_U], fresh[ZZ_SCAN_U];
-        unsigned int nfresh = 0;
+        bool act[ZZ_SCAN_U];
 #pragma unroll
         for (int u = 0; u < ZZ_SCAN_U; ++u) {
             const int32_t j = base + u * 32 + lane;
-            act[u] = false; fresh[u] = false;
-            if (j < c_hi) {
-                if (CRIT == 0) { const double tj = __ldcg(P.v.tau + j); act[u] = (tj < H) || (incl && tj == H); }
-                else {
-                    act[u] = (__ldcg(P.dstamp + j) == cur);
-                    if (TOUCH) { const double tj = __ldcg(P.v.tau + j); fresh[u] = act[u] && !((tj < H) || (incl && tj == H)); }
-                }
-            }
+            act[u] = false;
+            if (j < c_hi) { const double tj = __ldcg(P.v.tau + j); act[u] = (tj < H) || (incl && tj == H); }
         }
-        unsigned int mf[ZZ_SCAN_U];
 #pragma unroll
         for (int u = 0; u < ZZ_SCAN_U; ++u) {
             const unsigned int m = __ballot_sync(0xffffffffu, act[u]);
-            if (CRIT == 1 && TOUCH) { mf[u] = __ballot_sync(0xffffffffu, fresh[u]); nfresh += __popc(mf[u]); }
             if (m) {
                 unsigned int wb = 0;
                 if (lane == 0) wb = atomicAdd(sq_cnt, (unsigned int)__popc(m));
@@ -572,48 +561,36 @@ __device__ __forceinline__ unsigned int zz_build_queue(const ZzParams& P, unsign
                 if (act[u]) q[wb + __popc(m & ((1u << lane) - 1u))] = base + u * 32 + lane;
             }
         }
-        if (CRIT == 1 && TOUCH && nfresh) {   // not in the pass-1 queue: first touch
-            unsigned int tb = 0;
-            if (lane == 0) tb = atomicAdd(&C->touched_cnt[ws], nfresh);
-            tb = __shfl_sync(0xffffffffu, tb, 0);
-#pragma unroll
-            for (int u = 0; u < ZZ_SCAN_U; ++u) {
-                if (fresh[u]) P.touched[0][tb + __popc(mf[u] & ((1u << lane) - 1u))] = base + u * 32 + lane;
-                tb += __popc(mf[u]);
-            }
-        }
     }
     __syncthreads();
     const unsigned int qn = sq_cnt[0];
-    if (CRIT == 0 && TOUCH && qn) {   // every coordinate of the pass-1 queue is new to this window
+    if (TOUCH && qn) {
         if (threadIdx.x == 0) sq_cnt[1] = atomicAdd(&C->touched_cnt[ws], qn);
         __syncthreads();
         const unsigned int tb = sq_cnt[1];
-        for (unsigned int e = threadIdx.x; e < qn; e += blockDim.x) P.touched[0][tb + e] = q[e];
+        for (unsigned int e = threadIdx.x; e < qn; e += blockDim.x) P.touched[0][tb + e] = __ldcg(q + e);
     }
     qout = q;
     return qn;
 }
 
-template <int KIND, bool MULTI, int MODE, bool BYSTAMP>
+template <int KIND, bool MULTI, int MODE>
 __device__ __forceinline__ void zz_queue_pass(const ZzParams& P, unsigned int* sq_cnt, int32_t lo, int32_t hi, uint32_t li,
                                               double H, int incl, uint32_t w0, uint32_t cur, int nxt, int ws,
                                               unsigned long long& st_evals)
 {
     ZzDevCtl* C = P.ctl;
     const int32_t* q;
-    const unsigned int qn = zz_build_queue<BYSTAMP ? 1 : 0, !MULTI>(P, sq_cnt, lo, hi, li, H, incl, cur, ws, q);
+    const unsigned int qn = zz_build_queue<!MULTI>(P, sq_cnt, lo, hi, li, H, incl, ws, q);
     for (unsigned int e = threadIdx.x; e < qn; e += blockDim.x) {
         const int32_t j = __ldcg(q + e);
-        if (!BYSTAMP) {
-            if (MULTI) {
-                const uint32_t old = atomicMax_system(P.dstamp + j, cur);
-                if (old < w0) zz_append<MULTI>(P.touched[0], &C->touched_cnt[ws], j);
-            } else {
-                atomicMax(P.dstamp + j, cur);   // result unused (RED); the queue went to the touched list in bulk
-            }
+        if (MULTI) {
+            const uint32_t old = atomicMax_system(P.dstamp + j, cur);
+            if (old < w0) zz_append<MULTI>(P.touched[0], &C->touched_cnt[ws], j);
+        } else {
+            atomicMax(P.dstamp + j, cur);   // result unused (RED); the queue went to the touched list in bulk
         }
-        zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, !BYSTAMP, nxt, ws);
+        zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, true, nxt, ws);
         st_evals++;
     }
 }
@@ -690,7 +667,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             const int wz = (int)(wat % 3u);  // slot of the NEXT attempt
             C->touched_cnt[wz] = 0; C->smin_key[wz] = ~0ULL; C->nprop_win[wz] = 0;
         }
-        zz_queue_pass<KIND, MULTI, MODE, false>(P, sq_cnt_p, lo, hi, li, H, incl, w0, cur, nxt, ws, st_evals);
+        zz_queue_pass<KIND, MULTI, MODE>(P, sq_cnt_p, lo, hi, li, H, incl, w0, cur, nxt, ws, st_evals);
         ZZ_TOC(0);
         ZzXres xr = zz_boundary<MULTI>(P, epoch, xep, prof, MULTI ? &C->issued[nxt] : nullptr, nullptr,
                                        MULTI ? &C->wl_cnt[nxt] : nullptr, ZZ_OVF_BIT, ZZ_X_OVERFLOW);
