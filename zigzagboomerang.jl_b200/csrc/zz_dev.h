@@ -54,6 +54,8 @@ struct ZzDevCtl {
     unsigned long long issued[3];    // appends issued by this rank into ANY rank's next work list, per list slot
     unsigned long long xrelease;     // bumped by CTA 0 once the exchange of the current boundary is complete
     ZzMsg xres[2];                   // reduced result of the exchange, by boundary parity
+    unsigned long long tail_xep;     // sharded tail passes (CTA 0 only): exchange counter and last reduced result, for the other CTAs
+    ZzMsg tail_xres;
     ZzMsg mbox[2][ZZ_MAXRANKS];      // incoming messages, by boundary parity and sender
 };
 

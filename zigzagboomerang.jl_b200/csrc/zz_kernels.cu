@@ -86,6 +86,36 @@ __device__ __forceinline__ void zz_st_rel_sys(unsigned long long* p, unsigned lo
 
 struct ZzXres { unsigned long long sum, minkey; unsigned int flags; };
 
+// All-reduce of (sum, min, or) across the GPUs of the node by ONE thread: plain stores into the peers' mailboxes over NVLink
+// (double-buffered by the parity of the exchange counter), release / acquire at system scope.  The result is also left in the
+// control block for the other CTAs of this GPU.
+__device__ __forceinline__ ZzXres zz_exchange(const ZzParams& P, unsigned long long xep, unsigned long long ms,
+                                              unsigned long long mk, unsigned int mf)
+{
+    ZzDevCtl* C = P.ctl;
+    const int par = (int)(xep & 1ULL);
+    __threadfence_system();
+    for (int p = 0; p < P.v.nranks; ++p) {
+        ZzMsg* dst = &P.ctl_peer[p]->mbox[par][P.v.rank];
+        dst->sum = ms; dst->minkey = mk; dst->flags = mf;
+    }
+    __threadfence_system();
+    for (int p = 0; p < P.v.nranks; ++p) zz_st_rel_sys(&P.ctl_peer[p]->mbox[par][P.v.rank].epoch, xep);
+    ZzXres r; r.sum = 0ULL; r.minkey = ~0ULL; r.flags = 0u;
+    for (int p = 0; p < P.v.nranks; ++p) {
+        const ZzMsg* src = &C->mbox[par][p];
+        while (zz_ld_acq_sys(&src->epoch) < xep) { }
+        r.sum += *(volatile const unsigned long long*)&src->sum;
+        const unsigned long long kk = *(volatile const unsigned long long*)&src->minkey;
+        r.minkey = kk < r.minkey ? kk : r.minkey;
+        r.flags |= *(volatile const unsigned int*)&src->flags;
+    }
+    C->xres[par].sum = r.sum; C->xres[par].minkey = r.minkey; C->xres[par].flags = r.flags;
+    __threadfence();
+    atomicExch(&C->xrelease, xep);
+    return r;
+}
+
 // Pass boundary: local grid barrier, then (MULTI) an all-reduce of (sum, min, or) across the GPUs of the node done by
 // CTA 0 with plain stores into the peers' mailboxes over NVLink; the other CTAs are released once the result is known.
 // The caller passes this rank's contributions as addresses inside the control block; they are read by CTA 0 after
@@ -112,25 +142,7 @@ __device__ __forceinline__ ZzXres zz_boundary(const ZzParams& P, unsigned long l
         const unsigned long long ms = psum ? __ldcg(psum) : 0ULL;
         const unsigned long long mk = pmin ? __ldcg(pmin) : ~0ULL;
         const unsigned int mf = (pflag_word && (__ldcg(pflag_word) & flag_mask)) ? flag_value : 0u;
-        __threadfence_system();
-        for (int p = 0; p < P.v.nranks; ++p) {
-            ZzMsg* dst = &P.ctl_peer[p]->mbox[par][P.v.rank];
-            dst->sum = ms; dst->minkey = mk; dst->flags = mf;
-        }
-        __threadfence_system();
-        for (int p = 0; p < P.v.nranks; ++p) zz_st_rel_sys(&P.ctl_peer[p]->mbox[par][P.v.rank].epoch, xep);
-        unsigned long long s = 0ULL, k = ~0ULL; unsigned int f = 0u;
-        for (int p = 0; p < P.v.nranks; ++p) {
-            const ZzMsg* src = &C->mbox[par][p];
-            while (zz_ld_acq_sys(&src->epoch) < xep) { }
-            s += *(volatile const unsigned long long*)&src->sum;
-            const unsigned long long kk = *(volatile const unsigned long long*)&src->minkey;
-            k = kk < k ? kk : k;
-            f |= *(volatile const unsigned int*)&src->flags;
-        }
-        C->xres[par].sum = s; C->xres[par].minkey = k; C->xres[par].flags = f;
-        __threadfence();
-        atomicExch(&C->xrelease, xep);
+        zz_exchange(P, xep, ms, mk, mf);
         if (prof) prof[5] += zz_now() - t0;
     }
     if (threadIdx.x == 0) {
@@ -611,6 +623,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
     __syncthreads();
 #endif
     __shared__ ZzTailList tail_list;
+    __shared__ ZzXres tail_xr;   // sharded tail: result of CTA 0's last exchange
     __shared__ unsigned int sq_cnt2[2];   // entries of this CTA's scan queue / base of its bulk append
     unsigned int* const sq_cnt_p = sq_cnt2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -733,6 +746,49 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
                 }
                 zz_grid_barrier(C, epoch, prof);
                 li = __ldcg(&C->tail_li); cur = __ldcg(&C->tail_cur);
+                nxt = (int)((li + 1) % 3u);
+                continue;
+            }
+            if (MULTI && total <= ZZ_TAIL) {
+                // Sharded tail: every GPU's CTA 0 relaxes its own few coordinates and the CTAs 0 exchange the number of
+                // issued marks directly -- no local grid barrier, no release broadcast per pass; the other CTAs wait once.
+                if (blockIdx.x == 0) {
+                    ZZ_TIC();
+                    unsigned long long txep = xep;
+                    for (;;) {
+                        li = (li + 1) % 3u;
+                        nxt = (int)((li + 1) % 3u);
+                        cur++;
+                        if (threadIdx.x == 0) { C->wl_cnt[(li + 2) % 3u] = 0; C->issued[(li + 2) % 3u] = 0; }
+                        const unsigned int n = __ldcg(&C->wl_cnt[li]) & ~ZZ_OVF_BIT;   // this GPU's share of the list
+                        const int32_t* wlt = P.wl[li];
+                        for (unsigned int e = (unsigned int)lane * nwc + (unsigned int)warp; e < n; e += blockDim.x) {
+                            const int32_t j = __ldcg(wlt + e);
+                            zz_eval_publish<KIND, MULTI, MODE>(P, j, H, incl, w0, cur, false, nxt, ws);
+                            st_evals++;
+                        }
+                        __syncthreads();
+                        if (threadIdx.x == 0) {
+                            const unsigned long long ms = __ldcg(&C->issued[nxt]);
+                            const unsigned int mf = (__ldcg(&C->wl_cnt[nxt]) & ZZ_OVF_BIT) ? ZZ_X_OVERFLOW : 0u;
+                            txep += 1;
+                            const ZzXres t = zz_exchange(P, txep, ms, ~0ULL, mf);
+                            tail_xr.sum = t.sum; tail_xr.minkey = t.minkey; tail_xr.flags = t.flags;
+                        }
+                        __syncthreads();
+                        st_iters++;
+                        if (prof) prof[7] += 1;
+                        if (tail_xr.sum == 0ULL || tail_xr.sum > ZZ_TAIL || (tail_xr.flags & ZZ_X_OVERFLOW)) break;
+                    }
+                    if (threadIdx.x == 0) {
+                        C->tail_li = li; C->tail_cur = cur; C->tail_xep = txep;
+                        C->tail_xres.sum = tail_xr.sum; C->tail_xres.minkey = tail_xr.minkey; C->tail_xres.flags = tail_xr.flags;
+                    }
+                    ZZ_TOC(2);
+                }
+                zz_grid_barrier(C, epoch, prof);
+                li = __ldcg(&C->tail_li); cur = __ldcg(&C->tail_cur); xep = __ldcg(&C->tail_xep);
+                xr.sum = __ldcg(&C->tail_xres.sum); xr.minkey = __ldcg(&C->tail_xres.minkey); xr.flags = __ldcg(&C->tail_xres.flags);
                 nxt = (int)((li + 1) % 3u);
                 continue;
             }
