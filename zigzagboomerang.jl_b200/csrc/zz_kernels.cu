@@ -853,7 +853,8 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
             const unsigned int nt = __ldcg(&C->touched_cnt[ws]);
             unsigned int np = 0, nf = 0;
             // Single GPU: a coordinate can be listed twice (the bulk append of the pass-1 queue and a pass-1 mark of a neighbour
-            // that arrived before the coordinate's own stamp); the first visitor claims it with the commit tag.
+            // that arrived before the coordinate's own stamp); the first visitor claims it with the commit tag (larger than
+            // every stamp of the window: the relaxation only ends after a pass that issued no mark).
             for (unsigned int e = gtid; e < nt; e += nthreads) {
                 const int32_t j = __ldcg(P.touched[0] + e);
                 const ZzSpecR sp = zz_load_spec(P.spec + j);   // (issued before the claim so that the two round trips overlap)
