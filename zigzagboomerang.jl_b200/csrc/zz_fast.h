@@ -563,6 +563,102 @@ ZZ_HD void zz_boom_init(ZzHood<NB>& hd, const ZzHoodMu<NB>& hm, const ZzGraph& g
     v.kctr[j] = 2u;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Lattice interior (plain ZigZag, single GPU): the 5-point column {j-M, j-1, j, j+1, j+M} with weights {-1, -1, diag, -1, -1},
+// target == sampler matrix, no linear term, mu = 0.  Same arithmetic as zz_gather_grid + zz_timeline<5, false>, operation
+// for operation -- (-1) * x is written -x, gx - 0 is written gx, both exact -- with every flag test, bounds test and weight
+// load folded away: the common case costs about a third fewer instructions, which is what a lone warp in a late
+// relaxation pass is made of.  Neighbour positions follow the storage order of the column: 0, 1, (2 = self), 3, 4.
+ZZ_HD void zz_process_interior(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0, uint32_t cur,
+                               bool first_iter, ZzNodeOut& o)
+{
+    ZzOwn w;
+    zz_load_own(v, j, w);
+    const int32_t M = g.grid_m;
+    const int32_t idx[5] = { j - M, j - 1, j, j + 1, j + M };
+    double nth[5], ntf[5], nxf[5]; uint32_t h0[5], h1[5];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+        nth[m] = 0.0; ntf[m] = 0.0; nxf[m] = 0.0; h0[m] = 0; h1[m] = 0;
+        if (m != 2) zz_ld_kin(v.kin + idx[m], nth[m], ntf[m], nxf[m], h0[m], h1[m]);
+    }
+    ZzPool pool; pool.n = 0;
+    uint32_t flags = 0;
+    if (!first_iter) zz_gather_flips<5, false, false>(v, idx, h0, h1, 5, 2, w0, cur, pool, flags);
+
+    const double diag = g.grid_diag[4];
+    double th = w.th, tf = w.tf, xf = w.xf;
+    double a = w.a, b = w.b, told = w.told, c = w.c;
+    double c100 = c / 100;
+    double tau = w.tau;
+    uint32_t k = w.k;
+    uint32_t nprop = 0, nflip = 0, nitems = 0;
+    o.viol_t = 0.0; o.viol_l = 0.0; o.viol_lb = 0.0;
+    int p = 0;
+    for (int item = 0;; ++item) {
+        ++nitems;
+        const double nt = p < pool.n ? pool.t[p] : ZZ_INF;
+        const int nm = p < pool.n ? pool.m[p] : 0x7fffffff;
+        const bool own = (tau < nt) || (tau == nt && 2 < nm);
+        const double s = own ? tau : nt;
+        if (!(s < H || (incl && s == H))) break;
+        if (item >= ZZ_MAXITEMS) { flags |= ZZ_F_OVERFLOW; break; }
+        if (!own) {   // the neighbour at position nm flips at s (every lattice neighbour is a trigger)
+#pragma unroll
+            for (int m = 0; m < 5; ++m) {
+                if (m != 2 && m == nm) {
+                    nxf[m] = nxf[m] + nth[m] * (s - ntf[m]);
+                    ntf[m] = s;
+                    nth[m] = -nth[m];
+                }
+            }
+            ++p;
+        }
+        const uint32_t kr = own ? k + 1u : k;
+        const double L2 = zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, kr));
+        const double u1 = own ? zz_u01(v.seed0, v.seed1, (uint64_t)j, k) : 0.0;
+        k = kr + 1u;
+        const double xs = xf + th * (s - tf);
+        // idot over the column in storage order (common.jl:16-24): positions, velocities with +own / -own
+        double ax = 0.0, ap = 0.0, am = 0.0;
+#pragma unroll
+        for (int m = 0; m < 5; ++m) {
+            if (m == 2) {
+                ax += diag * xs; ap += diag * th; am += diag * (-th);
+            } else {
+                const double x = nxf[m] + nth[m] * (s - ntf[m]);
+                ax += -x; ap += -nth[m]; am += -nth[m];
+            }
+        }
+        double gth = ap;
+        if (own) {
+            const double l = zz_pos(ax * th);                 // fact_samplers.jl:28-30
+            const double lb = zz_pos(a + b * (s - told));     // sfact.jl:70
+            nprop++;
+            if (u1 * lb < l) {                                // sfact.jl:121
+                if (l >= lb) {                                // sfact.jl:123-128
+                    if (v.adapt) { c *= v.factor; c100 = c / 100; }
+                    else if (!(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
+                }
+                if (nflip == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#pragma unroll
+                for (int m = 0; m < ZZ_MAXFLIP; ++m)
+                    if (m == (int)nflip) o.fl[m] = s;
+                nflip++;
+                xf = xs; tf = s; th = -th;                    // dynamics.jl:46-49
+                gth = am;
+            }
+        }
+        a = c + ax * th;                                      // fact_samplers.jl:51 (mu = 0)
+        b = c100 + th * gth;                                  // fact_samplers.jl:52
+        told = s;
+        tau = s + zz_poisson_time_L(a, b, L2);                // sfact.jl:134,139
+    }
+    o.a = a; o.b = b; o.told = told; o.tau = tau; o.c = c;
+    o.k = k; o.nprop = nprop; o.nflip = nflip; o.flags = flags;
+    o.hdr0 = w.hdr0; o.hdr1 = w.hdr1; o.nitems = nitems;
+}
+
 // Entry points.  KIND 0: 5-point lattice (index arithmetic); KIND 1: general sparse columns.
 #define ZZ_KIND_GRID 0
 #define ZZ_KIND_CSR 1
@@ -578,6 +674,11 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
     ZzPool pool; uint32_t flags = 0;
     ZzOwn w;
     if (KIND == ZZ_KIND_GRID) {
+        if (MODE == ZZ_MODE_PLAIN && !MG) {   // lattice interior: the specialised evaluation
+            const int32_t M = g.grid_m, N = g.grid_n;
+            const int32_t col = j / M, row = j - col * M;
+            if (col > 0 && col < N - 1 && row > 0 && row < M - 1) { zz_process_interior(g, v, j, H, incl, w0, cur, first_iter, o); return; }
+        }
         ZzHood<5> hd;
         ZZ_SEG(0);
         zz_load_own(v, j, w);
@@ -625,7 +726,8 @@ ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double 
         if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, ZZ_MODE_LB>(g, v, j, H, incl, w0, cur, first_iter, o);
         else zz_process_node_k<ZZ_KIND_CSR, ZZ_MODE_LB>(g, v, j, H, incl, w0, cur, first_iter, o);
     } else {
-        if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, ZZ_MODE_PLAIN>(g, v, j, H, incl, w0, cur, first_iter, o);
+        if (g.grid_m && v.nranks <= 1) zz_process_node_k<ZZ_KIND_GRID, ZZ_MODE_PLAIN, false>(g, v, j, H, incl, w0, cur, first_iter, o);   // as the single-GPU kernel
+        else if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, ZZ_MODE_PLAIN>(g, v, j, H, incl, w0, cur, first_iter, o);
         else zz_process_node_k<ZZ_KIND_CSR, ZZ_MODE_PLAIN>(g, v, j, H, incl, w0, cur, first_iter, o);
     }
 }
