@@ -35,6 +35,17 @@ struct zzw_run {
 
 extern "C" {
 
+// exhaustive check of the multiply-shift lattice-column formula against the division, for tests
+int64_t zzw_check_grid_col(int32_t M, int64_t jmax)
+{
+    ZzGraph g; memset(&g, 0, sizeof g); g.grid_m = M; zz_grid_set_magic(g);
+    int64_t bad = 0;
+    for (int64_t j = 0; j <= jmax; ++j) bad += (zz_grid_col(g, (int32_t)j) != (int32_t)(j / M));
+    const int32_t edge[] = { 0x7fffffff, 0x7ffffffe, 0x40000000 };
+    for (int32_t j : edge) bad += (zz_grid_col(g, j) != j / M);
+    return bad;
+}
+
 zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const double* tnz, const double* h,
                    const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
                    const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
@@ -63,6 +74,7 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
     g.grid_m = (tag_limit & 0x80000000u) ? 0 : G.grid_m; g.grid_n = G.grid_n;  // top bit of tag_limit: force the CSR path
     tag_limit &= 0x7fffffffu;
     for (int q = 0; q < 5; ++q) g.grid_diag[q] = G.grid_diag[q];
+    zz_grid_set_magic(g);
     ZzView v; memset(&v, 0, sizeof v); v.nranks = 1; v.hi = (int32_t)d; v.shard = (int32_t)d; v.d = (int32_t)d; v.kin = kin.data(); v.flips = flips.data(); v.priv = priv.data();
     v.tau = tau.data(); v.kctr = kctr.data(); v.seed0 = seed[0]; v.seed1 = seed[1]; v.adapt = adapt; v.factor = factor; v.local_bound = local_bound;
     v.sticky = kappa ? 1 : 0; v.fth = (kappa || boom_sigma) ? fth.data() : nullptr; v.kappa = kappa;

@@ -105,3 +105,13 @@ def test_sticky_general_graph(zzb):
     c = 2.0 * Gt.colnorms() + 1
     ref = O.spdmp(Gt, Gt.scaled(0.9), 0.0, x0, th0, 15.0, c, h=h, mu=mu, kappa=kappa)
     O.assert_same_run(ref, O.window_sim(Gt, Gt.scaled(0.9), 0.0, x0, th0, 15.0, c, h=h, mu=mu, kappa=kappa))
+
+
+def test_lattice_column_multiply_shift_is_exact():
+    """zz_grid_col (j * magic >> shift) equals j // M for every coordinate the formula may see."""
+    import ctypes as C
+    L = O.wlib()
+    L.zzw_check_grid_col.restype = C.c_int64
+    L.zzw_check_grid_col.argtypes = [C.c_int32, C.c_int64]
+    for M in (1, 2, 3, 5, 7, 12, 100, 255, 256, 257, 1000, 1023, 1024, 1025, 4097, 46341, 65535, 65536, 1 << 20, (1 << 31) - 1):
+        assert L.zzw_check_grid_col(M, 3_000_000) == 0, M

@@ -67,7 +67,27 @@ struct ZzGraph {
     // follow from index arithmetic, no index/weight loads.  grid_m == 0 -> general CSR lists above.
     int32_t grid_m, grid_n;
     double grid_diag[5];   // diagonal entry by node degree (2, 3, 4), exactly as stored in the matrix
+    // j / grid_m for 0 <= j < 2^31 as one multiply and shift (zz_grid_set_magic / zz_grid_col)
+    uint64_t grid_magic;
+    int32_t grid_shift, grid_pad;
 };
+
+// Lattice column of coordinate j: floor(j / M) = (j * magic) >> shift with magic = floor(2^shift / M) + 1 and
+// shift = 31 + ceil(log2 M); exact for every 0 <= j < 2^31 (round-up method of Granlund & Montgomery; tested exhaustively
+// against the division for the lattice sizes of the test-suite).
+ZZ_HD void zz_grid_set_magic(ZzGraph& g)
+{
+    g.grid_magic = 0; g.grid_shift = 0; g.grid_pad = 0;
+    if (g.grid_m <= 0) return;
+    int l = 0;
+    while ((1LL << l) < (long long)g.grid_m) ++l;
+    g.grid_shift = 31 + l;
+    g.grid_magic = (uint64_t)((((unsigned __int128)1) << g.grid_shift) / (unsigned __int128)g.grid_m) + 1ULL;
+}
+ZZ_HD int32_t zz_grid_col(const ZzGraph& g, int32_t j)
+{
+    return (int32_t)(((uint64_t)(uint32_t)j * g.grid_magic) >> g.grid_shift);
+}
 
 struct ZzView {
     int32_t d;
@@ -128,6 +148,7 @@ struct ZzNodeOut {
     double viol_t, viol_l, viol_lb;
     uint32_t hdr0, hdr1;   // own flip-list headers as read at entry
     uint32_t nitems;       // timeline items processed by this evaluation (statistics of the host emulation)
+    uint32_t interior;     // evaluated by the lattice-interior path: all four readers exist
 };
 
 #if defined(__CUDA_ARCH__)

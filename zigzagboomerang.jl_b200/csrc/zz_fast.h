@@ -169,7 +169,7 @@ ZZ_HD void zz_gather_grid(const ZzGraph& g, const ZzView& v, int32_t j, uint32_t
                           ZzHood<5>& hd, ZzPool& pool, uint32_t& flags, ZzHoodMu<5>* hm = nullptr)
 {
     const int32_t M = g.grid_m, N = g.grid_n;
-    const int32_t col = j / M, row = j - col * M;
+    const int32_t col = zz_grid_col(g, j), row = j - col * M;
     int32_t idx[5]; uint32_t h0[5], h1[5];
     int n = 0;
     if (col > 0) idx[n++] = j - M;
@@ -656,7 +656,7 @@ ZZ_HD void zz_process_interior(const ZzGraph& g, const ZzView& v, int32_t j, dou
     }
     o.a = a; o.b = b; o.told = told; o.tau = tau; o.c = c;
     o.k = k; o.nprop = nprop; o.nflip = nflip; o.flags = flags;
-    o.hdr0 = w.hdr0; o.hdr1 = w.hdr1; o.nitems = nitems;
+    o.hdr0 = w.hdr0; o.hdr1 = w.hdr1; o.nitems = nitems; o.interior = 1u;
 }
 
 // Entry points.  KIND 0: 5-point lattice (index arithmetic); KIND 1: general sparse columns.
@@ -673,10 +673,11 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
 {
     ZzPool pool; uint32_t flags = 0;
     ZzOwn w;
+    o.interior = 0u;
     if (KIND == ZZ_KIND_GRID) {
         if (MODE == ZZ_MODE_PLAIN && !MG) {   // lattice interior: the specialised evaluation
             const int32_t M = g.grid_m, N = g.grid_n;
-            const int32_t col = j / M, row = j - col * M;
+            const int32_t col = zz_grid_col(g, j), row = j - col * M;
             if (col > 0 && col < N - 1 && row > 0 && row < M - 1) { zz_process_interior(g, v, j, H, incl, w0, cur, first_iter, o); return; }
         }
         ZzHood<5> hd;

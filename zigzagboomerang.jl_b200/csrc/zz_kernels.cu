@@ -331,12 +331,16 @@ __device__ __forceinline__ void zz_publish(const ZzParams& P, int32_t j, const Z
         // the appends of the whole warp share one atomicAdd per list (zz_append4)
         if (KIND == ZZ_KIND_GRID) {
             const int32_t M = P.g.grid_m, N = P.g.grid_n;
-            const int32_t col = j / M, row = j - col * M;
             int32_t kk[4];
+            if (o.interior) {   // all four readers exist
+                kk[0] = j - M; kk[1] = j - 1; kk[2] = j + 1; kk[3] = j + M;
+            } else {
+                const int32_t col = zz_grid_col(P.g, j), row = j - col * M;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const bool ok = (q == 0) ? (col > 0) : (q == 1) ? (row > 0) : (q == 2) ? (row < M - 1) : (col < N - 1);
-                kk[q] = ok ? j + ((q == 0) ? -M : (q == 1) ? -1 : (q == 2) ? 1 : M) : -1;
+                for (int q = 0; q < 4; ++q) {
+                    const bool ok = (q == 0) ? (col > 0) : (q == 1) ? (row > 0) : (q == 2) ? (row < M - 1) : (col < N - 1);
+                    kk[q] = ok ? j + ((q == 0) ? -M : (q == 1) ? -1 : (q == 2) ? 1 : M) : -1;
+                }
             }
             zz_mark4<MULTI>(P, kk, tagn, w0, nxt, ws, tl, tslot);
         } else {

@@ -327,6 +327,7 @@ int32_t zzb_problem_create_gaussian(zzb_problem_t* out, int64_t d, const int64_t
     p->g.h = hg.has_h ? p->h.as<double>() : nullptr; p->g.same = hg.same;
     p->g.grid_m = getenv("ZZB200_NO_GRID") ? 0 : hg.grid_m; p->g.grid_n = hg.grid_n;
     for (int q = 0; q < 5; ++q) p->g.grid_diag[q] = hg.grid_diag[q];
+    zz_grid_set_magic(p->g);
     *out = p;
     return ZZB_OK;
 }
