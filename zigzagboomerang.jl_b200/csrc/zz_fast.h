@@ -564,11 +564,12 @@ ZZ_HD void zz_boom_init(ZzHood<NB>& hd, const ZzHoodMu<NB>& hm, const ZzGraph& g
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Lattice interior (plain ZigZag, single GPU): the 5-point column {j-M, j-1, j, j+1, j+M} with weights {-1, -1, diag, -1, -1},
+// Lattice interior (plain ZigZag): the 5-point column {j-M, j-1, j, j+1, j+M} with weights {-1, -1, diag, -1, -1},
 // target == sampler matrix, no linear term, mu = 0.  Same arithmetic as zz_gather_grid + zz_timeline<5, false>, operation
 // for operation -- (-1) * x is written -x, gx - 0 is written gx, both exact -- with every flag test, bounds test and weight
 // load folded away: the common case costs about a third fewer instructions, which is what a lone warp in a late
 // relaxation pass is made of.  Neighbour positions follow the storage order of the column: 0, 1, (2 = self), 3, 4.
+template <bool MG>
 ZZ_HD void zz_process_interior(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0, uint32_t cur,
                                bool first_iter, ZzNodeOut& o)
 {
@@ -580,11 +581,11 @@ ZZ_HD void zz_process_interior(const ZzGraph& g, const ZzView& v, int32_t j, dou
 #pragma unroll
     for (int m = 0; m < 5; ++m) {
         nth[m] = 0.0; ntf[m] = 0.0; nxf[m] = 0.0; h0[m] = 0; h1[m] = 0;
-        if (m != 2) zz_ld_kin(v.kin + idx[m], nth[m], ntf[m], nxf[m], h0[m], h1[m]);
+        if (m != 2) zz_ld_kin(zz_kin_at<MG>(v, idx[m]), nth[m], ntf[m], nxf[m], h0[m], h1[m]);
     }
     ZzPool pool; pool.n = 0;
     uint32_t flags = 0;
-    if (!first_iter) zz_gather_flips<5, false, false>(v, idx, h0, h1, 5, 2, w0, cur, pool, flags);
+    if (!first_iter) zz_gather_flips<5, MG, false>(v, idx, h0, h1, 5, 2, w0, cur, pool, flags);
 
     const double diag = g.grid_diag[4];
     double th = w.th, tf = w.tf, xf = w.xf;
@@ -675,10 +676,10 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
     ZzOwn w;
     o.interior = 0u;
     if (KIND == ZZ_KIND_GRID) {
-        if (MODE == ZZ_MODE_PLAIN && !MG) {   // lattice interior: the specialised evaluation
+        if (MODE == ZZ_MODE_PLAIN) {   // lattice interior: the specialised evaluation
             const int32_t M = g.grid_m, N = g.grid_n;
             const int32_t col = zz_grid_col(g, j), row = j - col * M;
-            if (col > 0 && col < N - 1 && row > 0 && row < M - 1) { zz_process_interior(g, v, j, H, incl, w0, cur, first_iter, o); return; }
+            if (col > 0 && col < N - 1 && row > 0 && row < M - 1) { zz_process_interior<MG>(g, v, j, H, incl, w0, cur, first_iter, o); return; }
         }
         ZzHood<5> hd;
         ZZ_SEG(0);
