@@ -259,7 +259,7 @@ def run_ours(args):
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01d_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r01e_traffic.json")) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     except Exception:
         pass
