@@ -80,7 +80,7 @@ ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint
                            int n, int self, uint32_t w0, uint32_t cur, ZzPool& pool, uint32_t& flags)
 {
     pool.n = 0;
-    if (VEL) {   // sticky / Boomerang lists carry the velocity after each event (compile-time: the plain kernels stay small)
+    if constexpr (VEL) {   // sticky / Boomerang lists carry the velocity after each event (compile-time: the plain kernels stay small)
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
             if (m < n && m != self) {
@@ -93,38 +93,38 @@ ZZ_HD void zz_gather_flips(const ZzView& v, const int32_t (&idx)[NB], const uint
                 }
             }
         }
-        return;
-    }
-    // Plain lists: the first two entries of every non-empty neighbour list are fetched together (independent loads, one
-    // round trip) before anything is merged; longer lists (rare) continue entry by entry.  Insertion order -- neighbour by
-    // neighbour, entries ascending -- is unchanged, so the merged pool is the same.
-    uint32_t cnt[NB]; const double* fl[NB]; double f0[NB], f1[NB];
+    } else {
+        // Plain lists: the first two entries of every non-empty neighbour list are fetched together (independent loads, one
+        // round trip) before anything is merged; longer lists (rare) continue entry by entry.  Insertion order -- neighbour by
+        // neighbour, entries ascending -- is unchanged, so the merged pool is the same.
+        uint32_t cnt[NB]; const double* fl[NB]; double f0[NB], f1[NB];
 #pragma unroll
-    for (int m = 0; m < NB; ++m) {
-        cnt[m] = 0; fl[m] = nullptr; f0[m] = 0.0; f1[m] = 0.0;
-        if (m < n && m != self) {
-            int slot;
-            cnt[m] = zz_pick_slot(h0[m], h1[m], w0, cur, slot);
-            if (cnt[m]) fl[m] = zz_flips_at<MG>(v, idx[m]) + slot * ZZ_MAXFLIP;
+        for (int m = 0; m < NB; ++m) {
+            cnt[m] = 0; fl[m] = nullptr; f0[m] = 0.0; f1[m] = 0.0;
+            if (m < n && m != self) {
+                int slot;
+                cnt[m] = zz_pick_slot(h0[m], h1[m], w0, cur, slot);
+                if (cnt[m]) fl[m] = zz_flips_at<MG>(v, idx[m]) + slot * ZZ_MAXFLIP;
+            }
         }
-    }
 #pragma unroll
-    for (int m = 0; m < NB; ++m) {
-        if (cnt[m]) {
+        for (int m = 0; m < NB; ++m) {
+            if (cnt[m]) {
 #if defined(__CUDA_ARCH__)
-            const double2 u = __ldcg(reinterpret_cast<const double2*>(fl[m]));   // slots are 48-byte aligned
-            f0[m] = u.x; f1[m] = u.y;
+                const double2 u = __ldcg(reinterpret_cast<const double2*>(fl[m]));   // slots are 48-byte aligned
+                f0[m] = u.x; f1[m] = u.y;
 #else
-            f0[m] = fl[m][0]; f1[m] = fl[m][1];
+                f0[m] = fl[m][0]; f1[m] = fl[m][1];
 #endif
+            }
         }
-    }
 #pragma unroll
-    for (int m = 0; m < NB; ++m) {
-        if (cnt[m]) {
-            zz_pool_add<false>(pool, f0[m], m, flags);
-            if (cnt[m] > 1) zz_pool_add<false>(pool, f1[m], m, flags);
-            for (uint32_t q = 2; q < cnt[m]; ++q) zz_pool_add<false>(pool, zz_ld(fl[m] + q), m, flags);
+        for (int m = 0; m < NB; ++m) {
+            if (cnt[m]) {
+                zz_pool_add<false>(pool, f0[m], m, flags);
+                if (cnt[m] > 1) zz_pool_add<false>(pool, f1[m], m, flags);
+                for (uint32_t q = 2; q < cnt[m]; ++q) zz_pool_add<false>(pool, zz_ld(fl[m] + q), m, flags);
+            }
         }
     }
 }
