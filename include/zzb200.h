@@ -8,6 +8,8 @@
  *                                 becomes the CSC arrays of the target precision (+ optional linear term h);
  *                                 `ZigZag(G, mu)` (src/types.jl:19-27) becomes the CSC arrays of Z.Gamma and Z.mu;
  *                                 also performs the neighbourhood setup of src/sfact.jl:170-178
+ *   zzb_problem_create_logistic   the (grad_phi_moving closure, SelfMoving(), A, At, mu, y, ny, k) arguments of the subsampled
+ *                                 logistic regression, scripts/logistic.jl:78-107,167 (src/sfact.jl:64-68)
  *   zzb_spdmp_run                 spdmp(grad, t0, x0, th0, T, c, Z, args...; factor, adapt, seed)  src/sfact.jl:162-214
  *                                 and pdmp(...) src/sfact.jl:236 (same event law; the All() graph only changes which
  *                                 coordinates the CPU code moves eagerly)
@@ -80,6 +82,20 @@ int32_t zzb_event_elapsed_ms(float* ms);
  * grad phi_i(x) = sum_k tgt[k,i] x_k - hvec[i];  bound uses bnd (Z.Gamma) and bnd_mu (Z.mu), fact_samplers.jl:50-54. */
 int32_t zzb_problem_create_gaussian(zzb_problem_t* out, int64_t d,
                                     const int64_t* colptr, const int64_t* rowval, const double* nzval, const double* hvec,
+                                    const int64_t* bnd_colptr, const int64_t* bnd_rowval, const double* bnd_nzval,
+                                    const double* bnd_mu);
+/* Problem with the subsampled logistic-regression target of scripts/logistic.jl (BASELINE config 3): replaces the closure
+ * `grad_phi_moving(t, x, theta, i, t', F, A, At, mu, y, ny, k) = gamma0*x[i] - fdot_moving(...)` (scripts/logistic.jl:78-107)
+ * that the reference passes to spdmp together with `SelfMoving(), A, At, mu, y, ny, k` (:167; ExtendedForm dispatch,
+ * src/sfact.jl:64-68, src/types.jl:103-119).  A is the n x d design matrix and At = SparseMatrixCSC(A') (both Julia-layout
+ * CSC, passed as they are), y / ny the successes / failures per design row as Float64, mu_cv the control-variate point
+ * (the mode), gamma0 the prior precision, k the number of design rows drawn per evaluation.  bnd_* / bnd_mu are Z.Gamma /
+ * Z.mu of the sampler (the script's Zdrop).  The k row indices are drawn from the proposing coordinate's counter stream
+ * (the reference uses Julia's global RNG, :83,86).  Run with zzb_spdmp_run / the staged calls; plain ZigZag only. */
+int32_t zzb_problem_create_logistic(zzb_problem_t* out, int64_t d, int64_t n,
+                                    const int64_t* a_colptr, const int64_t* a_rowval, const double* a_nzval,
+                                    const int64_t* at_colptr, const int64_t* at_rowval, const double* at_nzval,
+                                    const double* y, const double* ny, const double* mu_cv, double gamma0, int64_t k,
                                     const int64_t* bnd_colptr, const int64_t* bnd_rowval, const double* bnd_nzval,
                                     const double* bnd_mu);
 int32_t zzb_problem_free(zzb_problem_t p);

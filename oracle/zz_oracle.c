@@ -325,11 +325,55 @@ static double next_time(double t, double a, double b, double Delta, double u, ch
     return t + dt;
 }
 
-zzo_run *zzo_spdmp(int64_t d,
+/* ---- subsampled logistic target, scripts/logistic.jl (config 3) --------------------------------
+ * grad phi_j = gamma0*x[j] - fdot_moving(A, At, j, t, x, theta, t', F, mu, y, ny, k)   (:78-95,107), called through the
+ * SelfMoving / ExtendedForm signature (src/sfact.jl:68).  A is the n x d design matrix (CSC), At = A' (CSC: column r =
+ * row r of A), y / ny the successes / failures per row, mu the mode (control variate), k the number of rows drawn.
+ * The reference draws the row indices from Julia's GLOBAL RNG (Random.SamplerRangeNDL, :83,86): mode seq uses a second
+ * xoroshiro stream for them, mode ctr the proposing coordinate's own counter stream (k draws before the thinning draw). */
+typedef struct {
+    int64_t n; csc A, At; const double *y, *ny, *mu; double gamma0; int64_t k; xoro grng;
+} logit;
+
+static double sigmoid_(double x) { return 1.0 / (1.0 + zz_exp(-x)); } /* :34 inv(one(x) + exp(-x)) */
+static double sigmoidn_(double x) { return sigmoid_(-x); }              /* :56 */
+static double nsigmoid_(double x) { return -sigmoid_(x); }              /* :57 */
+
+static double logit_grad(ctx *z, logit *L, int64_t j, double tp)
+{
+    const int64_t r0 = L->A.colptr[j - 1], l = L->A.colptr[j] - r0; /* nzrange(A, j) */
+    double s = 0.0;
+    for (int64_t it = 0; it < L->k; ++it) {
+        double ur = (z->mode & ZZO_RNG_CTR) ? draw(z, j) : xoro_rand(&L->grng);
+        int64_t i = (int64_t)(ur * (double)l);
+        if (i >= l) i = l - 1;
+        i += r0; /* 1-based position in rowvals(A) */
+        int64_t row = L->A.rowval[i - 1];
+        double val = L->A.nzval[i - 1];
+        double u = 0.0; /* idot_moving!(At, row, t, x, theta, t', F), src/common.jl:33-42 */
+        for (int64_t q = L->At.colptr[row - 1]; q < L->At.colptr[row]; ++q) {
+            int64_t m = L->At.rowval[q - 1];
+            if (!(z->mode & ZZO_ARITH_LAZY)) { /* smove_forward!(m, t, x, theta, t', F), sfact.jl:14-16 */
+                z->x[m - 1] = z->x[m - 1] + z->th[m - 1] * (tp - z->t[m - 1]);
+                z->t[m - 1] = tp;
+            }
+            u += L->At.nzval[q - 1] * pos_at(z, m, tp);
+        }
+        double lk = (double)l / (double)L->k;
+        s += lk * val * L->y[row - 1] * sigmoidn_(u);   /* :87 */
+        s += lk * val * L->ny[row - 1] * nsigmoid_(u);  /* :88 */
+        double u0 = idot(&L->At, row, L->mu);           /* :89 */
+        s -= lk * val * L->y[row - 1] * sigmoidn_(u0);  /* :90 */
+        s -= lk * val * L->ny[row - 1] * nsigmoid_(u0); /* :91 */
+    }
+    return L->gamma0 * pos_at(z, j, tp) - s;            /* :107 */
+}
+
+static zzo_run *spdmp_impl(int64_t d,
                    const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
                    const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
                    double t0, const double *x0, const double *th0, double T, const double *c_in,
-                   const uint64_t *seed, int adapt, double factor, int mode)
+                   const uint64_t *seed, int adapt, double factor, int mode, logit *lg)
 {
     zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run));
     ctx zs; ctx *z = &zs; memset(z, 0, sizeof(ctx));
@@ -391,8 +435,12 @@ zzo_run *zzo_spdmp(int64_t d,
                 h_set(&Q, i, next_time(tr, z->ba[i - 1], z->bb[i - 1], Delta, draw(z, i), &renew[i - 1]));
                 continue;
             }
-            double gi = idot_x(z, &z->tg, i, tp);           /* :118, user closure = idot(Gamma,i,x) */
-            if (h) gi = gi - h[i - 1];
+            double gi;
+            if (lg) gi = logit_grad(z, lg, i, tp);          /* :118 through the SelfMoving closure (sfact.jl:68) */
+            else {
+                gi = idot_x(z, &z->tg, i, tp);              /* :118, user closure = idot(Gamma,i,x) */
+                if (h) gi = gi - h[i - 1];
+            }
             double ti = lazy ? tp : z->t[i - 1];
             double l = zz_pos(gi * z->th[i - 1]);                                   /* :119, fact_samplers.jl:28-30 */
             double lb = zz_pos(z->ba[i - 1] + z->bb[i - 1] * (ti - z->t_old[i - 1])); /* sfact.jl:70 */
@@ -445,6 +493,44 @@ zzo_run *zzo_spdmp(int64_t d,
     free(z->g2ptr); free(z->g2idx); free(renew);
     return r;
 }
+
+zzo_run *zzo_spdmp(int64_t d,
+                   const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
+                   const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
+                   double t0, const double *x0, const double *th0, double T, const double *c_in,
+                   const uint64_t *seed, int adapt, double factor, int mode)
+{
+    return spdmp_impl(d, tg_colptr, tg_rowval, tg_nzval, h, bd_colptr, bd_rowval, bd_nzval, mu, t0, x0, th0, T, c_in,
+                      seed, adapt, factor, mode, NULL);
+}
+
+/* spdmp(grad_phi_moving, t0, x0, th0, T, c, Zdrop, SelfMoving(), A, At, mu, y, ny, k; adapt, factor), scripts/logistic.jl:167.
+ * (bd_*, bd_mu) = Zdrop.Gamma, Zdrop.mu; A is n x d, At its transpose (both Julia-layout CSC); mu_cv the control-variate point. */
+zzo_run *zzo_spdmp_logistic(int64_t d, int64_t n,
+                   const int64_t *a_colptr, const int64_t *a_rowval, const double *a_nzval,
+                   const int64_t *at_colptr, const int64_t *at_rowval, const double *at_nzval,
+                   const double *y, const double *ny, const double *mu_cv, double gamma0, int64_t k,
+                   const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *bd_mu,
+                   double t0, const double *x0, const double *th0, double T, const double *c_in,
+                   const uint64_t *seed, int adapt, double factor, int mode)
+{
+    logit L; memset(&L, 0, sizeof L);
+    L.n = n; L.A.colptr = a_colptr; L.A.rowval = a_rowval; L.A.nzval = a_nzval;
+    L.At.colptr = at_colptr; L.At.rowval = at_rowval; L.At.nzval = at_nzval;
+    L.y = y; L.ny = ny; L.mu = mu_cv; L.gamma0 = gamma0; L.k = k;
+    L.grng.x = seed[0] ^ 0x9E3779B97F4A7C15ULL; L.grng.y = seed[1] ^ 0xD1342543DE82EF95ULL;
+    if ((mode & (ZZO_LOCAL_BOUND | ZZO_GRAPH_ALL)) || k < 1) {
+        zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run)); r->d = 0; r->status = ZZO_E_ARG; return r;
+    }
+    for (int64_t j = 0; j < d; ++j)
+        if (a_colptr[j + 1] == a_colptr[j]) { /* rand(sampler) on an empty range throws upstream */
+            zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run)); r->d = 0; r->status = ZZO_E_ARG; return r;
+        }
+    /* the target matrix arguments are unused with a logistic target: pass the bound matrix */
+    return spdmp_impl(d, bd_colptr, bd_rowval, bd_nzval, NULL, bd_colptr, bd_rowval, bd_nzval, bd_mu, t0, x0, th0, T, c_in,
+                      seed, adapt, factor, mode, &L);
+}
+double zzo_exp(double x) { return zz_exp(x); }
 
 /* =====================================================================================================
  * Sticky ZigZag, sspdmp (src/ss_fact.jl:10-217): coordinates freeze when they hit 0 and thaw after an Exp(kappa_i) time.

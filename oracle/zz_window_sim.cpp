@@ -16,6 +16,7 @@
 #include "../zigzagboomerang.jl_b200/csrc/zz_core.h"
 #include "../zigzagboomerang.jl_b200/csrc/zz_ctl.h"
 #include "../zigzagboomerang.jl_b200/csrc/zz_host_graph.h"
+#include "../zigzagboomerang.jl_b200/csrc/zz_host_logit.h"
 
 struct zzw_event { double t; int64_t i; double x; double th; };
 
@@ -32,6 +33,12 @@ struct zzw_run {
     std::vector<int64_t> item_hist = std::vector<int64_t>(64, 0);  // timeline items processed, summed per pass index
     std::string msg;
 };
+
+static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, const double* tnz, const double* h,
+                   const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
+                   const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
+                   int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound, const double* kappa,
+                   const double* boom_sigma, double boom_lambdaref, double boom_rho, const ZzHostLogit* hl);
 
 extern "C" {
 
@@ -52,6 +59,33 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
                    int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound, const double* kappa,
                    const double* boom_sigma, double boom_lambdaref, double boom_rho)
 {
+    return zzw_impl(d, tcp, trv, tnz, h, bcp, brv, bnz, mu, t0, x0, th0, T, c_in, seed, adapt, factor, delta0, target_frac,
+                    tag_limit, local_bound, kappa, boom_sigma, boom_lambdaref, boom_rho, nullptr);
+}
+
+// the schedule with the subsampled logistic target (zz_logit.h; arguments as zzb_problem_create_logistic + zzb_spdmp_run)
+zzw_run* zzw_spdmp_logistic(int64_t d, int64_t n, const int64_t* acp, const int64_t* arv, const double* anz,
+                            const int64_t* atcp, const int64_t* atrv, const double* atnz, const double* y, const double* ny,
+                            const double* mu_cv, double gamma0, int64_t k,
+                            const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
+                            const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
+                            int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit)
+{
+    ZzHostLogit hl;
+    std::string e = zz_build_logit(hl, d, n, acp, arv, anz, atcp, atrv, atnz, y, ny, mu_cv, gamma0, k);
+    if (!e.empty()) { zzw_run* r = new zzw_run(); r->d = d; r->status = 4; r->msg = e; return r; }
+    return zzw_impl(d, hl.dep_cp.data(), hl.dep_rv.data(), hl.dep_nz.data(), nullptr, bcp, brv, bnz, mu, t0, x0, th0, T, c_in,
+                    seed, adapt, factor, delta0, target_frac, tag_limit | 0x80000000u, 0, nullptr, nullptr, 0.0, 0.0, &hl);
+}
+
+}  // extern "C"
+
+static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, const double* tnz, const double* h,
+                   const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
+                   const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
+                   int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound, const double* kappa,
+                   const double* boom_sigma, double boom_lambdaref, double boom_rho, const ZzHostLogit* hl)
+{
     zzw_run* r = new zzw_run();
     r->d = d;
     ZzHostGraph G;
@@ -70,7 +104,13 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
     r->acc.assign(d, 0); r->s1.assign(d, 0.0); r->s2.assign(d, 0.0);
 
     ZzGraph g; g.nptr = G.nptr.data(); g.nidx = G.nidx.data(); g.nwt = G.nwt.data(); g.nwb = G.nwb.data();
-    g.nfl = G.nfl.data(); g.gmu = G.gmu.data(); g.h = G.has_h ? G.h.data() : nullptr; g.same = G.same;
+    g.nfl = G.nfl.data(); g.gmu = G.gmu.data(); g.h = G.has_h ? G.h.data() : nullptr; g.same = hl ? 0 : G.same;
+    ZzLogit lg; memset(&lg, 0, sizeof lg);
+    if (hl) {
+        lg.acp = hl->acp.data(); lg.arow = hl->arow.data(); lg.aval = hl->aval.data(); lg.rp = hl->rp.data();
+        lg.rcol = hl->rcol.data(); lg.rval = hl->rval.data(); lg.y = hl->y.data(); lg.ny = hl->ny.data(); lg.u0 = hl->u0.data();
+        lg.gamma0 = hl->gamma0; lg.k = hl->k; lg.n = hl->n;
+    }
     g.grid_m = (tag_limit & 0x80000000u) ? 0 : G.grid_m; g.grid_n = G.grid_n;  // top bit of tag_limit: force the CSR path
     tag_limit &= 0x7fffffffu;
     for (int q = 0; q < 5; ++q) g.grid_diag[q] = G.grid_diag[q];
@@ -146,7 +186,8 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
                 if (tj < ctl.H || (ctl.incl && tj == ctl.H)) {
                     // dirtied already by an earlier node of this pass? then it is in `next` as well; fine.
                     if (dstamp[j] < w0) { dstamp[j] = cur; touched.push_back((int32_t)j); }
-                    zz_process_node(g, v, (int32_t)j, ctl.H, ctl.incl, w0, cur, true, o);
+                    if (hl) zz_process_node_logit(g, v, lg, (int32_t)j, ctl.H, ctl.incl, w0, cur, true, o);
+                    else zz_process_node(g, v, (int32_t)j, ctl.H, ctl.incl, w0, cur, true, o);
                     handle((int32_t)j, o, w0, cur);
                 }
             }
@@ -158,7 +199,8 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
                 r->pass_hist[std::min<int64_t>(it, 63)] += (int64_t)wl.size();
                 for (int32_t j : wl) {
                     o.nitems = 0;
-                    zz_process_node(g, v, j, ctl.H, ctl.incl, w0, cur, false, o);
+                    if (hl) zz_process_node_logit(g, v, lg, j, ctl.H, ctl.incl, w0, cur, false, o);
+                    else zz_process_node(g, v, j, ctl.H, ctl.incl, w0, cur, false, o);
                     r->item_hist[std::min<int64_t>(it, 63)] += o.nitems;
                     handle(j, o, w0, cur);
                 }
@@ -227,6 +269,8 @@ finish:
     for (int64_t j = 0; j < d; ++j) { r->t[j] = kin[j].tf; r->x[j] = kin[j].xf; r->th[j] = kin[j].theta; r->c[j] = priv[j].c; }
     return r;
 }
+
+extern "C" {
 
 int zzw_status(const zzw_run* r) { return r->status; }
 void zzw_error_info(const zzw_run* r, int64_t* i, double* t, double* l, double* lb) { *i = r->err_i; *t = r->err_t; *l = r->err_l; *lb = r->err_lb; }

@@ -37,13 +37,20 @@ def case_inputs(zzb, name):
         diag = G.to_scipy().diagonal()
         return dict(G=G, Zg=G, x0=rng.standard_normal(G.n), th0=rng.standard_normal(G.n) / np.sqrt(diag), c=G.colnorms(), T=6.0,
                     seed=(2, 3), kind="boomerang", boom=(diag ** -0.5, 5.0, 0.2))
+    if name == "logistic26":         # scripts/logistic.jl in small: subsampled logistic regression, adapt = true, factor = 5
+        import logistic_cases as LC
+        return dict(kind="logistic", cfg=LC.make(zzb, (4, 4), 2, 10, 3), T=30.0, seed=(5, 6))
     raise KeyError(name)
 
 
-CASES = ["gmrf16_T3", "gmrf12_tight", "spd8_adapt", "localbound16", "sticky12", "boomerang12"]
+CASES = ["gmrf16_T3", "gmrf12_tight", "spd8_adapt", "localbound16", "sticky12", "boomerang12", "logistic26"]
 
 
 def run_oracle(O, k):
+    if k["kind"] == "logistic":
+        import logistic_cases as LC
+        r = LC.run_oracle(O, k["cfg"], k["T"], seed=k["seed"])
+        return summary(r.events, r.num, r.acc)
     mode = O.PARITY_MODE | (O.LOCAL_BOUND if k["kind"] == "localbound" else 0)
     r = O.spdmp(k["G"], k["Zg"], 0.0, k["x0"], k["th0"], k["T"], k["c"], seed=k["seed"], mode=mode, adapt=k.get("adapt", False),
                 kappa=k.get("kappa"), boom=k.get("boom"))
@@ -51,6 +58,10 @@ def run_oracle(O, k):
 
 
 def run_device(zzb, k):
+    if k["kind"] == "logistic":
+        import logistic_cases as LC
+        r, _ = LC.run_device(zzb, k["cfg"], k["T"], seed=k["seed"])
+        return summary(r.events, r.num, r.acc)
     n = k["G"].n
     tgt = zzb.GaussianPotential(k["G"])
     if k["kind"] == "sticky":

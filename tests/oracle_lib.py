@@ -29,8 +29,8 @@ def lib():
     global _lib
     if _lib is None:
         so = os.path.join(ORACLE_DIR, "libzzoracle.so")
-        src = os.path.join(ORACLE_DIR, "zz_oracle.c")
-        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        srcs = [os.path.join(ORACLE_DIR, "zz_oracle.c"), os.path.join(ROOT, "zigzagboomerang.jl_b200", "csrc", "zz_math.h")]
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             build()
         L = C.CDLL(so)
         L.zzo_spdmp.restype = C.c_void_p
@@ -45,6 +45,11 @@ def lib():
         L.zzo_parallel_spdmp.restype = C.c_void_p
         L.zzo_parallel_spdmp.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
                                          C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_double]
+        L.zzo_spdmp_logistic.restype = C.c_void_p
+        L.zzo_spdmp_logistic.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 9 + [C.c_double, C.c_int64] + [C.c_void_p] * 4 + [
+            C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
+        L.zzo_exp.restype = C.c_double
+        L.zzo_exp.argtypes = [C.c_double]
         L.zzo_sincos.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
         L.zzo_randn.restype = C.c_double
         L.zzo_randn.argtypes = [C.c_double, C.c_double]
@@ -92,19 +97,27 @@ def block_diagonal(G, K):
 
 
 def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
-          mode=PARITY_MODE, kappa=None, boom=None, parallel=None):
+          mode=PARITY_MODE, kappa=None, boom=None, parallel=None, logistic=None):
     """Run the oracle.  ``target`` / ``bound`` are problems.CSC (target precision and the sampler's Z.Gamma).
     ``parallel = (K, Delta)`` runs the multithreaded parallel_spdmp (src/parallel.jl) on K threads.
     With ``kappa`` (thaw rates) the sticky sampler sspdmp (src/ss_fact.jl) is run instead of spdmp; with
     ``boom = (sigma, lambdaref, rho)`` the factorised Boomerang (F::FactBoomerang in src/sfact.jl)."""
     L = lib()
-    d = target.n
+    d = bound.n
     f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     x0, theta0, c = f8(x0), f8(theta0), f8(c)
     mu = np.zeros(d) if mu is None else f8(mu)
     h = None if h is None else f8(h)
     sd = np.array(seed, dtype=np.uint64)
-    if parallel is not None:   # (K threads, Delta): parallel_spdmp of src/parallel.jl; `bound` must be block diagonal
+    if logistic is not None:   # dict(A, At, y, ny, mu, gamma0, k): the subsampled logistic target of scripts/logistic.jl (`target` unused)
+        lg = logistic
+        A, At = lg["A"], lg["At"]
+        ly, lny, lmu = f8(lg["y"]), f8(lg["ny"]), f8(lg["mu"])
+        r = L.zzo_spdmp_logistic(d, A.nrows, _p(A.colptr), _p(A.rowval), _p(A.nzval), _p(At.colptr), _p(At.rowval), _p(At.nzval),
+                                 _p(ly), _p(lny), _p(lmu), float(lg["gamma0"]), int(lg["k"]),
+                                 _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
+                                 float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor), int(mode))
+    elif parallel is not None:   # (K threads, Delta): parallel_spdmp of src/parallel.jl; `bound` must be block diagonal
         r = L.zzo_parallel_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
                                  _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
                                  float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor),
@@ -162,7 +175,7 @@ def wlib():
     if _wlib is None:
         so = os.path.join(ORACLE_DIR, "libzzwindowsim.so")
         srcs = [os.path.join(ORACLE_DIR, "zz_window_sim.cpp")] + [
-            os.path.join(ROOT, "zigzagboomerang.jl_b200", "csrc", f) for f in ("zz_core.h", "zz_ctl.h", "zz_host_graph.h", "zz_math.h")]
+            os.path.join(ROOT, "zigzagboomerang.jl_b200", "csrc", f) for f in ("zz_core.h", "zz_fast.h", "zz_logit.h", "zz_ctl.h", "zz_host_graph.h", "zz_host_logit.h", "zz_math.h")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             build()
         L = C.CDLL(so)
@@ -170,6 +183,9 @@ def wlib():
         L.zzw_spdmp.argtypes = [C.c_int64] + [C.c_void_p] * 8 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double,
                                 C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_int, C.c_void_p,
                                 C.c_void_p, C.c_double, C.c_double]
+        L.zzw_spdmp_logistic.restype = C.c_void_p
+        L.zzw_spdmp_logistic.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 9 + [C.c_double, C.c_int64] + [C.c_void_p] * 4 + [
+            C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint32]
         L.zzw_status.argtypes = [C.c_void_p]
         L.zzw_trace_len.restype = C.c_int64
         L.zzw_trace_len.argtypes = [C.c_void_p]
@@ -187,20 +203,30 @@ def wlib():
 
 
 def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
-               delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False, kappa=None, boom=None):
+               delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False, kappa=None, boom=None, logistic=None):
     L = wlib()
-    d = target.n
+    d = bound.n
     f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     x0, theta0, c = f8(x0), f8(theta0), f8(c)
     mu = np.zeros(d) if mu is None else f8(mu)
     h = None if h is None else f8(h)
     sd = np.array(seed, dtype=np.uint64)
-    r = L.zzw_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
-                    _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
-                    float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor),
-                    float(delta0), float(target_frac), int(tag_limit), int(bool(local_bound)),
-                    _p(None if kappa is None else f8(kappa)),
-                    _p(None if boom is None else f8(boom[0])), 0.0 if boom is None else float(boom[1]), 0.0 if boom is None else float(boom[2]))
+    if logistic is not None:
+        lg = logistic
+        A, At = lg["A"], lg["At"]
+        ly, lny, lmu = f8(lg["y"]), f8(lg["ny"]), f8(lg["mu"])
+        r = L.zzw_spdmp_logistic(d, A.nrows, _p(A.colptr), _p(A.rowval), _p(A.nzval), _p(At.colptr), _p(At.rowval), _p(At.nzval),
+                                 _p(ly), _p(lny), _p(lmu), float(lg["gamma0"]), int(lg["k"]),
+                                 _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
+                                 float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor),
+                                 float(delta0), float(target_frac), int(tag_limit))
+    else:
+        r = L.zzw_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
+                        _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
+                        float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor),
+                        float(delta0), float(target_frac), int(tag_limit), int(bool(local_bound)),
+                        _p(None if kappa is None else f8(kappa)),
+                        _p(None if boom is None else f8(boom[0])), 0.0 if boom is None else float(boom[1]), 0.0 if boom is None else float(boom[2]))
     try:
         st = L.zzw_status(r)
         if st == 3:

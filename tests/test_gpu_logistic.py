@@ -1,0 +1,64 @@
+"""Config 3 of BASELINE.json on the device: sparse logistic regression, subsampled ZigZag (scripts/logistic.jl) through
+zzb_problem_create_logistic + zzb_spdmp_run, bit for bit against the CPU oracle (mode ctr|lazy)."""
+import numpy as np
+import pytest
+
+import logistic_cases as LC
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", LC.SMALL)
+def test_small_designs_bit_exact(gpu, case):
+    *design, T = case
+    cfg = LC.make(gpu, *design)
+    ref = LC.run_oracle(O, cfg, T)
+    got, Xi = LC.run_device(gpu, cfg, T)
+    O.assert_same_run(ref, got)
+    assert (got.c != cfg["c"]).any()                       # adapt = true multiplied some bounds by `factor`
+    m1, m2 = Xi.moments
+    assert np.allclose(m1, ref.m1, rtol=1e-12, atol=1e-300) and np.allclose(m2, ref.m2, rtol=1e-12, atol=1e-300)
+
+
+def test_window_policy_and_tag_rebase_do_not_change_results(gpu):
+    *design, T = LC.SMALL[1]
+    cfg = LC.make(gpu, *design)
+    ref = LC.run_oracle(O, cfg, T)
+    for tune in (dict(delta0=1e-3, target_frac=0.1), dict(delta0=2.0, target_frac=4.0, tag_limit=40), dict(grid=3)):
+        got, _ = LC.run_device(gpu, cfg, T, tune=tune)
+        O.assert_same_run(ref, got)
+
+
+def test_bound_violation_error(gpu):
+    """adapt = false with the script's c = 0.01: error("Tuning parameter `c` too small."), sfact.jl:124."""
+    cfg = LC.make(gpu, *LC.SMALL[0][:4])
+    with pytest.raises(gpu.BoundError, match="Tuning parameter `c` too small"):
+        LC.run_device(gpu, cfg, 20.0, adapt=False)
+
+
+def test_full_size_config3_bit_exact(gpu):
+    """n = 8840, p = 442, k = 10, c = 0.01, adapt = true, factor = 5 (scripts/logistic.jl:21,148,167; README.md:50)."""
+    cfg = LC.make(gpu, *LC.FULL)
+    T = 25.0
+    ref = LC.run_oracle(O, cfg, T)
+    got, Xi = LC.run_device(gpu, cfg, T)
+    O.assert_same_run(ref, got)
+    assert len(got.events) > 5000
+    print(f"config 3: {len(got.events)} events, {got.num} proposals in {Xi.device_ms:.1f} ms on the device "
+          f"({ref.loop_seconds * 1e3:.1f} ms in the oracle); stats {Xi.stats}")
+
+
+def test_refuses_unsupported_combinations(gpu):
+    cfg = LC.make(gpu, *LC.SMALL[0][:4])
+    lg = cfg["logistic"]
+    grad = gpu.LogisticSubsampled(lg["A"], lg["At"], lg["y"], lg["ny"], lg["mu"], lg["gamma0"], lg["k"])
+    Z = gpu.ZigZag(cfg["Gamma_drop"], cfg["mu"])
+    with pytest.raises(NotImplementedError):
+        gpu.spdmp(grad, 0.0, cfg["x0"], cfg["theta0"], 1.0, gpu.LocalBound(cfg["c"]), Z)
+    prob = gpu.Problem(grad, Z)
+    with pytest.raises(gpu.ZZBError):
+        gpu.Run(prob, kappa=np.ones(cfg["p"]))
+    bad = gpu.LogisticSubsampled(lg["A"], lg["A"], lg["y"], lg["ny"], lg["mu"], lg["gamma0"], lg["k"])   # At is not A'
+    with pytest.raises(gpu.ZZBError):
+        gpu.Problem(bad, Z)

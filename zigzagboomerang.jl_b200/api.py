@@ -33,6 +33,14 @@ class Matched:
     """`Matched()` neighbourhood marker (src/sfact.jl:3-4)."""
 
 
+class ExtendedForm:
+    """`ExtendedForm()` / `SelfMoving()` marker (src/types.jl:103-119): the closure takes the extended argument list and moves
+    the coordinates it needs itself.  On the device path positions are flip-anchored, so the marker only documents intent."""
+
+
+SelfMoving = ExtendedForm
+
+
 class ZigZag:
     """``ZigZag(Gamma, mu, sigma=diag(Gamma).^(-0.5); lambdaref=0.0, rho=0.0)`` (src/types.jl:19-27)."""
 
@@ -90,6 +98,31 @@ class GaussianPotential:
         for p in range(G.colptr[i - 1] - 1, G.colptr[i] - 1):
             s += G.nzval[p] * x[G.rowval[p] - 1]
         return s - (0.0 if self.h is None else self.h[i - 1])
+
+
+class LogisticSubsampled:
+    """Target descriptor for the subsampled logistic regression of scripts/logistic.jl: stands for the closure
+    ``grad_phi_moving(t, x, theta, i, t', F, A, At, mu, y, ny, k) = gamma0*x[i] - fdot_moving(...)`` (:78-107) together with
+    the arguments ``SelfMoving(), A, At, mu, y, ny, k`` the reference forwards to it (:167).  ``A`` / ``At`` are
+    :class:`problems.RectCSC` (design matrix and its transpose).  Calling it evaluates the FULL-data partial derivative
+    ``grad_phi(x, i, A, At, y, ny)`` (:104) -- the expectation of the subsampled estimate."""
+
+    def __init__(self, A, At, y, ny, mu, gamma0: float = 0.01, k: int = 10):
+        self.A, self.At = A, (At if At is not None else A.transpose())
+        self.y, self.ny, self.mu = f8(y), f8(ny), f8(mu)
+        self.gamma0, self.k = float(gamma0), int(k)
+
+    def __call__(self, x, i, *args):  # 1-based i
+        A, At = self.A, self.At
+        s = 0.0
+        for p in range(A.colptr[i - 1] - 1, A.colptr[i] - 1):
+            row = A.rowval[p]
+            u = 0.0
+            for q in range(At.colptr[row - 1] - 1, At.colptr[row] - 1):
+                u += At.nzval[q] * x[At.rowval[q] - 1]
+            sg = 1.0 / (1.0 + np.exp(-u))
+            s += A.nzval[p] * self.y[row - 1] * (1.0 - sg) - A.nzval[p] * self.ny[row - 1] * sg
+        return self.gamma0 * x[i - 1] - s
 
 
 class FactTrace:
@@ -227,9 +260,20 @@ def subtrace(tr: FactTrace, J):
 class Problem:
     """Device-resident problem: target potential + sampler matrices (``zzb_problem_create_gaussian``)."""
 
-    def __init__(self, target: GaussianPotential, Z: ZigZag):
+    def __init__(self, target, Z: ZigZag):
         _capi.init()
         self.target, self.Z = target, Z
+        if isinstance(target, LogisticSubsampled):   # zzb_problem_create_logistic
+            A, At, Gb = target.A, target.At, Z.Gamma
+            if A.ncols != Gb.n:
+                raise ValueError("design matrix and sampler dimensions differ")
+            self.d = Gb.n
+            self._h = C.c_void_p()
+            check(_capi.lib().zzb_problem_create_logistic(
+                C.byref(self._h), self.d, A.nrows, ptr(A.colptr), ptr(A.rowval), ptr(A.nzval), ptr(At.colptr), ptr(At.rowval),
+                ptr(At.nzval), ptr(target.y), ptr(target.ny), ptr(target.mu), target.gamma0, target.k,
+                ptr(Gb.colptr), ptr(Gb.rowval), ptr(Gb.nzval), ptr(Z.mu)))
+            return
         if target.Gamma.n != Z.Gamma.n:
             raise ValueError("target and sampler dimensions differ")
         self.d = target.Gamma.n
@@ -398,9 +442,11 @@ class Run:
 def _as_problem(grad, F):
     if isinstance(grad, Problem):
         return grad, False
-    if not isinstance(grad, GaussianPotential):
-        raise TypeError("the B200 path needs a target descriptor (GaussianPotential), not a closure: "
+    if not isinstance(grad, (GaussianPotential, LogisticSubsampled)):
+        raise TypeError("the B200 path needs a target descriptor (GaussianPotential / LogisticSubsampled), not a closure: "
                         "a device kernel cannot call back into the host")
+    if isinstance(grad, LogisticSubsampled) and not isinstance(F, ZigZag):
+        raise TypeError("the logistic target runs with ZigZag dynamics only")
     if not isinstance(F, (ZigZag, FactBoomerang)):
         raise TypeError("only ZigZag and FactBoomerang dynamics are implemented on the device path")
     if isinstance(F, ZigZag) and F.lambdaref != 0.0:
@@ -426,6 +472,8 @@ def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None,
         raise TypeError("spdmp: missing sampler F")
     F = rest.pop(0)
     local_bound = isinstance(c, LocalBound)   # spdmp(grad, t0, x0, th0, T, C::LocalBound, F, ...) src/local.jl:95,148
+    if local_bound and isinstance(grad, LogisticSubsampled):
+        raise NotImplementedError("LocalBound with the logistic target is not implemented on the device path")
     if local_bound:
         c = c.c
         if isinstance(grad, GaussianPotential):  # the bound comes from the target: F.Gamma / F.mu are ignored (local.jl:2-6)

@@ -5,6 +5,7 @@
 
 #include "zz_core.h"
 #include "zz_ctl.h"
+#include "zz_logit.h"
 
 struct ZzEvent {  // memory layout of Tuple{Float64,Int64,Float64,Float64}, src/trace.jl:38
     double t; long long i; double x; double theta;
@@ -90,6 +91,9 @@ struct ZzParams {
     int32_t* wl_peer[3][ZZ_MAXRANKS];
     int32_t* touched_peer[ZZ_MAXRANKS];
     ZzDevCtl* ctl_peer[ZZ_MAXRANKS];
+    // subsampled logistic target (zz_logit.h; only read by zz_run_kernel_csr_logit).  Kept LAST so that the parameter
+    // offsets the other kernels were compiled and profiled with do not move.
+    ZzLogit lg;
 };
 
 // order-preserving map double -> uint64 (so atomicMin works for any sign)

@@ -7,6 +7,9 @@
 //                     spdmp_inner! :73-145 inside), one grid barrier per relaxation pass
 //   zz_export_kernel  unpack the final (t, x, theta, c) for the host
 //
+//   zz_run_kernel_csr_logit: the same event loop with the subsampled logistic-regression target of scripts/logistic.jl
+//                     (zz_logit.h) instead of a Gaussian one
+//
 // Schedule: time is cut into windows [F, H).  Pass 1 of a window scans the proposal times,
 // compacts the coordinates with tau < H per warp and evaluates their timelines (zz_process_node); every
 // coordinate whose list of accepted flips changed marks the coordinates that read it; the following passes
@@ -380,7 +383,8 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
         P.ctl->dbg[3] += (unsigned long long)(c1 - c0);   // cycles in the evaluation
     }
 #else
-    zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, cur, first, o);
+    if constexpr (MODE == ZZ_MODE_LOGIT) zz_process_node_logit(P.g, P.v, P.lg, j, H, incl, w0, cur, first, o);
+    else zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, cur, first, o);
     zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws, tl, tslot);
 #endif
 }
@@ -920,3 +924,4 @@ ZZ_RUN_KERNEL(zz_run_kernel_grid_sticky, ZZ_KIND_GRID, false, ZZ_MODE_STICKY)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_sticky, ZZ_KIND_CSR, false, ZZ_MODE_STICKY)
 ZZ_RUN_KERNEL(zz_run_kernel_grid_boom, ZZ_KIND_GRID, false, ZZ_MODE_BOOM)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_boom, ZZ_KIND_CSR, false, ZZ_MODE_BOOM)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_logit, ZZ_KIND_CSR, false, ZZ_MODE_LOGIT)

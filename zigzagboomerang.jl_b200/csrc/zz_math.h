@@ -94,6 +94,44 @@ ZZ_HD double zz_log(double x)
     return dk * ln2_hi - ((s * (f - R) - dk * ln2_lo) - f);
 }
 
+// Exponential for finite x (the logistic target: sigmoid(x) = inv(1 + exp(-x)), scripts/logistic.jl:34).  Like zz_log
+// this is OUR routine so that host and device agree bit for bit: the Sun/fdlibm scheme -- x = k ln2 + r with ln2 split in
+// two pieces, exp(r) = 1 + 2r / (2 - c(r) ... ) with a degree-5 minimax polynomial in r^2 (error < 1 ulp), scaling by 2^k
+// through the exponent field; only + - * /, one double -> int conversion and integer operations.
+ZZ_HD double zz_exp(double x)
+{
+    const double ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10;
+    const double invln2 = 1.44269504088896338700e+00;
+    const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03, P3 = 6.61375632143793436117e-05;
+    const double P4 = -1.65339022054652515390e-06, P5 = 4.13813679705723846039e-08;
+    const double twom1000 = 9.33263618503218878990e-302;   // 2^-1000
+    if (x > 7.09782712893383973096e+02) return ZZ_INF;      // overflow
+    if (x < -7.45133219101941108420e+02) return 0.0;        // underflow
+    const double ax = x < 0.0 ? -x : x;
+    double hi = 0.0, lo = 0.0;
+    int32_t k = 0;
+    if (ax > 0.34657359027997264) {                         // |x| > ln2 / 2
+        k = (int32_t)(invln2 * x + (x < 0.0 ? -0.5 : 0.5));
+        const double t = (double)k;
+        hi = x - t * ln2HI;                                 // t * ln2HI is exact (ln2HI has 21 trailing zero bits)
+        lo = t * ln2LO;
+        x = hi - lo;
+    } else if (ax < 3.7252902984619141e-09) {               // |x| < 2^-28
+        return 1.0 + x;
+    }
+    const double t = x * x;
+    const double c = x - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+    if (k == 0) return 1.0 - ((x * c) / (c - 2.0) - x);
+    const double y = 1.0 - ((lo - (x * c) / (2.0 - c)) - hi);
+    if (k >= -1021) return zz_u2d(zz_d2u(y) + ((uint64_t)(int64_t)k << 52));
+    return zz_u2d(zz_d2u(y) + ((uint64_t)(int64_t)(k + 1000) << 52)) * twom1000;
+}
+
+// scripts/logistic.jl:34,56-57 -- sigmoid(x) = inv(one(x) + exp(-x)), sigmoidn(x) = sigmoid(-x), nsigmoid(x) = -sigmoid(x)
+ZZ_HD double zz_sigmoid(double x) { return 1.0 / (1.0 + zz_exp(-x)); }
+ZZ_HD double zz_sigmoidn(double x) { return zz_sigmoid(-x); }
+ZZ_HD double zz_nsigmoid(double x) { return -zz_sigmoid(x); }
+
 // ---------------------------------------------------------------------------------------------
 // Counter-based uniforms.  u(i,k) is the k-th draw of coordinate i's private stream:
 // two rounds of the splitmix64 finaliser over (seed, coordinate, counter).  The value is

@@ -21,6 +21,7 @@
 #include "../../include/zzb200.h"
 #include "zz_dev.h"
 #include "zz_host_graph.h"
+#include "zz_host_logit.h"
 
 #define ZZ_BLOCK 256
 
@@ -83,15 +84,16 @@ static int32_t cu_fail(CUresult r, const char* what)
     } while (0)
 
 // --------------------------------------------------------------------------------------------- global state
+#define ZZ_NKERN 13   // event-loop kernels in the image (see zzb_init)
 struct Global {
     bool ready = false;
     CUdevice dev = 0; int dev_id = 0;
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
-    CUfunction f_setup = nullptr, f_init = nullptr, f_init_boom = nullptr, f_run[12] = {}, f_export = nullptr, f_grid_tail = nullptr;
+    CUfunction f_setup = nullptr, f_init = nullptr, f_init_boom = nullptr, f_run[ZZ_NKERN] = {}, f_export = nullptr, f_grid_tail = nullptr;
     CUstream stream = nullptr;
     CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
-    int sm_count = 0; int blocks_per_sm[12] = {}; int run_block[2] = { 256, 256 };   // lattice / general-sparse kernels
+    int sm_count = 0; int blocks_per_sm[ZZ_NKERN] = {}; int run_block[2] = { 256, 256 };   // lattice / general-sparse kernels
     size_t total_mem = 0; char name[128] = { 0 };
 };
 static Global G;
@@ -146,6 +148,11 @@ struct zzb_problem_s {
     ZzHostGraph hg;
     DevBuf nptr, nidx, nwt, nwb, nfl, gmu, h, dptr, didx;
     ZzGraph g;
+    // subsampled logistic target (zzb_problem_create_logistic)
+    bool logit = false;
+    ZzHostLogit hl;
+    DevBuf l_acp, l_arow, l_aval, l_rp, l_rcol, l_rval, l_y, l_ny, l_u0;
+    ZzLogit lg;
 };
 
 struct zzb_run_s {
@@ -168,6 +175,7 @@ struct zzb_run_s {
     int grid = 0; int kind = 1;
     int kidx() const
     {
+        if (prob && prob->logit) return 12;
         if (flags & ZZB_FLAG_BOOMERANG) return 10 + kind;
         if (flags & ZZB_FLAG_STICKY) return 8 + kind;
         return kind + (nranks > 1 ? 2 : 0) + ((flags & ZZB_FLAG_LOCAL_BOUND) ? 4 : 0);
@@ -232,10 +240,12 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     // index = kind (0 lattice, 1 general) + 2 * multi-GPU + 4 * LocalBound
     // 8, 9: sticky ZigZag (single GPU)
     // 10, 11: factorised Boomerang (single GPU)
-    static const char* run_names[12] = { "zz_run_kernel_grid", "zz_run_kernel_csr", "zz_run_kernel_grid_multi", "zz_run_kernel_csr_multi",
+    // 12: subsampled logistic target (general sparse, single GPU)
+    static const char* run_names[ZZ_NKERN] = { "zz_run_kernel_grid", "zz_run_kernel_csr", "zz_run_kernel_grid_multi", "zz_run_kernel_csr_multi",
                                          "zz_run_kernel_grid_lb", "zz_run_kernel_csr_lb", "zz_run_kernel_grid_multi_lb", "zz_run_kernel_csr_multi_lb",
-                                         "zz_run_kernel_grid_sticky", "zz_run_kernel_csr_sticky", "zz_run_kernel_grid_boom", "zz_run_kernel_csr_boom" };
-    for (int k = 0; k < 12; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
+                                         "zz_run_kernel_grid_sticky", "zz_run_kernel_csr_sticky", "zz_run_kernel_grid_boom", "zz_run_kernel_csr_boom",
+                                         "zz_run_kernel_csr_logit" };
+    for (int k = 0; k < ZZ_NKERN; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuModuleGetFunction(&G.f_grid_tail, G.mod, "zz_grid_tail_kernel"));
     CU(cuStreamCreate(&G.stream, CU_STREAM_NON_BLOCKING));
@@ -251,8 +261,8 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
                 CU(cuMemcpyDtoH(&G.run_block[q], sym, sizeof(int)));
         }
     }
-    for (int k = 0; k < 12; ++k) {
-        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm[k], G.f_run[k], G.run_block[k & 1], 0));
+    for (int k = 0; k < ZZ_NKERN; ++k) {
+        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm[k], G.f_run[k], G.run_block[k == 12 ? 1 : (k & 1)], 0));
         if (G.blocks_per_sm[k] < 1) return fail(ZZB_E_CUDA, "zz_run_kernel does not fit on an SM");
     }
     G.ready = true;
@@ -332,6 +342,55 @@ int32_t zzb_problem_create_gaussian(zzb_problem_t* out, int64_t d, const int64_t
     return ZZB_OK;
 }
 
+// Target = the subsampled logistic-regression potential of scripts/logistic.jl (grad phi_j = gamma0 x_j - fdot_moving(...),
+// :78-107, evaluated through the SelfMoving closure signature, src/sfact.jl:68); sampler = ZigZag(bnd, bnd_mu) as usual.
+int32_t zzb_problem_create_logistic(zzb_problem_t* out, int64_t d, int64_t n, const int64_t* a_colptr, const int64_t* a_rowval,
+                                    const double* a_nzval, const int64_t* at_colptr, const int64_t* at_rowval,
+                                    const double* at_nzval, const double* y, const double* ny, const double* mu_cv,
+                                    double gamma0, int64_t k, const int64_t* bnd_colptr, const int64_t* bnd_rowval,
+                                    const double* bnd_nzval, const double* bnd_mu)
+{
+    if (!out || !a_colptr || !a_rowval || !a_nzval || !at_colptr || !at_rowval || !at_nzval || !y || !ny || !mu_cv ||
+        !bnd_colptr || !bnd_rowval || !bnd_nzval)
+        return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded -- zzb200 has no CPU fallback");
+    std::vector<double> zeros;
+    if (!bnd_mu) { zeros.assign((size_t)std::max<int64_t>(d, 1), 0.0); bnd_mu = zeros.data(); }
+    zzb_problem_s* p = new zzb_problem_s();
+    std::string e = zz_build_logit(p->hl, d, n, a_colptr, a_rowval, a_nzval, at_colptr, at_rowval, at_nzval, y, ny, mu_cv, gamma0, k);
+    if (!e.empty()) { delete p; return fail(ZZB_E_ARG, "%s", e.c_str()); }
+    // neighbour lists: the coordinates sharing a design row with j are its "target" entries (they only carry the
+    // dependency: weight 0), the sampler matrix gives the bound and trigger entries as for a Gaussian target
+    e = zz_build_graph(p->hg, d, p->hl.dep_cp.data(), p->hl.dep_rv.data(), p->hl.dep_nz.data(), nullptr, bnd_colptr, bnd_rowval,
+                       bnd_nzval, bnd_mu);
+    if (!e.empty()) { delete p; return fail(ZZB_E_GRAPH, "%s", e.c_str()); }
+    CtxGuard cg;
+    const ZzHostGraph& hg = p->hg;
+    const ZzHostLogit& hl = p->hl;
+    int32_t st = 0;
+#define UP(buf, vec) if (!st) st = upload(p->buf, hg.vec.data(), hg.vec.size() * sizeof(hg.vec[0]))
+    UP(nptr, nptr); UP(nidx, nidx); UP(nwt, nwt); UP(nwb, nwb); UP(nfl, nfl); UP(gmu, gmu); UP(dptr, dptr); UP(didx, didx);
+#undef UP
+#define UP(buf, vec) if (!st) st = upload(p->buf, hl.vec.data(), hl.vec.size() * sizeof(hl.vec[0]))
+    UP(l_acp, acp); UP(l_arow, arow); UP(l_aval, aval); UP(l_rp, rp); UP(l_rcol, rcol); UP(l_rval, rval); UP(l_y, y); UP(l_ny, ny);
+    UP(l_u0, u0);
+#undef UP
+    if (st) { delete p; return st; }
+    memset(&p->g, 0, sizeof p->g);
+    p->g.nptr = p->nptr.as<int32_t>(); p->g.nidx = p->nidx.as<int32_t>(); p->g.nwt = p->nwt.as<double>();
+    p->g.nwb = p->nwb.as<double>(); p->g.nfl = p->nfl.as<uint8_t>(); p->g.gmu = p->gmu.as<double>();
+    p->g.h = nullptr; p->g.same = 0; p->g.grid_m = 0; p->g.grid_n = 0;
+    zz_grid_set_magic(p->g);
+    p->hg.bnd_eq_tgt = false;
+    p->logit = true;
+    p->lg.acp = p->l_acp.as<int32_t>(); p->lg.arow = p->l_arow.as<int32_t>(); p->lg.aval = p->l_aval.as<double>();
+    p->lg.rp = p->l_rp.as<int32_t>(); p->lg.rcol = p->l_rcol.as<int32_t>(); p->lg.rval = p->l_rval.as<double>();
+    p->lg.y = p->l_y.as<double>(); p->lg.ny = p->l_ny.as<double>(); p->lg.u0 = p->l_u0.as<double>();
+    p->lg.gamma0 = hl.gamma0; p->lg.k = hl.k; p->lg.n = hl.n;
+    *out = p;
+    return ZZB_OK;
+}
+
 int32_t zzb_problem_free(zzb_problem_t p)
 {
     if (!p) return ZZB_OK;
@@ -344,6 +403,8 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
 {
     if (!p || !out) return fail(ZZB_E_ARG, "null argument");
     if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (p->logit && (flags & (ZZB_FLAG_STICKY | ZZB_FLAG_LOCAL_BOUND | ZZB_FLAG_BOOMERANG)))
+        return fail(ZZB_E_ARG, "the logistic target runs with the plain ZigZag sampler only (no sticky / LocalBound / Boomerang)");
     if ((flags & ZZB_FLAG_STICKY) && (flags & ZZB_FLAG_LOCAL_BOUND)) return fail(ZZB_E_ARG, "sticky and LocalBound cannot be combined");
     if ((flags & ZZB_FLAG_STICKY) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB)
         return fail(ZZB_E_ARG, "the sticky kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB, p->hg.maxdeg);
@@ -397,6 +458,7 @@ static void fill_params(zzb_run_s* r)
     ZzParams& P = r->P;
     memset(&P, 0, sizeof P);
     P.g = r->prob->g;
+    if (r->prob->logit) P.lg = r->prob->lg;
     P.v.d = r->d; P.v.kin = r->kin.as<ZzKin>(); P.v.flips = r->flips.as<double>(); P.v.priv = r->priv.as<ZzPriv>();
     P.v.tau = r->tau.as<double>(); P.v.kctr = r->kctr.as<uint32_t>();
     P.dptr = r->prob->dptr.as<int32_t>(); P.didx = r->prob->didx.as<int32_t>();
@@ -448,6 +510,7 @@ int32_t zzb_run_shard(zzb_run_t r, int32_t rank, int32_t nranks)
     if (!r) return fail(ZZB_E_ARG, "null argument");
     if (nranks < 1 || nranks > ZZ_MAXRANKS || rank < 0 || rank >= nranks) return fail(ZZB_E_ARG, "bad rank %d of %d", rank, nranks);
     if (nranks > 1 && (r->flags & (ZZB_FLAG_STICKY | ZZB_FLAG_BOOMERANG))) return fail(ZZB_E_ARG, "the sticky and Boomerang samplers are not sharded yet");
+    if (nranks > 1 && r->prob->logit) return fail(ZZB_E_ARG, "the logistic target is not sharded (its dependency graph is complete: replicas only)");
     const int64_t d = r->d;
     int64_t shard = (d + nranks - 1) / nranks;
     const int64_t m = r->prob->g.grid_m;

@@ -137,3 +137,100 @@ def random_sparse_spd(d: int, deg: int = 3, seed: int = 0) -> CSC:
                 M[j, i] += w
     M[np.diag_indices(d)] = np.abs(M).sum(axis=1) + rng.uniform(0.1, 1.0, size=d)
     return CSC.from_dense(M)
+
+
+@dataclasses.dataclass
+class RectCSC:
+    """Julia-layout CSC of a rectangular matrix (design matrices of regression targets)."""
+
+    nrows: int
+    ncols: int
+    colptr: np.ndarray
+    rowval: np.ndarray
+    nzval: np.ndarray
+
+    @staticmethod
+    def from_dense(M) -> "RectCSC":
+        """``sparse(M)``: column-major scan keeping every non-zero entry."""
+        M = np.asarray(M, dtype=np.float64)
+        rows, cols = np.nonzero(M.T)[::-1]  # column-major order: sort by column, then row
+        colptr = np.concatenate([[1], 1 + np.cumsum(np.bincount(cols, minlength=M.shape[1]))]).astype(np.int64)
+        return RectCSC(M.shape[0], M.shape[1], colptr, np.ascontiguousarray(rows.astype(np.int64) + 1),
+                       np.ascontiguousarray(M[rows, cols]))
+
+    def transpose(self) -> "RectCSC":
+        """``SparseMatrixCSC(A')`` (scripts/logistic.jl:31)."""
+        cols = np.repeat(np.arange(self.ncols), np.diff(self.colptr))
+        order = np.argsort(self.rowval, kind="stable")  # by row, columns ascending inside a row
+        colptr = np.concatenate([[1], 1 + np.cumsum(np.bincount(self.rowval - 1, minlength=self.nrows))]).astype(np.int64)
+        return RectCSC(self.ncols, self.nrows, colptr, np.ascontiguousarray(cols[order].astype(np.int64) + 1),
+                       np.ascontiguousarray(self.nzval[order]))
+
+    def to_dense(self) -> np.ndarray:
+        M = np.zeros((self.nrows, self.ncols))
+        cols = np.repeat(np.arange(self.ncols), np.diff(self.colptr))
+        M[self.rowval - 1, cols] = self.nzval
+        return M
+
+
+def sparse_design(d=(5, 5, 5), r: int = 5, m: int = 100, rng=None) -> np.ndarray:
+    """``sparse_design(d, r, m)`` of ``scripts/sparsedesign.jl:1-25`` (dense result; own RNG): ``len(d)`` categorical factors
+    (one random level per row, switched on with probability ``(d_k - 1) / d_k``), their pairwise interactions
+    (``0.3`` when both levels are on) and ``r`` continuous regressors ``0.1 randn``; ``n = m p`` rows."""
+    rng = np.random.default_rng(0) if rng is None else rng
+    d = tuple(int(v) for v in d)
+    K = len(d)
+    p = sum(d) + (sum(d) ** 2 - sum(v * v for v in d)) // 2 + r
+    n = m * p
+    D = np.concatenate([[0], np.cumsum(d)])
+    A = np.zeros((n, p))
+    rows = np.arange(n)
+    j = int(D[-1])
+    for k in range(K):
+        lev = rng.integers(0, d[k], size=n)
+        A[rows, D[k] + lev] = (rng.random(n) < (d[k] - 1) / d[k]).astype(np.float64)
+        for k2 in range(k):
+            for c2 in range(d[k2]):  # CartesianIndices((d[k], d[k2])): first index fastest
+                for c1 in range(d[k]):
+                    A[:, j] = 0.3 * ((A[:, D[k] + c1] == 1) & (A[:, D[k2] + c2] == 1))
+                    j += 1
+    for _ in range(r):
+        A[:, j] = 0.1 * rng.standard_normal(n)
+        j += 1
+    assert j == p
+    return A
+
+
+def logistic_config(levels=(20, 20), r: int = 2, m: int = 20, seed: int = 2, gamma0: float = 0.01, droptol: float = 1e-2,
+                    newton_steps: int = 30):
+    """Config 3 of SURVEY.md 8(d): the sparse logistic regression of ``scripts/logistic.jl:21-158`` (README: n = 8840,
+    p = 442 for ``m = 20``).  Returns a dict with the design ``A`` / ``At`` (:class:`RectCSC`), responses ``y`` / ``ny``, the
+    mode ``mu`` (30 Newton steps, :120-125), the Hessian at the mode ``Gamma`` and its sparsified copy ``Gamma_drop``
+    (``droptol!(copy(Gamma), 1e-2)``, :137; both :class:`CSC`), ``sigma = sqrt(diag(inv(Gamma)))`` (:150), ``x0 = mu``,
+    ``theta0 = +-sigma`` (:158), ``c = 0.01`` (:148) and ``gamma0``.  The Hessian is the analytic
+    ``gamma0 I + A' diag(s (1 - s)) A`` (the script differentiates the gradient with ReverseDiff, :134)."""
+    rng = np.random.default_rng(seed)
+    Ad = sparse_design(levels, r, m, rng)
+    n, p = Ad.shape
+    xtrue = 5 * rng.standard_normal(p)
+    sig = lambda v: 1.0 / (1.0 + np.exp(-v))
+    y = (rng.random(n) < sig(Ad @ xtrue)).astype(np.float64)
+    ny = 1.0 - y
+    x = 0.1 * rng.random(p)
+    for _ in range(newton_steps):
+        s = sig(Ad @ x)
+        grad = gamma0 * x + Ad.T @ (s - y)  # = gamma0 x - A'(y sigmoidn(Ax)) - A'(ny nsigmoid(Ax)), :102
+        H = gamma0 * np.eye(p) + (Ad.T * (s * (1 - s))) @ Ad
+        x = x - np.linalg.solve(H, grad)
+    s = sig(Ad @ x)
+    H = gamma0 * np.eye(p) + (Ad.T * (s * (1 - s))) @ Ad
+    H = 0.5 * (H + H.T)
+    pattern = (Ad != 0).T.astype(np.float64) @ (Ad != 0).astype(np.float64) > 0  # structure of A'A (:128-129)
+    Gamma = CSC.from_dense(np.where(pattern, H, 0.0))
+    # the diagonal is always kept: the script asserts nnz(diag(Gamma_drop)) == p (:138), which holds at full size anyway
+    Hd = np.where((pattern & (np.abs(H) > droptol)) | np.eye(p, dtype=bool), H, 0.0)
+    sigma = np.sqrt(np.diag(np.linalg.inv(H)))
+    theta0 = rng.choice(np.array([-1.0, 1.0]), size=p) * sigma
+    A = RectCSC.from_dense(Ad)
+    return dict(A=A, At=A.transpose(), y=y, ny=ny, mu=x.copy(), Gamma=Gamma, Gamma_drop=CSC.from_dense(Hd), sigma=sigma,
+                x0=x.copy(), theta0=theta0, c=np.full(p, 0.01), gamma0=gamma0, n=n, p=p)
