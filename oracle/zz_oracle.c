@@ -43,6 +43,9 @@
  *              Delta = 2/c/|theta| and is then renewed.  The target descriptor plays the role of the extended-form
  *              closure: (grad phi_i, v_i) = (idot(G,i,x) - h_i, theta_i idot(G,i,theta)) (local.jl:7).
  * GPU results must equal mode ctr|lazy (|8) bit for bit.
+ * Logistic target (zzo_spdmp_logistic): the same loop with the subsampled logistic-regression partial derivative of
+ * scripts/logistic.jl:78-107 (fdot_moving / grad_phi_moving, sigmoid helpers :34,56-57, idot_moving! src/common.jl:33-42)
+ * reached through the SelfMoving closure signature (src/sfact.jl:64-68); call site scripts/logistic.jl:167.
  * Further entry points below: zzo_sspdmp (sticky ZigZag, src/ss_fact.jl), zzo_spdmp_boom (FactBoomerang) and
  * zzo_parallel_spdmp (the reference's multithreaded parallel_spdmp, src/parallel.jl -- CPU baseline of bench.py).
  */
@@ -694,6 +697,198 @@ zzo_run *zzo_sspdmp(int64_t d,
     free(z->t_old); free(z->ba); free(z->bb); free(z->kctr); free(thf); free(f);
     free(Q.key); free(Q.val); free(Q.index);
     free(z->g2ptr); free(z->g2idx);
+    return r;
+}
+
+/* =====================================================================================================
+ * Sparse sticky ZigZag, sparsestickyzz / sspdmp3 (src/sparsestickyzz.jl:3-41,119-172,192-276,280-401,405-422) -- config 4
+ * as the reference runs it.  Restated faithfully for the CPU (mode seq only: one xoroshiro stream where the reference uses
+ * `rng`, a second one where it uses Julia's global RNG, :11,296,312): there is no separate device kernel for it -- the
+ * device serves config 4 with the sticky kernel of src/ss_fact.jl (zzo_sspdmp above is its contract), whose process has the
+ * same law.  tests/test_sparse_sticky.py checks that claim statistically against this restatement.
+ *   SparseState (:3-41): only unfrozen coordinates carry (t, x, theta); here dense arrays + an `active` flag.
+ *   ab (:136-142): CONSTANT "strong" bound a = c + grad_i theta_i, b = 0, valid until t + s/c (s = 1 - rand^2 when adapt);
+ *     a reflection reschedules ONLY the reflecting coordinate -- neighbours keep their bound until it expires (`renew`).
+ *   queue_time! (:144-172): tau = min(expiry, t + poisson_time((a, 0, 0.01), r), hitting time of 0) (poissontime.jl:86-92,39-65).
+ *   lambda (:129-134): (pos(grad_i theta_i), pos(a + b (t_i - t_ref))) -- the 0.01 floor is not in lb.
+ *   thaw clock Q0 (:218,325,362,368): ONE clock of rate kappa * #frozen; a thaw picks a frozen coordinate uniformly (:295-298)
+ *     and re-enters with velocity -1 + 2 p[i] (rule :sticky, :316) or a random sign (rule :reversible, :312).
+ *   events (:249): accepted thaw (:326), hit (:363; the record of a deleted coordinate is (t', 0, 0), :20-26) and accepted
+ *     reflection (:392).  clusteralpha = 1 (no cluster moves, :299-308,348-357).
+ * The target is grad_i(u) = idot(G, i, u) - h_i over the sparse state (:42-51; frozen coordinates contribute x = 0).
+ * ===================================================================================================== */
+static void hq_delete(heapq *q, int64_t key)
+{ /* delete!(Q, i) of DataStructures.PriorityQueue: move the last entry into the hole and restore the heap */
+    int64_t i = q->index[key];
+    int64_t lk = q->key[q->n]; double lv = q->val[q->n];
+    q->n -= 1;
+    q->index[key] = 0;
+    if (i > q->n) return;
+    q->key[i] = lk; q->val[i] = lv; q->index[lk] = i;
+    if (i > 1 && h_lt(q, lv, lk, q->val[i / 2], q->key[i / 2])) h_up(q, i); else h_down(q, i);
+}
+
+typedef struct {
+    int64_t d; csc G; const double *h;
+    char *active; double *t, *x, *th; char *p; double tmax;     /* SparseState: u, t', p */
+    char *action; double *bt, *ba, *bb, *bexp;                   /* clocks[i] = (action, (t_ref, a, b, t_expire)) */
+    heapq Q; double q0;                                          /* PriorityQueues(Q0, Q) */
+    double c; int adapt; double mult, kappa; int64_t nactive;
+    xoro rng, grng;
+    int64_t acc, num;                                            /* AcceptanceDiagnostics */
+} ssp;
+enum { A_HIT = 0, A_REFLECT = 1, A_RENEW = 2 };
+
+static double ss_grad(const ssp *S, int64_t i)
+{ /* idot(A, j, u::SparseState), :42-51 */
+    double s = 0.0;
+    for (int64_t q = S->G.colptr[i - 1]; q < S->G.colptr[i]; ++q) {
+        int64_t k = S->G.rowval[q - 1];
+        s += S->G.nzval[q - 1] * (S->active[k - 1] ? S->x[k - 1] : 0.0);
+    }
+    return S->h ? s - S->h[i - 1] : s;
+}
+static void ss_move(ssp *S, int64_t j, double tp)
+{ /* move_forward!(G, j, u, t', ::StickyFlow), :259-270: active neighbours only */
+    for (int64_t q = S->G.colptr[j - 1]; q < S->G.colptr[j]; ++q) {
+        int64_t i = S->G.rowval[q - 1];
+        if (!S->active[i - 1]) continue;
+        S->x[i - 1] = S->x[i - 1] + S->th[i - 1] * (tp - S->t[i - 1]);
+        S->t[i - 1] = tp;
+    }
+    if (S->tmax < tp) S->tmax = tp;
+}
+static void ss_ab(ssp *S, int64_t i, double gi)
+{ /* ab(rng, su, i, u, grad_i, flow), :136-142 */
+    double a = S->c + gi * S->th[i - 1];
+    double s = 1.0;
+    if (S->adapt) { double r = xoro_rand(&S->rng); s = 1.0 - r * r; }
+    S->bt[i - 1] = S->t[i - 1]; S->ba[i - 1] = a; S->bb[i - 1] = 0.0; S->bexp[i - 1] = S->t[i - 1] + s / S->c;
+}
+static void ss_queue_time(ssp *S, int64_t i, int enqueue)
+{ /* queue_time!, :144-172 */
+    double t = S->t[i - 1], x = S->x[i - 1], v = S->th[i - 1];
+    double trefresh = S->bexp[i - 1];
+    double dt = t - S->bt[i - 1];                                 /* poisson_time(t, b::Tuple, r), poissontime.jl:86-92 */
+    double trefl = t + zzo_poisson_time3(S->ba[i - 1] + dt * S->bb[i - 1], S->bb[i - 1], 0.01, xoro_rand(&S->rng));
+    double thit = (v * (x - 0.0) >= 0) ? INFINITY : t - (x - 0.0) / v;   /* hitting_time, :119-126 */
+    double tau = trefresh < trefl ? trefresh : trefl;
+    if (thit < tau) tau = thit;
+    if (enqueue) h_enqueue(&S->Q, i, tau); else h_set(&S->Q, i, tau);
+    S->action[i - 1] = (thit == tau) ? A_HIT : (trefl == tau) ? A_REFLECT : A_RENEW;
+}
+static double ss_randexp(xoro *r) { double u = xoro_rand(r); return -zz_log(u > 0 ? u : 0x1p-53); }
+
+/* rule: 0 = :sticky, 1 = :reversible.  th0 gives the initial velocities of the coordinates with x0 != 0 (the reference draws
+ * them from the global RNG, :11).  Returns events; acc[0] = accepted reflections, num = proposals (AcceptanceDiagnostics). */
+zzo_run *zzo_sparsestickyzz(int64_t d, const int64_t *g_colptr, const int64_t *g_rowval, const double *g_nzval, const double *h,
+                            const double *x0, const double *th0, double T, double c, double kappa, int rule, int adapt,
+                            double multiplier, const uint64_t *seed)
+{
+    zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run));
+    ssp Ss; ssp *S = &Ss; memset(S, 0, sizeof Ss);
+    r->d = d; S->d = d; S->G.colptr = g_colptr; S->G.rowval = g_rowval; S->G.nzval = g_nzval; S->h = h;
+    size_t nb = (size_t)d * sizeof(double);
+    S->active = (char *)calloc((size_t)d, 1); S->p = (char *)malloc((size_t)d); S->action = (char *)calloc((size_t)d, 1);
+    S->t = (double *)calloc((size_t)d, 8); S->x = (double *)calloc((size_t)d, 8); S->th = (double *)calloc((size_t)d, 8);
+    S->bt = (double *)calloc((size_t)d, 8); S->ba = (double *)calloc((size_t)d, 8); S->bb = (double *)calloc((size_t)d, 8);
+    S->bexp = (double *)calloc((size_t)d, 8);
+    r->acc = (int64_t *)calloc((size_t)d, sizeof(int64_t));
+    r->x0 = (double *)malloc(nb); memcpy(r->x0, x0, nb);
+    r->c = (double *)malloc(nb);
+    S->c = c; S->adapt = adapt; S->mult = multiplier; S->kappa = kappa;
+    S->rng.x = seed[0]; S->rng.y = seed[1];
+    S->grng.x = seed[0] ^ 0x9E3779B97F4A7C15ULL; S->grng.y = seed[1] ^ 0xD1342543DE82EF95ULL;
+    S->Q.n = 0; S->Q.lex = 0;
+    S->Q.key = (int64_t *)malloc(((size_t)d + 2) * sizeof(int64_t));
+    S->Q.val = (double *)malloc(((size_t)d + 2) * sizeof(double));
+    S->Q.index = (int64_t *)calloc((size_t)d + 2, sizeof(int64_t));
+    double tp = 0.0;                                             /* u.t' = 0 (:11) */
+    for (int64_t k = 0; k < d; ++k) {                            /* sparsestickystate (:10-12), u.p (:196-201) */
+        S->p[k] = 1;
+        if (x0[k] != 0) { S->active[k] = 1; S->x[k] = x0[k]; S->th[k] = th0[k]; S->p[k] = th0[k] > 0; S->nactive++; }
+    }
+    S->q0 = tp + ss_randexp(&S->rng) / (kappa * (double)(d - S->nactive));   /* :218 */
+    for (int64_t i = 1; i <= d; ++i) {                           /* :224-228 */
+        if (!S->active[i - 1]) continue;
+        ss_ab(S, i, ss_grad(S, i));
+        ss_queue_time(S, i, 1);
+    }
+    const double tl0 = now_s();
+    while (tp < T && r->status == ZZO_OK) {                      /* sparsesticky_main, :246 */
+        int64_t ev_i = 0;
+        for (;;) {                                               /* sparsestickyzz_inner!, :280-401 */
+            int64_t i; /* peek(Qs), morepriorityqueues.jl:33-42 */
+            if (S->Q.n == 0 || S->q0 < S->Q.val[1]) { i = 0; tp = S->q0; } else { i = S->Q.key[1]; tp = S->Q.val[1]; }
+            if (i == 0) {                                        /* thaw, :291-329 */
+                if (!(tp < INFINITY)) { r->status = 9; break; }
+                do { i = 1 + (int64_t)(xoro_rand(&S->grng) * (double)d); if (i > d) i = d; } while (S->active[i - 1]);
+                double vi = rule == 1 ? (xoro_rand(&S->grng) < 0.5 ? -1.0 : 1.0) : -1.0 + 2.0 * (double)S->p[i - 1];
+                S->active[i - 1] = 1; S->nactive++;              /* insert!(u, i, (t', barriers.x, vi)) */
+                S->t[i - 1] = tp; S->x[i - 1] = 0.0; S->th[i - 1] = vi;
+                if (S->tmax < tp) S->tmax = tp;
+                ss_move(S, i, tp);
+                ss_ab(S, i, ss_grad(S, i));
+                ss_queue_time(S, i, 1);
+                S->q0 = tp + ss_randexp(&S->rng) / (kappa * (double)(d - S->nactive));
+                ev_i = i;
+                break;
+            }
+            if (S->action[i - 1] == A_RENEW) {                   /* :330-340 */
+                ss_move(S, i, tp);
+                double gi = ss_grad(S, i);
+                double l = zz_pos(gi * S->th[i - 1]);
+                double lb = zz_pos(S->ba[i - 1] + S->bb[i - 1] * (S->t[i - 1] - S->bt[i - 1]));
+                if (l > lb) {
+                    if (!adapt) { r->status = ZZO_E_BOUND; r->err_i = i; r->err_t = tp; r->err_l = l; r->err_lb = lb; break; }
+                    S->acc = S->num = 0; S->c *= S->mult;
+                }
+                ss_ab(S, i, gi);
+                ss_queue_time(S, i, 0);
+                continue;
+            }
+            if (S->action[i - 1] == A_HIT) {                     /* :341-371 */
+                ss_move(S, i, tp);
+                if (fabs(S->x[i - 1]) > 1e-7) { r->status = 9; break; }
+                S->active[i - 1] = 0; S->nactive--;              /* delete!(u.u, i); delete!(clocks, i); delete!(Q, i) */
+                S->x[i - 1] = 0.0; S->th[i - 1] = 0.0;
+                hq_delete(&S->Q, i);
+                S->q0 = tp + ss_randexp(&S->rng) / (kappa * (double)(d - S->nactive));
+                ev_i = i;
+                break;
+            }
+            ss_move(S, i, tp);                                   /* reflection time or event of the bound, :372-399 */
+            double gi = ss_grad(S, i);
+            double l = zz_pos(gi * S->th[i - 1]);
+            double lb = zz_pos(S->ba[i - 1] + S->bb[i - 1] * (S->t[i - 1] - S->bt[i - 1]));
+            if (xoro_rand(&S->rng) * lb < l) {
+                S->acc++; S->num++; r->acc[i - 1]++;
+                if (l > lb) {
+                    if (!adapt) { r->status = ZZO_E_BOUND; r->err_i = i; r->err_t = tp; r->err_l = l; r->err_lb = lb; break; }
+                    S->acc = S->num = 0; S->c *= S->mult;
+                }
+                S->th[i - 1] = -S->th[i - 1];                    /* reflect!, :271-275 */
+                if (rule == 0) S->p[i - 1] = S->th[i - 1] > 0;
+                ss_ab(S, i, ss_grad(S, i));
+                ss_queue_time(S, i, 0);
+                ev_i = i;
+                break;
+            }
+            S->num++;
+            ss_ab(S, i, gi);
+            ss_queue_time(S, i, 0);
+        }
+        if (r->status != ZZO_OK) break;
+        /* push!(Xi, event(i, u, flow)), :249: (t_i, i, x_i, theta_i), (t', 0, 0) for a coordinate that was just deleted */
+        if (S->active[ev_i - 1]) push_event(r, S->t[ev_i - 1], ev_i, S->x[ev_i - 1], S->th[ev_i - 1]);
+        else push_event(r, S->tmax, ev_i, 0.0, 0.0);
+    }
+    r->loop_seconds = now_s() - tl0;
+    r->num = S->num;
+    for (int64_t k = 0; k < d; ++k) { r->c[k] = S->c; if (!S->active[k]) { S->t[k] = S->tmax; S->x[k] = 0.0; S->th[k] = 0.0; } }
+    r->t = S->t; r->x = S->x; r->th = S->th;
+    free(S->active); free(S->p); free(S->action); free(S->bt); free(S->ba); free(S->bb); free(S->bexp);
+    free(S->Q.key); free(S->Q.val); free(S->Q.index);
     return r;
 }
 

@@ -50,6 +50,8 @@ def lib():
             C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
         L.zzo_exp.restype = C.c_double
         L.zzo_exp.argtypes = [C.c_double]
+        L.zzo_sparsestickyzz.restype = C.c_void_p
+        L.zzo_sparsestickyzz.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_void_p]
         L.zzo_sincos.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
         L.zzo_randn.restype = C.c_double
         L.zzo_randn.argtypes = [C.c_double, C.c_double]
@@ -161,6 +163,46 @@ def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), 
         out.t0, out.x0, out.theta0 = t0, x0.copy(), theta0.copy()
         out.loop_seconds = L.zzo_loop_seconds(r)
         return out
+    finally:
+        L.zzo_free(r)
+
+
+def _collect(L, r, d, t0, x0, theta0):
+    st = L.zzo_status(r)
+    if st == 3:
+        i = C.c_int64(); t = C.c_double(); l = C.c_double(); lb = C.c_double()
+        L.zzo_error_info(r, C.byref(i), C.byref(t), C.byref(l), C.byref(lb))
+        raise BoundError("Tuning parameter `c` too small. (i=%d t=%g l=%g lb=%g)" % (i.value, t.value, l.value, lb.value))
+    if st != 0:
+        raise RuntimeError("oracle failed with status %d" % st)
+    out = OracleResult()
+    n = L.zzo_trace_len(r)
+    out.events = np.empty(n, dtype=EVENT_DTYPE)
+    L.zzo_trace_copy(r, _p(out.events), 0, n)
+    out.acc = np.empty(d, np.int64)
+    num = C.c_int64()
+    L.zzo_counts(r, _p(out.acc), C.byref(num))
+    out.num = num.value
+    out.t, out.x, out.theta, out.c = (np.empty(d) for _ in range(4))
+    L.zzo_final_state(r, _p(out.t), _p(out.x), _p(out.theta), _p(out.c))
+    out.t0, out.x0, out.theta0 = t0, x0.copy(), theta0.copy()
+    out.loop_seconds = L.zzo_loop_seconds(r)
+    return out
+
+
+def sparsestickyzz(G, x0, theta0, T, c, kappa, *, h=None, rule="sticky", adapt=False, multiplier=1.5, seed=(1, 2)):
+    """The reference's sparse sticky ZigZag (src/sparsestickyzz.jl, `sspdmp3`), restated for the CPU (faithful draw order,
+    mode seq).  Scalar ``c`` and ``kappa``; ``theta0`` gives the velocities of the coordinates with ``x0 != 0``."""
+    L = lib()
+    d = G.n
+    f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    x0, theta0 = f8(x0), f8(theta0)
+    h = None if h is None else f8(h)
+    sd = np.array(seed, dtype=np.uint64)
+    r = L.zzo_sparsestickyzz(d, _p(G.colptr), _p(G.rowval), _p(G.nzval), _p(h), _p(x0), _p(theta0), float(T), float(c), float(kappa),
+                             {"sticky": 0, "reversible": 1}[rule], int(adapt), float(multiplier), _p(sd))
+    try:
+        return _collect(L, r, d, 0.0, x0, theta0)
     finally:
         L.zzo_free(r)
 

@@ -1,0 +1,93 @@
+"""SURVEY 8(a) row a18 / BASELINE config 4: the reference's sparse sticky ZigZag (src/sparsestickyzz.jl, `sspdmp3`) restated
+for the CPU, and the statistical check behind DESIGN.md's claim that the sticky sampler the device runs (src/ss_fact.jl,
+per-coordinate thaw clocks and affine bounds) is the same process in law (one thaw clock of rate kappa * #frozen with a
+uniform pick, constant expiring bounds)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from sticky_stats import chain_precision, occupancy
+
+
+def test_event_records_follow_the_reference(zzb):
+    """Thaw: (t', i, 0, +-1); hit: the record of a deleted coordinate (t', i, 0, 0) (sparsestickyzz.jl:20-26,326,363);
+    reflection: velocity flipped (:392).  A coordinate alternates thaw -> reflections -> hit."""
+    p = 12
+    G = chain_precision(zzb, p)
+    r = O.sparsestickyzz(G, np.zeros(p), np.ones(p), 300.0, 2.5, 0.3, seed=(1, 2))
+    ev = r.events
+    assert len(ev) > 500 and np.all(np.diff(ev["t"]) >= 0) and ev["t"][-1] >= 300.0 and ev["t"][-2] < 300.0
+    for j in range(1, p + 1):
+        e = ev[ev["i"] == j]
+        frozen = True
+        for t, _, x, th in e:
+            if frozen:
+                assert x == 0.0 and abs(th) == 1.0      # thaw
+                frozen = False
+            elif th == 0.0:
+                assert x == 0.0                          # hit: frozen again
+                frozen = True
+            else:
+                assert abs(th) == 1.0                    # reflection
+    assert r.num >= r.acc.sum() > 0
+
+
+def test_sticky_rule_remembers_the_direction(zzb):
+    """rule :sticky re-enters with the sign the coordinate had when it hit 0 (-1 + 2p[i], :316,386-388): the velocity of a
+    thaw equals the velocity before the preceding hit."""
+    p = 8
+    G = chain_precision(zzb, p)
+    ev = O.sparsestickyzz(G, np.zeros(p), np.ones(p), 400.0, 2.5, 0.5, rule="sticky", seed=(3, 4)).events
+    checked = 0
+    for j in range(1, p + 1):
+        th = ev[ev["i"] == j]["theta"]
+        for k in range(2, len(th)):
+            if th[k - 1] == 0.0 and th[k] != 0.0:       # ... v, hit, thaw
+                assert th[k] == th[k - 2]
+                checked += 1
+    assert checked > 20
+
+
+@pytest.mark.parametrize("p,kappa,T", [(30, 0.5, 12000.0), (12, 0.1, 30000.0)])
+def test_same_law_as_the_sticky_sampler_of_the_device_contract(zzb, p, kappa, T):
+    """Occupancy (fraction of time away from 0) and second moments per coordinate agree between the reference's sparse
+    sticky algorithm and sspdmp in the device's parity mode (ctr|lazy) -- two independent runs, Monte Carlo tolerance."""
+    G = chain_precision(zzb, p)
+    x0 = np.zeros(p)
+    a = O.sparsestickyzz(G, x0, np.ones(p), T, 2.5, kappa, rule="sticky", seed=(3, 4))
+    th0 = np.random.default_rng(0).choice(np.array([-1.0, 1.0]), p)
+    b = O.spdmp(G, G, 0.0, x0, th0, T, G.colnorms(), kappa=np.full(p, kappa), seed=(5, 6), mode=O.PARITY_MODE)
+    oa, ma = occupancy(a.events, p, x0, T)
+    ob, mb = occupancy(b.events, p, x0, T)
+    assert abs(oa.mean() - ob.mean()) < 0.01 and np.abs(oa - ob).max() < 0.04
+    assert abs(ma.mean() - mb.mean()) < 0.03 * mb.mean() and np.abs(ma - mb).max() < 0.15 * mb.max()
+    assert abs(len(a.events) - len(b.events)) < 0.02 * len(b.events)   # thaws + hits + reflections per unit time
+
+
+def test_reversible_rule_and_adaptation(zzb):
+    p = 16
+    G = chain_precision(zzb, p)
+    a = O.sparsestickyzz(G, np.zeros(p), np.ones(p), 4000.0, 2.5, 0.4, rule="reversible", seed=(7, 8))
+    b = O.sparsestickyzz(G, np.zeros(p), np.ones(p), 4000.0, 2.5, 0.4, rule="sticky", seed=(9, 10))
+    oa, _ = occupancy(a.events, p, np.zeros(p), 4000.0)
+    ob, _ = occupancy(b.events, p, np.zeros(p), 4000.0)
+    assert 0.2 < oa.mean() < 0.9 and 0.2 < ob.mean() < 0.9      # both mix between frozen and moving
+    # c far too small: the strong bound is violated -> error without adapt (:334,381), c multiplied with adapt (:336,383)
+    with pytest.raises(O.BoundError):
+        O.sparsestickyzz(G, np.zeros(p), np.ones(p), 500.0, 0.05, 0.4, seed=(1, 2))
+    r = O.sparsestickyzz(G, np.zeros(p), np.ones(p), 500.0, 0.05, 0.4, adapt=True, multiplier=1.5, seed=(1, 2))
+    assert r.c[0] > 0.05 and np.all(r.c == r.c[0])
+
+
+def test_nonzero_start_and_linear_term(zzb):
+    """Active coordinates at t = 0 (x0 != 0, velocities given) and a target with a linear term (the heart target's data term,
+    research/sticky/heart/heart_sparse2.jl:52, is of this form)."""
+    p = 10
+    G = chain_precision(zzb, p)
+    rng = np.random.default_rng(2)
+    x0 = np.where(rng.random(p) < 0.5, rng.standard_normal(p), 0.0)
+    r = O.sparsestickyzz(G, x0, rng.choice(np.array([-1.0, 1.0]), p), 3000.0, 4.0, 0.3, h=np.full(p, 0.8), seed=(1, 2))
+    occ, _ = occupancy(r.events, p, x0, 3000.0)
+    r0 = O.sparsestickyzz(G, x0, np.ones(p), 3000.0, 4.0, 0.3, seed=(1, 2))
+    occ0, _ = occupancy(r0.events, p, x0, 3000.0)
+    assert occ.mean() > occ0.mean() + 0.05     # the pull of h keeps coordinates away from 0 longer

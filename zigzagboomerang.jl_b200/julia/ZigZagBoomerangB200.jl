@@ -2,7 +2,7 @@
 #
 # Adds GPU methods to the reference's own `spdmp` / `pdmp` / `sspdmp` generic functions (ZigZag, LocalBound, sticky ZigZag,
 # FactBoomerang): they are selected by dispatch when
-# the "gradient" argument is a `GaussianPotential` descriptor instead of a closure, and return exactly what the
+# the "gradient" argument is a `GaussianPotential` / `LogisticSubsampled` descriptor instead of a closure, and return exactly what the
 # reference returns: `Ξ::FactTrace, (t, x, θ), (acc, num), c` (src/sfact.jl:211).
 #
 # NOTE: Julia is not installed in the build image, so this file is UNTESTED there; it is kept in lock-step with the
@@ -53,25 +53,79 @@ function init(device::Integer = 0)
     check(ccall((:zzb_init, libzzb200), Int32, (Int32, Ptr{Int32}, Cstring), 1, ids, cubin))
     initialised[] = true
 end
+"""
+    LogisticSubsampled(A, At, y, ny, μ, γ0 = 0.01, k = 10)
+
+Target descriptor standing in for the closure `∇ϕmoving(t, x, θ, i, t′, F, A, At, μ, y, ny, k)` of `scripts/logistic.jl:78-107`
+together with the trailing arguments `SelfMoving(), A, At, μ, y, ny, k` the script forwards to it (`:167`): the subsampled
+partial derivative of the logistic-regression potential with a control variate at `μ`.  Calling it evaluates the full-data
+partial derivative (`∇ϕ(x, i, A, At, y, ny)`, `:104`), so the same object also works with the reference's CPU `spdmp`.
+"""
+struct LogisticSubsampled{T<:SparseMatrixCSC{Float64,Int}}
+    A::T
+    At::T
+    y::Vector{Float64}
+    ny::Vector{Float64}
+    μ::Vector{Float64}
+    γ0::Float64
+    k::Int
+end
+LogisticSubsampled(A, At, y, ny, μ, γ0 = 0.01, k = 10) =
+    LogisticSubsampled(A, At, Vector{Float64}(y), Vector{Float64}(ny), Vector{Float64}(μ), Float64(γ0), Int(k))
+function (g::LogisticSubsampled)(x, i, args...)
+    sig(u) = inv(one(u) + exp(-u))
+    rows, vals = rowvals(g.A), nonzeros(g.A)
+    s = 0.0
+    for p in nzrange(g.A, i)
+        u = ZigZagBoomerang.idot(g.At, rows[p], x)
+        s += vals[p]*g.y[rows[p]]*sig(-u) - vals[p]*g.ny[rows[p]]*sig(u)
+    end
+    g.γ0*x[i] - s
+end
+
+# zzb_problem_create_logistic: Julia's CSC arrays of A and At as they are
+function create_problem(prob, ∇ϕ::LogisticSubsampled, F, μ, d)
+    Γb = F.Γ
+    check(ccall((:zzb_problem_create_logistic, libzzb200), Int32,
+                (Ref{Ptr{Cvoid}}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+                prob, d, size(∇ϕ.A, 1), ∇ϕ.A.colptr, ∇ϕ.A.rowval, ∇ϕ.A.nzval, ∇ϕ.At.colptr, ∇ϕ.At.rowval, ∇ϕ.At.nzval,
+                ∇ϕ.y, ∇ϕ.ny, ∇ϕ.μ, ∇ϕ.γ0, ∇ϕ.k, Γb.colptr, Γb.rowval, Γb.nzval, μ))
+end
+
+# spdmp(∇ϕmoving, t0, x0, θ0, T, c, Zdrop, SelfMoving(), A, At, μ, y, ny, k; adapt, factor) (scripts/logistic.jl:167) becomes
+# spdmp(LogisticSubsampled(A, At, y, ny, μ, γ0, k), t0, x0, θ0, T, c, Zdrop; adapt, factor); trailing arguments are ignored
+function spdmp(∇ϕ::LogisticSubsampled, t0, x0, θ0, T, c, G::Union{ZigZagBoomerang.All,ZigZagBoomerang.Matched}, F::ZigZag, args...;
+               factor = 1.8, adapt = false, adaptscale = false, progress = false, progress_stops = 20, seed = Seed())
+    F.λref == 0 || error("ZigZag refreshments (λref > 0) are not implemented on the device path")
+    Ξ, u, an, cv = device_run(:zigzag, ∇ϕ, t0, x0, θ0, T, c, F; factor = factor, adapt = adapt, seed = seed)
+    c .= cv
+    Ξ, u, an, c
+end
+spdmp(∇ϕ::LogisticSubsampled, t0, x0, θ0, T, c, F::ZigZag, args...; kargs...) =
+    spdmp(∇ϕ, t0, x0, θ0, T, c, ZigZagBoomerang.Matched(), F, args...; kargs...)
 
 # One device run: problem from (∇ϕ, F), then the one-call entry point selected by `kind`, then the results in the
 # reference's return shape.  `kind`: :zigzag (zzb_spdmp_run, flags = 0 or ZZB_FLAG_LOCAL_BOUND), :sticky (zzb_sspdmp_run),
 # :boomerang (zzb_spdmp_boomerang_run).
-function device_run(kind::Symbol, ∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F; κ = nothing, flags = UInt32(0),
+function device_run(kind::Symbol, ∇ϕ::Union{GaussianPotential,LogisticSubsampled}, t0, x0, θ0, T, c, F; κ = nothing, flags = UInt32(0),
                     factor = 1.8, adapt = false, seed = Seed())
     init()
     d = length(x0)
-    Γt, Γb = ∇ϕ.Γ, F.Γ
+    logistic = ∇ϕ isa LogisticSubsampled
+    Γt, Γb = logistic ? F.Γ : ∇ϕ.Γ, F.Γ
     μ = Vector{Float64}(F.μ)
     x0v, θ0v, cv = Vector{Float64}(x0), Vector{Float64}(θ0), Vector{Float64}(c)
     prob = Ref{Ptr{Cvoid}}(C_NULL)
     run = Ref{Ptr{Cvoid}}(C_NULL)
-    h = ∇ϕ.h === nothing ? Ptr{Float64}(C_NULL) : pointer(∇ϕ.h)
+    h = (logistic || ∇ϕ.h === nothing) ? Ptr{Float64}(C_NULL) : pointer(∇ϕ.h)
     sd = UInt64[seed[1], seed[2]]
     κv = κ === nothing ? Float64[] : Vector{Float64}(κ isa Number ? fill(κ, d) : κ)
     σv = kind === :boomerang ? Vector{Float64}(F.σ) : Float64[]
     GC.@preserve Γt Γb μ x0v θ0v cv sd κv σv ∇ϕ begin
-        if flags & ZZB_FLAG_LOCAL_BOUND != 0     # the bound comes from the target itself (src/local.jl:2-6): bnd_* = NULL
+        if logistic
+            create_problem(prob, ∇ϕ, F, μ, d)
+        elseif flags & ZZB_FLAG_LOCAL_BOUND != 0     # the bound comes from the target itself (src/local.jl:2-6): bnd_* = NULL
             check(ccall((:zzb_problem_create_gaussian, libzzb200), Int32,
                         (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64},
                          Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
@@ -164,5 +218,5 @@ for FT in (:ZigZag, :FactBoomerang)
     end
 end
 
-export GaussianPotential
+export GaussianPotential, LogisticSubsampled
 end # module
