@@ -14,6 +14,13 @@ def make(zzb, levels, r, m, seed, k=10):
     return cfg
 
 
+def replicas(zzb, cfg, R):
+    out = zzb.replicate_logistic(cfg, R)
+    lg = cfg["logistic"]
+    out["logistic"] = dict(A=out["A"], At=out["At"], y=out["y"], ny=out["ny"], mu=out["mu"], gamma0=lg["gamma0"], k=lg["k"])
+    return out
+
+
 def run_oracle(O, cfg, T, *, seed=(5, 6), adapt=True, factor=5.0, mode=None, c=None):
     """spdmp(grad_phi_moving, t0, x0, th0, T, c, Zdrop, SelfMoving(), A, At, mu, y, ny, k; adapt, factor) (scripts/logistic.jl:167)"""
     return O.spdmp(None, cfg["Gamma_drop"], 0.0, cfg["x0"], cfg["theta0"], T, cfg["c"] if c is None else c, mu=cfg["mu"],

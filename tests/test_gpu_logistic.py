@@ -62,3 +62,17 @@ def test_refuses_unsupported_combinations(gpu):
     bad = gpu.LogisticSubsampled(lg["A"], lg["A"], lg["y"], lg["ny"], lg["mu"], lg["gamma0"], lg["k"])   # At is not A'
     with pytest.raises(gpu.ZZBError):
         gpu.Problem(bad, Z)
+
+
+def test_replicas_bit_exact(gpu):
+    """R independent chains as one block-diagonal problem (config 3 = plumbing + replicas): bit-exact against the oracle on
+    the joint problem; the device time per event falls with R because the passes of the chains overlap."""
+    cfg = LC.make(gpu, *LC.FULL)
+    R, T = 8, 4.0
+    big = LC.replicas(gpu, cfg, R)
+    ref = LC.run_oracle(O, big, T)
+    got, Xi = LC.run_device(gpu, big, T)
+    O.assert_same_run(ref, got)
+    one, Xi1 = LC.run_device(gpu, cfg, T)
+    print(f"config 3 replicas: R = {R}: {len(got.events)} events in {Xi.device_ms:.1f} ms; R = 1: {len(one.events)} events in "
+          f"{Xi1.device_ms:.1f} ms; oracle (R = {R}) {ref.loop_seconds * 1e3:.1f} ms")

@@ -114,3 +114,26 @@ def test_lazy_and_inplace_arithmetic_agree(zzb):
     n = min(len(a.events), len(b.events), 60)
     assert n >= 40 and np.array_equal(a.events["i"][:n], b.events["i"][:n])
     assert np.allclose(a.events["t"][:n], b.events["t"][:n], rtol=1e-9)
+
+
+def test_replicas_are_independent_chains_in_one_problem(zzb):
+    """Block-diagonal replication (config 3 is "plumbing + replicas"): the schedule emulation equals the oracle on the joint
+    problem, the replicas do not interact (each one's event count is that of a chain of its own) and they differ from
+    each other (own counter streams)."""
+    *design, T = LC.SMALL[0]
+    cfg = LC.make(zzb, *design)
+    R, p = 3, cfg["p"]
+    big = LC.replicas(zzb, cfg, R)
+    assert big["A"].ncols == R * p and big["Gamma_drop"].n == R * p
+    ref = LC.run_oracle(O, big, T)
+    sim = O.window_sim(None, big["Gamma_drop"], 0.0, big["x0"], big["theta0"], T, big["c"], mu=big["mu"], adapt=True, factor=5.0,
+                       logistic=big["logistic"], seed=(5, 6))
+    O.assert_same_run(ref, sim)
+    one = LC.run_oracle(O, cfg, T)
+    block = (ref.events["i"] - 1) // p
+    first = ref.events[block == 0]
+    # replica 0 has the coordinate ids (hence the streams) of the single chain: identical events up to the stopping rule
+    n = min(len(first), len(one.events)) - 1
+    assert n > 50 and np.array_equal(first["i"][:n], one.events["i"][:n]) and np.array_equal(first["t"][:n], one.events["t"][:n])
+    counts = np.bincount(block, minlength=R)
+    assert counts.min() > 0.6 * counts.max() and len({tuple(ref.events["t"][block == r][:5]) for r in range(R)}) == R

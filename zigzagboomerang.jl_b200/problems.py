@@ -234,3 +234,28 @@ def logistic_config(levels=(20, 20), r: int = 2, m: int = 20, seed: int = 2, gam
     A = RectCSC.from_dense(Ad)
     return dict(A=A, At=A.transpose(), y=y, ny=ny, mu=x.copy(), Gamma=Gamma, Gamma_drop=CSC.from_dense(Hd), sigma=sigma,
                 x0=x.copy(), theta0=theta0, c=np.full(p, 0.01), gamma0=gamma0, n=n, p=p)
+
+
+def _block_diag_csc(blocks_rows: int, blocks_cols: int, colptr, rowval, nzval, R: int):
+    nnz = len(nzval)
+    cp = np.concatenate([[1]] + [colptr[1:] + r * nnz for r in range(R)]).astype(np.int64)
+    rv = np.concatenate([rowval + r * blocks_rows for r in range(R)]).astype(np.int64)
+    return cp, rv, np.tile(nzval, R)
+
+
+def replicate_logistic(cfg: dict, R: int) -> dict:
+    """R independent replicas of a logistic configuration as ONE block-diagonal problem (design ``I_R (x) A``, sampler matrix
+    ``I_R (x) Gamma_drop``): the components never interact, every coordinate has its own counter stream, so one device run
+    simulates R independent chains side by side (config 3 is "plumbing + replicas": one chain of p = 442 coordinates with a
+    complete dependency graph cannot fill a GPU)."""
+    A, G = cfg["A"], cfg["Gamma_drop"]
+    cp, rv, nz = _block_diag_csc(A.nrows, A.ncols, A.colptr, A.rowval, A.nzval, R)
+    AR = RectCSC(A.nrows * R, A.ncols * R, cp, rv, nz)
+    gcp, grv, gnz = _block_diag_csc(G.n, G.n, G.colptr, G.rowval, G.nzval, R)
+    out = dict(cfg)
+    out.update(A=AR, At=AR.transpose(), y=np.tile(cfg["y"], R), ny=np.tile(cfg["ny"], R), mu=np.tile(cfg["mu"], R),
+               Gamma_drop=CSC(G.n * R, gcp, grv, gnz), sigma=np.tile(cfg["sigma"], R), x0=np.tile(cfg["x0"], R),
+               theta0=np.tile(cfg["theta0"], R), c=np.tile(cfg["c"], R), n=cfg["n"] * R, p=cfg["p"] * R, replicas=R)
+    out.pop("Gamma", None)
+    out.pop("logistic", None)
+    return out
