@@ -76,3 +76,14 @@ def test_replicas_bit_exact(gpu):
     one, Xi1 = LC.run_device(gpu, cfg, T)
     print(f"config 3 replicas: R = {R}: {len(got.events)} events in {Xi.device_ms:.1f} ms; R = 1: {len(one.events)} events in "
           f"{Xi1.device_ms:.1f} ms; oracle (R = {R}) {ref.loop_seconds * 1e3:.1f} ms")
+
+
+def test_random_designs_on_the_device(gpu):
+    """tools/fuzz_logistic.py on the CUDA path: 25 random cases, bit-exact or a bound error on both sides."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fuzz_logistic", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_logistic.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    n_ok, n_err = fz.run(gpu, 11, 25, gpu=True, verbose=False)
+    assert n_ok >= 12

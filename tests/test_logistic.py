@@ -137,3 +137,14 @@ def test_replicas_are_independent_chains_in_one_problem(zzb):
     assert n > 50 and np.array_equal(first["i"][:n], one.events["i"][:n]) and np.array_equal(first["t"][:n], one.events["t"][:n])
     counts = np.bincount(block, minlength=R)
     assert counts.min() > 0.6 * counts.max() and len({tuple(ref.events["t"][block == r][:5]) for r in range(R)}) == R
+
+
+def test_random_designs_emulation_equals_oracle(zzb):
+    """A slice of tools/fuzz_logistic.py: random designs / subsample counts / bounds / window policies."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("fuzz_logistic", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_logistic.py"))
+    fz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fz)
+    n_ok, n_err = fz.run(zzb, 7, 40, verbose=False)
+    assert n_ok >= 20 and n_err >= 1
