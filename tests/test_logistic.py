@@ -148,3 +148,32 @@ def test_random_designs_emulation_equals_oracle(zzb):
     spec.loader.exec_module(fz)
     n_ok, n_err = fz.run(zzb, 7, 40, verbose=False)
     assert n_ok >= 20 and n_err >= 1
+
+
+def test_host_preparation_rejects_malformed_designs(zzb):
+    """zz_build_logit (shared by libzzb200.so and the schedule emulation): At must be the transpose of A, every column of A
+    needs an entry (upstream: rand over an empty range throws), k >= 1."""
+    cfg = LC.make(zzb, *LC.SMALL[0][:4])
+    lg = dict(cfg["logistic"])
+
+    def sim(**over):
+        l2 = dict(lg)
+        l2.update(over)
+        return O.window_sim(None, cfg["Gamma_drop"], 0.0, cfg["x0"], cfg["theta0"], 1.0, cfg["c"], mu=cfg["mu"], adapt=True,
+                            logistic=l2, seed=(1, 2))
+    sim()
+    At = lg["At"]
+    bad_vals = zzb.RectCSC(At.nrows, At.ncols, At.colptr, At.rowval, At.nzval * 1.5)
+    with pytest.raises(RuntimeError, match="status 4"):
+        sim(At=bad_vals)
+    with pytest.raises(RuntimeError, match="status 4"):
+        sim(k=0)
+    A = lg["A"]
+    dense = A.to_dense()
+    dense[:, 3] = 0.0                                  # an empty column
+    A0 = zzb.RectCSC.from_dense(dense)
+    with pytest.raises(RuntimeError, match="status 4"):
+        sim(A=A0, At=A0.transpose())
+    with pytest.raises(RuntimeError):                  # the oracle refuses it as well
+        O.spdmp(None, cfg["Gamma_drop"], 0.0, cfg["x0"], cfg["theta0"], 1.0, cfg["c"], mu=cfg["mu"], adapt=True,
+                logistic=dict(lg, A=A0, At=A0.transpose()))
