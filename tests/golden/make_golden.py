@@ -13,7 +13,7 @@ import golden_cases as GC  # noqa: E402
 import oracle_lib as O  # noqa: E402
 
 zzb = graft.load_package()
-for name in GC.CASES:
+for name in GC.CASES + GC.LOGISTIC_CASES:
     out = GC.run_oracle(O, GC.case_inputs(zzb, name))
     json.dump(out, open(os.path.join(HERE, name + ".json"), "w"), indent=1)
     print(name, out["num"], out["n_events"], out["acc_sum"])

@@ -43,7 +43,8 @@ def case_inputs(zzb, name):
     raise KeyError(name)
 
 
-CASES = ["gmrf16_T3", "gmrf12_tight", "spd8_adapt", "localbound16", "sticky12", "boomerang12", "logistic26"]
+CASES = ["gmrf16_T3", "gmrf12_tight", "spd8_adapt", "localbound16", "sticky12", "boomerang12"]
+LOGISTIC_CASES = ["logistic26"]   # checked by tests/test_logistic.py (oracle) and tests/test_gpu_zz_logistic.py (device)
 
 
 def run_oracle(O, k):

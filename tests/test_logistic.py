@@ -177,3 +177,14 @@ def test_host_preparation_rejects_malformed_designs(zzb):
     with pytest.raises(RuntimeError):                  # the oracle refuses it as well
         O.spdmp(None, cfg["Gamma_drop"], 0.0, cfg["x0"], cfg["theta0"], 1.0, cfg["c"], mu=cfg["mu"], adapt=True,
                 logistic=dict(lg, A=A0, At=A0.transpose()))
+
+
+def test_logistic_golden_fixture(zzb):
+    """tests/golden/logistic26.json pins our RNG / arithmetic contract for the logistic target across rounds."""
+    import json
+    import os
+
+    import golden_cases as GC
+    for name in GC.LOGISTIC_CASES:
+        g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", name + ".json")))
+        assert GC.run_oracle(O, GC.case_inputs(zzb, name)) == g
