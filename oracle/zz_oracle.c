@@ -717,6 +717,40 @@ zzo_run *zzo_sspdmp(int64_t d,
  *     reflection (:392).  clusteralpha = 1 (no cluster moves, :299-308,348-357).
  * The target is grad_i(u) = idot(G, i, u) - h_i over the sparse state (:42-51; frozen coordinates contribute x = 0).
  * ===================================================================================================== */
+/* peek(q::PriorityQueues), src/morepriorityqueues.jl:33-42, with a LinearQueue head (:12-19: findmin = first minimum) and
+ * a heap tail: the head wins only with a STRICTLY smaller time.  Returns the key; head keys are head_first + position. */
+static int64_t pqs_peek(const double *head_vals, int64_t nhead, int64_t head_first, const heapq *tail, double *t)
+{
+    int64_t i1 = 0; double t1 = head_vals[0];
+    for (int64_t k = 1; k < nhead; ++k) if (head_vals[k] < t1) { t1 = head_vals[k]; i1 = k; }
+    if (tail->n == 0 || t1 < tail->val[1]) { *t = t1; return head_first + i1; }
+    *t = tail->val[1];
+    return tail->key[1];
+}
+
+/* Test hook (tests/test_oracle.py replays test/priority.jl:11-31 and random scripts through it): build the heap by
+ * enqueueing (keys0, vals0) in order, then apply the updates `key -> val` (setindex!, priorityqueue.jl:95-105; a key of the
+ * head range updates the LinearQueue) and record peek after each one (slot 0 = before any update). */
+void zzo_queue_script(const double *head_vals_in, int64_t nhead, int64_t head_first, const int64_t *keys0, const double *vals0,
+                      int64_t n0, int64_t maxkey, const int64_t *op_keys, const double *op_vals, int64_t nops,
+                      int64_t *peek_keys, double *peek_vals)
+{
+    heapq Q; Q.n = 0; Q.lex = 0;
+    Q.key = (int64_t *)malloc(((size_t)maxkey + 2) * sizeof(int64_t));
+    Q.val = (double *)malloc(((size_t)maxkey + 2) * sizeof(double));
+    Q.index = (int64_t *)calloc((size_t)maxkey + 2, sizeof(int64_t));
+    double *head = (double *)malloc((size_t)(nhead > 0 ? nhead : 1) * sizeof(double));
+    memcpy(head, head_vals_in, (size_t)nhead * sizeof(double));
+    for (int64_t k = 0; k < n0; ++k) h_enqueue(&Q, keys0[k], vals0[k]);
+    peek_keys[0] = pqs_peek(head, nhead, head_first, &Q, &peek_vals[0]);
+    for (int64_t k = 0; k < nops; ++k) {
+        if (op_keys[k] >= head_first && op_keys[k] < head_first + nhead) head[op_keys[k] - head_first] = op_vals[k];
+        else h_set(&Q, op_keys[k], op_vals[k]);
+        peek_keys[k + 1] = pqs_peek(head, nhead, head_first, &Q, &peek_vals[k + 1]);
+    }
+    free(Q.key); free(Q.val); free(Q.index); free(head);
+}
+
 static void hq_delete(heapq *q, int64_t key)
 { /* delete!(Q, i) of DataStructures.PriorityQueue: move the last entry into the hole and restore the heap */
     int64_t i = q->index[key];
@@ -818,8 +852,7 @@ zzo_run *zzo_sparsestickyzz(int64_t d, const int64_t *g_colptr, const int64_t *g
     while (tp < T && r->status == ZZO_OK) {                      /* sparsesticky_main, :246 */
         int64_t ev_i = 0;
         for (;;) {                                               /* sparsestickyzz_inner!, :280-401 */
-            int64_t i; /* peek(Qs), morepriorityqueues.jl:33-42 */
-            if (S->Q.n == 0 || S->q0 < S->Q.val[1]) { i = 0; tp = S->q0; } else { i = S->Q.key[1]; tp = S->Q.val[1]; }
+            int64_t i = pqs_peek(&S->q0, 1, 0, &S->Q, &tp); /* peek(Qs), morepriorityqueues.jl:33-42; key 0 = thaw clock */
             if (i == 0) {                                        /* thaw, :291-329 */
                 if (!(tp < INFINITY)) { r->status = 9; break; }
                 do { i = 1 + (int64_t)(xoro_rand(&S->grng) * (double)d); if (i > d) i = d; } while (S->active[i - 1]);

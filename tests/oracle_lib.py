@@ -52,6 +52,9 @@ def lib():
         L.zzo_exp.argtypes = [C.c_double]
         L.zzo_sparsestickyzz.restype = C.c_void_p
         L.zzo_sparsestickyzz.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_void_p]
+        L.zzo_queue_script.restype = None
+        L.zzo_queue_script.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_int64, C.c_void_p, C.c_void_p]
         L.zzo_sincos.argtypes = [C.c_double, C.c_void_p, C.c_void_p]
         L.zzo_randn.restype = C.c_double
         L.zzo_randn.argtypes = [C.c_double, C.c_double]
@@ -165,6 +168,18 @@ def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), 
         return out
     finally:
         L.zzo_free(r)
+
+
+def queue_script(head_vals, head_first, keys0, vals0, ops):
+    """Composite queue of src/morepriorityqueues.jl (LinearQueue head + heap tail): peek before and after each update."""
+    L = lib()
+    hv = np.ascontiguousarray(head_vals, dtype=np.float64)
+    k0 = np.ascontiguousarray(keys0, dtype=np.int64); v0 = np.ascontiguousarray(vals0, dtype=np.float64)
+    ok = np.ascontiguousarray([o[0] for o in ops], dtype=np.int64); ov = np.ascontiguousarray([o[1] for o in ops], dtype=np.float64)
+    pk = np.zeros(len(ops) + 1, np.int64); pv = np.zeros(len(ops) + 1)
+    maxkey = int(max([0] + list(k0) + list(ok)))
+    L.zzo_queue_script(_p(hv), len(hv), int(head_first), _p(k0), _p(v0), len(k0), maxkey, _p(ok), _p(ov), len(ops), _p(pk), _p(pv))
+    return list(zip(pk.tolist(), pv.tolist()))
 
 
 def _collect(L, r, d, t0, x0, theta0):

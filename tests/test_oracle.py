@@ -263,3 +263,30 @@ def test_config1_two_dimensional_gaussian_pdmp(zzb):
     for mode in (O.RNG_SEQ | O.ARITH_INPLACE | O.GRAPH_ALL, O.PARITY_MODE):
         r = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, T, c, seed=(5, 6), mode=mode)
         _cov_check(r, zzb, G, x0, th0, T, 2.0, 2.5)
+
+
+def test_queue_known_answers_of_the_reference():
+    """test/priority.jl:11-31 ("Queues"): LinearQueue(0:2, [3.0, 1.0, 0.5]) in front of PriorityQueue(3 => 1.0, 4 => 0.6)."""
+    pk = O.queue_script([3.0, 1.0, 0.5], 0, [3, 4], [1.0, 0.6], [(1, 0.0), (0, 5.0), (3, 11.0), (3, 13.0), (2, 20.0), (1, 20.0), (4, 0.6)])
+    assert pk[0] == (2, 0.5)            # @test peek(Q) == (2, 0.5)
+    assert pk[1] == (1, 0.0)            # L[1] = 0.0; @test peek(Q) == (1, 0.)
+    assert pk[2] == (1, 0.0) and pk[3] == (1, 0.0) and pk[4] == (1, 0.0)   # Q[0] = 5.0, Q[3] = 11.0, Q[3] = 13 leave the minimum
+    assert pk[5] == (1, 0.0)
+    assert pk[6] == (4, 0.6)            # head all later than the tail's minimum: the tail wins
+    assert pk[7] == (4, 0.6)
+    # ties: the head wins only with a strictly smaller time (morepriorityqueues.jl:37-41)
+    assert O.queue_script([0.6], 0, [3, 4], [1.0, 0.6], [])[0] == (4, 0.6)
+
+
+def test_indexed_heap_against_brute_force():
+    """SPriorityQueue semantics (src/priorityqueue.jl:44-117): peek is the minimum after any sequence of key updates."""
+    rng = np.random.default_rng(0)
+    n = 200
+    vals = rng.random(n)
+    ops = [(int(rng.integers(1, n + 1)), float(rng.random() * 2)) for _ in range(3000)]
+    pk = O.queue_script([np.inf], 0, np.arange(1, n + 1), vals, ops)
+    cur = vals.copy()
+    assert pk[0][1] == cur.min() and cur[pk[0][0] - 1] == cur.min()
+    for (k, v), (pkey, pval) in zip(ops, pk[1:]):
+        cur[k - 1] = v
+        assert pval == cur.min() and cur[pkey - 1] == pval
