@@ -6,6 +6,7 @@
 // against the sequential oracle (zz_oracle.c, mode ctr|lazy) on a machine without a GPU.  It is not a
 // fallback: the product library (csrc/zzb200.cpp) never links or calls it and fails loudly without CUDA.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -137,6 +138,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
         zz_ctl_init(ctl, std::min(F0, T), T, delta0, target, std::max(0.25 * target, 2.0));
         uint32_t cur = 0;
         std::vector<int32_t> wl, next, touched;
+        bool ovf_seen = false;   // like the kernel (ZZ_OVF_BIT): an overflowing evaluation ends the window at the next pass boundary
         auto handle = [&](int32_t j, const ZzNodeOut& o, uint32_t w0, uint32_t curtag) {
             int slot;
             uint32_t cnt = zz_pick_slot(kin[j].hdr[0], kin[j].hdr[1], w0, curtag, slot);
@@ -167,6 +169,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
             ZzSpec& s = spec[j];
             s.a = o.a; s.b = o.b; s.told = o.told; s.tau = o.tau; s.c = o.c; s.k = o.k;
             s.nprop = (uint16_t)o.nprop; s.nflip = (uint8_t)o.nflip; s.flags = (uint8_t)o.flags;
+            if (o.flags & ZZ_F_OVERFLOW) ovf_seen = true;
             vt[j] = o.viol_t; vl[j] = o.viol_l; vlb[j] = o.viol_lb;
             r->node_evals++;
         };
@@ -178,7 +181,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
             zz_ctl_begin(ctl);
             const uint32_t w0 = cur + 1;
             cur = w0;
-            wl.clear(); next.clear(); touched.clear();
+            wl.clear(); next.clear(); touched.clear(); ovf_seen = false;
             ZzNodeOut o;
             int64_t it = 1;
             for (int64_t j = 0; j < d; ++j) {
@@ -194,7 +197,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
             for (;;) {
                 cur++;
                 wl.swap(next); next.clear();
-                if (wl.empty()) break;
+                if (wl.empty() || ovf_seen) break;
                 ++it;
                 r->pass_hist[std::min<int64_t>(it, 63)] += (int64_t)wl.size();
                 for (int32_t j : wl) {
@@ -206,7 +209,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                 }
             }
             r->iters += it; r->max_iters = std::max(r->max_iters, it);
-            bool overflow = false; double smin = ZZ_INF; unsigned long long nprop = 0;  // accepted flips (length controller)
+            bool overflow = ovf_seen; double smin = ZZ_INF; unsigned long long nprop = 0;  // accepted flips (length controller)
             for (int32_t j : touched) {
                 const ZzSpec& s = spec[j];
                 if (s.flags & ZZ_F_OVERFLOW) overflow = true;

@@ -1,4 +1,4 @@
-# one-shot GPU check of the logistic target (config 3) + regression run of the whole GPU suite
+# GPU check of the logistic target (config 3): parity tests, then timing of 1 / 8 / 64 replicas
 set -x
-timeout 150 python -m pytest tests/test_gpu_zz_logistic.py -x -q -s --runxfail 2>&1 | tail -30
-timeout 100 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_zz_logistic.py 2>&1 | tail -5
+timeout 60 python -m pytest tests/test_gpu_zz_logistic.py -x -q -s 2>&1 | tail -12
+timeout 45 python tools/logit_bench.py 10 1 8 64 2>&1 | tail -6

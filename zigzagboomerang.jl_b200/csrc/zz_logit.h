@@ -89,7 +89,9 @@ ZZ_HD void zz_eval_bnd(const ZzGraph& g, const ZzView& v, int32_t j, double s, i
 
 // Timeline of coordinate j inside the window (zz_process_node_slow with the logistic target): own proposals evaluate the
 // subsampled gradient (src/sfact.jl:118 through the SelfMoving closure), reschedules use ab of fact_samplers.jl:50-54.
-ZZ_HD void zz_process_node_logit(const ZzGraph& g, const ZzView& v, const ZzLogit& L, int32_t j, double H, int incl,
+// List-walking version: every timeline item re-reads the neighbour records from memory (one dependent round trip per entry);
+// used only for columns with more than ZZ_LNB bound / trigger entries.
+ZZ_HD void zz_process_node_logit_walk(const ZzGraph& g, const ZzView& v, const ZzLogit& L, int32_t j, double H, int incl,
                                  uint32_t w0, uint32_t cur, bool first_iter, ZzNodeOut& o)
 {
     double th, tf, xf; uint32_t hh0, hh1;
@@ -150,6 +152,164 @@ ZZ_HD void zz_process_node_logit(const ZzGraph& g, const ZzView& v, const ZzLogi
     o.a = a; o.b = b; o.told = told; o.tau = tau; o.c = c;
     o.k = k; o.nprop = nprop; o.nflip = nflip; o.flags = flags;
     o.hdr0 = hh0; o.hdr1 = hh1; o.nitems = nitems;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Gather-first version (what zz_fast.h does for short columns, for columns of up to ZZ_LNB bound / trigger entries): the
+// records of the neighbours that enter the bound or reschedule j are fetched ONCE per evaluation, in batches of independent
+// loads, into a per-thread scratch (local memory, L1-resident); their recorded flips are merged into one pool ordered by
+// (time, coordinate) and applied incrementally, so a timeline item costs arithmetic over the scratch instead of a chain of
+// L2 round trips per neighbour.  Same operations in the same order as the list-walking version -- bit-identical results.
+// (Measured with the list-walking version alone: 2.6 ms per relaxation pass on config 3, whose dense regressors have 147
+// bound entries and are dirtied by every flip.)
+#define ZZ_LNB 192     // cached bound / trigger entries of column j (j included)
+#define ZZ_LPOOL 32    // neighbour flips merged per coordinate and window
+#define ZZ_LBATCH 8    // neighbour records fetched together
+
+struct ZzLHood {
+    int n;
+    int32_t idx[ZZ_LNB];
+    double wb[ZZ_LNB];
+    uint8_t fl[ZZ_LNB];
+    double th[ZZ_LNB], tf[ZZ_LNB], xf[ZZ_LNB];
+};
+
+struct ZzLPool {
+    int n;
+    double t[ZZ_LPOOL];
+    int32_t id[ZZ_LPOOL];   // flipping coordinate
+    int32_t m[ZZ_LPOOL];    // its position in the scratch
+};
+
+ZZ_HD void zz_lpool_add(ZzLPool& pool, double fs, int32_t id, int32_t m, uint32_t& flags)
+{
+    int p = pool.n;
+    if (p == ZZ_LPOOL) {   // full: the window will be retried shorter; keep the EARLIEST flips so that what is evaluated stays causal
+        flags |= ZZ_F_OVERFLOW;
+        if (!(pool.t[p - 1] > fs || (pool.t[p - 1] == fs && pool.id[p - 1] > id))) return;
+        pool.n = --p;
+    }
+    while (p > 0 && (pool.t[p - 1] > fs || (pool.t[p - 1] == fs && pool.id[p - 1] > id))) {
+        pool.t[p] = pool.t[p - 1]; pool.id[p] = pool.id[p - 1]; pool.m[p] = pool.m[p - 1];
+        --p;
+    }
+    pool.t[p] = fs; pool.id[p] = id; pool.m[p] = m; pool.n++;
+}
+
+ZZ_HD void zz_process_node_logit(const ZzGraph& g, const ZzView& v, const ZzLogit& L, int32_t j, double H, int incl,
+                                 uint32_t w0, uint32_t cur, bool first_iter, ZzNodeOut& o)
+{
+    // ---- which entries of the merged list are cached: bound or trigger ones (target-only entries are read on demand)
+    ZzLHood hd;
+    {
+        int n = 0;
+        const int32_t e1 = g.nptr[j + 1];
+        for (int32_t e = g.nptr[j]; e < e1; ++e) {
+            const uint32_t fl = g.nfl[e];
+            if (!(fl & (ZZ_NB_BND | ZZ_NB_TRIG))) continue;
+            if (n == ZZ_LNB) { zz_process_node_logit_walk(g, v, L, j, H, incl, w0, cur, first_iter, o); return; }
+            hd.idx[n] = g.nidx[e]; hd.fl[n] = (uint8_t)fl; hd.wb[n] = g.nwb[e];
+            ++n;
+        }
+        hd.n = n;
+    }
+    ZzOwn w;
+    zz_load_own(v, j, w);
+    // ---- gather: ZZ_LBATCH records at a time (independent loads in flight), then their flip lists into the pool
+    ZzLPool pool; pool.n = 0;
+    uint32_t flags = 0;
+    for (int b0 = 0; b0 < hd.n; b0 += ZZ_LBATCH) {
+        double bth[ZZ_LBATCH], btf[ZZ_LBATCH], bxf[ZZ_LBATCH]; uint32_t bh0[ZZ_LBATCH], bh1[ZZ_LBATCH];
+#pragma unroll
+        for (int q = 0; q < ZZ_LBATCH; ++q) {
+            bth[q] = 0.0; btf[q] = 0.0; bxf[q] = 0.0; bh0[q] = 0; bh1[q] = 0;
+            if (b0 + q < hd.n && hd.idx[b0 + q] != j) zz_ld_kin(zz_kin_at<false>(v, hd.idx[b0 + q]), bth[q], btf[q], bxf[q], bh0[q], bh1[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < ZZ_LBATCH; ++q) {
+            if (b0 + q < hd.n) {
+                const int m = b0 + q;
+                hd.th[m] = bth[q]; hd.tf[m] = btf[q]; hd.xf[m] = bxf[q];
+                if (!first_iter && hd.idx[m] != j) {
+                    int slot;
+                    const uint32_t cnt = zz_pick_slot(bh0[q], bh1[q], w0, cur, slot);
+                    if (cnt) {
+                        const double* fl = zz_flips_at<false>(v, hd.idx[m]) + slot * ZZ_MAXFLIP;
+                        for (uint32_t r = 0; r < cnt; ++r) zz_lpool_add(pool, zz_ld(fl + r), hd.idx[m], m, flags);
+                    }
+                }
+            }
+        }
+    }
+
+    double th = w.th, tf = w.tf, xf = w.xf;
+    double a = w.a, b = w.b, told = w.told, c = w.c;
+    double c100 = c / 100;
+    double tau = w.tau;
+    uint32_t k = w.k;
+    const double gmu = g.gmu[j];
+    uint32_t nprop = 0, nflip = 0, nitems = 0;
+    o.viol_t = 0.0; o.viol_l = 0.0; o.viol_lb = 0.0;
+    o.interior = 0u;
+    int p = 0;
+    for (int item = 0;; ++item) {
+        const double nt = p < pool.n ? pool.t[p] : ZZ_INF;
+        const int32_t ni = p < pool.n ? pool.id[p] : 0x7fffffff;
+        const bool own = (tau < nt) || (tau == nt && j < ni);
+        const double s = own ? tau : nt;
+        if (!(s < H || (incl && s == H))) break;
+        if (item >= ZZ_MAXITEMS) { flags |= ZZ_F_OVERFLOW; break; }
+        if (!own) {   // a cached neighbour flips at s: advance its anchor; reschedule j only if it is a trigger
+            const int m = pool.m[p];
+            hd.xf[m] = hd.xf[m] + hd.th[m] * (s - hd.tf[m]);
+            hd.tf[m] = s;
+            hd.th[m] = -hd.th[m];
+            ++p;
+            if (!(hd.fl[m] & ZZ_NB_TRIG)) continue;
+        }
+        ++nitems;
+        const double xs = xf + th * (s - tf);
+        double gt = 0.0;
+        if (own) gt = zz_logit_grad(L, v, j, s, xs, w0, cur, k);   // draws k .. k + L.k - 1
+        // idot(Z.Gamma, j, x(s)), idot(Z.Gamma, j, theta) with +own / -own velocity, storage order (common.jl:16-24)
+        double ax = 0.0, ap = 0.0, am = 0.0;
+        for (int m = 0; m < hd.n; ++m) {
+            if (!(hd.fl[m] & ZZ_NB_BND)) continue;
+            const double wb = hd.wb[m];
+            if (hd.idx[m] == j) { ax += wb * xs; ap += wb * th; am += wb * (-th); }
+            else {
+                const double x = hd.xf[m] + hd.th[m] * (s - hd.tf[m]);
+                ax += wb * x; ap += wb * hd.th[m]; am += wb * hd.th[m];
+            }
+        }
+        double gth = ap;
+        if (own) {
+            const double l = zz_pos(gt * th);                 // fact_samplers.jl:28-30
+            const double lb = zz_pos(a + b * (s - told));     // sfact.jl:70
+            const double u = zz_u01(v.seed0, v.seed1, (uint64_t)j, k++);
+            nprop++;
+            if (u * lb < l) {                                 // sfact.jl:121
+                if (l >= lb) {                                // sfact.jl:123-128
+                    if (v.adapt) { c *= v.factor; c100 = c / 100; }
+                    else if (!(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
+                }
+                if (nflip == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#pragma unroll
+                for (int m = 0; m < ZZ_MAXFLIP; ++m)
+                    if (m == (int)nflip) o.fl[m] = s;
+                nflip++;
+                xf = xs; tf = s; th = -th;                    // dynamics.jl:46-49
+                gth = am;
+            }
+        }
+        a = c + (ax - gmu) * th;                              // fact_samplers.jl:51
+        b = c100 + th * gth;                                  // fact_samplers.jl:52
+        told = s;
+        tau = s + zz_poisson_time(a, b, zz_u01(v.seed0, v.seed1, (uint64_t)j, k++));   // sfact.jl:134,139
+    }
+    o.a = a; o.b = b; o.told = told; o.tau = tau; o.c = c;
+    o.k = k; o.nprop = nprop; o.nflip = nflip; o.flags = flags;
+    o.hdr0 = w.hdr0; o.hdr1 = w.hdr1; o.nitems = nitems;
 }
 
 #endif  // ZZ_LOGIT_H
