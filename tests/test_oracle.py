@@ -290,3 +290,53 @@ def test_indexed_heap_against_brute_force():
     for (k, v), (pkey, pval) in zip(ops, pk[1:]):
         cur[k - 1] = v
         assert pval == cur.min() and cur[pkey - 1] == pval
+
+
+@pytest.mark.parametrize("mode", [O.RNG_SEQ | O.ARITH_INPLACE, O.PARITY_MODE])
+def test_maintest_selfmoving_moments(zzb, mode):
+    """test/maintest.jl:64-83 ("SZigZagSelfMoving"): speeds in {0.5, 1}, c = 0.8 ||Gamma[:, i]||, the SelfMoving closure
+    `idot_moving!` (src/common.jl:33-42) -- the same partial derivative, coordinates advanced by the closure itself (mode
+    inplace) resp. read from their flip anchors (mode lazy)."""
+    d, T = 8, 1000.0
+    G = zzb.random_spd(d, seed=2)
+    rng = np.random.default_rng(6)
+    x0 = rng.random(d)
+    th0 = rng.choice(np.array([-1.0, -0.5, 0.5, 1.0]), d)
+    r = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, T, 0.8 * G.colnorms(), seed=(21, 22), mode=mode)
+    _cov_check(r, zzb, G, x0, th0, T, 2.0, 2.5)
+
+
+@pytest.mark.parametrize("mode", [O.RNG_SEQ | O.ARITH_INPLACE | O.GRAPH_ALL, O.PARITY_MODE])
+def test_maintest_independent_bound_moments(zzb, mode):
+    """test/maintest.jl:280-301 ("ZigZag (independent)"): the sampler matrix is the identity (G1[i] = {i}: a flip reschedules
+    nobody else, the bound ignores the couplings) with c = 10 ||Gamma[:, i]|| to keep it valid; pdmp."""
+    d, T = 8, 1000.0
+    G = zzb.random_spd(d, seed=2)
+    Id = zzb.CSC.from_dense(np.eye(d))
+    rng = np.random.default_rng(7)
+    x0 = rng.random(d)
+    th0 = rng.choice(np.array([-1.0, 1.0]), d)
+    # full-entropy seed words: a xoroshiro state with a few low bits set returns u = 0 for its first draws, poisson_time(a, b, 0)
+    # is Inf (as upstream), and with G1[i] = {i} nobody ever reschedules such a coordinate -- upstream seeds with gen_seed
+    r = O.spdmp(G, Id, 0.0, x0, th0, T, 10.0 * G.colnorms(), seed=(0x9E3779B97F4A7C15, 0xD1B54A32D192ED03), mode=mode)
+    _cov_check(r, zzb, G, x0, th0, T, 2.0, 2.5)
+
+
+def test_schedule_emulation_with_an_unrelated_bound_pattern(zzb):
+    """Target and sampler matrices with different sparsity patterns (identity bound, maintest.jl:280-301): the merged
+    neighbour lists carry target-only entries; the windowed schedule still equals the sequential loop bit for bit."""
+    d = 8
+    G = zzb.random_spd(d, seed=2)
+    Id = zzb.CSC.from_dense(np.eye(d))
+    rng = np.random.default_rng(7)
+    x0, th0 = rng.random(d), rng.choice(np.array([-1.0, 1.0]), d)
+    c = 10.0 * G.colnorms()
+    ref = O.spdmp(G, Id, 0.0, x0, th0, 60.0, c, seed=(31, 32))
+    sim = O.window_sim(G, Id, 0.0, x0, th0, 60.0, c, seed=(31, 32))
+    O.assert_same_run(ref, sim)
+    Gs = zzb.random_sparse_spd(40, deg=3, seed=4)
+    Is = zzb.CSC.from_dense(np.diag(np.linspace(0.5, 2.0, 40)))
+    x0, th0 = rng.standard_normal(40), rng.choice(np.array([-1.0, -0.5, 0.5, 1.0]), 40)
+    ref = O.spdmp(Gs, Is, 0.0, x0, th0, 25.0, 12.0 * Gs.colnorms(), seed=(1, 2), adapt=True)
+    sim = O.window_sim(Gs, Is, 0.0, x0, th0, 25.0, 12.0 * Gs.colnorms(), seed=(1, 2), adapt=True)
+    O.assert_same_run(ref, sim)
