@@ -7,8 +7,9 @@ import numpy as np
 import oracle_lib as O
 
 
-def run_cases(z, ncases, seed, verbose=False):
-    """Returns (failures, bound_errors); prints failing cases."""
+def run_cases(z, ncases, seed, verbose=False, sim=False):
+    """Returns (failures, bound_errors); prints failing cases.  sim = True: instead of the CUDA path, the host emulation of the
+    device schedule (oracle/zz_window_sim.cpp: the kernels' own per-coordinate code) is compared with the oracle -- no GPU."""
     rng = np.random.default_rng(seed)
     nb = [0]
     class R:
@@ -54,12 +55,19 @@ def run_cases(z, ncases, seed, verbose=False):
             c = np.full(d, float(rng.choice([0.05, 0.5, 2.0])))
         desc = f"case {case}: {kind} d={d} T={T} adapt={adapt} cs={cs} mu={mu is not None} h={h is not None} tune={tune}"
         tgt = z.GaussianPotential(G, h)
+
+        def sim_fn(**kw):
+            tk = {k: v for k, v in (tune or {}).items() if k in ("target_frac", "delta0", "tag_limit")}
+            r = O.window_sim(G, Zg, 0.0, x0, th0, T, c, h=h, mu=mu, seed=sd, **tk, **kw)
+            return r.events, r.t, r.x, r.theta, r.c, r.acc, r.num
         if kind == "sticky":
             kappa = np.full(d, float(rng.choice([0.3, 1.0, 5.0])))
             c = 3.0 * G.colnorms() + (np.abs(h) if h is not None else 0.0)
             ref_fn = lambda: O.spdmp(G, Zg, 0.0, x0, th0, T, c, h=h, seed=sd, kappa=kappa)
 
             def dev_fn():
+                if sim:
+                    return sim_fn(kappa=kappa)
                 Xi, (t, x, th), (acc, num), cc = z.sspdmp(tgt, 0.0, x0, th0, T, c, z.ZigZag(Zg, np.zeros(d)), kappa, seed=sd, tune=tune)
                 return Xi.events, t, x, th, cc, Xi.acc_per_coordinate, num
         elif kind == "boomerang":
@@ -69,6 +77,8 @@ def run_cases(z, ncases, seed, verbose=False):
             ref_fn = lambda: O.spdmp(G, Zg, 0.0, x0, th0, T, c, h=h, mu=mu, seed=sd, adapt=adapt, boom=boom)
 
             def dev_fn():
+                if sim:
+                    return sim_fn(boom=boom, adapt=adapt)
                 F = z.FactBoomerang(Zg, np.zeros(d) if mu is None else mu, boom[1], boom[0], rho=boom[2])
                 Xi, (t, x, th), (acc, num), cc = z.spdmp(tgt, 0.0, x0, th0, T, c, F, seed=sd, adapt=adapt, tune=tune)
                 return Xi.events, t, x, th, cc, acc, num
@@ -77,6 +87,8 @@ def run_cases(z, ncases, seed, verbose=False):
             ref_fn = lambda: O.spdmp(G, Zg, 0.0, x0, th0, T, c, h=h, mu=mu, seed=sd, adapt=adapt, mode=mode)
 
             def dev_fn():
+                if sim:
+                    return sim_fn(adapt=adapt, local_bound=(kind == "localbound"))
                 cc_in = z.LocalBound(c) if kind == "localbound" else c
                 Xi, (t, x, th), (acc, num), cc = z.spdmp(tgt, 0.0, x0, th0, T, cc_in, z.ZigZag(Zg, np.zeros(d) if mu is None else mu),
                                                          seed=sd, adapt=adapt, tune=tune)
@@ -88,7 +100,7 @@ def run_cases(z, ncases, seed, verbose=False):
             ref = None
         try:
             out = dev_fn()
-        except z.BoundError:
+        except (z.BoundError, O.BoundError):
             out = None
         try:
             assert (ref is None) == (out is None), "bound violation reported by one side only"

@@ -115,3 +115,12 @@ def test_lattice_column_multiply_shift_is_exact():
     L.zzw_check_grid_col.argtypes = [C.c_int32, C.c_int64]
     for M in (1, 2, 3, 5, 7, 12, 100, 255, 256, 257, 1000, 1023, 1024, 1025, 4097, 46341, 65535, 65536, 1 << 20, (1 << 31) - 1):
         assert L.zzw_check_grid_col(M, 3_000_000) == 0, M
+
+
+def test_random_campaign_emulation_equals_oracle(zzb):
+    """The randomised campaign of tests/fuzz_cases.py (random lattices / sparse graphs, ZigZag / LocalBound / sticky / Boomerang,
+    mu, h, scaled sampler matrix, window policies, bounds that are violated) with the host emulation of the device schedule in
+    place of the CUDA path: the kernels' per-coordinate code against the sequential oracle, bit for bit, without a GPU."""
+    import fuzz_cases
+    bad, nbound = fuzz_cases.run_cases(zzb, 150, 4, sim=True)
+    assert bad == 0
