@@ -925,6 +925,116 @@ zzo_run *zzo_sparsestickyzz(int64_t d, const int64_t *g_colptr, const int64_t *g
     return r;
 }
 
+/* ---- the same sampler in the parity arithmetic (mode ctr|lazy): the contract a device kernel for the strong-bound sticky
+ * sampler has to reproduce bit for bit (none exists yet; config 4 runs on the ss_fact.jl kernel).  Differences to the
+ * faithful restatement above, all equal in law:
+ *   * per-coordinate counter streams u(i, k) (zz_math.h): coordinate i draws, in the order of ITS OWN events, the thaw
+ *     waiting time when it freezes (and at t = 0 if it starts frozen), [rule :reversible: the sign at a thaw], the time of
+ *     its next proposal whenever it is queued, and the thinning uniform of a proposal;
+ *   * one Exp(kappa) thaw clock PER frozen coordinate instead of one clock of rate kappa * #frozen with a uniform pick
+ *     (:218,291-298) -- the superposition of the former is the latter;
+ *   * flip-anchored positions x_k(s) = xf_k + th_k (s - tf_k), rewritten only when the velocity of k changes (thaw, hit,
+ *     accepted reflection); a frozen coordinate sits at 0; ties in time are broken by coordinate;
+ *   * adapt is refused (the adapted bound is ONE global c, :336,383: its value depends on the global event order).
+ * A reflection still reschedules nobody but the reflecting coordinate: in the windowed scheme of the device the timeline of
+ * a coordinate then has OWN items only, and neighbours enter through the positions read at those items. */
+zzo_run *zzo_sparsestickyzz_ctr(int64_t d, const int64_t *g_colptr, const int64_t *g_rowval, const double *g_nzval, const double *h,
+                                const double *x0, const double *th0, double T, double c, double kappa, int rule,
+                                const uint64_t *seed)
+{
+    zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run));
+    csc G = { g_colptr, g_rowval, g_nzval };
+    size_t nb = (size_t)d * sizeof(double);
+    r->d = d;
+    char *active = (char *)calloc((size_t)d, 1), *psign = (char *)malloc((size_t)d), *action = (char *)calloc((size_t)d, 1);
+    double *tf = (double *)calloc((size_t)d, 8), *xf = (double *)calloc((size_t)d, 8), *th = (double *)calloc((size_t)d, 8);
+    double *bt = (double *)calloc((size_t)d, 8), *ba = (double *)calloc((size_t)d, 8), *bexp = (double *)calloc((size_t)d, 8);
+    uint32_t *kc = (uint32_t *)calloc((size_t)d, sizeof(uint32_t));
+    r->acc = (int64_t *)calloc((size_t)d, sizeof(int64_t));
+    r->x0 = (double *)malloc(nb); memcpy(r->x0, x0, nb);
+    r->c = (double *)malloc(nb);
+    heapq Q; Q.n = 0; Q.lex = 1;
+    Q.key = (int64_t *)malloc(((size_t)d + 2) * sizeof(int64_t));
+    Q.val = (double *)malloc(((size_t)d + 2) * sizeof(double));
+    Q.index = (int64_t *)calloc((size_t)d + 2, sizeof(int64_t));
+    enum { C_HIT = 0, C_REFLECT = 1, C_RENEW = 2, C_THAW = 3 };
+#define SC_U(i) zz_u01(seed[0], seed[1], (uint64_t)((i) - 1), kc[(i) - 1]++)
+#define SC_POS(k, s) (active[(k) - 1] ? xf[(k) - 1] + th[(k) - 1] * ((s) - tf[(k) - 1]) : 0.0)
+#define SC_GRAD(i, s, out) do { double acc_ = 0.0; \
+        for (int64_t q_ = G.colptr[(i) - 1]; q_ < G.colptr[(i)]; ++q_) { int64_t k_ = G.rowval[q_ - 1]; acc_ += G.nzval[q_ - 1] * SC_POS(k_, (s)); } \
+        (out) = h ? acc_ - h[(i) - 1] : acc_; } while (0)
+    /* ab (:136-142) at time s, then queue_time! (:144-172) */
+#define SC_QUEUE(i, s, gi) do { \
+        ba[(i) - 1] = c + (gi) * th[(i) - 1]; bt[(i) - 1] = (s); bexp[(i) - 1] = (s) + 1.0 / c; \
+        double xs_ = SC_POS((i), (s)); \
+        double trefl_ = (s) + zzo_poisson_time3(ba[(i) - 1], 0.0, 0.01, SC_U(i)); \
+        double thit_ = (th[(i) - 1] * xs_ >= 0) ? INFINITY : (s) - xs_ / th[(i) - 1]; \
+        double tau_ = bexp[(i) - 1] < trefl_ ? bexp[(i) - 1] : trefl_; \
+        if (thit_ < tau_) tau_ = thit_; \
+        action[(i) - 1] = (thit_ == tau_) ? C_HIT : (trefl_ == tau_) ? C_REFLECT : C_RENEW; \
+        if (Q.index[(i)]) h_set(&Q, (i), tau_); else h_enqueue(&Q, (i), tau_); } while (0)
+    for (int64_t k = 0; k < d; ++k) {
+        psign[k] = 1;
+        if (x0[k] != 0) { active[k] = 1; xf[k] = x0[k]; th[k] = th0[k]; psign[k] = th0[k] > 0; }
+    }
+    for (int64_t i = 1; i <= d; ++i) {
+        if (active[i - 1]) { double gi; SC_GRAD(i, 0.0, gi); SC_QUEUE(i, 0.0, gi); }
+        else { action[i - 1] = C_THAW; h_enqueue(&Q, i, 0.0 - zz_log(SC_U(i)) / kappa); }
+    }
+    double tp = 0.0; int64_t num = 0;
+    const double tl0 = now_s();
+    while (tp < T && r->status == ZZO_OK) {
+        for (;;) {
+            int64_t i = Q.key[1]; tp = Q.val[1];
+            double gi;
+            if (action[i - 1] == C_THAW) {
+                double vi = rule == 1 ? (SC_U(i) < 0.5 ? -1.0 : 1.0) : -1.0 + 2.0 * (double)psign[i - 1];
+                active[i - 1] = 1; tf[i - 1] = tp; xf[i - 1] = 0.0; th[i - 1] = vi;
+                SC_GRAD(i, tp, gi); SC_QUEUE(i, tp, gi);
+                push_event(r, tp, i, 0.0, vi);
+                break;
+            }
+            if (action[i - 1] == C_HIT) {
+                if (fabs(SC_POS(i, tp)) > 1e-7) { r->status = 9; break; }
+                active[i - 1] = 0; tf[i - 1] = tp; xf[i - 1] = 0.0; th[i - 1] = 0.0;
+                action[i - 1] = C_THAW;
+                h_set(&Q, i, tp - zz_log(SC_U(i)) / kappa);
+                push_event(r, tp, i, 0.0, 0.0);
+                break;
+            }
+            SC_GRAD(i, tp, gi);
+            double l = zz_pos(gi * th[i - 1]), lb = zz_pos(ba[i - 1]);
+            if (action[i - 1] == C_RENEW) {
+                if (l > lb) { r->status = ZZO_E_BOUND; r->err_i = i; r->err_t = tp; r->err_l = l; r->err_lb = lb; break; }
+                SC_QUEUE(i, tp, gi);
+                continue;
+            }
+            num++;
+            if (SC_U(i) * lb < l) {
+                r->acc[i - 1]++;
+                if (l > lb) { r->status = ZZO_E_BOUND; r->err_i = i; r->err_t = tp; r->err_l = l; r->err_lb = lb; break; }
+                xf[i - 1] = SC_POS(i, tp); tf[i - 1] = tp; th[i - 1] = -th[i - 1];
+                if (rule == 0) psign[i - 1] = th[i - 1] > 0;
+                SC_GRAD(i, tp, gi); SC_QUEUE(i, tp, gi);
+                push_event(r, tp, i, xf[i - 1], th[i - 1]);
+                break;
+            }
+            SC_QUEUE(i, tp, gi);
+        }
+    }
+#undef SC_U
+#undef SC_POS
+#undef SC_GRAD
+#undef SC_QUEUE
+    r->loop_seconds = now_s() - tl0;
+    r->num = num;
+    for (int64_t k = 0; k < d; ++k) r->c[k] = c;
+    r->t = tf; r->x = xf; r->th = th;
+    free(active); free(psign); free(action); free(bt); free(ba); free(bexp); free(kc);
+    free(Q.key); free(Q.val); free(Q.index);
+    return r;
+}
+
 /* =====================================================================================================
  * Factorised Boomerang in spdmp / pdmp (src/sfact.jl:29-48,73-145,162-212 with F::FactBoomerang):
  *   flow                     sfact.jl:29-38 / dynamics.jl:29-36 (rotation of (x - mu, theta), `sincos` -> zz_sincos)

@@ -52,6 +52,8 @@ def lib():
         L.zzo_exp.argtypes = [C.c_double]
         L.zzo_sparsestickyzz.restype = C.c_void_p
         L.zzo_sparsestickyzz.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_void_p]
+        L.zzo_sparsestickyzz_ctr.restype = C.c_void_p
+        L.zzo_sparsestickyzz_ctr.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
         L.zzo_queue_script.restype = None
         L.zzo_queue_script.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_int64, C.c_void_p, C.c_void_p]
@@ -205,10 +207,23 @@ def _collect(L, r, d, t0, x0, theta0):
     return out
 
 
-def sparsestickyzz(G, x0, theta0, T, c, kappa, *, h=None, rule="sticky", adapt=False, multiplier=1.5, seed=(1, 2)):
+def sparsestickyzz(G, x0, theta0, T, c, kappa, *, h=None, rule="sticky", adapt=False, multiplier=1.5, seed=(1, 2), ctr=False):
     """The reference's sparse sticky ZigZag (src/sparsestickyzz.jl, `sspdmp3`), restated for the CPU (faithful draw order,
-    mode seq).  Scalar ``c`` and ``kappa``; ``theta0`` gives the velocities of the coordinates with ``x0 != 0``."""
+    mode seq).  Scalar ``c`` and ``kappa``; ``theta0`` gives the velocities of the coordinates with ``x0 != 0``.
+    ``ctr=True``: the parity arithmetic (per-coordinate streams and thaw clocks, flip-anchored positions)."""
     L = lib()
+    if ctr:
+        assert not adapt
+        d = G.n
+        x0c, th0c = np.ascontiguousarray(x0, dtype=np.float64), np.ascontiguousarray(theta0, dtype=np.float64)
+        hc = None if h is None else np.ascontiguousarray(h, dtype=np.float64)
+        sd = np.array(seed, dtype=np.uint64)
+        r = L.zzo_sparsestickyzz_ctr(d, _p(G.colptr), _p(G.rowval), _p(G.nzval), _p(hc), _p(x0c), _p(th0c), float(T), float(c), float(kappa),
+                                     {"sticky": 0, "reversible": 1}[rule], _p(sd))
+        try:
+            return _collect(L, r, d, 0.0, x0c, th0c)
+        finally:
+            L.zzo_free(r)
     d = G.n
     f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     x0, theta0 = f8(x0), f8(theta0)

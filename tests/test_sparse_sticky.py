@@ -91,3 +91,27 @@ def test_nonzero_start_and_linear_term(zzb):
     r0 = O.sparsestickyzz(G, x0, np.ones(p), 3000.0, 4.0, 0.3, seed=(1, 2))
     occ0, _ = occupancy(r0.events, p, x0, 3000.0)
     assert occ.mean() > occ0.mean() + 0.05     # the pull of h keeps coordinates away from 0 longer
+
+
+@pytest.mark.parametrize("rule", ["sticky", "reversible"])
+def test_parity_arithmetic_has_the_same_law(zzb, rule):
+    """zzo_sparsestickyzz_ctr (per-coordinate streams and thaw clocks, flip-anchored positions -- the contract of a future
+    strong-bound device kernel) against the faithful restatement: occupancy, second moments, event and proposal rates."""
+    p, kappa, T = 30, 0.5, 12000.0
+    G = chain_precision(zzb, p)
+    x0 = np.zeros(p)
+    a = O.sparsestickyzz(G, x0, np.ones(p), T, 2.5, kappa, rule=rule, seed=(3, 4))
+    b = O.sparsestickyzz(G, x0, np.ones(p), T, 2.5, kappa, rule=rule, seed=(3, 4), ctr=True)
+    oa, ma = occupancy(a.events, p, x0, T)
+    ob, mb = occupancy(b.events, p, x0, T)
+    assert abs(oa.mean() - ob.mean()) < 0.01 and np.abs(oa - ob).max() < 0.04
+    assert abs(ma.mean() - mb.mean()) < 0.04 * mb.mean()
+    assert abs(len(a.events) - len(b.events)) < 0.02 * len(b.events) and abs(a.num - b.num) < 0.02 * b.num
+    # deterministic in the seed, different across seeds; a non-zero start is honoured
+    b2 = O.sparsestickyzz(G, x0, np.ones(p), 200.0, 2.5, kappa, rule=rule, seed=(3, 4), ctr=True)
+    b3 = O.sparsestickyzz(G, x0, np.ones(p), 200.0, 2.5, kappa, rule=rule, seed=(3, 5), ctr=True)
+    assert np.array_equal(b2.events, b.events[: len(b2.events)]) and not np.array_equal(b3.events["t"][:20], b2.events["t"][:20])
+    x1 = np.where(np.arange(p) % 3 == 0, 0.7, 0.0)
+    b4 = O.sparsestickyzz(G, x1, -np.ones(p), 50.0, 2.5, kappa, rule=rule, seed=(1, 2), ctr=True)
+    first = {int(i): (x, th) for t, i, x, th in b4.events[::-1]}
+    assert all(first[j + 1][0] != 0.0 or first[j + 1][1] == 0.0 for j in range(p) if x1[j] != 0 and (j + 1) in first)
