@@ -989,17 +989,19 @@ zzo_run *zzo_sparsestickyzz_ctr(int64_t d, const int64_t *g_colptr, const int64_
             double gi;
             if (action[i - 1] == C_THAW) {
                 double vi = rule == 1 ? (SC_U(i) < 0.5 ? -1.0 : 1.0) : -1.0 + 2.0 * (double)psign[i - 1];
-                active[i - 1] = 1; tf[i - 1] = tp; xf[i - 1] = 0.0; th[i - 1] = vi;
+                active[i - 1] = 1; tf[i - 1] = tp; th[i - 1] = vi;   /* xf stays the (signed) zero of the hit / of x0 */
                 SC_GRAD(i, tp, gi); SC_QUEUE(i, tp, gi);
-                push_event(r, tp, i, 0.0, vi);
+                push_event(r, tp, i, xf[i - 1], vi);
                 break;
             }
             if (action[i - 1] == C_HIT) {
                 if (fabs(SC_POS(i, tp)) > 1e-7) { r->status = 9; break; }
-                active[i - 1] = 0; tf[i - 1] = tp; xf[i - 1] = 0.0; th[i - 1] = 0.0;
+                /* the frozen record is x = -0*theta, theta = 0 -- the signed zero the sticky kernels commit (ss_fact.jl:92); the
+                   reference's record of a deleted coordinate is (t', 0.0, 0.0) (:20-26): equal up to the sign of zero */
+                active[i - 1] = 0; tf[i - 1] = tp; xf[i - 1] = -0.0 * th[i - 1]; th[i - 1] = 0.0;
                 action[i - 1] = C_THAW;
                 h_set(&Q, i, tp - zz_log(SC_U(i)) / kappa);
-                push_event(r, tp, i, 0.0, 0.0);
+                push_event(r, tp, i, xf[i - 1], 0.0);
                 break;
             }
             SC_GRAD(i, tp, gi);

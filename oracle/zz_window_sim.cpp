@@ -18,6 +18,7 @@
 #include "../zigzagboomerang.jl_b200/csrc/zz_ctl.h"
 #include "../zigzagboomerang.jl_b200/csrc/zz_host_graph.h"
 #include "../zigzagboomerang.jl_b200/csrc/zz_host_logit.h"
+#include "../zigzagboomerang.jl_b200/csrc/zz_strong.h"
 
 struct zzw_event { double t; int64_t i; double x; double th; };
 
@@ -39,7 +40,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                    const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
                    const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
                    int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound, const double* kappa,
-                   const double* boom_sigma, double boom_lambdaref, double boom_rho, const ZzHostLogit* hl);
+                   const double* boom_sigma, double boom_lambdaref, double boom_rho, const ZzHostLogit* hl, const ZzStrong* st = nullptr);
 
 extern "C" {
 
@@ -79,13 +80,26 @@ zzw_run* zzw_spdmp_logistic(int64_t d, int64_t n, const int64_t* acp, const int6
                     seed, adapt, factor, delta0, target_frac, tag_limit | 0x80000000u, 0, nullptr, nullptr, 0.0, 0.0, &hl);
 }
 
+// the schedule with the strong-bound sparse sticky timeline (zz_strong.h; contract: zzo_sparsestickyzz_ctr).  Coordinates with
+// x0 == 0 start frozen (velocity 0 in their record); scalar c and kappa.
+zzw_run* zzw_sparsesticky(int64_t d, const int64_t* gcp, const int64_t* grv, const double* gnz, const double* h, const double* x0,
+                          const double* th0, double T, double c, double kappa, int rule, const uint64_t* seed, double delta0,
+                          double target_frac, uint32_t tag_limit)
+{
+    ZzStrong st; st.c = c; st.kappa = kappa; st.rule = rule; st.pad = 0;
+    std::vector<double> th((size_t)d), cv((size_t)d, c), kap((size_t)d, kappa), zero((size_t)d, 0.0);
+    for (int64_t j = 0; j < d; ++j) th[j] = (x0[j] != 0.0) ? th0[j] : 0.0;
+    return zzw_impl(d, gcp, grv, gnz, h, gcp, grv, gnz, zero.data(), 0.0, x0, th.data(), T, cv.data(), seed, 0, 1.0, delta0, target_frac,
+                    tag_limit | 0x80000000u, 0, kap.data(), nullptr, 0.0, 0.0, nullptr, &st);
+}
+
 }  // extern "C"
 
 static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, const double* tnz, const double* h,
                    const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
                    const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
                    int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound, const double* kappa,
-                   const double* boom_sigma, double boom_lambdaref, double boom_rho, const ZzHostLogit* hl)
+                   const double* boom_sigma, double boom_lambdaref, double boom_rho, const ZzHostLogit* hl, const ZzStrong* st)
 {
     zzw_run* r = new zzw_run();
     r->d = d;
@@ -129,8 +143,12 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
         priv[j].c = c_in[j];
     }
     double F0 = ZZ_INF;
-    for (int64_t j = 0; j < d; ++j) { if (v.boom) zz_init_node_boom(g, v, (int32_t)j, t0); else zz_init_node(g, v, (int32_t)j, t0);
-        F0 = std::min(F0, tau[j]); }
+    for (int64_t j = 0; j < d; ++j) {
+        if (st) { if (!zz_init_node_strong(g, v, *st, (int32_t)j, t0)) { r->status = 1; r->msg = "column too long"; return r; } }
+        else if (v.boom) zz_init_node_boom(g, v, (int32_t)j, t0);
+        else zz_init_node(g, v, (int32_t)j, t0);
+        F0 = std::min(F0, tau[j]);
+    }
     if (!(t0 < T)) goto finish;  // while t' < T never entered (sfact.jl:199)
     {
         ZzCtl ctl;
@@ -189,7 +207,8 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                 if (tj < ctl.H || (ctl.incl && tj == ctl.H)) {
                     // dirtied already by an earlier node of this pass? then it is in `next` as well; fine.
                     if (dstamp[j] < w0) { dstamp[j] = cur; touched.push_back((int32_t)j); }
-                    if (hl) zz_process_node_logit(g, v, lg, (int32_t)j, ctl.H, ctl.incl, w0, cur, true, o);
+                    if (st) zz_process_node_strong(g, v, *st, (int32_t)j, ctl.H, ctl.incl, w0, cur, true, o);
+                    else if (hl) zz_process_node_logit(g, v, lg, (int32_t)j, ctl.H, ctl.incl, w0, cur, true, o);
                     else zz_process_node(g, v, (int32_t)j, ctl.H, ctl.incl, w0, cur, true, o);
                     handle((int32_t)j, o, w0, cur);
                 }
@@ -202,7 +221,8 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                 r->pass_hist[std::min<int64_t>(it, 63)] += (int64_t)wl.size();
                 for (int32_t j : wl) {
                     o.nitems = 0;
-                    if (hl) zz_process_node_logit(g, v, lg, j, ctl.H, ctl.incl, w0, cur, false, o);
+                    if (st) zz_process_node_strong(g, v, *st, j, ctl.H, ctl.incl, w0, cur, false, o);
+                    else if (hl) zz_process_node_logit(g, v, lg, j, ctl.H, ctl.incl, w0, cur, false, o);
                     else zz_process_node(g, v, j, ctl.H, ctl.incl, w0, cur, false, o);
                     r->item_hist[std::min<int64_t>(it, 63)] += o.nitems;
                     handle(j, o, w0, cur);

@@ -247,7 +247,7 @@ def wlib():
     if _wlib is None:
         so = os.path.join(ORACLE_DIR, "libzzwindowsim.so")
         srcs = [os.path.join(ORACLE_DIR, "zz_window_sim.cpp")] + [
-            os.path.join(ROOT, "zigzagboomerang.jl_b200", "csrc", f) for f in ("zz_core.h", "zz_fast.h", "zz_logit.h", "zz_ctl.h", "zz_host_graph.h", "zz_host_logit.h", "zz_math.h")]
+            os.path.join(ROOT, "zigzagboomerang.jl_b200", "csrc", f) for f in ("zz_core.h", "zz_fast.h", "zz_logit.h", "zz_strong.h", "zz_ctl.h", "zz_host_graph.h", "zz_host_logit.h", "zz_math.h")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
             build()
         L = C.CDLL(so)
@@ -258,6 +258,9 @@ def wlib():
         L.zzw_spdmp_logistic.restype = C.c_void_p
         L.zzw_spdmp_logistic.argtypes = [C.c_int64, C.c_int64] + [C.c_void_p] * 9 + [C.c_double, C.c_int64] + [C.c_void_p] * 4 + [
             C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_uint32]
+        L.zzw_sparsesticky.restype = C.c_void_p
+        L.zzw_sparsesticky.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_double,
+                                       C.c_double, C.c_uint32]
         L.zzw_status.argtypes = [C.c_void_p]
         L.zzw_trace_len.restype = C.c_int64
         L.zzw_trace_len.argtypes = [C.c_void_p]
@@ -275,7 +278,10 @@ def wlib():
 
 
 def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
-               delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False, kappa=None, boom=None, logistic=None):
+               delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False, kappa=None, boom=None, logistic=None,
+               strong=None):
+    """``strong = rule`` ("sticky" / "reversible"): the strong-bound sparse sticky timeline (zz_strong.h) with scalar ``c`` and
+    ``kappa``, target = ``bound``; contract: :func:`sparsestickyzz` with ``ctr=True``."""
     L = wlib()
     d = bound.n
     f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
@@ -283,7 +289,10 @@ def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1,
     mu = np.zeros(d) if mu is None else f8(mu)
     h = None if h is None else f8(h)
     sd = np.array(seed, dtype=np.uint64)
-    if logistic is not None:
+    if strong is not None:
+        r = L.zzw_sparsesticky(d, _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(h), _p(x0), _p(theta0), float(T), float(c[0]),
+                               float(kappa), {"sticky": 0, "reversible": 1}[strong], _p(sd), float(delta0), float(target_frac), int(tag_limit))
+    elif logistic is not None:
         lg = logistic
         A, At = lg["A"], lg["At"]
         ly, lny, lmu = f8(lg["y"]), f8(lg["ny"]), f8(lg["mu"])

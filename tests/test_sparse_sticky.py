@@ -115,3 +115,42 @@ def test_parity_arithmetic_has_the_same_law(zzb, rule):
     b4 = O.sparsestickyzz(G, x1, -np.ones(p), 50.0, 2.5, kappa, rule=rule, seed=(1, 2), ctr=True)
     first = {int(i): (x, th) for t, i, x, th in b4.events[::-1]}
     assert all(first[j + 1][0] != 0.0 or first[j + 1][1] == 0.0 for j in range(p) if x1[j] != 0 and (j + 1) in first)
+
+
+def test_windowed_schedule_with_the_strong_bound_timeline_equals_its_contract(zzb):
+    """zz_strong.h (the per-coordinate timeline a strong-bound device kernel would run: own items only, neighbours enter
+    through positions) inside the host emulation of the device schedule against zzo_sparsestickyzz_ctr, bit for bit: random
+    chains and lattices, both rules, frozen and moving starts, linear term, window policies, tag rebases.  The relaxation needs
+    ~3 passes per window here against ~12 for the samplers in which a flip reschedules its neighbours."""
+    rng = np.random.default_rng(0)
+    max_iters = 0
+    for case in range(40):
+        if rng.random() < 0.5:
+            p = int(rng.integers(2, 120))
+            G = chain_precision(zzb, max(p, 2))
+        else:
+            G = zzb.grid_precision(int(rng.integers(2, 9)), int(rng.integers(2, 9)), shift=0.1)
+        p = G.n
+        x0 = np.where(rng.random(p) < rng.choice([0.0, 0.3, 1.0]), rng.standard_normal(p), 0.0)
+        th0 = rng.choice(np.array([-1.0, 1.0]), p)
+        h = 0.5 * rng.standard_normal(p) if rng.random() < 0.3 else None
+        rule = str(rng.choice(["sticky", "reversible"]))
+        kappa, T = float(rng.choice([0.1, 0.5, 3.0])), float(rng.uniform(5, 60))
+        c = float(rng.choice([3.0, 6.0])) + 2.0 * float(np.abs(G.nzval).max()) + (0.0 if h is None else float(np.abs(h).max()))
+        sd = (int(rng.integers(1 << 40)), int(rng.integers(1 << 40)))
+        kw = dict(delta0=float(10 ** rng.uniform(-3, 0.3)), target_frac=float(10 ** rng.uniform(-1.3, 0.7)))
+        if rng.random() < 0.3:
+            kw["tag_limit"] = int(rng.integers(30, 200))
+        try:
+            ref = O.sparsestickyzz(G, x0, th0, T, c, kappa, h=h, rule=rule, seed=sd, ctr=True)
+        except O.BoundError:
+            ref = None
+        try:
+            sim = O.window_sim(None, G, 0.0, x0, th0, T, np.full(p, c), h=h, kappa=kappa, strong=rule, seed=sd, **kw)
+        except O.BoundError:
+            sim = None
+        assert (ref is None) == (sim is None), case
+        if ref is not None:
+            O.assert_same_run(ref, sim)
+            max_iters = max(max_iters, sim.stats["max_iters"])
+    assert 2 <= max_iters <= 8
