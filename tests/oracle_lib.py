@@ -144,29 +144,10 @@ def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), 
                         _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
                         float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor), int(mode))
     try:
-        st = L.zzo_status(r)
-        if st == 3:
-            i = C.c_int64(); t = C.c_double(); l = C.c_double(); lb = C.c_double()
-            L.zzo_error_info(r, C.byref(i), C.byref(t), C.byref(l), C.byref(lb))
-            raise BoundError("Tuning parameter `c` too small. (i=%d t=%g l=%g lb=%g)" % (i.value, t.value, l.value, lb.value))
-        if st != 0:
-            raise RuntimeError("oracle failed with status %d" % st)
-        out = OracleResult()
-        n = L.zzo_trace_len(r)
-        out.events = np.empty(n, dtype=EVENT_DTYPE)
-        L.zzo_trace_copy(r, _p(out.events), 0, n)
-        out.acc = np.empty(d, np.int64)
-        num = C.c_int64()
-        L.zzo_counts(r, _p(out.acc), C.byref(num))
-        out.num = num.value
-        out.t, out.x, out.theta, out.c = (np.empty(d) for _ in range(4))
-        L.zzo_final_state(r, _p(out.t), _p(out.x), _p(out.theta), _p(out.c))
-        out.m1, out.m2, out.s1, out.s2 = (np.empty(d) for _ in range(4))
-        L.zzo_moments(r, _p(out.m1), _p(out.m2), _p(out.s1), _p(out.s2))
-        if boom is not None:   # the event-based moments assume a piecewise linear path (trace.jl:182-200)
-            del out.m1, out.m2, out.s1, out.s2
-        out.t0, out.x0, out.theta0 = t0, x0.copy(), theta0.copy()
-        out.loop_seconds = L.zzo_loop_seconds(r)
+        out = _collect(L, r, d, t0, x0, theta0)
+        if boom is None:   # the event-based moments assume a piecewise linear path (trace.jl:182-200)
+            out.m1, out.m2, out.s1, out.s2 = (np.empty(d) for _ in range(4))
+            L.zzo_moments(r, _p(out.m1), _p(out.m2), _p(out.s1), _p(out.s2))
         return out
     finally:
         L.zzo_free(r)
