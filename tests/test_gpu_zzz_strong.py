@@ -1,0 +1,60 @@
+"""EXPERIMENTAL image only (make -C zigzagboomerang.jl_b200/csrc strong; tools/gpu_strong.sh): the strong-bound sparse sticky
+kernel (src/sparsestickyzz.jl as the reference runs config 4; csrc/zz_strong.h) against its contract zzo_sparsestickyzz_ctr,
+bit for bit.  Skipped with the default image, which does not contain the kernel; NOT yet run on a GPU (written after the GPU
+budget of round 1 was spent) -- on the CPU the same per-coordinate code equals the contract inside the schedule emulation
+(tests/test_sparse_sticky.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from sticky_stats import chain_precision
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("ZZB200_EXPERIMENTAL"),
+                                                  reason="needs the experimental image (tools/gpu_strong.sh)")]
+
+
+def run_strong(zzb, G, x0, th0, T, c, kappa, rule, seed, h=None, tune=None):
+    p = G.n
+    prob = zzb.Problem(zzb.GaussianPotential(G, h), zzb.ZigZag(G, np.zeros(p)))
+    run = zzb.Run(prob, kappa=np.full(p, kappa))
+    try:
+        run.set(strong_c=c, strong_rule={"sticky": 0, "reversible": 1}[rule], **(tune or {}))
+        run.upload(0.0, x0, th0, np.full(p, c), seed=seed)
+        run.execute(T)
+
+        class R:
+            pass
+        r = R()
+        r.events = run.events()
+        r.t, r.x, r.theta, r.c = run.final_state()
+        r.acc, r.num = run.counts()
+        r.stats, r.device_ms = run.stats(), run.device_ms
+        return r
+    finally:
+        run.close()
+        prob.close()
+
+
+@pytest.mark.parametrize("p,kappa,T,rule", [(12, 0.5, 50.0, "sticky"), (30, 0.3, 80.0, "reversible"), (2000, 0.5, 30.0, "sticky")])
+def test_chain_bit_exact(gpu, p, kappa, T, rule):
+    G = chain_precision(gpu, p)
+    rng = np.random.default_rng(p)
+    x0 = np.where(rng.random(p) < 0.3, rng.standard_normal(p), 0.0)
+    th0 = rng.choice(np.array([-1.0, 1.0]), p)
+    ref = O.sparsestickyzz(G, x0, th0, T, 2.5, kappa, rule=rule, seed=(3, 4), ctr=True)
+    got = run_strong(gpu, G, x0, th0, T, 2.5, kappa, rule, (3, 4))
+    O.assert_same_run(ref, got)
+
+
+def test_config4_full_size_timing(gpu):
+    """p = 10^5 chain, x0 = 0 (all frozen), kappa = 2000/p, c = 2.5: parity at T = 5 and the passes per window."""
+    p, T = 100000, 5.0
+    G = chain_precision(gpu, p)
+    x0, th0 = np.zeros(p), np.ones(p)
+    ref = O.sparsestickyzz(G, x0, th0, T, 2.5, 2000.0 / p, seed=(5, 6), ctr=True)
+    got = run_strong(gpu, G, x0, th0, T, 2.5, 2000.0 / p, "sticky", (5, 6))
+    O.assert_same_run(ref, got)
+    st = got.stats
+    print(f"strong-bound config 4: {len(got.events)} events in {got.device_ms:.2f} ms, {st['windows']} windows, {st['passes']} passes")

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libzzb200.so")
+LIB_PATH = os.environ.get("ZZB200_LIB") or os.path.join(PKG_DIR, "libzzb200.so")
 CUBIN_PATH = os.environ.get("ZZB200_CUBIN") or os.path.join(PKG_DIR, "zzb200_kernels.cubin")
 
 ZZB_OK, ZZB_E_ARG, ZZB_E_CUDA, ZZB_E_BOUND, ZZB_E_GRAPH, ZZB_E_NOMEM, ZZB_E_TRACE, ZZB_E_INTERNAL = 0, 1, 2, 3, 4, 5, 6, 9

@@ -6,6 +6,9 @@
 #include "zz_core.h"
 #include "zz_ctl.h"
 #include "zz_logit.h"
+#ifdef ZZ_ENABLE_STRONG   // experimental build: strong-bound sparse sticky kernel (not in the default image, see zz_strong.h)
+#include "zz_strong.h"
+#endif
 
 struct ZzEvent {  // memory layout of Tuple{Float64,Int64,Float64,Float64}, src/trace.jl:38
     double t; long long i; double x; double theta;
@@ -94,6 +97,9 @@ struct ZzParams {
     // subsampled logistic target (zz_logit.h; only read by zz_run_kernel_csr_logit).  Kept LAST so that the parameter
     // offsets the other kernels were compiled and profiled with do not move.
     ZzLogit lg;
+#ifdef ZZ_ENABLE_STRONG
+    ZzStrong st;
+#endif
 };
 
 // order-preserving map double -> uint64 (so atomicMin works for any sign)

@@ -668,7 +668,8 @@ ZZ_HD void zz_process_interior(const ZzGraph& g, const ZzView& v, int32_t j, dou
 #define ZZ_MODE_STICKY 2   // sticky ZigZag (src/ss_fact.jl)
 #define ZZ_MODE_BOOM 3     // factorised Boomerang (F::FactBoomerang in src/sfact.jl)
 #define ZZ_MODE_LOGIT 4    // plain ZigZag with the subsampled logistic target (zz_logit.h; general sparse kernels only)
-#define ZZ_MODE_HAS_VEL(M) ((M) == ZZ_MODE_STICKY || (M) == ZZ_MODE_BOOM)   // flip lists carry the velocity after each event
+#define ZZ_MODE_STRONG 5   // strong-bound sparse sticky ZigZag (zz_strong.h); only in -DZZ_ENABLE_STRONG builds of the image
+#define ZZ_MODE_HAS_VEL(M) ((M) == ZZ_MODE_STICKY || (M) == ZZ_MODE_BOOM || (M) == ZZ_MODE_STRONG)   // flip lists carry the velocity after each event
 template <int KIND, int MODE, bool MG = true>
 ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                              uint32_t cur, bool first_iter, ZzNodeOut& o)

@@ -384,6 +384,9 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
     }
 #else
     if constexpr (MODE == ZZ_MODE_LOGIT) zz_process_node_logit(P.g, P.v, P.lg, j, H, incl, w0, cur, first, o);
+#ifdef ZZ_ENABLE_STRONG
+    else if constexpr (MODE == ZZ_MODE_STRONG) zz_process_node_strong(P.g, P.v, P.st, j, H, incl, w0, cur, first, o);
+#endif
     else zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, cur, first, o);
     zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws, tl, tslot);
 #endif
@@ -533,6 +536,20 @@ __device__ __forceinline__ void zz_init_body(const ZzParams& P)
 }
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel(const ZzParams P) { zz_init_body<false>(P); }
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel_boom(const ZzParams P) { zz_init_body<true>(P); }
+#ifdef ZZ_ENABLE_STRONG
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel_strong(const ZzParams P)
+{
+    unsigned long long kmin = ~0ULL;
+    for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < P.v.d; j += gridDim.x * blockDim.x) {
+        zz_init_node_strong(P.g, P.v, P.st, j, P.t0);
+        const unsigned long long k = zz_key(P.v.tau[j]);
+        kmin = k < kmin ? k : kmin;
+    }
+    cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
+    kmin = cg::reduce(w, kmin, cg::less<unsigned long long>());
+    if (w.thread_rank() == 0 && kmin != ~0ULL) atomicMin(&P.ctl->f0_key, kmin);
+}
+#endif
 
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK)
 zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ x, double* __restrict__ th,
@@ -925,3 +942,6 @@ ZZ_RUN_KERNEL(zz_run_kernel_csr_sticky, ZZ_KIND_CSR, false, ZZ_MODE_STICKY)
 ZZ_RUN_KERNEL(zz_run_kernel_grid_boom, ZZ_KIND_GRID, false, ZZ_MODE_BOOM)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_boom, ZZ_KIND_CSR, false, ZZ_MODE_BOOM)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_logit, ZZ_KIND_CSR, false, ZZ_MODE_LOGIT)
+#ifdef ZZ_ENABLE_STRONG
+ZZ_RUN_KERNEL(zz_run_kernel_csr_strong, ZZ_KIND_CSR, false, ZZ_MODE_STRONG)
+#endif

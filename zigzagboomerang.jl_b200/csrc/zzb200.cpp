@@ -84,12 +84,23 @@ static int32_t cu_fail(CUresult r, const char* what)
     } while (0)
 
 // --------------------------------------------------------------------------------------------- global state
+#ifdef ZZ_ENABLE_STRONG   // experimental build (make strong): + the strong-bound sparse sticky kernel, zz_strong.h
+#define ZZ_NKERN 14
+#define ZZ_KERN_BLOCK_IDX(k) ((k) >= 12 ? 1 : ((k) & 1))
+#define ZZ_RUN_BLOCK_OF(r) ((r)->kidx() >= 12 ? 1 : (r)->kind)      // the strong kernel is a general-sparse kernel on any graph
+#else
 #define ZZ_NKERN 13   // event-loop kernels in the image (see zzb_init)
+#define ZZ_KERN_BLOCK_IDX(k) (k == 12 ? 1 : (k & 1))
+#define ZZ_RUN_BLOCK_OF(r) ((r)->kind)
+#endif
 struct Global {
     bool ready = false;
     CUdevice dev = 0; int dev_id = 0;
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
+#ifdef ZZ_ENABLE_STRONG
+    CUfunction f_init_strong = nullptr;
+#endif
     CUfunction f_setup = nullptr, f_init = nullptr, f_init_boom = nullptr, f_run[ZZ_NKERN] = {}, f_export = nullptr, f_grid_tail = nullptr;
     CUstream stream = nullptr;
     CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
@@ -173,8 +184,14 @@ struct zzb_run_s {
     ZzDevCtl hc;                       // last copy of the device control block
     int64_t launches = 0;
     int grid = 0; int kind = 1;
+#ifdef ZZ_ENABLE_STRONG
+    bool strong = false; double strong_c = 0.0, kappa0 = 0.0; int strong_rule = 0;
+#endif
     int kidx() const
     {
+#ifdef ZZ_ENABLE_STRONG
+        if (strong) return 13;
+#endif
         if (prob && prob->logit) return 12;
         if (flags & ZZB_FLAG_BOOMERANG) return 10 + kind;
         if (flags & ZZB_FLAG_STICKY) return 8 + kind;
@@ -244,7 +261,14 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     static const char* run_names[ZZ_NKERN] = { "zz_run_kernel_grid", "zz_run_kernel_csr", "zz_run_kernel_grid_multi", "zz_run_kernel_csr_multi",
                                          "zz_run_kernel_grid_lb", "zz_run_kernel_csr_lb", "zz_run_kernel_grid_multi_lb", "zz_run_kernel_csr_multi_lb",
                                          "zz_run_kernel_grid_sticky", "zz_run_kernel_csr_sticky", "zz_run_kernel_grid_boom", "zz_run_kernel_csr_boom",
-                                         "zz_run_kernel_csr_logit" };
+                                         "zz_run_kernel_csr_logit"
+#ifdef ZZ_ENABLE_STRONG
+                                         , "zz_run_kernel_csr_strong"
+#endif
+    };
+#ifdef ZZ_ENABLE_STRONG
+    CU(cuModuleGetFunction(&G.f_init_strong, G.mod, "zz_init_kernel_strong"));
+#endif
     for (int k = 0; k < ZZ_NKERN; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuModuleGetFunction(&G.f_grid_tail, G.mod, "zz_grid_tail_kernel"));
@@ -262,7 +286,7 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
         }
     }
     for (int k = 0; k < ZZ_NKERN; ++k) {
-        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm[k], G.f_run[k], G.run_block[k == 12 ? 1 : (k & 1)], 0));
+        CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&G.blocks_per_sm[k], G.f_run[k], G.run_block[ZZ_KERN_BLOCK_IDX(k)], 0));
         if (G.blocks_per_sm[k] < 1) return fail(ZZB_E_CUDA, "zz_run_kernel does not fit on an SM");
     }
     G.ready = true;
@@ -479,6 +503,9 @@ static void fill_params(zzb_run_s* r)
         P.v.bref_rate = r->lambdaref / (double)r->d; P.v.brho = r->rho; P.v.brhobar = sqrt(1 - r->rho * r->rho);
     }
     P.v.kappa = P.v.sticky ? r->kappa.as<double>() : nullptr;
+#ifdef ZZ_ENABLE_STRONG
+    P.st.c = r->strong_c; P.st.kappa = r->kappa0; P.st.rule = r->strong_rule; P.st.pad = 0;
+#endif
     P.v.nranks = r->nranks; P.v.rank = r->rank; P.v.shard = r->shard; P.v.lo = r->lo; P.v.hi = r->hi;
     if (r->nranks > 1) {
         for (int q = 0; q < r->nranks; ++q) {
@@ -564,6 +591,15 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     else if (!strcmp(key, "target_flip_frac")) r->target_flip_frac = value;
     else if (!strcmp(key, "tag_limit")) r->tag_limit = (unsigned int)value;
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
+#ifdef ZZ_ENABLE_STRONG
+    // switch a sticky run to the strong-bound sampler of src/sparsestickyzz.jl: scalar bound constant c, rule (0 sticky, 1 reversible);
+    // kappa[0] of zzb_run_upload_kappa is the thaw rate; coordinates with x0 == 0 start frozen.  Before zzb_run_upload.
+    else if (!strcmp(key, "strong_c")) {
+        if (!(r->flags & ZZB_FLAG_STICKY) || !(value > 0.0)) return fail(ZZB_E_ARG, "strong_c needs a sticky run and c > 0");
+        r->strong = true; r->strong_c = value; r->grid = G.sm_count * G.blocks_per_sm[r->kidx()];
+    }
+    else if (!strcmp(key, "strong_rule")) r->strong_rule = (int)value;
+#endif
     else if (!strcmp(key, "grid")) r->grid = std::max(1, std::min((int)value, G.sm_count * G.blocks_per_sm[r->kidx()]));
     else return fail(ZZB_E_ARG, "unknown tuning key %s", key);
     return ZZB_OK;
@@ -579,6 +615,9 @@ int32_t zzb_run_upload_kappa(zzb_run_t r, const double* kappa)
     CtxGuard cg;
     CU(cuMemcpyHtoD(r->kappa.p, kappa, (size_t)r->d * 8));
     r->have_kappa = true;
+#ifdef ZZ_ENABLE_STRONG
+    r->kappa0 = kappa[0];
+#endif
     return ZZB_OK;
 }
 
@@ -622,6 +661,10 @@ int32_t zzb_run_reset(zzb_run_t r)
     void* a1[] = { &P, &px, &pth, &pc };
     CU(cuLaunchKernel(G.f_setup, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a1, nullptr));
     void* a2[] = { &P };
+#ifdef ZZ_ENABLE_STRONG
+    if (r->strong) CU(cuLaunchKernel(G.f_init_strong, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a2, nullptr));
+    else
+#endif
     CU(cuLaunchKernel((r->flags & ZZB_FLAG_BOOMERANG) ? G.f_init_boom : G.f_init, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a2, nullptr));
     CU(cuStreamSynchronize(G.stream));
     r->launches += 2;
@@ -641,6 +684,13 @@ int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* t
         r->seed[0] = seed[0]; r->seed[1] = seed[1]; r->adapt = adapt; r->factor = factor;
         r->t0 = t0;
         CU(cuMemcpyHtoDAsync(r->in_x.p, x0, nb, G.stream));
+#ifdef ZZ_ENABLE_STRONG
+        if (r->strong) {   // sparsestickystate (sparsestickyzz.jl:10-12): x0 == 0 starts frozen = velocity 0 in its record
+            std::vector<double> th(theta0, theta0 + r->d);
+            for (int32_t j = 0; j < r->d; ++j) if (x0[j] == 0.0) th[j] = 0.0;
+            CU(cuMemcpyHtoD(r->in_th.p, th.data(), nb));
+        } else
+#endif
         CU(cuMemcpyHtoDAsync(r->in_th.p, theta0, nb, G.stream));
         CU(cuMemcpyHtoDAsync(r->in_c.p, c, nb, G.stream));
         r->have_inputs = true;
@@ -690,7 +740,7 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
         CU(cuMemsetD8Async(r->ctl.p, 0, 8, G.stream));  // barrier counter
         void* args[] = { &P };
         CU(cuEventRecord(G.ev0, G.stream));
-        CU(cuLaunchCooperativeKernel(G.f_run[r->kidx()], (unsigned)r->grid, 1, 1, (unsigned)G.run_block[r->kind], 1, 1, 0, G.stream, args));
+        CU(cuLaunchCooperativeKernel(G.f_run[r->kidx()], (unsigned)r->grid, 1, 1, (unsigned)G.run_block[ZZ_RUN_BLOCK_OF(r)], 1, 1, 0, G.stream, args));
         CU(cuEventRecord(G.ev1, G.stream));
         CU(cuStreamSynchronize(G.stream));
         r->launches++;
