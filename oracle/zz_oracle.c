@@ -372,11 +372,20 @@ static double logit_grad(ctx *z, logit *L, int64_t j, double tp)
     return L->gamma0 * pos_at(z, j, tp) - s;            /* :107 */
 }
 
+/* velocity refreshments of the ZigZag in spdmp (hasrefresh(Z) = Z.lambdaref > 0, fact_samplers.jl:19): sfact.jl:78-114,188-190.
+ * One clock of rate lambdaref at queue key n+1; it picks a coordinate with the GLOBAL rng -- twice (:80,:84: the
+ * neighbourhood of the first pick is moved, the second pick is refreshed) -- sets theta_i = sigma_i * rand(rng, (-1, 1))
+ * (:100-101), re-arms with waiting_time_ref(F) (global rng, :107; dynamics.jl:100-101) and reschedules G1[i] (:109-113); the
+ * refreshment is a trace event (:143).  Mode seq: both generators are the one xoroshiro stream (documented deviation for
+ * the global-rng draws).  Mode ctr: one clock of rate lambdaref/d PER coordinate (superposition), its draws from the
+ * coordinate's own stream.  No device kernel runs this yet (the host API refuses lambdaref > 0). */
+typedef struct { double lambdaref; const double *sigma; } refr;
+
 static zzo_run *spdmp_impl(int64_t d,
                    const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
                    const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
                    double t0, const double *x0, const double *th0, double T, const double *c_in,
-                   const uint64_t *seed, int adapt, double factor, int mode, logit *lg)
+                   const uint64_t *seed, int adapt, double factor, int mode, logit *lg, const refr *rf)
 {
     zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run));
     ctx zs; ctx *z = &zs; memset(z, 0, sizeof(ctx));
@@ -404,10 +413,12 @@ static zzo_run *spdmp_impl(int64_t d,
     if (!all && !lazy) build_g2(z); /* sfact.jl:171-179 (lazy arithmetic needs no moves at all) */
 
     heapq Q; Q.n = 0; Q.lex = (mode & ZZO_RNG_CTR) != 0;
-    Q.key = (int64_t *)malloc(((size_t)d + 2) * sizeof(int64_t));
-    Q.val = (double *)malloc(((size_t)d + 2) * sizeof(double));
-    Q.index = (int64_t *)malloc(((size_t)d + 2) * sizeof(int64_t));
+    Q.key = (int64_t *)malloc((2 * (size_t)d + 2) * sizeof(int64_t));
+    Q.val = (double *)malloc((2 * (size_t)d + 2) * sizeof(double));
+    Q.index = (int64_t *)malloc((2 * (size_t)d + 2) * sizeof(int64_t));
     const int lbnd = (mode & ZZO_LOCAL_BOUND) != 0;
+    const int ctr = (mode & ZZO_RNG_CTR) != 0;
+    const double lam1 = rf ? (ctr ? rf->lambdaref / (double)d : rf->lambdaref) : 0.0;
     char *renew = (char *)calloc((size_t)d, 1);
     if (lbnd) {
         /* local.jl:118-123: bound and first time per coordinate, t[i] + ... (here t0 IS added) */
@@ -421,16 +432,39 @@ static zzo_run *spdmp_impl(int64_t d,
         for (int64_t i = 1; i <= d; ++i) h_enqueue(&Q, i, o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i)));
     }
 
+    if (rf) { /* sfact.jl:188-190: enqueue!(Q, (n + 1) => waiting_time_ref(rng, F)), no "+ t0" */
+        if (ctr) { for (int64_t i = 1; i <= d; ++i) h_enqueue(&Q, d + i, -zz_log(draw(z, i)) / lam1); }
+        else h_enqueue(&Q, d + 1, -zz_log(xoro_rand(&z->rng)) / lam1);
+    }
     int64_t num = 0;
     const double tl0 = now_s();
-    /* sfact.jl:199 outer loop; body = spdmp_inner! (:73-145), refresh branch omitted (lambda_ref == 0,
-       fact_samplers.jl:19) */
+    /* sfact.jl:199 outer loop; body = spdmp_inner! (:73-145) */
     while (tp < T && r->status == ZZO_OK) {
         for (;;) {
             int64_t i = Q.key[1]; tp = Q.val[1]; /* peek :77 */
+            const int refresh = i > d;           /* :78 */
+            const int64_t qkey = i;
+            if (refresh) i = ctr ? i - d : (int64_t)(xoro_rand(&z->rng) * (double)d) + 1;   /* :80 rand(1:n) */
             const int64_t *nb = &z->bd.rowval[z->bd.colptr[i - 1] - 1];
             int64_t nnb = z->bd.colptr[i] - z->bd.colptr[i - 1];
             if (!lazy) { if (all) move_all(z, tp); else move_nbhd(z, nb, nnb, tp); } /* :82 */
+            if (refresh) {
+                if (!ctr) i = (int64_t)(xoro_rand(&z->rng) * (double)d) + 1;                 /* :84 second pick */
+                nb = &z->bd.rowval[z->bd.colptr[i - 1] - 1]; nnb = z->bd.colptr[i] - z->bd.colptr[i - 1];
+                if (!lazy && !all) move_nbhd(z, &z->g2idx[z->g2ptr[i - 1]], z->g2ptr[i] - z->g2ptr[i - 1], tp); /* :85 */
+                if (lazy) { z->xf[i - 1] = pos_at(z, i, tp); z->tf[i - 1] = tp; }
+                z->th[i - 1] = rf->sigma[i - 1] * (draw(z, i) < 0.5 ? -1.0 : 1.0);            /* :100-101 */
+                h_set(&Q, qkey, tp - zz_log(ctr ? draw(z, i) : xoro_rand(&z->rng)) / lam1);  /* :107 */
+                for (int64_t q = 0; q < nnb; ++q) {                                          /* :109-113 */
+                    int64_t j = nb[q];
+                    double tj = lazy ? tp : z->t[j - 1];
+                    z->t_old[j - 1] = tj;
+                    ab_zigzag(z, j, tp);
+                    h_set(&Q, j, tj + o_poisson_time(z->ba[j - 1], z->bb[j - 1], draw(z, j)));
+                }
+                push_event(r, lazy ? tp : z->t[i - 1], i, lazy ? z->xf[i - 1] : z->x[i - 1], z->th[i - 1]); /* :143 */
+                break;
+            }
             if (lbnd && renew[i - 1]) { /* local.jl:34-41: the bound expired, renew it */
                 double Delta = ab_local(z, i, tp);
                 double tr = lazy ? tp : z->t[i - 1];
@@ -504,7 +538,23 @@ zzo_run *zzo_spdmp(int64_t d,
                    const uint64_t *seed, int adapt, double factor, int mode)
 {
     return spdmp_impl(d, tg_colptr, tg_rowval, tg_nzval, h, bd_colptr, bd_rowval, bd_nzval, mu, t0, x0, th0, T, c_in,
-                      seed, adapt, factor, mode, NULL);
+                      seed, adapt, factor, mode, NULL, NULL);
+}
+
+/* spdmp with Z = ZigZag(Gamma, mu, sigma; lambdaref > 0): zzo_spdmp plus the refreshment clock (see `refr` above) */
+zzo_run *zzo_spdmp_refresh(int64_t d,
+                   const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
+                   const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
+                   const double *sigma, double lambdaref,
+                   double t0, const double *x0, const double *th0, double T, const double *c_in,
+                   const uint64_t *seed, int adapt, double factor, int mode)
+{
+    refr rf = { lambdaref, sigma };
+    if ((mode & ZZO_LOCAL_BOUND) || !(lambdaref > 0.0)) {
+        zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run)); r->d = 0; r->status = ZZO_E_ARG; return r;
+    }
+    return spdmp_impl(d, tg_colptr, tg_rowval, tg_nzval, h, bd_colptr, bd_rowval, bd_nzval, mu, t0, x0, th0, T, c_in,
+                      seed, adapt, factor, mode, NULL, &rf);
 }
 
 /* spdmp(grad_phi_moving, t0, x0, th0, T, c, Zdrop, SelfMoving(), A, At, mu, y, ny, k; adapt, factor), scripts/logistic.jl:167.
@@ -531,7 +581,7 @@ zzo_run *zzo_spdmp_logistic(int64_t d, int64_t n,
         }
     /* the target matrix arguments are unused with a logistic target: pass the bound matrix */
     return spdmp_impl(d, bd_colptr, bd_rowval, bd_nzval, NULL, bd_colptr, bd_rowval, bd_nzval, bd_mu, t0, x0, th0, T, c_in,
-                      seed, adapt, factor, mode, &L);
+                      seed, adapt, factor, mode, &L, NULL);
 }
 double zzo_exp(double x) { return zz_exp(x); }
 

@@ -52,6 +52,9 @@ def lib():
         L.zzo_exp.argtypes = [C.c_double]
         L.zzo_sparsestickyzz.restype = C.c_void_p
         L.zzo_sparsestickyzz.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, C.c_void_p]
+        L.zzo_spdmp_refresh.restype = C.c_void_p
+        L.zzo_spdmp_refresh.argtypes = [C.c_int64] + [C.c_void_p] * 9 + [C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_double,
+                                        C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
         L.zzo_sparsestickyzz_ctr.restype = C.c_void_p
         L.zzo_sparsestickyzz_ctr.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
         L.zzo_queue_script.restype = None
@@ -104,7 +107,7 @@ def block_diagonal(G, K):
 
 
 def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
-          mode=PARITY_MODE, kappa=None, boom=None, parallel=None, logistic=None):
+          mode=PARITY_MODE, kappa=None, boom=None, parallel=None, logistic=None, refresh=None):
     """Run the oracle.  ``target`` / ``bound`` are problems.CSC (target precision and the sampler's Z.Gamma).
     ``parallel = (K, Delta)`` runs the multithreaded parallel_spdmp (src/parallel.jl) on K threads.
     With ``kappa`` (thaw rates) the sticky sampler sspdmp (src/ss_fact.jl) is run instead of spdmp; with
@@ -116,7 +119,12 @@ def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), 
     mu = np.zeros(d) if mu is None else f8(mu)
     h = None if h is None else f8(h)
     sd = np.array(seed, dtype=np.uint64)
-    if logistic is not None:   # dict(A, At, y, ny, mu, gamma0, k): the subsampled logistic target of scripts/logistic.jl (`target` unused)
+    if refresh is not None:   # (sigma, lambdaref): ZigZag velocity refreshments in spdmp (sfact.jl:78-114), Z.lambdaref > 0
+        sigma = f8(refresh[0])
+        r = L.zzo_spdmp_refresh(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
+                                _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu), _p(sigma), float(refresh[1]),
+                                float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor), int(mode))
+    elif logistic is not None:   # dict(A, At, y, ny, mu, gamma0, k): the subsampled logistic target of scripts/logistic.jl (`target` unused)
         lg = logistic
         A, At = lg["A"], lg["At"]
         ly, lny, lmu = f8(lg["y"]), f8(lg["ny"]), f8(lg["mu"])

@@ -340,3 +340,26 @@ def test_schedule_emulation_with_an_unrelated_bound_pattern(zzb):
     ref = O.spdmp(Gs, Is, 0.0, x0, th0, 25.0, 12.0 * Gs.colnorms(), seed=(1, 2), adapt=True)
     sim = O.window_sim(Gs, Is, 0.0, x0, th0, 25.0, 12.0 * Gs.colnorms(), seed=(1, 2), adapt=True)
     O.assert_same_run(ref, sim)
+
+
+@pytest.mark.parametrize("mode", [O.RNG_SEQ | O.ARITH_INPLACE, O.RNG_SEQ | O.ARITH_INPLACE | O.GRAPH_ALL, O.PARITY_MODE])
+def test_zigzag_refreshments(zzb, mode):
+    """spdmp with Z = ZigZag(0.9 Gamma, 0, sigma; lambdaref = 0.5) (the refresh branch of spdmp_inner!, sfact.jl:78-114,188-190):
+    refreshments are trace events with velocity +-sigma_i, they leave N(0, inv(Gamma)) invariant (moment bounds of
+    test/maintest.jl), and their number is Poisson(lambdaref T)."""
+    d, T, lam = 8, 1000.0, 0.5
+    G = zzb.random_spd(d, seed=2)
+    rng = np.random.default_rng(8)
+    x0 = rng.random(d)
+    th0 = rng.choice(np.array([-1.0, 1.0]), d)
+    sigma = G.to_scipy().diagonal() ** -0.5                 # ZigZag(Gamma, mu) default, src/types.jl:27
+    c = 0.7 * G.colnorms()
+    seed = (0x9E3779B97F4A7C15, 0xD1B54A32D192ED03)
+    r = O.spdmp(G, G.scaled(0.9), 0.0, x0, th0, T, c, seed=seed, mode=mode, refresh=(sigma, lam))
+    ev = r.events
+    speeds = np.abs(ev["theta"])
+    refreshed = np.isclose(speeds, sigma[ev["i"] - 1]) & ~np.isclose(sigma[ev["i"] - 1], 1.0)
+    assert refreshed.sum() > 100                            # after its first refreshment a coordinate moves at speed sigma_i
+    n_ref = len(ev) - r.acc.sum()                           # trace events that are not accepted reflections
+    assert abs(n_ref - lam * T) < 5 * math.sqrt(lam * T)
+    _cov_check(r, zzb, G, x0, th0, T, 2.0, 2.5)
