@@ -188,3 +188,16 @@ def test_logistic_golden_fixture(zzb):
     for name in GC.LOGISTIC_CASES:
         g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", name + ".json")))
         assert GC.run_oracle(O, GC.case_inputs(zzb, name)) == g
+
+
+def test_columns_longer_than_the_gather_scratch_fall_back_to_list_walking(zzb):
+    """No sparsification (droptol = 0): the dense regressors couple to all p = 257 > ZZ_LNB = 192 coordinates, so their
+    timelines run in the list-walking version next to gather-first ones for the short columns -- same bits."""
+    cfg = zzb.logistic_config(levels=(15, 15), r=2, m=12, seed=4, droptol=0.0)
+    assert np.diff(cfg["A"].colptr).min() >= 1 and np.diff(cfg["Gamma_drop"].colptr).max() > 192
+    cfg["logistic"] = dict(A=cfg["A"], At=cfg["At"], y=cfg["y"], ny=cfg["ny"], mu=cfg["mu"], gamma0=cfg["gamma0"], k=10)
+    ref = LC.run_oracle(O, cfg, 2.0)
+    sim = O.window_sim(None, cfg["Gamma_drop"], 0.0, cfg["x0"], cfg["theta0"], 2.0, cfg["c"], mu=cfg["mu"], adapt=True, factor=5.0,
+                       logistic=cfg["logistic"], seed=(5, 6))
+    assert len(ref.events) > 100
+    O.assert_same_run(ref, sim)
