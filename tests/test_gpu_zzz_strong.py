@@ -1,7 +1,6 @@
-"""EXPERIMENTAL image only (make -C zigzagboomerang.jl_b200/csrc strong; tools/gpu_strong.sh): the strong-bound sparse sticky
-kernel (src/sparsestickyzz.jl as the reference runs config 4; csrc/zz_strong.h) against its contract zzo_sparsestickyzz_ctr,
-bit for bit.  Skipped with the default image, which does not contain the kernel; NOT yet run on a GPU (written after the GPU
-budget of round 1 was spent) -- on the CPU the same per-coordinate code equals the contract inside the schedule emulation
+"""The strong-bound sparse sticky kernel (src/sparsestickyzz.jl as the reference runs config 4; csrc/zz_strong.h,
+zz_run_kernel_csr_strong) against its contract zzo_sparsestickyzz_ctr, bit for bit.  First green on a B200 in round 2
+(profiles/r02a_strong.log); on the CPU the same per-coordinate code equals the contract inside the schedule emulation
 (tests/test_sparse_sticky.py)."""
 import os
 
@@ -11,8 +10,7 @@ import pytest
 import oracle_lib as O
 from sticky_stats import chain_precision
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.environ.get("ZZB200_EXPERIMENTAL"),
-                                                  reason="needs the experimental image (tools/gpu_strong.sh)")]
+pytestmark = pytest.mark.gpu
 
 
 def run_strong(zzb, G, x0, th0, T, c, kappa, rule, seed, h=None, tune=None):

@@ -6,9 +6,7 @@
 #include "zz_core.h"
 #include "zz_ctl.h"
 #include "zz_logit.h"
-#ifdef ZZ_ENABLE_STRONG   // experimental build: strong-bound sparse sticky kernel (not in the default image, see zz_strong.h)
 #include "zz_strong.h"
-#endif
 
 struct ZzEvent {  // memory layout of Tuple{Float64,Int64,Float64,Float64}, src/trace.jl:38
     double t; long long i; double x; double theta;
@@ -61,6 +59,11 @@ struct ZzDevCtl {
     unsigned long long tail_xep;     // sharded tail passes (CTA 0 only): exchange counter and last reduced result, for the other CTAs
     ZzMsg tail_xres;
     ZzMsg mbox[2][ZZ_MAXRANKS];      // incoming messages, by boundary parity and sender
+    // asynchronous tile-local relaxation (zz_run_body_async), per window attempt (attempt number mod 3):
+    long long pending[3];            // timeline evaluations queued or in flight on the whole GPU (+1 token per CTA that has not
+                                     // finished its scan yet); 0 = the window has converged
+    unsigned int abortf[3];          // some evaluation overflowed (flips / pool / items / tags / inbox): retry the window shorter
+    unsigned int pad_async;
 };
 
 struct ZzParams {
@@ -94,12 +97,16 @@ struct ZzParams {
     int32_t* wl_peer[3][ZZ_MAXRANKS];
     int32_t* touched_peer[ZZ_MAXRANKS];
     ZzDevCtl* ctl_peer[ZZ_MAXRANKS];
-    // subsampled logistic target (zz_logit.h; only read by zz_run_kernel_csr_logit).  Kept LAST so that the parameter
-    // offsets the other kernels were compiled and profiled with do not move.
+    // asynchronous relaxation: marks that cross a tile boundary are pushed into the owning CTA's inbox.  Entry =
+    // (window attempt << 32) | coordinate, so stale entries of earlier attempts read as "not written yet"; the counters rotate
+    // with the attempt number mod 3 and are reset by their owner one attempt ahead.
+    unsigned long long* inbox;      // [grid][inbox_cap]
+    unsigned int* inbox_cnt;        // [3][grid]
+    unsigned int inbox_cap;
+    unsigned int flag_words;        // 32-bit words per per-tile bit array (dynamic shared memory = 2 arrays)
+    // subsampled logistic target (zz_logit.h; only read by zz_run_kernel_csr_logit)
     ZzLogit lg;
-#ifdef ZZ_ENABLE_STRONG
     ZzStrong st;
-#endif
 };
 
 // order-preserving map double -> uint64 (so atomicMin works for any sign)

@@ -384,9 +384,7 @@ __device__ __noinline__ void zz_eval_publish(const ZzParams& P, int32_t j, doubl
     }
 #else
     if constexpr (MODE == ZZ_MODE_LOGIT) zz_process_node_logit(P.g, P.v, P.lg, j, H, incl, w0, cur, first, o);
-#ifdef ZZ_ENABLE_STRONG
     else if constexpr (MODE == ZZ_MODE_STRONG) zz_process_node_strong(P.g, P.v, P.st, j, H, incl, w0, cur, first, o);
-#endif
     else zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, cur, first, o);
     zz_publish<KIND, MULTI, MODE>(P, j, o, w0, cur, nxt, ws, tl, tslot);
 #endif
@@ -536,7 +534,6 @@ __device__ __forceinline__ void zz_init_body(const ZzParams& P)
 }
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel(const ZzParams P) { zz_init_body<false>(P); }
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel_boom(const ZzParams P) { zz_init_body<true>(P); }
-#ifdef ZZ_ENABLE_STRONG
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel_strong(const ZzParams P)
 {
     unsigned long long kmin = ~0ULL;
@@ -549,7 +546,6 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel_strong(con
     kmin = cg::reduce(w, kmin, cg::less<unsigned long long>());
     if (w.thread_rank() == 0 && kmin != ~0ULL) atomicMin(&P.ctl->f0_key, kmin);
 }
-#endif
 
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK)
 zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ x, double* __restrict__ th,
@@ -927,21 +923,496 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
     if (lane == 0 && st_evals) atomicAdd(&C->node_evals, st_evals);
 }
 
-#define ZZ_RUN_KERNEL(name, KIND, MULTI, MODE) \
-    extern "C" __global__ void __launch_bounds__((KIND == ZZ_KIND_GRID ? ZZ_RUN_BLOCK_GRID : ZZ_RUN_BLOCK_CSR), ZZ_MINB) name(const __grid_constant__ ZzParams P) { zz_run_body<KIND, MULTI, MODE>(P); }
-ZZ_RUN_KERNEL(zz_run_kernel_grid, ZZ_KIND_GRID, false, ZZ_MODE_PLAIN)
-ZZ_RUN_KERNEL(zz_run_kernel_csr, ZZ_KIND_CSR, false, ZZ_MODE_PLAIN)
-ZZ_RUN_KERNEL(zz_run_kernel_grid_multi, ZZ_KIND_GRID, true, ZZ_MODE_PLAIN)
-ZZ_RUN_KERNEL(zz_run_kernel_csr_multi, ZZ_KIND_CSR, true, ZZ_MODE_PLAIN)
-ZZ_RUN_KERNEL(zz_run_kernel_grid_lb, ZZ_KIND_GRID, false, ZZ_MODE_LB)
-ZZ_RUN_KERNEL(zz_run_kernel_csr_lb, ZZ_KIND_CSR, false, ZZ_MODE_LB)
-ZZ_RUN_KERNEL(zz_run_kernel_grid_multi_lb, ZZ_KIND_GRID, true, ZZ_MODE_LB)
-ZZ_RUN_KERNEL(zz_run_kernel_csr_multi_lb, ZZ_KIND_CSR, true, ZZ_MODE_LB)
-ZZ_RUN_KERNEL(zz_run_kernel_grid_sticky, ZZ_KIND_GRID, false, ZZ_MODE_STICKY)
-ZZ_RUN_KERNEL(zz_run_kernel_csr_sticky, ZZ_KIND_CSR, false, ZZ_MODE_STICKY)
-ZZ_RUN_KERNEL(zz_run_kernel_grid_boom, ZZ_KIND_GRID, false, ZZ_MODE_BOOM)
-ZZ_RUN_KERNEL(zz_run_kernel_csr_boom, ZZ_KIND_CSR, false, ZZ_MODE_BOOM)
-ZZ_RUN_KERNEL(zz_run_kernel_csr_logit, ZZ_KIND_CSR, false, ZZ_MODE_LOGIT)
-#ifdef ZZ_ENABLE_STRONG
-ZZ_RUN_KERNEL(zz_run_kernel_csr_strong, ZZ_KIND_CSR, false, ZZ_MODE_STRONG)
+
+// =====================================================================================================================
+// Asynchronous tile-local relaxation (round 2).  Same windows, same per-coordinate timelines, same fixed point -- but no
+// grid barrier per relaxation pass.  Every CTA owns a contiguous tile of coordinates and relaxes it to a LOCAL fixed point
+// with block barriers only: work queues and dedupe bits live in shared memory, a coordinate whose list of accepted flips
+// changed queues its readers for the CTA's next round (Gauss-Seidel: readers that have not started yet simply see the new
+// list).  Only marks that cross a tile boundary leave the SM: they are pushed into the owning CTA's inbox.  One counter
+// (`pending` = evaluations queued or in flight anywhere) detects quiescence of the whole window; two grid barriers per
+// WINDOW (agree on the outcome, publish the committed frontier) replace one per pass.
+//
+// Why any order of evaluation is exact: the converged state is the unique fixed point "every published list equals the
+// timeline of its coordinate under the published lists of its neighbours" (DESIGN.md section 3); a reader is re-queued
+// AFTER the list it reads is complete (publisher: data, fence, mark; consumer: clear the mark, fence, read), so an
+// evaluation that raced with a publication -- even one that saw a half-written list -- is always followed by one that
+// did not, and `pending` cannot reach zero before that one has finished.
+#define ZZ_TAG_STRIDE 64u    // list tags one window attempt may use (a coordinate publishes at most once per evaluation)
+#define ZZ_SQCAP 2048u       // queue entries kept in shared memory; longer queues continue in the CTA's slice of P.wl[]
+
+struct ZzAsyncSh {
+    int32_t sq[2][ZZ_SQCAP];
+    unsigned int n[2];        // entries of the two queues
+    unsigned int tcount;      // coordinates of this tile evaluated at least once in the window (commit list)
+    unsigned int head;        // inbox entries consumed
+    unsigned int dups;        // inbox entries dropped because the coordinate was queued already
+    unsigned int state;       // decision of the polling thread
+    unsigned int aborted;
+};
+#define ZZ_ST_WORK 1u
+#define ZZ_ST_DONE 2u
+#define ZZ_ST_ABORT 3u
+
+__device__ __forceinline__ unsigned int zz_ld_acq32(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+struct ZzTile {
+    int32_t lo, per, c_lo, c_hi;
+    int32_t* gq[2];       // global continuation of the two queues (this CTA's slice)
+    int32_t* tlist;       // this CTA's slice of the touched list
+    unsigned int* dirty;  // bit per coordinate of the tile: queued for a re-evaluation that has not started
+    unsigned int* tbits;  // bit per coordinate: already on the commit list
+};
+
+__device__ __forceinline__ void zz_q_put(ZzAsyncSh& S, const ZzTile& t, int buf, unsigned int pos, int32_t k)
+{
+    if (pos < ZZ_SQCAP) S.sq[buf][pos] = k; else t.gq[buf][pos] = k;
+}
+__device__ __forceinline__ int32_t zz_q_get(const ZzAsyncSh& S, const ZzTile& t, int buf, unsigned int pos)
+{
+    return pos < ZZ_SQCAP ? S.sq[buf][pos] : __ldcg(t.gq[buf] + pos);
+}
+
+// Queue coordinate k of THIS tile into queue `buf` unless it is queued already; returns false for a duplicate.
+__device__ __forceinline__ bool zz_mark_local(ZzAsyncSh& S, const ZzTile& t, int32_t k, int buf)
+{
+    const unsigned int li = (unsigned int)(k - t.c_lo), w = li >> 5, b = 1u << (li & 31u);
+    const unsigned int old = atomicOr(&t.dirty[w], b);
+    if (old & b) return false;
+    const unsigned int pos = atomicAdd(&S.n[buf], 1u);
+    zz_q_put(S, t, buf, pos, k);
+    const unsigned int ot = atomicOr(&t.tbits[w], b);
+    if (!(ot & b)) t.tlist[atomicAdd(&S.tcount, 1u)] = k;
+    return true;
+}
+
+// Marks of one changed coordinate: readers inside the tile go to the CTA's next queue; readers of other tiles are counted
+// into `pending` first, then (after a fence that also orders the list written above) pushed into their owners' inboxes.
+template <int NK>
+__device__ __forceinline__ void zz_mark_async(const ZzParams& P, ZzAsyncSh& S, const ZzTile& t, const int32_t (&kk)[NK],
+                                              int nxt, int ws, uint32_t wat)
+{
+    ZzDevCtl* C = P.ctl;
+    unsigned int nrem = 0;
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+        if (kk[q] < 0) continue;
+        if ((unsigned int)(kk[q] - t.c_lo) < (unsigned int)(t.c_hi - t.c_lo)) zz_mark_local(S, t, kk[q], nxt);
+        else nrem++;
+    }
+    if (nrem) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)nrem);
+        __threadfence();
+#pragma unroll
+        for (int q = 0; q < NK; ++q) {
+            if (kk[q] < 0 || (unsigned int)(kk[q] - t.c_lo) < (unsigned int)(t.c_hi - t.c_lo)) continue;
+            const unsigned int owner = (unsigned int)(kk[q] - t.lo) / (unsigned int)t.per;
+            const unsigned int pos = atomicAdd(P.inbox_cnt + (size_t)ws * gridDim.x + owner, 1u);
+            if (pos < P.inbox_cap)
+                *(volatile unsigned long long*)(P.inbox + (size_t)owner * P.inbox_cap + pos) = ((unsigned long long)wat << 32) | (unsigned int)kk[q];
+            else
+                atomicExch(&C->abortf[ws], 1u);
+        }
+    }
+}
+
+// Warp 0 moves the valid prefix of this CTA's inbox into queue `buf`.
+__device__ __forceinline__ void zz_drain_inbox(const ZzParams& P, ZzAsyncSh& S, const ZzTile& t, int buf, int ws, uint32_t wat)
+{
+    const unsigned int lane = threadIdx.x & 31u;
+    unsigned int head = S.head;
+    const unsigned long long* box = P.inbox + (size_t)blockIdx.x * P.inbox_cap;
+    for (;;) {
+        unsigned int tail = 0;
+        if (lane == 0) tail = zz_ld_acq32(P.inbox_cnt + (size_t)ws * gridDim.x + blockIdx.x);
+        tail = __shfl_sync(0xffffffffu, tail, 0);
+        if (tail > P.inbox_cap) tail = P.inbox_cap;
+        if (head >= tail) break;
+        const unsigned int e = head + lane;
+        bool ok = false; int32_t k = -1;
+        if (e < tail) {
+            const unsigned long long v = zz_ld_acq(box + e);
+            ok = ((uint32_t)(v >> 32) == wat);
+            k = (int32_t)(uint32_t)v;
+        }
+        const unsigned int m = __ballot_sync(0xffffffffu, ok);
+        const unsigned int nvalid = (m == 0xffffffffu) ? 32u : (unsigned int)(__ffs((int)~m) - 1);
+        if (lane < nvalid && !zz_mark_local(S, t, k, buf)) atomicAdd(&S.dups, 1u);
+        head += nvalid;
+        if (nvalid < 32u) break;   // reached the tail, or an entry whose producer has not stored it yet (picked up next time)
+    }
+    __syncwarp();
+    if (lane == 0) S.head = head;
+}
+
+template <int KIND, bool MULTI, int MODE>
+__device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S, const ZzTile& t, int32_t j, const ZzNodeOut& o,
+                                                 uint32_t w0, int nxt, int ws, uint32_t wat)
+{
+    ZzDevCtl* C = P.ctl;
+    int slot;
+    const uint32_t cnt = zz_pick_slot(o.hdr0, o.hdr1, w0, 0xffffffffu, slot);
+    bool same = (cnt == o.nflip);
+    uint32_t flags = o.flags;
+    if (same && cnt) {
+        const double* fl = P.v.flips + ((size_t)j * 2 + slot) * ZZ_MAXFLIP;
+#pragma unroll
+        for (int m = 0; m < ZZ_MAXFLIP; ++m)
+            if (m < (int)cnt) same = same && (zz_d2u(__ldcg(fl + m)) == zz_d2u(o.fl[m]));
+        if (ZZ_MODE_HAS_VEL(MODE)) {
+            const double* ft = P.v.fth + ((size_t)j * 2 + slot) * ZZ_MAXFLIP;
+#pragma unroll
+            for (int m = 0; m < ZZ_MAXFLIP; ++m)
+                if (m < (int)cnt) same = same && (zz_d2u(__ldcg(ft + m)) == zz_d2u(o.fth[m]));
+        }
+    }
+    if (!same) {
+        const int wsl = (slot == 0) ? 1 : 0;
+        const uint32_t newtag = (slot < 0) ? w0 : (((slot == 0) ? o.hdr0 : o.hdr1) >> 4) + 1u;
+        if (newtag - w0 >= ZZ_TAG_STRIDE) {
+            flags |= ZZ_F_OVERFLOW;   // out of tags for this attempt: retry the window shorter
+        } else {
+            double* fl = P.v.flips + ((size_t)j * 2 + wsl) * ZZ_MAXFLIP;
+#pragma unroll
+            for (int m = 0; m < ZZ_MAXFLIP; ++m)
+                if (m < (int)o.nflip) fl[m] = o.fl[m];
+            if (ZZ_MODE_HAS_VEL(MODE)) {
+                double* ft = P.v.fth + ((size_t)j * 2 + wsl) * ZZ_MAXFLIP;
+#pragma unroll
+                for (int m = 0; m < ZZ_MAXFLIP; ++m)
+                    if (m < (int)o.nflip) ft[m] = o.fth[m];
+            }
+            __threadfence_block();   // list before header (readers of this CTA; others are covered by the fence before their mark)
+            reinterpret_cast<volatile uint32_t*>(P.v.kin + j)[6 + wsl] = (newtag << 4) | o.nflip;
+            __threadfence_block();   // header before the marks
+            if (KIND == ZZ_KIND_GRID) {
+                const int32_t M = P.g.grid_m, N = P.g.grid_n;
+                int32_t kk[4];
+                if (o.interior) {
+                    kk[0] = j - M; kk[1] = j - 1; kk[2] = j + 1; kk[3] = j + M;
+                } else {
+                    const int32_t col = zz_grid_col(P.g, j), row = j - col * M;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const bool ok = (q == 0) ? (col > 0) : (q == 1) ? (row > 0) : (q == 2) ? (row < M - 1) : (col < N - 1);
+                        kk[q] = ok ? j + ((q == 0) ? -M : (q == 1) ? -1 : (q == 2) ? 1 : M) : -1;
+                    }
+                }
+                zz_mark_async<4>(P, S, t, kk, nxt, ws, wat);
+            } else {
+                const int32_t q1 = P.dptr[j + 1];
+                for (int32_t q0 = P.dptr[j]; q0 < q1; q0 += 4) {
+                    int32_t kk[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) kk[q] = (q0 + q < q1) ? P.didx[q0 + q] : -1;
+                    zz_mark_async<4>(P, S, t, kk, nxt, ws, wat);
+                }
+            }
+        }
+    }
+    ZzNodeOut oo = o; oo.flags = flags;
+    zz_store_spec(P.spec + j, oo);
+    if (flags & ZZ_F_VIOL) {
+        double* vi = P.viol_info + (size_t)j * 3;
+        vi[0] = o.viol_t; vi[1] = o.viol_l; vi[2] = o.viol_lb;
+    }
+    if (flags & ZZ_F_OVERFLOW) atomicExch(&C->abortf[ws], 1u);
+}
+
+template <int KIND, bool MULTI, int MODE>
+__device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
+{
+    ZzDevCtl* C = P.ctl;
+    __shared__ ZzAsyncSh S;
+    extern __shared__ unsigned int zz_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int nwc = blockDim.x >> 5;
+    const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
+    const int32_t lo = 0, hi = P.v.d;
+    ZzTile t;
+    t.lo = lo;
+    t.per = (((hi - lo + (int32_t)gridDim.x - 1) / (int32_t)gridDim.x) + 31) & ~31;
+    t.c_lo = lo + (int32_t)blockIdx.x * t.per; if (t.c_lo > hi) t.c_lo = hi;
+    t.c_hi = (t.c_lo + t.per < hi) ? t.c_lo + t.per : hi;
+    t.gq[0] = P.wl[0] + t.c_lo; t.gq[1] = P.wl[1] + t.c_lo; t.tlist = P.touched[0] + t.c_lo;
+    t.dirty = zz_dyn; t.tbits = zz_dyn + P.flag_words;
+    unsigned long long epoch = 0;
+
+    ZzCtl ctl; uint32_t cur, wat;
+    if (__ldcg(&C->started)) {
+        ctl = C->ctl; cur = C->cur;
+    } else {
+        double F0 = zz_unkey(__ldcg(&C->f0_key));
+        zz_ctl_init(ctl, F0 < P.T ? F0 : P.T, P.T, P.delta0, P.target, P.target_flips);
+        cur = 0;
+    }
+    wat = __ldcg(&C->wattempt);   // (the host starts every run of a handle with fresh attempt numbers: they tag the inbox entries)
+    unsigned long long nprop_prev = (unsigned long long)P.target | ((unsigned long long)P.target_flips << 32);
+    unsigned int windows_done = 0;
+    unsigned long long st_iters = 0, st_retries = 0, st_evals = 0, st_rebases = 0;
+    bool stop = false;
+    unsigned long long profbuf[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+    unsigned long long* prof = leader ? profbuf : nullptr;
+    unsigned long long tmark = 0;
+
+    // slots of the first attempt of this launch (later ones are prepared one attempt ahead, see below)
+    if (threadIdx.x == 0) {
+        const int ws0 = (int)(wat % 3u);
+        P.inbox_cnt[(size_t)ws0 * gridDim.x + blockIdx.x] = 0u;
+        if (blockIdx.x == 0) {
+            C->pending[ws0] = (long long)gridDim.x; C->abortf[ws0] = 0u;
+            C->touched_cnt[ws0] = 0; C->smin_key[ws0] = ~0ULL; C->nprop_win[ws0] = 0;
+        }
+    }
+    zz_grid_barrier(C, epoch, prof);
+
+    while (ctl.phase < ZZ_PH_DONE && !stop) {
+        if (cur > P.tag_limit) {  // list tags are about to run out of bits: forget all of them
+            for (int32_t j = t.c_lo + (int32_t)threadIdx.x; j < t.c_hi; j += blockDim.x)
+                reinterpret_cast<unsigned long long*>(P.v.kin + j)[3] = 0ULL;
+            zz_grid_barrier(C, epoch, prof);
+            cur = 0; st_rebases++;
+        }
+        const ZzCtl saved = ctl;
+        zz_ctl_begin(ctl);
+        const uint32_t w0 = cur + 1;
+        cur = w0 + ZZ_TAG_STRIDE;   // every tag of this attempt is in [w0, w0 + ZZ_TAG_STRIDE)
+        const int ws = (int)(wat % 3u);
+        const uint32_t watn = wat;   // attempt number stamped into inbox entries
+        wat++;
+        const double H = ctl.H; const int incl = ctl.incl;
+
+        // ---------------- scan: the coordinates of this tile with a proposal inside the window
+        ZZ_TIC();
+        if (threadIdx.x == 0) {
+            const int wz = (int)(wat % 3u);   // slots of the NEXT attempt
+            P.inbox_cnt[(size_t)wz * gridDim.x + blockIdx.x] = 0u;
+            if (blockIdx.x == 0) {
+                C->pending[wz] = (long long)gridDim.x; C->abortf[wz] = 0u;
+                C->touched_cnt[wz] = 0; C->smin_key[wz] = ~0ULL; C->nprop_win[wz] = 0;
+            }
+            S.n[0] = 0u; S.n[1] = 0u; S.tcount = 0u; S.head = 0u; S.dups = 0u; S.aborted = 0u;
+        }
+        __syncthreads();
+        for (int32_t base = t.c_lo + warp * (32 * ZZ_SCAN_U); base < t.c_hi; base += (int32_t)nwc * (32 * ZZ_SCAN_U)) {
+            bool act[ZZ_SCAN_U];
+#pragma unroll
+            for (int u = 0; u < ZZ_SCAN_U; ++u) {
+                const int32_t j = base + u * 32 + lane;
+                act[u] = false;
+                if (j < t.c_hi) { const double tj = __ldcg(P.v.tau + j); act[u] = (tj < H) || (incl && tj == H); }
+            }
+#pragma unroll
+            for (int u = 0; u < ZZ_SCAN_U; ++u) {
+                const unsigned int m = __ballot_sync(0xffffffffu, act[u]);
+                if (base + u * 32 < t.c_hi) {
+                    if (lane == 0) {   // the ballot IS the bit word of these 32 coordinates
+                        const unsigned int w = (unsigned int)(base + u * 32 - t.c_lo) >> 5;
+                        t.dirty[w] = m; t.tbits[w] = m;
+                    }
+                    if (m) {
+                        unsigned int wb = 0;
+                        if (lane == 0) wb = atomicAdd(&S.n[0], (unsigned int)__popc(m));
+                        wb = __shfl_sync(0xffffffffu, wb, 0);
+                        if (act[u]) {
+                            const unsigned int pos = wb + __popc(m & ((1u << lane) - 1u));
+                            zz_q_put(S, t, 0, pos, base + u * 32 + lane);
+                            t.tlist[pos] = base + u * 32 + lane;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            S.tcount = S.n[0];
+            const long long dlt = (long long)S.n[0] - 1LL;   // hand back this CTA's token
+            if (dlt) atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)dlt);
+        }
+        ZZ_TOC(0);
+
+        // ---------------- local rounds until the whole window is quiescent
+        int cq = 0;
+        for (;;) {
+            __syncthreads();
+            if (warp == 0) zz_drain_inbox(P, S, t, cq, ws, watn);
+            __syncthreads();
+            const unsigned int n = S.n[cq];
+            if (threadIdx.x == 0 && S.dups) {
+                atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)(-(long long)S.dups));
+                S.dups = 0u;
+            }
+            if (n == 0) {
+                if (threadIdx.x == 0) {
+                    ZZ_TIC();
+                    unsigned int st = 0;
+                    const unsigned int* myc = P.inbox_cnt + (size_t)ws * gridDim.x + blockIdx.x;
+                    for (;;) {
+                        unsigned int tail = zz_ld_acq32(myc);
+                        if (tail > P.inbox_cap) tail = P.inbox_cap;
+                        if (tail > S.head) { st = ZZ_ST_WORK; break; }
+                        const long long pend = (long long)zz_ld_acq(reinterpret_cast<const unsigned long long*>(&C->pending[ws]));
+                        const unsigned int ab = zz_ld_acq32(&C->abortf[ws]);
+                        if (ab) { st = ZZ_ST_ABORT; break; }
+                        if (pend == 0) { st = ZZ_ST_DONE; break; }
+                    }
+                    S.state = st;
+                    ZZ_TOC(2);
+                }
+                __syncthreads();
+                if (S.state == ZZ_ST_WORK) continue;
+                break;
+            }
+            ZZ_TIC();
+            const int nq = cq ^ 1;
+            // entry e goes to warp e % (#warps), lane e / (#warps): a short queue occupies a few lanes of every warp
+            for (unsigned int e = (unsigned int)lane * nwc + (unsigned int)warp; e < n; e += blockDim.x) {
+                const int32_t j = zz_q_get(S, t, cq, e);
+                const unsigned int li = (unsigned int)(j - t.c_lo);
+                atomicAnd(&t.dirty[li >> 5], ~(1u << (li & 31u)));
+                __threadfence_block();   // the mark is cleared before anything is read (a later publication re-queues j)
+                ZzNodeOut o;
+                if constexpr (MODE == ZZ_MODE_LOGIT) zz_process_node_logit(P.g, P.v, P.lg, j, H, incl, w0, 0xffffffffu, false, o);
+                else if constexpr (MODE == ZZ_MODE_STRONG) zz_process_node_strong(P.g, P.v, P.st, j, H, incl, w0, 0xffffffffu, false, o);
+                else zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, 0xffffffffu, false, o);
+                zz_publish_async<KIND, MULTI, MODE>(P, S, t, j, o, w0, nq, ws, watn);
+                st_evals++;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const long long dlt = (long long)S.n[nq] - (long long)n;
+                if (dlt) atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)dlt);
+                S.n[cq] = 0u;
+                if (zz_ld_acq32(&C->abortf[ws])) S.aborted = 1u;
+            }
+            cq = nq;
+            st_iters++;
+            if (prof) prof[7] += 1;
+            ZZ_TOC(1);
+            __syncthreads();
+            if (S.aborted) break;
+        }
+
+        // ---------------- agree on the outcome: overflow anywhere?  size of the commit list, earliest flip (phase B)
+        const unsigned int tcount = S.tcount;
+        if (threadIdx.x == 0 && tcount) atomicAdd(&C->touched_cnt[ws], tcount);
+        if (ctl.phase == ZZ_PH_B) {
+            ZZ_TIC();
+            unsigned long long kmin = ~0ULL;
+            for (unsigned int e = threadIdx.x; e < tcount; e += blockDim.x) {
+                const int32_t j = __ldcg(t.tlist + e);
+                const ZzSpecR s = zz_load_spec(P.spec + j);
+                if (s.nflip) {
+                    double th, tf, xf; uint32_t h0, h1;
+                    zz_ld_kin(P.v.kin + j, th, tf, xf, h0, h1);
+                    int slot;
+                    zz_pick_slot(h0, h1, w0, 0xffffffffu, slot);
+                    const unsigned long long k = zz_key(__ldcg(P.v.flips + ((size_t)j * 2 + slot) * ZZ_MAXFLIP));
+                    kmin = k < kmin ? k : kmin;
+                }
+            }
+            if (kmin != ~0ULL) atomicMin(&C->smin_key[ws], kmin);
+            ZZ_TOC(5);
+        }
+        zz_grid_barrier(C, epoch, prof);
+        const bool overflow = __ldcg(&C->abortf[ws]) != 0u;
+        double smin = ZZ_INF;
+        if (!overflow && ctl.phase == ZZ_PH_B) {
+            const unsigned long long mk = __ldcg(&C->smin_key[ws]);
+            if (mk != ~0ULL) smin = zz_unkey(mk);
+        }
+
+        ZzCtl trial = ctl;
+        const int act = zz_ctl_end(trial, overflow, smin, nprop_prev);
+        if (act == ZZ_ACT_COMMIT && P.record_trace) {
+            // every event of this window must fit; otherwise hand the buffer to the host first
+            const unsigned long long tl = __ldcg(&C->trace_len);
+            const unsigned long long need = (unsigned long long)__ldcg(&C->touched_cnt[ws]) * ZZ_MAXFLIP + 1ULL;
+            if (tl + need > P.trace_cap) {
+                ctl = saved;
+                if (leader) C->need_drain = 1u;
+                break;
+            }
+        }
+        ctl = trial;
+        if (act == ZZ_ACT_COMMIT) {
+            ZZ_TIC();
+            unsigned int np = 0, nf = 0;
+            for (unsigned int e = threadIdx.x; e < tcount; e += blockDim.x) {
+                const int32_t j = __ldcg(t.tlist + e);
+                const ZzSpecR sp = zz_load_spec(P.spec + j);
+                zz_commit_node<MODE>(P, j, sp, w0, 0xffffffffu, np, nf);
+            }
+            cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
+            np = cg::reduce(w, np, cg::plus<unsigned int>());
+            nf = cg::reduce(w, nf, cg::plus<unsigned int>());
+            if (lane == 0 && (np | nf)) {
+                atomicAdd(&C->nprop_win[ws], (unsigned long long)np | ((unsigned long long)nf << 32));
+                atomicAdd(&C->num, (unsigned long long)np);
+                atomicAdd(&C->nacc, (unsigned long long)nf);
+            }
+            ZZ_TOC(3);
+            zz_grid_barrier(C, epoch, prof);
+            if (leader && P.record_trace) {  // window-end marker (i = 0): lets the host sort window by window
+                const unsigned long long pos = atomicAdd(&C->trace_len, 1ULL);
+                if (pos < P.trace_cap) {
+                    double2* e = reinterpret_cast<double2*>(P.trace + pos);
+                    e[0] = make_double2(H, __longlong_as_double(0LL));
+                    e[1] = make_double2(0.0, 0.0);
+                } else {
+                    C->trace_full = 1u;
+                }
+            }
+            nprop_prev = __ldcg(&C->nprop_win[ws]);
+            windows_done++;
+            if (__ldcg(&C->viol)) stop = true;
+            if (P.max_windows && windows_done >= P.max_windows) stop = true;
+        } else {
+            st_retries++;
+        }
+    }
+
+    if (leader) {
+        C->ctl = ctl; C->cur = cur; C->itg = 0; C->wattempt = wat; C->started = 1u;
+        for (int q = 0; q < 8; ++q) C->tprof[q] += profbuf[q];
+        C->windows += windows_done; C->retries += st_retries; C->iters += st_iters; C->rebases += st_rebases;
+    }
+    cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
+    st_evals = cg::reduce(w, st_evals, cg::plus<unsigned long long>());
+    if (lane == 0 && st_evals) atomicAdd(&C->node_evals, st_evals);
+}
+
+// ZZ_ASYNC 1 (default): single-GPU kernels run the asynchronous tile-local relaxation; the sharded (_multi) kernels and
+// zz_run_kernel_grid_sync (A/B reference, zzb_run_set("schedule", 0)) run the pass-synchronous body of round 1.
+#ifndef ZZ_ASYNC
+#define ZZ_ASYNC 1
 #endif
+template <int KIND, bool MULTI, int MODE, bool ASYNC>
+__device__ __forceinline__ void zz_run_dispatch(const ZzParams& P)
+{
+    if constexpr (ASYNC && !MULTI) zz_run_body_async<KIND, MULTI, MODE>(P);
+    else zz_run_body<KIND, MULTI, MODE>(P);
+}
+#define ZZ_RUN_KERNEL(name, KIND, MULTI, MODE, ASYNC) \
+    extern "C" __global__ void __launch_bounds__((KIND == ZZ_KIND_GRID ? ZZ_RUN_BLOCK_GRID : ZZ_RUN_BLOCK_CSR), ZZ_MINB) name(const __grid_constant__ ZzParams P) { zz_run_dispatch<KIND, MULTI, MODE, ASYNC>(P); }
+ZZ_RUN_KERNEL(zz_run_kernel_grid, ZZ_KIND_GRID, false, ZZ_MODE_PLAIN, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_csr, ZZ_KIND_CSR, false, ZZ_MODE_PLAIN, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_multi, ZZ_KIND_GRID, true, ZZ_MODE_PLAIN, 0)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_multi, ZZ_KIND_CSR, true, ZZ_MODE_PLAIN, 0)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_lb, ZZ_KIND_GRID, false, ZZ_MODE_LB, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_lb, ZZ_KIND_CSR, false, ZZ_MODE_LB, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_multi_lb, ZZ_KIND_GRID, true, ZZ_MODE_LB, 0)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_multi_lb, ZZ_KIND_CSR, true, ZZ_MODE_LB, 0)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_sticky, ZZ_KIND_GRID, false, ZZ_MODE_STICKY, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_sticky, ZZ_KIND_CSR, false, ZZ_MODE_STICKY, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_boom, ZZ_KIND_GRID, false, ZZ_MODE_BOOM, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_boom, ZZ_KIND_CSR, false, ZZ_MODE_BOOM, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_logit, ZZ_KIND_CSR, false, ZZ_MODE_LOGIT, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_strong, ZZ_KIND_CSR, false, ZZ_MODE_STRONG, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_sync, ZZ_KIND_GRID, false, ZZ_MODE_PLAIN, 0)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_sync, ZZ_KIND_CSR, false, ZZ_MODE_PLAIN, 0)

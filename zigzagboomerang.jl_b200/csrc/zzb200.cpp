@@ -46,7 +46,7 @@ static int32_t fail(int32_t code, const char* fmt, ...)
     X(cuStreamDestroy) X(cuStreamSynchronize) X(cuLaunchKernel) X(cuLaunchCooperativeKernel) X(cuEventCreate) \
     X(cuEventDestroy) X(cuEventRecord) X(cuEventSynchronize) X(cuEventElapsedTime) X(cuGetErrorString) \
     X(cuOccupancyMaxActiveBlocksPerMultiprocessor) X(cuMemGetInfo) X(cuMemHostAlloc) X(cuMemFreeHost) \
-    X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle) X(cuModuleGetGlobal)
+    X(cuIpcGetMemHandle) X(cuIpcOpenMemHandle) X(cuIpcCloseMemHandle) X(cuModuleGetGlobal) X(cuFuncSetAttribute)
 
 struct Drv {
 #define X(name) decltype(&name) p_##name = nullptr;
@@ -84,23 +84,16 @@ static int32_t cu_fail(CUresult r, const char* what)
     } while (0)
 
 // --------------------------------------------------------------------------------------------- global state
-#ifdef ZZ_ENABLE_STRONG   // experimental build (make strong): + the strong-bound sparse sticky kernel, zz_strong.h
-#define ZZ_NKERN 14
-#define ZZ_KERN_BLOCK_IDX(k) ((k) >= 12 ? 1 : ((k) & 1))
-#define ZZ_RUN_BLOCK_OF(r) ((r)->kidx() >= 12 ? 1 : (r)->kind)      // the strong kernel is a general-sparse kernel on any graph
-#else
-#define ZZ_NKERN 13   // event-loop kernels in the image (see zzb_init)
-#define ZZ_KERN_BLOCK_IDX(k) (k == 12 ? 1 : (k & 1))
-#define ZZ_RUN_BLOCK_OF(r) ((r)->kind)
-#endif
+#define ZZ_NKERN 16   // event-loop kernels in the image (see zzb_init)
+#define ZZ_KERN_BLOCK_IDX(k) ((k) == 12 || (k) == 13 ? 1 : ((k) & 1))
+#define ZZ_RUN_BLOCK_OF(r) ZZ_KERN_BLOCK_IDX((r)->kidx())      // the logistic / strong kernels are general-sparse kernels on any graph
+#define ZZ_KERN_ASYNC(k) (!((k) == 2 || (k) == 3 || (k) == 6 || (k) == 7 || (k) >= 14))   // asynchronous tile-local relaxation (zz_run_body_async)
 struct Global {
     bool ready = false;
     CUdevice dev = 0; int dev_id = 0;
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
-#ifdef ZZ_ENABLE_STRONG
     CUfunction f_init_strong = nullptr;
-#endif
     CUfunction f_setup = nullptr, f_init = nullptr, f_init_boom = nullptr, f_run[ZZ_NKERN] = {}, f_export = nullptr, f_grid_tail = nullptr;
     CUstream stream = nullptr;
     CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
@@ -184,17 +177,17 @@ struct zzb_run_s {
     ZzDevCtl hc;                       // last copy of the device control block
     int64_t launches = 0;
     int grid = 0; int kind = 1;
-#ifdef ZZ_ENABLE_STRONG
     bool strong = false; double strong_c = 0.0, kappa0 = 0.0; int strong_rule = 0;
-#endif
+    int schedule = 1;                  // 1: asynchronous tile-local relaxation; 0: pass-synchronous schedule of round 1 (plain ZigZag only)
+    DevBuf inbox, inbox_cnt; unsigned int inbox_cap = 0, flag_words = 0; int inbox_grid = 0;
+    unsigned int wat_next = 0;         // window-attempt numbers tag the inbox entries: never reused by a later run of this handle
     int kidx() const
     {
-#ifdef ZZ_ENABLE_STRONG
         if (strong) return 13;
-#endif
         if (prob && prob->logit) return 12;
         if (flags & ZZB_FLAG_BOOMERANG) return 10 + kind;
         if (flags & ZZB_FLAG_STICKY) return 8 + kind;
+        if (!schedule && nranks <= 1 && !(flags & ZZB_FLAG_LOCAL_BOUND)) return 14 + kind;
         return kind + (nranks > 1 ? 2 : 0) + ((flags & ZZB_FLAG_LOCAL_BOUND) ? 4 : 0);
     }
     DevBuf dfth, kappa; bool have_kappa = false;
@@ -261,14 +254,9 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     static const char* run_names[ZZ_NKERN] = { "zz_run_kernel_grid", "zz_run_kernel_csr", "zz_run_kernel_grid_multi", "zz_run_kernel_csr_multi",
                                          "zz_run_kernel_grid_lb", "zz_run_kernel_csr_lb", "zz_run_kernel_grid_multi_lb", "zz_run_kernel_csr_multi_lb",
                                          "zz_run_kernel_grid_sticky", "zz_run_kernel_csr_sticky", "zz_run_kernel_grid_boom", "zz_run_kernel_csr_boom",
-                                         "zz_run_kernel_csr_logit"
-#ifdef ZZ_ENABLE_STRONG
-                                         , "zz_run_kernel_csr_strong"
-#endif
-    };
-#ifdef ZZ_ENABLE_STRONG
+                                         "zz_run_kernel_csr_logit", "zz_run_kernel_csr_strong",
+                                         "zz_run_kernel_grid_sync", "zz_run_kernel_csr_sync" };   // 14, 15: round-1 schedule (A/B reference)
     CU(cuModuleGetFunction(&G.f_init_strong, G.mod, "zz_init_kernel_strong"));
-#endif
     for (int k = 0; k < ZZ_NKERN; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuModuleGetFunction(&G.f_grid_tail, G.mod, "zz_grid_tail_kernel"));
@@ -492,6 +480,8 @@ static void fill_params(zzb_run_s* r)
     P.touched[0] = r->touched.as<int32_t>();
     P.trace = r->trace.as<ZzEvent>(); P.trace_cap = r->trace_cap;
     P.ctl = r->ctl.as<ZzDevCtl>();
+    P.inbox = r->inbox.as<unsigned long long>(); P.inbox_cnt = r->inbox_cnt.as<unsigned int>();
+    P.inbox_cap = r->inbox_cap; P.flag_words = r->flag_words;
     P.record_trace = (r->flags & ZZB_FLAG_NO_TRACE) ? 0 : 1;
     P.grid = r->grid_n ? r->gridbuf.as<double>() : nullptr; P.grid_dt = r->grid_dt; P.grid_n = r->grid_n;
     P.v.local_bound = (r->flags & ZZB_FLAG_LOCAL_BOUND) ? 1 : 0;
@@ -503,9 +493,7 @@ static void fill_params(zzb_run_s* r)
         P.v.bref_rate = r->lambdaref / (double)r->d; P.v.brho = r->rho; P.v.brhobar = sqrt(1 - r->rho * r->rho);
     }
     P.v.kappa = P.v.sticky ? r->kappa.as<double>() : nullptr;
-#ifdef ZZ_ENABLE_STRONG
     P.st.c = r->strong_c; P.st.kappa = r->kappa0; P.st.rule = r->strong_rule; P.st.pad = 0;
-#endif
     P.v.nranks = r->nranks; P.v.rank = r->rank; P.v.shard = r->shard; P.v.lo = r->lo; P.v.hi = r->hi;
     if (r->nranks > 1) {
         for (int q = 0; q < r->nranks; ++q) {
@@ -591,7 +579,7 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     else if (!strcmp(key, "target_flip_frac")) r->target_flip_frac = value;
     else if (!strcmp(key, "tag_limit")) r->tag_limit = (unsigned int)value;
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
-#ifdef ZZ_ENABLE_STRONG
+    else if (!strcmp(key, "schedule")) { r->schedule = value != 0.0; r->grid = G.sm_count * G.blocks_per_sm[r->kidx()]; }
     // switch a sticky run to the strong-bound sampler of src/sparsestickyzz.jl: scalar bound constant c, rule (0 sticky, 1 reversible);
     // kappa[0] of zzb_run_upload_kappa is the thaw rate; coordinates with x0 == 0 start frozen.  Before zzb_run_upload.
     else if (!strcmp(key, "strong_c")) {
@@ -599,7 +587,6 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
         r->strong = true; r->strong_c = value; r->grid = G.sm_count * G.blocks_per_sm[r->kidx()];
     }
     else if (!strcmp(key, "strong_rule")) r->strong_rule = (int)value;
-#endif
     else if (!strcmp(key, "grid")) r->grid = std::max(1, std::min((int)value, G.sm_count * G.blocks_per_sm[r->kidx()]));
     else return fail(ZZB_E_ARG, "unknown tuning key %s", key);
     return ZZB_OK;
@@ -615,9 +602,7 @@ int32_t zzb_run_upload_kappa(zzb_run_t r, const double* kappa)
     CtxGuard cg;
     CU(cuMemcpyHtoD(r->kappa.p, kappa, (size_t)r->d * 8));
     r->have_kappa = true;
-#ifdef ZZ_ENABLE_STRONG
     r->kappa0 = kappa[0];
-#endif
     return ZZB_OK;
 }
 
@@ -654,6 +639,7 @@ int32_t zzb_run_reset(zzb_run_t r)
     ZzParams& P = r->P;
     ZzDevCtl hc; memset(&hc, 0, sizeof hc);
     hc.f0_key = ~0ULL; for (int k = 0; k < 3; ++k) hc.smin_key[k] = ~0ULL;
+    hc.wattempt = r->wat_next;
     CU(cuMemcpyHtoDAsync(r->ctl.p, &hc, sizeof hc, G.stream));
     const unsigned grid = (unsigned)std::min<size_t>(((size_t)r->d + ZZ_BLOCK - 1) / ZZ_BLOCK, (size_t)G.sm_count * 8);
     if (r->grid_n) CU(cuMemsetD8Async(r->gridbuf.p, 0xff, (size_t)r->grid_n * (size_t)r->d * 8, G.stream));   // all-ones = NaN
@@ -661,10 +647,8 @@ int32_t zzb_run_reset(zzb_run_t r)
     void* a1[] = { &P, &px, &pth, &pc };
     CU(cuLaunchKernel(G.f_setup, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a1, nullptr));
     void* a2[] = { &P };
-#ifdef ZZ_ENABLE_STRONG
     if (r->strong) CU(cuLaunchKernel(G.f_init_strong, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a2, nullptr));
     else
-#endif
     CU(cuLaunchKernel((r->flags & ZZB_FLAG_BOOMERANG) ? G.f_init_boom : G.f_init, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a2, nullptr));
     CU(cuStreamSynchronize(G.stream));
     r->launches += 2;
@@ -684,13 +668,11 @@ int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* t
         r->seed[0] = seed[0]; r->seed[1] = seed[1]; r->adapt = adapt; r->factor = factor;
         r->t0 = t0;
         CU(cuMemcpyHtoDAsync(r->in_x.p, x0, nb, G.stream));
-#ifdef ZZ_ENABLE_STRONG
         if (r->strong) {   // sparsestickystate (sparsestickyzz.jl:10-12): x0 == 0 starts frozen = velocity 0 in its record
             std::vector<double> th(theta0, theta0 + r->d);
             for (int32_t j = 0; j < r->d; ++j) if (x0[j] == 0.0) th[j] = 0.0;
             CU(cuMemcpyHtoD(r->in_th.p, th.data(), nb));
         } else
-#endif
         CU(cuMemcpyHtoDAsync(r->in_th.p, theta0, nb, G.stream));
         CU(cuMemcpyHtoDAsync(r->in_c.p, c, nb, G.stream));
         r->have_inputs = true;
@@ -736,11 +718,32 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
     float total_ms = 0.f;
     if (device_ms) *device_ms = 0.f;
     if (!(r->t0 < T)) { r->executed = true; return ZZB_OK; }  // `while t' < T` never entered (sfact.jl:199)
+    unsigned dyn_smem = 0;
+    if (ZZ_KERN_ASYNC(r->kidx())) {
+        // tiles of the asynchronous relaxation: `per` coordinates per CTA (a multiple of 32, as zz_run_body_async computes it),
+        // two bit arrays per tile in dynamic shared memory, one inbox per CTA for marks that cross a tile boundary
+        const long long per = ((((long long)r->d + r->grid - 1) / r->grid) + 31) & ~31LL;
+        P.flag_words = r->flag_words = (unsigned int)(per / 32);
+        dyn_smem = 2u * 4u * r->flag_words;
+        if (dyn_smem > 200u * 1024u) return fail(ZZB_E_ARG, "d = %d is too large for %d tiles (bit arrays of %u bytes per CTA)", r->d, r->grid, dyn_smem);
+        if (dyn_smem > 32u * 1024u)
+            CU(cuFuncSetAttribute(G.f_run[r->kidx()], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn_smem));
+        const unsigned int cap = (unsigned int)std::max<long long>(1024, 2 * per);
+        if (r->inbox_grid != r->grid || r->inbox_cap != cap) {
+            int32_t st = r->inbox.alloc((size_t)r->grid * cap * 8);
+            if (!st) st = r->inbox_cnt.alloc((size_t)3 * r->grid * 4);
+            if (st) return st == ZZB_E_CUDA ? ZZB_E_NOMEM : st;
+            CU(cuMemsetD8Async(r->inbox.p, 0xff, (size_t)r->grid * cap * 8, G.stream));   // attempt tag 0xffffffff: "not written"
+            CU(cuMemsetD8Async(r->inbox_cnt.p, 0, (size_t)3 * r->grid * 4, G.stream));
+            r->inbox_grid = r->grid; r->inbox_cap = cap;
+        }
+        P.inbox = r->inbox.as<unsigned long long>(); P.inbox_cnt = r->inbox_cnt.as<unsigned int>(); P.inbox_cap = r->inbox_cap;
+    }
     for (;;) {
         CU(cuMemsetD8Async(r->ctl.p, 0, 8, G.stream));  // barrier counter
         void* args[] = { &P };
         CU(cuEventRecord(G.ev0, G.stream));
-        CU(cuLaunchCooperativeKernel(G.f_run[r->kidx()], (unsigned)r->grid, 1, 1, (unsigned)G.run_block[ZZ_RUN_BLOCK_OF(r)], 1, 1, 0, G.stream, args));
+        CU(cuLaunchCooperativeKernel(G.f_run[r->kidx()], (unsigned)r->grid, 1, 1, (unsigned)G.run_block[ZZ_RUN_BLOCK_OF(r)], 1, 1, dyn_smem, G.stream, args));
         CU(cuEventRecord(G.ev1, G.stream));
         CU(cuStreamSynchronize(G.stream));
         r->launches++;
@@ -749,6 +752,7 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
         total_ms += ms;
         CU(cuMemcpyDtoH(&r->hc, r->ctl.p, sizeof(ZzDevCtl)));
         const ZzDevCtl& hc = r->hc;
+        r->wat_next = hc.wattempt + 1u;
         if (hc.trace_full) return fail(ZZB_E_INTERNAL, "trace record dropped (internal protocol error)");
         if (hc.viol) break;
         if (hc.ctl.phase == ZZ_PH_FAIL) return fail(ZZB_E_INTERNAL, "window controller failed");
