@@ -16,6 +16,7 @@ ref = None
 for sched in scheds:
     for frac in fracs:
         run = z.Run(prob, record_trace=False); run.set(target_frac=frac, schedule=sched)
+        if os.environ.get("FLIPSCALE"): run.set(target_flip_frac=float(os.environ["FLIPSCALE"]) * frac)
         run.upload(0.0, x0, th0, c, seed=(1, 2))
         best = 1e30
         for rep in range(3):
@@ -24,6 +25,6 @@ for sched in scheds:
         t, x, th, cc = run.final_state()
         sig = (num, nacc, float(np.sum(x)), float(np.sum(t)))
         if ref is None: ref = sig
-        keep = {k: st[k] for k in ("windows", "retries", "passes", "node_evals", "ns_scan", "ns_relax", "ns_tail", "ns_commit", "ns_barrier", "n_barriers", "n_tail_passes")}
+        keep = {k: st[k] for k in ("windows", "retries", "passes", "node_evals", "ns_scan", "ns_relax", "ns_tail", "ns_commit", "ns_barrier", "ns_phaseb", "n_barriers", "n_tail_passes", "dbg0", "dbg1", "dbg2", "dbg3", "dbg4", "dbg5", "dbg6", "dbg7")}
         print(f"sched={sched} n={n} T={T} frac={frac}: best {best:.3f} ms; {nacc} switches {num} proposals -> {nacc/best*1e3:.3e} switches/s; same={sig == ref}; {keep}", flush=True)
         run.close()

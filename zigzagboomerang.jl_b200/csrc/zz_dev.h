@@ -20,6 +20,7 @@ struct ZzMsg {
     unsigned int pad;
     unsigned long long epoch;    // written last; the receiver polls it
 };
+#define ZZ_DBG_REC 96
 #define ZZ_X_OVERFLOW 1u
 #define ZZ_X_STOP 2u
 
@@ -104,6 +105,9 @@ struct ZzParams {
     unsigned int* inbox_cnt;        // [3][grid]
     unsigned int inbox_cap;
     unsigned int flag_words;        // 32-bit words per per-tile bit array (dynamic shared memory = 2 arrays)
+    // development: per-CTA log of one window (records of 4 x u64: kind, count, globaltimer, clock64), ZZB200_DBG_WINDOW
+    unsigned long long* dbgbuf;     // [grid][ZZ_DBG_REC][4] or null
+    unsigned int dbg_window, dbg_pad;
     // subsampled logistic target (zz_logit.h; only read by zz_run_kernel_csr_logit)
     ZzLogit lg;
     ZzStrong st;

@@ -941,6 +941,13 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
 #define ZZ_TAG_STRIDE 64u    // list tags one window attempt may use (a coordinate publishes at most once per evaluation)
 #define ZZ_SQCAP 2048u       // queue entries kept in shared memory; longer queues continue in the CTA's slice of P.wl[]
 
+#define ZZ_SCAN_B 16         // 32-coordinate words per warp and scan batch
+
+__device__ __forceinline__ void zz_prefetch_l2(const void* p)
+{
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
 struct ZzAsyncSh {
     int32_t sq[2][ZZ_SQCAP];
     unsigned int n[2];        // entries of the two queues
@@ -1006,6 +1013,11 @@ __device__ __forceinline__ void zz_mark_async(const ZzParams& P, ZzAsyncSh& S, c
         else nrem++;
     }
     if (nrem) {
+#ifdef ZZ_PROF_TAIL2
+        const long long r0 = clock64();
+#endif
+        // (`pending` first: the receiver may finish the evaluation and subtract it as soon as it sees the entry; the fence
+        // keeps the order of the two atomics as seen from another SM)
         atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)nrem);
         __threadfence();
 #pragma unroll
@@ -1015,13 +1027,32 @@ __device__ __forceinline__ void zz_mark_async(const ZzParams& P, ZzAsyncSh& S, c
             const unsigned int pos = atomicAdd(P.inbox_cnt + (size_t)ws * gridDim.x + owner, 1u);
             if (pos < P.inbox_cap)
                 *(volatile unsigned long long*)(P.inbox + (size_t)owner * P.inbox_cap + pos) = ((unsigned long long)wat << 32) | (unsigned int)kk[q];
-            else
+            else {
                 atomicExch(&C->abortf[ws], 1u);
+                atomicAdd(&C->dbg[2], 1ULL);   // inbox full
+            }
         }
+        atomicAdd(&C->dbg[3], (unsigned long long)nrem);
+#ifdef ZZ_PROF_TAIL2
+        if (S.n[nxt ^ 1] <= 8u) { atomicAdd(&C->dbg[0], (unsigned long long)(clock64() - r0)); atomicAdd(&C->dbg[1], 1ULL); }
+#endif
     }
 }
 
-// Warp 0 moves the valid prefix of this CTA's inbox into queue `buf`.
+// Lattice kernels relax in Gauss-Seidel order over the checkerboard: queue 0 holds the coordinates with (row + column) even,
+// queue 1 the odd ones, and the CTA alternates between them.  All readers of a coordinate have the other colour, so two
+// coordinates that read each other are never evaluated in the same round -- which is what makes pass-synchronous (Jacobi)
+// relaxation chase phantom flips for dozens of rounds when two neighbours keep cancelling each other's speculative flips.
+template <int KIND>
+__device__ __forceinline__ int zz_colour(const ZzParams& P, int32_t k, int other)
+{
+    if (KIND != ZZ_KIND_GRID) return other;   // general graphs: whatever is not being processed (pass-synchronous inside the tile)
+    const int32_t col = zz_grid_col(P.g, k);
+    return (int)((unsigned int)(k - col * P.g.grid_m + col) & 1u);
+}
+
+// Warp 0 moves the valid prefix of this CTA's inbox into the queues (lattice: by colour; otherwise into queue `buf`).
+template <int KIND>
 __device__ __forceinline__ void zz_drain_inbox(const ZzParams& P, ZzAsyncSh& S, const ZzTile& t, int buf, int ws, uint32_t wat)
 {
     const unsigned int lane = threadIdx.x & 31u;
@@ -1042,7 +1073,7 @@ __device__ __forceinline__ void zz_drain_inbox(const ZzParams& P, ZzAsyncSh& S, 
         }
         const unsigned int m = __ballot_sync(0xffffffffu, ok);
         const unsigned int nvalid = (m == 0xffffffffu) ? 32u : (unsigned int)(__ffs((int)~m) - 1);
-        if (lane < nvalid && !zz_mark_local(S, t, k, buf)) atomicAdd(&S.dups, 1u);
+        if (lane < nvalid && !zz_mark_local(S, t, k, zz_colour<KIND>(P, k, buf))) atomicAdd(&S.dups, 1u);
         head += nvalid;
         if (nvalid < 32u) break;   // reached the tail, or an entry whose producer has not stored it yet (picked up next time)
     }
@@ -1076,6 +1107,8 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
         const uint32_t newtag = (slot < 0) ? w0 : (((slot == 0) ? o.hdr0 : o.hdr1) >> 4) + 1u;
         if (newtag - w0 >= ZZ_TAG_STRIDE) {
             flags |= ZZ_F_OVERFLOW;   // out of tags for this attempt: retry the window shorter
+            atomicAdd(&C->dbg[1], 1ULL);
+            C->dbg[2] = (unsigned long long)j | ((unsigned long long)S.state << 32) | ((unsigned long long)o.nflip << 48);   // (S.state: rounds of this window, ZZ_PROF_SCAN)
         } else {
             double* fl = P.v.flips + ((size_t)j * 2 + wsl) * ZZ_MAXFLIP;
 #pragma unroll
@@ -1087,9 +1120,29 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
                 for (int m = 0; m < ZZ_MAXFLIP; ++m)
                     if (m < (int)o.nflip) ft[m] = o.fth[m];
             }
-            __threadfence_block();   // list before header (readers of this CTA; others are covered by the fence before their mark)
             reinterpret_cast<volatile uint32_t*>(P.v.kin + j)[6 + wsl] = (newtag << 4) | o.nflip;
-            __threadfence_block();   // header before the marks
+#ifdef ZZ_PROF_SCAN
+            if (P.dbgbuf && newtag - w0 >= 16u && newtag - w0 < 40u) {   // development: who keeps re-publishing?
+                const unsigned long long pos = atomicAdd(&C->dbg[7], 1ULL);
+                if (pos < 4096ULL) {
+                    unsigned long long* r = P.dbgbuf + (size_t)gridDim.x * ZZ_DBG_REC * 4 + pos * 16;
+                    r[0] = (unsigned long long)j; r[1] = newtag - w0; r[2] = o.nflip | ((unsigned long long)cnt << 8) | ((unsigned long long)(slot + 1) << 16) | ((unsigned long long)S.state << 32);
+                    r[3] = zz_d2u(o.fl[0]); r[4] = zz_d2u(o.fl[1]);
+                    r[5] = (unsigned long long)o.hdr0 | ((unsigned long long)o.hdr1 << 32);
+                    const double* flo = P.v.flips + ((size_t)j * 2 + (slot < 0 ? 0 : slot)) * ZZ_MAXFLIP;
+                    r[6] = zz_d2u(__ldcg(flo)); r[7] = zz_d2u(__ldcg(flo + 1));
+                    const int32_t nb[4] = { j - P.g.grid_m, j - 1, j + 1, j + P.g.grid_m };
+                    for (int q = 0; q < 4; ++q) r[8 + q] = (unsigned long long)__double_as_longlong(__ldcg(reinterpret_cast<const double*>(P.v.kin + nb[q]) + 3));
+                    r[12] = zz_d2u(o.tau); r[13] = w0; r[14] = o.nprop; r[15] = o.nitems;
+                }
+            }
+#endif
+            // The list and its header must be VISIBLE IN L2 before any reader is marked: a reader that raced with the stores
+            // above (and may have seen the new header with the old contents of the slot) cleared its mark before it read, so the
+            // marks below re-queue it; a reader that clears its mark after them reads complete data.  A block-scope fence is not
+            // enough even for readers of this CTA -- everybody reads through L2 (ld.cg), and a block-scope fence does not wait
+            // for the stores to arrive there (seen on the B200 as two neighbours re-publishing each other's stale lists forever).
+            __threadfence();
             if (KIND == ZZ_KIND_GRID) {
                 const int32_t M = P.g.grid_m, N = P.g.grid_n;
                 int32_t kk[4];
@@ -1121,13 +1174,20 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
         double* vi = P.viol_info + (size_t)j * 3;
         vi[0] = o.viol_t; vi[1] = o.viol_l; vi[2] = o.viol_lb;
     }
-    if (flags & ZZ_F_OVERFLOW) atomicExch(&C->abortf[ws], 1u);
+    if (flags & ZZ_F_OVERFLOW) {
+        atomicExch(&C->abortf[ws], 1u);
+        if (o.flags & ZZ_F_OVERFLOW) atomicAdd(&C->dbg[0], 1ULL);   // flips / pool / items of the timeline itself
+    }
 }
+
+#define ZZ_DBGLOG(kind, cnt) do { if (dbg_on && threadIdx.x == 0 && dbg_n < ZZ_DBG_REC) { unsigned long long* _r = P.dbgbuf + ((size_t)blockIdx.x * ZZ_DBG_REC + dbg_n) * 4; \
+    _r[0] = (unsigned long long)(kind); _r[1] = (unsigned long long)(cnt); _r[2] = zz_now(); _r[3] = (unsigned long long)clock64(); dbg_n++; } } while (0)
 
 template <int KIND, bool MULTI, int MODE>
 __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
 {
     ZzDevCtl* C = P.ctl;
+    unsigned int dbg_n = 0;
     __shared__ ZzAsyncSh S;
     extern __shared__ unsigned int zz_dyn[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1186,6 +1246,8 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
         const uint32_t watn = wat;   // attempt number stamped into inbox entries
         wat++;
         const double H = ctl.H; const int incl = ctl.incl;
+        const bool dbg_on = P.dbgbuf && windows_done == P.dbg_window;
+        ZZ_DBGLOG(1, wat);
 
         // ---------------- scan: the coordinates of this tile with a proposal inside the window
         ZZ_TIC();
@@ -1196,57 +1258,97 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
                 C->pending[wz] = (long long)gridDim.x; C->abortf[wz] = 0u;
                 C->touched_cnt[wz] = 0; C->smin_key[wz] = ~0ULL; C->nprop_win[wz] = 0;
             }
-            S.n[0] = 0u; S.n[1] = 0u; S.tcount = 0u; S.head = 0u; S.dups = 0u; S.aborted = 0u;
+            S.n[0] = 0u; S.n[1] = 0u; S.tcount = 0u; S.head = 0u; S.dups = 0u; S.aborted = 0u; S.state = 0u;
         }
         __syncthreads();
-        for (int32_t base = t.c_lo + warp * (32 * ZZ_SCAN_U); base < t.c_hi; base += (int32_t)nwc * (32 * ZZ_SCAN_U)) {
-            bool act[ZZ_SCAN_U];
+#ifdef ZZ_PROF_SCAN
+        const long long sc0 = clock64(); long long sc1 = sc0, sc2 = sc0;
+#endif
+        // Warp w takes the 32-coordinate words w, w + #warps, ... of the tile, ZZ_SCAN_B words per batch: all loads of a batch are
+        // in flight together, the ballot of a word IS its bit word, and the warp reserves its queue slots with ONE shared-memory
+        // atomic per batch (an atomic per word serialises 200 of them on one address: 17 us per window in the first version).
+        {
+            const unsigned int nwords = (unsigned int)(t.c_hi - t.c_lo + 31) >> 5;
+            for (unsigned int wb = (unsigned int)warp; wb < nwords; wb += nwc * ZZ_SCAN_B) {
+                double tj[ZZ_SCAN_B];
 #pragma unroll
-            for (int u = 0; u < ZZ_SCAN_U; ++u) {
-                const int32_t j = base + u * 32 + lane;
-                act[u] = false;
-                if (j < t.c_hi) { const double tj = __ldcg(P.v.tau + j); act[u] = (tj < H) || (incl && tj == H); }
-            }
+                for (int u = 0; u < ZZ_SCAN_B; ++u) {
+                    const unsigned int w = wb + (unsigned int)u * nwc;
+                    const int32_t j = t.c_lo + (int32_t)(w << 5) + lane;
+                    tj[u] = (w < nwords && j < t.c_hi) ? __ldcg(P.v.tau + j) : ZZ_INF;
+                }
+                unsigned int msk[ZZ_SCAN_B], red[ZZ_SCAN_B];
+                unsigned int total = 0, total_red = 0;
 #pragma unroll
-            for (int u = 0; u < ZZ_SCAN_U; ++u) {
-                const unsigned int m = __ballot_sync(0xffffffffu, act[u]);
-                if (base + u * 32 < t.c_hi) {
-                    if (lane == 0) {   // the ballot IS the bit word of these 32 coordinates
-                        const unsigned int w = (unsigned int)(base + u * 32 - t.c_lo) >> 5;
-                        t.dirty[w] = m; t.tbits[w] = m;
-                    }
-                    if (m) {
-                        unsigned int wb = 0;
-                        if (lane == 0) wb = atomicAdd(&S.n[0], (unsigned int)__popc(m));
-                        wb = __shfl_sync(0xffffffffu, wb, 0);
-                        if (act[u]) {
-                            const unsigned int pos = wb + __popc(m & ((1u << lane) - 1u));
-                            zz_q_put(S, t, 0, pos, base + u * 32 + lane);
-                            t.tlist[pos] = base + u * 32 + lane;
+                for (int u = 0; u < ZZ_SCAN_B; ++u) {
+                    const bool act = (tj[u] < H) || (incl && tj[u] == H);
+                    const int32_t j = t.c_lo + (int32_t)((wb + (unsigned int)u * nwc) << 5) + lane;
+                    msk[u] = __ballot_sync(0xffffffffu, act);
+                    red[u] = msk[u];
+                    if (KIND == ZZ_KIND_GRID) red[u] = __ballot_sync(0xffffffffu, act && zz_colour<KIND>(P, j, 0) == 0);
+                    total += (unsigned int)__popc(msk[u]);
+                    total_red += (unsigned int)__popc(red[u]);
+                    if (act) {   // the records the evaluation will gather: start them towards L2 now
+                        zz_prefetch_l2(P.v.kin + j); zz_prefetch_l2(P.v.priv + j); zz_prefetch_l2(P.v.kctr + j);
+                        if (KIND == ZZ_KIND_GRID) {
+                            if (j >= P.g.grid_m) zz_prefetch_l2(P.v.kin + j - P.g.grid_m);
+                            if (j + P.g.grid_m < P.v.d) zz_prefetch_l2(P.v.kin + j + P.g.grid_m);
                         }
+                    }
+                }
+#ifdef ZZ_PROF_SCAN
+                sc1 = clock64();
+#endif
+                // one atomic per queue and batch: [0] queue 0 (lattice: even colour), [1] queue 1, [2] commit list
+                unsigned int base0 = 0, base1 = 0, baset = 0;
+                if (lane == 0 && total) {
+                    if (total_red) base0 = atomicAdd(&S.n[0], total_red);
+                    if (total - total_red) base1 = atomicAdd(&S.n[1], total - total_red);
+                    baset = atomicAdd(&S.tcount, total);
+                }
+                base0 = __shfl_sync(0xffffffffu, base0, 0);
+                base1 = __shfl_sync(0xffffffffu, base1, 0);
+                baset = __shfl_sync(0xffffffffu, baset, 0);
+#pragma unroll
+                for (int u = 0; u < ZZ_SCAN_B; ++u) {
+                    const unsigned int w = wb + (unsigned int)u * nwc;
+                    if (w < nwords) {
+                        if (lane == 0) { t.dirty[w] = msk[u]; t.tbits[w] = msk[u]; }
+                        const unsigned int below = (1u << lane) - 1u;
+                        if (msk[u] & (1u << lane)) {
+                            const int32_t j = t.c_lo + (int32_t)(w << 5) + lane;
+                            if (red[u] & (1u << lane)) zz_q_put(S, t, 0, base0 + __popc(red[u] & below), j);
+                            else zz_q_put(S, t, 1, base1 + __popc((msk[u] & ~red[u]) & below), j);
+                            t.tlist[baset + __popc(msk[u] & below)] = j;
+                        }
+                        base0 += (unsigned int)__popc(red[u]);
+                        base1 += (unsigned int)__popc(msk[u] & ~red[u]);
+                        baset += (unsigned int)__popc(msk[u]);
                     }
                 }
             }
         }
+#ifdef ZZ_PROF_SCAN
+        sc2 = clock64();
+#endif
         __syncthreads();
+#ifdef ZZ_PROF_SCAN
+        if (leader) { const long long sc3 = clock64(); C->dbg[4] += 1; C->dbg[5] += (unsigned long long)(sc1 - sc0); C->dbg[6] += (unsigned long long)(sc3 - sc1); }
+#endif
         if (threadIdx.x == 0) {
-            S.tcount = S.n[0];
-            const long long dlt = (long long)S.n[0] - 1LL;   // hand back this CTA's token
+            const long long dlt = (long long)S.tcount - 1LL;   // queued evaluations; hand back this CTA's token
             if (dlt) atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)dlt);
         }
         ZZ_TOC(0);
+        ZZ_DBGLOG(2, S.tcount);
 
         // ---------------- local rounds until the whole window is quiescent
+        // Invariant at the top: queue `cq` is complete (local marks of the previous round + drained inbox entries), every
+        // thread of the CTA is past a block barrier.  Two block barriers per round.
         int cq = 0;
         for (;;) {
-            __syncthreads();
-            if (warp == 0) zz_drain_inbox(P, S, t, cq, ws, watn);
-            __syncthreads();
             const unsigned int n = S.n[cq];
-            if (threadIdx.x == 0 && S.dups) {
-                atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)(-(long long)S.dups));
-                S.dups = 0u;
-            }
+            if (n == 0 && S.n[cq ^ 1] != 0u) { cq ^= 1; continue; }   // (uniform: read after a block barrier)
             if (n == 0) {
                 if (threadIdx.x == 0) {
                     ZZ_TIC();
@@ -1256,6 +1358,7 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
                         unsigned int tail = zz_ld_acq32(myc);
                         if (tail > P.inbox_cap) tail = P.inbox_cap;
                         if (tail > S.head) { st = ZZ_ST_WORK; break; }
+                        // order matters: an evaluation that overflowed raised the flag BEFORE it was subtracted from `pending`
                         const long long pend = (long long)zz_ld_acq(reinterpret_cast<const unsigned long long*>(&C->pending[ws]));
                         const unsigned int ab = zz_ld_acq32(&C->abortf[ws]);
                         if (ab) { st = ZZ_ST_ABORT; break; }
@@ -1263,13 +1366,37 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
                     }
                     S.state = st;
                     ZZ_TOC(2);
+                    ZZ_DBGLOG(4, st);
                 }
                 __syncthreads();
-                if (S.state == ZZ_ST_WORK) continue;
-                break;
+                if (S.state != ZZ_ST_WORK) break;
+                if (warp == 0) {
+                    zz_drain_inbox<KIND>(P, S, t, cq, ws, watn);
+                    if (lane == 0 && S.dups) {
+                        atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)(-(long long)S.dups));
+                        S.dups = 0u;
+                    }
+                }
+                __syncthreads();
+                continue;
             }
             ZZ_TIC();
+            ZZ_DBGLOG(3, n);
+#ifdef ZZ_PROF_SCAN
+            if (threadIdx.x == 0) S.state = (S.state >= 1000u ? S.state : 1000u) + 1u;
+#endif
+#ifdef ZZ_PROF_TAIL2
+            const long long q0 = clock64();
+#endif
             const int nq = cq ^ 1;
+            const unsigned int other0 = S.n[nq];   // (lattice: the other colour may hold entries of the scan or of the inbox already)
+            // the inbox counter and the abort flag are needed only AFTER the evaluations: start the loads now (plain loads:
+            // the entries themselves are read with acquire semantics, the flag is only a hint to stop early)
+            unsigned int tail_pre = 0, abort_pre = 0;
+            if (threadIdx.x == 0) {
+                tail_pre = *(volatile const unsigned int*)(P.inbox_cnt + (size_t)ws * gridDim.x + blockIdx.x);
+                abort_pre = *(volatile const unsigned int*)&C->abortf[ws];
+            }
             // entry e goes to warp e % (#warps), lane e / (#warps): a short queue occupies a few lanes of every warp
             for (unsigned int e = (unsigned int)lane * nwc + (unsigned int)warp; e < n; e += blockDim.x) {
                 const int32_t j = zz_q_get(S, t, cq, e);
@@ -1277,24 +1404,49 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
                 atomicAnd(&t.dirty[li >> 5], ~(1u << (li & 31u)));
                 __threadfence_block();   // the mark is cleared before anything is read (a later publication re-queues j)
                 ZzNodeOut o;
+#ifdef ZZ_PROF_TAIL2
+                const long long c0 = clock64();
+#endif
                 if constexpr (MODE == ZZ_MODE_LOGIT) zz_process_node_logit(P.g, P.v, P.lg, j, H, incl, w0, 0xffffffffu, false, o);
                 else if constexpr (MODE == ZZ_MODE_STRONG) zz_process_node_strong(P.g, P.v, P.st, j, H, incl, w0, 0xffffffffu, false, o);
                 else zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, 0xffffffffu, false, o);
+#ifdef ZZ_PROF_TAIL2
+                const long long c1 = clock64();
+#endif
                 zz_publish_async<KIND, MULTI, MODE>(P, S, t, j, o, w0, nq, ws, watn);
+#ifdef ZZ_PROF_TAIL2
+                if (n <= 8 && e == 0) {   // lone evaluations of tail rounds: cycles in the timeline / in the publication
+                    const long long c2 = clock64();
+                    atomicAdd(&C->dbg[4], 1ULL); atomicAdd(&C->dbg[5], (unsigned long long)(c1 - c0)); atomicAdd(&C->dbg[6], (unsigned long long)(c2 - c1));
+                    atomicAdd(&C->dbg[7], (unsigned long long)o.nitems);
+                }
+#endif
                 st_evals++;
             }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                const long long dlt = (long long)S.n[nq] - (long long)n;
-                if (dlt) atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)dlt);
-                S.n[cq] = 0u;
-                if (zz_ld_acq32(&C->abortf[ws])) S.aborted = 1u;
+            __syncthreads();   // every publication and every local mark of this round is done
+            if (warp == 0) {
+                const unsigned int produced = S.n[nq] - other0;   // local marks only: inbox entries were counted by their senders
+                if (lane == 0) S.n[cq] = 0u;                          // (before the drain: on the lattice it may refill this queue)
+                __syncwarp();
+                tail_pre = __shfl_sync(0xffffffffu, tail_pre, 0);
+                if (tail_pre > S.head) zz_drain_inbox<KIND>(P, S, t, nq, ws, watn);
+                if (lane == 0) {
+                    const long long dlt = (long long)produced - (long long)n - (long long)S.dups;
+                    if (dlt) atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)dlt);
+                    S.dups = 0u;
+                    if (abort_pre) S.aborted = 1u;
+                }
             }
             cq = nq;
             st_iters++;
             if (prof) prof[7] += 1;
             ZZ_TOC(1);
             __syncthreads();
+#ifdef ZZ_PROF_TAIL2
+            if (threadIdx.x == 0 && n <= 8u) {   // whole tail round, thread 0 of every CTA
+                atomicAdd(&C->tprof[5], (unsigned long long)(clock64() - q0)); atomicAdd(&C->dbg[2], 1ULL);
+            }
+#endif
             if (S.aborted) break;
         }
 
@@ -1319,7 +1471,9 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
             if (kmin != ~0ULL) atomicMin(&C->smin_key[ws], kmin);
             ZZ_TOC(5);
         }
+        ZZ_DBGLOG(5, tcount);
         zz_grid_barrier(C, epoch, prof);
+        ZZ_DBGLOG(6, 0);
         const bool overflow = __ldcg(&C->abortf[ws]) != 0u;
         double smin = ZZ_INF;
         if (!overflow && ctl.phase == ZZ_PH_B) {
@@ -1357,7 +1511,9 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
                 atomicAdd(&C->nacc, (unsigned long long)nf);
             }
             ZZ_TOC(3);
+            ZZ_DBGLOG(7, np);
             zz_grid_barrier(C, epoch, prof);
+            ZZ_DBGLOG(8, 0);
             if (leader && P.record_trace) {  // window-end marker (i = 0): lets the host sort window by window
                 const unsigned long long pos = atomicAdd(&C->trace_len, 1ULL);
                 if (pos < P.trace_cap) {

@@ -180,6 +180,7 @@ struct zzb_run_s {
     bool strong = false; double strong_c = 0.0, kappa0 = 0.0; int strong_rule = 0;
     int schedule = 1;                  // 1: asynchronous tile-local relaxation; 0: pass-synchronous schedule of round 1 (plain ZigZag only)
     DevBuf inbox, inbox_cnt; unsigned int inbox_cap = 0, flag_words = 0; int inbox_grid = 0;
+    DevBuf dbgbuf; std::vector<unsigned long long> dbghost;
     unsigned int wat_next = 0;         // window-attempt numbers tag the inbox entries: never reused by a later run of this handle
     int kidx() const
     {
@@ -738,6 +739,13 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
             r->inbox_grid = r->grid; r->inbox_cap = cap;
         }
         P.inbox = r->inbox.as<unsigned long long>(); P.inbox_cnt = r->inbox_cnt.as<unsigned int>(); P.inbox_cap = r->inbox_cap;
+        if (const char* dw = getenv("ZZB200_DBG_WINDOW")) {   // development: log the rounds of one window per CTA (tools/window_trace.py)
+            const size_t nb = (size_t)r->grid * ZZ_DBG_REC * 4 * 8 + 4096 * 16 * 8;
+            int32_t st = r->dbgbuf.alloc(nb);
+            if (st) return st;
+            CU(cuMemsetD8Async(r->dbgbuf.p, 0, nb, G.stream));
+            P.dbgbuf = r->dbgbuf.as<unsigned long long>(); P.dbg_window = (unsigned int)atoi(dw);
+        } else P.dbgbuf = nullptr;
     }
     for (;;) {
         CU(cuMemsetD8Async(r->ctl.p, 0, 8, G.stream));  // barrier counter
@@ -769,6 +777,11 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
         if (r->max_windows && !hc.need_drain) break;  // caller asked for a bounded slice
     }
     if (device_ms) *device_ms = total_ms;
+    if (P.dbgbuf) {
+        r->dbghost.resize((size_t)r->grid * ZZ_DBG_REC * 4 + 4096 * 16);
+        CU(cuMemcpyDtoH(r->dbghost.data(), r->dbgbuf.p, r->dbghost.size() * 8));
+        if (const char* f = getenv("ZZB200_DBG_FILE")) { FILE* fp = fopen(f, "wb"); if (fp) { fwrite(r->dbghost.data(), 8, r->dbghost.size(), fp); fclose(fp); } }
+    }
     r->executed = true; r->fetched = false;
     if (r->hc.viol == 2u) return fail(ZZB_E_INTERNAL, "sticky sampler: a freezing coordinate was not at 0 (ss_fact.jl:89-91)");
     if (r->hc.viol) {
