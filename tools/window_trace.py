@@ -17,7 +17,7 @@ if sys.argv[1] == "run":
         run = z.Run(prob, record_trace=False); run.upload(0.0, x0, th0, c, seed=(1, 2)); ms = run.execute(2.0); run.close()
     print("kernel ms", ms)
 else:
-    a = np.fromfile(sys.argv[2], dtype=np.uint64).reshape(-1, REC, 4)
+    a = np.fromfile(sys.argv[2], dtype=np.uint64); a = a[:len(a) - 4096 * 16].reshape(-1, REC, 4)
     ncta = a.shape[0]
     # align the per-CTA time axis at the start record (kind 1) -- globaltimer is global already
     t0 = min(int(a[b, 0, 2]) for b in range(ncta) if a[b, 0, 0] == 1)

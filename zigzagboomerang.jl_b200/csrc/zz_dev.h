@@ -105,9 +105,13 @@ struct ZzParams {
     unsigned int* inbox_cnt;        // [3][grid]
     unsigned int inbox_cap;
     unsigned int flag_words;        // 32-bit words per per-tile bit array (dynamic shared memory = 2 arrays)
+    unsigned long long* inbox_peer[ZZ_MAXRANKS];   // sharded runs: the inboxes / counters of every rank (own entries = the plain pointers)
+    unsigned int* inbox_cnt_peer[ZZ_MAXRANKS];
+    int32_t tile_per, tile_pad;     // coordinates per tile (a multiple of 32), identical on every rank
     // development: per-CTA log of one window (records of 4 x u64: kind, count, globaltimer, clock64), ZZB200_DBG_WINDOW
     unsigned long long* dbgbuf;     // [grid][ZZ_DBG_REC][4] or null
-    unsigned int dbg_window, dbg_pad;
+    unsigned int dbg_window;
+    unsigned int eval_threads;      // development: threads of a CTA that take queue entries (0 = all)
     // subsampled logistic target (zz_logit.h; only read by zz_run_kernel_csr_logit)
     ZzLogit lg;
     ZzStrong st;

@@ -411,8 +411,10 @@ __device__ __forceinline__ void zz_grid_fill(const ZzParams& P, int32_t j, doubl
     }
 }
 
+template <int KIND> __device__ __forceinline__ unsigned int zz_reader_ranks(const ZzParams& P, int32_t j);
+
 // Fold the converged end-of-window state of coordinate j into the frontier.
-template <int MODE>
+template <int MODE, int KIND = ZZ_KIND_CSR, bool MULTI = false>
 __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, const ZzSpecR& s, uint32_t w0, uint32_t cur,
                                                unsigned int& nprop_acc, unsigned int& nflip_acc)
 {
@@ -489,6 +491,15 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, con
         double2* kq = reinterpret_cast<double2*>(P.v.kin + j);
         kq[0] = make_double2(th, tf);
         reinterpret_cast<double*>(P.v.kin + j)[2] = xf;
+        if (MULTI) {   // sharded: the new anchor also goes into the replicas of the ranks that read j
+            for (unsigned int rm = (KIND == ZZ_KIND_GRID) ? zz_reader_ranks<ZZ_KIND_GRID>(P, j) : zz_reader_ranks<ZZ_KIND_CSR>(P, j); rm; rm &= rm - 1u) {
+                const int rr = __ffs((int)rm) - 1;
+                double2* kr = reinterpret_cast<double2*>(P.v.kin_peer[rr] + j);
+                kr[0] = make_double2(th, tf);
+                reinterpret_cast<double*>(P.v.kin_peer[rr] + j)[2] = xf;
+                __threadfence_system();   // (ordered before the node-wide boundary that ends the commit)
+            }
+        }
     }
 }
 
@@ -938,7 +949,7 @@ __device__ __forceinline__ void zz_run_body(const ZzParams& P)
 // AFTER the list it reads is complete (publisher: data, fence, mark; consumer: clear the mark, fence, read), so an
 // evaluation that raced with a publication -- even one that saw a half-written list -- is always followed by one that
 // did not, and `pending` cannot reach zero before that one has finished.
-#define ZZ_TAG_STRIDE 64u    // list tags one window attempt may use (a coordinate publishes at most once per evaluation)
+#define ZZ_TAG_STRIDE 256u   // list tags one window attempt may use (a coordinate publishes at most once per evaluation)
 #define ZZ_SQCAP 2048u       // queue entries kept in shared memory; longer queues continue in the CTA's slice of P.wl[]
 
 #define ZZ_SCAN_B 16         // 32-coordinate words per warp and scan batch
@@ -956,6 +967,7 @@ struct ZzAsyncSh {
     unsigned int dups;        // inbox entries dropped because the coordinate was queued already
     unsigned int state;       // decision of the polling thread
     unsigned int aborted;
+    unsigned int wsum[32];    // per-warp totals of the scan's prefix sum
 };
 #define ZZ_ST_WORK 1u
 #define ZZ_ST_DONE 2u
@@ -966,6 +978,31 @@ __device__ __forceinline__ unsigned int zz_ld_acq32(const unsigned int* p)
     unsigned int v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+__device__ __forceinline__ unsigned int zz_ld_acq32_sys(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// `pending` / `abortf` of a sharded run live in rank 0's control block: system scope over NVLink
+template <bool MULTI> __device__ __forceinline__ void zz_pending_add(long long* p, long long v)
+{
+    if (MULTI) atomicAdd_system(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+    else atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+template <bool MULTI> __device__ __forceinline__ long long zz_pending_ld(const long long* p)
+{
+    return (long long)(MULTI ? zz_ld_acq_sys(reinterpret_cast<const unsigned long long*>(p)) : zz_ld_acq(reinterpret_cast<const unsigned long long*>(p)));
+}
+template <bool MULTI> __device__ __forceinline__ unsigned int zz_flag_ld(const unsigned int* p)
+{
+    return MULTI ? zz_ld_acq32_sys(p) : zz_ld_acq32(p);
+}
+template <bool MULTI> __device__ __forceinline__ void zz_flag_raise(unsigned int* p)
+{
+    if (MULTI) atomicExch_system(p, 1u); else atomicExch(p, 1u);
 }
 
 struct ZzTile {
@@ -998,44 +1035,48 @@ __device__ __forceinline__ bool zz_mark_local(ZzAsyncSh& S, const ZzTile& t, int
     return true;
 }
 
-// Marks of one changed coordinate: readers inside the tile go to the CTA's next queue; readers of other tiles are counted
-// into `pending` first, then (after a fence that also orders the list written above) pushed into their owners' inboxes.
-template <int NK>
+// Marks of one changed coordinate: readers inside the tile go to the CTA's other queue; readers of other tiles (possibly on
+// another GPU) are counted into `pending` first, then -- after a fence that orders both the counter and the list written by the
+// caller before the entry -- pushed into their owners' inboxes.
+template <int NK, bool MULTI>
 __device__ __forceinline__ void zz_mark_async(const ZzParams& P, ZzAsyncSh& S, const ZzTile& t, const int32_t (&kk)[NK],
                                               int nxt, int ws, uint32_t wat)
 {
     ZzDevCtl* C = P.ctl;
-    unsigned int nrem = 0;
+    ZzDevCtl* G0 = MULTI ? P.ctl_peer[0] : C;
+    unsigned int nrem = 0; bool offgpu = false;
 #pragma unroll
     for (int q = 0; q < NK; ++q) {
         if (kk[q] < 0) continue;
         if ((unsigned int)(kk[q] - t.c_lo) < (unsigned int)(t.c_hi - t.c_lo)) zz_mark_local(S, t, kk[q], nxt);
-        else nrem++;
+        else { nrem++; if (MULTI && (kk[q] < P.v.lo || kk[q] >= P.v.hi)) offgpu = true; }
     }
     if (nrem) {
-#ifdef ZZ_PROF_TAIL2
-        const long long r0 = clock64();
-#endif
-        // (`pending` first: the receiver may finish the evaluation and subtract it as soon as it sees the entry; the fence
-        // keeps the order of the two atomics as seen from another SM)
-        atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)nrem);
-        __threadfence();
+        // (`pending` first: the receiver may finish the evaluation and subtract it as soon as it sees the entry)
+        zz_pending_add<MULTI>(&G0->pending[ws], (long long)nrem);
+        if (MULTI && offgpu) __threadfence_system(); else __threadfence();
 #pragma unroll
         for (int q = 0; q < NK; ++q) {
             if (kk[q] < 0 || (unsigned int)(kk[q] - t.c_lo) < (unsigned int)(t.c_hi - t.c_lo)) continue;
-            const unsigned int owner = (unsigned int)(kk[q] - t.lo) / (unsigned int)t.per;
-            const unsigned int pos = atomicAdd(P.inbox_cnt + (size_t)ws * gridDim.x + owner, 1u);
+            unsigned int* cnt; unsigned long long* box; unsigned int owner;
+            if (MULTI) {
+                const int r = kk[q] / P.v.shard;
+                owner = (unsigned int)(kk[q] - r * P.v.shard) / (unsigned int)t.per;
+                cnt = P.inbox_cnt_peer[r]; box = P.inbox_peer[r];
+            } else {
+                owner = (unsigned int)(kk[q] - t.lo) / (unsigned int)t.per;
+                cnt = P.inbox_cnt; box = P.inbox;
+            }
+            const unsigned int pos = MULTI ? atomicAdd_system(cnt + (size_t)ws * gridDim.x + owner, 1u)
+                                           : atomicAdd(cnt + (size_t)ws * gridDim.x + owner, 1u);
             if (pos < P.inbox_cap)
-                *(volatile unsigned long long*)(P.inbox + (size_t)owner * P.inbox_cap + pos) = ((unsigned long long)wat << 32) | (unsigned int)kk[q];
+                *(volatile unsigned long long*)(box + (size_t)owner * P.inbox_cap + pos) = ((unsigned long long)wat << 32) | (unsigned int)kk[q];
             else {
-                atomicExch(&C->abortf[ws], 1u);
+                zz_flag_raise<MULTI>(&G0->abortf[ws]);
                 atomicAdd(&C->dbg[2], 1ULL);   // inbox full
             }
         }
         atomicAdd(&C->dbg[3], (unsigned long long)nrem);
-#ifdef ZZ_PROF_TAIL2
-        if (S.n[nxt ^ 1] <= 8u) { atomicAdd(&C->dbg[0], (unsigned long long)(clock64() - r0)); atomicAdd(&C->dbg[1], 1ULL); }
-#endif
     }
 }
 
@@ -1052,7 +1093,7 @@ __device__ __forceinline__ int zz_colour(const ZzParams& P, int32_t k, int other
 }
 
 // Warp 0 moves the valid prefix of this CTA's inbox into the queues (lattice: by colour; otherwise into queue `buf`).
-template <int KIND>
+template <int KIND, bool MULTI>
 __device__ __forceinline__ void zz_drain_inbox(const ZzParams& P, ZzAsyncSh& S, const ZzTile& t, int buf, int ws, uint32_t wat)
 {
     const unsigned int lane = threadIdx.x & 31u;
@@ -1060,14 +1101,14 @@ __device__ __forceinline__ void zz_drain_inbox(const ZzParams& P, ZzAsyncSh& S, 
     const unsigned long long* box = P.inbox + (size_t)blockIdx.x * P.inbox_cap;
     for (;;) {
         unsigned int tail = 0;
-        if (lane == 0) tail = zz_ld_acq32(P.inbox_cnt + (size_t)ws * gridDim.x + blockIdx.x);
+        if (lane == 0) tail = zz_flag_ld<MULTI>(P.inbox_cnt + (size_t)ws * gridDim.x + blockIdx.x);
         tail = __shfl_sync(0xffffffffu, tail, 0);
         if (tail > P.inbox_cap) tail = P.inbox_cap;
         if (head >= tail) break;
         const unsigned int e = head + lane;
         bool ok = false; int32_t k = -1;
         if (e < tail) {
-            const unsigned long long v = zz_ld_acq(box + e);
+            const unsigned long long v = MULTI ? zz_ld_acq_sys(box + e) : zz_ld_acq(box + e);
             ok = ((uint32_t)(v >> 32) == wat);
             k = (int32_t)(uint32_t)v;
         }
@@ -1079,6 +1120,25 @@ __device__ __forceinline__ void zz_drain_inbox(const ZzParams& P, ZzAsyncSh& S, 
     }
     __syncwarp();
     if (lane == 0) S.head = head;
+}
+
+// Sharded runs: every rank keeps a replica of the records it reads from other ranks at the SAME global index of its own
+// (full-length) arrays; the owner pushes every change -- published lists, committed anchors -- into the replicas of the ranks
+// that read the coordinate, so that no evaluation ever loads over NVLink.  Bit r of the result: rank r (other than the owner)
+// reads coordinate j.
+template <int KIND>
+__device__ __forceinline__ unsigned int zz_reader_ranks(const ZzParams& P, int32_t j)
+{
+    unsigned int m = 0;
+    if (KIND == ZZ_KIND_GRID) {   // whole lattice columns per rank: only the j -+ M readers can live elsewhere
+        const int32_t M = P.g.grid_m;
+        if (j - M >= 0) m |= 1u << ((j - M) / P.v.shard);
+        if (j + M < P.v.d) m |= 1u << ((j + M) / P.v.shard);
+    } else {
+        const int32_t q1 = P.dptr[j + 1];
+        for (int32_t q = P.dptr[j]; q < q1; ++q) m |= 1u << (P.didx[q] / P.v.shard);
+    }
+    return m & ~(1u << P.v.rank);
 }
 
 template <int KIND, bool MULTI, int MODE>
@@ -1121,6 +1181,16 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
                     if (m < (int)o.nflip) ft[m] = o.fth[m];
             }
             reinterpret_cast<volatile uint32_t*>(P.v.kin + j)[6 + wsl] = (newtag << 4) | o.nflip;
+            if (MULTI) {   // the same list and header into the replicas of the ranks that read j (plain stores over NVLink)
+                for (unsigned int rm = zz_reader_ranks<KIND>(P, j); rm; rm &= rm - 1u) {
+                    const int rr = __ffs((int)rm) - 1;
+                    double* flr = P.v.flips_peer[rr] + ((size_t)j * 2 + wsl) * ZZ_MAXFLIP;
+#pragma unroll
+                    for (int m = 0; m < ZZ_MAXFLIP; ++m)
+                        if (m < (int)o.nflip) flr[m] = o.fl[m];
+                    reinterpret_cast<volatile uint32_t*>(P.v.kin_peer[rr] + j)[6 + wsl] = (newtag << 4) | o.nflip;
+                }
+            }
 #ifdef ZZ_PROF_SCAN
             if (P.dbgbuf && newtag - w0 >= 16u && newtag - w0 < 40u) {   // development: who keeps re-publishing?
                 const unsigned long long pos = atomicAdd(&C->dbg[7], 1ULL);
@@ -1142,6 +1212,7 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
             // marks below re-queue it; a reader that clears its mark after them reads complete data.  A block-scope fence is not
             // enough even for readers of this CTA -- everybody reads through L2 (ld.cg), and a block-scope fence does not wait
             // for the stores to arrive there (seen on the B200 as two neighbours re-publishing each other's stale lists forever).
+            // (sharded: a reader on another GPU is only ever reached through zz_mark_async, whose system-scope fence is cumulative)
             __threadfence();
             if (KIND == ZZ_KIND_GRID) {
                 const int32_t M = P.g.grid_m, N = P.g.grid_n;
@@ -1156,14 +1227,14 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
                         kk[q] = ok ? j + ((q == 0) ? -M : (q == 1) ? -1 : (q == 2) ? 1 : M) : -1;
                     }
                 }
-                zz_mark_async<4>(P, S, t, kk, nxt, ws, wat);
+                zz_mark_async<4, MULTI>(P, S, t, kk, nxt, ws, wat);
             } else {
                 const int32_t q1 = P.dptr[j + 1];
                 for (int32_t q0 = P.dptr[j]; q0 < q1; q0 += 4) {
                     int32_t kk[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) kk[q] = (q0 + q < q1) ? P.didx[q0 + q] : -1;
-                    zz_mark_async<4>(P, S, t, kk, nxt, ws, wat);
+                    zz_mark_async<4, MULTI>(P, S, t, kk, nxt, ws, wat);
                 }
             }
         }
@@ -1175,7 +1246,7 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
         vi[0] = o.viol_t; vi[1] = o.viol_l; vi[2] = o.viol_lb;
     }
     if (flags & ZZ_F_OVERFLOW) {
-        atomicExch(&C->abortf[ws], 1u);
+        zz_flag_raise<MULTI>(&(MULTI ? P.ctl_peer[0] : C)->abortf[ws]);
         if (o.flags & ZZ_F_OVERFLOW) atomicAdd(&C->dbg[0], 1ULL);   // flips / pool / items of the timeline itself
     }
 }
@@ -1193,10 +1264,14 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int nwc = blockDim.x >> 5;
     const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
-    const int32_t lo = 0, hi = P.v.d;
+    const int32_t lo = MULTI ? P.v.lo : 0, hi = MULTI ? P.v.hi : P.v.d;   // owned coordinates
+    ZzDevCtl* const G0 = MULTI ? P.ctl_peer[0] : C;                       // home of `pending` / `abortf`
+    const bool gleader = leader && (!MULTI || P.v.rank == 0);
+    const long long ntokens = (long long)gridDim.x * (MULTI ? P.v.nranks : 1);
+    unsigned long long xep = MULTI ? __ldcg(&C->xrelease) : 0ULL;         // cross-GPU boundary counter (persists)
     ZzTile t;
     t.lo = lo;
-    t.per = (((hi - lo + (int32_t)gridDim.x - 1) / (int32_t)gridDim.x) + 31) & ~31;
+    t.per = P.tile_per;
     t.c_lo = lo + (int32_t)blockIdx.x * t.per; if (t.c_lo > hi) t.c_lo = hi;
     t.c_hi = (t.c_lo + t.per < hi) ? t.c_lo + t.per : hi;
     t.gq[0] = P.wl[0] + t.c_lo; t.gq[1] = P.wl[1] + t.c_lo; t.tlist = P.touched[0] + t.c_lo;
@@ -1225,17 +1300,22 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
         const int ws0 = (int)(wat % 3u);
         P.inbox_cnt[(size_t)ws0 * gridDim.x + blockIdx.x] = 0u;
         if (blockIdx.x == 0) {
-            C->pending[ws0] = (long long)gridDim.x; C->abortf[ws0] = 0u;
+            if (gleader) { G0->pending[ws0] = ntokens; G0->abortf[ws0] = 0u; }
             C->touched_cnt[ws0] = 0; C->smin_key[ws0] = ~0ULL; C->nprop_win[ws0] = 0;
         }
     }
-    zz_grid_barrier(C, epoch, prof);
+    zz_boundary<MULTI>(P, epoch, xep, prof, nullptr, nullptr, nullptr, 0u, 0u);
 
     while (ctl.phase < ZZ_PH_DONE && !stop) {
         if (cur > P.tag_limit) {  // list tags are about to run out of bits: forget all of them
-            for (int32_t j = t.c_lo + (int32_t)threadIdx.x; j < t.c_hi; j += blockDim.x)
-                reinterpret_cast<unsigned long long*>(P.v.kin + j)[3] = 0ULL;
-            zz_grid_barrier(C, epoch, prof);
+            if (MULTI) {   // own records and the replicas of the other ranks' records alike (nobody publishes before the boundary below)
+                for (int32_t j = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x); j < P.v.d; j += (int32_t)(gridDim.x * blockDim.x))
+                    reinterpret_cast<unsigned long long*>(P.v.kin + j)[3] = 0ULL;
+            } else {
+                for (int32_t j = t.c_lo + (int32_t)threadIdx.x; j < t.c_hi; j += blockDim.x)
+                    reinterpret_cast<unsigned long long*>(P.v.kin + j)[3] = 0ULL;
+            }
+            zz_boundary<MULTI>(P, epoch, xep, prof, nullptr, nullptr, nullptr, 0u, 0u);
             cur = 0; st_rebases++;
         }
         const ZzCtl saved = ctl;
@@ -1255,7 +1335,7 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
             const int wz = (int)(wat % 3u);   // slots of the NEXT attempt
             P.inbox_cnt[(size_t)wz * gridDim.x + blockIdx.x] = 0u;
             if (blockIdx.x == 0) {
-                C->pending[wz] = (long long)gridDim.x; C->abortf[wz] = 0u;
+                if (gleader) { G0->pending[wz] = ntokens; G0->abortf[wz] = 0u; }
                 C->touched_cnt[wz] = 0; C->smin_key[wz] = ~0ULL; C->nprop_win[wz] = 0;
             }
             S.n[0] = 0u; S.n[1] = 0u; S.tcount = 0u; S.head = 0u; S.dups = 0u; S.aborted = 0u; S.state = 0u;
@@ -1264,69 +1344,65 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
 #ifdef ZZ_PROF_SCAN
         const long long sc0 = clock64(); long long sc1 = sc0, sc2 = sc0;
 #endif
-        // Warp w takes the 32-coordinate words w, w + #warps, ... of the tile, ZZ_SCAN_B words per batch: all loads of a batch are
-        // in flight together, the ballot of a word IS its bit word, and the warp reserves its queue slots with ONE shared-memory
-        // atomic per batch (an atomic per word serialises 200 of them on one address: 17 us per window in the first version).
-        {
-            const unsigned int nwords = (unsigned int)(t.c_hi - t.c_lo + 31) >> 5;
-            for (unsigned int wb = (unsigned int)warp; wb < nwords; wb += nwc * ZZ_SCAN_B) {
-                double tj[ZZ_SCAN_B];
+        // Phase A: warp w takes the 32-coordinate words w, w + #warps, ... of the tile, ZZ_SCAN_B words per batch (all loads of a
+        // batch in flight together); the ballot of a word IS its bit word (queued = touched = proposal inside the window).
+        const unsigned int nwords = (unsigned int)(t.c_hi - t.c_lo + 31) >> 5;
+        for (unsigned int wb = (unsigned int)warp; wb < nwords; wb += nwc * ZZ_SCAN_B) {
+            double tj[ZZ_SCAN_B];
 #pragma unroll
-                for (int u = 0; u < ZZ_SCAN_B; ++u) {
-                    const unsigned int w = wb + (unsigned int)u * nwc;
-                    const int32_t j = t.c_lo + (int32_t)(w << 5) + lane;
-                    tj[u] = (w < nwords && j < t.c_hi) ? __ldcg(P.v.tau + j) : ZZ_INF;
-                }
-                unsigned int msk[ZZ_SCAN_B], red[ZZ_SCAN_B];
-                unsigned int total = 0, total_red = 0;
+            for (int u = 0; u < ZZ_SCAN_B; ++u) {
+                const unsigned int w = wb + (unsigned int)u * nwc;
+                const int32_t j = t.c_lo + (int32_t)(w << 5) + lane;
+                tj[u] = (w < nwords && j < t.c_hi) ? __ldcg(P.v.tau + j) : ZZ_INF;
+            }
 #pragma unroll
-                for (int u = 0; u < ZZ_SCAN_B; ++u) {
-                    const bool act = (tj[u] < H) || (incl && tj[u] == H);
-                    const int32_t j = t.c_lo + (int32_t)((wb + (unsigned int)u * nwc) << 5) + lane;
-                    msk[u] = __ballot_sync(0xffffffffu, act);
-                    red[u] = msk[u];
-                    if (KIND == ZZ_KIND_GRID) red[u] = __ballot_sync(0xffffffffu, act && zz_colour<KIND>(P, j, 0) == 0);
-                    total += (unsigned int)__popc(msk[u]);
-                    total_red += (unsigned int)__popc(red[u]);
-                    if (act) {   // the records the evaluation will gather: start them towards L2 now
-                        zz_prefetch_l2(P.v.kin + j); zz_prefetch_l2(P.v.priv + j); zz_prefetch_l2(P.v.kctr + j);
-                        if (KIND == ZZ_KIND_GRID) {
-                            if (j >= P.g.grid_m) zz_prefetch_l2(P.v.kin + j - P.g.grid_m);
-                            if (j + P.g.grid_m < P.v.d) zz_prefetch_l2(P.v.kin + j + P.g.grid_m);
-                        }
-                    }
-                }
+            for (int u = 0; u < ZZ_SCAN_B; ++u) {
+                const unsigned int w = wb + (unsigned int)u * nwc;
+                const unsigned int m = __ballot_sync(0xffffffffu, (tj[u] < H) || (incl && tj[u] == H));
+                if (lane == 0 && w < nwords) { t.dirty[w] = m; t.tbits[w] = m; }
+            }
+        }
+        __syncthreads();
 #ifdef ZZ_PROF_SCAN
-                sc1 = clock64();
+        sc1 = clock64();
 #endif
-                // one atomic per queue and batch: [0] queue 0 (lattice: even colour), [1] queue 1, [2] commit list
-                unsigned int base0 = 0, base1 = 0, baset = 0;
-                if (lane == 0 && total) {
-                    if (total_red) base0 = atomicAdd(&S.n[0], total_red);
-                    if (total - total_red) base1 = atomicAdd(&S.n[1], total - total_red);
-                    baset = atomicAdd(&S.tcount, total);
-                }
-                base0 = __shfl_sync(0xffffffffu, base0, 0);
-                base1 = __shfl_sync(0xffffffffu, base1, 0);
-                baset = __shfl_sync(0xffffffffu, baset, 0);
-#pragma unroll
-                for (int u = 0; u < ZZ_SCAN_B; ++u) {
-                    const unsigned int w = wb + (unsigned int)u * nwc;
-                    if (w < nwords) {
-                        if (lane == 0) { t.dirty[w] = msk[u]; t.tbits[w] = msk[u]; }
-                        const unsigned int below = (1u << lane) - 1u;
-                        if (msk[u] & (1u << lane)) {
-                            const int32_t j = t.c_lo + (int32_t)(w << 5) + lane;
-                            if (red[u] & (1u << lane)) zz_q_put(S, t, 0, base0 + __popc(red[u] & below), j);
-                            else zz_q_put(S, t, 1, base1 + __popc((msk[u] & ~red[u]) & below), j);
-                            t.tlist[baset + __popc(msk[u] & below)] = j;
-                        }
-                        base0 += (unsigned int)__popc(red[u]);
-                        base1 += (unsigned int)__popc(msk[u] & ~red[u]);
-                        baset += (unsigned int)__popc(msk[u]);
-                    }
+        // Phase B: compaction.  One THREAD per word walks its set bits (about six): count per queue (lattice: per colour), block-wide
+        // exclusive scan of the counts, write the entries.  No atomics, a few dozen instructions per word.
+        for (unsigned int w0c = 0; w0c < nwords; w0c += blockDim.x) {
+            const unsigned int w = w0c + threadIdx.x;
+            unsigned int m = (w < nwords) ? t.tbits[w] : 0u;
+            const int32_t j0 = t.c_lo + (int32_t)(w << 5);
+            unsigned int redm = m;   // bits that go to queue 0
+            if (KIND == ZZ_KIND_GRID) {
+                redm = 0u;
+                for (unsigned int mm = m; mm; mm &= mm - 1u) {
+                    const int b = __ffs((int)mm) - 1;
+                    if (zz_colour<KIND>(P, j0 + b, 0) == 0) redm |= 1u << b;
                 }
             }
+            const unsigned int nr = (unsigned int)__popc(redm), nb = (unsigned int)__popc(m & ~redm);
+            // exclusive scan of (nr | nb << 16) over the block (counts per chunk stay below 2^16: 32 per word, <= 1024 words)
+            unsigned int v = nr | (nb << 16), incl_v = v;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned int up = __shfl_up_sync(0xffffffffu, incl_v, off);
+                if (lane >= off) incl_v += up;
+            }
+            if (lane == 31) S.wsum[warp] = incl_v;
+            __syncthreads();
+            unsigned int pre = 0, tot = 0;
+            for (unsigned int q = 0; q < nwc; ++q) { const unsigned int x = S.wsum[q]; if (q < (unsigned int)warp) pre += x; tot += x; }
+            const unsigned int excl = pre + incl_v - v;
+            unsigned int pr = S.n[0] + (excl & 0xffffu), pb = S.n[1] + (excl >> 16), pt = S.tcount + (excl & 0xffffu) + (excl >> 16);
+            for (unsigned int mm = m; mm; mm &= mm - 1u) {
+                const int b = __ffs((int)mm) - 1;
+                const int32_t j = j0 + b;
+                if (redm & (1u << b)) zz_q_put(S, t, 0, pr++, j); else zz_q_put(S, t, 1, pb++, j);
+                t.tlist[pt++] = j;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) { S.n[0] += tot & 0xffffu; S.n[1] += tot >> 16; S.tcount += (tot & 0xffffu) + (tot >> 16); }
+            __syncthreads();
         }
 #ifdef ZZ_PROF_SCAN
         sc2 = clock64();
@@ -1337,7 +1413,7 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
 #endif
         if (threadIdx.x == 0) {
             const long long dlt = (long long)S.tcount - 1LL;   // queued evaluations; hand back this CTA's token
-            if (dlt) atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)dlt);
+            if (dlt) zz_pending_add<MULTI>(&G0->pending[ws], dlt);
         }
         ZZ_TOC(0);
         ZZ_DBGLOG(2, S.tcount);
@@ -1346,6 +1422,7 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
         // Invariant at the top: queue `cq` is complete (local marks of the previous round + drained inbox entries), every
         // thread of the CTA is past a block barrier.  Two block barriers per round.
         int cq = 0;
+        unsigned int outcome = ZZ_ST_ABORT;
         for (;;) {
             const unsigned int n = S.n[cq];
             if (n == 0 && S.n[cq ^ 1] != 0u) { cq ^= 1; continue; }   // (uniform: read after a block barrier)
@@ -1355,12 +1432,12 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
                     unsigned int st = 0;
                     const unsigned int* myc = P.inbox_cnt + (size_t)ws * gridDim.x + blockIdx.x;
                     for (;;) {
-                        unsigned int tail = zz_ld_acq32(myc);
+                        unsigned int tail = zz_flag_ld<MULTI>(myc);
                         if (tail > P.inbox_cap) tail = P.inbox_cap;
                         if (tail > S.head) { st = ZZ_ST_WORK; break; }
                         // order matters: an evaluation that overflowed raised the flag BEFORE it was subtracted from `pending`
-                        const long long pend = (long long)zz_ld_acq(reinterpret_cast<const unsigned long long*>(&C->pending[ws]));
-                        const unsigned int ab = zz_ld_acq32(&C->abortf[ws]);
+                        const long long pend = zz_pending_ld<MULTI>(&G0->pending[ws]);
+                        const unsigned int ab = zz_flag_ld<MULTI>(&G0->abortf[ws]);
                         if (ab) { st = ZZ_ST_ABORT; break; }
                         if (pend == 0) { st = ZZ_ST_DONE; break; }
                     }
@@ -1369,11 +1446,11 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
                     ZZ_DBGLOG(4, st);
                 }
                 __syncthreads();
-                if (S.state != ZZ_ST_WORK) break;
+                if (S.state != ZZ_ST_WORK) { outcome = S.state; break; }
                 if (warp == 0) {
-                    zz_drain_inbox<KIND>(P, S, t, cq, ws, watn);
+                    zz_drain_inbox<KIND, MULTI>(P, S, t, cq, ws, watn);
                     if (lane == 0 && S.dups) {
-                        atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)(-(long long)S.dups));
+                        zz_pending_add<MULTI>(&G0->pending[ws], -(long long)S.dups);
                         S.dups = 0u;
                     }
                 }
@@ -1395,10 +1472,12 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
             unsigned int tail_pre = 0, abort_pre = 0;
             if (threadIdx.x == 0) {
                 tail_pre = *(volatile const unsigned int*)(P.inbox_cnt + (size_t)ws * gridDim.x + blockIdx.x);
-                abort_pre = *(volatile const unsigned int*)&C->abortf[ws];
+                abort_pre = *(volatile const unsigned int*)&G0->abortf[ws];
             }
             // entry e goes to warp e % (#warps), lane e / (#warps): a short queue occupies a few lanes of every warp
-            for (unsigned int e = (unsigned int)lane * nwc + (unsigned int)warp; e < n; e += blockDim.x) {
+            const unsigned int estride = P.eval_threads ? P.eval_threads : blockDim.x;
+            for (unsigned int e = (unsigned int)lane * nwc + (unsigned int)warp; e < n; e += estride) {
+                if ((unsigned int)lane * nwc + (unsigned int)warp >= estride) break;
                 const int32_t j = zz_q_get(S, t, cq, e);
                 const unsigned int li = (unsigned int)(j - t.c_lo);
                 atomicAnd(&t.dirty[li >> 5], ~(1u << (li & 31u)));
@@ -1409,7 +1488,7 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
 #endif
                 if constexpr (MODE == ZZ_MODE_LOGIT) zz_process_node_logit(P.g, P.v, P.lg, j, H, incl, w0, 0xffffffffu, false, o);
                 else if constexpr (MODE == ZZ_MODE_STRONG) zz_process_node_strong(P.g, P.v, P.st, j, H, incl, w0, 0xffffffffu, false, o);
-                else zz_process_node_k<KIND, MODE, MULTI>(P.g, P.v, j, H, incl, w0, 0xffffffffu, false, o);
+                else zz_process_node_k<KIND, MODE, false>(P.g, P.v, j, H, incl, w0, 0xffffffffu, false, o);   // (sharded: local replicas)
 #ifdef ZZ_PROF_TAIL2
                 const long long c1 = clock64();
 #endif
@@ -1429,10 +1508,10 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
                 if (lane == 0) S.n[cq] = 0u;                          // (before the drain: on the lattice it may refill this queue)
                 __syncwarp();
                 tail_pre = __shfl_sync(0xffffffffu, tail_pre, 0);
-                if (tail_pre > S.head) zz_drain_inbox<KIND>(P, S, t, nq, ws, watn);
+                if (tail_pre > S.head) zz_drain_inbox<KIND, MULTI>(P, S, t, nq, ws, watn);
                 if (lane == 0) {
                     const long long dlt = (long long)produced - (long long)n - (long long)S.dups;
-                    if (dlt) atomicAdd(reinterpret_cast<unsigned long long*>(&C->pending[ws]), (unsigned long long)dlt);
+                    if (dlt) zz_pending_add<MULTI>(&G0->pending[ws], dlt);
                     S.dups = 0u;
                     if (abort_pre) S.aborted = 1u;
                 }
@@ -1450,40 +1529,44 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
             if (S.aborted) break;
         }
 
-        // ---------------- agree on the outcome: overflow anywhere?  size of the commit list, earliest flip (phase B)
+        // ---------------- the outcome is known to every CTA without a barrier: the window converged (`pending` reached zero:
+        // no evaluation queued or in flight anywhere, so every list and every speculative end state is final) or it was aborted
+        // (the flag is raised before the overflowing evaluation is subtracted from `pending`, and never lowered).  A grid-wide
+        // (sharded: node-wide) barrier is needed only to agree on the earliest flip of a phase-B trial window, or on the room
+        // left in the trace buffer.
+        const bool overflow = (outcome != ZZ_ST_DONE);
         const unsigned int tcount = S.tcount;
-        if (threadIdx.x == 0 && tcount) atomicAdd(&C->touched_cnt[ws], tcount);
-        if (ctl.phase == ZZ_PH_B) {
-            ZZ_TIC();
-            unsigned long long kmin = ~0ULL;
-            for (unsigned int e = threadIdx.x; e < tcount; e += blockDim.x) {
-                const int32_t j = __ldcg(t.tlist + e);
-                const ZzSpecR s = zz_load_spec(P.spec + j);
-                if (s.nflip) {
-                    double th, tf, xf; uint32_t h0, h1;
-                    zz_ld_kin(P.v.kin + j, th, tf, xf, h0, h1);
-                    int slot;
-                    zz_pick_slot(h0, h1, w0, 0xffffffffu, slot);
-                    const unsigned long long k = zz_key(__ldcg(P.v.flips + ((size_t)j * 2 + slot) * ZZ_MAXFLIP));
-                    kmin = k < kmin ? k : kmin;
-                }
-            }
-            if (kmin != ~0ULL) atomicMin(&C->smin_key[ws], kmin);
-            ZZ_TOC(5);
-        }
-        ZZ_DBGLOG(5, tcount);
-        zz_grid_barrier(C, epoch, prof);
-        ZZ_DBGLOG(6, 0);
-        const bool overflow = __ldcg(&C->abortf[ws]) != 0u;
+        const bool need_b1 = (ctl.phase == ZZ_PH_B) || (!MULTI && P.record_trace);
         double smin = ZZ_INF;
-        if (!overflow && ctl.phase == ZZ_PH_B) {
-            const unsigned long long mk = __ldcg(&C->smin_key[ws]);
-            if (mk != ~0ULL) smin = zz_unkey(mk);
+        if (need_b1) {
+            if (threadIdx.x == 0 && tcount) atomicAdd(&C->touched_cnt[ws], tcount);
+            if (!overflow && ctl.phase == ZZ_PH_B) {
+                ZZ_TIC();
+                unsigned long long kmin = ~0ULL;
+                for (unsigned int e = threadIdx.x; e < tcount; e += blockDim.x) {
+                    const int32_t j = __ldcg(t.tlist + e);
+                    const ZzSpecR s = zz_load_spec(P.spec + j);
+                    if (s.nflip) {
+                        double th, tf, xf; uint32_t h0, h1;
+                        zz_ld_kin(P.v.kin + j, th, tf, xf, h0, h1);
+                        int slot;
+                        zz_pick_slot(h0, h1, w0, 0xffffffffu, slot);
+                        const unsigned long long k = zz_key(__ldcg(P.v.flips + ((size_t)j * 2 + slot) * ZZ_MAXFLIP));
+                        kmin = k < kmin ? k : kmin;
+                    }
+                }
+                if (kmin != ~0ULL) atomicMin(&C->smin_key[ws], kmin);
+                ZZ_TOC(5);
+            }
+            ZZ_DBGLOG(5, tcount);
+            const ZzXres xb = zz_boundary<MULTI>(P, epoch, xep, prof, nullptr, &C->smin_key[ws], nullptr, 0u, 0u);
+            ZZ_DBGLOG(6, 0);
+            if (!overflow && ctl.phase == ZZ_PH_B && xb.minkey != ~0ULL) smin = zz_unkey(xb.minkey);
         }
 
         ZzCtl trial = ctl;
         const int act = zz_ctl_end(trial, overflow, smin, nprop_prev);
-        if (act == ZZ_ACT_COMMIT && P.record_trace) {
+        if (!MULTI && act == ZZ_ACT_COMMIT && P.record_trace) {
             // every event of this window must fit; otherwise hand the buffer to the host first
             const unsigned long long tl = __ldcg(&C->trace_len);
             const unsigned long long need = (unsigned long long)__ldcg(&C->touched_cnt[ws]) * ZZ_MAXFLIP + 1ULL;
@@ -1500,7 +1583,7 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
             for (unsigned int e = threadIdx.x; e < tcount; e += blockDim.x) {
                 const int32_t j = __ldcg(t.tlist + e);
                 const ZzSpecR sp = zz_load_spec(P.spec + j);
-                zz_commit_node<MODE>(P, j, sp, w0, 0xffffffffu, np, nf);
+                zz_commit_node<MODE, KIND, MULTI>(P, j, sp, w0, 0xffffffffu, np, nf);
             }
             cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
             np = cg::reduce(w, np, cg::plus<unsigned int>());
@@ -1512,7 +1595,9 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
             }
             ZZ_TOC(3);
             ZZ_DBGLOG(7, np);
-            zz_grid_barrier(C, epoch, prof);
+            // the committed frontier is published; proposals / flips of the window (length controller) and the stop word
+            // (bound violation on ANY GPU stops all of them) are reduced on the way
+            const ZzXres xc = zz_boundary<MULTI>(P, epoch, xep, prof, &C->nprop_win[ws], nullptr, &C->viol, 0xffffffffu, ZZ_X_STOP);
             ZZ_DBGLOG(8, 0);
             if (leader && P.record_trace) {  // window-end marker (i = 0): lets the host sort window by window
                 const unsigned long long pos = atomicAdd(&C->trace_len, 1ULL);
@@ -1524,9 +1609,9 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
                     C->trace_full = 1u;
                 }
             }
-            nprop_prev = __ldcg(&C->nprop_win[ws]);
+            nprop_prev = xc.sum;
             windows_done++;
-            if (__ldcg(&C->viol)) stop = true;
+            if (xc.flags & ZZ_X_STOP) stop = true;
             if (P.max_windows && windows_done >= P.max_windows) stop = true;
         } else {
             st_retries++;
@@ -1551,19 +1636,19 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
 template <int KIND, bool MULTI, int MODE, bool ASYNC>
 __device__ __forceinline__ void zz_run_dispatch(const ZzParams& P)
 {
-    if constexpr (ASYNC && !MULTI) zz_run_body_async<KIND, MULTI, MODE>(P);
+    if constexpr (ASYNC) zz_run_body_async<KIND, MULTI, MODE>(P);
     else zz_run_body<KIND, MULTI, MODE>(P);
 }
 #define ZZ_RUN_KERNEL(name, KIND, MULTI, MODE, ASYNC) \
     extern "C" __global__ void __launch_bounds__((KIND == ZZ_KIND_GRID ? ZZ_RUN_BLOCK_GRID : ZZ_RUN_BLOCK_CSR), ZZ_MINB) name(const __grid_constant__ ZzParams P) { zz_run_dispatch<KIND, MULTI, MODE, ASYNC>(P); }
 ZZ_RUN_KERNEL(zz_run_kernel_grid, ZZ_KIND_GRID, false, ZZ_MODE_PLAIN, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_csr, ZZ_KIND_CSR, false, ZZ_MODE_PLAIN, ZZ_ASYNC)
-ZZ_RUN_KERNEL(zz_run_kernel_grid_multi, ZZ_KIND_GRID, true, ZZ_MODE_PLAIN, 0)
-ZZ_RUN_KERNEL(zz_run_kernel_csr_multi, ZZ_KIND_CSR, true, ZZ_MODE_PLAIN, 0)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_multi, ZZ_KIND_GRID, true, ZZ_MODE_PLAIN, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_multi, ZZ_KIND_CSR, true, ZZ_MODE_PLAIN, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_grid_lb, ZZ_KIND_GRID, false, ZZ_MODE_LB, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_lb, ZZ_KIND_CSR, false, ZZ_MODE_LB, ZZ_ASYNC)
-ZZ_RUN_KERNEL(zz_run_kernel_grid_multi_lb, ZZ_KIND_GRID, true, ZZ_MODE_LB, 0)
-ZZ_RUN_KERNEL(zz_run_kernel_csr_multi_lb, ZZ_KIND_CSR, true, ZZ_MODE_LB, 0)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_multi_lb, ZZ_KIND_GRID, true, ZZ_MODE_LB, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_multi_lb, ZZ_KIND_CSR, true, ZZ_MODE_LB, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_grid_sticky, ZZ_KIND_GRID, false, ZZ_MODE_STICKY, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_sticky, ZZ_KIND_CSR, false, ZZ_MODE_STICKY, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_grid_boom, ZZ_KIND_GRID, false, ZZ_MODE_BOOM, ZZ_ASYNC)

@@ -87,7 +87,7 @@ static int32_t cu_fail(CUresult r, const char* what)
 #define ZZ_NKERN 16   // event-loop kernels in the image (see zzb_init)
 #define ZZ_KERN_BLOCK_IDX(k) ((k) == 12 || (k) == 13 ? 1 : ((k) & 1))
 #define ZZ_RUN_BLOCK_OF(r) ZZ_KERN_BLOCK_IDX((r)->kidx())      // the logistic / strong kernels are general-sparse kernels on any graph
-#define ZZ_KERN_ASYNC(k) (!((k) == 2 || (k) == 3 || (k) == 6 || (k) == 7 || (k) >= 14))   // asynchronous tile-local relaxation (zz_run_body_async)
+#define ZZ_KERN_ASYNC(k) ((k) < 14)   // asynchronous tile-local relaxation (zz_run_body_async)
 struct Global {
     bool ready = false;
     CUdevice dev = 0; int dev_id = 0;
@@ -181,6 +181,7 @@ struct zzb_run_s {
     int schedule = 1;                  // 1: asynchronous tile-local relaxation; 0: pass-synchronous schedule of round 1 (plain ZigZag only)
     DevBuf inbox, inbox_cnt; unsigned int inbox_cap = 0, flag_words = 0; int inbox_grid = 0;
     DevBuf dbgbuf; std::vector<unsigned long long> dbghost;
+    int tile_per = 0; unsigned int eval_threads = 0;
     unsigned int wat_next = 0;         // window-attempt numbers tag the inbox entries: never reused by a later run of this handle
     int kidx() const
     {
@@ -466,6 +467,27 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     return ZZB_OK;
 }
 
+// Tiles of the asynchronous relaxation: `per` coordinates per CTA (a multiple of 32; sharded runs: derived from the nominal
+// shard size so that every rank computes the same value), two bit arrays per tile in dynamic shared memory, one inbox per CTA
+// for marks that cross a tile boundary.
+static int32_t setup_tiles(zzb_run_s* r)
+{
+    const long long span = r->nranks > 1 ? r->shard : r->d;
+    const long long per = (((span + r->grid - 1) / r->grid) + 31) & ~31LL;
+    r->tile_per = (int)per;
+    r->flag_words = (unsigned int)(per / 32);
+    const unsigned int cap = (unsigned int)std::max<long long>(1024, 2 * per);
+    if (r->inbox_grid != r->grid || r->inbox_cap != cap) {
+        int32_t st = r->inbox.alloc((size_t)r->grid * cap * 8);
+        if (!st) st = r->inbox_cnt.alloc((size_t)3 * r->grid * 4);
+        if (st) return st == ZZB_E_CUDA ? ZZB_E_NOMEM : st;
+        CU(cuMemsetD8(r->inbox.p, 0xff, (size_t)r->grid * cap * 8));   // attempt tag 0xffffffff: "not written"
+        CU(cuMemsetD8(r->inbox_cnt.p, 0, (size_t)3 * r->grid * 4));
+        r->inbox_grid = r->grid; r->inbox_cap = cap;
+    }
+    return ZZB_OK;
+}
+
 static void fill_params(zzb_run_s* r)
 {
     ZzParams& P = r->P;
@@ -482,7 +504,7 @@ static void fill_params(zzb_run_s* r)
     P.trace = r->trace.as<ZzEvent>(); P.trace_cap = r->trace_cap;
     P.ctl = r->ctl.as<ZzDevCtl>();
     P.inbox = r->inbox.as<unsigned long long>(); P.inbox_cnt = r->inbox_cnt.as<unsigned int>();
-    P.inbox_cap = r->inbox_cap; P.flag_words = r->flag_words;
+    P.inbox_cap = r->inbox_cap; P.flag_words = r->flag_words; P.tile_per = r->tile_per;
     P.record_trace = (r->flags & ZZB_FLAG_NO_TRACE) ? 0 : 1;
     P.grid = r->grid_n ? r->gridbuf.as<double>() : nullptr; P.grid_dt = r->grid_dt; P.grid_n = r->grid_n;
     P.v.local_bound = (r->flags & ZZB_FLAG_LOCAL_BOUND) ? 1 : 0;
@@ -501,8 +523,10 @@ static void fill_params(zzb_run_s* r)
             const bool me = (q == r->rank);
             P.v.kin_peer[q] = me ? P.v.kin : reinterpret_cast<ZzKin*>(r->peer[q][0]);
             P.v.flips_peer[q] = me ? P.v.flips : reinterpret_cast<double*>(r->peer[q][1]);
+            P.inbox_peer[q] = me ? P.inbox : reinterpret_cast<unsigned long long*>(r->peer[q][3]);
+            P.inbox_cnt_peer[q] = me ? P.inbox_cnt : reinterpret_cast<unsigned int*>(r->peer[q][4]);
             P.dstamp_peer[q] = me ? P.dstamp : reinterpret_cast<unsigned int*>(r->peer[q][2]);
-            for (int k = 0; k < 3; ++k) P.wl_peer[k][q] = me ? P.wl[k] : reinterpret_cast<int32_t*>(r->peer[q][3 + k]);
+            for (int k = 0; k < 3; ++k) P.wl_peer[k][q] = P.wl[k];   // (work lists are private to their rank in the asynchronous schedule)
             P.touched_peer[q] = me ? P.touched[0] : reinterpret_cast<int32_t*>(r->peer[q][6]);
             P.ctl_peer[q] = me ? P.ctl : reinterpret_cast<ZzDevCtl*>(r->peer[q][7]);
         }
@@ -513,7 +537,7 @@ static CUdeviceptr shared_buf(zzb_run_s* r, int k)
 {
     switch (k) {
     case 0: return r->kin.p; case 1: return r->flips.p; case 2: return r->dstamp.p;
-    case 3: return r->wl[0].p; case 4: return r->wl[1].p; case 5: return r->wl[2].p;
+    case 3: return r->inbox.p; case 4: return r->inbox_cnt.p; case 5: return r->wl[2].p;
     case 6: return r->touched.p; default: return r->ctl.p;
     }
 }
@@ -535,10 +559,11 @@ int32_t zzb_run_shard(zzb_run_t r, int32_t rank, int32_t nranks)
     r->lo = (int)std::min<int64_t>(d, shard * rank);
     r->hi = (int)std::min<int64_t>(d, shard * (rank + 1));
     r->grid = G.sm_count * G.blocks_per_sm[r->kidx()];
-    return ZZB_OK;
+    CtxGuard cg;
+    return setup_tiles(r);   // (the inboxes are exported to the peers: allocate them now)
 }
 
-// 8 IPC handles (kin, flips, dstamp, three work lists, touched list, control block) of this rank's allocations.
+// 8 IPC handles (kin, flips, dstamp, inbox, inbox counters, [unused work list], touched list, control block) of this rank.
 int32_t zzb_run_ipc_export(zzb_run_t r, void* buf, int64_t cap, int64_t* len)
 {
     if (!r || !buf || !len) return fail(ZZB_E_ARG, "null argument");
@@ -580,6 +605,7 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     else if (!strcmp(key, "target_flip_frac")) r->target_flip_frac = value;
     else if (!strcmp(key, "tag_limit")) r->tag_limit = (unsigned int)value;
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
+    else if (!strcmp(key, "eval_threads")) r->eval_threads = (unsigned int)value;
     else if (!strcmp(key, "schedule")) { r->schedule = value != 0.0; r->grid = G.sm_count * G.blocks_per_sm[r->kidx()]; }
     // switch a sticky run to the strong-bound sampler of src/sparsestickyzz.jl: scalar bound constant c, rule (0 sticky, 1 reversible);
     // kappa[0] of zzb_run_upload_kappa is the thaw rate; coordinates with x0 == 0 start frozen.  Before zzb_run_upload.
@@ -721,24 +747,19 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
     if (!(r->t0 < T)) { r->executed = true; return ZZB_OK; }  // `while t' < T` never entered (sfact.jl:199)
     unsigned dyn_smem = 0;
     if (ZZ_KERN_ASYNC(r->kidx())) {
-        // tiles of the asynchronous relaxation: `per` coordinates per CTA (a multiple of 32, as zz_run_body_async computes it),
-        // two bit arrays per tile in dynamic shared memory, one inbox per CTA for marks that cross a tile boundary
-        const long long per = ((((long long)r->d + r->grid - 1) / r->grid) + 31) & ~31LL;
-        P.flag_words = r->flag_words = (unsigned int)(per / 32);
+        if (r->nranks <= 1) { int32_t st = setup_tiles(r); if (st) return st; }   // (sharded: done by zzb_run_shard, before the IPC export)
+        if (!r->tile_per) return fail(ZZB_E_ARG, "zzb_run_shard must precede zzb_run_execute for a sharded run");
         dyn_smem = 2u * 4u * r->flag_words;
         if (dyn_smem > 200u * 1024u) return fail(ZZB_E_ARG, "d = %d is too large for %d tiles (bit arrays of %u bytes per CTA)", r->d, r->grid, dyn_smem);
         if (dyn_smem > 32u * 1024u)
             CU(cuFuncSetAttribute(G.f_run[r->kidx()], CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn_smem));
-        const unsigned int cap = (unsigned int)std::max<long long>(1024, 2 * per);
-        if (r->inbox_grid != r->grid || r->inbox_cap != cap) {
-            int32_t st = r->inbox.alloc((size_t)r->grid * cap * 8);
-            if (!st) st = r->inbox_cnt.alloc((size_t)3 * r->grid * 4);
-            if (st) return st == ZZB_E_CUDA ? ZZB_E_NOMEM : st;
-            CU(cuMemsetD8Async(r->inbox.p, 0xff, (size_t)r->grid * cap * 8, G.stream));   // attempt tag 0xffffffff: "not written"
-            CU(cuMemsetD8Async(r->inbox_cnt.p, 0, (size_t)3 * r->grid * 4, G.stream));
-            r->inbox_grid = r->grid; r->inbox_cap = cap;
-        }
         P.inbox = r->inbox.as<unsigned long long>(); P.inbox_cnt = r->inbox_cnt.as<unsigned int>(); P.inbox_cap = r->inbox_cap;
+        P.flag_words = r->flag_words; P.tile_per = r->tile_per; P.eval_threads = r->eval_threads;
+        for (int q = 0; q < r->nranks && r->nranks > 1; ++q) {
+            const bool me = (q == r->rank);
+            P.inbox_peer[q] = me ? P.inbox : reinterpret_cast<unsigned long long*>(r->peer[q][3]);
+            P.inbox_cnt_peer[q] = me ? P.inbox_cnt : reinterpret_cast<unsigned int*>(r->peer[q][4]);
+        }
         if (const char* dw = getenv("ZZB200_DBG_WINDOW")) {   // development: log the rounds of one window per CTA (tools/window_trace.py)
             const size_t nb = (size_t)r->grid * ZZ_DBG_REC * 4 * 8 + 4096 * 16 * 8;
             int32_t st = r->dbgbuf.alloc(nb);
