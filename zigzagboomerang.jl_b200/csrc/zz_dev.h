@@ -61,10 +61,14 @@ struct ZzDevCtl {
     ZzMsg tail_xres;
     ZzMsg mbox[2][ZZ_MAXRANKS];      // incoming messages, by boundary parity and sender
     // asynchronous tile-local relaxation (zz_run_body_async), per window attempt (attempt number mod 3):
-    long long pending[3];            // timeline evaluations queued or in flight on the whole GPU (+1 token per CTA that has not
-                                     // finished its scan yet); 0 = the window has converged
+    // Quiescence detection with two MONOTONE counters per GPU: created = evaluations queued for tiles of this GPU (by anybody;
+    // + one token per CTA until its scan is done), done = evaluations finished (or dropped as duplicates) by this GPU.  The window
+    // has converged when the sums over all GPUs agree -- read `done` first, `created` second: created >= done at all times, so
+    // equal sums prove that nothing was queued or in flight anywhere at an instant in between.
+    unsigned long long created[3], done[3];
     unsigned int abortf[3];          // some evaluation overflowed (flips / pool / items / tags / inbox): retry the window shorter
-    unsigned int pad_async;
+                                     // (sharded: raised in EVERY rank's copy, read locally)
+    unsigned int doneflag[3];        // sharded: CTA 0 of this GPU saw the node-wide sums agree
 };
 
 struct ZzParams {

@@ -963,7 +963,7 @@ struct ZzAsyncSh {
     int32_t sq[2][ZZ_SQCAP];
     unsigned int n[2];        // entries of the two queues
     unsigned int tcount;      // coordinates of this tile evaluated at least once in the window (commit list)
-    unsigned int head;        // inbox entries consumed
+    unsigned int head[ZZ_MAXRANKS];   // inbox entries consumed, per sending rank
     unsigned int dups;        // inbox entries dropped because the coordinate was queued already
     unsigned int state;       // decision of the polling thread
     unsigned int aborted;
@@ -986,23 +986,11 @@ __device__ __forceinline__ unsigned int zz_ld_acq32_sys(const unsigned int* p)
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// `pending` / `abortf` of a sharded run live in rank 0's control block: system scope over NVLink
-template <bool MULTI> __device__ __forceinline__ void zz_pending_add(long long* p, long long v)
+// the abort flag of a sharded run is raised in every rank's copy (rare), so that everybody polls local memory only
+template <bool MULTI> __device__ __forceinline__ void zz_abort_raise(const ZzParams& P, int ws)
 {
-    if (MULTI) atomicAdd_system(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
-    else atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
-}
-template <bool MULTI> __device__ __forceinline__ long long zz_pending_ld(const long long* p)
-{
-    return (long long)(MULTI ? zz_ld_acq_sys(reinterpret_cast<const unsigned long long*>(p)) : zz_ld_acq(reinterpret_cast<const unsigned long long*>(p)));
-}
-template <bool MULTI> __device__ __forceinline__ unsigned int zz_flag_ld(const unsigned int* p)
-{
-    return MULTI ? zz_ld_acq32_sys(p) : zz_ld_acq32(p);
-}
-template <bool MULTI> __device__ __forceinline__ void zz_flag_raise(unsigned int* p)
-{
-    if (MULTI) atomicExch_system(p, 1u); else atomicExch(p, 1u);
+    if (MULTI) { for (int r = 0; r < P.v.nranks; ++r) atomicExch_system(&P.ctl_peer[r]->abortf[ws], 1u); }
+    else atomicExch(&P.ctl->abortf[ws], 1u);
 }
 
 struct ZzTile {
@@ -1035,48 +1023,52 @@ __device__ __forceinline__ bool zz_mark_local(ZzAsyncSh& S, const ZzTile& t, int
     return true;
 }
 
-// Marks of one changed coordinate: readers inside the tile go to the CTA's other queue; readers of other tiles (possibly on
-// another GPU) are counted into `pending` first, then -- after a fence that orders both the counter and the list written by the
-// caller before the entry -- pushed into their owners' inboxes.
+// Marks of one changed coordinate, in two steps around ONE fence (zz_publish_async): count the readers that live in other
+// tiles (possibly on another GPU) -- they are added to `pending` before the fence, because the receiver may finish the
+// evaluation and subtract it as soon as it sees the entry -- then queue the readers: those of this tile into the CTA's other
+// queue, the others into their owners' inboxes.  An inbox is split by SENDING rank and the slot counter of a sender lives in the
+// sender's own memory, so a push is one local atomic plus one store (over NVLink when the owner is another GPU): nothing on
+// this path waits for a round trip to a peer.
 template <int NK, bool MULTI>
-__device__ __forceinline__ void zz_mark_async(const ZzParams& P, ZzAsyncSh& S, const ZzTile& t, const int32_t (&kk)[NK],
-                                              int nxt, int ws, uint32_t wat)
+__device__ __forceinline__ void zz_mark_count(const ZzParams& P, const ZzTile& t, const int32_t (&kk)[NK], int ws, unsigned int& nrem, bool& offgpu)
+{
+#pragma unroll
+    for (int q = 0; q < NK; ++q) {
+        if (kk[q] < 0 || (unsigned int)(kk[q] - t.c_lo) < (unsigned int)(t.c_hi - t.c_lo)) continue;
+        if (MULTI && (kk[q] < P.v.lo || kk[q] >= P.v.hi)) {   // queued for a tile of another GPU: counted there
+            atomicAdd_system(&P.ctl_peer[kk[q] / P.v.shard]->created[ws], 1ULL);
+            offgpu = true;
+        } else {
+            nrem++;
+        }
+    }
+}
+
+template <int NK, bool MULTI>
+__device__ __forceinline__ void zz_mark_push(const ZzParams& P, ZzAsyncSh& S, const ZzTile& t, const int32_t (&kk)[NK],
+                                             int nxt, int ws, uint32_t wat)
 {
     ZzDevCtl* C = P.ctl;
-    ZzDevCtl* G0 = MULTI ? P.ctl_peer[0] : C;
-    unsigned int nrem = 0; bool offgpu = false;
+    const int nr = MULTI ? P.v.nranks : 1, me = MULTI ? P.v.rank : 0;
 #pragma unroll
     for (int q = 0; q < NK; ++q) {
         if (kk[q] < 0) continue;
-        if ((unsigned int)(kk[q] - t.c_lo) < (unsigned int)(t.c_hi - t.c_lo)) zz_mark_local(S, t, kk[q], nxt);
-        else { nrem++; if (MULTI && (kk[q] < P.v.lo || kk[q] >= P.v.hi)) offgpu = true; }
-    }
-    if (nrem) {
-        // (`pending` first: the receiver may finish the evaluation and subtract it as soon as it sees the entry)
-        zz_pending_add<MULTI>(&G0->pending[ws], (long long)nrem);
-        if (MULTI && offgpu) __threadfence_system(); else __threadfence();
-#pragma unroll
-        for (int q = 0; q < NK; ++q) {
-            if (kk[q] < 0 || (unsigned int)(kk[q] - t.c_lo) < (unsigned int)(t.c_hi - t.c_lo)) continue;
-            unsigned int* cnt; unsigned long long* box; unsigned int owner;
-            if (MULTI) {
-                const int r = kk[q] / P.v.shard;
-                owner = (unsigned int)(kk[q] - r * P.v.shard) / (unsigned int)t.per;
-                cnt = P.inbox_cnt_peer[r]; box = P.inbox_peer[r];
-            } else {
-                owner = (unsigned int)(kk[q] - t.lo) / (unsigned int)t.per;
-                cnt = P.inbox_cnt; box = P.inbox;
-            }
-            const unsigned int pos = MULTI ? atomicAdd_system(cnt + (size_t)ws * gridDim.x + owner, 1u)
-                                           : atomicAdd(cnt + (size_t)ws * gridDim.x + owner, 1u);
-            if (pos < P.inbox_cap)
-                *(volatile unsigned long long*)(box + (size_t)owner * P.inbox_cap + pos) = ((unsigned long long)wat << 32) | (unsigned int)kk[q];
-            else {
-                zz_flag_raise<MULTI>(&G0->abortf[ws]);
-                atomicAdd(&C->dbg[2], 1ULL);   // inbox full
-            }
+        if ((unsigned int)(kk[q] - t.c_lo) < (unsigned int)(t.c_hi - t.c_lo)) { zz_mark_local(S, t, kk[q], nxt); continue; }
+        int r = 0; unsigned int owner; unsigned long long* box = P.inbox;
+        if (MULTI) {
+            r = kk[q] / P.v.shard;
+            owner = (unsigned int)(kk[q] - r * P.v.shard) / (unsigned int)t.per;
+            box = P.inbox_peer[r];
+        } else {
+            owner = (unsigned int)(kk[q] - t.lo) / (unsigned int)t.per;
         }
-        atomicAdd(&C->dbg[3], (unsigned long long)nrem);
+        const unsigned int pos = atomicAdd(P.inbox_cnt + ((size_t)ws * nr + r) * gridDim.x + owner, 1u);
+        if (pos < P.inbox_cap)
+            *(volatile unsigned long long*)(box + ((size_t)owner * nr + me) * P.inbox_cap + pos) = ((unsigned long long)wat << 32) | (unsigned int)kk[q];
+        else {
+            zz_abort_raise<MULTI>(P, ws);
+            atomicAdd(&C->dbg[2], 1ULL);   // inbox full
+        }
     }
 }
 
@@ -1092,34 +1084,49 @@ __device__ __forceinline__ int zz_colour(const ZzParams& P, int32_t k, int other
     return (int)((unsigned int)(k - col * P.g.grid_m + col) & 1u);
 }
 
-// Warp 0 moves the valid prefix of this CTA's inbox into the queues (lattice: by colour; otherwise into queue `buf`).
+// Warp 0 moves the valid prefixes of this CTA's inbox (one sub-box per sending rank) into the queues (lattice: by colour;
+// otherwise into queue `buf`).  An entry is valid when it carries the number of the current window attempt.
 template <int KIND, bool MULTI>
 __device__ __forceinline__ void zz_drain_inbox(const ZzParams& P, ZzAsyncSh& S, const ZzTile& t, int buf, int ws, uint32_t wat)
 {
     const unsigned int lane = threadIdx.x & 31u;
-    unsigned int head = S.head;
-    const unsigned long long* box = P.inbox + (size_t)blockIdx.x * P.inbox_cap;
-    for (;;) {
-        unsigned int tail = 0;
-        if (lane == 0) tail = zz_flag_ld<MULTI>(P.inbox_cnt + (size_t)ws * gridDim.x + blockIdx.x);
-        tail = __shfl_sync(0xffffffffu, tail, 0);
-        if (tail > P.inbox_cap) tail = P.inbox_cap;
-        if (head >= tail) break;
-        const unsigned int e = head + lane;
-        bool ok = false; int32_t k = -1;
-        if (e < tail) {
-            const unsigned long long v = MULTI ? zz_ld_acq_sys(box + e) : zz_ld_acq(box + e);
-            ok = ((uint32_t)(v >> 32) == wat);
-            k = (int32_t)(uint32_t)v;
+    const int nr = MULTI ? P.v.nranks : 1;
+    for (int sr = 0; sr < nr; ++sr) {
+        unsigned int head = S.head[sr];
+        const unsigned long long* box = P.inbox + ((size_t)blockIdx.x * nr + sr) * P.inbox_cap;
+        for (;;) {
+            const unsigned int e = head + lane;
+            bool ok = false; int32_t k = -1;
+            if (e < P.inbox_cap) {
+                const unsigned long long v = MULTI ? zz_ld_acq_sys(box + e) : zz_ld_acq(box + e);
+                ok = ((uint32_t)(v >> 32) == wat);
+                k = (int32_t)(uint32_t)v;
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, ok);
+            const unsigned int nvalid = (m == 0xffffffffu) ? 32u : (unsigned int)(__ffs((int)~m) - 1);
+            if (lane < nvalid && !zz_mark_local(S, t, k, zz_colour<KIND>(P, k, buf))) atomicAdd(&S.dups, 1u);
+            head += nvalid;
+            if (nvalid < 32u) break;   // the next entry has not been written (yet)
         }
-        const unsigned int m = __ballot_sync(0xffffffffu, ok);
-        const unsigned int nvalid = (m == 0xffffffffu) ? 32u : (unsigned int)(__ffs((int)~m) - 1);
-        if (lane < nvalid && !zz_mark_local(S, t, k, zz_colour<KIND>(P, k, buf))) atomicAdd(&S.dups, 1u);
-        head += nvalid;
-        if (nvalid < 32u) break;   // reached the tail, or an entry whose producer has not stored it yet (picked up next time)
+        __syncwarp();
+        if (lane == 0) S.head[sr] = head;
     }
-    __syncwarp();
-    if (lane == 0) S.head = head;
+    (void)ws;
+}
+
+// Has any sender left an entry that has not been consumed?  (lanes 0 .. nranks-1 of warp 0 look at one sub-box each)
+template <bool MULTI>
+__device__ __forceinline__ bool zz_inbox_nonempty(const ZzParams& P, const ZzAsyncSh& S, uint32_t wat)
+{
+    const unsigned int lane = threadIdx.x & 31u;
+    const int nr = MULTI ? P.v.nranks : 1;
+    bool ok = false;
+    if ((int)lane < nr && S.head[lane] < P.inbox_cap) {
+        const unsigned long long* e = P.inbox + ((size_t)blockIdx.x * nr + lane) * P.inbox_cap + S.head[lane];
+        const unsigned long long v = MULTI ? zz_ld_acq_sys(e) : zz_ld_acq(e);
+        ok = ((uint32_t)(v >> 32) == wat);
+    }
+    return __any_sync(0xffffffffu, ok);
 }
 
 // Sharded runs: every rank keeps a replica of the records it reads from other ranks at the SAME global index of its own
@@ -1207,13 +1214,12 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
                 }
             }
 #endif
-            // The list and its header must be VISIBLE IN L2 before any reader is marked: a reader that raced with the stores
-            // above (and may have seen the new header with the old contents of the slot) cleared its mark before it read, so the
-            // marks below re-queue it; a reader that clears its mark after them reads complete data.  A block-scope fence is not
-            // enough even for readers of this CTA -- everybody reads through L2 (ld.cg), and a block-scope fence does not wait
-            // for the stores to arrive there (seen on the B200 as two neighbours re-publishing each other's stale lists forever).
-            // (sharded: a reader on another GPU is only ever reached through zz_mark_async, whose system-scope fence is cumulative)
-            __threadfence();
+            // The list and its header must be VISIBLE (in L2; in the replicas of other GPUs) before any reader is marked: a reader
+            // that raced with the stores above (and may have seen the new header with the old contents of the slot) cleared its
+            // mark before it read, so the marks below re-queue it; a reader that clears its mark after them reads complete data.
+            // A block-scope fence is not enough even for readers of this CTA: everybody reads through L2 (ld.cg).  The same
+            // fence orders the increment of `pending` before the inbox entries.
+            unsigned int nrem = 0; bool offgpu = false;
             if (KIND == ZZ_KIND_GRID) {
                 const int32_t M = P.g.grid_m, N = P.g.grid_n;
                 int32_t kk[4];
@@ -1227,14 +1233,25 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
                         kk[q] = ok ? j + ((q == 0) ? -M : (q == 1) ? -1 : (q == 2) ? 1 : M) : -1;
                     }
                 }
-                zz_mark_async<4, MULTI>(P, S, t, kk, nxt, ws, wat);
+                zz_mark_count<4, MULTI>(P, t, kk, ws, nrem, offgpu);
+                if (nrem) { atomicAdd(&C->created[ws], (unsigned long long)nrem); atomicAdd(&C->dbg[3], (unsigned long long)nrem); }
+                if (MULTI && offgpu) __threadfence_system(); else __threadfence();
+                zz_mark_push<4, MULTI>(P, S, t, kk, nxt, ws, wat);
             } else {
                 const int32_t q1 = P.dptr[j + 1];
                 for (int32_t q0 = P.dptr[j]; q0 < q1; q0 += 4) {
                     int32_t kk[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) kk[q] = (q0 + q < q1) ? P.didx[q0 + q] : -1;
-                    zz_mark_async<4, MULTI>(P, S, t, kk, nxt, ws, wat);
+                    zz_mark_count<4, MULTI>(P, t, kk, ws, nrem, offgpu);
+                }
+                if (nrem) { atomicAdd(&C->created[ws], (unsigned long long)nrem); atomicAdd(&C->dbg[3], (unsigned long long)nrem); }
+                if (MULTI && offgpu) __threadfence_system(); else __threadfence();
+                for (int32_t q0 = P.dptr[j]; q0 < q1; q0 += 4) {
+                    int32_t kk[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) kk[q] = (q0 + q < q1) ? P.didx[q0 + q] : -1;
+                    zz_mark_push<4, MULTI>(P, S, t, kk, nxt, ws, wat);
                 }
             }
         }
@@ -1246,7 +1263,7 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
         vi[0] = o.viol_t; vi[1] = o.viol_l; vi[2] = o.viol_lb;
     }
     if (flags & ZZ_F_OVERFLOW) {
-        zz_flag_raise<MULTI>(&(MULTI ? P.ctl_peer[0] : C)->abortf[ws]);
+        zz_abort_raise<MULTI>(P, ws);
         if (o.flags & ZZ_F_OVERFLOW) atomicAdd(&C->dbg[0], 1ULL);   // flips / pool / items of the timeline itself
     }
 }
@@ -1265,9 +1282,6 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
     const unsigned int nwc = blockDim.x >> 5;
     const bool leader = (blockIdx.x == 0 && threadIdx.x == 0);
     const int32_t lo = MULTI ? P.v.lo : 0, hi = MULTI ? P.v.hi : P.v.d;   // owned coordinates
-    ZzDevCtl* const G0 = MULTI ? P.ctl_peer[0] : C;                       // home of `pending` / `abortf`
-    const bool gleader = leader && (!MULTI || P.v.rank == 0);
-    const long long ntokens = (long long)gridDim.x * (MULTI ? P.v.nranks : 1);
     unsigned long long xep = MULTI ? __ldcg(&C->xrelease) : 0ULL;         // cross-GPU boundary counter (persists)
     ZzTile t;
     t.lo = lo;
@@ -1298,9 +1312,10 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
     // slots of the first attempt of this launch (later ones are prepared one attempt ahead, see below)
     if (threadIdx.x == 0) {
         const int ws0 = (int)(wat % 3u);
-        P.inbox_cnt[(size_t)ws0 * gridDim.x + blockIdx.x] = 0u;
+        for (int r = 0; r < (MULTI ? P.v.nranks : 1); ++r)   // this rank's slot counters for pushes INTO tile blockIdx.x of rank r
+            P.inbox_cnt[((size_t)ws0 * (MULTI ? P.v.nranks : 1) + r) * gridDim.x + blockIdx.x] = 0u;
         if (blockIdx.x == 0) {
-            if (gleader) { G0->pending[ws0] = ntokens; G0->abortf[ws0] = 0u; }
+            C->created[ws0] = (unsigned long long)gridDim.x; C->done[ws0] = 0ULL; C->abortf[ws0] = 0u; C->doneflag[ws0] = 0u;
             C->touched_cnt[ws0] = 0; C->smin_key[ws0] = ~0ULL; C->nprop_win[ws0] = 0;
         }
     }
@@ -1333,12 +1348,15 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
         ZZ_TIC();
         if (threadIdx.x == 0) {
             const int wz = (int)(wat % 3u);   // slots of the NEXT attempt
-            P.inbox_cnt[(size_t)wz * gridDim.x + blockIdx.x] = 0u;
+            for (int r = 0; r < (MULTI ? P.v.nranks : 1); ++r)
+                P.inbox_cnt[((size_t)wz * (MULTI ? P.v.nranks : 1) + r) * gridDim.x + blockIdx.x] = 0u;
             if (blockIdx.x == 0) {
-                if (gleader) { G0->pending[wz] = ntokens; G0->abortf[wz] = 0u; }
+                C->created[wz] = (unsigned long long)gridDim.x; C->done[wz] = 0ULL; C->abortf[wz] = 0u; C->doneflag[wz] = 0u;
                 C->touched_cnt[wz] = 0; C->smin_key[wz] = ~0ULL; C->nprop_win[wz] = 0;
             }
-            S.n[0] = 0u; S.n[1] = 0u; S.tcount = 0u; S.head = 0u; S.dups = 0u; S.aborted = 0u; S.state = 0u;
+            S.n[0] = 0u; S.n[1] = 0u; S.tcount = 0u; S.dups = 0u;
+            for (int r = 0; r < ZZ_MAXRANKS; ++r) S.head[r] = 0u;
+             S.aborted = 0u; S.state = 0u;
         }
         __syncthreads();
 #ifdef ZZ_PROF_SCAN
@@ -1412,8 +1430,10 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
         if (leader) { const long long sc3 = clock64(); C->dbg[4] += 1; C->dbg[5] += (unsigned long long)(sc1 - sc0); C->dbg[6] += (unsigned long long)(sc3 - sc1); }
 #endif
         if (threadIdx.x == 0) {
-            const long long dlt = (long long)S.tcount - 1LL;   // queued evaluations; hand back this CTA's token
-            if (dlt) zz_pending_add<MULTI>(&G0->pending[ws], dlt);
+            // queued evaluations first, then hand back this CTA's token (the second atomic consumes the result of the first, so
+            // that it cannot be performed earlier: created >= done at all times)
+            const unsigned long long oc = atomicAdd(&C->created[ws], (unsigned long long)S.tcount);
+            atomicAdd(&C->done[ws], 1ULL + (oc >> 63));
         }
         ZZ_TOC(0);
         ZZ_DBGLOG(2, S.tcount);
@@ -1427,21 +1447,35 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
             const unsigned int n = S.n[cq];
             if (n == 0 && S.n[cq ^ 1] != 0u) { cq ^= 1; continue; }   // (uniform: read after a block barrier)
             if (n == 0) {
-                if (threadIdx.x == 0) {
+                if (warp == 0) {
                     ZZ_TIC();
                     unsigned int st = 0;
-                    const unsigned int* myc = P.inbox_cnt + (size_t)ws * gridDim.x + blockIdx.x;
                     for (;;) {
-                        unsigned int tail = zz_flag_ld<MULTI>(myc);
-                        if (tail > P.inbox_cap) tail = P.inbox_cap;
-                        if (tail > S.head) { st = ZZ_ST_WORK; break; }
-                        // order matters: an evaluation that overflowed raised the flag BEFORE it was subtracted from `pending`
-                        const long long pend = zz_pending_ld<MULTI>(&G0->pending[ws]);
-                        const unsigned int ab = zz_flag_ld<MULTI>(&G0->abortf[ws]);
+                        if (zz_inbox_nonempty<MULTI>(P, S, watn)) { st = ZZ_ST_WORK; break; }
+                        // order matters: `done` before `created` (see ZzDevCtl); an evaluation that overflowed raised the flag
+                        // BEFORE it was added to `done`, so whoever sees the sums agree also sees the flag
+                        unsigned long long dsum = 0, csum = 1; unsigned int ab = 0, fl = 0;
+                        if (!MULTI) {
+                            if (lane == 0) { dsum = zz_ld_acq(&C->done[ws]); csum = zz_ld_acq(&C->created[ws]); ab = zz_ld_acq32(&C->abortf[ws]); }
+                        } else if (blockIdx.x == 0) {   // CTA 0 compares the node-wide sums (one peer load per lane and counter) ...
+                            const bool have = lane < (unsigned int)P.v.nranks;
+                            unsigned long long dv = have ? zz_ld_acq_sys(&P.ctl_peer[lane]->done[ws]) : 0ULL;
+                            dv = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), dv, cg::plus<unsigned long long>());
+                            unsigned long long cv = have ? zz_ld_acq_sys(&P.ctl_peer[lane]->created[ws]) : 0ULL;
+                            cv = cg::reduce(cg::tiled_partition<32>(cg::this_thread_block()), cv, cg::plus<unsigned long long>());
+                            dsum = dv; csum = cv;
+                            if (lane == 0) {
+                                ab = zz_ld_acq32_sys(&C->abortf[ws]);
+                                if (dsum == csum && !ab) { __threadfence(); atomicExch(&C->doneflag[ws], 1u); }
+                            }
+                        } else {                        // ... the other CTAs of the GPU wait for its verdict
+                            if (lane == 0) { ab = zz_ld_acq32_sys(&C->abortf[ws]); fl = zz_ld_acq32(&C->doneflag[ws]); if (fl) csum = dsum; }
+                        }
+                        dsum = __shfl_sync(0xffffffffu, dsum, 0); csum = __shfl_sync(0xffffffffu, csum, 0); ab = __shfl_sync(0xffffffffu, ab, 0);
                         if (ab) { st = ZZ_ST_ABORT; break; }
-                        if (pend == 0) { st = ZZ_ST_DONE; break; }
+                        if (dsum == csum) { st = ZZ_ST_DONE; break; }
                     }
-                    S.state = st;
+                    if (lane == 0) S.state = st;
                     ZZ_TOC(2);
                     ZZ_DBGLOG(4, st);
                 }
@@ -1450,7 +1484,7 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
                 if (warp == 0) {
                     zz_drain_inbox<KIND, MULTI>(P, S, t, cq, ws, watn);
                     if (lane == 0 && S.dups) {
-                        zz_pending_add<MULTI>(&G0->pending[ws], -(long long)S.dups);
+                        atomicAdd(&C->done[ws], (unsigned long long)S.dups);
                         S.dups = 0u;
                     }
                 }
@@ -1469,11 +1503,8 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
             const unsigned int other0 = S.n[nq];   // (lattice: the other colour may hold entries of the scan or of the inbox already)
             // the inbox counter and the abort flag are needed only AFTER the evaluations: start the loads now (plain loads:
             // the entries themselves are read with acquire semantics, the flag is only a hint to stop early)
-            unsigned int tail_pre = 0, abort_pre = 0;
-            if (threadIdx.x == 0) {
-                tail_pre = *(volatile const unsigned int*)(P.inbox_cnt + (size_t)ws * gridDim.x + blockIdx.x);
-                abort_pre = *(volatile const unsigned int*)&G0->abortf[ws];
-            }
+            unsigned int abort_pre = 0;
+            if (threadIdx.x == 0) abort_pre = *(volatile const unsigned int*)&C->abortf[ws];
             // entry e goes to warp e % (#warps), lane e / (#warps): a short queue occupies a few lanes of every warp
             const unsigned int estride = P.eval_threads ? P.eval_threads : blockDim.x;
             for (unsigned int e = (unsigned int)lane * nwc + (unsigned int)warp; e < n; e += estride) {
@@ -1507,11 +1538,10 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
                 const unsigned int produced = S.n[nq] - other0;   // local marks only: inbox entries were counted by their senders
                 if (lane == 0) S.n[cq] = 0u;                          // (before the drain: on the lattice it may refill this queue)
                 __syncwarp();
-                tail_pre = __shfl_sync(0xffffffffu, tail_pre, 0);
-                if (tail_pre > S.head) zz_drain_inbox<KIND, MULTI>(P, S, t, nq, ws, watn);
+                if (zz_inbox_nonempty<MULTI>(P, S, watn)) zz_drain_inbox<KIND, MULTI>(P, S, t, nq, ws, watn);
                 if (lane == 0) {
-                    const long long dlt = (long long)produced - (long long)n - (long long)S.dups;
-                    if (dlt) zz_pending_add<MULTI>(&G0->pending[ws], dlt);
+                    const unsigned long long oc = atomicAdd(&C->created[ws], (unsigned long long)produced);   // (performed before `done`)
+                    atomicAdd(&C->done[ws], (unsigned long long)n + (unsigned long long)S.dups + (oc >> 63));
                     S.dups = 0u;
                     if (abort_pre) S.aborted = 1u;
                 }

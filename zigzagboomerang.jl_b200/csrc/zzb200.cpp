@@ -181,7 +181,7 @@ struct zzb_run_s {
     int schedule = 1;                  // 1: asynchronous tile-local relaxation; 0: pass-synchronous schedule of round 1 (plain ZigZag only)
     DevBuf inbox, inbox_cnt; unsigned int inbox_cap = 0, flag_words = 0; int inbox_grid = 0;
     DevBuf dbgbuf; std::vector<unsigned long long> dbghost;
-    int tile_per = 0; unsigned int eval_threads = 0;
+    int tile_per = 0; unsigned int eval_threads = 0; int inbox_nr = 0;
     unsigned int wat_next = 0;         // window-attempt numbers tag the inbox entries: never reused by a later run of this handle
     int kidx() const
     {
@@ -476,14 +476,17 @@ static int32_t setup_tiles(zzb_run_s* r)
     const long long per = (((span + r->grid - 1) / r->grid) + 31) & ~31LL;
     r->tile_per = (int)per;
     r->flag_words = (unsigned int)(per / 32);
+    // one sub-box per (receiving tile, sending rank); the slot counters [attempt mod 3][destination rank][destination tile] are the
+    // SENDER's and live in its own memory
     const unsigned int cap = (unsigned int)std::max<long long>(1024, 2 * per);
-    if (r->inbox_grid != r->grid || r->inbox_cap != cap) {
-        int32_t st = r->inbox.alloc((size_t)r->grid * cap * 8);
-        if (!st) st = r->inbox_cnt.alloc((size_t)3 * r->grid * 4);
+    const size_t nr = (size_t)r->nranks;
+    if (r->inbox_grid != r->grid || r->inbox_cap != cap || r->inbox_nr != r->nranks) {
+        int32_t st = r->inbox.alloc((size_t)r->grid * nr * cap * 8);
+        if (!st) st = r->inbox_cnt.alloc((size_t)3 * nr * r->grid * 4);
         if (st) return st == ZZB_E_CUDA ? ZZB_E_NOMEM : st;
-        CU(cuMemsetD8(r->inbox.p, 0xff, (size_t)r->grid * cap * 8));   // attempt tag 0xffffffff: "not written"
-        CU(cuMemsetD8(r->inbox_cnt.p, 0, (size_t)3 * r->grid * 4));
-        r->inbox_grid = r->grid; r->inbox_cap = cap;
+        CU(cuMemsetD8(r->inbox.p, 0xff, (size_t)r->grid * nr * cap * 8));   // attempt tag 0xffffffff: "not written"
+        CU(cuMemsetD8(r->inbox_cnt.p, 0, (size_t)3 * nr * r->grid * 4));
+        r->inbox_grid = r->grid; r->inbox_cap = cap; r->inbox_nr = r->nranks;
     }
     return ZZB_OK;
 }
