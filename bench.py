@@ -95,6 +95,44 @@ def workload(args):
     return zzb, G, x0, th0, c
 
 
+def workload_string(args, d):
+    """The ONE description of the bench workload, identical in both arms (the driver compares the strings)."""
+    return (f"local ZigZag spdmp, {args.n}x{args.n} grid GMRF (d={d}), c={'sqrt(eps)' if args.tight else '||Gamma[:,i]||'}, "
+            f"T_step={args.T}, one step = full run from (x0, theta0)")
+
+
+def run_signature(acc, num, t, x, theta, c=None, s1=None, s2=None):
+    """Order-independent fingerprint of a finished run (bit patterns, not rounded values)."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.int64(num).tobytes())
+    for a in (acc, t, x, theta, c, s1, s2):
+        if a is not None:
+            h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()[:16]
+
+
+def oracle_parity(O, G, x0, th0, c, T, got):
+    """The bench workload once more on the CPU oracle in the device's contract mode (ctr | lazy), compared bit for bit with
+    what the device produced (`got`: dict with acc, num, t, x, theta, c, s1, s2 and optionally events).  Outside every timed region."""
+    ref = O.spdmp(G, G, 0.0, x0, th0, T, c, seed=(1, 2))
+    out = {"oracle": "zzo_spdmp mode ctr|lazy (oracle/zz_oracle.c), same inputs, T = %g" % T,
+           "num_equal": int(ref.num) == int(got["num"]),
+           "acc_equal": bool(np.array_equal(ref.acc, got["acc"])),
+           "final_state_equal": all(bool(np.array_equal(getattr(ref, f).view(np.uint64), got[f].view(np.uint64))) for f in ("t", "x", "theta", "c")),
+           "moment_sums_equal": bool(np.array_equal(ref.s1.view(np.uint64), got["s1"].view(np.uint64)) and
+                                     np.array_equal(ref.s2.view(np.uint64), got["s2"].view(np.uint64))),
+           "switches": int(ref.acc.sum()), "proposals": int(ref.num),
+           "signature_oracle": run_signature(ref.acc, ref.num, ref.t, ref.x, ref.theta, ref.c, ref.s1, ref.s2),
+           "signature_device": run_signature(got["acc"], got["num"], got["t"], got["x"], got["theta"], got["c"], got["s1"], got["s2"])}
+    if got.get("events") is not None:
+        ev = got["events"]
+        out["events_equal"] = bool(len(ev) == len(ref.events) and np.array_equal(ev["i"], ref.events["i"]) and
+                                   all(np.array_equal(ev[f].view(np.uint64), ref.events[f].view(np.uint64)) for f in ("t", "x", "theta")))
+    out["ok"] = all(v for k, v in out.items() if k.endswith("_equal"))
+    return out
+
+
 def cpu_reference_step(O, G, x0, th0, c, T, seed):
     """One step on the host, single thread: the oracle's faithful restatement of spdmp (binary heap, single xoroshiro
     stream, in-place moves; src/sfact.jl:162-212).  Returns (switches, proposals, seconds of the event loop, setup excluded)."""
@@ -159,25 +197,56 @@ def cpu_baselines(O, G, x0, th0, c, T, delta=0.02):
 
 
 def run_reference(args):
+    """CPU arm: the restatement of the reference's own CPU implementation of the path on the box's host cores.  Exactly
+    `--warmup` untimed and `--steps` timed steps; a step is one run of the faster of (single-thread spdmp, multithreaded
+    parallel_spdmp on all host threads) over the bounded sample [0, cpu_T] of the workload; `value` = events of the timed steps /
+    their event-loop seconds."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle_lib as O
     zzb, G, x0, th0, c = workload(args)
-    T = args.cpu_T if args.cpu_T else args.T
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(O, G, x0, th0, c, min(T, 0.1), (1, 2))
-    steps = max(1, min(args.steps, 3))   # every step is a bounded sample of the workload (about 10 s of CPU work)
-    runs = [cpu_baselines(O, G, x0, th0, c, T) for _ in range(steps)]
-    cb = max(runs, key=lambda r: r["value"])
-    val = cb["value"]
+    d = G.n
+    T = args.cpu_T if args.cpu_T else min(args.T, 1.0)
+    cores = host_cores()
+    delta = 0.02
+    # which variant is faster on this box?  (one probe each, untimed)
+    a1, b1, s1 = cpu_reference_step(O, G, x0, th0, c, min(T, 0.25), (1, 2))
+    cand = [("single", None, None, a1 / s1)]
+    for K in parallel_chunks(d, cores):
+        if K > 1:
+            G2 = O.block_diagonal(G, K)
+            a2, b2, s2 = cpu_parallel_step(O, G, G2, K, x0, th0, c, min(T, 0.25), (1, 2), delta)
+            cand.append(("parallel", K, G2, a2 / s2))
+    kind, K, G2, _ = max(cand, key=lambda r: r[3])
+
+    def step():
+        if kind == "single":
+            return cpu_reference_step(O, G, x0, th0, c, T, (1, 2))
+        return cpu_parallel_step(O, G, G2, K, x0, th0, c, T, (1, 2), delta)
+
+    for _ in range(args.warmup):
+        step()
+    ev = pr = 0
+    sec = 0.0
+    for _ in range(args.steps):
+        a, b, sdt = step()
+        ev += a; pr += b; sec += sdt
+    val = ev / sec
+    single_val = a1 / s1
+    cb = {"value": val, "unit": "events/s", "cores": (K + 1) if kind == "parallel" else 1, "kind": "port",
+          "sample": (f"{args.steps} runs of spdmp over [0,{T}] on the same d={d} GMRF, event loop only (setup excluded): "
+                     + (f"multithreaded parallel_spdmp restatement (src/parallel.jl), {K} chunk threads + outer task, Delta={delta}"
+                        if kind == "parallel" else "single-thread spdmp restatement (src/sfact.jl), faithful draw order")
+                     + f"; {ev} switches in {sec:.2f} s; host has {cores} cores"),
+          "proposals_per_s": pr / sec, "seconds": sec, "variant": kind,
+          "single_thread_events_per_s_probe": single_val, "probe_events_per_s": {k: v for k, _, _, v in cand}, "host_cores": cores}
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "events/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * cb["seconds"], "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "events/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"local ZigZag spdmp, {args.n}x{args.n} grid GMRF (d={G.n}), c={'sqrt(eps)' if args.tight else '||Gamma[:,i]||'}, "
-                               f"T_step={T}", "proposals_per_s": cb["proposals_per_s"],
-                   "note": "CPU restatement of the reference (Julia is not installed): best of the single-thread spdmp and the multithreaded parallel_spdmp"},
+        "config": {"workload": workload_string(args, d)},
+        "note": "CPU restatement of the reference (Julia is not installed here or on the GPU box); a step is the bounded sample described in cpu_baseline.sample",
         "cpu_baseline": cb,
         "e2e": {"value": val, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -252,6 +321,39 @@ def run_ours(args):
     h2d = 3 * d * 8
     d2h = 7 * d * 8  # t, x, theta, c, acc, s1, s2
 
+    # ---- e2e WITH the sampler's primary output: the full trace (32 B per switching event) ordered by time in host memory
+    e2e_trace = None
+    trace_events = None
+    if not args.no_trace:
+        run4 = zzb.Run(prob, record_trace=True)
+        run4.set(target_frac=args.frac)
+        t_steps = max(1, min(args.steps, 3))
+        for _ in range(1):
+            run4.upload(0.0, px0, pth, pc, seed=(1, 2)); run4.execute(args.T); evbuf = run4.events()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(t_steps):
+            run4.upload(0.0, px0, pth, pc, seed=(1, 2))
+            run4.execute(args.T)
+            n4, a4 = run4.fetch_into(**out)
+            evbuf = run4.events()                          # D2H of the events + ordering by (time, coordinate)
+        torch.cuda.synchronize()
+        t_dt = time.perf_counter() - t0
+        assert a4 == nacc and len(evbuf) == nacc
+        e2e_trace = {"value": a4 * t_steps / t_dt, "unit": "events/s", "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h + 32 * len(evbuf), "steps": t_steps, "ms_per_step": 1e3 * t_dt / t_steps,
+                     "what": "as e2e, plus the complete trace (t, i, x, theta per event) copied to the host and ordered by time"}
+        trace_events = evbuf
+        run4.close()
+
+    # ---- parity of what was timed: the same workload on the CPU oracle (contract mode), bit for bit; outside the timed regions
+    parity = None
+    if not args.no_parity:
+        import oracle_lib as O
+        got = dict(acc=out["acc"].copy(), num=n2, t=out["t"], x=out["x"], theta=out["theta"], c=out["c"], s1=out["s1"], s2=out["s2"],
+                   events=trace_events)
+        parity = oracle_parity(O, G, x0, th0, c, args.T, got)
+
     # ---- roofline of the dominant kernel (the persistent event loop)
     peak, peak_src = peaks()
     alg_bytes = B_PROPOSAL * num + B_ACCEPT * nacc        # per launch
@@ -259,7 +361,7 @@ def run_ours(args):
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01e_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     except Exception:
         pass
@@ -293,18 +395,21 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"local ZigZag spdmp, {args.n}x{args.n} grid GMRF (d={d}), c={'sqrt(eps)' if args.tight else '||Gamma[:,i]||'}, "
-                               f"T_step={args.T}, one step = full run from (x0, theta0)",
+        "config": {"workload": workload_string(args, d),
                    "l2": "device working set (state + flip lists + work lists ~ 0.4 KB/coordinate = 400 MB) exceeds the 126 MB L2",
                    "switches_per_step": nacc, "proposals_per_step": int(num), "proposals_per_s": num * args.steps / (total_ms * 1e-3),
-                   "windows_per_step": st["windows"], "passes_per_step": st["passes"], "target_frac": args.frac,
+                   "windows_per_step": st["windows"], "rounds_of_cta0_per_step": st["passes"], "timeline_evaluations_per_step": st["node_evals"],
+                   "target_frac": args.frac, "schedule": "asynchronous tile-local relaxation (DESIGN.md section 3b)",
                    "tight_bound_variant": tight},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "zz_run_kernel_grid", "kernel_ms_per_launch": k_ms,
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "latency/synchronisation-bound sparse event loop: see DESIGN.md (roofline) for why frac is small"},
+                     "note": "latency-bound sparse event loop: see DESIGN.md (roofline) for why frac is small"},
         "e2e": {"value": e2e_val, "unit": "events/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
-                "ms_per_step": 1e3 * e_dt / e_steps},
+                "ms_per_step": 1e3 * e_dt / e_steps,
+                "what": "upload of (x0, theta0, c) from pinned host memory + initialisation + event loop + D2H of final state, adapted c, counts and moment sums (no trace: see e2e_trace)"},
+        "e2e_trace": e2e_trace,
+        "parity_check": parity,
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk.summary(),
     }
@@ -361,19 +466,30 @@ def run_ours_sharded(args, zzb, G, x0, th0, c, world, rank, local):
     nacc, nprop = int(tot[0].item()), int(tot[1].item())
     k_ms = mx[2].item() / args.steps          # device time of the slowest rank's event-loop kernel
     st = run.stats()
-    # e2e through the host-buffer path: upload (H2D of the full inputs on every rank) + kernels + D2H of the owned results
+    # e2e through the host-buffer path: every rank uploads its slab (+ one halo column on either side) from pinned memory, runs,
+    # and reads back the results of its OWNED coordinates -- the node moves ~ d values each way whatever N is
     e_steps = max(1, min(args.steps, 5))
+    px0 = torch.from_numpy(x0).pin_memory().numpy(); pth = torch.from_numpy(th0).pin_memory().numpy(); pc = torch.from_numpy(c).pin_memory().numpy()
+    pin = lambda dt: torch.empty(d, dtype=dt).pin_memory().numpy()
+    outb = dict(t=pin(torch.float64), x=pin(torch.float64), theta=pin(torch.float64), c=pin(torch.float64),
+                acc=pin(torch.int64), s1=pin(torch.float64), s2=pin(torch.float64))
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e_steps):
         dist.barrier()
-        run.upload(0.0, x0, th0, c, seed=(1, 2))
+        run.upload(0.0, px0, pth, pc, seed=(1, 2))
         dist.barrier()
         run.execute(args.T)
-        run.counts(); run.final_state(); run.sums()
+        run.fetch_into(**outb)
     torch.cuda.synchronize()
     dist.barrier()
     e_dt = time.perf_counter() - t0
+    m_rows = args.n
+    h2d_rank = 3 * 8 * (min(d, hi + m_rows) - max(0, lo - m_rows))
+    d2h_rank = 7 * 8 * (hi - lo)
+    io = torch.tensor([float(h2d_rank), float(d2h_rank)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(io, op=dist.ReduceOp.SUM)
+    h2d_total, d2h_total = int(io[0].item()), int(io[1].item())
     # ---- context: the same N GPUs running N INDEPENDENT chains of the full problem (how multi-GPU MCMC is usually run; no
     # exchange at all).  Reported beside the sharded headline, never instead of it.
     runc = zzb.Run(prob, record_trace=False)
@@ -394,6 +510,18 @@ def run_ours_sharded(args, zzb, G, x0, th0, c, world, rank, local):
     chains_events_per_s = chains[0].item() / (chains_max[1].item() * 1e-3)
     runc.close()
 
+    # ---- parity of what was timed: gather the owned parts, compare with the CPU oracle (contract mode) bit for bit on rank 0
+    parity = None
+    if not args.no_parity:
+        t_, x_, th_, c_ = run.final_state(); s1_, s2_ = run.sums()
+        part = dict(lo=lo, hi=hi, acc=acc, num=num, t=t_, x=x_, theta=th_, c=c_, s1=s1_, s2=s2_, events=np.empty(0, dtype=_capi.EVENT_DTYPE))
+        parts = [None] * world
+        dist.all_gather_object(parts, part)
+        if rank == 0:
+            import oracle_lib as O
+            got = zzb.multigpu.merge_shards(parts, d)
+            got["events"] = None
+            parity = oracle_parity(O, G, x0, th0, c, args.T, got)
     peak, peak_src = peaks()
     alg_bytes = B_PROPOSAL * nprop + B_ACCEPT * nacc
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
@@ -403,20 +531,23 @@ def run_ours_sharded(args, zzb, G, x0, th0, c, world, rank, local):
             "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": k_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"local ZigZag spdmp, {args.n}x{args.n} grid GMRF (d={d}) sharded by lattice columns over {world} GPUs, "
-                                   f"c={'sqrt(eps)' if args.tight else '||Gamma[:,i]||'}, T_step={args.T}",
+            "config": {"workload": workload_string(args, d),
+                       "sharding": f"coordinates sharded by whole lattice columns over {world} GPUs (one process per GPU)",
                        "l2": "per-GPU working set 400 MB (full-length arrays on every rank) exceeds the 126 MB L2",
                        "switches_per_step": nacc, "proposals_per_step": nprop, "windows_per_step": st["windows"],
-                       "passes_per_step": st["passes"], "wall_ms_per_step_incl_host_barriers": 1e3 * wall / args.steps,
-                       "exchange": "peer loads/atomics over NVLink + mailbox all-reduce per pass (no per-event collective)",
+                       "rounds_of_cta0_per_step": st["passes"], "wall_ms_per_step_incl_host_barriers": 1e3 * wall / args.steps,
+                       "exchange": "asynchronous tile-local relaxation on every GPU; marks that cross a GPU boundary are pushed into the "
+                                   "owner's inbox and changed halo records into its replica over NVLink (plain stores); two node-wide "
+                                   "barriers per WINDOW (mailbox all-reduce), none per pass or per event",
                        "independent_chains_events_per_s": chains_events_per_s,
-                       "note": "one chain is latency-bound (passes x evaluation latency), so sharding d = 10^6 buys capacity, not speed; "
-                               "independent_chains_events_per_s = the same GPUs running one full-size chain each"},
+                       "note": "independent_chains_events_per_s = the same GPUs running one full-size chain each (context, never the headline)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak * world, "unit": "GB/s", "frac": achieved / (peak * world),
                          "traffic": None, "peak_source": peak_src + f" x {world} GPUs", "kernel": "zz_run_kernel_grid_multi",
                          "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": alg_bytes},
-            "e2e": {"value": nacc * e_steps / e_dt, "unit": "events/s", "h2d_bytes_per_step": 3 * d * 8 * world,
-                    "d2h_bytes_per_step": 7 * d * 8 * world, "steps": e_steps, "ms_per_step": 1e3 * e_dt / e_steps},
+            "e2e": {"value": nacc * e_steps / e_dt, "unit": "events/s", "h2d_bytes_per_step": h2d_total,
+                    "d2h_bytes_per_step": d2h_total, "steps": e_steps, "ms_per_step": 1e3 * e_dt / e_steps,
+                    "what": "per rank: H2D of its slab + halo columns of (x0, theta0, c) from pinned memory, initialisation, event loop, D2H of the owned final state / counts / moment sums; host barriers between the phases included"},
+            "parity_check": parity,
             "gpu_launches": 3 * args.steps * world, "clocks": clk.summary(),
         }))
     dist.barrier()
@@ -438,6 +569,8 @@ def main():
     ap.add_argument("--tight", action="store_true", help="c = sqrt(eps) (scripts/example.jl:39) instead of column norms")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tight", action="store_true", help="skip the extra c = sqrt(eps) measurement")
+    ap.add_argument("--no-trace", action="store_true", help="skip the e2e measurement with the full trace")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the bench workload")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -11,7 +11,7 @@ T = float(sys.argv[2]) if len(sys.argv) > 2 else 2.0
 G, x0, th0, c = z.gmrf_config(n)
 for rep in range(2):
     part, st, ms = z.spdmp_sharded(z, z.GaussianPotential(G), z.ZigZag(G, np.zeros(G.n)), 0.0, x0, th0, T, c, seed=(1, 2),
-                                   record_trace=False, gather=False)
+                                   record_trace=False, gather=False, tune=({"target_frac": float(os.environ["FRAC"]), "target_flip_frac": 0.18 * float(os.environ["FRAC"])} if os.environ.get("FRAC") else None))
     dist.barrier()
     if rep == 1:
         keys = ("windows", "passes", "ns_scan", "ns_relax", "ns_tail", "ns_commit", "ns_barrier", "ns_phaseb", "n_barriers")

@@ -112,6 +112,8 @@ struct ZzParams {
     unsigned long long* inbox_peer[ZZ_MAXRANKS];   // sharded runs: the inboxes / counters of every rank (own entries = the plain pointers)
     unsigned int* inbox_cnt_peer[ZZ_MAXRANKS];
     int32_t tile_per, tile_pad;     // coordinates per tile (a multiple of 32), identical on every rank
+    int32_t setup_lo, setup_hi;     // records written by zz_setup_kernel (sharded lattice: slab + halo columns; otherwise [0, d))
+    int32_t init_lo, init_hi;       // coordinates initialised by zz_init_kernel (sharded lattice: the owned slab; otherwise [0, d))
     // development: per-CTA log of one window (records of 4 x u64: kind, count, globaltimer, clock64), ZZB200_DBG_WINDOW
     unsigned long long* dbgbuf;     // [grid][ZZ_DBG_REC][4] or null
     unsigned int dbg_window;

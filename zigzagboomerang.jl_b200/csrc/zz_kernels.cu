@@ -507,7 +507,7 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK)
 zz_setup_kernel(const ZzParams P, const double* __restrict__ x0, const double* __restrict__ th0,
                 const double* __restrict__ c0)
 {
-    for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < P.v.d; j += gridDim.x * blockDim.x) {
+    for (int32_t j = P.setup_lo + blockIdx.x * blockDim.x + threadIdx.x; j < P.setup_hi; j += gridDim.x * blockDim.x) {
         ZzKin k; k.theta = th0[j]; k.tf = P.t0; k.xf = x0[j]; k.hdr[0] = 0; k.hdr[1] = 0;
         P.v.kin[j] = k;
         ZzPriv p; p.a = 0.0; p.b = 0.0; p.told = P.t0; p.c = c0[j];
@@ -531,9 +531,9 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_grid_tail_kernel(const
 template <bool BOOM>
 __device__ __forceinline__ void zz_init_body(const ZzParams& P)
 {
-    ZzView vloc = P.v; vloc.nranks = 1;   // every rank initialises all coordinates from its own (identical) copies
+    ZzView vloc = P.v; vloc.nranks = 1;   // from this rank's own copies (sharded lattice: the owned slab, whose halo is set up too)
     unsigned long long kmin = ~0ULL;
-    for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < P.v.d; j += gridDim.x * blockDim.x) {
+    for (int32_t j = P.init_lo + blockIdx.x * blockDim.x + threadIdx.x; j < P.init_hi; j += gridDim.x * blockDim.x) {
         if (BOOM) zz_init_node_boom(P.g, vloc, j, P.t0);
         else zz_init_node(P.g, vloc, j, P.t0);
         const unsigned long long k = zz_key(vloc.tau[j]);
@@ -548,7 +548,7 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel_boom(const
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_init_kernel_strong(const ZzParams P)
 {
     unsigned long long kmin = ~0ULL;
-    for (int32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < P.v.d; j += gridDim.x * blockDim.x) {
+    for (int32_t j = P.init_lo + blockIdx.x * blockDim.x + threadIdx.x; j < P.init_hi; j += gridDim.x * blockDim.x) {
         zz_init_node_strong(P.g, P.v, P.st, j, P.t0);
         const unsigned long long k = zz_key(P.v.tau[j]);
         kmin = k < kmin ? k : kmin;
@@ -1319,7 +1319,13 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
             C->touched_cnt[ws0] = 0; C->smin_key[ws0] = ~0ULL; C->nprop_win[ws0] = 0;
         }
     }
-    zz_boundary<MULTI>(P, epoch, xep, prof, nullptr, nullptr, nullptr, 0u, 0u);
+    {   // (sharded: the earliest initial proposal over ALL ranks starts the first window; every rank initialised its own slab)
+        const ZzXres x0r = zz_boundary<MULTI>(P, epoch, xep, prof, nullptr, &C->f0_key, nullptr, 0u, 0u);
+        if (MULTI && !__ldcg(&C->started)) {
+            const double F0 = zz_unkey(x0r.minkey);
+            zz_ctl_init(ctl, F0 < P.T ? F0 : P.T, P.T, P.delta0, P.target, P.target_flips);
+        }
+    }
 
     while (ctl.phase < ZZ_PH_DONE && !stop) {
         if (cur > P.tag_limit) {  // list tags are about to run out of bits: forget all of them

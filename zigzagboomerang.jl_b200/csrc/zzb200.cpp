@@ -182,6 +182,7 @@ struct zzb_run_s {
     DevBuf inbox, inbox_cnt; unsigned int inbox_cap = 0, flag_words = 0; int inbox_grid = 0;
     DevBuf dbgbuf; std::vector<unsigned long long> dbghost;
     int tile_per = 0; unsigned int eval_threads = 0; int inbox_nr = 0;
+    int setup_lo = 0, setup_hi = 0;    // coordinates whose records this rank sets up (sharded lattice: slab + halo; otherwise all)
     unsigned int wat_next = 0;         // window-attempt numbers tag the inbox entries: never reused by a later run of this handle
     int kidx() const
     {
@@ -664,6 +665,9 @@ int32_t zzb_run_reset(zzb_run_t r)
     for (int q = 0; q < r->nranks; ++q)
         if (q != r->rank && !r->peer_open[q]) return fail(ZZB_E_ARG, "peer %d of a sharded run has not been imported", q);
     fill_params(r);
+    r->P.setup_lo = r->setup_lo; r->P.setup_hi = r->setup_hi ? r->setup_hi : r->d;
+    r->P.init_lo = (r->nranks > 1 && r->setup_hi && (r->setup_lo > 0 || r->setup_hi < r->d)) ? r->lo : 0;
+    r->P.init_hi = (r->nranks > 1 && r->setup_hi && (r->setup_lo > 0 || r->setup_hi < r->d)) ? r->hi : r->d;
     r->P.v.seed0 = r->seed[0]; r->P.v.seed1 = r->seed[1]; r->P.v.adapt = r->adapt; r->P.v.factor = r->factor; r->P.t0 = r->t0;
     CtxGuard cg;
     ZzParams& P = r->P;
@@ -694,17 +698,25 @@ int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* t
     if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
     {
         CtxGuard cg;
-        const size_t nb = (size_t)r->d * 8;
+        size_t nb = (size_t)r->d * 8;
         r->seed[0] = seed[0]; r->seed[1] = seed[1]; r->adapt = adapt; r->factor = factor;
         r->t0 = t0;
-        CU(cuMemcpyHtoDAsync(r->in_x.p, x0, nb, G.stream));
+        // sharded lattice run: this rank sets up its slab and one lattice column on either side (the replicas it reads); the
+        // host-to-device traffic of the node is then ~ d, not N d
+        size_t so = 0;
+        r->setup_lo = 0; r->setup_hi = r->d;
+        if (r->nranks > 1 && r->prob->g.grid_m && !r->strong) {
+            r->setup_lo = std::max(0, r->lo - r->prob->g.grid_m); r->setup_hi = std::min(r->d, r->hi + r->prob->g.grid_m);
+            so = (size_t)r->setup_lo * 8; nb = (size_t)(r->setup_hi - r->setup_lo) * 8;
+        }
+        CU(cuMemcpyHtoDAsync(r->in_x.p + so, x0 + so / 8, nb, G.stream));
         if (r->strong) {   // sparsestickystate (sparsestickyzz.jl:10-12): x0 == 0 starts frozen = velocity 0 in its record
             std::vector<double> th(theta0, theta0 + r->d);
             for (int32_t j = 0; j < r->d; ++j) if (x0[j] == 0.0) th[j] = 0.0;
             CU(cuMemcpyHtoD(r->in_th.p, th.data(), nb));
         } else
-        CU(cuMemcpyHtoDAsync(r->in_th.p, theta0, nb, G.stream));
-        CU(cuMemcpyHtoDAsync(r->in_c.p, c, nb, G.stream));
+        CU(cuMemcpyHtoDAsync(r->in_th.p + so, theta0 + so / 8, nb, G.stream));
+        CU(cuMemcpyHtoDAsync(r->in_c.p + so, c + so / 8, nb, G.stream));
         r->have_inputs = true;
     }
     return zzb_run_reset(r);
@@ -920,13 +932,17 @@ int32_t zzb_run_fetch(zzb_run_t r, double* t, double* x, double* theta, double* 
     void* a[] = { &r->P, &pt, &px, &pth, &pc, &pa };
     CU(cuLaunchKernel(G.f_export, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a, nullptr));
     r->launches++;
-    if (t) CU(cuMemcpyDtoHAsync(t, pt, d * 8, G.stream));
-    if (x) CU(cuMemcpyDtoHAsync(x, px, d * 8, G.stream));
-    if (theta) CU(cuMemcpyDtoHAsync(theta, pth, d * 8, G.stream));
-    if (c) CU(cuMemcpyDtoHAsync(c, pc, d * 8, G.stream));
-    if (acc) CU(cuMemcpyDtoHAsync(acc, pa, d * 8, G.stream));
-    if (s1) CU(cuMemcpyDtoHAsync(s1, r->s1.p, d * 8, G.stream));
-    if (s2) CU(cuMemcpyDtoHAsync(s2, r->s2.p, d * 8, G.stream));
+    // a sharded run holds results for its owned coordinates only: copy [lo, hi) into the same positions of the caller's arrays
+    const size_t lo = r->nranks > 1 ? (size_t)r->lo : 0, n = r->nranks > 1 ? (size_t)(r->hi - r->lo) : d, o8 = lo * 8, n8 = n * 8;
+    if (n) {
+        if (t) CU(cuMemcpyDtoHAsync(t + lo, pt + o8, n8, G.stream));
+        if (x) CU(cuMemcpyDtoHAsync(x + lo, px + o8, n8, G.stream));
+        if (theta) CU(cuMemcpyDtoHAsync(theta + lo, pth + o8, n8, G.stream));
+        if (c) CU(cuMemcpyDtoHAsync(c + lo, pc + o8, n8, G.stream));
+        if (acc) CU(cuMemcpyDtoHAsync(acc + lo, pa + o8, n8, G.stream));
+        if (s1) CU(cuMemcpyDtoHAsync(s1 + lo, r->s1.p + o8, n8, G.stream));
+        if (s2) CU(cuMemcpyDtoHAsync(s2 + lo, r->s2.p + o8, n8, G.stream));
+    }
     CU(cuMemcpyDtoHAsync(&r->hc, r->ctl.p, sizeof(ZzDevCtl), G.stream));
     CU(cuStreamSynchronize(G.stream));
     if (num) *num = (int64_t)r->hc.num;
