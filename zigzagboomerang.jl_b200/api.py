@@ -394,10 +394,15 @@ class Run:
         check(_capi.lib().zzb_run_final_state(self._h, ptr(t), ptr(x), ptr(th), ptr(c)))
         return t, x, th, c
 
-    def events(self):
+    def events(self, out=None):
+        """The trace so far, ordered by (time, coordinate).  `out`: an optional preallocated EVENT_DTYPE array (e.g. in pinned
+        memory: the events ordered on the device are then copied from HBM at PCIe speed); a view of its first n entries is returned."""
         n = C.c_int64()
         check(_capi.lib().zzb_trace_len(self._h, C.byref(n)))
-        ev = np.empty(n.value, dtype=EVENT_DTYPE)
+        if out is not None and len(out) >= n.value:
+            ev = out[: n.value]
+        else:
+            ev = np.empty(n.value, dtype=EVENT_DTYPE)
         if n.value:
             check(_capi.lib().zzb_trace_copy(self._h, ptr(ev), 0, n.value))
         return ev

@@ -568,6 +568,121 @@ zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Device-side ordering of the trace (src/trace.jl:38 is a time-ordered vector; upstream's own parallel samplers sort too,
+// src/asynchzz.jl:131, src/parallel.jl:168).  The commit appends the events of a window in arbitrary order; before the host
+// reads them they are ordered by (time, coordinate) here: a bucket sort on the time axis -- the bucket of an event is a
+// monotone function of its time, so buckets are ordered among themselves -- followed by a bitonic sort of every bucket in
+// shared memory.  Window-end markers (i == 0) are dropped.  A bucket that does not fit raises `ovf` and the host falls back to
+// its own sort.
+#define ZZ_TSORT_CAP 1024u     // events per bucket the in-shared-memory sort handles
+struct ZzTsort {
+    const ZzEvent* in; ZzEvent* out;
+    unsigned long long n;       // records in `in` (events + markers)
+    double tmin, scale;         // bucket = min(nb - 1, (t - tmin) * scale)
+    unsigned int nb;
+    unsigned int* cnt;          // [nb]     events per bucket
+    unsigned int* base;         // [nb + 1] exclusive prefix sum
+    unsigned int* fill;         // [nb]     scatter cursors
+    unsigned int* ovf;          // [1]
+};
+__device__ __forceinline__ unsigned int zz_tsort_bucket(const ZzTsort& Q, double t)
+{
+    const double u = (t - Q.tmin) * Q.scale;
+    if (!(u > 0.0)) return 0u;
+    return u >= (double)(Q.nb - 1u) ? Q.nb - 1u : (unsigned int)u;
+}
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_tsort_hist_kernel(const ZzTsort Q)
+{
+    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < Q.n; e += (unsigned long long)gridDim.x * blockDim.x)
+        if (Q.in[e].i != 0) atomicAdd(Q.cnt + zz_tsort_bucket(Q, Q.in[e].t), 1u);
+}
+extern "C" __global__ void __launch_bounds__(1024) zz_tsort_scan_kernel(const ZzTsort Q)
+{   // one CTA: exclusive prefix sum of the bucket counts (chunks of 1024 with a running carry)
+    __shared__ unsigned int wsum[32];
+    __shared__ unsigned int carry;
+    if (threadIdx.x == 0) carry = 0u;
+    __syncthreads();
+    const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (unsigned int b0 = 0; b0 < Q.nb; b0 += blockDim.x) {
+        const unsigned int b = b0 + threadIdx.x;
+        const unsigned int v = b < Q.nb ? Q.cnt[b] : 0u;
+        if (v > ZZ_TSORT_CAP) *Q.ovf = 1u;
+        unsigned int inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const unsigned int up = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += up; }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        unsigned int pre = 0, tot = 0;
+        for (unsigned int q = 0; q < (blockDim.x >> 5); ++q) { const unsigned int x = wsum[q]; if (q < warp) pre += x; tot += x; }
+        if (b < Q.nb) Q.base[b] = carry + pre + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) Q.base[Q.nb] = carry;
+}
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_tsort_scatter_kernel(const ZzTsort Q)
+{
+    for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < Q.n; e += (unsigned long long)gridDim.x * blockDim.x) {
+        const double2* src = reinterpret_cast<const double2*>(Q.in + e);
+        const double2 a = src[0], b = src[1];
+        if (__double_as_longlong(a.y) == 0LL) continue;   // window-end marker
+        const unsigned int bk = zz_tsort_bucket(Q, a.x);
+        const unsigned int pos = Q.base[bk] + atomicAdd(Q.fill + bk, 1u);
+        double2* dst = reinterpret_cast<double2*>(Q.out + pos);
+        dst[0] = a; dst[1] = b;
+    }
+}
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_tsort_sort_kernel(const ZzTsort Q)
+{
+    __shared__ unsigned long long key[ZZ_TSORT_CAP];   // order-preserving image of the time
+    __shared__ unsigned int sub[ZZ_TSORT_CAP];          // coordinate (ties in time are broken by it)
+    __shared__ unsigned short idx[ZZ_TSORT_CAP];        // position inside the bucket before the sort
+    for (unsigned int bk = blockIdx.x; bk < Q.nb; bk += gridDim.x) {
+        const unsigned int n = Q.cnt[bk];
+        if (n < 2u || n > ZZ_TSORT_CAP) continue;
+        ZzEvent* ev = Q.out + Q.base[bk];
+        unsigned int m = 2; while (m < n) m <<= 1;
+        __syncthreads();
+        for (unsigned int e = threadIdx.x; e < m; e += blockDim.x) {
+            if (e < n) { key[e] = zz_key(ev[e].t); sub[e] = (unsigned int)ev[e].i; idx[e] = (unsigned short)e; }
+            else { key[e] = ~0ULL; sub[e] = 0xffffffffu; idx[e] = 0xffffu; }
+        }
+        __syncthreads();
+        for (unsigned int k = 2; k <= m; k <<= 1) {
+            for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+                for (unsigned int e = threadIdx.x; e < m; e += blockDim.x) {
+                    const unsigned int p = e ^ j;
+                    if (p > e) {
+                        const bool up = ((e & k) == 0u);
+                        const bool gt = key[e] > key[p] || (key[e] == key[p] && sub[e] > sub[p]);
+                        if (gt == up) {
+                            const unsigned long long tk = key[e]; key[e] = key[p]; key[p] = tk;
+                            const unsigned int ts = sub[e]; sub[e] = sub[p]; sub[p] = ts;
+                            const unsigned short ti = idx[e]; idx[e] = idx[p]; idx[p] = ti;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // permute the records in place: every thread first reads the (at most four) records that belong at its positions
+        double2 ra[4], rb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned int e = threadIdx.x + (unsigned int)q * blockDim.x;
+            if (e < n) { const double2* src = reinterpret_cast<const double2*>(ev + idx[e]); ra[q] = src[0]; rb[q] = src[1]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned int e = threadIdx.x + (unsigned int)q * blockDim.x;
+            if (e < n) { double2* dst = reinterpret_cast<double2*>(ev + e); dst[0] = ra[q]; dst[1] = rb[q]; }
+        }
+    }
+}
+
 // Pass 1 finds its coordinates by scanning: every CTA scans its contiguous share of the owned proposal times and compacts
 // the coordinates with a proposal inside the window into a CTA-wide queue (the work list consumed last is free during this
 // pass; the CTA uses the slice that mirrors its share); the CTA then works through the queue with all its threads:

@@ -94,6 +94,7 @@ struct Global {
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
     CUfunction f_init_strong = nullptr;
+    CUfunction f_ts_hist = nullptr, f_ts_scan = nullptr, f_ts_scatter = nullptr, f_ts_sort = nullptr;
     CUfunction f_setup = nullptr, f_init = nullptr, f_init_boom = nullptr, f_run[ZZ_NKERN] = {}, f_export = nullptr, f_grid_tail = nullptr;
     CUstream stream = nullptr;
     CUevent ev0 = nullptr, ev1 = nullptr, tev0 = nullptr, tev1 = nullptr;
@@ -182,6 +183,8 @@ struct zzb_run_s {
     DevBuf inbox, inbox_cnt; unsigned int inbox_cap = 0, flag_words = 0; int inbox_grid = 0;
     DevBuf dbgbuf; std::vector<unsigned long long> dbghost;
     int tile_per = 0; unsigned int eval_threads = 0; int inbox_nr = 0;
+    // device-side ordering of the trace (zz_tsort_*): the events of the last execute, sorted, still in HBM
+    DevBuf trace_sorted, ts_work; bool dev_sorted = false; unsigned long long n_sorted = 0; bool host_sort_only = false;
     int setup_lo = 0, setup_hi = 0;    // coordinates whose records this rank sets up (sharded lattice: slab + halo; otherwise all)
     unsigned int wat_next = 0;         // window-attempt numbers tag the inbox entries: never reused by a later run of this handle
     int kidx() const
@@ -263,6 +266,10 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     for (int k = 0; k < ZZ_NKERN; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuModuleGetFunction(&G.f_grid_tail, G.mod, "zz_grid_tail_kernel"));
+    CU(cuModuleGetFunction(&G.f_ts_hist, G.mod, "zz_tsort_hist_kernel"));
+    CU(cuModuleGetFunction(&G.f_ts_scan, G.mod, "zz_tsort_scan_kernel"));
+    CU(cuModuleGetFunction(&G.f_ts_scatter, G.mod, "zz_tsort_scatter_kernel"));
+    CU(cuModuleGetFunction(&G.f_ts_sort, G.mod, "zz_tsort_sort_kernel"));
     CU(cuStreamCreate(&G.stream, CU_STREAM_NON_BLOCKING));
     CU(cuEventCreate(&G.ev0, CU_EVENT_DEFAULT));
     CU(cuEventCreate(&G.ev1, CU_EVENT_DEFAULT));
@@ -609,6 +616,7 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     else if (!strcmp(key, "target_flip_frac")) r->target_flip_frac = value;
     else if (!strcmp(key, "tag_limit")) r->tag_limit = (unsigned int)value;
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
+    else if (!strcmp(key, "host_sort")) r->host_sort_only = value != 0.0;   // order the trace on the host (A/B of the device sort)
     else if (!strcmp(key, "eval_threads")) r->eval_threads = (unsigned int)value;
     else if (!strcmp(key, "schedule")) { r->schedule = value != 0.0; r->grid = G.sm_count * G.blocks_per_sm[r->kidx()]; }
     // switch a sticky run to the strong-bound sampler of src/sparsestickyzz.jl: scalar bound constant c, rule (0 sticky, 1 reversible);
@@ -688,6 +696,7 @@ int32_t zzb_run_reset(zzb_run_t r)
     r->launches += 2;
     r->uploaded = true; r->executed = false; r->fetched = false;
     r->events.clear();
+    r->dev_sorted = false; r->n_sorted = 0;
     return ZZB_OK;
 }
 
@@ -720,6 +729,44 @@ int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* t
         r->have_inputs = true;
     }
     return zzb_run_reset(r);
+}
+
+struct ZzTsortHost {   // same layout as ZzTsort in zz_kernels.cu
+    CUdeviceptr in, out; unsigned long long n; double tmin, scale; unsigned int nb; unsigned int pad;
+    CUdeviceptr cnt, base, fill, ovf;
+};
+
+// Order the n records of the device trace buffer by (time, coordinate) on the device (markers dropped); true in *ok when the
+// sorted events are in r->trace_sorted, false when a time bucket overflowed (caller falls back to the host sort).
+static int32_t device_sort_trace(zzb_run_s* r, unsigned long long n, double tmin, double tmax, bool* ok)
+{
+    *ok = false;
+    const unsigned int nb = (unsigned int)std::max<unsigned long long>(1, n / 128);
+    int32_t st = ZZB_OK;
+    if (r->trace_sorted.n < (size_t)n * sizeof(zzb_event)) st = r->trace_sorted.alloc((size_t)r->trace_cap * sizeof(zzb_event));
+    const size_t wbytes = ((size_t)3 * nb + 2) * 4;
+    if (!st && r->ts_work.n < wbytes) st = r->ts_work.alloc(wbytes + 4096);
+    if (st) return ZZB_OK;   // no memory for the second buffer: the host sorts
+    CU(cuMemsetD8Async(r->ts_work.p, 0, wbytes, G.stream));
+    ZzTsortHost Q;
+    Q.in = r->trace.p; Q.out = r->trace_sorted.p; Q.n = n; Q.tmin = tmin;
+    Q.scale = (tmax > tmin) ? (double)nb / (tmax - tmin) : 0.0; Q.nb = nb; Q.pad = 0;
+    Q.cnt = r->ts_work.p; Q.base = r->ts_work.p + (size_t)nb * 4; Q.fill = r->ts_work.p + ((size_t)2 * nb + 1) * 4; Q.ovf = r->ts_work.p + ((size_t)3 * nb + 1) * 4;
+    void* a[] = { &Q };
+    const unsigned grid = (unsigned)std::min<unsigned long long>((n + ZZ_BLOCK - 1) / ZZ_BLOCK, (unsigned long long)G.sm_count * 16);
+    CU(cuLaunchKernel(G.f_ts_hist, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a, nullptr));
+    CU(cuLaunchKernel(G.f_ts_scan, 1, 1, 1, 1024, 1, 1, 0, G.stream, a, nullptr));
+    CU(cuLaunchKernel(G.f_ts_scatter, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a, nullptr));
+    CU(cuLaunchKernel(G.f_ts_sort, std::min<unsigned>(nb, (unsigned)G.sm_count * 8), 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a, nullptr));
+    r->launches += 4;
+    unsigned int tail[2] = { 0, 0 };   // base[nb] is followed by fill[]; ovf is read separately
+    CU(cuMemcpyDtoHAsync(&tail[0], Q.base + (size_t)nb * 4, 4, G.stream));
+    CU(cuMemcpyDtoHAsync(&tail[1], Q.ovf, 4, G.stream));
+    CU(cuStreamSynchronize(G.stream));
+    if (tail[1]) return ZZB_OK;
+    r->n_sorted = tail[0];
+    *ok = true;
+    return ZZB_OK;
 }
 
 // sort every window segment (records between two i == 0 markers) by (time, coordinate) and drop the markers
@@ -783,6 +830,15 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
             P.dbgbuf = r->dbgbuf.as<unsigned long long>(); P.dbg_window = (unsigned int)atoi(dw);
         } else P.dbgbuf = nullptr;
     }
+    // events of an earlier execute that are still on the device (sorted) join the host vector first
+    if (r->dev_sorted && r->n_sorted) {
+        const size_t at = r->events.size();
+        r->events.resize(at + (size_t)r->n_sorted);
+        CU(cuMemcpyDtoH(r->events.data() + at, r->trace_sorted.p, (size_t)r->n_sorted * sizeof(zzb_event)));
+    }
+    r->dev_sorted = false; r->n_sorted = 0;
+    const double t_front0 = r->executed ? r->hc.ctl.F : r->t0;   // every event of this call is at or after the current frontier
+    bool drained = !r->events.empty() || r->host_sort_only;      // (then the host vector stays the one home of the trace)
     for (;;) {
         CU(cuMemsetD8Async(r->ctl.p, 0, 8, G.stream));  // barrier counter
         void* args[] = { &P };
@@ -800,7 +856,22 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
         if (hc.trace_full) return fail(ZZB_E_INTERNAL, "trace record dropped (internal protocol error)");
         if (hc.viol) break;
         if (hc.ctl.phase == ZZ_PH_FAIL) return fail(ZZB_E_INTERNAL, "window controller failed");
+        const bool last = (hc.ctl.phase == ZZ_PH_DONE) || (r->max_windows && !hc.need_drain);
+        if (P.record_trace && last && !drained && !hc.need_drain && hc.trace_len) {
+            // everything this call produced is still in HBM: order it there; zzb_trace_copy reads the sorted buffer directly
+            bool ok = false;
+            int32_t st = device_sort_trace(r, hc.trace_len, std::min(t_front0, hc.ctl.F), hc.ctl.F, &ok);
+            if (st) return st;
+            if (ok) {
+                r->dev_sorted = true;
+                ZzDevCtl z = hc; z.trace_len = 0; z.need_drain = 0;
+                CU(cuMemcpyHtoD(r->ctl.p, &z, sizeof z));
+                r->hc.trace_len = 0;
+                break;
+            }
+        }
         if (P.record_trace && (hc.need_drain || hc.ctl.phase == ZZ_PH_DONE || r->max_windows)) {
+            drained = true;
             if (hc.need_drain && hc.trace_len == 0) return fail(ZZB_E_TRACE, "trace buffer (%llu records) too small for one window", r->trace_cap);
             std::vector<zzb_event> chunk((size_t)hc.trace_len);
             if (hc.trace_len) CU(cuMemcpyDtoH(chunk.data(), r->trace.p, (size_t)hc.trace_len * sizeof(zzb_event)));
@@ -994,7 +1065,7 @@ int32_t zzb_trace_len(zzb_run_t r, int64_t* n)
         *n = (int64_t)r->hc.nacc;
         return ZZB_OK;
     }
-    *n = (int64_t)r->events.size();
+    *n = (int64_t)(r->events.size() + (r->dev_sorted ? (size_t)r->n_sorted : 0));
     return ZZB_OK;
 }
 
@@ -1002,8 +1073,18 @@ int32_t zzb_trace_copy(zzb_run_t r, zzb_event* dst, int64_t first, int64_t count
 {
     if (!r || !dst) return fail(ZZB_E_ARG, "null argument");
     if (r->flags & ZZB_FLAG_NO_TRACE) return fail(ZZB_E_ARG, "run was created with ZZB_FLAG_NO_TRACE");
-    if (first < 0 || count < 0 || (size_t)(first + count) > r->events.size()) return fail(ZZB_E_ARG, "trace range out of bounds");
-    memcpy(dst, r->events.data() + first, (size_t)count * sizeof(zzb_event));
+    const size_t nh = r->events.size(), nd = r->dev_sorted ? (size_t)r->n_sorted : 0;
+    if (first < 0 || count < 0 || (size_t)(first + count) > nh + nd) return fail(ZZB_E_ARG, "trace range out of bounds");
+    size_t f = (size_t)first, c = (size_t)count;
+    if (f < nh) {   // part that was drained to the host during the run
+        const size_t k = std::min(c, nh - f);
+        memcpy(dst, r->events.data() + f, k * sizeof(zzb_event));
+        dst += k; f += k; c -= k;
+    }
+    if (c) {        // part ordered on the device: straight from HBM into the caller's buffer
+        CtxGuard cg;
+        CU(cuMemcpyDtoH(dst, r->trace_sorted.p + (f - nh) * sizeof(zzb_event), c * sizeof(zzb_event)));
+    }
     return ZZB_OK;
 }
 
@@ -1012,6 +1093,7 @@ int32_t zzb_trace_clear(zzb_run_t r)
 {
     if (!r) return fail(ZZB_E_ARG, "null argument");
     r->events.clear();
+    r->dev_sorted = false; r->n_sorted = 0;
     return ZZB_OK;
 }
 
