@@ -157,6 +157,10 @@ int32_t zzb_trace_sums(zzb_run_t r, double* s1, double* s2);        /* the unsca
 int32_t zzb_run_discretize(zzb_run_t r, double dt, int64_t n_rows);
 int32_t zzb_run_grid(zzb_run_t r, double* xs, int64_t first_row, int64_t n, int64_t* valid_rows);
 int32_t zzb_run_error_info(zzb_run_t r, int64_t* i, double* t, double* l, double* lb);  /* after ZZB_E_BOUND */
+/* Test probe: the DEVICE build of the scalar primitives the kernels and the oracle share (csrc/zz_math.h) on host-supplied
+ * arguments -- kind 0 log(x), 1 exp(x), 2 sincos(x) -> (o1, o2), 3 poisson_time(a = x, b = y, u = z) (src/poissontime.jl:8-30),
+ * 4 the counter-based uniforms u(seed = (x[0], y[0]) bit patterns, coordinate k, counter k ^ 0x5bd1), k = 0 .. n-1. */
+int32_t zzb_math_probe(int32_t kind, int64_t n, const double* x, const double* y, const double* z, double* o1, double* o2);
 int32_t zzb_run_free(zzb_run_t r);
 
 #ifdef __cplusplus

@@ -136,6 +136,18 @@ double zzo_poisson_time3(double a, double b, double c, double u)
 double zzo_log(double x) { return zz_log(x); }
 double zzo_u01(uint64_t s0, uint64_t s1, uint64_t i, uint64_t k) { return zz_u01(s0, s1, i, k); }
 
+/* HOST build of the shared primitives on arrays: the counterpart of zzb_math_probe (device build), same kinds */
+void zzo_math_probe(int kind, int64_t n, const double* x, const double* y, const double* z, double* o1, double* o2)
+{
+    for (int64_t k = 0; k < n; ++k) {
+        if (kind == 0) o1[k] = zz_log(x[k]);
+        else if (kind == 1) o1[k] = zz_exp(x[k]);
+        else if (kind == 2) zz_sincos(x[k], &o1[k], &o2[k]);
+        else if (kind == 3) o1[k] = zz_poisson_time(x[k], y[k], z[k]);
+        else o1[k] = zz_u01(zz_d2u(x[0]), zz_d2u(y[0]), (uint64_t)k, (uint64_t)(k ^ 0x5bd1));
+    }
+}
+
 /* ---- xoroshiro128+ (RandomNumbers.jl Xorshifts.Xoroshiro128Plus; restated, unpinned) ------- */
 typedef struct { uint64_t x, y; } xoro;
 static inline uint64_t rotl64(uint64_t v, int k) { return (v << k) | (v >> (64 - k)); }

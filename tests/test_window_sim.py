@@ -124,3 +124,18 @@ def test_random_campaign_emulation_equals_oracle(zzb):
     import fuzz_cases
     bad, nbound = fuzz_cases.run_cases(zzb, 150, 4, sim=True)
     assert bad == 0
+
+
+def test_bound_matrix_without_stored_diagonal_is_refused(zzb):
+    """The reference reschedules i after its own flip only because i is in G1[i] (src/sfact.jl:131-135,170); the graph builder
+    shared by the product library and this emulation (csrc/zz_host_graph.h) refuses a sampler matrix whose column lacks the
+    diagonal entry instead of silently sampling a different process (the C-ABI maps the message to ZZB_E_GRAPH)."""
+    import scipy.sparse as sp
+    d = 6
+    G = zzb.CSC.from_scipy(sp.diags([np.full(d, 2.0), -np.ones(d - 1), -np.ones(d - 1)], [0, 1, -1]).tocsc())
+    offdiag = sp.diags([-np.ones(d - 1), -np.ones(d - 1)], [1, -1]).tocsc()
+    Gb = zzb.CSC.from_scipy(offdiag)
+    x0, th0, c = np.zeros(d), np.ones(d), np.ones(d)
+    with pytest.raises(RuntimeError, match="status 4"):
+        O.window_sim(G, Gb, 0.0, x0, th0, 1.0, c)
+    O.window_sim(G, G, 0.0, x0, th0, 1.0, c)   # with the diagonal stored it runs

@@ -232,17 +232,34 @@ def _discretize_flow(trace: FactTrace, dt: float):
     return np.array(ts), np.array(xs)
 
 
+def _previous_per_coordinate(tr: FactTrace):
+    """For every event of a time-ordered trace: the time and position of the SAME coordinate's previous event (or its initial
+    state).  Vectorised (one stable sort by coordinate) -- no Python loop over events."""
+    ev = tr.events
+    i = ev["i"].astype(np.int64) - 1
+    order = np.argsort(i, kind="stable")
+    si, st, sx = i[order], ev["t"][order], ev["x"][order]
+    first = np.r_[True, si[1:] != si[:-1]] if len(si) else np.zeros(0, bool)
+    pt = np.r_[tr.t0, st[:-1]] if len(si) else st
+    px = np.r_[0.0, sx[:-1]] if len(si) else sx
+    pt = np.where(first, tr.t0, pt)
+    px = np.where(first, tr.x0[si] if len(si) else px, px)
+    t_prev, x_prev = np.empty_like(pt), np.empty_like(px)
+    t_prev[order], x_prev[order] = pt, px
+    return i, t_prev, x_prev
+
+
 def mean(trace: FactTrace):
-    """``Statistics.mean(::Trace)`` (src/trace.jl:182-200)."""
-    x = trace.x0.copy()
-    y = np.zeros_like(x)
-    T = trace.events["t"][-1]
-    t = np.full(len(x), trace.t0)
+    """``Statistics.mean(::Trace)`` (src/trace.jl:182-200).  The per-coordinate sums run in event order (np.add.at is
+    unbuffered and sequential), i.e. with the roundings of the reference's loop."""
+    ev = trace.events
+    y = np.zeros(len(trace.x0))
+    if not len(ev):
+        return y
+    T = ev["t"][-1]
     scale = 1 / (2 * T)
-    for t2, i, xi, _ in trace.events:
-        y[i - 1] += (x[i - 1] + xi) * (t2 - t[i - 1]) * scale
-        t[i - 1] = t2
-        x[i - 1] = xi
+    i, t_prev, x_prev = _previous_per_coordinate(trace)
+    np.add.at(y, i, (x_prev + ev["x"]) * (ev["t"] - t_prev) * scale)
     return y
 
 
@@ -529,6 +546,8 @@ def sspdmp(grad, t0, x0, theta0, T, c, *rest, seed=None, record_trace=True, tune
     if rest and (rest[0] is None or isinstance(rest[0], (All, Matched))):
         rest.pop(0)
     F, kappa = rest[0], rest[1]
+    if not isinstance(F, ZigZag):   # the reference's method is sspdmp(..., F::ZigZag, kappa, ...) (src/ss_fact.jl:159)
+        raise TypeError("sspdmp: the sticky sampler is defined for F::ZigZag only (src/ss_fact.jl:159), got %s" % type(F).__name__)
     prob, own = _as_problem(grad, F)
     if seed is None:
         seed = (secrets.randbits(64), secrets.randbits(64))
@@ -567,11 +586,25 @@ class FactSampler:
         self.seed = seed if seed is not None else (secrets.randbits(64), secrets.randbits(64))
         self.windows_per_pull = int(windows_per_pull)
 
-    def __iter__(self):
-        t0, (x0, th0) = self.u0
+    def _open(self):
+        """Problem and run for this sampler: the same dispatch as spdmp (FactBoomerang dynamics, LocalBound bounds)."""
+        F = self.F
         local_bound = isinstance(self.c, LocalBound)
-        prob, own = _as_problem(self.grad, self.F)
-        run = Run(prob, record_trace=True, local_bound=local_bound)
+        if local_bound and isinstance(self.grad, LogisticSubsampled):
+            raise NotImplementedError("LocalBound with the logistic target is not implemented on the device path")
+        if local_bound and isinstance(F, FactBoomerang):
+            raise NotImplementedError("LocalBound with FactBoomerang is not implemented on the device path")
+        if local_bound and isinstance(self.grad, GaussianPotential):   # the bound comes from the target (src/local.jl:2-6)
+            F = ZigZag(self.grad.Gamma, np.zeros(self.grad.Gamma.n), F.sigma, lambdaref=F.lambdaref, rho=F.rho)
+        prob, own = _as_problem(self.grad, F)
+        run = Run(prob, record_trace=True, local_bound=local_bound, boomerang=F if isinstance(F, FactBoomerang) else None)
+        return prob, own, run, local_bound
+
+    def chunks(self):
+        """The same stream as iteration, but handed over as numpy record arrays (EVENT_DTYPE, time-ordered), one per pull of
+        `windows_per_pull` windows: no Python object per event."""
+        t0, (x0, th0) = self.u0
+        prob, own, run, local_bound = self._open()
         try:
             run.set(max_windows=self.windows_per_pull)
             run.upload(t0, x0, th0, self.c.c if local_bound else self.c, seed=self.seed, adapt=self.adapt, factor=self.factor)
@@ -579,53 +612,62 @@ class FactSampler:
                 run.execute(np.inf)          # a bounded slice of windows; the controller state persists on the device
                 ev = run.events()
                 run.clear_events()
-                for e in ev:
-                    yield float(e["t"]), (float(e["t"]), int(e["i"]), float(e["x"]), float(e["theta"]))
+                yield ev
         finally:
             run.close()
             if own:
                 prob.close()
+
+    def __iter__(self):
+        for ev in self.chunks():
+            for t, i, x, th in zip(ev["t"].tolist(), ev["i"].tolist(), ev["x"].tolist(), ev["theta"].tolist()):
+                yield t, (t, i, x, th)
 
 
 def trace(FS: FactSampler, T):
     """``trace(FS, T)`` (src/sfactiter.jl:66-79), including its quirk: the first event of the iteration is consumed and
     not stored; events with t > T end the collection."""
     t0, (x0, th0) = FS.u0
-    it = iter(FS)
-    next(it)
-    out = []
-    for t, ev in it:
-        if t > T:
+    parts, first = [], True
+    gen = FS.chunks()
+    for ev in gen:
+        if first and len(ev):
+            ev, first = ev[1:], False          # the first event is consumed, not stored (sfactiter.jl:68-70)
+        k = int(np.searchsorted(ev["t"], T, side="right"))   # events are time-ordered: stop at the first one with t > T
+        parts.append(ev[:k])
+        if k < len(ev):
             break
-        out.append(ev)
-    it.close()
-    return FactTrace(FS.F, t0, x0, th0, np.array(out, dtype=EVENT_DTYPE))
+    gen.close()
+    return FactTrace(FS.F, t0, x0, th0, np.concatenate(parts) if parts else np.empty(0, dtype=EVENT_DTYPE))
 
 
 def cummean(tr: FactTrace):
-    """``cummean(trace)`` (src/trace.jl:203-225): per coordinate the running time-average at each of its events."""
-    x = tr.x0.copy()
-    y = np.zeros_like(x)
-    t = np.full(len(x), tr.t0)
-    ys = [([tr.t0], [xi]) for xi in x]
-    for t2, i, xi, _ in tr.events:
-        y[i - 1] += (x[i - 1] + xi) * (t2 - t[i - 1])
-        t[i - 1] = t2
-        x[i - 1] = xi
-        ys[i - 1][0].append(t2)
-        ys[i - 1][1].append(y[i - 1] / (2 * t2))
-    return ys
+    """``cummean(trace)`` (src/trace.jl:203-225): per coordinate the running time-average at each of its events, as a list of
+    ``(times, values)`` pairs starting with ``(t0, x0_i)``."""
+    ev = tr.events
+    d = len(tr.x0)
+    i, t_prev, x_prev = _previous_per_coordinate(tr)
+    term = (x_prev + ev["x"]) * (ev["t"] - t_prev)
+    order = np.argsort(i, kind="stable")
+    si = i[order]
+    bounds = np.searchsorted(si, np.arange(d + 1))
+    out = []
+    for k in range(d):
+        sel = order[bounds[k]:bounds[k + 1]]
+        tt = ev["t"][sel]
+        run = np.cumsum(term[sel])              # sequential partial sums, as the reference's y[i] += ...
+        out.append((np.r_[tr.t0, tt], np.r_[tr.x0[k], run / (2 * tt)]))
+    return out
 
 
 def inclusion_prob(tr: FactTrace):
     """``inclusion_prob(trace)`` (src/trace.jl:161-178): fraction of time a coordinate is away from 0 (sticky samplers).
     Julia parses ``x[i] != 0 | xi != 0`` as ``x[i] != (0 | xi) != 0``; the evident intent (either end non-zero) is used."""
-    x = tr.x0.copy()
-    y = np.zeros_like(x)
-    T = tr.events["t"][-1]
-    t = np.full(len(x), tr.t0)
-    for t2, i, xi, _ in tr.events:
-        y[i - 1] += float((x[i - 1] != 0) or (xi != 0)) * (t2 - t[i - 1]) / T
-        t[i - 1] = t2
-        x[i - 1] = xi
+    ev = tr.events
+    y = np.zeros(len(tr.x0))
+    if not len(ev):
+        return y
+    T = ev["t"][-1]
+    i, t_prev, x_prev = _previous_per_coordinate(tr)
+    np.add.at(y, i, ((x_prev != 0) | (ev["x"] != 0)).astype(np.float64) * (ev["t"] - t_prev) / T)
     return y

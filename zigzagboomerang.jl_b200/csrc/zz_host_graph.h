@@ -89,6 +89,14 @@ static inline std::string zz_build_graph(ZzHostGraph& G, int64_t d, const int64_
     if (!e.empty()) return e;
     e = check(bcp, brv, "bound");
     if (!e.empty()) return e;
+    // The reference reschedules coordinate i after its own accepted flip only because i is in G1[i] = rows of column i of
+    // Z.Gamma (src/sfact.jl:131-135,170); without a stored diagonal entry it would spin on the same queue time for ever.  The
+    // device always reschedules the flipping coordinate, so such a matrix would silently sample a different process: refuse it.
+    for (int64_t j = 0; j < d; ++j) {
+        bool diag = false;
+        for (int64_t p = bcp[j] - 1; p < bcp[j + 1] - 1 && !diag; ++p) diag = (brv[p] == j + 1);
+        if (!diag) return "bound: column " + std::to_string(j + 1) + " of Z.Gamma has no stored diagonal entry (i must be in G1[i], src/sfact.jl:131-135)";
+    }
 
     // same matrix? (pattern and values identical, no linear term, mu == 0)
     bool same = (tcp[d] == bcp[d]);

@@ -568,6 +568,23 @@ zz_export_kernel(const ZzParams P, double* __restrict__ t, double* __restrict__ 
     }
 }
 
+// Test probe: the scalar primitives of zz_math.h evaluated ON THE DEVICE for host-supplied arguments, so that the tests can pin
+// them against libm and against the host build of the same header (oracle and kernels share these routines: an error in one of
+// them would cancel in every device == oracle comparison).  kind 0: log(x); 1: exp(x); 2: sincos(x) -> (o1, o2);
+// 3: poisson_time(a = x, b = y, u = z); 4: u01(seed = (x, y) bit patterns, coordinate = k, counter = k ^ 0x5bd1)
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK)
+zz_math_probe_kernel(int kind, long long n, const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ z,
+                     double* __restrict__ o1, double* __restrict__ o2)
+{
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        if (kind == 0) o1[k] = zz_log(x[k]);
+        else if (kind == 1) o1[k] = zz_exp(x[k]);
+        else if (kind == 2) { double sn, cs; zz_sincos(x[k], &sn, &cs); o1[k] = sn; o2[k] = cs; }
+        else if (kind == 3) o1[k] = zz_poisson_time(x[k], y[k], z[k]);
+        else o1[k] = zz_u01(zz_d2u(x[0]), zz_d2u(y[0]), (uint64_t)k, (uint64_t)(k ^ 0x5bd1));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // Device-side ordering of the trace (src/trace.jl:38 is a time-ordered vector; upstream's own parallel samplers sort too,
 // src/asynchzz.jl:131, src/parallel.jl:168).  The commit appends the events of a window in arbitrary order; before the host

@@ -94,6 +94,7 @@ struct Global {
     CUcontext ctx = nullptr;
     CUmodule mod = nullptr;
     CUfunction f_init_strong = nullptr;
+    CUfunction f_math_probe = nullptr;
     CUfunction f_ts_hist = nullptr, f_ts_scan = nullptr, f_ts_scatter = nullptr, f_ts_sort = nullptr;
     CUfunction f_setup = nullptr, f_init = nullptr, f_init_boom = nullptr, f_run[ZZ_NKERN] = {}, f_export = nullptr, f_grid_tail = nullptr;
     CUstream stream = nullptr;
@@ -266,6 +267,7 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     for (int k = 0; k < ZZ_NKERN; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuModuleGetFunction(&G.f_grid_tail, G.mod, "zz_grid_tail_kernel"));
+    CU(cuModuleGetFunction(&G.f_math_probe, G.mod, "zz_math_probe_kernel"));
     CU(cuModuleGetFunction(&G.f_ts_hist, G.mod, "zz_tsort_hist_kernel"));
     CU(cuModuleGetFunction(&G.f_ts_scan, G.mod, "zz_tsort_scan_kernel"));
     CU(cuModuleGetFunction(&G.f_ts_scatter, G.mod, "zz_tsort_scatter_kernel"));
@@ -1159,6 +1161,32 @@ int32_t zzb_run_grid(zzb_run_t r, double* xs, int64_t first_row, int64_t n, int6
         while (k > 0 && r->t0 + (double)(k - 1) * r->grid_dt > tend) --k;
         *valid_rows = k;
     }
+    return ZZB_OK;
+}
+
+// Test probe (tests/test_gpu_math.py): the device build of the scalar primitives of zz_math.h on host-supplied arguments.
+int32_t zzb_math_probe(int32_t kind, int64_t n, const double* x, const double* y, const double* z, double* o1, double* o2)
+{
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (n < 1 || !x || !o1 || kind < 0 || kind > 4) return fail(ZZB_E_ARG, "bad argument");
+    CtxGuard cg;
+    const size_t nb = (size_t)n * 8, nin = (kind == 4) ? 8 : nb;
+    DevBuf dx, dy, dz, d1, d2;
+    int32_t st = dx.alloc(nin);
+    if (!st) st = dy.alloc(nin);
+    if (!st) st = dz.alloc(nin);
+    if (!st) st = d1.alloc(nb);
+    if (!st) st = d2.alloc(nb);
+    if (st) return st;
+    CU(cuMemcpyHtoD(dx.p, x, nin));
+    if (y) CU(cuMemcpyHtoD(dy.p, y, nin));
+    if (z) CU(cuMemcpyHtoD(dz.p, z, nin));
+    int k = kind; long long nn = n;
+    void* a[] = { &k, &nn, &dx.p, &dy.p, &dz.p, &d1.p, &d2.p };
+    CU(cuLaunchKernel(G.f_math_probe, (unsigned)G.sm_count * 8, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a, nullptr));
+    CU(cuStreamSynchronize(G.stream));
+    CU(cuMemcpyDtoH(o1, d1.p, nb));
+    if (o2) CU(cuMemcpyDtoH(o2, d2.p, nb));
     return ZZB_OK;
 }
 

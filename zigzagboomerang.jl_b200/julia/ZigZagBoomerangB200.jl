@@ -151,6 +151,8 @@ function device_run(kind::Symbol, ∇ϕ::Union{GaussianPotential,LogisticSubsamp
                    UInt32, Ref{Ptr{Cvoid}}), prob[], t0, x0v, θ0v, T, cv, sd, adapt, factor, flags, run)
         end
         if st != 0
+            # ZZB_E_BOUND still hands back a run (partial trace, error details): free it too before throwing
+            run[] != C_NULL && ccall((:zzb_run_free, libzzb200), Int32, (Ptr{Cvoid},), run[])
             ccall((:zzb_problem_free, libzzb200), Int32, (Ptr{Cvoid},), prob[])
             check(st)
         end
@@ -158,8 +160,9 @@ function device_run(kind::Symbol, ∇ϕ::Union{GaussianPotential,LogisticSubsamp
     try
         n = Ref{Int64}(0)
         check(ccall((:zzb_trace_len, libzzb200), Int32, (Ptr{Cvoid}, Ref{Int64}), run[], n))
-        Ξ = Trace(t0, x0, θ0, F)                       # FactTrace with Tuple{Float64,Int,Float64,Float64}[] events
-        resize!(Ξ.events, n[])
+        # the library writes 32-byte (Float64, Int64, Float64, Float64) records: build the trace with exactly that element type,
+        # whatever the types of t0 (e.g. an Int) and of x0 / θ0 (e.g. Float32) are
+        Ξ = ZigZagBoomerang.FactTrace(F, Float64(t0), x0v, θ0v, Vector{Tuple{Float64,Int,Float64,Float64}}(undef, n[]))
         check(ccall((:zzb_trace_copy, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64), run[], Ξ.events, 0, n[]))
         t, x, θ = similar(x0v), similar(x0v), similar(x0v)
         check(ccall((:zzb_run_final_state, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
@@ -179,6 +182,7 @@ const Nbhd = Union{ZigZagBoomerang.All,ZigZagBoomerang.Matched}
 function spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G::Nbhd, F::ZigZag, args...;
                factor = 1.8, adapt = false, adaptscale = false, progress = false, progress_stops = 20, seed = Seed())
     F.λref == 0 || error("ZigZag refreshments (λref > 0) are not implemented on the device path")
+    adaptscale && error("adaptscale = true is not implemented on the device path")
     Ξ, u, an, cv = device_run(:zigzag, ∇ϕ, t0, x0, θ0, T, c, F; factor = factor, adapt = adapt, seed = seed)
     c .= cv                                            # adapted bounds, like the in-place `adapt!` of the reference
     Ξ, u, an, c
@@ -187,6 +191,7 @@ end
 # spdmp / pdmp, F::FactBoomerang (same generic function upstream; flow src/sfact.jl:29-48, rate/bound src/fact_samplers.jl:37-39,58-65)
 function spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G::Nbhd, F::FactBoomerang, args...;
                factor = 1.8, adapt = false, adaptscale = false, progress = false, progress_stops = 20, seed = Seed())
+    adaptscale && error("adaptscale = true is not implemented on the device path")
     Ξ, u, an, cv = device_run(:boomerang, ∇ϕ, t0, x0, θ0, T, c, F; factor = factor, adapt = adapt, seed = seed)
     c .= cv
     Ξ, u, an, c
@@ -199,6 +204,19 @@ function spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, C::LocalBound, G::Nbhd,
     C.c .= cv
     Ξ, u, an, C
 end
+
+# Without G: the generated spdmp / pdmp(∇ϕ::GaussianPotential, ..., c, F::ZigZag, ...) methods below are more specific than the
+# reference's spdmp / pdmp(∇ϕ, ..., C::LocalBound, F::Union{ZigZag,FactBoomerang,JointFlow}, ...) (src/local.jl:148-149) in
+# arguments 1 and 7 but less specific in argument 6: state the intersection explicitly so that the documented drop-in call
+# spdmp(GaussianPotential(Γ), t0, x0, θ0, T, LocalBound(c), Z) is not ambiguous.
+spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, C::LocalBound, F::ZigZag, args...; kargs...) =
+    spdmp(∇ϕ, t0, x0, θ0, T, C, ZigZagBoomerang.Matched(), F, args...; kargs...)
+pdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, C::LocalBound, F::ZigZag, args...; kargs...) =
+    spdmp(∇ϕ, t0, x0, θ0, T, C, ZigZagBoomerang.All(), F, args...; kargs...)
+spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, C::LocalBound, F::FactBoomerang, args...; kargs...) =
+    error("LocalBound with FactBoomerang is not implemented on the device path")
+pdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, C::LocalBound, F::FactBoomerang, args...; kargs...) =
+    error("LocalBound with FactBoomerang is not implemented on the device path")
 
 # sspdmp(∇ϕ, t0, x0, θ0, T, c, [G,] F::ZigZag, κ, ...) (src/ss_fact.jl:159-217); acc is the scalar count of reflections
 function sspdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G, F::ZigZag, κ, args...;
