@@ -120,6 +120,13 @@ int32_t zzb_spdmp_boomerang_run(zzb_problem_t p, double t0, const double* x0, co
                                 const double* sigma, double lambdaref, double rho, const uint64_t* seed, int32_t adapt,
                                 double factor, uint32_t flags, zzb_run_t* out);
 
+/* sspdmp3 / sparsestickyzz (src/sparsestickyzz.jl:405-422,192-257): the strong-bound sparse sticky ZigZag of BASELINE config 4.
+ * One bound constant c (SparseStickyUpperBounds :127-142, adapt = false), one thaw rate kappa (StickyBarriers), rule 0 = :sticky,
+ * 1 = :reversible.  Coordinates with x0 == 0 start frozen (sparsestickystate :10-12); theta0 = velocities of the others; time
+ * starts at 0.  Trace records as for zzb_sspdmp_run (theta == 0: the coordinate froze). */
+int32_t zzb_sspdmp3_run(zzb_problem_t p, const double* x0, const double* theta0, double T, double c, double kappa, int32_t rule,
+                        const uint64_t* seed, uint32_t flags, zzb_run_t* out);
+
 /* Staged form (what zzb_spdmp_run is made of); lets a caller keep inputs resident in HBM and time the kernel alone. */
 int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_events, zzb_run_t* out);
 int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* theta0, const double* c,

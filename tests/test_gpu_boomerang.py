@@ -72,3 +72,32 @@ def test_boomerang_bound_violation_and_argument_errors(gpu):
         run_gpu(gpu, G, Zg, sigma, None, None, x0, th0, 500.0, 1e-3 * c, 0.3, 0.0, seed=(1, 1))
     with pytest.raises(gpu.ZZBError, match="lambdaref > 0"):
         run_gpu(gpu, G, Zg, sigma, None, None, x0, th0, 5.0, c, 0.0, 0.0, seed=(1, 1))
+
+
+def test_fact_sampler_dispatches_on_boomerang_and_local_bound(gpu):
+    """FactSampler(grad, u0, c, F) takes F::Union{ZigZag,FactBoomerang} (src/sfactiter.jl:5-40): with a FactBoomerang the pulled
+    events are the Boomerang's (not a ZigZag run with F.Gamma as the bound); with LocalBound(c) they are those of
+    spdmp(..., LocalBound(c), Z).  Same seed => the same events as the one-shot calls."""
+    d, T = 8, 40.0
+    G = gpu.random_spd(d, seed=2)
+    rng = np.random.default_rng(5)
+    Zg, sigma, x0, th0, c = boom_inputs(gpu, G, 1.2, rng)
+    F = gpu.FactBoomerang(Zg, np.zeros(d), 0.7)
+    Xi, _, _, _ = gpu.spdmp(gpu.GaussianPotential(G), 0.0, x0, th0, T, c, F, seed=(3, 9))
+    FS = gpu.FactSampler(gpu.GaussianPotential(G), (0.0, (x0, th0)), c, F, seed=(3, 9), windows_per_pull=3)
+    tr = gpu.trace(FS, T)
+    k = len(tr.events)
+    assert k > 50
+    one = Xi.events[1:1 + k]                 # trace(FS, T) drops the first event (sfactiter.jl:68-70)
+    assert np.array_equal(tr.events["i"], one["i"]) and np.array_equal(tr.events["t"].view(np.uint64), one["t"].view(np.uint64))
+    assert np.array_equal(tr.events["theta"].view(np.uint64), one["theta"].view(np.uint64))
+    # LocalBound through the iterator == LocalBound through spdmp
+    Gl, xl, tl, _ = gpu.gmrf_config(12)
+    Z = gpu.ZigZag(Gl.scaled(0.5), np.zeros(Gl.n))   # (F.Gamma is ignored by LocalBound: the bound comes from the target)
+    cl = np.full(Gl.n, 1.0)
+    Xl, _, _, _ = gpu.spdmp(gpu.GaussianPotential(Gl), 0.0, xl, tl, 3.0, gpu.LocalBound(cl.copy()), Z, seed=(4, 4))
+    trl = gpu.trace(gpu.FactSampler(gpu.GaussianPotential(Gl), (0.0, (xl, tl)), gpu.LocalBound(cl.copy()), Z, seed=(4, 4)), 3.0)
+    kl = len(trl.events)
+    assert kl > 50 and np.array_equal(trl.events["t"].view(np.uint64), Xl.events["t"][1:1 + kl].view(np.uint64))
+    with pytest.raises(TypeError, match="F::ZigZag only"):
+        gpu.sspdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 1.0, c, F, 1.0)

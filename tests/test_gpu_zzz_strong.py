@@ -56,3 +56,21 @@ def test_config4_full_size_timing(gpu):
     O.assert_same_run(ref, got)
     st = got.stats
     print(f"strong-bound config 4: {len(got.events)} events in {got.device_ms:.2f} ms, {st['windows']} windows, {st['passes']} passes")
+
+
+def test_sspdmp3_api_matches_the_contract(gpu):
+    """The reference-shaped call sspdmp3(grad, u0, T, c, nothing, Z, kappa; rule) (src/sparsestickyzz.jl:405-422) through
+    zzb200.sspdmp3: same events as the contract oracle, acc = accepted reflections."""
+    p, kappa, T = 300, 0.4, 40.0
+    G = chain_precision(gpu, p)
+    rng = np.random.default_rng(11)
+    x0 = np.where(rng.random(p) < 0.25, rng.standard_normal(p), 0.0)
+    th0 = rng.choice(np.array([-1.0, 1.0]), p)
+    ref = O.sparsestickyzz(G, x0, th0, T, 2.5, kappa, rule="reversible", seed=(7, 8), ctr=True)
+    Xi, (acc, num), (t, x, th) = gpu.sspdmp3(gpu.GaussianPotential(G), (x0, th0), T, 2.5, None, gpu.ZigZag(G, np.zeros(p)), kappa,
+                                             rule="reversible", seed=(7, 8))
+    assert num == ref.num and acc == int(ref.acc.sum())
+    assert np.array_equal(Xi.events["i"], ref.events["i"])
+    for f in ("t", "x", "theta"):
+        assert np.array_equal(Xi.events[f].view(np.uint64), ref.events[f].view(np.uint64))
+    assert np.array_equal(x.view(np.uint64), ref.x.view(np.uint64))

@@ -571,6 +571,44 @@ def sspdmp(grad, t0, x0, theta0, T, c, *rest, seed=None, record_trace=True, tune
             prob.close()
 
 
+def sspdmp3(grad, u0, T, c, G, Z, kappa, *args, rule="reversible", adapt=False, factor=1.5, seed=None, record_trace=True, tune=None,
+            clusteralpha=1.0):
+    """``sspdmp3(grad, u0, T, c, nothing, Z, kappa, args...; adapt=false, factor=1.5, rule=:reversible, clusterα=1.0)`` =
+    ``trace, acc, uT`` (src/sparsestickyzz.jl:405-422): the strong-bound sparse sticky ZigZag -- one bound constant ``c`` valid
+    for ``1/c`` and then renewed (:136-142), a reflection reschedules nobody else, coordinates stick at 0 and thaw at rate
+    ``kappa`` each.  ``u0 = (x0, theta0)``: coordinates with ``x0 == 0`` start frozen (``sparsestickystate``, :10-12; the
+    reference draws the velocities of the others from the global RNG -- here they are an argument).  Returns
+    ``trace, (acc, num), (t, x, theta)``; `acc` = accepted reflections.  Not on the device path: ``adapt``, ``clusterα < 1``."""
+    if adapt:
+        raise NotImplementedError("sspdmp3(...; adapt=true) is not implemented on the device path")
+    if clusteralpha != 1.0:
+        raise NotImplementedError("sspdmp3(...; clusterα < 1) is not implemented on the device path")
+    if not isinstance(Z, ZigZag):
+        raise TypeError("sspdmp3: Z must be a ZigZag (its Gamma gives the dependency structure, src/sparsestickyzz.jl:407)")
+    x0, th0 = u0
+    prob, own = _as_problem(grad, Z)
+    if seed is None:
+        seed = (secrets.randbits(64), secrets.randbits(64))
+    d = prob.d
+    run = Run(prob, record_trace=record_trace, kappa=np.full(d, float(kappa)))
+    try:
+        run.set(strong_c=float(c), strong_rule={"sticky": 0, "reversible": 1}[rule], **(tune or {}))
+        run.upload(0.0, x0, th0, np.full(d, float(c)), seed=seed)
+        run.execute(T)
+        t, x, th, _ = run.final_state()
+        acc, num = run.counts()
+        ev = run.events() if record_trace else np.empty(0, dtype=EVENT_DTYPE)
+        Xi = FactTrace(Z, 0.0, f8(x0), np.where(f8(x0) != 0.0, f8(th0), 0.0), ev)
+        Xi.stats = run.stats()
+        Xi.device_ms = run.device_ms
+        Xi.acc_per_coordinate = acc
+        return Xi, (int(acc.sum()), num), (t, x, th)
+    finally:
+        run.close()
+        if own:
+            prob.close()
+
+
 class FactSampler:
     """``FactSampler(grad, u0, c, [G,] F; factor=1.8, adapt=false, seed)`` with ``u0 = (t0, (x0, theta0))`` -- the pull-style
     interface of src/sfactiter.jl:5-64.  Iterating yields ``(t, (t, i, x_i, theta_i))`` pairs, one per accepted event, in

@@ -967,6 +967,33 @@ int32_t zzb_sspdmp_run(zzb_problem_t p, double t0, const double* x0, const doubl
     return st;
 }
 
+// sspdmp3 / sparsestickyzz (src/sparsestickyzz.jl:405-422,192-257): the strong-bound sparse sticky ZigZag as the reference runs
+// BASELINE config 4 -- one scalar bound constant c (SparseStickyUpperBounds, :127-142, adapt = false), one thaw rate kappa
+// (StickyBarriers), rule 0 = :sticky / 1 = :reversible; coordinates with x0 == 0 start frozen (sparsestickystate, :10-12),
+// theta0 gives the velocities of the others.  Time starts at 0 like the reference's SparseState.
+int32_t zzb_sspdmp3_run(zzb_problem_t p, const double* x0, const double* theta0, double T, double c, double kappa, int32_t rule,
+                        const uint64_t* seed, uint32_t flags, zzb_run_t* out)
+{
+    if (!out || !x0 || !theta0 || !seed) return fail(ZZB_E_ARG, "null argument");
+    if (!p) return fail(ZZB_E_ARG, "null argument");
+    if (!(c > 0.0) || !(kappa > 0.0) || (rule != 0 && rule != 1)) return fail(ZZB_E_ARG, "sspdmp3 needs c > 0, kappa > 0 and rule 0 (:sticky) or 1 (:reversible)");
+    zzb_run_t r = nullptr;
+    int32_t st = zzb_run_create(p, flags | ZZB_FLAG_STICKY, 0, &r);
+    if (st) return st;
+    const size_t d = (size_t)r->d;
+    std::vector<double> kap(d, kappa), cv(d, c);
+    st = zzb_run_upload_kappa(r, kap.data());
+    if (!st) st = zzb_run_set(r, "strong_c", c);
+    if (!st) st = zzb_run_set(r, "strong_rule", (double)rule);
+    if (!st) st = zzb_run_upload(r, 0.0, x0, theta0, cv.data(), seed, 0, 1.0);
+    if (!st) st = zzb_run_execute(r, T, nullptr);
+    if (st) { zzb_run_free(r); return st; }
+    int32_t st2 = fetch_state(r);
+    if (st2) { zzb_run_free(r); return st2; }
+    *out = r;
+    return ZZB_OK;
+}
+
 int32_t zzb_spdmp_boomerang_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, double* c,
                                 const double* sigma, double lambdaref, double rho, const uint64_t* seed, int32_t adapt,
                                 double factor, uint32_t flags, zzb_run_t* out)

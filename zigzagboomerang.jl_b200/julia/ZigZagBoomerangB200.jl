@@ -12,7 +12,7 @@ module ZigZagBoomerangB200
 using ZigZagBoomerang
 using ZigZagBoomerang: ZigZag, FactBoomerang, LocalBound, FactTrace, Trace, Seed
 using SparseArrays
-import ZigZagBoomerang: spdmp, pdmp, sspdmp
+import ZigZagBoomerang: spdmp, pdmp, sspdmp, sspdmp3
 
 const libzzb200 = get(ENV, "ZZB200_LIB", joinpath(@__DIR__, "..", "libzzb200.so"))
 const cubin = get(ENV, "ZZB200_CUBIN", joinpath(@__DIR__, "..", "zzb200_kernels.cubin"))
@@ -226,6 +226,51 @@ function sspdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G, F::ZigZag, κ, a
     Ξ, u, (sum(acc), num), c
 end
 sspdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F::ZigZag, κ, args...; kargs...) = sspdmp(∇ϕ, t0, x0, θ0, T, c, nothing, F, κ, args...; kargs...)
+
+# sspdmp3(∇ϕ, u0, T, c, nothing, Z, κ, ...; rule) (src/sparsestickyzz.jl:405-422): the strong-bound sparse sticky ZigZag.  u0 is the
+# reference's sparse state (`sparsestickystate(x0)`); its dense image (x0, θ0) is what the library takes -- coordinates at 0
+# start frozen.  Returns trace, (acc, num), (t, x, θ).
+function sspdmp3(∇ϕ::GaussianPotential, u0, T, c, ::Nothing, Z::ZigZag, κ, args...; adapt = false, factor = 1.5, rule = :reversible,
+                 progress = false, progress_stops = 20, clusterα = 1.0, seed = Seed())
+    (adapt || clusterα != 1.0) && error("sspdmp3 options adapt / clusterα < 1 are not implemented on the device path")
+    init()
+    d = length(u0)
+    x0v, θ0v = zeros(d), zeros(d)
+    for (i, ui) in pairs(u0.u)            # SparseState: i => (t, x, θ) for the active coordinates (src/sparsestickyzz.jl:3-16)
+        x0v[i], θ0v[i] = ui[2], ui[3]
+    end
+    Γ = ∇ϕ.Γ
+    prob = Ref{Ptr{Cvoid}}(C_NULL); run = Ref{Ptr{Cvoid}}(C_NULL)
+    h = ∇ϕ.h === nothing ? Ptr{Float64}(C_NULL) : pointer(∇ϕ.h)
+    sd = UInt64[seed[1], seed[2]]
+    GC.@preserve Γ x0v θ0v sd ∇ϕ begin
+        check(ccall((:zzb_problem_create_gaussian, libzzb200), Int32,
+                    (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+                    prob, d, Γ.colptr, Γ.rowval, Γ.nzval, h, C_NULL, C_NULL, C_NULL, C_NULL))
+        st = ccall((:zzb_sspdmp3_run, libzzb200), Int32,
+                   (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Float64, Int32, Ptr{UInt64}, UInt32, Ref{Ptr{Cvoid}}),
+                   prob[], x0v, θ0v, T, c, κ, rule === :sticky ? 0 : 1, sd, UInt32(0), run)
+        if st != 0
+            run[] != C_NULL && ccall((:zzb_run_free, libzzb200), Int32, (Ptr{Cvoid},), run[])
+            ccall((:zzb_problem_free, libzzb200), Int32, (Ptr{Cvoid},), prob[])
+            check(st)
+        end
+    end
+    try
+        n = Ref{Int64}(0)
+        check(ccall((:zzb_trace_len, libzzb200), Int32, (Ptr{Cvoid}, Ref{Int64}), run[], n))
+        Ξ = ZigZagBoomerang.FactTrace(Z, 0.0, x0v, θ0v, Vector{Tuple{Float64,Int,Float64,Float64}}(undef, n[]))
+        check(ccall((:zzb_trace_copy, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64), run[], Ξ.events, 0, n[]))
+        t, x, θ, cv = zeros(d), zeros(d), zeros(d), zeros(d)
+        check(ccall((:zzb_run_final_state, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), run[], t, x, θ, cv))
+        acc = Vector{Int}(undef, d); num = Ref{Int64}(0)
+        check(ccall((:zzb_run_counts, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ref{Int64}), run[], acc, num))
+        return Ξ, (sum(acc), num[]), (t, x, θ)
+    finally
+        ccall((:zzb_run_free, libzzb200), Int32, (Ptr{Cvoid},), run[])
+        ccall((:zzb_problem_free, libzzb200), Int32, (Ptr{Cvoid},), prob[])
+    end
+end
 
 for FT in (:ZigZag, :FactBoomerang)
     @eval begin
