@@ -12,7 +12,7 @@ rng = np.random.default_rng(1)
 d = G.n
 x0 = rng.standard_normal(d); th0 = rng.choice(np.array([-1.0, 1.0]), d); c = G.colnorms()
 for rep in range(2):
-    part, st, ms = z.spdmp_sharded(z, z.GaussianPotential(G), z.ZigZag(G, np.zeros(d)), 0.0, x0, th0, T, c, seed=(1, 2), record_trace=False, gather=False)
+    part, st, ms = z.spdmp_sharded(z, z.GaussianPotential(G), z.ZigZag(G, np.zeros(d)), 0.0, x0, th0, T, c, seed=(1, 2), record_trace=False, gather=False, tune=({"target_frac": float(os.environ["FRAC"]), "target_flip_frac": 0.18 * float(os.environ["FRAC"])} if os.environ.get("FRAC") else None))
     dist.barrier()
-    print(f"rep {rep} rank {dist.get_rank()}: kernel {ms:.2f} ms windows {st['windows']} retries {st['retries']} rounds {st['passes']} relax {st['ns_relax']/1e6:.2f} idle {st['ns_tail']/1e6:.2f} dbg {[st['dbg%d' % q] for q in range(4)]}", flush=True)
+    print(f"rep {rep} rank {dist.get_rank()}: kernel {ms:.2f} ms windows {st['windows']} retries {st['retries']} rounds {st['passes']} relax {st['ns_relax']/1e6:.2f} xchg {st['ns_phaseb']/1e6:.2f} idle {st['ns_tail']/1e6:.2f} dbg {[st['dbg%d' % q] for q in range(4)]}", flush=True)
 dist.destroy_process_group()

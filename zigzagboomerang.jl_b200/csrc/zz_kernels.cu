@@ -89,33 +89,42 @@ __device__ __forceinline__ void zz_st_rel_sys(unsigned long long* p, unsigned lo
 
 struct ZzXres { unsigned long long sum, minkey; unsigned int flags; };
 
-// All-reduce of (sum, min, or) across the GPUs of the node by ONE thread: plain stores into the peers' mailboxes over NVLink
-// (double-buffered by the parity of the exchange counter), release / acquire at system scope.  The result is also left in the
-// control block for the other CTAs of this GPU.
+// All-reduce of (sum, min, or) across the GPUs of the node by WARP 0 of CTA 0: lane p writes this rank's contribution into
+// peer p's mailbox (plain stores over NVLink, double-buffered by the parity of the exchange counter), one system-scope fence,
+// then the epoch word; lane p then waits for peer p's message in the own mailbox and the warp reduces.  All peers are served
+// in parallel: the cost is one NVLink round trip, not one per peer.  The result is also left in the control block for the other
+// CTAs of this GPU.  Must be called by all 32 lanes of the warp.
 __device__ __forceinline__ ZzXres zz_exchange(const ZzParams& P, unsigned long long xep, unsigned long long ms,
                                               unsigned long long mk, unsigned int mf)
 {
     ZzDevCtl* C = P.ctl;
     const int par = (int)(xep & 1ULL);
-    __threadfence_system();
-    for (int p = 0; p < P.v.nranks; ++p) {
-        ZzMsg* dst = &P.ctl_peer[p]->mbox[par][P.v.rank];
+    const int lane = threadIdx.x & 31;
+    const bool have = lane < P.v.nranks;
+    if (have) {
+        ZzMsg* dst = &P.ctl_peer[lane]->mbox[par][P.v.rank];
         dst->sum = ms; dst->minkey = mk; dst->flags = mf;
     }
     __threadfence_system();
-    for (int p = 0; p < P.v.nranks; ++p) zz_st_rel_sys(&P.ctl_peer[p]->mbox[par][P.v.rank].epoch, xep);
-    ZzXres r; r.sum = 0ULL; r.minkey = ~0ULL; r.flags = 0u;
-    for (int p = 0; p < P.v.nranks; ++p) {
-        const ZzMsg* src = &C->mbox[par][p];
+    if (have) *(volatile unsigned long long*)&P.ctl_peer[lane]->mbox[par][P.v.rank].epoch = xep;
+    unsigned long long s = 0ULL, k = ~0ULL; unsigned int f = 0u;
+    if (have) {
+        const ZzMsg* src = &C->mbox[par][lane];
         while (zz_ld_acq_sys(&src->epoch) < xep) { }
-        r.sum += *(volatile const unsigned long long*)&src->sum;
-        const unsigned long long kk = *(volatile const unsigned long long*)&src->minkey;
-        r.minkey = kk < r.minkey ? kk : r.minkey;
-        r.flags |= *(volatile const unsigned int*)&src->flags;
+        s = *(volatile const unsigned long long*)&src->sum;
+        k = *(volatile const unsigned long long*)&src->minkey;
+        f = *(volatile const unsigned int*)&src->flags;
     }
-    C->xres[par].sum = r.sum; C->xres[par].minkey = r.minkey; C->xres[par].flags = r.flags;
-    __threadfence();
-    atomicExch(&C->xrelease, xep);
+    cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
+    ZzXres r;
+    r.sum = cg::reduce(w, s, cg::plus<unsigned long long>());
+    r.minkey = cg::reduce(w, k, cg::less<unsigned long long>());
+    r.flags = cg::reduce(w, f, cg::bit_or<unsigned int>());
+    if (lane == 0) {
+        C->xres[par].sum = r.sum; C->xres[par].minkey = r.minkey; C->xres[par].flags = r.flags;
+        __threadfence();
+        atomicExch(&C->xrelease, xep);
+    }
     return r;
 }
 
@@ -140,7 +149,7 @@ __device__ __forceinline__ ZzXres zz_boundary(const ZzParams& P, unsigned long l
     }
     xep += 1;
     const int par = (int)(xep & 1ULL);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
         const unsigned long long t0 = prof ? zz_now() : 0ULL;
         const unsigned long long ms = psum ? __ldcg(psum) : 0ULL;
         const unsigned long long mk = pmin ? __ldcg(pmin) : ~0ULL;
