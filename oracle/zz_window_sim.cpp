@@ -42,7 +42,17 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                    int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound, const double* kappa,
                    const double* boom_sigma, double boom_lambdaref, double boom_rho, const ZzHostLogit* hl, const ZzStrong* st = nullptr);
 
+// Which schedule the emulation runs: 0 = pass-synchronous (Jacobi) relaxation of round 1; T > 0 = the ASYNCHRONOUS tile-local
+// relaxation of zz_run_body_async with T tiles: per-tile queues (lattice: one per checkerboard colour, processed alternately),
+// dedupe bits, inboxes for marks that cross a tile boundary (delivered with a random delay), list tags owned by the publisher,
+// every evaluation with the freshest lists (cur = ~0).  Tiles take turns in a pseudo-random order derived from `seed`, so the
+// tests exercise many interleavings; the fixed point -- hence every output bit -- must not depend on it.
+static int g_async_tiles = 0;
+static uint64_t g_async_seed = 1;
+
 extern "C" {
+
+void zzw_set_schedule(int tiles, uint64_t seed) { g_async_tiles = tiles; g_async_seed = seed ? seed : 1; }
 
 // exhaustive check of the multiply-shift lattice-column formula against the division, for tests
 int64_t zzw_check_grid_col(int32_t M, int64_t jmax)
@@ -202,6 +212,95 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
             wl.clear(); next.clear(); touched.clear(); ovf_seen = false;
             ZzNodeOut o;
             int64_t it = 1;
+            if (g_async_tiles > 0) {
+                // ---------------- asynchronous tile-local relaxation (emulation of zz_run_body_async) ----------------
+                const int NT = g_async_tiles;
+                const int64_t per = (d + NT - 1) / NT;
+                const uint32_t STRIDE = 256;
+                uint64_t rs = g_async_seed * 0x9E3779B97F4A7C15ULL + (uint64_t)w0;
+                auto rnd = [&]() { rs ^= rs << 13; rs ^= rs >> 7; rs ^= rs << 17; return rs; };
+                auto colour = [&](int32_t k) -> int { if (!g.grid_m) return -1; const int32_t c = k / g.grid_m; return (int)(((k - c * g.grid_m) + c) & 1); };
+                std::vector<std::vector<int32_t>> q[2] = { std::vector<std::vector<int32_t>>(NT), std::vector<std::vector<int32_t>>(NT) };
+                std::vector<std::vector<int32_t>> inbox(NT);
+                std::vector<uint8_t> dirty(d, 0), tb(d, 0);
+                std::vector<int> cq(NT, 0);
+                for (int64_t j = 0; j < d; ++j) {
+                    const double tj = tau[j];
+                    if (tj < ctl.H || (ctl.incl && tj == ctl.H)) {
+                        const int c = colour((int32_t)j);
+                        q[c < 0 ? 0 : c][j / per].push_back((int32_t)j);
+                        dirty[j] = 1; tb[j] = 1; touched.push_back((int32_t)j);
+                    }
+                }
+                auto mark = [&](int tile, int32_t k, int nxt) {   // a local mark of tile `tile` (or a drained inbox entry)
+                    if (dirty[k]) return;
+                    dirty[k] = 1;
+                    const int c = colour(k);
+                    q[c < 0 ? nxt : c][tile].push_back(k);
+                    if (!tb[k]) { tb[k] = 1; touched.push_back(k); }
+                };
+                auto publish = [&](int tile, int32_t j, const ZzNodeOut& oo, int nxt) {
+                    int slot;
+                    uint32_t cnt = zz_pick_slot(oo.hdr0, oo.hdr1, w0, 0xffffffffu, slot);
+                    bool same = (cnt == oo.nflip);
+                    if (same && cnt) {
+                        const double* fl = &flips[((size_t)j * 2 + slot) * ZZ_MAXFLIP];
+                        for (uint32_t m = 0; m < cnt && same; ++m) same = (zz_d2u(fl[m]) == zz_d2u(oo.fl[m]));
+                        const double* ft = &fth[((size_t)j * 2 + slot) * ZZ_MAXFLIP];
+                        for (uint32_t m = 0; vel && m < cnt && same; ++m) same = (zz_d2u(ft[m]) == zz_d2u(oo.fth[m]));
+                    }
+                    uint32_t fl_ = oo.flags;
+                    if (!same) {
+                        const int wsl = (slot == 0) ? 1 : 0;
+                        const uint32_t newtag = (slot < 0) ? w0 : (((slot == 0) ? oo.hdr0 : oo.hdr1) >> 4) + 1u;
+                        if (newtag - w0 >= STRIDE) fl_ |= ZZ_F_OVERFLOW;
+                        else {
+                            double* fl = &flips[((size_t)j * 2 + wsl) * ZZ_MAXFLIP];
+                            for (uint32_t m = 0; m < oo.nflip; ++m) fl[m] = oo.fl[m];
+                            double* ft = &fth[((size_t)j * 2 + wsl) * ZZ_MAXFLIP];
+                            for (uint32_t m = 0; vel && m < oo.nflip; ++m) ft[m] = oo.fth[m];
+                            kin[j].hdr[wsl] = (newtag << 4) | oo.nflip;
+                            for (int32_t qd = G.dptr[j]; qd < G.dptr[j + 1]; ++qd) {
+                                const int32_t k = G.didx[qd];
+                                if (k / per == tile) mark(tile, k, nxt);
+                                else inbox[k / per].push_back(k);        // delivered when the owner drains
+                            }
+                        }
+                    }
+                    ZzSpec& sp = spec[j];
+                    sp.a = oo.a; sp.b = oo.b; sp.told = oo.told; sp.tau = oo.tau; sp.c = oo.c; sp.k = oo.k;
+                    sp.nprop = (uint16_t)oo.nprop; sp.nflip = (uint8_t)oo.nflip; sp.flags = (uint8_t)fl_;
+                    if (fl_ & ZZ_F_OVERFLOW) ovf_seen = true;
+                    vt[j] = oo.viol_t; vl[j] = oo.viol_l; vlb[j] = oo.viol_lb;
+                    r->node_evals++;
+                };
+                for (;;) {
+                    // pick a tile with work (queue or inbox) at random; none left -> quiescent
+                    std::vector<int> cand;
+                    for (int tl = 0; tl < NT; ++tl) if (!q[0][tl].empty() || !q[1][tl].empty() || !inbox[tl].empty()) cand.push_back(tl);
+                    if (cand.empty() || ovf_seen) break;
+                    const int tl = cand[rnd() % cand.size()];
+                    if (!inbox[tl].empty() && (rnd() & 1)) {            // drain (sometimes later: messages are asynchronous)
+                        std::vector<int32_t> in; in.swap(inbox[tl]);
+                        for (int32_t k : in) mark(tl, k, cq[tl]);
+                    }
+                    if (q[cq[tl]][tl].empty()) { if (!q[cq[tl] ^ 1][tl].empty()) cq[tl] ^= 1; else continue; }
+                    std::vector<int32_t> cur_items; cur_items.swap(q[cq[tl]][tl]);
+                    for (size_t a = cur_items.size(); a > 1; --a) std::swap(cur_items[a - 1], cur_items[rnd() % a]);   // order inside a round
+                    ++it;
+                    for (int32_t j : cur_items) {
+                        dirty[j] = 0;
+                        o.nitems = 0;
+                        if (st) zz_process_node_strong(g, v, *st, j, ctl.H, ctl.incl, w0, 0xffffffffu, false, o);
+                        else if (hl) zz_process_node_logit(g, v, lg, j, ctl.H, ctl.incl, w0, 0xffffffffu, false, o);
+                        else zz_process_node(g, v, j, ctl.H, ctl.incl, w0, 0xffffffffu, false, o);
+                        publish(tl, j, o, cq[tl] ^ 1);
+                    }
+                    cq[tl] ^= 1;
+                }
+                cur = w0 + STRIDE;   // every tag of this attempt lies below
+            } else {
+
             for (int64_t j = 0; j < d; ++j) {
                 double tj = tau[j];
                 if (tj < ctl.H || (ctl.incl && tj == ctl.H)) {
@@ -228,6 +327,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                     handle(j, o, w0, cur);
                 }
             }
+            }
             r->iters += it; r->max_iters = std::max(r->max_iters, it);
             bool overflow = ovf_seen; double smin = ZZ_INF; unsigned long long nprop = 0;  // accepted flips (length controller)
             for (int32_t j : touched) {
@@ -235,7 +335,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                 if (s.flags & ZZ_F_OVERFLOW) overflow = true;
                 nprop += (unsigned long long)s.nprop | ((unsigned long long)s.nflip << 32);
                 if (s.nflip) {
-                    int slot; zz_pick_slot(kin[j].hdr[0], kin[j].hdr[1], w0, cur, slot);
+                    int slot; zz_pick_slot(kin[j].hdr[0], kin[j].hdr[1], w0, g_async_tiles > 0 ? 0xffffffffu : cur, slot);
                     smin = std::min(smin, flips[((size_t)j * 2 + slot) * ZZ_MAXFLIP]);
                 }
             }
@@ -253,7 +353,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                 tau[j] = s.tau; kctr[j] = s.k;
                 r->num += s.nprop;
                 if (s.nflip) {
-                    int slot; zz_pick_slot(kin[j].hdr[0], kin[j].hdr[1], w0, cur, slot);
+                    int slot; zz_pick_slot(kin[j].hdr[0], kin[j].hdr[1], w0, g_async_tiles > 0 ? 0xffffffffu : cur, slot);
                     const double* fl = &flips[((size_t)j * 2 + slot) * ZZ_MAXFLIP];
                     double th = kin[j].theta, tf = kin[j].tf, xf = kin[j].xf;
                     const double* ft = &fth[((size_t)j * 2 + slot) * ZZ_MAXFLIP];

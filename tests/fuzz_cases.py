@@ -7,7 +7,7 @@ import numpy as np
 import oracle_lib as O
 
 
-def run_cases(z, ncases, seed, verbose=False, sim=False):
+def run_cases(z, ncases, seed, verbose=False, sim=False, async_sim=False):
     """Returns (failures, bound_errors); prints failing cases.  sim = True: instead of the CUDA path, the host emulation of the
     device schedule (oracle/zz_window_sim.cpp: the kernels' own per-coordinate code) is compared with the oracle -- no GPU."""
     rng = np.random.default_rng(seed)
@@ -58,6 +58,9 @@ def run_cases(z, ncases, seed, verbose=False, sim=False):
 
         def sim_fn(**kw):
             tk = {k: v for k, v in (tune or {}).items() if k in ("target_frac", "delta0", "tag_limit")}
+            if async_sim:   # the asynchronous tile-local schedule: the `grid` knob is the number of tiles; a fresh interleaving per case
+                tk["async_tiles"] = int((tune or {}).get("grid", 1 + case % 9))
+                tk["order_seed"] = 1000 + case
             r = O.window_sim(G, Zg, 0.0, x0, th0, T, c, h=h, mu=mu, seed=sd, **tk, **kw)
             return r.events, r.t, r.x, r.theta, r.c, r.acc, r.num
         if kind == "sticky":

@@ -268,11 +268,16 @@ def wlib():
 
 def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
                delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False, kappa=None, boom=None, logistic=None,
-               strong=None):
+               strong=None, async_tiles=0, order_seed=1):
     """``strong = rule`` ("sticky" / "reversible"): the strong-bound sparse sticky timeline (zz_strong.h) with scalar ``c`` and
     ``kappa``, target = ``bound``; contract: :func:`sparsestickyzz` with ``ctr=True``."""
     L = wlib()
     d = bound.n
+    # which schedule: 0 = pass-synchronous relaxation; T > 0 = the asynchronous tile-local relaxation with T tiles, tiles and
+    # items taking turns in an order derived from order_seed (csrc/zz_kernels.cu: zz_run_body_async)
+    L.zzw_set_schedule.restype = None
+    L.zzw_set_schedule.argtypes = [C.c_int, C.c_uint64]
+    L.zzw_set_schedule(int(async_tiles), int(order_seed))
     f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
     x0, theta0, c = f8(x0), f8(theta0), f8(c)
     mu = np.zeros(d) if mu is None else f8(mu)

@@ -139,3 +139,56 @@ def test_bound_matrix_without_stored_diagonal_is_refused(zzb):
     with pytest.raises(RuntimeError, match="status 4"):
         O.window_sim(G, Gb, 0.0, x0, th0, 1.0, c)
     O.window_sim(G, G, 0.0, x0, th0, 1.0, c)   # with the diagonal stored it runs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The ASYNCHRONOUS tile-local relaxation of round 2 (zz_run_body_async), emulated on the host with the device's own
+# per-coordinate code: per-tile queues (lattice: checkerboard colours), dedupe bits, inboxes with delayed delivery, publisher-owned
+# list tags, every evaluation with the freshest lists.  Any interleaving must give the oracle's bits.
+@pytest.mark.parametrize("tiles,order_seed", [(1, 1), (3, 2), (7, 3), (16, 4), (16, 5), (37, 6)])
+def test_async_schedule_lattice(zzb, tiles, order_seed):
+    G, x0, th0, c = zzb.gmrf_config(16)
+    ref = O.spdmp(G, G, 0.0, x0, th0, 4.0, c)
+    got = O.window_sim(G, G, 0.0, x0, th0, 4.0, c, async_tiles=tiles, order_seed=order_seed)
+    O.assert_same_run(ref, got)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_async_schedule_random_sparse_adapt(zzb, seed):
+    d = 50
+    Gt = zzb.random_sparse_spd(d, deg=2 + seed % 3, seed=seed)
+    Gb = Gt.scaled(0.9)
+    rng = np.random.default_rng(seed)
+    x0, th0 = rng.standard_normal(d), rng.choice(np.array([-1.0, -0.5, 0.5, 1.0]), d)
+    h, mu = 0.3 * rng.standard_normal(d), 0.1 * rng.standard_normal(d)
+    c = 0.2 * Gt.colnorms()
+    ref = O.spdmp(Gt, Gb, 0.0, x0, th0, 10.0, c, h=h, mu=mu, adapt=True)
+    got = O.window_sim(Gt, Gb, 0.0, x0, th0, 10.0, c, h=h, mu=mu, adapt=True, async_tiles=1 + seed * 3, order_seed=100 + seed,
+                       target_frac=[0.05, 0.4, 2.0][seed % 3])
+    O.assert_same_run(ref, got)
+
+
+def test_async_schedule_other_samplers(zzb):
+    """LocalBound, sticky and Boomerang timelines under the asynchronous schedule."""
+    G, x0, th0, _ = zzb.gmrf_config(10)
+    c = np.full(G.n, 1.0)
+    LB = O.PARITY_MODE | O.LOCAL_BOUND
+    ref = O.spdmp(G, G, 0.0, x0, th0, 3.0, c, mode=LB)
+    O.assert_same_run(ref, O.window_sim(G, G, 0.0, x0, th0, 3.0, c, local_bound=True, async_tiles=5, order_seed=7))
+    kap = np.full(G.n, 0.7)
+    c2 = np.full(G.n, 5.0)
+    ref = O.spdmp(G, G, 0.0, x0, th0, 3.0, c2, kappa=kap)
+    O.assert_same_run(ref, O.window_sim(G, G, 0.0, x0, th0, 3.0, c2, kappa=kap, async_tiles=4, order_seed=8))
+    rng = np.random.default_rng(3)
+    sigma = 1.0 / np.sqrt(np.array([G.to_scipy()[i, i] for i in range(G.n)]))
+    thb = sigma * rng.standard_normal(G.n)
+    cb = np.full(G.n, 8.0)
+    ref = O.spdmp(G, G, 0.0, x0, thb, 2.0, cb, boom=(sigma, 20.0, 0.2), mode=O.PARITY_MODE)
+    O.assert_same_run(ref, O.window_sim(G, G, 0.0, x0, thb, 2.0, cb, boom=(sigma, 20.0, 0.2), async_tiles=6, order_seed=9))
+
+
+def test_async_schedule_randomised_campaign(zzb):
+    """The randomised campaign of tests/fuzz_cases.py under the asynchronous schedule (random tile counts and interleavings)."""
+    import fuzz_cases
+    bad, nbound = fuzz_cases.run_cases(zzb, 120, 11, sim=True, async_sim=True)
+    assert bad == 0
