@@ -59,6 +59,8 @@ extern "C" {
                                    second directional derivatives, valid for 2/c/|theta|, then renewed (problem: bnd_* = NULL) */
 
 #define ZZB_FLAG_STICKY 4u      /* sticky ZigZag sspdmp (src/ss_fact.jl): coordinates freeze at 0, thaw after Exp(kappa_i) */
+#define ZZB_FLAG_STICKY_REVERSIBLE 16u /* sspdmp(...; reversible = true): a thawing coordinate re-enters with a random sign, ss_fact.jl:111-113 */
+#define ZZB_FLAG_STICKY_STRONG_UB 32u  /* sspdmp(...; strong_upperbounds = true): a freeze reschedules nobody, ss_fact.jl:97-107 */
 #define ZZB_FLAG_BOOMERANG 8u   /* factorised Boomerang (F::FactBoomerang): rotation around Z.mu, velocity refreshments */
 
 typedef struct zzb_problem_s* zzb_problem_t;
@@ -157,6 +159,11 @@ int32_t zzb_trace_copy(zzb_run_t r, zzb_event* dst, int64_t first, int64_t count
 int32_t zzb_trace_clear(zzb_run_t r);                                 /* streaming: drop the events already copied out */
 int32_t zzb_trace_moments(zzb_run_t r, double* m1, double* m2);     /* time averages of x and x^2 over [t0, last event] */
 int32_t zzb_trace_sums(zzb_run_t r, double* s1, double* s2);        /* the unscaled device accumulators */
+/* subtrace at the source (src/trace.jl:275-290): only the events of the coordinates J (1-based, strictly ascending) are recorded,
+ * renumbered to their position in J; nJ = 0 lifts the filter.  Before zzb_run_upload. */
+int32_t zzb_run_trace_filter(zzb_run_t r, const int64_t* J, int64_t nJ);
+/* inclusion_prob(trace) (src/trace.jl:161-178) of a sticky run from a device accumulator (no trace needed) */
+int32_t zzb_trace_inclusion(zzb_run_t r, double* p);
 /* Device-side discretisation.  zzb_run_discretize (before zzb_run_upload) asks for the n_rows grid times t0 + k dt,
  * k = 0 .. n_rows-1; zzb_run_grid (after zzb_run_execute) copies rows [first_row, first_row + n) of the row-major
  * n_rows x d array (row k = x(t0 + k dt), evaluated from the anchor of the segment containing the grid time) and reports in

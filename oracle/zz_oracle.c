@@ -61,6 +61,8 @@
 #define ZZO_ARITH_LAZY 2
 #define ZZO_GRAPH_ALL 4
 #define ZZO_LOCAL_BOUND 8 /* spdmp(..., C::LocalBound, ...) of src/local.jl:95-149 */
+#define ZZO_STICKY_REVERSIBLE 16 /* sspdmp(...; reversible = true): a thawing coordinate re-enters with a random sign, ss_fact.jl:111-113 */
+#define ZZO_STICKY_STRONG_UB 32  /* sspdmp(...; strong_upperbounds = true): a freeze reschedules nobody, ss_fact.jl:97-107 */
 
 #define ZZO_OK 0
 #define ZZO_E_BOUND 3 /* "Tuning parameter `c` too small." sfact.jl:124 */
@@ -693,6 +695,7 @@ zzo_run *zzo_sspdmp(int64_t d,
                 thf[i - 1] = z->th[i - 1]; z->th[i - 1] = 0.0;      /* :93 */
                 z->t_old[i - 1] = tp; f[i - 1] = 0;
                 h_set(&Q, i, tp - zz_log(draw(z, i)) / kappa[i - 1]); /* :96 */
+                if (!(mode & ZZO_STICKY_STRONG_UB)) {               /* :97 if !strong_upperbounds */
                 if (!lazy) { s_move_nbhd(z, nbv, nnb, tp); s_move_nbhd(z, g2, ng2, tp); }
                 for (int64_t q = 0; q < nnb; ++q) {                 /* :100-106 */
                     int64_t j = nbv[q];
@@ -703,9 +706,11 @@ zzo_run *zzo_sspdmp(int64_t d,
                         s_queue_time(&S, j, tj, lazy ? pos_at(z, j, tp) : z->x[j - 1]);
                     }
                 }
+                }
             } else if ((lazy ? z->xf[i - 1] : z->x[i - 1]) == 0 && z->th[i - 1] == 0) { /* case 2: thaw, :108-123 */
                 if (lazy) z->tf[i - 1] = tp; else z->t[i - 1] = tp;
                 z->th[i - 1] = thf[i - 1]; thf[i - 1] = 0.0;
+                if (mode & ZZO_STICKY_REVERSIBLE) z->th[i - 1] *= (draw(z, i) < 0.5 ? -1.0 : 1.0);   /* :111-113 theta[i] *= rand((-1,1)) */
                 z->t_old[i - 1] = tp;
                 if (!lazy) { s_move_nbhd(z, nbv, nnb, tp); s_move_nbhd(z, g2, ng2, tp); }
                 for (int64_t q = 0; q < nnb; ++q) {

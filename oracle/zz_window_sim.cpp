@@ -113,6 +113,8 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
 {
     zzw_run* r = new zzw_run();
     r->d = d;
+    const int sticky_opts = local_bound & (ZZ_STICKY_REVERSIBLE | ZZ_STICKY_STRONG_UB);   // (the sspdmp option bits travel in `local_bound`)
+    local_bound &= 1;
     ZzHostGraph G;
     std::vector<double> zero_mu((size_t)d, 0.0);
     // LocalBound (src/local.jl): the bound is built from the TARGET's derivatives; the sampler matrix is not used
@@ -142,7 +144,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
     zz_grid_set_magic(g);
     ZzView v; memset(&v, 0, sizeof v); v.nranks = 1; v.hi = (int32_t)d; v.shard = (int32_t)d; v.d = (int32_t)d; v.kin = kin.data(); v.flips = flips.data(); v.priv = priv.data();
     v.tau = tau.data(); v.kctr = kctr.data(); v.seed0 = seed[0]; v.seed1 = seed[1]; v.adapt = adapt; v.factor = factor; v.local_bound = local_bound;
-    v.sticky = kappa ? 1 : 0; v.fth = (kappa || boom_sigma) ? fth.data() : nullptr; v.kappa = kappa;
+    v.sticky = kappa ? (1 | sticky_opts) : 0; v.fth = (kappa || boom_sigma) ? fth.data() : nullptr; v.kappa = kappa;
     const bool vel = kappa || boom_sigma;   // lists carry the velocity after each event
     v.boom = boom_sigma ? 1 : 0; v.bmu = mu; v.bsig = boom_sigma; v.bref_rate = boom_lambdaref / (double)d; v.brho = boom_rho;
     v.brhobar = sqrt(1 - boom_rho * boom_rho);

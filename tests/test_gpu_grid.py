@@ -87,3 +87,35 @@ def test_grid_full_size_statistics(gpu):
     step = np.abs(xs[1:] - xs[:-1]).max()
     assert 0 < step <= 0.05 * (1 + 1e-12)                  # unit speed: no coordinate moves more than dt between rows
     run.close(); prob.close()
+
+
+def test_subtrace_filter_and_inclusion_prob_on_device(gpu):
+    """f1 of SURVEY 8(f): subtrace (src/trace.jl:275-290) applied at the source -- only the selected coordinates' events are
+    recorded, renumbered -- equals subtrace() of the full trace; inclusion_prob (:161-178) of a sticky run from the device
+    accumulator equals the host mirror evaluated on the full trace; the sspdmp options reversible / strong_upperbounds (src/ss_fact.jl:97-113)
+    against the oracle."""
+    import oracle_lib as O
+    G, x0, th0, c = gpu.gmrf_config(20)
+    Z = gpu.ZigZag(G, np.zeros(G.n))
+    full, _, (acc, num), _ = gpu.spdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 3.0, c, Z, seed=(1, 2))
+    J = np.array([1, 2, 7, 40, 41, 199, 200, 399, 400])
+    sub, _, (acc2, num2), _ = gpu.spdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 3.0, c, Z, seed=(1, 2), trace_filter=J)
+    want = gpu.subtrace(full, J)
+    assert num2 == num and np.array_equal(acc, acc2)
+    assert len(want.events) >= 10 and np.array_equal(sub.events, want.events)
+    assert np.array_equal(sub.x0, want.x0)
+    # sticky: inclusion probabilities
+    d = G.n
+    kap = np.full(d, 0.7)
+    cs = 4.0 * G.colnorms()
+    Xs, _, _, _ = gpu.sspdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 5.0, cs, Z, kap, seed=(3, 4))
+    host = gpu.inclusion_prob(Xs)
+    assert np.allclose(Xs.inclusion_prob, host, rtol=1e-12, atol=1e-15) and 0.05 < host.mean() < 0.95
+    for rev, strong in ((True, False), (False, True), (True, True)):
+        mode = O.PARITY_MODE | (O.STICKY_REVERSIBLE if rev else 0) | (O.STICKY_STRONG_UB if strong else 0)
+        ref = O.spdmp(G, G, 0.0, x0, th0, 5.0, cs, kappa=kap, seed=(3, 4), mode=mode)
+        Xo, (t, x, th), (a, n), _ = gpu.sspdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 5.0, cs, Z, kap, seed=(3, 4), reversible=rev,
+                                               strong_upperbounds=strong)
+        assert n == ref.num and a == int(ref.acc.sum()) and np.array_equal(Xo.events["i"], ref.events["i"])
+        for f in ("t", "x", "theta"):
+            assert np.array_equal(Xo.events[f].view(np.uint64), ref.events[f].view(np.uint64))

@@ -192,3 +192,21 @@ def test_async_schedule_randomised_campaign(zzb):
     import fuzz_cases
     bad, nbound = fuzz_cases.run_cases(zzb, 120, 11, sim=True, async_sim=True)
     assert bad == 0
+
+
+@pytest.mark.parametrize("reversible,strong", [(True, False), (False, True), (True, True)])
+def test_sticky_options_reversible_and_strong_upperbounds(zzb, reversible, strong):
+    """sspdmp(...; reversible, strong_upperbounds) (src/ss_fact.jl:97-113): the device's sticky timeline against the oracle, under
+    both schedules of the emulation."""
+    G = zzb.grid_precision(7, 9, shift=0.5)
+    rng = np.random.default_rng(4)
+    d = G.n
+    x0, th0 = rng.standard_normal(d), rng.choice(np.array([-1.0, 1.0]), d)
+    c, kap = 4.0 * G.colnorms(), np.full(d, 0.8)
+    mode = O.PARITY_MODE | (O.STICKY_REVERSIBLE if reversible else 0) | (O.STICKY_STRONG_UB if strong else 0)
+    ref = O.spdmp(G, G, 0.0, x0, th0, 6.0, c, kappa=kap, mode=mode)
+    plain = O.spdmp(G, G, 0.0, x0, th0, 6.0, c, kappa=kap)
+    assert len(ref.events) > 200 and not np.array_equal(ref.events["t"][:len(plain.events)], plain.events["t"][:len(ref.events)])
+    for tiles in (0, 5):
+        got = O.window_sim(G, G, 0.0, x0, th0, 6.0, c, kappa=kap, reversible=reversible, strong_upperbounds=strong, async_tiles=tiles)
+        O.assert_same_run(ref, got)

@@ -316,12 +316,14 @@ class Run:
     """One sampler run on the device (staged form of the C-ABI)."""
 
     def __init__(self, problem: Problem, *, record_trace: bool = True, trace_capacity: int = 0, local_bound: bool = False,
-                 kappa=None, boomerang=None):
+                 kappa=None, boomerang=None, reversible: bool = False, strong_upperbounds: bool = False):
         self.problem = problem
         self.d = problem.d
         self._h = C.c_void_p()
         flags = (0 if record_trace else _capi.ZZB_FLAG_NO_TRACE) | (_capi.ZZB_FLAG_LOCAL_BOUND if local_bound else 0) \
-            | (_capi.ZZB_FLAG_STICKY if kappa is not None else 0) | (_capi.ZZB_FLAG_BOOMERANG if boomerang is not None else 0)
+            | (_capi.ZZB_FLAG_STICKY if kappa is not None else 0) | (_capi.ZZB_FLAG_BOOMERANG if boomerang is not None else 0) \
+            | (_capi.ZZB_FLAG_STICKY_REVERSIBLE if (kappa is not None and reversible) else 0) \
+            | (_capi.ZZB_FLAG_STICKY_STRONG_UB if (kappa is not None and strong_upperbounds) else 0)
         self.record_trace = record_trace
         check(_capi.lib().zzb_run_create(problem._h, flags, int(trace_capacity), C.byref(self._h)))
         if kappa is not None:
@@ -378,6 +380,19 @@ class Run:
         lo, hi = C.c_int64(), C.c_int64()
         check(_capi.lib().zzb_run_range(self._h, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
+
+    def trace_filter(self, J):
+        """``subtrace`` at the source (src/trace.jl:275-290): record only the events of the coordinates `J` (1-based, strictly
+        ascending), renumbered to their position in `J`.  Before :meth:`upload`.  ``None`` / empty lifts the filter."""
+        J = np.ascontiguousarray([] if J is None else J, dtype=np.int64)
+        check(_capi.lib().zzb_run_trace_filter(self._h, ptr(J), len(J)))
+        return self
+
+    def inclusion_prob(self):
+        """``inclusion_prob(trace)`` (src/trace.jl:161-178) of a sticky run, from a device accumulator (no trace needed)."""
+        p = np.empty(self.d)
+        check(_capi.lib().zzb_trace_inclusion(self._h, ptr(p)))
+        return p
 
     def reset(self):
         """Re-initialise the device state from the inputs already resident in HBM (no host traffic)."""
@@ -477,7 +492,7 @@ def _as_problem(grad, F):
 
 
 def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None, record_trace=True, tune=None,
-          discretize_dt=None):
+          discretize_dt=None, trace_filter=None):
     """``spdmp(grad, t0, x0, theta0, T, c, [G,] F, args...; factor=1.8, adapt=false, seed=Seed())``
     = ``Xi, (t, x, theta), (acc, num), c`` (src/sfact.jl:162-214).
 
@@ -512,12 +527,18 @@ def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None,
             run.set(**tune)
         if discretize_dt is not None:
             run.discretize(discretize_dt, int(np.floor((T - t0) / discretize_dt)) + 1)
+        if trace_filter is not None:   # the returned trace is subtrace(Xi, J), produced on the device (src/trace.jl:275-290)
+            run.trace_filter(trace_filter)
         run.upload(t0, x0, theta0, c, seed=seed, adapt=adapt, factor=factor)
         run.execute(T)
         t, x, th, cc = run.final_state()
         acc, num = run.counts()
         ev = run.events() if record_trace else np.empty(0, dtype=EVENT_DTYPE)
-        Xi = FactTrace(F, t0, x0, theta0, ev)
+        if trace_filter is not None:
+            Jm = np.asarray(trace_filter, dtype=np.int64) - 1
+            Xi = FactTrace(F, t0, f8(x0)[Jm], f8(theta0)[Jm], ev)
+        else:
+            Xi = FactTrace(F, t0, x0, theta0, ev)
         Xi.grid = run.grid() if discretize_dt is not None else None
         Xi.moments = run.moments() if (num and boom is None) else None   # event-based moments assume linear segments
         Xi.stats = run.stats()
@@ -534,13 +555,16 @@ def pdmp(grad, t0, x0, theta0, T, c, F, *args, **kw):
     return spdmp(grad, t0, x0, theta0, T, c, All(), F, *args, **kw)
 
 
-def sspdmp(grad, t0, x0, theta0, T, c, *rest, seed=None, record_trace=True, tune=None, **unsupported):
-    """``sspdmp(grad, t0, x0, theta0, T, c, [G,] F::ZigZag, kappa, args...)`` = ``Xi, (t, x, theta), (acc, num), c``
-    (src/ss_fact.jl:159-217): sticky ZigZag -- coordinates freeze when they hit 0 and thaw after an Exp(kappa_i) time.
-    `acc` is the number of accepted reflections (a scalar, like the reference).  Options of the reference that are
-    not available on the device path raise (``adapt``, ``reversible``, ``strong_upperbounds``)."""
+def sspdmp(grad, t0, x0, theta0, T, c, *rest, seed=None, record_trace=True, tune=None, reversible=False, strong_upperbounds=False,
+           **unsupported):
+    """``sspdmp(grad, t0, x0, theta0, T, c, [G,] F::ZigZag, kappa, args...; reversible=false, strong_upperbounds=false)`` =
+    ``Xi, (t, x, theta), (acc, num), c`` (src/ss_fact.jl:159-217): sticky ZigZag -- coordinates freeze when they hit 0 and thaw
+    after an Exp(kappa_i) time.  ``reversible``: a thawing coordinate re-enters with a random sign (:111-113);
+    ``strong_upperbounds``: a freeze reschedules nobody (:97-107).  `acc` is the number of accepted reflections (a scalar, like
+    the reference).  ``adapt=true`` is not available on the device path (the reference then also RESETS acc and num at every
+    adaptation, :133-135) and raises."""
     for k, v in unsupported.items():
-        if v not in (False, None) and k in ("adapt", "reversible", "strong_upperbounds"):
+        if v not in (False, None) and k in ("adapt",):
             raise NotImplementedError(f"sspdmp(...; {k}=true) is not implemented on the device path")
     rest = list(rest)
     if rest and (rest[0] is None or isinstance(rest[0], (All, Matched))):
@@ -551,7 +575,8 @@ def sspdmp(grad, t0, x0, theta0, T, c, *rest, seed=None, record_trace=True, tune
     prob, own = _as_problem(grad, F)
     if seed is None:
         seed = (secrets.randbits(64), secrets.randbits(64))
-    run = Run(prob, record_trace=record_trace, kappa=np.broadcast_to(f8(kappa), (prob.d,)).copy())
+    run = Run(prob, record_trace=record_trace, kappa=np.broadcast_to(f8(kappa), (prob.d,)).copy(), reversible=bool(reversible),
+              strong_upperbounds=bool(strong_upperbounds))
     try:
         if tune:
             run.set(**tune)
@@ -564,6 +589,7 @@ def sspdmp(grad, t0, x0, theta0, T, c, *rest, seed=None, record_trace=True, tune
         Xi.stats = run.stats()
         Xi.acc_per_coordinate = acc
         Xi.sums = run.sums()
+        Xi.inclusion_prob = run.inclusion_prob() if num else None   # src/trace.jl:161-178 from the device accumulator
         return Xi, (t, x, th), (int(acc.sum()), num), cc
     finally:
         run.close()

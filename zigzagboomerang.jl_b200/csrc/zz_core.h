@@ -29,6 +29,8 @@
 #define ZZ_F_OVERFLOW 1u  // more than ZZ_MAXFLIP flips / ZZ_MAXITEMS items: the window must be shortened
 #define ZZ_F_VIOL 2u      // accepted with l >= lb and adapt == false  (sfact.jl:123-124)
 #define ZZ_F_STICKY_ERR 4u  // a freezing coordinate was not at 0 (ss_fact.jl:89-91)
+#define ZZ_STICKY_REVERSIBLE 2   // bits of ZzView::sticky (bit 0: sticky sampler): sspdmp options reversible / strong_upperbounds
+#define ZZ_STICKY_STRONG_UB 4
 #define ZZ_RENEW_BIT 0x80000000u  // in the draw counter: the queued time is a bound expiry, not a proposal (local.jl:34)
 
 // Kinematic record of one coordinate, read by its neighbours: 32 B = one DRAM/L2 sector.

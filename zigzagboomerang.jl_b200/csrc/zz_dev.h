@@ -118,6 +118,12 @@ struct ZzParams {
     unsigned long long* dbgbuf;     // [grid][ZZ_DBG_REC][4] or null
     unsigned int dbg_window;
     unsigned int eval_threads;      // development: threads of a CTA that take queue entries (0 = all)
+    // subtrace at the source (src/trace.jl:275-290): when set, only events of coordinates with trace_map[j] != 0 are recorded,
+    // renumbered to trace_map[j] (the 1-based position of j in the caller's sorted list J)
+    const int32_t* trace_map;
+    // sticky samplers: time spent away from 0 per coordinate, sum of [x_prev != 0 or x_new != 0] (t_new - t_prev) over its
+    // events (inclusion_prob of src/trace.jl:161-178, unscaled); null = not wanted
+    double* s3;
     // subsampled logistic target (zz_logit.h; only read by zz_run_kernel_csr_logit)
     ZzLogit lg;
     ZzStrong st;

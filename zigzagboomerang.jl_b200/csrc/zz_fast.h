@@ -360,8 +360,11 @@ ZZ_HD void zz_timeline_sticky(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w
             }
             ++p;
             if (!trig || frozen) continue;           // frozen coordinates are not rescheduled
+            if ((v.sticky & ZZ_STICKY_STRONG_UB) && tha == 0.0) continue;   // strong_upperbounds: a freeze reschedules nobody (:97)
         } else if (frozen) {                         // thaw (:108-116): restore the speed, then reschedule below
             th = thf; thf = 0.0; tf = s; frozen = false;
+            if (v.sticky & ZZ_STICKY_REVERSIBLE)     // reversible: re-enter with a random sign (:111-113)
+                th *= (zz_u01(v.seed0, v.seed1, (uint64_t)j, k++) < 0.5 ? -1.0 : 1.0);
             if (nev == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
 #pragma unroll
             for (int m = 0; m < ZZ_MAXFLIP; ++m) if (m == (int)nev) { o.fl[m] = s; o.fth[m] = th; }

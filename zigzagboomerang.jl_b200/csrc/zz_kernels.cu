@@ -449,10 +449,12 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, con
         zz_pick_slot(h0, h1, w0, cur, slot);
         const double* fl = P.v.flips + ((size_t)j * 2 + slot) * ZZ_MAXFLIP;
         unsigned long long pos = 0;
+        const int32_t tid = P.trace_map ? __ldg(P.trace_map + j) : j + 1;   // id in the trace (0: filtered out, src/trace.jl:275-290)
+        const bool rec = P.record_trace && tid != 0;
         if (P.record_trace) {
             const unsigned int mask = __activemask();
             unsigned int tot;
-            const unsigned int pre = zz_prefix3(mask, s.nflip, tot);   // nflip <= ZZ_MAXFLIP = 6
+            const unsigned int pre = zz_prefix3(mask, rec ? s.nflip : 0u, tot);   // nflip <= ZZ_MAXFLIP = 6
             const int leadl = __ffs(mask) - 1;
             unsigned long long base = 0;
             if ((threadIdx.x & 31) == leadl) base = atomicAdd(&C->trace_len, (unsigned long long)tot);
@@ -461,6 +463,7 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, con
         }
         double a1 = __ldcg(P.s1 + j), a2 = __ldcg(P.s2 + j);
         const double* ft = ZZ_MODE_HAS_VEL(MODE) ? P.v.fth + ((size_t)j * 2 + slot) * ZZ_MAXFLIP : nullptr;
+        double a3 = (ft && P.s3) ? __ldcg(P.s3 + j) : 0.0;
         const bool boom = (MODE == ZZ_MODE_BOOM);
         const double muj = boom ? P.v.bmu[j] : 0.0;
         unsigned int nrefl = boom ? ((s.flags >> 3) & 7u) : 0u;   // Boomerang: reflections counted by the timeline (refreshments are events too)
@@ -484,11 +487,12 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, con
                 a1 += (xf + xs) * (fs - tf);                      // trace.jl:194 (scaled by 1/(2T) on the host)
                 a2 += (fs - tf) * (xf * xf + xf * xs + xs * xs);
             }
+            if (ft && !boom && P.s3) a3 += ((xf != 0.0 || xs != 0.0) ? 1.0 : 0.0) * (fs - tf);   // trace.jl:170-172
             th = thn; tf = fs; xf = xs;
-            if (P.record_trace) {
+            if (rec) {
                 if (pos + m < P.trace_cap) {
                     double2* e = reinterpret_cast<double2*>(P.trace + pos + m);   // sfact.jl:50-52
-                    e[0] = make_double2(fs, __longlong_as_double((long long)j + 1));
+                    e[0] = make_double2(fs, __longlong_as_double((long long)tid));
                     e[1] = make_double2(xs, th);
                 } else {
                     C->trace_full = 1u;
@@ -496,6 +500,7 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, con
             }
         }
         P.s1[j] = a1; P.s2[j] = a2;
+        if (ft && P.s3) P.s3[j] = a3;
         P.acc[j] = __ldcg(P.acc + j) + nrefl;            // accepted reflections (freezes and thaws are events, not acceptances)
         double2* kq = reinterpret_cast<double2*>(P.v.kin + j);
         kq[0] = make_double2(th, tf);
@@ -522,6 +527,7 @@ zz_setup_kernel(const ZzParams P, const double* __restrict__ x0, const double* _
         ZzPriv p; p.a = 0.0; p.b = 0.0; p.told = P.t0; p.c = c0[j];
         P.v.priv[j] = p;
         P.dstamp[j] = 0; P.acc[j] = 0; P.s1[j] = 0.0; P.s2[j] = 0.0;
+        if (P.s3) P.s3[j] = 0.0;
         if (P.grid_n) P.grid[j] = x0[j];   // row 0: x(t0)
     }
 }

@@ -186,6 +186,7 @@ struct zzb_run_s {
     int tile_per = 0; unsigned int eval_threads = 0; int inbox_nr = 0;
     // device-side ordering of the trace (zz_tsort_*): the events of the last execute, sorted, still in HBM
     DevBuf trace_sorted, ts_work; bool dev_sorted = false; unsigned long long n_sorted = 0; bool host_sort_only = false;
+    DevBuf trace_map, s3; bool have_map = false;   // subtrace filter / inclusion-time accumulator (sticky)
     int setup_lo = 0, setup_hi = 0;    // coordinates whose records this rank sets up (sharded lattice: slab + halo; otherwise all)
     unsigned int wat_next = 0;         // window-attempt numbers tag the inbox entries: never reused by a later run of this handle
     int kidx() const
@@ -449,7 +450,7 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     AL(touched, d * 8);   // up to two entries per coordinate (see zz_commit_node)
     AL(ctl, sizeof(ZzDevCtl));
     AL(in_x, d * 8); AL(in_th, d * 8); AL(in_c, d * 8);
-    if (flags & ZZB_FLAG_STICKY) { AL(dfth, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(kappa, d * 8); }
+    if (flags & ZZB_FLAG_STICKY) { AL(dfth, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(kappa, d * 8); AL(s3, d * 8); }
     if (flags & ZZB_FLAG_BOOMERANG) {
         AL(dfth, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(bsig, d * 8);
         if (!st) st = upload(r->bmu, p->hg.mu.data(), d * 8);
@@ -519,9 +520,12 @@ static void fill_params(zzb_run_s* r)
     P.inbox = r->inbox.as<unsigned long long>(); P.inbox_cnt = r->inbox_cnt.as<unsigned int>();
     P.inbox_cap = r->inbox_cap; P.flag_words = r->flag_words; P.tile_per = r->tile_per;
     P.record_trace = (r->flags & ZZB_FLAG_NO_TRACE) ? 0 : 1;
+    P.trace_map = r->have_map ? r->trace_map.as<int32_t>() : nullptr;
+    P.s3 = (r->flags & ZZB_FLAG_STICKY) ? r->s3.as<double>() : nullptr;
     P.grid = r->grid_n ? r->gridbuf.as<double>() : nullptr; P.grid_dt = r->grid_dt; P.grid_n = r->grid_n;
     P.v.local_bound = (r->flags & ZZB_FLAG_LOCAL_BOUND) ? 1 : 0;
-    P.v.sticky = (r->flags & ZZB_FLAG_STICKY) ? 1 : 0;
+    P.v.sticky = (r->flags & ZZB_FLAG_STICKY) ? (1 | ((r->flags & ZZB_FLAG_STICKY_REVERSIBLE) ? ZZ_STICKY_REVERSIBLE : 0) |
+                                                 ((r->flags & ZZB_FLAG_STICKY_STRONG_UB) ? ZZ_STICKY_STRONG_UB : 0)) : 0;
     P.v.boom = (r->flags & ZZB_FLAG_BOOMERANG) ? 1 : 0;
     P.v.fth = (P.v.sticky || P.v.boom) ? r->dfth.as<double>() : nullptr;
     if (P.v.boom) {
@@ -1147,6 +1151,41 @@ int32_t zzb_trace_moments(zzb_run_t r, double* m1, double* m2)
         if (m1) m1[j] = r->hs1[j] * (1 / (2 * Tl));   // scale = 1/(2T), trace.jl:190
         if (m2) m2[j] = r->hs2[j] / (3 * Tl);
     }
+    return ZZB_OK;
+}
+
+// subtrace at the source (src/trace.jl:275-290): record only the events of the coordinates J (1-based, strictly ascending),
+// renumbered to their position in J; nJ = 0 lifts the filter.  Before zzb_run_upload / zzb_run_reset.
+int32_t zzb_run_trace_filter(zzb_run_t r, const int64_t* J, int64_t nJ)
+{
+    if (!r || (nJ > 0 && !J)) return fail(ZZB_E_ARG, "null argument");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (nJ <= 0) { r->have_map = false; r->uploaded = false; return ZZB_OK; }
+    std::vector<int32_t> map((size_t)r->d, 0);
+    for (int64_t q = 0; q < nJ; ++q) {
+        if (J[q] < 1 || J[q] > r->d || (q && J[q] <= J[q - 1])) return fail(ZZB_E_ARG, "J must be strictly ascending indices in 1..d");
+        map[(size_t)J[q] - 1] = (int32_t)(q + 1);
+    }
+    CtxGuard cg;
+    int32_t st = upload(r->trace_map, map.data(), map.size() * 4);
+    if (st) return st;
+    r->have_map = true;
+    r->uploaded = false;   // the launch parameters change: zzb_run_upload / zzb_run_reset must follow
+    return ZZB_OK;
+}
+
+// inclusion_prob(trace) of src/trace.jl:161-178 for a sticky run, from the device accumulator: fraction of [t0, last event] a
+// coordinate's segments have a non-zero end.
+int32_t zzb_trace_inclusion(zzb_run_t r, double* p)
+{
+    if (!r || !p) return fail(ZZB_E_ARG, "null argument");
+    if (!(r->flags & ZZB_FLAG_STICKY)) return fail(ZZB_E_ARG, "inclusion probabilities are accumulated by the sticky samplers only");
+    int32_t st = fetch_state(r);
+    if (st) return st;
+    CtxGuard cg;
+    CU(cuMemcpyDtoH(p, r->s3.p, (size_t)r->d * 8));
+    const double Tl = r->hc.ctl.F;
+    for (int32_t j = 0; j < r->d; ++j) p[j] = p[j] / Tl;
     return ZZB_OK;
 }
 
