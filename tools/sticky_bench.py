@@ -36,3 +36,37 @@ for rep in range(2):
     print(f"sticky heart-like GMRF n={n} (d={d}) T={T}: kernel {ms:.1f} ms, {nev} trace events (reflections {int(acc.sum())}), {num} proposals "
           f"-> {nev / ms * 1e3:.3e} events/s; active fraction at T {np.mean(th != 0):.3f}; windows {st['windows']} passes {st['passes']}")
     run.close()
+# the reference's own sampler for this workload: the STRONG-BOUND sparse sticky ZigZag (src/sparsestickyzz.jl, sspdmp3; upstream runs
+# it with c = 4.26, heart_sparse2.jl:127): zz_run_kernel_csr_strong.  The constant bound must dominate |grad_i| on the path.
+cs = float(sys.argv[3]) if len(sys.argv) > 3 else 4.26
+for rep in range(2):
+    run = z.Run(prob, record_trace=False, kappa=np.full(d, kappa))
+    run.set(strong_c=cs, strong_rule=0)
+    run.upload(0.0, x0, th0, np.full(d, cs), seed=(1, 2))
+    try:
+        ms = run.execute(T)
+    except z.BoundError as e:
+        print("strong-bound sampler: bound too small:", str(e)[:100]); run.close(); break
+    acc, num = run.counts(); nev = run.n_events(); st = run.stats()
+    t, x, th, _ = run.final_state()
+    print(f"STRONG-BOUND sparse sticky (sspdmp3) n={n} (d={d}) T={T} c={cs}: kernel {ms:.1f} ms, {nev} trace events (reflections {int(acc.sum())}), {num} proposals "
+          f"-> {nev / ms * 1e3:.3e} events/s; active fraction at T {np.mean(th != 0):.3f}; windows {st['windows']} rounds {st['passes']}")
+    run.close()
+# BASELINE config 4 itself: the p = 10^5 chain of test/sparsesticky.jl:17-54 (x0 = 0, kappa = 2000/p, c = 2.5, T = 500)
+import scipy.sparse as sp
+p = 100000
+main = np.full(p, 2.1); main[0] = main[-1] = 1.1
+Gc = z.CSC.from_scipy(sp.diags([main, -np.ones(p - 1), -np.ones(p - 1)], [0, 1, -1]).tocsc())
+probc = z.Problem(z.GaussianPotential(Gc), z.ZigZag(Gc, np.zeros(p)))
+Tc = float(sys.argv[4]) if len(sys.argv) > 4 else 100.0
+for name, strong in (("ss_fact kernel (sspdmp)", False), ("strong-bound kernel (sspdmp3)", True)):
+    for rep in range(2):
+        run = z.Run(probc, record_trace=False, kappa=np.full(p, 2000.0 / p))
+        if strong:
+            run.set(strong_c=2.5, strong_rule=0)
+        run.upload(0.0, np.zeros(p), np.ones(p), np.full(p, 2.5), seed=(5, 6))
+        ms = run.execute(Tc)
+        acc, num = run.counts(); nev = run.n_events(); st = run.stats()
+    print(f"config 4 chain p={p} T={Tc} {name}: kernel {ms:.1f} ms, {nev} trace events, {num} proposals -> {nev / ms * 1e3:.3e} events/s; "
+          f"windows {st['windows']} rounds {st['passes']} evals {st['node_evals']}")
+    run.close()
