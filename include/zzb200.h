@@ -61,6 +61,7 @@ extern "C" {
 #define ZZB_FLAG_STICKY 4u      /* sticky ZigZag sspdmp (src/ss_fact.jl): coordinates freeze at 0, thaw after Exp(kappa_i) */
 #define ZZB_FLAG_STICKY_REVERSIBLE 16u /* sspdmp(...; reversible = true): a thawing coordinate re-enters with a random sign, ss_fact.jl:111-113 */
 #define ZZB_FLAG_STICKY_STRONG_UB 32u  /* sspdmp(...; strong_upperbounds = true): a freeze reschedules nobody, ss_fact.jl:97-107 */
+#define ZZB_FLAG_REFRESH 64u    /* ZigZag with velocity refreshments (Z.lambdaref > 0): src/sfact.jl:78-114,188-190; zzb_run_upload_refresh */
 #define ZZB_FLAG_BOOMERANG 8u   /* factorised Boomerang (F::FactBoomerang): rotation around Z.mu, velocity refreshments */
 
 typedef struct zzb_problem_s* zzb_problem_t;
@@ -129,6 +130,13 @@ int32_t zzb_spdmp_boomerang_run(zzb_problem_t p, double t0, const double* x0, co
 int32_t zzb_sspdmp3_run(zzb_problem_t p, const double* x0, const double* theta0, double T, double c, double kappa, int32_t rule,
                         const uint64_t* seed, uint32_t flags, zzb_run_t* out);
 
+/* spdmp / pdmp with Z = ZigZag(Gamma, mu, sigma; lambdaref > 0): velocity refreshments theta_i <- sigma_i * (+-1) at total rate
+ * lambdaref (hasrefresh src/fact_samplers.jl:19; refresh branch src/sfact.jl:78-114, clock :188-190).  Refreshments are trace events
+ * but not acceptances.  Per-coordinate clocks of rate lambdaref / d (superposition of the reference's single clock). */
+int32_t zzb_spdmp_refresh_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, double* c,
+                              const double* sigma, double lambdaref, const uint64_t* seed, int32_t adapt, double factor,
+                              uint32_t flags, zzb_run_t* out);
+
 /* Staged form (what zzb_spdmp_run is made of); lets a caller keep inputs resident in HBM and time the kernel alone. */
 int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_events, zzb_run_t* out);
 int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* theta0, const double* c,
@@ -143,6 +151,7 @@ int32_t zzb_run_ipc_import(zzb_run_t r, int32_t peer_rank, const void* buf, int6
 int32_t zzb_run_range(zzb_run_t r, int64_t* lo, int64_t* hi);       /* owned coordinates [lo, hi), 0-based */
 int32_t zzb_run_upload_kappa(zzb_run_t r, const double* kappa);      /* sticky runs: before zzb_run_upload */
 int32_t zzb_run_upload_boomerang(zzb_run_t r, const double* sigma, double lambdaref, double rho);  /* Boomerang runs: before zzb_run_upload */
+int32_t zzb_run_upload_refresh(zzb_run_t r, const double* sigma, double lambdaref);   /* ZZB_FLAG_REFRESH runs: before zzb_run_upload */
 int32_t zzb_run_reset(zzb_run_t r);                                  /* re-initialise from the inputs resident in HBM */
 int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms);   /* device_ms: CUDA-event time of the kernel(s) */
 int32_t zzb_run_set(zzb_run_t r, const char* key, double value);    /* "delta0", "target_frac" / "target_flip_frac" (proposals / accepted flips per window over d), "tag_limit", "max_windows", "grid" */

@@ -40,7 +40,8 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                    const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
                    const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
                    int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound, const double* kappa,
-                   const double* boom_sigma, double boom_lambdaref, double boom_rho, const ZzHostLogit* hl, const ZzStrong* st = nullptr);
+                   const double* boom_sigma, double boom_lambdaref, double boom_rho, const ZzHostLogit* hl, const ZzStrong* st = nullptr,
+                   const double* refresh_sigma = nullptr, double refresh_lambdaref = 0.0);
 
 // Which schedule the emulation runs: 0 = pass-synchronous (Jacobi) relaxation of round 1; T > 0 = the ASYNCHRONOUS tile-local
 // relaxation of zz_run_body_async with T tiles: per-tile queues (lattice: one per checkerboard colour, processed alternately),
@@ -73,6 +74,16 @@ zzw_run* zzw_spdmp(int64_t d, const int64_t* tcp, const int64_t* trv, const doub
 {
     return zzw_impl(d, tcp, trv, tnz, h, bcp, brv, bnz, mu, t0, x0, th0, T, c_in, seed, adapt, factor, delta0, target_frac,
                     tag_limit, local_bound, kappa, boom_sigma, boom_lambdaref, boom_rho, nullptr);
+}
+
+// ZigZag with velocity refreshments (Z.lambdaref > 0, src/sfact.jl:78-114); contract: zzo_spdmp_refresh in mode ctr | lazy
+zzw_run* zzw_spdmp_refresh(int64_t d, const int64_t* tcp, const int64_t* trv, const double* tnz, const double* h,
+                           const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, const double* sigma, double lambdaref,
+                           double t0, const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
+                           int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit)
+{
+    return zzw_impl(d, tcp, trv, tnz, h, bcp, brv, bnz, mu, t0, x0, th0, T, c_in, seed, adapt, factor, delta0, target_frac,
+                    tag_limit, 0, nullptr, nullptr, 0.0, 0.0, nullptr, nullptr, sigma, lambdaref);
 }
 
 // the schedule with the subsampled logistic target (zz_logit.h; arguments as zzb_problem_create_logistic + zzb_spdmp_run)
@@ -109,7 +120,8 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                    const int64_t* bcp, const int64_t* brv, const double* bnz, const double* mu, double t0,
                    const double* x0, const double* th0, double T, const double* c_in, const uint64_t* seed,
                    int adapt, double factor, double delta0, double target_frac, uint32_t tag_limit, int local_bound, const double* kappa,
-                   const double* boom_sigma, double boom_lambdaref, double boom_rho, const ZzHostLogit* hl, const ZzStrong* st)
+                   const double* boom_sigma, double boom_lambdaref, double boom_rho, const ZzHostLogit* hl, const ZzStrong* st,
+                   const double* refresh_sigma, double refresh_lambdaref)
 {
     zzw_run* r = new zzw_run();
     r->d = d;
@@ -145,7 +157,11 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
     ZzView v; memset(&v, 0, sizeof v); v.nranks = 1; v.hi = (int32_t)d; v.shard = (int32_t)d; v.d = (int32_t)d; v.kin = kin.data(); v.flips = flips.data(); v.priv = priv.data();
     v.tau = tau.data(); v.kctr = kctr.data(); v.seed0 = seed[0]; v.seed1 = seed[1]; v.adapt = adapt; v.factor = factor; v.local_bound = local_bound;
     v.sticky = kappa ? (1 | sticky_opts) : 0; v.fth = (kappa || boom_sigma) ? fth.data() : nullptr; v.kappa = kappa;
-    const bool vel = kappa || boom_sigma;   // lists carry the velocity after each event
+    std::vector<double> rst((size_t)d * 2, 0.0), rspec((size_t)d * 2, 0.0);
+    v.refresh = refresh_sigma ? 1 : 0; v.rsig = refresh_sigma; v.rlam1 = refresh_lambdaref / (double)d; v.rst = rst.data(); v.rspec = rspec.data();
+    if (refresh_sigma) v.fth = fth.data();
+    if (refresh_sigma && !g.grid_m && G.maxdeg > ZZ_NB) { r->status = 1; r->msg = "column too long"; return r; }
+    const bool vel = kappa || boom_sigma || refresh_sigma;   // lists carry the velocity after each event
     v.boom = boom_sigma ? 1 : 0; v.bmu = mu; v.bsig = boom_sigma; v.bref_rate = boom_lambdaref / (double)d; v.brho = boom_rho;
     v.brhobar = sqrt(1 - boom_rho * boom_rho);
     if (boom_sigma && !g.grid_m && G.maxdeg > ZZ_NB) { r->status = 1; r->msg = "column too long"; return r; }
@@ -199,6 +215,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
             ZzSpec& s = spec[j];
             s.a = o.a; s.b = o.b; s.told = o.told; s.tau = o.tau; s.c = o.c; s.k = o.k;
             s.nprop = (uint16_t)o.nprop; s.nflip = (uint8_t)o.nflip; s.flags = (uint8_t)o.flags;
+            if (refresh_sigma) { rspec[2 * (size_t)j] = o.tprop; rspec[2 * (size_t)j + 1] = o.tref; }
             if (o.flags & ZZ_F_OVERFLOW) ovf_seen = true;
             vt[j] = o.viol_t; vl[j] = o.viol_l; vlb[j] = o.viol_lb;
             r->node_evals++;
@@ -272,6 +289,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                     ZzSpec& sp = spec[j];
                     sp.a = oo.a; sp.b = oo.b; sp.told = oo.told; sp.tau = oo.tau; sp.c = oo.c; sp.k = oo.k;
                     sp.nprop = (uint16_t)oo.nprop; sp.nflip = (uint8_t)oo.nflip; sp.flags = (uint8_t)fl_;
+                    if (refresh_sigma) { rspec[2 * (size_t)j] = oo.tprop; rspec[2 * (size_t)j + 1] = oo.tref; }
                     if (fl_ & ZZ_F_OVERFLOW) ovf_seen = true;
                     vt[j] = oo.viol_t; vl[j] = oo.viol_l; vlb[j] = oo.viol_lb;
                     r->node_evals++;
@@ -353,6 +371,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                 }
                 priv[j].a = s.a; priv[j].b = s.b; priv[j].told = s.told; priv[j].c = s.c;
                 tau[j] = s.tau; kctr[j] = s.k;
+                if (refresh_sigma) { rst[2 * (size_t)j] = rspec[2 * (size_t)j]; rst[2 * (size_t)j + 1] = rspec[2 * (size_t)j + 1]; }
                 r->num += s.nprop;
                 if (s.nflip) {
                     int slot; zz_pick_slot(kin[j].hdr[0], kin[j].hdr[1], w0, g_async_tiles > 0 ? 0xffffffffu : cur, slot);
@@ -365,6 +384,9 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
                         if (boom_sigma) {   // reflection / refreshment (zz_commit_node)
                             double tho; zz_boom_at(tf, xf, th, mu[j], fs, &xs, &tho);
                             thn = ft[m];
+                            if (m == 0) r->acc[j] += (s.flags >> 3) & 7u;
+                        } else if (refresh_sigma) {   // reflection or refreshment: the recorded velocity; reflections counted by the timeline
+                            xs = xf + th * (fs - tf); thn = ft[m];
                             if (m == 0) r->acc[j] += (s.flags >> 3) & 7u;
                         } else if (kappa) {   // sticky: flip / freeze / thaw (zz_commit_node)
                             thn = ft[m];

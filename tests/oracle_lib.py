@@ -269,7 +269,7 @@ def wlib():
 
 def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
                delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False, kappa=None, boom=None, logistic=None,
-               strong=None, async_tiles=0, order_seed=1, reversible=False, strong_upperbounds=False):
+               strong=None, async_tiles=0, order_seed=1, reversible=False, strong_upperbounds=False, refresh=None):
     """``strong = rule`` ("sticky" / "reversible"): the strong-bound sparse sticky timeline (zz_strong.h) with scalar ``c`` and
     ``kappa``, target = ``bound``; contract: :func:`sparsestickyzz` with ``ctr=True``."""
     L = wlib()
@@ -284,7 +284,14 @@ def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1,
     mu = np.zeros(d) if mu is None else f8(mu)
     h = None if h is None else f8(h)
     sd = np.array(seed, dtype=np.uint64)
-    if strong is not None:
+    if refresh is not None:   # (sigma, lambdaref): ZigZag with velocity refreshments
+        L.zzw_spdmp_refresh.restype = C.c_void_p
+        r = L.zzw_spdmp_refresh(C.c_int64(d), _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
+                                _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu), _p(f8(refresh[0])), C.c_double(float(refresh[1])),
+                                C.c_double(float(t0)), _p(x0), _p(theta0), C.c_double(float(T)), _p(c), _p(sd), C.c_int(int(adapt)), C.c_double(float(factor)),
+                                C.c_double(float(delta0)), C.c_double(float(target_frac)), C.c_uint32(int(tag_limit)))
+        r = C.c_void_p(r)
+    elif strong is not None:
         r = L.zzw_sparsesticky(d, _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(h), _p(x0), _p(theta0), float(T), float(c[0]),
                                float(kappa), {"sticky": 0, "reversible": 1}[strong], _p(sd), float(delta0), float(target_frac), int(tag_limit))
     elif logistic is not None:

@@ -304,3 +304,30 @@ def test_testiter_fact_sampler_moments(gpu):
     ts, xs = gpu.discretize(tr, 0.5)
     assert np.mean(np.abs(xs.mean(axis=0))) < 2 / math.sqrt(T)                            # :30
     assert np.mean(np.abs(np.cov(xs.T) - np.linalg.inv(G.to_scipy().toarray()))) < 2.5 / math.sqrt(T)   # :31
+
+
+@pytest.mark.parametrize("lattice", [True, False])
+def test_zigzag_refreshments_on_device(gpu, lattice):
+    """spdmp with Z = ZigZag(Gamma, mu, sigma; lambdaref > 0) (hasrefresh: src/fact_samplers.jl:19; refresh branch src/sfact.jl:78-114,
+    188-190) on the device (zz_run_kernel_*_refresh): events (reflections AND refreshments), counters, state against the oracle's
+    per-coordinate-clock contract zzo_spdmp_refresh, bit for bit; refreshments are trace events but not acceptances."""
+    rng = np.random.default_rng(6)
+    if lattice:
+        G = gpu.grid_precision(30, 20, shift=0.3)
+        Gb, mu, h = G, None, None
+    else:
+        G = next(g for g in (gpu.random_sparse_spd(80, deg=2, seed=sd) for sd in range(3, 60)) if np.diff(g.colptr).max() <= 8)
+        Gb, mu, h = G.scaled(0.9), 0.1 * rng.standard_normal(80), 0.2 * rng.standard_normal(80)
+    d = G.n
+    sigma = 0.5 + rng.random(d)
+    x0, th0 = rng.standard_normal(d), sigma * rng.choice(np.array([-1.0, 1.0]), d)
+    c = 3.0 * G.colnorms() * sigma.max()
+    lam = 0.8 * d
+    ref = O.spdmp(G, Gb, 0.0, x0, th0, 5.0, c, h=h, mu=mu, seed=(5, 7), refresh=(sigma, lam), adapt=True)
+    Z = gpu.ZigZag(Gb, np.zeros(d) if mu is None else mu, sigma, lambdaref=lam)
+    Xi, (t, x, th), (acc, num), cc = gpu.spdmp(gpu.GaussianPotential(G, h), 0.0, x0, th0, 5.0, c.copy(), Z, seed=(5, 7), adapt=True)
+    got = R()
+    got.events, got.t, got.x, got.theta, got.c, got.acc, got.num = Xi.events, t, x, th, cc, acc, num
+    O.assert_same_run(ref, got)
+    assert len(ref.events) - int(ref.acc.sum()) > 100 and int(ref.acc.sum()) > 100
+    assert set(np.round(np.abs(Xi.events["theta"]) / sigma[Xi.events["i"] - 1], 12)) == {1.0}    # |theta_i| = sigma_i after every event

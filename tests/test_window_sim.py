@@ -210,3 +210,25 @@ def test_sticky_options_reversible_and_strong_upperbounds(zzb, reversible, stron
     for tiles in (0, 5):
         got = O.window_sim(G, G, 0.0, x0, th0, 6.0, c, kappa=kap, reversible=reversible, strong_upperbounds=strong, async_tiles=tiles)
         O.assert_same_run(ref, got)
+
+
+@pytest.mark.parametrize("lattice,tiles", [(True, 0), (True, 5), (False, 0), (False, 4)])
+def test_zigzag_refreshments(zzb, lattice, tiles):
+    """ZigZag with velocity refreshments (Z.lambdaref > 0: src/sfact.jl:78-114,188-190): the device timeline
+    (zz_timeline_refresh) inside the schedule emulation against the oracle's per-coordinate-clock contract, both schedules."""
+    rng = np.random.default_rng(6)
+    if lattice:
+        G = zzb.grid_precision(9, 7, shift=0.3)
+        Gb, mu, h = G, None, None
+    else:
+        G = zzb.random_sparse_spd(40, deg=2, seed=3)
+        Gb, mu, h = G.scaled(0.9), 0.1 * rng.standard_normal(40), 0.2 * rng.standard_normal(40)
+    d = G.n
+    sigma = 0.5 + rng.random(d)
+    x0, th0 = rng.standard_normal(d), sigma * rng.choice(np.array([-1.0, 1.0]), d)
+    c = 3.0 * G.colnorms() * sigma.max()
+    ref = O.spdmp(G, Gb, 0.0, x0, th0, 6.0, c, h=h, mu=mu, seed=(5, 7), refresh=(sigma, 0.8 * d), adapt=True)
+    nrefresh = len(ref.events) - int(ref.acc.sum())
+    assert nrefresh > 0.5 * 0.8 * d * 6.0 * 0.5 and int(ref.acc.sum()) > 50          # both kinds of event occur
+    got = O.window_sim(G, Gb, 0.0, x0, th0, 6.0, c, h=h, mu=mu, seed=(5, 7), refresh=(sigma, 0.8 * d), adapt=True, async_tiles=tiles)
+    O.assert_same_run(ref, got)

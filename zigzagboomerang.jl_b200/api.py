@@ -316,19 +316,23 @@ class Run:
     """One sampler run on the device (staged form of the C-ABI)."""
 
     def __init__(self, problem: Problem, *, record_trace: bool = True, trace_capacity: int = 0, local_bound: bool = False,
-                 kappa=None, boomerang=None, reversible: bool = False, strong_upperbounds: bool = False):
+                 kappa=None, boomerang=None, reversible: bool = False, strong_upperbounds: bool = False, refresh=None):
         self.problem = problem
         self.d = problem.d
         self._h = C.c_void_p()
         flags = (0 if record_trace else _capi.ZZB_FLAG_NO_TRACE) | (_capi.ZZB_FLAG_LOCAL_BOUND if local_bound else 0) \
             | (_capi.ZZB_FLAG_STICKY if kappa is not None else 0) | (_capi.ZZB_FLAG_BOOMERANG if boomerang is not None else 0) \
             | (_capi.ZZB_FLAG_STICKY_REVERSIBLE if (kappa is not None and reversible) else 0) \
-            | (_capi.ZZB_FLAG_STICKY_STRONG_UB if (kappa is not None and strong_upperbounds) else 0)
+            | (_capi.ZZB_FLAG_STICKY_STRONG_UB if (kappa is not None and strong_upperbounds) else 0) \
+            | (_capi.ZZB_FLAG_REFRESH if refresh is not None else 0)
         self.record_trace = record_trace
         check(_capi.lib().zzb_run_create(problem._h, flags, int(trace_capacity), C.byref(self._h)))
         if kappa is not None:
             self._kappa = f8(kappa)
             check(_capi.lib().zzb_run_upload_kappa(self._h, ptr(self._kappa)))
+        if refresh is not None:     # a ZigZag with lambdaref > 0: velocity refreshments theta_i <- sigma_i * (+-1) (src/sfact.jl:78-114)
+            self._rsigma = f8(refresh.sigma)
+            check(_capi.lib().zzb_run_upload_refresh(self._h, ptr(self._rsigma), float(refresh.lambdaref)))
         if boomerang is not None:   # a FactBoomerang: sigma, lambdaref, rho (its Gamma / mu are the problem's sampler matrices)
             self._sigma = f8(boomerang.sigma)
             check(_capi.lib().zzb_run_upload_boomerang(self._h, ptr(self._sigma), boomerang.lambdaref, boomerang.rho))
@@ -486,8 +490,8 @@ def _as_problem(grad, F):
         raise TypeError("the logistic target runs with ZigZag dynamics only")
     if not isinstance(F, (ZigZag, FactBoomerang)):
         raise TypeError("only ZigZag and FactBoomerang dynamics are implemented on the device path")
-    if isinstance(F, ZigZag) and F.lambdaref != 0.0:
-        raise NotImplementedError("refreshments (lambdaref > 0) are not implemented on the device path")
+    if isinstance(F, ZigZag) and F.lambdaref != 0.0 and isinstance(grad, LogisticSubsampled):
+        raise NotImplementedError("refreshments (lambdaref > 0) with the logistic target are not implemented on the device path")
     return Problem(grad, F), True
 
 
@@ -521,7 +525,10 @@ def spdmp(grad, t0, x0, theta0, T, c, *rest, factor=1.8, adapt=False, seed=None,
     boom = F if isinstance(F, FactBoomerang) else None
     if boom is not None and local_bound:
         raise NotImplementedError("LocalBound with FactBoomerang is not implemented on the device path")
-    run = Run(prob, record_trace=record_trace, local_bound=local_bound, boomerang=boom)
+    refr = F if (isinstance(F, ZigZag) and F.lambdaref != 0.0) else None   # hasrefresh(Z) (src/fact_samplers.jl:19)
+    if refr is not None and local_bound:
+        raise NotImplementedError("LocalBound with ZigZag refreshments is not implemented on the device path")
+    run = Run(prob, record_trace=record_trace, local_bound=local_bound, boomerang=boom, refresh=refr)
     try:
         if tune:
             run.set(**tune)
@@ -661,7 +668,8 @@ class FactSampler:
         if local_bound and isinstance(self.grad, GaussianPotential):   # the bound comes from the target (src/local.jl:2-6)
             F = ZigZag(self.grad.Gamma, np.zeros(self.grad.Gamma.n), F.sigma, lambdaref=F.lambdaref, rho=F.rho)
         prob, own = _as_problem(self.grad, F)
-        run = Run(prob, record_trace=True, local_bound=local_bound, boomerang=F if isinstance(F, FactBoomerang) else None)
+        run = Run(prob, record_trace=True, local_bound=local_bound, boomerang=F if isinstance(F, FactBoomerang) else None,
+                  refresh=F if (isinstance(F, ZigZag) and F.lambdaref != 0.0) else None)
         return prob, own, run, local_bound
 
     def chunks(self):

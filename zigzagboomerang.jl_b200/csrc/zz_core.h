@@ -121,6 +121,15 @@ struct ZzView {
     // Factorised Boomerang (F::FactBoomerang in src/sfact.jl): rotation around bmu, velocity refreshment
     // theta <- brho theta + brhobar bsig N(0,1) at rate bref_rate = lambda_ref / d per coordinate; lists carry
     // (time, velocity after) like the sticky ones (fth)
+    // ZigZag with velocity refreshments (hasrefresh(Z): Z.lambdaref > 0, src/sfact.jl:78-114,188-190; mode ZZ_MODE_REFRESH): one
+    // refreshment clock of rate rlam1 = lambdaref / d per coordinate (superposition of the reference's single clock), refreshed
+    // velocity = rsig[j] * (+-1); lists carry the velocity after each event (fth).  rst[j] = (next proposal time, next
+    // refreshment time) of the frontier -- tau[j] is the earlier of the two -- and rspec[j] the speculative end-of-window pair.
+    int32_t refresh, pad_refresh;
+    const double* rsig;
+    double rlam1;
+    double* rst;      // [d][2]
+    double* rspec;    // [d][2]
     int32_t boom, pad_boom;
     const double* bmu;
     const double* bsig;
@@ -149,6 +158,7 @@ struct ZzNodeOut {
     double fth[ZZ_MAXFLIP];  // sticky only: velocity after each recorded event
     double viol_t, viol_l, viol_lb;
     uint32_t hdr0, hdr1;   // own flip-list headers as read at entry
+    double tprop, tref;    // ZZ_MODE_REFRESH: next proposal / refreshment time after the window
     uint32_t nitems;       // timeline items processed by this evaluation (statistics of the host emulation)
     uint32_t interior;     // evaluated by the lattice-interior path: all four readers exist
 };
@@ -408,6 +418,12 @@ ZZ_HD void zz_init_node(const ZzGraph& g, const ZzView& v, int32_t j, double t0)
         v.tau[j] = lbm ? zz_next_time(t0, dt, pr.c, th, true, renew) : dt;   // sfact.jl:186 has no "+ t0"; local.jl:122 has
     }
     v.kctr[j] = 1u | (renew ? ZZ_RENEW_BIT : 0u);
+    if (v.refresh) {   // sfact.jl:188-190 (per-coordinate clock, contract zzo_spdmp_refresh in mode ctr): second draw of the stream, no "+ t0"
+        const double tref = -zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, 1)) / v.rlam1;
+        v.rst[2 * (size_t)j] = dt; v.rst[2 * (size_t)j + 1] = tref;
+        v.tau[j] = dt <= tref ? dt : tref;
+        v.kctr[j] = 2u;
+    }
 }
 
 #endif  // ZZ_CORE_H

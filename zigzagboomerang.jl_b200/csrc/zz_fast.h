@@ -567,6 +567,99 @@ ZZ_HD void zz_boom_init(ZzHood<NB>& hd, const ZzHoodMu<NB>& hm, const ZzGraph& g
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// ZigZag with velocity refreshments (Z.lambdaref > 0: src/sfact.jl:78-114,188-190) seen from coordinate j.  Own items: proposal
+// (as zz_timeline) and refreshment -- theta_j <- sigma_j * (+-1) (:100-101), next refreshment after Exp(lambdaref / d), then the
+// reschedule of :109-113.  Neighbour items: any recorded event of a trigger neighbour (reflection or refreshment; the lists carry
+// the velocity after).  Contract: zzo_spdmp_refresh in mode ctr | lazy -- per coordinate the draws are: first proposal (k = 0),
+// first refreshment time (k = 1); a proposal consumes (thinning, reschedule); a neighbour's event (reschedule); a refreshment
+// (sign, next refreshment time, reschedule).
+template <int NB>
+ZZ_HD void zz_timeline_refresh(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w, const ZzGraph& g, const ZzView& v,
+                               int32_t j, double H, int incl, uint32_t flags0, ZzNodeOut& o)
+{
+    double th = w.th, tf = w.tf, xf = w.xf;
+    double a = w.a, b = w.b, told = w.told, c = w.c;
+    double c100 = c / 100;
+    double tauP = zz_ld(v.rst + 2 * (size_t)j), tref = zz_ld(v.rst + 2 * (size_t)j + 1);
+    uint32_t k = w.k;
+    const double gmu = g.grid_m ? 0.0 : g.gmu[j];
+    const bool has_h = (!g.same && g.h);
+    const double hj = has_h ? g.h[j] : 0.0;
+    const double sigj = v.rsig[j];
+    uint32_t nprop = 0, nev = 0, nrefl = 0, flags = flags0;
+    o.viol_t = 0.0; o.viol_l = 0.0; o.viol_lb = 0.0;
+    int p = 0;
+    for (int item = 0;; ++item) {
+        const double nt = p < pool.n ? pool.t[p] : ZZ_INF;
+        const int nm = p < pool.n ? pool.m[p] : 0x7fffffff;
+        const bool isprop = tauP <= tref;
+        const double town = isprop ? tauP : tref;
+        const bool own = (town < nt) || (town == nt && hd.self < nm);
+        const double s = own ? town : nt;
+        if (!(s < H || (incl && s == H))) break;
+        if (item >= ZZ_MAXITEMS) { flags |= ZZ_F_OVERFLOW; break; }
+        if (!own) {
+            const double tha = pool.th[p];
+            bool trig = false;
+#pragma unroll
+            for (int m = 0; m < NB; ++m) {
+                if (m == nm) {
+                    hd.xf[m] = hd.xf[m] + hd.th[m] * (s - hd.tf[m]);
+                    hd.tf[m] = s;
+                    hd.th[m] = tha;
+                    trig = (hd.fl[m] & ZZ_NB_TRIG) != 0;
+                }
+            }
+            ++p;
+            if (!trig) continue;
+        }
+        const double xs = xf + th * (s - tf);
+        if (own && !isprop) {                              // refreshment, sfact.jl:100-108
+            const double u1 = zz_u01(v.seed0, v.seed1, (uint64_t)j, k);
+            const double u2 = zz_u01(v.seed0, v.seed1, (uint64_t)j, k + 1u);
+            k += 2u;
+            const double thn = sigj * (u1 < 0.5 ? -1.0 : 1.0);
+            if (nev == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#pragma unroll
+            for (int m = 0; m < ZZ_MAXFLIP; ++m) if (m == (int)nev) { o.fl[m] = s; o.fth[m] = thn; }
+            nev++;
+            xf = xs; tf = s; th = thn;
+            tref = s - zz_log(u2) / v.rlam1;
+        }
+        double gt, gx, gp, gm;
+        zz_eval_hood<NB>(hd, g.same != 0, s, xs, th, gt, gx, gp, gm);
+        double gth = gp;
+        if (own && isprop) {
+            if (has_h) gt = gt - hj;
+            const double l = zz_pos(gt * th);                 // fact_samplers.jl:28-30
+            const double lb = zz_pos(a + b * (s - told));     // sfact.jl:70
+            const double u1 = zz_u01(v.seed0, v.seed1, (uint64_t)j, k++);
+            nprop++;
+            if (u1 * lb < l) {                                // sfact.jl:121
+                if (l >= lb) {
+                    if (v.adapt) { c *= v.factor; c100 = c / 100; }
+                    else if (!(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
+                }
+                if (nev == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
+#pragma unroll
+                for (int m = 0; m < ZZ_MAXFLIP; ++m) if (m == (int)nev) { o.fl[m] = s; o.fth[m] = -th; }
+                nev++; nrefl++;
+                xf = xs; tf = s; th = -th;                    // dynamics.jl:46-49
+                gth = gm;
+            }
+        }
+        a = c + (gx - gmu) * th;                              // fact_samplers.jl:51
+        b = c100 + th * gth;                                  // fact_samplers.jl:52
+        told = s;
+        tauP = s + zz_poisson_time(a, b, zz_u01(v.seed0, v.seed1, (uint64_t)j, k++));   // sfact.jl:112,134,139
+    }
+    o.a = a; o.b = b; o.told = told; o.tau = tauP <= tref ? tauP : tref; o.c = c;
+    o.tprop = tauP; o.tref = tref;
+    o.k = k; o.nprop = nprop; o.nflip = nev; o.flags = flags | (nrefl << 3);
+    o.hdr0 = w.hdr0; o.hdr1 = w.hdr1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Lattice interior (plain ZigZag): the 5-point column {j-M, j-1, j, j+1, j+M} with weights {-1, -1, diag, -1, -1},
 // target == sampler matrix, no linear term, mu = 0.  Same arithmetic as zz_gather_grid + zz_timeline<5, false>, operation
 // for operation -- (-1) * x is written -x, gx - 0 is written gx, both exact -- with every flag test, bounds test and weight
@@ -672,7 +765,8 @@ ZZ_HD void zz_process_interior(const ZzGraph& g, const ZzView& v, int32_t j, dou
 #define ZZ_MODE_BOOM 3     // factorised Boomerang (F::FactBoomerang in src/sfact.jl)
 #define ZZ_MODE_LOGIT 4    // plain ZigZag with the subsampled logistic target (zz_logit.h; general sparse kernels only)
 #define ZZ_MODE_STRONG 5   // strong-bound sparse sticky ZigZag (zz_strong.h); only in -DZZ_ENABLE_STRONG builds of the image
-#define ZZ_MODE_HAS_VEL(M) ((M) == ZZ_MODE_STICKY || (M) == ZZ_MODE_BOOM || (M) == ZZ_MODE_STRONG)   // flip lists carry the velocity after each event
+#define ZZ_MODE_REFRESH 6  // ZigZag with velocity refreshments (Z.lambdaref > 0, src/sfact.jl:78-114)
+#define ZZ_MODE_HAS_VEL(M) ((M) == ZZ_MODE_STICKY || (M) == ZZ_MODE_BOOM || (M) == ZZ_MODE_STRONG || (M) == ZZ_MODE_REFRESH)   // flip lists carry the velocity after each event
 template <int KIND, int MODE, bool MG = true>
 ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                              uint32_t cur, bool first_iter, ZzNodeOut& o)
@@ -695,9 +789,10 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
             zz_timeline_boom<5>(hd, hm, pool, w, g, v, j, H, incl, flags, o);
             return;
         }
-        zz_gather_grid<MG, MODE == ZZ_MODE_STICKY>(g, v, j, w0, cur, first_iter, hd, pool, flags);
+        zz_gather_grid<MG, MODE == ZZ_MODE_STICKY || MODE == ZZ_MODE_REFRESH>(g, v, j, w0, cur, first_iter, hd, pool, flags);
         ZZ_SEG(2);
-        if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<5>(hd, pool, w, g, v, j, H, incl, flags, o);
+        if (MODE == ZZ_MODE_REFRESH) zz_timeline_refresh<5>(hd, pool, w, g, v, j, H, incl, flags, o);
+        else if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<5>(hd, pool, w, g, v, j, H, incl, flags, o);
         else zz_timeline<5, MODE == ZZ_MODE_LB>(hd, pool, w, g, v, j, H, incl, flags, o);
         ZZ_SEG(5);
         return;
@@ -711,8 +806,9 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
             zz_timeline_boom<ZZ_NB>(hd, hm, pool, w, g, v, j, H, incl, flags, o);
             return;
         }
-        zz_gather_csr<ZZ_NB, MG, MODE == ZZ_MODE_STICKY>(g, v, j, w0, cur, first_iter, hd, pool, flags);
-        if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<ZZ_NB>(hd, pool, w, g, v, j, H, incl, flags, o);
+        zz_gather_csr<ZZ_NB, MG, MODE == ZZ_MODE_STICKY || MODE == ZZ_MODE_REFRESH>(g, v, j, w0, cur, first_iter, hd, pool, flags);
+        if (MODE == ZZ_MODE_REFRESH) zz_timeline_refresh<ZZ_NB>(hd, pool, w, g, v, j, H, incl, flags, o);
+        else if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<ZZ_NB>(hd, pool, w, g, v, j, H, incl, flags, o);
         else zz_timeline<ZZ_NB, MODE == ZZ_MODE_LB>(hd, pool, w, g, v, j, H, incl, flags, o);
         return;
     }
@@ -723,7 +819,10 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
 ZZ_HD void zz_process_node(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                            uint32_t cur, bool first_iter, ZzNodeOut& o)
 {
-    if (v.boom) {
+    if (v.refresh) {
+        if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, ZZ_MODE_REFRESH>(g, v, j, H, incl, w0, cur, first_iter, o);
+        else zz_process_node_k<ZZ_KIND_CSR, ZZ_MODE_REFRESH>(g, v, j, H, incl, w0, cur, first_iter, o);
+    } else if (v.boom) {
         if (g.grid_m) zz_process_node_k<ZZ_KIND_GRID, ZZ_MODE_BOOM>(g, v, j, H, incl, w0, cur, first_iter, o);
         else zz_process_node_k<ZZ_KIND_CSR, ZZ_MODE_BOOM>(g, v, j, H, incl, w0, cur, first_iter, o);
     } else if (v.sticky) {

@@ -439,6 +439,10 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, con
     pq[1] = make_double2(s.told, s.c);
     P.v.tau[j] = s.tau;
     P.v.kctr[j] = s.k;
+    if (MODE == ZZ_MODE_REFRESH) {   // next proposal / refreshment time (tau is the earlier of the two)
+        const double2 rs = __ldcg(reinterpret_cast<const double2*>(P.v.rspec) + j);
+        reinterpret_cast<double2*>(P.v.rst)[j] = rs;
+    }
     nprop_acc += s.nprop;
     if (s.flags & ZZ_F_STICKY_ERR) atomicExch(&C->viol, 2u);      // error("x[i] !~ 0"), ss_fact.jl:89-91
     if (s.nflip) {
@@ -466,7 +470,8 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, con
         double a3 = (ft && P.s3) ? __ldcg(P.s3 + j) : 0.0;
         const bool boom = (MODE == ZZ_MODE_BOOM);
         const double muj = boom ? P.v.bmu[j] : 0.0;
-        unsigned int nrefl = boom ? ((s.flags >> 3) & 7u) : 0u;   // Boomerang: reflections counted by the timeline (refreshments are events too)
+        const bool counted = boom || MODE == ZZ_MODE_REFRESH;     // reflections counted by the timeline (refreshments are events too)
+        unsigned int nrefl = counted ? ((s.flags >> 3) & 7u) : 0u;
         for (unsigned int m = 0; m < s.nflip; ++m) {
             const double fs = __ldcg(fl + m);
             double xs, thn;
@@ -478,7 +483,7 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, con
                 thn = __ldcg(ft + m);
                 if (thn == 0.0) xs = -0.0 * th;
                 else if (th == 0.0) xs = xf;
-                else { xs = xf + th * (fs - tf); nrefl++; }
+                else { xs = xf + th * (fs - tf); if (!counted) nrefl++; }
             } else {
                 xs = xf + th * (fs - tf); thn = -th; nrefl++;
             }
@@ -1405,6 +1410,7 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
     }
     ZzNodeOut oo = o; oo.flags = flags;
     zz_store_spec(P.spec + j, oo);
+    if (MODE == ZZ_MODE_REFRESH) reinterpret_cast<double2*>(P.v.rspec)[j] = make_double2(o.tprop, o.tref);
     if (flags & ZZ_F_VIOL) {
         double* vi = P.viol_info + (size_t)j * 3;
         vi[0] = o.viol_t; vi[1] = o.viol_l; vi[2] = o.viol_lb;
@@ -1838,5 +1844,7 @@ ZZ_RUN_KERNEL(zz_run_kernel_grid_boom, ZZ_KIND_GRID, false, ZZ_MODE_BOOM, ZZ_ASY
 ZZ_RUN_KERNEL(zz_run_kernel_csr_boom, ZZ_KIND_CSR, false, ZZ_MODE_BOOM, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_logit, ZZ_KIND_CSR, false, ZZ_MODE_LOGIT, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_strong, ZZ_KIND_CSR, false, ZZ_MODE_STRONG, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_refresh, ZZ_KIND_GRID, false, ZZ_MODE_REFRESH, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_refresh, ZZ_KIND_CSR, false, ZZ_MODE_REFRESH, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_grid_sync, ZZ_KIND_GRID, false, ZZ_MODE_PLAIN, 0)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_sync, ZZ_KIND_CSR, false, ZZ_MODE_PLAIN, 0)

@@ -84,10 +84,10 @@ static int32_t cu_fail(CUresult r, const char* what)
     } while (0)
 
 // --------------------------------------------------------------------------------------------- global state
-#define ZZ_NKERN 16   // event-loop kernels in the image (see zzb_init)
+#define ZZ_NKERN 18   // event-loop kernels in the image (see zzb_init)
 #define ZZ_KERN_BLOCK_IDX(k) ((k) == 12 || (k) == 13 ? 1 : ((k) & 1))
 #define ZZ_RUN_BLOCK_OF(r) ZZ_KERN_BLOCK_IDX((r)->kidx())      // the logistic / strong kernels are general-sparse kernels on any graph
-#define ZZ_KERN_ASYNC(k) ((k) < 14)   // asynchronous tile-local relaxation (zz_run_body_async)
+#define ZZ_KERN_ASYNC(k) ((k) < 14 || (k) >= 16)   // asynchronous tile-local relaxation (zz_run_body_async)
 struct Global {
     bool ready = false;
     CUdevice dev = 0; int dev_id = 0;
@@ -193,6 +193,7 @@ struct zzb_run_s {
     {
         if (strong) return 13;
         if (prob && prob->logit) return 12;
+        if (flags & ZZB_FLAG_REFRESH) return 16 + kind;
         if (flags & ZZB_FLAG_BOOMERANG) return 10 + kind;
         if (flags & ZZB_FLAG_STICKY) return 8 + kind;
         if (!schedule && nranks <= 1 && !(flags & ZZB_FLAG_LOCAL_BOUND)) return 14 + kind;
@@ -200,6 +201,7 @@ struct zzb_run_s {
     }
     DevBuf dfth, kappa; bool have_kappa = false;
     DevBuf bmu, bsig; bool have_boom = false; double lambdaref = 0, rho = 0;
+    DevBuf rsig, rst, rspec; bool have_refresh = false; double rlambdaref = 0;   // ZigZag with refreshments (ZZB_FLAG_REFRESH)
     DevBuf gridbuf; double grid_dt = 0; long long grid_n = 0;   // device-side discretize
     int rank = 0, nranks = 1, shard = 0, lo = 0, hi = 0;
     CUdeviceptr peer[ZZ_MAXRANKS][8] = {};   // imported mappings: kin, flips, dstamp, wl0, wl1, wl2, touched, ctl
@@ -263,7 +265,8 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
                                          "zz_run_kernel_grid_lb", "zz_run_kernel_csr_lb", "zz_run_kernel_grid_multi_lb", "zz_run_kernel_csr_multi_lb",
                                          "zz_run_kernel_grid_sticky", "zz_run_kernel_csr_sticky", "zz_run_kernel_grid_boom", "zz_run_kernel_csr_boom",
                                          "zz_run_kernel_csr_logit", "zz_run_kernel_csr_strong",
-                                         "zz_run_kernel_grid_sync", "zz_run_kernel_csr_sync" };   // 14, 15: round-1 schedule (A/B reference)
+                                         "zz_run_kernel_grid_sync", "zz_run_kernel_csr_sync",      // 14, 15: round-1 schedule (A/B reference)
+                                         "zz_run_kernel_grid_refresh", "zz_run_kernel_csr_refresh" };   // 16, 17: ZigZag with refreshments
     CU(cuModuleGetFunction(&G.f_init_strong, G.mod, "zz_init_kernel_strong"));
     for (int k = 0; k < ZZ_NKERN; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
@@ -434,6 +437,10 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     if ((flags & ZZB_FLAG_STICKY) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB)
         return fail(ZZB_E_ARG, "the sticky kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB, p->hg.maxdeg);
     if ((flags & ZZB_FLAG_BOOMERANG) && (flags & (ZZB_FLAG_STICKY | ZZB_FLAG_LOCAL_BOUND))) return fail(ZZB_E_ARG, "Boomerang cannot be combined with sticky / LocalBound");
+    if ((flags & ZZB_FLAG_REFRESH) && (flags & (ZZB_FLAG_STICKY | ZZB_FLAG_LOCAL_BOUND | ZZB_FLAG_BOOMERANG))) return fail(ZZB_E_ARG, "ZigZag refreshments cannot be combined with sticky / LocalBound / Boomerang");
+    if ((flags & ZZB_FLAG_REFRESH) && p->logit) return fail(ZZB_E_ARG, "ZigZag refreshments are not available with the logistic target");
+    if ((flags & ZZB_FLAG_REFRESH) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB)
+        return fail(ZZB_E_ARG, "the refreshment kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB, p->hg.maxdeg);
     if ((flags & ZZB_FLAG_BOOMERANG) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB)
         return fail(ZZB_E_ARG, "the Boomerang kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB, p->hg.maxdeg);
     if ((flags & ZZB_FLAG_LOCAL_BOUND) && !p->hg.bnd_eq_tgt)
@@ -451,6 +458,7 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     AL(ctl, sizeof(ZzDevCtl));
     AL(in_x, d * 8); AL(in_th, d * 8); AL(in_c, d * 8);
     if (flags & ZZB_FLAG_STICKY) { AL(dfth, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(kappa, d * 8); AL(s3, d * 8); }
+    if (flags & ZZB_FLAG_REFRESH) { AL(dfth, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(rsig, d * 8); AL(rst, d * 16); AL(rspec, d * 16); }
     if (flags & ZZB_FLAG_BOOMERANG) {
         AL(dfth, d * 2 * ZZ_MAXFLIP * sizeof(double)); AL(bsig, d * 8);
         if (!st) st = upload(r->bmu, p->hg.mu.data(), d * 8);
@@ -527,7 +535,12 @@ static void fill_params(zzb_run_s* r)
     P.v.sticky = (r->flags & ZZB_FLAG_STICKY) ? (1 | ((r->flags & ZZB_FLAG_STICKY_REVERSIBLE) ? ZZ_STICKY_REVERSIBLE : 0) |
                                                  ((r->flags & ZZB_FLAG_STICKY_STRONG_UB) ? ZZ_STICKY_STRONG_UB : 0)) : 0;
     P.v.boom = (r->flags & ZZB_FLAG_BOOMERANG) ? 1 : 0;
-    P.v.fth = (P.v.sticky || P.v.boom) ? r->dfth.as<double>() : nullptr;
+    P.v.refresh = (r->flags & ZZB_FLAG_REFRESH) ? 1 : 0;
+    P.v.fth = (P.v.sticky || P.v.boom || P.v.refresh) ? r->dfth.as<double>() : nullptr;
+    if (P.v.refresh) {
+        P.v.rsig = r->rsig.as<double>(); P.v.rlam1 = r->rlambdaref / (double)r->d;
+        P.v.rst = r->rst.as<double>(); P.v.rspec = r->rspec.as<double>();
+    }
     if (P.v.boom) {
         P.v.bmu = r->bmu.as<double>(); P.v.bsig = r->bsig.as<double>();
         P.v.bref_rate = r->lambdaref / (double)r->d; P.v.brho = r->rho; P.v.brhobar = sqrt(1 - r->rho * r->rho);
@@ -666,6 +679,21 @@ int32_t zzb_run_upload_boomerang(zzb_run_t r, const double* sigma, double lambda
     return ZZB_OK;
 }
 
+// ZigZag velocity refreshments (Z = ZigZag(Gamma, mu, sigma; lambdaref > 0): hasrefresh(Z), src/fact_samplers.jl:19, src/sfact.jl:78-114):
+// sigma scales the refreshed velocities (theta_i <- sigma_i * (+-1)), lambdaref = total refreshment rate.  Before zzb_run_upload.
+int32_t zzb_run_upload_refresh(zzb_run_t r, const double* sigma, double lambdaref)
+{
+    if (!r || !sigma) return fail(ZZB_E_ARG, "null argument");
+    if (!(r->flags & ZZB_FLAG_REFRESH)) return fail(ZZB_E_ARG, "run was not created with ZZB_FLAG_REFRESH");
+    if (!G.ready) return fail(ZZB_E_CUDA, "zzb_init has not succeeded");
+    if (!(lambdaref > 0.0)) return fail(ZZB_E_ARG, "refreshments need lambdaref > 0");
+    for (int32_t j = 0; j < r->d; ++j) if (!(sigma[j] > 0.0)) return fail(ZZB_E_ARG, "sigma[%d] must be positive", j + 1);
+    CtxGuard cg;
+    CU(cuMemcpyHtoD(r->rsig.p, sigma, (size_t)r->d * 8));
+    r->rlambdaref = lambdaref; r->have_refresh = true;
+    return ZZB_OK;
+}
+
 // (Re)initialise the device state from the inputs already resident in HBM: per-coordinate records, initial
 // bounds and first proposal times (sfact.jl:167-187).  No host<->device traffic except the 200-byte control block.
 int32_t zzb_run_reset(zzb_run_t r)
@@ -675,6 +703,8 @@ int32_t zzb_run_reset(zzb_run_t r)
     if (!r->have_inputs) return fail(ZZB_E_ARG, "zzb_run_upload must precede zzb_run_reset");
     if ((r->flags & ZZB_FLAG_STICKY) && !r->have_kappa) return fail(ZZB_E_ARG, "zzb_run_upload_kappa must precede zzb_run_upload for a sticky run");
     if ((r->flags & ZZB_FLAG_BOOMERANG) && !r->have_boom) return fail(ZZB_E_ARG, "zzb_run_upload_boomerang must precede zzb_run_upload for a Boomerang run");
+    if ((r->flags & ZZB_FLAG_REFRESH) && !r->have_refresh) return fail(ZZB_E_ARG, "zzb_run_upload_refresh must precede zzb_run_upload for a run with ZZB_FLAG_REFRESH");
+    if ((r->flags & ZZB_FLAG_REFRESH) && r->nranks > 1) return fail(ZZB_E_ARG, "ZigZag refreshments are not sharded yet");
     if ((r->flags & ZZB_FLAG_STICKY) && r->adapt) return fail(ZZB_E_ARG, "adapt is not supported by the sticky sampler on the device path");
     for (int q = 0; q < r->nranks; ++q)
         if (q != r->rank && !r->peer_open[q]) return fail(ZZB_E_ARG, "peer %d of a sharded run has not been imported", q);
@@ -1007,6 +1037,29 @@ int32_t zzb_spdmp_boomerang_run(zzb_problem_t p, double t0, const double* x0, co
     int32_t st = zzb_run_create(p, flags | ZZB_FLAG_BOOMERANG, 0, &r);
     if (st) return st;
     st = zzb_run_upload_boomerang(r, sigma, lambdaref, rho);
+    if (!st) st = zzb_run_upload(r, t0, x0, theta0, c, seed, adapt, factor);
+    if (!st) st = zzb_run_execute(r, T, nullptr);
+    if (st && st != ZZB_E_BOUND) { zzb_run_free(r); return st; }
+    int32_t st2 = fetch_state(r);
+    if (st2) { zzb_run_free(r); return st2; }
+    memcpy(c, r->fc.data(), (size_t)r->d * 8);
+    *out = r;
+    if (st == ZZB_E_BOUND)
+        fail(ZZB_E_BOUND, "Tuning parameter `c` too small. (coordinate %d, t = %.17g, l = %.17g, lb = %.17g)", r->hc.viol_i,
+             r->hc.viol_t, r->hc.viol_l, r->hc.viol_lb);
+    return st;
+}
+
+// spdmp / pdmp with Z = ZigZag(Gamma, mu, sigma; lambdaref > 0): the refresh branch of src/sfact.jl:78-114,188-190 (one-call form)
+int32_t zzb_spdmp_refresh_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, double* c,
+                              const double* sigma, double lambdaref, const uint64_t* seed, int32_t adapt, double factor,
+                              uint32_t flags, zzb_run_t* out)
+{
+    if (!out || !c || !sigma) return fail(ZZB_E_ARG, "null argument");
+    zzb_run_t r = nullptr;
+    int32_t st = zzb_run_create(p, flags | ZZB_FLAG_REFRESH, 0, &r);
+    if (st) return st;
+    st = zzb_run_upload_refresh(r, sigma, lambdaref);
     if (!st) st = zzb_run_upload(r, t0, x0, theta0, c, seed, adapt, factor);
     if (!st) st = zzb_run_execute(r, T, nullptr);
     if (st && st != ZZB_E_BOUND) { zzb_run_free(r); return st; }

@@ -121,7 +121,7 @@ function device_run(kind::Symbol, ∇ϕ::Union{GaussianPotential,LogisticSubsamp
     h = (logistic || ∇ϕ.h === nothing) ? Ptr{Float64}(C_NULL) : pointer(∇ϕ.h)
     sd = UInt64[seed[1], seed[2]]
     κv = κ === nothing ? Float64[] : Vector{Float64}(κ isa Number ? fill(κ, d) : κ)
-    σv = kind === :boomerang ? Vector{Float64}(F.σ) : Float64[]
+    σv = (kind === :boomerang || kind === :refresh) ? Vector{Float64}(F.σ) : Float64[]
     GC.@preserve Γt Γb μ x0v θ0v cv sd κv σv ∇ϕ begin
         if logistic
             create_problem(prob, ∇ϕ, F, μ, d)
@@ -140,6 +140,11 @@ function device_run(kind::Symbol, ∇ϕ::Union{GaussianPotential,LogisticSubsamp
             ccall((:zzb_sspdmp_run, libzzb200), Int32,
                   (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{UInt64}, UInt32,
                    Ref{Ptr{Cvoid}}), prob[], t0, x0v, θ0v, T, cv, κv, sd, flags, run)
+        elseif kind === :refresh          # spdmp with Z.λref > 0 (hasrefresh, src/fact_samplers.jl:19): refresh branch src/sfact.jl:78-114
+            ccall((:zzb_spdmp_refresh_run, libzzb200), Int32,
+                  (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Float64,
+                   Ptr{UInt64}, Int32, Float64, UInt32, Ref{Ptr{Cvoid}}),
+                  prob[], t0, x0v, θ0v, T, cv, σv, F.λref, sd, adapt, factor, flags, run)
         elseif kind === :boomerang        # spdmp with F::FactBoomerang, src/sfact.jl:29-48,73-145
             ccall((:zzb_spdmp_boomerang_run, libzzb200), Int32,
                   (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Float64,
@@ -181,9 +186,8 @@ const Nbhd = Union{ZigZagBoomerang.All,ZigZagBoomerang.Matched}
 # spdmp / pdmp, F::ZigZag (src/sfact.jl:162-214,236).  Matched() and All() select the same kernel (INTEGRATION.md).
 function spdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G::Nbhd, F::ZigZag, args...;
                factor = 1.8, adapt = false, adaptscale = false, progress = false, progress_stops = 20, seed = Seed())
-    F.λref == 0 || error("ZigZag refreshments (λref > 0) are not implemented on the device path")
     adaptscale && error("adaptscale = true is not implemented on the device path")
-    Ξ, u, an, cv = device_run(:zigzag, ∇ϕ, t0, x0, θ0, T, c, F; factor = factor, adapt = adapt, seed = seed)
+    Ξ, u, an, cv = device_run(F.λref == 0 ? :zigzag : :refresh, ∇ϕ, t0, x0, θ0, T, c, F; factor = factor, adapt = adapt, seed = seed)
     c .= cv                                            # adapted bounds, like the in-place `adapt!` of the reference
     Ξ, u, an, c
 end
