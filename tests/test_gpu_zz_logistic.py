@@ -11,12 +11,15 @@ import oracle_lib as O
 pytestmark = pytest.mark.gpu
 
 
+# schedule 2 = sequential chains (zz_seq.cuh, the default for this target), 1 = the windowed relaxation (zz_run_kernel_csr_logit)
+@pytest.mark.parametrize("schedule", [2, 1])
 @pytest.mark.parametrize("case", LC.SMALL)
-def test_small_designs_bit_exact(gpu, case):
+def test_small_designs_bit_exact(gpu, case, schedule):
     *design, T = case
     cfg = LC.make(gpu, *design)
     ref = LC.run_oracle(O, cfg, T)
-    got, Xi = LC.run_device(gpu, cfg, T)
+    got, Xi = LC.run_device(gpu, cfg, T, tune=dict(schedule=schedule))
+    assert (Xi.stats["windows"] == 0) == (schedule == 2)
     O.assert_same_run(ref, got)
     assert (got.c != cfg["c"]).any()                       # adapt = true multiplied some bounds by `factor`
     m1, m2 = Xi.moments
@@ -28,15 +31,16 @@ def test_window_policy_and_tag_rebase_do_not_change_results(gpu):
     cfg = LC.make(gpu, *design)
     ref = LC.run_oracle(O, cfg, T)
     for tune in (dict(delta0=1e-3, target_frac=0.1), dict(delta0=2.0, target_frac=4.0, tag_limit=40), dict(grid=3)):
-        got, _ = LC.run_device(gpu, cfg, T, tune=tune)
+        got, _ = LC.run_device(gpu, cfg, T, tune=dict(schedule=1, **tune))
         O.assert_same_run(ref, got)
 
 
 def test_bound_violation_error(gpu):
     """adapt = false with the script's c = 0.01: error("Tuning parameter `c` too small."), sfact.jl:124."""
     cfg = LC.make(gpu, *LC.SMALL[0][:4])
-    with pytest.raises(gpu.BoundError, match="Tuning parameter `c` too small"):
-        LC.run_device(gpu, cfg, 20.0, adapt=False)
+    for schedule in (2, 1):
+        with pytest.raises(gpu.BoundError, match="Tuning parameter `c` too small"):
+            LC.run_device(gpu, cfg, 20.0, adapt=False, tune=dict(schedule=schedule))
 
 
 def test_full_size_config3_bit_exact(gpu):
@@ -44,11 +48,12 @@ def test_full_size_config3_bit_exact(gpu):
     cfg = LC.make(gpu, *LC.FULL)
     T = 25.0
     ref = LC.run_oracle(O, cfg, T)
-    got, Xi = LC.run_device(gpu, cfg, T)
-    O.assert_same_run(ref, got)
-    assert len(got.events) > 5000
-    print(f"config 3: {len(got.events)} events, {got.num} proposals in {Xi.device_ms:.1f} ms on the device "
-          f"({ref.loop_seconds * 1e3:.1f} ms in the oracle); stats {Xi.stats}")
+    for schedule in (2, 1):
+        got, Xi = LC.run_device(gpu, cfg, T, tune=dict(schedule=schedule))
+        O.assert_same_run(ref, got)
+        assert len(got.events) > 5000
+        print(f"config 3, schedule {schedule}: {len(got.events)} events, {got.num} proposals in {Xi.device_ms:.1f} ms on the device "
+              f"({ref.loop_seconds * 1e3:.1f} ms in the oracle); stats {Xi.stats}")
 
 
 def test_refuses_unsupported_combinations(gpu):
@@ -73,11 +78,12 @@ def test_replicas_bit_exact(gpu):
     R, T = 8, 4.0
     big = LC.replicas(gpu, cfg, R)
     ref = LC.run_oracle(O, big, T)
-    got, Xi = LC.run_device(gpu, big, T)
-    O.assert_same_run(ref, got)
-    one, Xi1 = LC.run_device(gpu, cfg, T)
-    print(f"config 3 replicas: R = {R}: {len(got.events)} events in {Xi.device_ms:.1f} ms; R = 1: {len(one.events)} events in "
-          f"{Xi1.device_ms:.1f} ms; oracle (R = {R}) {ref.loop_seconds * 1e3:.1f} ms")
+    for schedule in (2, 1):
+        got, Xi = LC.run_device(gpu, big, T, tune=dict(schedule=schedule))
+        O.assert_same_run(ref, got)
+        one, Xi1 = LC.run_device(gpu, cfg, T, tune=dict(schedule=schedule))
+        print(f"config 3 replicas, schedule {schedule}: R = {R}: {len(got.events)} events in {Xi.device_ms:.1f} ms; R = 1: {len(one.events)} "
+              f"events in {Xi1.device_ms:.1f} ms; oracle (R = {R}) {ref.loop_seconds * 1e3:.1f} ms")
 
 
 def test_random_designs_on_the_device(gpu):
@@ -87,8 +93,10 @@ def test_random_designs_on_the_device(gpu):
     spec = importlib.util.spec_from_file_location("fuzz_logistic", os.path.join(os.path.dirname(os.path.dirname(__file__)), "tools", "fuzz_logistic.py"))
     fz = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(fz)
-    n_ok, n_err = fz.run(gpu, 11, 25, gpu=True, verbose=False)
+    n_ok, n_err = fz.run(gpu, 11, 25, gpu=True, verbose=False)                 # default schedule: sequential chains
     assert n_ok >= 12
+    n_ok, n_err = fz.run(gpu, 12, 12, gpu=True, verbose=False, schedule=1)     # windowed relaxation
+    assert n_ok >= 5
 
 
 def test_device_reproduces_logistic_fixture(gpu):

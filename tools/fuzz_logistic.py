@@ -16,7 +16,7 @@ import logistic_cases as LC  # noqa: E402
 import oracle_lib as O  # noqa: E402
 
 
-def run(z, seed, n, gpu=False, verbose=True):
+def run(z, seed, n, gpu=False, verbose=True, schedule=None):
     rng = np.random.default_rng(seed)
     n_ok = n_err = 0
     t0 = time.time()
@@ -35,6 +35,8 @@ def run(z, seed, n, gpu=False, verbose=True):
         kw = dict(delta0=float(10 ** rng.uniform(-3, 0.5)), target_frac=float(10 ** rng.uniform(-1.3, 0.7)))
         if rng.random() < 0.3:
             kw["tag_limit"] = int(rng.integers(30, 200))
+        if gpu and schedule is not None:   # 1: windowed relaxation, 2: sequential chains (the default for this target)
+            kw["schedule"] = schedule
         try:
             ref = LC.run_oracle(O, cfg, T, seed=sd, adapt=adapt, factor=factor, c=c)
         except O.BoundError:

@@ -1,5 +1,6 @@
 """Config 3 (scripts/logistic.jl, n = 8840, p = 442) on the device: time of the event loop for R independent replicas run as one
-block-diagonal problem, next to the single-threaded oracle.  python tools/logit_bench.py [T] [R ...]"""
+block-diagonal problem, next to the single-threaded oracle.  python tools/logit_bench.py [T] [R ...]
+SCHEDULE=1 in the environment times the windowed relaxation instead of the sequential chains (the default for this target)."""
 import os
 import sys
 import time
@@ -23,7 +24,7 @@ for R in Rs:
     t0 = time.time()
     big = cfg if R == 1 else LC.replicas(z, cfg, R)
     t1 = time.time()
-    got, Xi = LC.run_device(z, big, T)
+    got, Xi = LC.run_device(z, big, T, tune=dict(schedule=int(os.environ.get("SCHEDULE", "2"))))
     st = Xi.stats
     print(f"R = {R}: d = {big['p']}, {len(got.events)} events, {got.num} proposals in {Xi.device_ms:.1f} ms on the device = "
           f"{len(got.events) / (Xi.device_ms * 1e-3):.3g} events/s; windows {st['windows']}, passes {st['passes']}, evaluations {st['node_evals']}, "

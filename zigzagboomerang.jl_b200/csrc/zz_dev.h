@@ -129,6 +129,19 @@ struct ZzParams {
     ZzStrong st;
 };
 
+// Sequential chains (zz_seq.cuh): one warp runs the exact event loop of one connected component of the dependency graph.
+// Compact 0-based CSC copies of the sampler matrix Z.Gamma (bound and reschedule lists, G1[i] = rows of column i) and -- for a
+// Gaussian target that is not the same object -- of the target precision; comp[] holds the ncomp + 1 component boundaries
+// (components are contiguous index ranges).  phase: 0 = every item before T; 1 = probe (no writes) for the first accepted flip
+// at or after T, its time min-reduced into ctl->smin_key[0]; 2 = every item up to and including that time.
+struct ZzSeq {
+    const int32_t* bcp; const int32_t* brow; const double* bval;
+    const int32_t* tcp; const int32_t* trow; const double* tval;
+    const int32_t* comp;
+    int32_t ncomp, phase, ncmax, pad;
+};
+#define ZZ_SEQ_BYTES_PER_COORD 80u   // shared memory per coordinate of a chain (zz_seq.cuh)
+
 // order-preserving map double -> uint64 (so atomicMin works for any sign)
 ZZ_HD unsigned long long zz_key(double x)
 {

@@ -1848,3 +1848,5 @@ ZZ_RUN_KERNEL(zz_run_kernel_grid_refresh, ZZ_KIND_GRID, false, ZZ_MODE_REFRESH, 
 ZZ_RUN_KERNEL(zz_run_kernel_csr_refresh, ZZ_KIND_CSR, false, ZZ_MODE_REFRESH, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_grid_sync, ZZ_KIND_GRID, false, ZZ_MODE_PLAIN, 0)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_sync, ZZ_KIND_CSR, false, ZZ_MODE_PLAIN, 0)
+
+#include "zz_seq.cuh"

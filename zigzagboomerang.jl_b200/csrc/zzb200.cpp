@@ -22,6 +22,7 @@
 #include "zz_dev.h"
 #include "zz_host_graph.h"
 #include "zz_host_logit.h"
+#include "zz_host_seq.h"
 
 #define ZZ_BLOCK 256
 
@@ -95,6 +96,7 @@ struct Global {
     CUmodule mod = nullptr;
     CUfunction f_init_strong = nullptr;
     CUfunction f_math_probe = nullptr;
+    CUfunction f_seq = nullptr, f_seq_logit = nullptr;
     CUfunction f_ts_hist = nullptr, f_ts_scan = nullptr, f_ts_scatter = nullptr, f_ts_sort = nullptr;
     CUfunction f_setup = nullptr, f_init = nullptr, f_init_boom = nullptr, f_run[ZZ_NKERN] = {}, f_export = nullptr, f_grid_tail = nullptr;
     CUstream stream = nullptr;
@@ -159,6 +161,10 @@ struct zzb_problem_s {
     ZzHostLogit hl;
     DevBuf l_acp, l_arow, l_aval, l_rp, l_rcol, l_rval, l_y, l_ny, l_u0;
     ZzLogit lg;
+    // sequential-chain schedule (zz_seq.cuh): compact matrices + connected components; hs.ok says whether it is available
+    ZzHostSeq hs;
+    DevBuf s_bcp, s_brow, s_bval, s_tcp, s_trow, s_tval, s_comp;
+    ZzSeq sq;
 };
 
 struct zzb_run_s {
@@ -180,7 +186,15 @@ struct zzb_run_s {
     int64_t launches = 0;
     int grid = 0; int kind = 1;
     bool strong = false; double strong_c = 0.0, kappa0 = 0.0; int strong_rule = 0;
-    int schedule = 1;                  // 1: asynchronous tile-local relaxation; 0: pass-synchronous schedule of round 1 (plain ZigZag only)
+    // -1: automatic (sequential chains for the logistic target when available, else 1); 2: sequential chains (zz_seq.cuh);
+    // 1: asynchronous tile-local relaxation; 0: pass-synchronous schedule of round 1 (plain ZigZag only)
+    int schedule = -1;
+    bool seq_capable() const
+    {
+        return prob && prob->hs.ok && nranks <= 1 && !strong && !grid_n &&
+               !(flags & (ZZB_FLAG_LOCAL_BOUND | ZZB_FLAG_STICKY | ZZB_FLAG_BOOMERANG | ZZB_FLAG_REFRESH));
+    }
+    int sched() const { return schedule >= 0 ? schedule : ((prob && prob->logit && seq_capable() && !max_windows) ? 2 : 1); }
     DevBuf inbox, inbox_cnt; unsigned int inbox_cap = 0, flag_words = 0; int inbox_grid = 0;
     DevBuf dbgbuf; std::vector<unsigned long long> dbghost;
     int tile_per = 0; unsigned int eval_threads = 0; int inbox_nr = 0;
@@ -196,7 +210,7 @@ struct zzb_run_s {
         if (flags & ZZB_FLAG_REFRESH) return 16 + kind;
         if (flags & ZZB_FLAG_BOOMERANG) return 10 + kind;
         if (flags & ZZB_FLAG_STICKY) return 8 + kind;
-        if (!schedule && nranks <= 1 && !(flags & ZZB_FLAG_LOCAL_BOUND)) return 14 + kind;
+        if (!sched() && nranks <= 1 && !(flags & ZZB_FLAG_LOCAL_BOUND)) return 14 + kind;
         return kind + (nranks > 1 ? 2 : 0) + ((flags & ZZB_FLAG_LOCAL_BOUND) ? 4 : 0);
     }
     DevBuf dfth, kappa; bool have_kappa = false;
@@ -272,6 +286,8 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuModuleGetFunction(&G.f_grid_tail, G.mod, "zz_grid_tail_kernel"));
     CU(cuModuleGetFunction(&G.f_math_probe, G.mod, "zz_math_probe_kernel"));
+    CU(cuModuleGetFunction(&G.f_seq, G.mod, "zz_seq_kernel"));
+    CU(cuModuleGetFunction(&G.f_seq_logit, G.mod, "zz_seq_kernel_logit"));
     CU(cuModuleGetFunction(&G.f_ts_hist, G.mod, "zz_tsort_hist_kernel"));
     CU(cuModuleGetFunction(&G.f_ts_scan, G.mod, "zz_tsort_scan_kernel"));
     CU(cuModuleGetFunction(&G.f_ts_scatter, G.mod, "zz_tsort_scatter_kernel"));
@@ -340,6 +356,27 @@ int32_t zzb_event_elapsed_ms(float* ms)
     return ZZB_OK;
 }
 
+// Sequential-chain schedule: upload the compact matrices and the component table when the problem qualifies (zz_host_seq.h).
+#define ZZ_SEQ_RES_HOST 32u   // = ZZ_SEQ_RES of zz_seq.cuh
+#define ZZ_SEQ_MAX_NC 2900   // coordinates per component: 76 bytes of shared memory each
+static int32_t upload_seq(zzb_problem_s* p)
+{
+    const ZzHostSeq& hs = p->hs;
+    memset(&p->sq, 0, sizeof p->sq);
+    if (!hs.ok) return ZZB_OK;
+    int32_t st = 0;
+#define UPS(buf, vec) if (!st) st = upload(p->buf, hs.vec.data(), hs.vec.size() * sizeof(hs.vec[0]))
+    UPS(s_bcp, bcp); UPS(s_brow, brow); UPS(s_bval, bval); UPS(s_comp, comp);
+    if (hs.have_tgt) { UPS(s_tcp, tcp); UPS(s_trow, trow); UPS(s_tval, tval); }
+#undef UPS
+    if (st) return st;
+    p->sq.bcp = p->s_bcp.as<int32_t>(); p->sq.brow = p->s_brow.as<int32_t>(); p->sq.bval = p->s_bval.as<double>();
+    if (hs.have_tgt) { p->sq.tcp = p->s_tcp.as<int32_t>(); p->sq.trow = p->s_trow.as<int32_t>(); p->sq.tval = p->s_tval.as<double>(); }
+    p->sq.comp = p->s_comp.as<int32_t>();
+    p->sq.ncomp = (int32_t)hs.comp.size() - 1; p->sq.ncmax = hs.ncmax;
+    return ZZB_OK;
+}
+
 int32_t zzb_problem_create_gaussian(zzb_problem_t* out, int64_t d, const int64_t* colptr, const int64_t* rowval,
                                     const double* nzval, const double* hvec, const int64_t* bnd_colptr,
                                     const int64_t* bnd_rowval, const double* bnd_nzval, const double* bnd_mu)
@@ -366,6 +403,13 @@ int32_t zzb_problem_create_gaussian(zzb_problem_t* out, int64_t d, const int64_t
     p->g.grid_m = getenv("ZZB200_NO_GRID") ? 0 : hg.grid_m; p->g.grid_n = hg.grid_n;
     for (int q = 0; q < 5; ++q) p->g.grid_diag[q] = hg.grid_diag[q];
     zz_grid_set_magic(p->g);
+    if (d <= (1 << 18)) {   // small problems may run as sequential chains (zzb_run_set("schedule", 2))
+        const bool sep = !hg.same;
+        zz_build_seq(p->hs, d, bnd_colptr, bnd_rowval, bnd_nzval, sep ? colptr : nullptr, sep ? rowval : nullptr, sep ? nzval : nullptr,
+                     nullptr, nullptr, ZZ_SEQ_MAX_NC);
+        st = upload_seq(p);
+        if (st) { delete p; return st; }
+    } else p->hs.why = "prepared for d <= 262144 only";
     *out = p;
     return ZZB_OK;
 }
@@ -415,6 +459,9 @@ int32_t zzb_problem_create_logistic(zzb_problem_t* out, int64_t d, int64_t n, co
     p->lg.rp = p->l_rp.as<int32_t>(); p->lg.rcol = p->l_rcol.as<int32_t>(); p->lg.rval = p->l_rval.as<double>();
     p->lg.y = p->l_y.as<double>(); p->lg.ny = p->l_ny.as<double>(); p->lg.u0 = p->l_u0.as<double>();
     p->lg.gamma0 = hl.gamma0; p->lg.k = hl.k; p->lg.n = hl.n;
+    zz_build_seq(p->hs, d, bnd_colptr, bnd_rowval, bnd_nzval, nullptr, nullptr, nullptr, hl.dep_cp.data(), hl.dep_rv.data(), ZZ_SEQ_MAX_NC);
+    st = upload_seq(p);
+    if (st) { delete p; return st; }
     *out = p;
     return ZZB_OK;
 }
@@ -637,7 +684,14 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
     else if (!strcmp(key, "host_sort")) r->host_sort_only = value != 0.0;   // order the trace on the host (A/B of the device sort)
     else if (!strcmp(key, "eval_threads")) r->eval_threads = (unsigned int)value;
-    else if (!strcmp(key, "schedule")) { r->schedule = value != 0.0; r->grid = G.sm_count * G.blocks_per_sm[r->kidx()]; }
+    else if (!strcmp(key, "schedule")) {   // 0 / 1: windowed relaxation (pass-synchronous / asynchronous); 2: sequential chains; -1: automatic
+        const int v = (int)value;
+        if (v < -1 || v > 2) return fail(ZZB_E_ARG, "schedule must be -1, 0, 1 or 2");
+        if (v == 2 && !r->seq_capable())
+            return fail(ZZB_E_ARG, "the sequential-chain schedule is not available for this run (%s)",
+                        r->prob->hs.ok ? "plain ZigZag on one GPU only, no device-side discretisation" : r->prob->hs.why.c_str());
+        r->schedule = v; r->grid = G.sm_count * G.blocks_per_sm[r->kidx()];
+    }
     // switch a sticky run to the strong-bound sampler of src/sparsestickyzz.jl: scalar bound constant c, rule (0 sticky, 1 reversible);
     // kappa[0] of zzb_run_upload_kappa is the thaw rate; coordinates with x0 == 0 start frozen.  Before zzb_run_upload.
     else if (!strcmp(key, "strong_c")) {
@@ -826,6 +880,108 @@ static void absorb_trace_chunk(zzb_run_s* r, std::vector<zzb_event>& chunk)
     for (auto& s : segs) r->events.insert(r->events.end(), chunk.begin() + s.first, chunk.begin() + s.second);
 }
 
+// Sequential-chain schedule (zz_seq.cuh): one warp per connected component runs the reference's event loop as written.  Phase 0
+// processes every item before T, phase 1 finds the first accepted flip at or after T over all chains (the loop of
+// src/sfact.jl:199 ends there), phase 2 processes every item up to that time.  A full trace buffer interrupts a phase: the
+// host drains it and relaunches (the chains resume from their saved state).
+static int32_t execute_seq(zzb_run_s* r, double T, float* device_ms)
+{
+    ZzParams& P = r->P;
+    zzb_problem_s* pb = r->prob;
+    if (!r->seq_capable())
+        return fail(ZZB_E_ARG, "the sequential-chain schedule is not available for this run (%s)",
+                    pb->hs.ok ? "plain ZigZag on one GPU only, no device-side discretisation" : pb->hs.why.c_str());
+    if (!(T < (double)INFINITY)) return fail(ZZB_E_ARG, "the sequential-chain schedule needs a finite end time");
+    if (r->executed && !(r->hc.ctl.F < T)) return ZZB_OK;   // `while t' < T` (sfact.jl:199): the last event is already at or after T
+    ZzSeq Q = pb->sq;
+    const unsigned dyn = 76u * (unsigned)Q.ncmax;
+    CUfunction f = pb->logit ? G.f_seq_logit : G.f_seq;
+    if (dyn > 48u * 1024u) CU(cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn));
+    if (P.record_trace && r->trace_cap < (unsigned long long)ZZ_SEQ_RES_HOST * (unsigned long long)Q.ncomp)
+        return fail(ZZB_E_TRACE, "trace buffer (%llu records) too small for %d chains (%u records reserved at a time)", r->trace_cap, Q.ncomp, ZZ_SEQ_RES_HOST);
+    if (r->dev_sorted && r->n_sorted) {   // events of an earlier execute that are still on the device (sorted) join the host vector first
+        const size_t at = r->events.size();
+        r->events.resize(at + (size_t)r->n_sorted);
+        CU(cuMemcpyDtoH(r->events.data() + at, r->trace_sorted.p, (size_t)r->n_sorted * sizeof(zzb_event)));
+    }
+    r->dev_sorted = false; r->n_sorted = 0;
+    const double t_front0 = r->executed ? r->hc.ctl.F : r->t0;
+    const size_t ev_start = r->events.size();
+    bool drained = !r->events.empty() || r->host_sort_only;
+    float total_ms = 0.f;
+    ZzDevCtl& hc = r->hc;
+    auto launch = [&](int phase) -> int32_t {
+        Q.phase = phase;
+        void* args[] = { &P, &Q };
+        CU(cuEventRecord(G.ev0, G.stream));
+        CU(cuLaunchKernel(f, (unsigned)Q.ncomp, 1, 1, 32, 1, 1, dyn, G.stream, args, nullptr));
+        CU(cuEventRecord(G.ev1, G.stream));
+        CU(cuStreamSynchronize(G.stream));
+        r->launches++;
+        float ms = 0.f;
+        CU(cuEventElapsedTime(&ms, G.ev0, G.ev1));
+        total_ms += ms;
+        CU(cuMemcpyDtoH(&hc, r->ctl.p, sizeof(ZzDevCtl)));
+        return ZZB_OK;
+    };
+    auto drain = [&]() -> int32_t {   // unordered records of the buffer (markers dropped) join the host vector
+        const unsigned long long n = std::min<unsigned long long>(hc.trace_len, r->trace_cap);
+        std::vector<zzb_event> chunk((size_t)n);
+        if (n) CU(cuMemcpyDtoH(chunk.data(), r->trace.p, (size_t)n * sizeof(zzb_event)));
+        for (const zzb_event& e : chunk) if (e.i != 0) r->events.push_back(e);
+        hc.trace_len = 0; hc.need_drain = 0;
+        CU(cuMemcpyHtoD(r->ctl.p, &hc, sizeof hc));
+        drained = true;
+        return ZZB_OK;
+    };
+    double t_end = T;
+    bool viol = false;
+    for (int phase = 0; phase < 3 && !viol; ++phase) {
+        if (phase == 1) {
+            CU(cuMemcpyDtoH(&hc, r->ctl.p, sizeof(ZzDevCtl)));
+            hc.smin_key[0] = ~0ULL;
+            CU(cuMemcpyHtoD(r->ctl.p, &hc, sizeof hc));
+        }
+        for (;;) {
+            int32_t st = launch(phase);
+            if (st) return st;
+            if (hc.viol) { viol = true; break; }
+            if (!hc.need_drain) break;
+            if (!P.record_trace) return fail(ZZB_E_INTERNAL, "sequential schedule: drain requested without a trace");
+            st = drain();
+            if (st) return st;
+        }
+        if (phase == 1) {
+            if (hc.smin_key[0] == ~0ULL) break;   // no chain will ever flip again: everything before T has been processed
+            t_end = zz_unkey(hc.smin_key[0]);
+        }
+    }
+    hc.ctl.F = viol ? std::max(t_front0, std::min(T, hc.viol_t)) : t_end;
+    hc.ctl.phase = ZZ_PH_DONE;
+    if (P.record_trace) {
+        const unsigned long long n = std::min<unsigned long long>(hc.trace_len, r->trace_cap);
+        bool ok = false;
+        if (!drained && !viol && n) {
+            int32_t st = device_sort_trace(r, n, t_front0, hc.ctl.F, &ok);
+            if (st) return st;
+            if (ok) { r->dev_sorted = true; hc.trace_len = 0; hc.need_drain = 0; }
+        }
+        if (!ok) {
+            int32_t st = drain();
+            if (st) return st;
+            auto cmp = [](const zzb_event& a, const zzb_event& b) { return a.t < b.t || (a.t == b.t && a.i < b.i); };
+            std::sort(r->events.begin() + (std::ptrdiff_t)ev_start, r->events.end(), cmp);
+        }
+    }
+    CU(cuMemcpyHtoD(r->ctl.p, &hc, sizeof hc));
+    if (device_ms) *device_ms = total_ms;
+    r->executed = true; r->fetched = false;
+    if (viol)
+        return fail(ZZB_E_BOUND, "Tuning parameter `c` too small. (coordinate %d, t = %.17g, l = %.17g, lb = %.17g)",
+                    hc.viol_i, hc.viol_t, hc.viol_l, hc.viol_lb);
+    return ZZB_OK;
+}
+
 int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
 {
     if (!r) return fail(ZZB_E_ARG, "null argument");
@@ -843,6 +999,7 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
     float total_ms = 0.f;
     if (device_ms) *device_ms = 0.f;
     if (!(r->t0 < T)) { r->executed = true; return ZZB_OK; }  // `while t' < T` never entered (sfact.jl:199)
+    if (r->sched() == 2) return execute_seq(r, T, device_ms);
     unsigned dyn_smem = 0;
     if (ZZ_KERN_ASYNC(r->kidx())) {
         if (r->nranks <= 1) { int32_t st = setup_tiles(r); if (st) return st; }   // (sharded: done by zzb_run_shard, before the IPC export)
