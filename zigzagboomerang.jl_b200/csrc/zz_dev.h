@@ -134,13 +134,22 @@ struct ZzParams {
 // Gaussian target that is not the same object -- of the target precision; comp[] holds the ncomp + 1 component boundaries
 // (components are contiguous index ranges).  phase: 0 = every item before T; 1 = probe (no writes) for the first accepted flip
 // at or after T, its time min-reduced into ctl->smin_key[0]; 2 = every item up to and including that time.
+struct __attribute__((aligned(32))) ZzSeqEnt {   // one stored entry of the design matrix A and where its row starts: one 32-byte sector
+    int32_t row, q0, len, pad;       // row of A; offset / length of that row in (rcol, rval)
+    double val, pad2;
+};
+struct __attribute__((aligned(32))) ZzSeqRow {   // per design row: y, m - y, sigmoidn(u0), nsigmoid(u0) with u0 = idot(At, row, mu)
+    double y, ny, sn0, ns0;          // (scripts/logistic.jl:89-91: the control-variate terms do not depend on the state)
+};
 struct ZzSeq {
     const int32_t* bcp; const int32_t* brow; const double* bval;
     const int32_t* tcp; const int32_t* trow; const double* tval;
     const int32_t* comp;
-    int32_t ncomp, phase, ncmax, pad;
+    const ZzSeqEnt* ent;             // logistic target: entries of A, column by column (same order as ZzLogit::arow)
+    const ZzSeqRow* rowrec;
+    int32_t ncomp, phase, ncmax;
+    int32_t colmax;                  // scratch entries per column-product array: max(32, longest column), even
 };
-#define ZZ_SEQ_BYTES_PER_COORD 80u   // shared memory per coordinate of a chain (zz_seq.cuh)
 
 // order-preserving map double -> uint64 (so atomicMin works for any sign)
 ZZ_HD unsigned long long zz_key(double x)

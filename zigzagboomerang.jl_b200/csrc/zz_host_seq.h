@@ -20,6 +20,7 @@ struct ZzHostSeq {
     std::vector<int32_t> bcp, brow, tcp, trow, comp;
     std::vector<double> bval, tval;
     int32_t ncmax = 0;        // coordinates of the largest component, rounded up to an even number
+    int32_t colmax = 32;      // longest column of either matrix (at least 32), rounded up to an even number
     bool have_tgt = false;
 };
 
@@ -66,6 +67,9 @@ static inline void zz_build_seq(ZzHostSeq& S, int64_t d, const int64_t* bcp, con
     if (bcp[d] - 1 > 0x7ffffff0LL || (tcp && tcp[d] - 1 > 0x7ffffff0LL)) { S.why = "too many non-zeros"; return; }
     copy(bcp, brv, bnz, S.bcp, S.brow, S.bval);
     S.have_tgt = tcp != nullptr;
+    int64_t cm = 32;
+    for (int64_t j = 0; j < d; ++j) { cm = std::max(cm, bcp[j + 1] - bcp[j]); if (tcp) cm = std::max(cm, tcp[j + 1] - tcp[j]); }
+    S.colmax = (int32_t)((cm + 1) & ~(int64_t)1);
     if (tcp) copy(tcp, trv, tnz, S.tcp, S.trow, S.tval);
     S.ok = true; S.why.clear();
 }

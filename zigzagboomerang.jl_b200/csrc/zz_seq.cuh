@@ -27,11 +27,13 @@
 #define ZZ_SEQ_CUH
 
 #define ZZ_SEQ_RES 32u
+#define ZZ_SEQ_LONG 64    // neighbours with longer columns are rescheduled by the whole warp, one after the other
 
 struct ZzSeqSh {
     double *xf, *tf, *th, *tau, *a, *b, *told, *c;
     uint32_t* kc;
     int32_t *a0, *al;
+    double *g, *cx, *ct;   // scratch: terms of the logistic gradient (64), products of one column of Z.Gamma (colmax each)
     int32_t lo, nc;
 };
 
@@ -40,84 +42,79 @@ __device__ __forceinline__ double zz_seq_pos(const ZzSeqSh& S, int32_t k, double
     return S.xf[k] + S.th[k] * (s - S.tf[k]);
 }
 
-// Ordered sums over column jg of a CSC matrix: sx = sum val * x_k(s), st = sum val * theta_k, storage order.
-// Cooperative: one entry per lane, accumulated in order through shuffles (every lane ends with the sums).
+// In-order sums of a[0..n) and b[0..n) (shared memory; readable up to n + 8): the loads of the next four terms are in flight
+// while the two dependent chains consume the current four.
+__device__ __forceinline__ void zz_seq_sum2(const double* a, const double* b, int32_t n, double& sa, double& sb)
+{
+    double x0 = a[0], x1 = a[1], x2 = a[2], x3 = a[3], y0 = b[0], y1 = b[1], y2 = b[2], y3 = b[3];
+    double ax = 0.0, ay = 0.0;
+    for (int32_t q = 0; q < n; q += 4) {
+        const double nx0 = a[q + 4], nx1 = a[q + 5], nx2 = a[q + 6], nx3 = a[q + 7];
+        const double ny0 = b[q + 4], ny1 = b[q + 5], ny2 = b[q + 6], ny3 = b[q + 7];
+        ax += x0; ay += y0;
+        if (q + 1 < n) { ax += x1; ay += y1; }
+        if (q + 2 < n) { ax += x2; ay += y2; }
+        if (q + 3 < n) { ax += x3; ay += y3; }
+        x0 = nx0; x1 = nx1; x2 = nx2; x3 = nx3; y0 = ny0; y1 = ny1; y2 = ny2; y3 = ny3;
+    }
+    sa = ax; sb = ay;
+}
+
+// Ordered sums over entries [e0, e1) of a CSC column: sx = sum val * x_k(s), st = sum val * theta_k, storage order.
+// Cooperative: the lanes form the products side by side and park them in shared memory, then every lane adds them up in
+// order (the same addresses in every lane: broadcast reads, no shuffles).
 __device__ __forceinline__ void zz_seq_col_coop(const ZzSeqSh& S, const int32_t* __restrict__ row, const double* __restrict__ val,
                                                 int32_t e0, int32_t e1, double s, int lane, double& sx, double& st)
 {
-    double ax = 0.0, at = 0.0;
-    for (int32_t base = e0; base < e1; base += 32) {
-        const int32_t e = base + lane;
-        double px = 0.0, pt = 0.0;
-        if (e < e1) {
-            const int32_t k = __ldg(row + e) - S.lo;
-            const double w = __ldg(val + e);
-            const double thk = S.th[k];
-            px = w * (S.xf[k] + thk * (s - S.tf[k]));
-            pt = w * thk;
-        }
-        const int cnt = min(32, e1 - base);
-        for (int q = 0; q < cnt; ++q) {
-            ax += __shfl_sync(0xffffffffu, px, q);
-            at += __shfl_sync(0xffffffffu, pt, q);
-        }
+    const int32_t n = e1 - e0;
+    __syncwarp();   // (earlier readers of the scratch arrays are done)
+#pragma unroll 4
+    for (int32_t q = lane; q < n; q += 32) {
+        const int32_t k = __ldg(row + e0 + q) - S.lo;
+        const double w = __ldg(val + e0 + q);
+        const double thk = S.th[k];
+        S.cx[q] = w * (S.xf[k] + thk * (s - S.tf[k]));
+        S.ct[q] = w * thk;
     }
-    sx = ax; st = at;
+    __syncwarp();
+    sx = 0.0; st = 0.0;
+    if (n > 0) zz_seq_sum2(S.cx, S.ct, n, sx, st);
 }
 
-// The same sums by one lane on its own.
+// The same sums by one lane on its own (four entries in flight at a time).
 __device__ __forceinline__ void zz_seq_col_serial(const ZzSeqSh& S, const int32_t* __restrict__ row, const double* __restrict__ val,
                                                   int32_t e0, int32_t e1, double s, double& sx, double& st)
 {
     double ax = 0.0, at = 0.0;
-    for (int32_t e = e0; e < e1; ++e) {
-        const int32_t k = __ldg(row + e) - S.lo;
-        const double w = __ldg(val + e);
-        const double thk = S.th[k];
-        ax += w * (S.xf[k] + thk * (s - S.tf[k]));
-        at += w * thk;
+    for (int32_t e = e0; e < e1; e += 4) {
+        int32_t k[4]; double w[4];
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {
+            const bool ok = e + z < e1;
+            k[z] = ok ? __ldg(row + e + z) - S.lo : 0;
+            w[z] = ok ? __ldg(val + e + z) : 0.0;
+        }
+#pragma unroll
+        for (int z = 0; z < 4; ++z)
+            if (e + z < e1) {
+                const double thk = S.th[k[z]];
+                ax += w[z] * (S.xf[k[z]] + thk * (s - S.tf[k[z]]));
+                at += w[z] * thk;
+            }
     }
     sx = ax; st = at;
 }
 
-// gamma0 x_j - fdot_moving(...) at time s (scripts/logistic.jl:78-95,107): draws kc .. kc + L.k - 1 of coordinate jg's stream,
-// lane r evaluates sampled row r; the 4 k terms are added in the reference's order.
-__device__ __forceinline__ double zz_seq_logit_grad(const ZzLogit& L, const ZzView& v, const ZzSeqSh& S, int32_t li, int32_t jg,
-                                                    double s, double xown, uint32_t kc, int lane)
+// Lexicographic arg-min of (time, index) over the warp: three REDUX steps on the order-preserving image of the time.
+__device__ __forceinline__ void zz_seq_argmin(double bt, int bi, double& tp, int& li)
 {
-    const int32_t e0 = S.a0[li], l = S.al[li];
-    const double lk = (double)l / (double)L.k;
-    double sacc = 0.0;
-    for (int32_t r0 = 0; r0 < L.k; r0 += 32) {
-        const int32_t r = r0 + lane;
-        double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0;
-        if (r < L.k) {
-            const double ur = zz_u01(v.seed0, v.seed1, (uint64_t)jg, (uint64_t)(kc + (uint32_t)r));
-            int32_t i = (int32_t)(ur * (double)l);                  // uniform index into nzrange(A, j) (:83,86)
-            if (i >= l) i = l - 1;
-            const int32_t row = __ldg(L.arow + e0 + i);
-            const double w = lk * __ldg(L.aval + e0 + i);
-            const int32_t q0 = __ldg(L.rp + row), q1 = __ldg(L.rp + row + 1);
-            const double yr = __ldg(L.y + row), nyr = __ldg(L.ny + row), u0 = __ldg(L.u0 + row);
-            double u = 0.0;                                         // idot_moving!(At, row, ...), src/common.jl:33-42
-            for (int32_t q = q0; q < q1; ++q) {
-                const int32_t m = __ldg(L.rcol + q) - S.lo;
-                u += __ldg(L.rval + q) * zz_seq_pos(S, m, s);
-            }
-            t1 = w * yr * zz_sigmoidn(u);                           // :87-88
-            t2 = w * nyr * zz_nsigmoid(u);
-            t3 = w * yr * zz_sigmoidn(u0);                          // :90-91 (control variate at the mode)
-            t4 = w * nyr * zz_nsigmoid(u0);
-        }
-        const int cnt = min(32, L.k - r0);
-        for (int q = 0; q < cnt; ++q) {
-            sacc += __shfl_sync(0xffffffffu, t1, q);
-            sacc += __shfl_sync(0xffffffffu, t2, q);
-            sacc -= __shfl_sync(0xffffffffu, t3, q);
-            sacc -= __shfl_sync(0xffffffffu, t4, q);
-        }
-    }
-    return L.gamma0 * xown - sacc;                                  // :107
+    const unsigned long long key = zz_key(bt);
+    const unsigned int hi = (unsigned int)(key >> 32), lo = (unsigned int)key;
+    const unsigned int mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned int ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    const bool win = (hi == mh) && (lo == ml);
+    li = (int)__reduce_min_sync(0xffffffffu, win ? (unsigned int)bi : 0xffffffffu);
+    tp = zz_unkey(((unsigned long long)mh << 32) | (unsigned long long)ml);
 }
 
 template <bool LOGIT>
@@ -138,6 +135,8 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
         S.kc = reinterpret_cast<uint32_t*>(base + 8 * n);
         S.a0 = reinterpret_cast<int32_t*>(S.kc + n);
         S.al = S.a0 + n;
+        S.g = reinterpret_cast<double*>(S.al + n + (n & 1));   // (3 n words + padding: 8-byte aligned again)
+        S.cx = S.g + 72; S.ct = S.cx + Q.colmax + 8;   // (the pipelined sums read up to 8 entries past the end)
     }
     const int32_t lo = S.lo, nc = S.nc;
     for (int32_t q = lane; q < nc; q += 32) {
@@ -157,6 +156,7 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
     const uint64_t seed0 = P.v.seed0, seed1 = P.v.seed1;
     unsigned long long nprop = 0, nflip = 0;
     unsigned long long tr_pos = 0, tr_end = 0;
+    const int half = lane >> 4, r16 = lane & 15;   // logistic gradient: lanes r and r + 16 share sampled row r
 
 #ifdef ZZ_SEQ_PROF
     long long pc[6] = { 0, 0, 0, 0, 0, 0 }; long long pt0;
@@ -174,15 +174,10 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
             const double t = S.tau[q];
             if (t < bt) { bt = t; bi = q; }
         }
-#pragma unroll
-        for (int off = 16; off; off >>= 1) {
-            const double ot = __shfl_xor_sync(0xffffffffu, bt, off);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-            if (ot < bt || (ot == bt && oi < bi)) { bt = ot; bi = oi; }
-        }
-        if (bi == 0x7fffffff) break;   // nothing will ever happen in this chain
-        const double tp = bt;
-        const int32_t li = bi, jg = lo + bi;
+        double tp; int li;
+        zz_seq_argmin(bt, bi, tp, li);
+        if (!(tp < ZZ_INF)) break;   // nothing will ever happen in this chain
+        const int32_t jg = lo + li;
         if (phase == 0) { if (!(tp < P.T)) break; }
         else if (phase == 2) { if (!(tp <= tend)) break; }
 
@@ -202,35 +197,110 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
             }
             tr_pos = base; tr_end = base + ZZ_SEQ_RES;
         }
-
         ZZ_SP_TOC(0);
         ZZ_SP_TIC();
-        // ---- the proposal of coordinate i at tp (sfact.jl:118-121)
+
+        // ---- the proposal of coordinate i at tp (sfact.jl:118-121).  Everything that does not depend on the outcome is
+        // started first: the loads of the own column of Z.Gamma (bound after a rejection), the uniform of the thinning test and
+        // the logarithm of the uniform of the NEXT proposal time (poisson_time is a function of log u, src/poissontime.jl).
         const int32_t be0 = __ldg(Q.bcp + jg), be1 = __ldg(Q.bcp + jg + 1);
         const double gmu_i = __ldg(P.g.gmu + jg);
         const double th_i = S.th[li], tf_i = S.tf[li], xf_i = S.xf[li];
         const double xi = xf_i + th_i * (tp - tf_i);
         double c = S.c[li];
         uint32_t kc = S.kc[li];
+        const bool short_col = (be1 - be0) <= 32;
         double gt, sx = 0.0, sth = 0.0;
         bool have_s = false;
+        double u, Lrej;
         if (LOGIT) {
-            gt = zz_seq_logit_grad(P.lg, P.v, S, li, jg, tp, xi, kc, lane);
-            kc += (uint32_t)P.lg.k;
-        } else if (Q.tcp) {
-            double d0, d1;
-            zz_seq_col_coop(S, Q.trow, Q.tval, __ldg(Q.tcp + jg), __ldg(Q.tcp + jg + 1), tp, lane, d0, d1);
-            gt = P.g.h ? d0 - __ldg(P.g.h + jg) : d0;
+            const ZzLogit& L = P.lg;
+            const int32_t a0 = S.a0[li], l = S.al[li];
+            const double lk = (double)l / (double)L.k;
+            double sacc = 0.0;
+            for (int32_t r0 = 0; r0 < L.k; r0 += 16) {
+                const int32_t r = r0 + r16;
+                const bool act = r < L.k;
+                // sampled row r (scripts/logistic.jl:83,86): its entry of A and the row's constants
+                int32_t q0 = 0, len = 0; double w = 0.0, ya = 0.0, c0 = 0.0;
+                if (act) {
+                    const double ur = zz_u01(seed0, seed1, (uint64_t)jg, (uint64_t)(kc + (uint32_t)r));
+                    int32_t i = (int32_t)(ur * (double)l);
+                    if (i >= l) i = l - 1;
+                    const int4 eh = __ldg(reinterpret_cast<const int4*>(Q.ent + a0 + i));
+                    w = lk * __ldg(&Q.ent[a0 + i].val);
+                    q0 = eh.y; len = eh.z;
+                    const double2 rr = __ldg(reinterpret_cast<const double2*>(Q.rowrec + eh.x) + half);   // (y, ny) | (sn0, ns0)
+                    const double2 r2 = __ldg(reinterpret_cast<const double2*>(Q.rowrec + eh.x) + (half ^ 1));
+                    // lanes 0-15: y and sigmoidn; lanes 16-31: ny and nsigmoid
+                    ya = half ? r2.y : rr.x;
+                    c0 = half ? rr.y : r2.x;
+                }
+                // own column of Z.Gamma, first round only (speculative: needed when the proposal is rejected)
+                int32_t ck = 0; double cw = 0.0;
+                const bool cin = (r0 == 0) && short_col && (be0 + lane < be1);
+                if (cin) { ck = __ldg(Q.brow + be0 + lane) - lo; cw = __ldg(Q.bval + be0 + lane); }
+                if (r0 == 0) {
+                    u = zz_u01(seed0, seed1, (uint64_t)jg, (uint64_t)(kc + (uint32_t)L.k));
+                    Lrej = zz_log(zz_u01(seed0, seed1, (uint64_t)jg, (uint64_t)(kc + (uint32_t)L.k + 1u)));
+                }
+                double uu = 0.0;                                        // idot_moving!(At, row, ...), src/common.jl:33-42
+                for (int32_t qb = 0; qb < len; qb += 8) {
+                    int32_t m[8]; double v[8];
+#pragma unroll
+                    for (int z = 0; z < 8; ++z) {
+                        const bool ok = qb + z < len;
+                        m[z] = ok ? __ldg(L.rcol + q0 + qb + z) - lo : 0;
+                        v[z] = ok ? __ldg(L.rval + q0 + qb + z) : 0.0;
+                    }
+#pragma unroll
+                    for (int z = 0; z < 8; ++z)
+                        if (qb + z < len) uu += v[z] * zz_seq_pos(S, m[z], tp);
+                }
+                // sigmoidn(u) = 1 / (1 + exp(u)) on lanes 0-15, nsigmoid(u) = -(1 / (1 + exp(-u))) on lanes 16-31 (:34,56-57)
+                const double sg = 1.0 / (1.0 + zz_exp(half ? -uu : uu));
+                __syncwarp();   // (the scratch arrays are free again)
+                if (act) {
+                    S.g[4 * r16 + half] = w * ya * (half ? -sg : sg);       // :87 | :88
+                    S.g[4 * r16 + 2 + half] = -(w * ya * c0);               // :90 | :91 (control variate at the mode), subtracted
+                }
+                if (cin) { const double thk = S.th[ck]; S.cx[lane] = cw * (S.xf[ck] + thk * (tp - S.tf[ck])); S.ct[lane] = cw * thk; }
+                __syncwarp();
+                const int cnt = 4 * min(16, L.k - r0);
+                const int ccnt = (r0 == 0 && short_col) ? be1 - be0 : 0;
+                // three independent ordered sums, every lane the same (broadcast reads): the 4 k terms of the gradient in the
+                // reference's order, and the two column sums of the bound
+                {
+                    double g0 = S.g[0], g1 = S.g[1], g2 = S.g[2], g3 = S.g[3];
+                    for (int q = 0; q < cnt; q += 4) {   // (cnt is a multiple of 4; S.g holds 64 + 8 entries)
+                        const double n0 = S.g[q + 4], n1 = S.g[q + 5], n2 = S.g[q + 6], n3 = S.g[q + 7];
+                        sacc += g0; sacc += g1; sacc += g2; sacc += g3;
+                        g0 = n0; g1 = n1; g2 = n2; g3 = n3;
+                    }
+                }
+                if (ccnt > 0) zz_seq_sum2(S.cx, S.ct, ccnt, sx, sth);
+            }
+            have_s = short_col;
+            gt = L.gamma0 * xi - sacc;                                      // :107
+            kc += (uint32_t)L.k + 1u;
         } else {
-            zz_seq_col_coop(S, Q.brow, Q.bval, be0, be1, tp, lane, sx, sth);
-            have_s = true;
-            gt = sx;
+            u = zz_u01(seed0, seed1, (uint64_t)jg, (uint64_t)kc);
+            Lrej = zz_log(zz_u01(seed0, seed1, (uint64_t)jg, (uint64_t)(kc + 1u)));
+            kc += 1u;
+            if (Q.tcp) {
+                double d0, d1;
+                zz_seq_col_coop(S, Q.trow, Q.tval, __ldg(Q.tcp + jg), __ldg(Q.tcp + jg + 1), tp, lane, d0, d1);
+                gt = P.g.h ? d0 - __ldg(P.g.h + jg) : d0;
+            } else {
+                zz_seq_col_coop(S, Q.brow, Q.bval, be0, be1, tp, lane, sx, sth);
+                have_s = true;
+                gt = sx;
+            }
         }
         ZZ_SP_TOC(1);
         ZZ_SP_TIC();
         const double l = zz_pos(gt * th_i);                                  // fact_samplers.jl:28-30
         const double lb = zz_pos(S.a[li] + S.b[li] * (tp - S.told[li]));     // sfact.jl:70
-        const double u = zz_u01(seed0, seed1, (uint64_t)jg, (uint64_t)(kc++));
         nprop++;
         ZZ_SP_TOC(2);
         ZZ_SP_TIC();
@@ -263,20 +333,33 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
             }
             if (rec && tid != 0) tr_pos++;
             __syncwarp();
-            // reschedule G1[i] = rows of column i of Z.Gamma (i among them), one neighbour per lane (:131-135)
+            // reschedule G1[i] = rows of column i of Z.Gamma (i among them), one neighbour per lane (:131-135); neighbours with a
+            // long column are then served one after the other by the whole warp
             for (int32_t base = be0; base < be1; base += 32) {
                 const int32_t e = base + lane;
-                if (e < be1) {
-                    const int32_t jj = __ldg(Q.brow + e), lj = jj - lo;
-                    const int32_t f0 = __ldg(Q.bcp + jj), f1 = __ldg(Q.bcp + jj + 1);
-                    const double gmu_j = __ldg(P.g.gmu + jj);
-                    double sxj, stj;
-                    zz_seq_col_serial(S, Q.brow, Q.bval, f0, f1, tp, sxj, stj);
+                const bool valid = e < be1;
+                int32_t jj = 0, lj = 0, f0 = 0, f1 = 0; double gmu_j = 0.0, Lj = 0.0; uint32_t kj = 0;
+                if (valid) {
+                    jj = __ldg(Q.brow + e); lj = jj - lo;
+                    f0 = __ldg(Q.bcp + jj); f1 = __ldg(Q.bcp + jj + 1);
+                    gmu_j = __ldg(P.g.gmu + jj);
+                    kj = S.kc[lj];
+                    Lj = zz_log(zz_u01(seed0, seed1, (uint64_t)jj, (uint64_t)(kj++)));
+                }
+                const bool islong = valid && (f1 - f0 > ZZ_SEQ_LONG);
+                double sxj = 0.0, stj = 0.0;
+                if (valid && !islong) zz_seq_col_serial(S, Q.brow, Q.bval, f0, f1, tp, sxj, stj);
+                for (unsigned int lm = __ballot_sync(0xffffffffu, islong); lm; lm &= lm - 1u) {
+                    const int src = __ffs((int)lm) - 1;
+                    double cx, ct;
+                    zz_seq_col_coop(S, Q.brow, Q.bval, __shfl_sync(0xffffffffu, f0, src), __shfl_sync(0xffffffffu, f1, src), tp, lane, cx, ct);
+                    if (lane == src) { sxj = cx; stj = ct; }
+                }
+                if (valid) {
                     const double cj = S.c[lj], thj = S.th[lj];
                     const double aj = cj + (sxj - gmu_j) * thj;               // fact_samplers.jl:51-52
                     const double bj = cj / 100 + thj * stj;
-                    uint32_t kj = S.kc[lj];
-                    const double tj = tp + zz_poisson_time(aj, bj, zz_u01(seed0, seed1, (uint64_t)jj, (uint64_t)(kj++)));
+                    const double tj = tp + zz_poisson_time_L(aj, bj, Lj);
                     S.a[lj] = aj; S.b[lj] = bj; S.told[lj] = tp; S.tau[lj] = tj; S.kc[lj] = kj;
                 }
             }
@@ -286,7 +369,8 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
             if (!have_s) zz_seq_col_coop(S, Q.brow, Q.bval, be0, be1, tp, lane, sx, sth);
             const double a = c + (sx - gmu_i) * th_i;
             const double b = c / 100 + th_i * sth;
-            const double tau = tp + zz_poisson_time(a, b, zz_u01(seed0, seed1, (uint64_t)jg, (uint64_t)(kc++)));
+            const double tau = tp + zz_poisson_time_L(a, b, Lrej);
+            kc += 1u;
             __syncwarp();
             if (lane == 0) { S.a[li] = a; S.b[li] = b; S.told[li] = tp; S.tau[li] = tau; S.kc[li] = kc; }
             __syncwarp();

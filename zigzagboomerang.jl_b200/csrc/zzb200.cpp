@@ -163,7 +163,7 @@ struct zzb_problem_s {
     ZzLogit lg;
     // sequential-chain schedule (zz_seq.cuh): compact matrices + connected components; hs.ok says whether it is available
     ZzHostSeq hs;
-    DevBuf s_bcp, s_brow, s_bval, s_tcp, s_trow, s_tval, s_comp;
+    DevBuf s_bcp, s_brow, s_bval, s_tcp, s_trow, s_tval, s_comp, s_ent, s_rowrec;
     ZzSeq sq;
 };
 
@@ -373,7 +373,22 @@ static int32_t upload_seq(zzb_problem_s* p)
     p->sq.bcp = p->s_bcp.as<int32_t>(); p->sq.brow = p->s_brow.as<int32_t>(); p->sq.bval = p->s_bval.as<double>();
     if (hs.have_tgt) { p->sq.tcp = p->s_tcp.as<int32_t>(); p->sq.trow = p->s_trow.as<int32_t>(); p->sq.tval = p->s_tval.as<double>(); }
     p->sq.comp = p->s_comp.as<int32_t>();
-    p->sq.ncomp = (int32_t)hs.comp.size() - 1; p->sq.ncmax = hs.ncmax;
+    p->sq.ncomp = (int32_t)hs.comp.size() - 1; p->sq.ncmax = hs.ncmax; p->sq.colmax = hs.colmax;
+    if (p->logit) {   // packed design entries and per-row constants (the control-variate sigmoids are evaluated once, here)
+        const ZzHostLogit& hl = p->hl;
+        std::vector<ZzSeqEnt> ent(hl.arow.size());
+        for (size_t e = 0; e < ent.size(); ++e) {
+            const int32_t row = hl.arow[e];
+            ZzSeqEnt& q = ent[e];
+            q.row = row; q.q0 = hl.rp[row]; q.len = hl.rp[row + 1] - hl.rp[row]; q.pad = 0; q.val = hl.aval[e]; q.pad2 = 0.0;
+        }
+        std::vector<ZzSeqRow> rr((size_t)hl.n);
+        for (int32_t r = 0; r < hl.n; ++r) { rr[r].y = hl.y[r]; rr[r].ny = hl.ny[r]; rr[r].sn0 = zz_sigmoidn(hl.u0[r]); rr[r].ns0 = zz_nsigmoid(hl.u0[r]); }
+        st = upload(p->s_ent, ent.data(), ent.size() * sizeof(ZzSeqEnt));
+        if (!st) st = upload(p->s_rowrec, rr.data(), rr.size() * sizeof(ZzSeqRow));
+        if (st) return st;
+        p->sq.ent = p->s_ent.as<ZzSeqEnt>(); p->sq.rowrec = p->s_rowrec.as<ZzSeqRow>();
+    }
     return ZZB_OK;
 }
 
@@ -894,7 +909,8 @@ static int32_t execute_seq(zzb_run_s* r, double T, float* device_ms)
     if (!(T < (double)INFINITY)) return fail(ZZB_E_ARG, "the sequential-chain schedule needs a finite end time");
     if (r->executed && !(r->hc.ctl.F < T)) return ZZB_OK;   // `while t' < T` (sfact.jl:199): the last event is already at or after T
     ZzSeq Q = pb->sq;
-    const unsigned dyn = 76u * (unsigned)Q.ncmax;
+    const unsigned dyn = 76u * (unsigned)Q.ncmax + 8u + 8u * (72u + 2u * ((unsigned)Q.colmax + 8u));   // state + scratch (zz_seq.cuh)
+    if (dyn > 220u * 1024u) return fail(ZZB_E_ARG, "the sequential-chain schedule needs %u bytes of shared memory per chain", dyn);
     CUfunction f = pb->logit ? G.f_seq_logit : G.f_seq;
     if (dyn > 48u * 1024u) CU(cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn));
     if (P.record_trace && r->trace_cap < (unsigned long long)ZZ_SEQ_RES_HOST * (unsigned long long)Q.ncomp)
