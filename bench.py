@@ -393,10 +393,20 @@ def run_ours(args):
                  "switches_per_step": int(acc3.sum()), "proposals_per_step": int(num3)}
         run3.close()
 
+    # ---- config 3 of BASELINE.json (sparse logistic regression, n = 8840, p = 442, subsampled ZigZag) as replicas side by side:
+    # reported beside the headline, not part of it (sequential chains)
+    config3 = None
+    if not args.no_config3:
+        try:
+            config3 = config3_leg(zzb, args.config3_replicas)
+        except Exception as e:   # (never let the side measurement take the headline down)
+            config3 = {"error": f"{type(e).__name__}: {e}"}
+
     out = {
         "metric": METRIC, "value": value, "unit": "events/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
+        "other_configs": {"config3_logistic_replicas": config3},
         "config": {"workload": workload_string(args, d),
                    "l2": "device working set (state + flip lists + work lists ~ 0.4 KB/coordinate = 400 MB) exceeds the 126 MB L2",
                    "switches_per_step": nacc, "proposals_per_step": int(num), "proposals_per_s": num * args.steps / (total_ms * 1e-3),
@@ -560,6 +570,30 @@ def run_ours_sharded(args, zzb, G, x0, th0, c, world, rank, local):
     dist.destroy_process_group()
 
 
+def config3_leg(zzb, R, T=10.0):
+    """R independent chains of the logistic configuration (scripts/logistic.jl) as one block-diagonal problem, event loop only."""
+    cfg = zzb.logistic_config()
+    big = zzb.replicate_logistic(cfg, R) if R > 1 else cfg
+    grad = zzb.LogisticSubsampled(big["A"], big["At"], big["y"], big["ny"], big["mu"], cfg["gamma0"], 10)
+    Z = zzb.ZigZag(big["Gamma_drop"], big["mu"], big["sigma"], rho=0.5)
+    prob = zzb.Problem(grad, Z)
+    run = zzb.Run(prob, record_trace=False)
+    try:
+        run.upload(0.0, big["x0"], big["theta0"], big["c"], seed=(5, 6), adapt=True, factor=5.0)
+        run.execute(T)          # warm-up (fills the L2 with the design)
+        run.reset()
+        run.execute(T)
+        acc, num = run.counts()
+        ms = run.device_ms
+        return {"workload": f"sparse logistic regression n=8840 p=442 k=10 subsampled ZigZag (scripts/logistic.jl), {R} replicas side by side, "
+                            f"T=[0,{T:g}], c=0.01, adapt, factor 5", "schedule": "sequential chains: one warp per chain (zz_seq_kernel_logit)",
+                "replicas": R, "events": int(acc.sum()), "proposals": int(num), "kernel_ms": ms,
+                "events_per_s": int(acc.sum()) / (ms * 1e-3), "proposals_per_s": int(num) / (ms * 1e-3)}
+    finally:
+        run.close()
+        prob.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -573,6 +607,8 @@ def main():
     ap.add_argument("--tight", action="store_true", help="c = sqrt(eps) (scripts/example.jl:39) instead of column norms")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tight", action="store_true", help="skip the extra c = sqrt(eps) measurement")
+    ap.add_argument("--no-config3", action="store_true", help="skip the side measurement of config 3 (logistic replicas)")
+    ap.add_argument("--config3-replicas", type=int, default=296)
     ap.add_argument("--no-trace", action="store_true", help="skip the e2e measurement with the full trace")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the bench workload")
     args = ap.parse_args()

@@ -66,6 +66,33 @@ def test_block_diagonal_components_end_at_the_global_last_event(gpu):
         assert np.allclose(m1, ref.m1, rtol=1e-12, atol=1e-300)
 
 
+@pytest.mark.auto_schedule
+def test_scattered_components_and_automatic_choice(gpu):
+    """Components that are NOT contiguous index ranges (a symmetric permutation of a block-diagonal matrix): the host renumbers
+    the coordinates chain by chain; draw streams, trace ids and the returned arrays keep the caller's numbering.  Small
+    components make the sequential schedule the automatic choice."""
+    from zzb200.problems import CSC
+    G, x0, th0, c = gpu.gmrf_config(12)
+    Gb = O.block_diagonal(G, 6)
+    perm = np.random.default_rng(7).permutation(Gb.n)
+    D = Gb.to_scipy().toarray()[np.ix_(perm, perm)]
+    Gp = CSC.from_dense(D)
+    x0, th0, c = x0[perm], th0[perm], c[perm]
+    ref = O.spdmp(Gp, Gp, 0.0, x0, th0, 6.0, c)
+    got, Xi = run_gpu(gpu, Gp, Gp, 0.0, x0, th0, 6.0, c, tune=SEQ)
+    O.assert_same_run(ref, got)
+    auto, Xa = run_gpu(gpu, Gp, Gp, 0.0, x0, th0, 6.0, c)           # components of 24 coordinates: sequential by default
+    O.assert_same_run(ref, auto)
+    assert Xa.stats["windows"] == 0
+    win, Xw = run_gpu(gpu, Gp, Gp, 0.0, x0, th0, 6.0, c, tune=dict(schedule=1))
+    O.assert_same_run(ref, win)
+    assert Xw.stats["windows"] > 0
+    # one large sparse component: the windowed relaxation stays the automatic choice
+    G2, x2, t2, c2 = gpu.gmrf_config(16)
+    _, X2 = run_gpu(gpu, G2, G2, 0.0, x2, t2, 1.0, c2)
+    assert X2.stats["windows"] > 0
+
+
 def test_trace_drain_continue_and_filter(gpu):
     """A trace buffer that holds a fraction of the events (drain and relaunch), two execute calls on one run (the chains resume
     from their saved state), the trace filter (subtrace at the source) and the host-side ordering."""

@@ -145,8 +145,11 @@ struct ZzSeq {
     const int32_t* bcp; const int32_t* brow; const double* bval;
     const int32_t* tcp; const int32_t* trow; const double* tval;
     const int32_t* comp;
+    const int32_t* orig;             // chain-order id -> original id: the matrices above and comp[] use chain-order ids (every chain a
+                                     // contiguous range); draw streams, trace ids and all per-coordinate arrays keep the original ids
     const ZzSeqEnt* ent;             // logistic target: entries of A, column by column (same order as ZzLogit::arow)
     const ZzSeqRow* rowrec;
+    const int32_t* rcoln;            // ZzLogit::rcol in chain-order ids
     int32_t ncomp, phase, ncmax;
     int32_t colmax;                  // scratch entries per column-product array: max(32, longest column), even
 };

@@ -33,6 +33,7 @@ struct ZzSeqSh {
     double *xf, *tf, *th, *tau, *a, *b, *told, *c;
     uint32_t* kc;
     int32_t *a0, *al;
+    int32_t* og;           // original id of every coordinate of the chain (draw stream, trace id, per-coordinate arrays)
     double *g, *cx, *ct;   // scratch: terms of the logistic gradient (64), products of one column of Z.Gamma (colmax each)
     int32_t lo, nc;
 };
@@ -135,18 +136,21 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
         S.kc = reinterpret_cast<uint32_t*>(base + 8 * n);
         S.a0 = reinterpret_cast<int32_t*>(S.kc + n);
         S.al = S.a0 + n;
-        S.g = reinterpret_cast<double*>(S.al + n + (n & 1));   // (3 n words + padding: 8-byte aligned again)
+        S.og = S.al + n;
+        S.g = reinterpret_cast<double*>(S.og + n);              // (4 n words, n even: 8-byte aligned again)
         S.cx = S.g + 72; S.ct = S.cx + Q.colmax + 8;   // (the pipelined sums read up to 8 entries past the end)
     }
     const int32_t lo = S.lo, nc = S.nc;
     for (int32_t q = lane; q < nc; q += 32) {
+        const int32_t o = __ldg(Q.orig + lo + q);
         double th, tf, xf; uint32_t h0, h1;
-        zz_ld_kin(P.v.kin + lo + q, th, tf, xf, h0, h1);
-        const ZzPriv pr = zz_ld_priv(P.v.priv + lo + q);
-        S.xf[q] = xf; S.tf[q] = tf; S.th[q] = th; S.tau[q] = __ldcg(P.v.tau + lo + q);
+        zz_ld_kin(P.v.kin + o, th, tf, xf, h0, h1);
+        const ZzPriv pr = zz_ld_priv(P.v.priv + o);
+        S.xf[q] = xf; S.tf[q] = tf; S.th[q] = th; S.tau[q] = __ldcg(P.v.tau + o);
         S.a[q] = pr.a; S.b[q] = pr.b; S.told[q] = pr.told; S.c[q] = pr.c;
-        S.kc[q] = __ldcg(P.v.kctr + lo + q);
-        if (LOGIT) { const int32_t e0 = __ldg(P.lg.acp + lo + q); S.a0[q] = e0; S.al[q] = __ldg(P.lg.acp + lo + q + 1) - e0; }
+        S.kc[q] = __ldcg(P.v.kctr + o);
+        S.og[q] = o;
+        if (LOGIT) { const int32_t e0 = __ldg(P.lg.acp + o); S.a0[q] = e0; S.al[q] = __ldg(P.lg.acp + o + 1) - e0; }
     }
     __syncwarp();
 
@@ -177,7 +181,7 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
         double tp; int li;
         zz_seq_argmin(bt, bi, tp, li);
         if (!(tp < ZZ_INF)) break;   // nothing will ever happen in this chain
-        const int32_t jg = lo + li;
+        const int32_t jn = lo + li, jg = S.og[li];   // chain-order id (matrices) and original id (streams, arrays)
         if (phase == 0) { if (!(tp < P.T)) break; }
         else if (phase == 2) { if (!(tp <= tend)) break; }
 
@@ -203,7 +207,7 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
         // ---- the proposal of coordinate i at tp (sfact.jl:118-121).  Everything that does not depend on the outcome is
         // started first: the loads of the own column of Z.Gamma (bound after a rejection), the uniform of the thinning test and
         // the logarithm of the uniform of the NEXT proposal time (poisson_time is a function of log u, src/poissontime.jl).
-        const int32_t be0 = __ldg(Q.bcp + jg), be1 = __ldg(Q.bcp + jg + 1);
+        const int32_t be0 = __ldg(Q.bcp + jn), be1 = __ldg(Q.bcp + jn + 1);
         const double gmu_i = __ldg(P.g.gmu + jg);
         const double th_i = S.th[li], tf_i = S.tf[li], xf_i = S.xf[li];
         const double xi = xf_i + th_i * (tp - tf_i);
@@ -250,7 +254,7 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
 #pragma unroll
                     for (int z = 0; z < 8; ++z) {
                         const bool ok = qb + z < len;
-                        m[z] = ok ? __ldg(L.rcol + q0 + qb + z) - lo : 0;
+                        m[z] = ok ? __ldg(Q.rcoln + q0 + qb + z) - lo : 0;
                         v[z] = ok ? __ldg(L.rval + q0 + qb + z) : 0.0;
                     }
 #pragma unroll
@@ -289,7 +293,7 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
             kc += 1u;
             if (Q.tcp) {
                 double d0, d1;
-                zz_seq_col_coop(S, Q.trow, Q.tval, __ldg(Q.tcp + jg), __ldg(Q.tcp + jg + 1), tp, lane, d0, d1);
+                zz_seq_col_coop(S, Q.trow, Q.tval, __ldg(Q.tcp + jn), __ldg(Q.tcp + jn + 1), tp, lane, d0, d1);
                 gt = P.g.h ? d0 - __ldg(P.g.h + jg) : d0;
             } else {
                 zz_seq_col_coop(S, Q.brow, Q.bval, be0, be1, tp, lane, sx, sth);
@@ -340,8 +344,9 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
                 const bool valid = e < be1;
                 int32_t jj = 0, lj = 0, f0 = 0, f1 = 0; double gmu_j = 0.0, Lj = 0.0; uint32_t kj = 0;
                 if (valid) {
-                    jj = __ldg(Q.brow + e); lj = jj - lo;
-                    f0 = __ldg(Q.bcp + jj); f1 = __ldg(Q.bcp + jj + 1);
+                    const int32_t jc = __ldg(Q.brow + e);   // chain-order id of the neighbour
+                    lj = jc - lo; jj = S.og[lj];
+                    f0 = __ldg(Q.bcp + jc); f1 = __ldg(Q.bcp + jc + 1);
                     gmu_j = __ldg(P.g.gmu + jj);
                     kj = S.kc[lj];
                     Lj = zz_log(zz_u01(seed0, seed1, (uint64_t)jj, (uint64_t)(kj++)));
@@ -385,14 +390,15 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
     if (phase == 1) return;
     __syncwarp();
     for (int32_t q = lane; q < nc; q += 32) {
-        double2* kq = reinterpret_cast<double2*>(P.v.kin + lo + q);
+        const int32_t o = S.og[q];
+        double2* kq = reinterpret_cast<double2*>(P.v.kin + o);
         kq[0] = make_double2(S.th[q], S.tf[q]);
-        reinterpret_cast<double*>(P.v.kin + lo + q)[2] = S.xf[q];
-        double2* pq = reinterpret_cast<double2*>(P.v.priv + lo + q);
+        reinterpret_cast<double*>(P.v.kin + o)[2] = S.xf[q];
+        double2* pq = reinterpret_cast<double2*>(P.v.priv + o);
         pq[0] = make_double2(S.a[q], S.b[q]);
         pq[1] = make_double2(S.told[q], S.c[q]);
-        P.v.tau[lo + q] = S.tau[q];
-        P.v.kctr[lo + q] = S.kc[q];
+        P.v.tau[o] = S.tau[q];
+        P.v.kctr[o] = S.kc[q];
     }
     for (unsigned long long p = tr_pos + (unsigned long long)lane; p < tr_end; p += 32ULL) {   // unused reservations
         double2* e = reinterpret_cast<double2*>(P.trace + p);

@@ -163,7 +163,7 @@ struct zzb_problem_s {
     ZzLogit lg;
     // sequential-chain schedule (zz_seq.cuh): compact matrices + connected components; hs.ok says whether it is available
     ZzHostSeq hs;
-    DevBuf s_bcp, s_brow, s_bval, s_tcp, s_trow, s_tval, s_comp, s_ent, s_rowrec;
+    DevBuf s_bcp, s_brow, s_bval, s_tcp, s_trow, s_tval, s_comp, s_ent, s_rowrec, s_orig, s_rcoln;
     ZzSeq sq;
 };
 
@@ -194,7 +194,7 @@ struct zzb_run_s {
         return prob && prob->hs.ok && nranks <= 1 && !strong && !grid_n &&
                !(flags & (ZZB_FLAG_LOCAL_BOUND | ZZB_FLAG_STICKY | ZZB_FLAG_BOOMERANG | ZZB_FLAG_REFRESH));
     }
-    int sched() const { return schedule >= 0 ? schedule : ((prob && prob->logit && seq_capable() && !max_windows) ? 2 : 1); }
+    int sched() const { return schedule >= 0 ? schedule : ((prob && (prob->logit || prob->hs.prefer) && seq_capable() && !max_windows) ? 2 : 1); }
     DevBuf inbox, inbox_cnt; unsigned int inbox_cap = 0, flag_words = 0; int inbox_grid = 0;
     DevBuf dbgbuf; std::vector<unsigned long long> dbghost;
     int tile_per = 0; unsigned int eval_threads = 0; int inbox_nr = 0;
@@ -358,7 +358,7 @@ int32_t zzb_event_elapsed_ms(float* ms)
 
 // Sequential-chain schedule: upload the compact matrices and the component table when the problem qualifies (zz_host_seq.h).
 #define ZZ_SEQ_RES_HOST 32u   // = ZZ_SEQ_RES of zz_seq.cuh
-#define ZZ_SEQ_MAX_NC 2900   // coordinates per component: 76 bytes of shared memory each
+#define ZZ_SEQ_MAX_NC 2700   // coordinates per component: 80 bytes of shared memory each (+ scratch, checked in zz_build_seq)
 static int32_t upload_seq(zzb_problem_s* p)
 {
     const ZzHostSeq& hs = p->hs;
@@ -366,13 +366,13 @@ static int32_t upload_seq(zzb_problem_s* p)
     if (!hs.ok) return ZZB_OK;
     int32_t st = 0;
 #define UPS(buf, vec) if (!st) st = upload(p->buf, hs.vec.data(), hs.vec.size() * sizeof(hs.vec[0]))
-    UPS(s_bcp, bcp); UPS(s_brow, brow); UPS(s_bval, bval); UPS(s_comp, comp);
+    UPS(s_bcp, bcp); UPS(s_brow, brow); UPS(s_bval, bval); UPS(s_comp, comp); UPS(s_orig, orig);
     if (hs.have_tgt) { UPS(s_tcp, tcp); UPS(s_trow, trow); UPS(s_tval, tval); }
 #undef UPS
     if (st) return st;
     p->sq.bcp = p->s_bcp.as<int32_t>(); p->sq.brow = p->s_brow.as<int32_t>(); p->sq.bval = p->s_bval.as<double>();
     if (hs.have_tgt) { p->sq.tcp = p->s_tcp.as<int32_t>(); p->sq.trow = p->s_trow.as<int32_t>(); p->sq.tval = p->s_tval.as<double>(); }
-    p->sq.comp = p->s_comp.as<int32_t>();
+    p->sq.comp = p->s_comp.as<int32_t>(); p->sq.orig = p->s_orig.as<int32_t>();
     p->sq.ncomp = (int32_t)hs.comp.size() - 1; p->sq.ncmax = hs.ncmax; p->sq.colmax = hs.colmax;
     if (p->logit) {   // packed design entries and per-row constants (the control-variate sigmoids are evaluated once, here)
         const ZzHostLogit& hl = p->hl;
@@ -384,10 +384,13 @@ static int32_t upload_seq(zzb_problem_s* p)
         }
         std::vector<ZzSeqRow> rr((size_t)hl.n);
         for (int32_t r = 0; r < hl.n; ++r) { rr[r].y = hl.y[r]; rr[r].ny = hl.ny[r]; rr[r].sn0 = zz_sigmoidn(hl.u0[r]); rr[r].ns0 = zz_nsigmoid(hl.u0[r]); }
-        st = upload(p->s_ent, ent.data(), ent.size() * sizeof(ZzSeqEnt));
+        std::vector<int32_t> rcoln(hl.rcol.size());
+        for (size_t q = 0; q < rcoln.size(); ++q) rcoln[q] = hs.newid[hl.rcol[q]];
+        st = upload(p->s_rcoln, rcoln.data(), rcoln.size() * sizeof(int32_t));
+        if (!st) st = upload(p->s_ent, ent.data(), ent.size() * sizeof(ZzSeqEnt));
         if (!st) st = upload(p->s_rowrec, rr.data(), rr.size() * sizeof(ZzSeqRow));
         if (st) return st;
-        p->sq.ent = p->s_ent.as<ZzSeqEnt>(); p->sq.rowrec = p->s_rowrec.as<ZzSeqRow>();
+        p->sq.ent = p->s_ent.as<ZzSeqEnt>(); p->sq.rowrec = p->s_rowrec.as<ZzSeqRow>(); p->sq.rcoln = p->s_rcoln.as<int32_t>();
     }
     return ZZB_OK;
 }
@@ -510,6 +513,10 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     CtxGuard cg;
     zzb_run_s* r = new zzb_run_s();
     r->prob = p; r->d = p->hg.d; r->flags = flags;
+    if (const char* e = getenv("ZZB200_DEFAULT_SCHEDULE")) {   // tests: pin the schedule that zzb_run_set("schedule") would otherwise choose
+        const int v = atoi(e);
+        if (v >= 0 && v <= 1) r->schedule = v;
+    }
     const size_t d = (size_t)r->d;
     int32_t st = 0;
 #define AL(buf, bytes) if (!st) st = r->buf.alloc(bytes)
@@ -909,7 +916,7 @@ static int32_t execute_seq(zzb_run_s* r, double T, float* device_ms)
     if (!(T < (double)INFINITY)) return fail(ZZB_E_ARG, "the sequential-chain schedule needs a finite end time");
     if (r->executed && !(r->hc.ctl.F < T)) return ZZB_OK;   // `while t' < T` (sfact.jl:199): the last event is already at or after T
     ZzSeq Q = pb->sq;
-    const unsigned dyn = 76u * (unsigned)Q.ncmax + 8u + 8u * (72u + 2u * ((unsigned)Q.colmax + 8u));   // state + scratch (zz_seq.cuh)
+    const unsigned dyn = 80u * (unsigned)Q.ncmax + 8u + 8u * (72u + 2u * ((unsigned)Q.colmax + 8u));   // state + scratch (zz_seq.cuh)
     if (dyn > 220u * 1024u) return fail(ZZB_E_ARG, "the sequential-chain schedule needs %u bytes of shared memory per chain", dyn);
     CUfunction f = pb->logit ? G.f_seq_logit : G.f_seq;
     if (dyn > 48u * 1024u) CU(cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn));
