@@ -76,6 +76,28 @@ __device__ __forceinline__ void zz_grid_barrier(ZzDevCtl* C, unsigned long long&
     __syncthreads();
 }
 
+// The same barrier in two halves: everything this CTA wrote before zz_grid_arrive is visible to every CTA that has returned
+// from zz_grid_wait; work that needs nothing from the other CTAs can run in between.
+__device__ __forceinline__ void zz_grid_arrive(ZzDevCtl* C, unsigned long long& epoch)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        epoch += gridDim.x;
+        __threadfence();
+        atomicAdd(&C->bar, 1ULL);
+    }
+}
+__device__ __forceinline__ void zz_grid_wait(ZzDevCtl* C, unsigned long long epoch, unsigned long long* prof)
+{
+    if (threadIdx.x == 0) {
+        const unsigned long long t0 = prof ? zz_now() : 0ULL;
+        while (zz_ld_acq(&C->bar) < epoch) { }
+        __threadfence();
+        if (prof) { prof[4] += zz_now() - t0; prof[6] += 1; }
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ unsigned long long zz_ld_acq_sys(const unsigned long long* p)
 {
     unsigned long long v;
@@ -136,10 +158,11 @@ template <bool MULTI>
 __device__ __forceinline__ ZzXres zz_boundary(const ZzParams& P, unsigned long long& epoch, unsigned long long& xep,
                                               unsigned long long* prof, const unsigned long long* psum,
                                               const unsigned long long* pmin, const unsigned int* pflag_word,
-                                              unsigned int flag_mask, unsigned int flag_value)
+                                              unsigned int flag_mask, unsigned int flag_value, bool arrived = false)
 {
     ZzDevCtl* C = P.ctl;
-    zz_grid_barrier(C, epoch, prof);
+    if (arrived) zz_grid_wait(C, epoch, prof);   // (the caller has called zz_grid_arrive for this boundary already)
+    else zz_grid_barrier(C, epoch, prof);
     ZzXres r;
     if (!MULTI) {
         r.sum = psum ? __ldcg(psum) : 0ULL;
@@ -1424,6 +1447,9 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
 #define ZZ_DBGLOG(kind, cnt) do { if (dbg_on && threadIdx.x == 0 && dbg_n < ZZ_DBG_REC) { unsigned long long* _r = P.dbgbuf + ((size_t)blockIdx.x * ZZ_DBG_REC + dbg_n) * 4; \
     _r[0] = (unsigned long long)(kind); _r[1] = (unsigned long long)(cnt); _r[2] = zz_now(); _r[3] = (unsigned long long)clock64(); dbg_n++; } } while (0)
 
+#ifndef ZZ_PRESCAN
+#define ZZ_PRESCAN 1
+#endif
 template <int KIND, bool MULTI, int MODE>
 __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
 {
@@ -1480,27 +1506,23 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
         }
     }
 
-    while (ctl.phase < ZZ_PH_DONE && !stop) {
-        if (cur > P.tag_limit) {  // list tags are about to run out of bits: forget all of them
-            if (MULTI) {   // own records and the replicas of the other ranks' records alike (nobody publishes before the boundary below)
-                for (int32_t j = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x); j < P.v.d; j += (int32_t)(gridDim.x * blockDim.x))
-                    reinterpret_cast<unsigned long long*>(P.v.kin + j)[3] = 0ULL;
-            } else {
-                for (int32_t j = t.c_lo + (int32_t)threadIdx.x; j < t.c_hi; j += blockDim.x)
-                    reinterpret_cast<unsigned long long*>(P.v.kin + j)[3] = 0ULL;
-            }
-            zz_boundary<MULTI>(P, epoch, xep, prof, nullptr, nullptr, nullptr, 0u, 0u);
-            cur = 0; st_rebases++;
-        }
-        const ZzCtl saved = ctl;
+    // Attempt state.  The prologue of an attempt (controller step, slot resets, scan of the tile, tokens) is a lambda because it
+    // runs in one of two places: at the top of the loop, or -- after a commit -- BEFORE the barrier that publishes the committed
+    // frontier: the scan reads only this tile's own proposal times, which the CTA has just committed itself, so it overlaps with
+    // the wait for the other tiles ("pre-scan").  Evaluations start after the barrier, as before.
+    ZzCtl saved = ctl;
+    uint32_t w0 = 0, watn = 0; int ws = 0; double H = 0.0; int incl = 0; bool dbg_on = false;
+    bool prescanned = false;
+    auto begin_attempt = [&]() {
+        saved = ctl;
         zz_ctl_begin(ctl);
-        const uint32_t w0 = cur + 1;
+        w0 = cur + 1;
         cur = w0 + ZZ_TAG_STRIDE;   // every tag of this attempt is in [w0, w0 + ZZ_TAG_STRIDE)
-        const int ws = (int)(wat % 3u);
-        const uint32_t watn = wat;   // attempt number stamped into inbox entries
+        ws = (int)(wat % 3u);
+        watn = wat;   // attempt number stamped into inbox entries
         wat++;
-        const double H = ctl.H; const int incl = ctl.incl;
-        const bool dbg_on = P.dbgbuf && windows_done == P.dbg_window;
+        H = ctl.H; incl = ctl.incl;
+        dbg_on = P.dbgbuf && windows_done == P.dbg_window;
         ZZ_DBGLOG(1, wat);
 
         // ---------------- scan: the coordinates of this tile with a proposal inside the window
@@ -1596,6 +1618,25 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
         }
         ZZ_TOC(0);
         ZZ_DBGLOG(2, S.tcount);
+    };
+
+    while (ctl.phase < ZZ_PH_DONE && !stop) {
+        if (!prescanned) {
+            if (cur > P.tag_limit) {  // list tags are about to run out of bits: forget all of them
+
+                if (MULTI) {   // own records and the replicas of the other ranks' records alike (nobody publishes before the boundary below)
+                    for (int32_t j = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x); j < P.v.d; j += (int32_t)(gridDim.x * blockDim.x))
+                        reinterpret_cast<unsigned long long*>(P.v.kin + j)[3] = 0ULL;
+                } else {
+                    for (int32_t j = t.c_lo + (int32_t)threadIdx.x; j < t.c_hi; j += blockDim.x)
+                        reinterpret_cast<unsigned long long*>(P.v.kin + j)[3] = 0ULL;
+                }
+                zz_boundary<MULTI>(P, epoch, xep, prof, nullptr, nullptr, nullptr, 0u, 0u);
+                cur = 0; st_rebases++;
+            }
+            begin_attempt();
+        }
+        prescanned = false;
 
         // ---------------- local rounds until the whole window is quiescent
         // Invariant at the top: queue `cq` is complete (local marks of the previous round + drained inbox entries), every
@@ -1784,15 +1825,28 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
             }
             ZZ_TOC(3);
             ZZ_DBGLOG(7, np);
-            // the committed frontier is published; proposals / flips of the window (length controller) and the stop word
-            // (bound violation on ANY GPU stops all of them) are reduced on the way
-            const ZzXres xc = zz_boundary<MULTI>(P, epoch, xep, prof, &C->nprop_win[ws], nullptr, &C->viol, 0xffffffffu, ZZ_X_STOP);
+            // Pre-scan: the prologue of the next attempt (its window end follows from the controller state alone -- the proposal
+            // count reduced at the barrier below enters one window later) runs before the barrier, on this tile's own freshly
+            // committed proposal times.  Not when the run may end here, when the tags are about to be rebased (that needs a
+            // barrier of its own first) or when a window is being logged.
+            const int wsc = ws; const double Hc = H;          // the committed attempt's slot and window end
+            const ZzCtl ctl_c = ctl; const uint32_t cur_c = cur, wat_c = wat;
+            // The barrier is split: this CTA ARRIVES first (its committed frontier is published), scans, and only then waits.
+            zz_grid_arrive(C, epoch);   // (its block barrier also makes the committed times of this tile visible to the whole CTA)
+            if (ZZ_PRESCAN && ctl.phase < ZZ_PH_DONE && !(P.max_windows && windows_done + 1u >= P.max_windows) && !(cur > P.tag_limit) &&
+                !P.dbgbuf) {
+                begin_attempt();
+                prescanned = true;
+            }
+            // proposals / flips of the window (length controller) and the stop word (bound violation on ANY GPU stops all of
+            // them) are reduced on the way
+            const ZzXres xc = zz_boundary<MULTI>(P, epoch, xep, prof, &C->nprop_win[wsc], nullptr, &C->viol, 0xffffffffu, ZZ_X_STOP, true);
             ZZ_DBGLOG(8, 0);
             if (leader && P.record_trace) {  // window-end marker (i = 0): lets the host sort window by window
                 const unsigned long long pos = atomicAdd(&C->trace_len, 1ULL);
                 if (pos < P.trace_cap) {
                     double2* e = reinterpret_cast<double2*>(P.trace + pos);
-                    e[0] = make_double2(H, __longlong_as_double(0LL));
+                    e[0] = make_double2(Hc, __longlong_as_double(0LL));
                     e[1] = make_double2(0.0, 0.0);
                 } else {
                     C->trace_full = 1u;
@@ -1802,6 +1856,9 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
             windows_done++;
             if (xc.flags & ZZ_X_STOP) stop = true;
             if (P.max_windows && windows_done >= P.max_windows) stop = true;
+            if (stop && prescanned) {   // the run ends here: forget the attempt that was only scanned (the next launch prepares its slots again)
+                ctl = ctl_c; cur = cur_c; wat = wat_c; prescanned = false;
+            }
         } else {
             st_retries++;
         }

@@ -136,20 +136,21 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
         S.kc = reinterpret_cast<uint32_t*>(base + 8 * n);
         S.a0 = reinterpret_cast<int32_t*>(S.kc + n);
         S.al = S.a0 + n;
-        S.og = S.al + n;
-        S.g = reinterpret_cast<double*>(S.og + n);              // (4 n words, n even: 8-byte aligned again)
+        // original ids: only when the host renumbered the coordinates (Q.orig set); otherwise id = lo + local index
+        S.og = Q.orig ? S.al + n : nullptr;
+        S.g = reinterpret_cast<double*>(S.al + n + (Q.orig ? n : (n & 1)));   // (3 n or 4 n words + padding: 8-byte aligned again)
         S.cx = S.g + 72; S.ct = S.cx + Q.colmax + 8;   // (the pipelined sums read up to 8 entries past the end)
     }
     const int32_t lo = S.lo, nc = S.nc;
     for (int32_t q = lane; q < nc; q += 32) {
-        const int32_t o = __ldg(Q.orig + lo + q);
+        const int32_t o = Q.orig ? __ldg(Q.orig + lo + q) : lo + q;
         double th, tf, xf; uint32_t h0, h1;
         zz_ld_kin(P.v.kin + o, th, tf, xf, h0, h1);
         const ZzPriv pr = zz_ld_priv(P.v.priv + o);
         S.xf[q] = xf; S.tf[q] = tf; S.th[q] = th; S.tau[q] = __ldcg(P.v.tau + o);
         S.a[q] = pr.a; S.b[q] = pr.b; S.told[q] = pr.told; S.c[q] = pr.c;
         S.kc[q] = __ldcg(P.v.kctr + o);
-        S.og[q] = o;
+        if (S.og) S.og[q] = o;
         if (LOGIT) { const int32_t e0 = __ldg(P.lg.acp + o); S.a0[q] = e0; S.al[q] = __ldg(P.lg.acp + o + 1) - e0; }
     }
     __syncwarp();
@@ -181,7 +182,7 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
         double tp; int li;
         zz_seq_argmin(bt, bi, tp, li);
         if (!(tp < ZZ_INF)) break;   // nothing will ever happen in this chain
-        const int32_t jn = lo + li, jg = S.og[li];   // chain-order id (matrices) and original id (streams, arrays)
+        const int32_t jn = lo + li, jg = S.og ? S.og[li] : jn;   // chain-order id (matrices) and original id (streams, arrays)
         if (phase == 0) { if (!(tp < P.T)) break; }
         else if (phase == 2) { if (!(tp <= tend)) break; }
 
@@ -345,7 +346,7 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
                 int32_t jj = 0, lj = 0, f0 = 0, f1 = 0; double gmu_j = 0.0, Lj = 0.0; uint32_t kj = 0;
                 if (valid) {
                     const int32_t jc = __ldg(Q.brow + e);   // chain-order id of the neighbour
-                    lj = jc - lo; jj = S.og[lj];
+                    lj = jc - lo; jj = S.og ? S.og[lj] : jc;
                     f0 = __ldg(Q.bcp + jc); f1 = __ldg(Q.bcp + jc + 1);
                     gmu_j = __ldg(P.g.gmu + jj);
                     kj = S.kc[lj];
@@ -390,7 +391,7 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
     if (phase == 1) return;
     __syncwarp();
     for (int32_t q = lane; q < nc; q += 32) {
-        const int32_t o = S.og[q];
+        const int32_t o = S.og ? S.og[q] : lo + q;
         double2* kq = reinterpret_cast<double2*>(P.v.kin + o);
         kq[0] = make_double2(S.th[q], S.tf[q]);
         reinterpret_cast<double*>(P.v.kin + o)[2] = S.xf[q];

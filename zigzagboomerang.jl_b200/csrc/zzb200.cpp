@@ -372,7 +372,10 @@ static int32_t upload_seq(zzb_problem_s* p)
     if (st) return st;
     p->sq.bcp = p->s_bcp.as<int32_t>(); p->sq.brow = p->s_brow.as<int32_t>(); p->sq.bval = p->s_bval.as<double>();
     if (hs.have_tgt) { p->sq.tcp = p->s_tcp.as<int32_t>(); p->sq.trow = p->s_trow.as<int32_t>(); p->sq.tval = p->s_tval.as<double>(); }
-    p->sq.comp = p->s_comp.as<int32_t>(); p->sq.orig = p->s_orig.as<int32_t>();
+    p->sq.comp = p->s_comp.as<int32_t>();
+    bool ident = true;   // chains that are contiguous ranges already: no renumbering, 4 bytes of shared memory per coordinate less
+    for (size_t j = 0; j < hs.orig.size() && ident; ++j) ident = (hs.orig[j] == (int32_t)j);
+    p->sq.orig = ident ? nullptr : p->s_orig.as<int32_t>();
     p->sq.ncomp = (int32_t)hs.comp.size() - 1; p->sq.ncmax = hs.ncmax; p->sq.colmax = hs.colmax;
     if (p->logit) {   // packed design entries and per-row constants (the control-variate sigmoids are evaluated once, here)
         const ZzHostLogit& hl = p->hl;
@@ -916,7 +919,7 @@ static int32_t execute_seq(zzb_run_s* r, double T, float* device_ms)
     if (!(T < (double)INFINITY)) return fail(ZZB_E_ARG, "the sequential-chain schedule needs a finite end time");
     if (r->executed && !(r->hc.ctl.F < T)) return ZZB_OK;   // `while t' < T` (sfact.jl:199): the last event is already at or after T
     ZzSeq Q = pb->sq;
-    const unsigned dyn = 80u * (unsigned)Q.ncmax + 8u + 8u * (72u + 2u * ((unsigned)Q.colmax + 8u));   // state + scratch (zz_seq.cuh)
+    const unsigned dyn = (Q.orig ? 80u : 76u) * (unsigned)Q.ncmax + 8u + 8u * (72u + 2u * ((unsigned)Q.colmax + 8u));   // state + scratch (zz_seq.cuh)
     if (dyn > 220u * 1024u) return fail(ZZB_E_ARG, "the sequential-chain schedule needs %u bytes of shared memory per chain", dyn);
     CUfunction f = pb->logit ? G.f_seq_logit : G.f_seq;
     if (dyn > 48u * 1024u) CU(cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn));
