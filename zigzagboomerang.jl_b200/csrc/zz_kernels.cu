@@ -445,10 +445,10 @@ __device__ __forceinline__ void zz_grid_fill(const ZzParams& P, int32_t j, doubl
 
 template <int KIND> __device__ __forceinline__ unsigned int zz_reader_ranks(const ZzParams& P, int32_t j);
 
-// Fold the converged end-of-window state of coordinate j into the frontier.
-template <int MODE, int KIND = ZZ_KIND_CSR, bool MULTI = false>
-__device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, const ZzSpecR& s, uint32_t w0, uint32_t cur,
-                                               unsigned int& nprop_acc, unsigned int& nflip_acc)
+// Fold the converged end-of-window state of coordinate j into the frontier.  Two halves: the private record (every coordinate
+// with a proposal inside the window) and the kinematic record / moment sums / trace (only coordinates with events).
+template <int MODE>
+__device__ __forceinline__ void zz_commit_light(const ZzParams& P, int32_t j, const ZzSpecR& s, unsigned int& nprop_acc)
 {
     ZzDevCtl* C = P.ctl;
     if (s.flags & ZZ_F_VIOL) {
@@ -468,6 +468,12 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, con
     }
     nprop_acc += s.nprop;
     if (s.flags & ZZ_F_STICKY_ERR) atomicExch(&C->viol, 2u);      // error("x[i] !~ 0"), ss_fact.jl:89-91
+}
+template <int MODE, int KIND = ZZ_KIND_CSR, bool MULTI = false>
+__device__ __forceinline__ void zz_commit_heavy(const ZzParams& P, int32_t j, const ZzSpecR& s, uint32_t w0, uint32_t cur,
+                                                unsigned int& nflip_acc)
+{
+    ZzDevCtl* C = P.ctl;
     if (s.nflip) {
         nflip_acc += s.nflip;
         double th, tf, xf; uint32_t h0, h1;
@@ -543,6 +549,13 @@ __device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, con
             }
         }
     }
+}
+template <int MODE, int KIND = ZZ_KIND_CSR, bool MULTI = false>
+__device__ __forceinline__ void zz_commit_node(const ZzParams& P, int32_t j, const ZzSpecR& s, uint32_t w0, uint32_t cur,
+                                               unsigned int& nprop_acc, unsigned int& nflip_acc)
+{
+    zz_commit_light<MODE>(P, j, s, nprop_acc);
+    zz_commit_heavy<MODE, KIND, MULTI>(P, j, s, w0, cur, nflip_acc);
 }
 
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK)
@@ -1809,11 +1822,23 @@ __device__ __forceinline__ void zz_run_body_async(const ZzParams& P)
         ctl = trial;
         if (act == ZZ_ACT_COMMIT) {
             ZZ_TIC();
+            // Two passes, so that the lanes of a warp do the same thing: (1) the private record of every touched coordinate (two
+            // dependent loads, four stores), collecting the coordinates WITH events -- about one in five -- in the (empty) queue
+            // 0; (2) their kinematic records, moment sums and trace records, spread evenly over the CTA.  In one pass nearly every
+            // warp iteration had some lane on the long path and 26 lanes waiting for it.
             unsigned int np = 0, nf = 0;
             for (unsigned int e = threadIdx.x; e < tcount; e += blockDim.x) {
                 const int32_t j = __ldcg(t.tlist + e);
                 const ZzSpecR sp = zz_load_spec(P.spec + j);
-                zz_commit_node<MODE, KIND, MULTI>(P, j, sp, w0, 0xffffffffu, np, nf);
+                zz_commit_light<MODE>(P, j, sp, np);
+                if (sp.nflip) zz_q_put(S, t, 0, atomicAdd(&S.n[0], 1u), j);
+            }
+            __syncthreads();
+            const unsigned int nev = S.n[0];
+            for (unsigned int e = threadIdx.x; e < nev; e += blockDim.x) {
+                const int32_t j = zz_q_get(S, t, 0, e);
+                const ZzSpecR sp = zz_load_spec(P.spec + j);
+                zz_commit_heavy<MODE, KIND, MULTI>(P, j, sp, w0, 0xffffffffu, nf);
             }
             cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
             np = cg::reduce(w, np, cg::plus<unsigned int>());
