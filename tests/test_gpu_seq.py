@@ -40,6 +40,29 @@ def test_general_sparse_with_mu_h_adapt(gpu, seed):
     assert (got.c != c).any()
 
 
+@pytest.mark.parametrize("warps", [1, 2, 4])
+def test_speculative_thinning_any_number_of_warps(gpu, warps):
+    """The warps of a chain take the earliest queue entries side by side; an entry counts only if every earlier one of the step
+    was rejected and re-queued later.  Same bits for 1, 2 and 4 warps: Gaussian chains (several components, tight and loose
+    bounds: mostly accepted / mostly rejected proposals) and the logistic target."""
+    import logistic_cases as LC
+    G, x0, th0, c = gpu.gmrf_config(12)
+    Gb = O.block_diagonal(G, 3)
+    for scale, T in ((1.0, 8.0), (25.0, 3.0)):
+        ref = O.spdmp(Gb, Gb, 0.0, x0, th0, T, scale * c)
+        got, _ = run_gpu(gpu, Gb, Gb, 0.0, x0, th0, T, scale * c, tune=dict(schedule=2, seq_warps=warps))
+        O.assert_same_run(ref, got)
+    ct = np.full(Gb.n, np.sqrt(np.finfo(float).eps))
+    ref = O.spdmp(Gb, Gb, 0.0, x0, th0, 4.0, ct)
+    got, _ = run_gpu(gpu, Gb, Gb, 0.0, x0, th0, 4.0, ct, tune=dict(schedule=2, seq_warps=warps))
+    O.assert_same_run(ref, got)
+    *design, T = LC.SMALL[1]
+    cfg = LC.make(gpu, *design)
+    lref = LC.run_oracle(O, cfg, T)
+    lgot, _ = LC.run_device(gpu, cfg, T, tune=dict(schedule=2, seq_warps=warps))
+    O.assert_same_run(lref, lgot)
+
+
 def test_dense_columns(gpu):
     """Columns longer than a warp: the cooperative column sums run over several chunks."""
     d = 70

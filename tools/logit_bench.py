@@ -24,7 +24,7 @@ for R in Rs:
     t0 = time.time()
     big = cfg if R == 1 else LC.replicas(z, cfg, R)
     t1 = time.time()
-    got, Xi = LC.run_device(z, big, T, tune=dict(schedule=int(os.environ.get("SCHEDULE", "2"))))
+    got, Xi = LC.run_device(z, big, T, tune=dict(schedule=int(os.environ.get("SCHEDULE", "2")), seq_warps=int(os.environ.get("SEQ_WARPS", "0"))))
     st = Xi.stats
     print(f"R = {R}: d = {big['p']}, {len(got.events)} events, {got.num} proposals in {Xi.device_ms:.1f} ms on the device = "
           f"{len(got.events) / (Xi.device_ms * 1e-3):.3g} events/s; windows {st['windows']}, passes {st['passes']}, evaluations {st['node_evals']}, "

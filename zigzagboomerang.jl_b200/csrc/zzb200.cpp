@@ -198,6 +198,7 @@ struct zzb_run_s {
     DevBuf inbox, inbox_cnt; unsigned int inbox_cap = 0, flag_words = 0; int inbox_grid = 0;
     DevBuf dbgbuf; std::vector<unsigned long long> dbghost;
     int tile_per = 0; unsigned int eval_threads = 0; int inbox_nr = 0;
+    int seq_warps = 0;                 // sequential chains: warps per chain (0 = automatic)
     // device-side ordering of the trace (zz_tsort_*): the events of the last execute, sorted, still in HBM
     DevBuf trace_sorted, ts_work; bool dev_sorted = false; unsigned long long n_sorted = 0; bool host_sort_only = false;
     DevBuf trace_map, s3; bool have_map = false;   // subtrace filter / inclusion-time accumulator (sticky)
@@ -709,6 +710,7 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
     else if (!strcmp(key, "host_sort")) r->host_sort_only = value != 0.0;   // order the trace on the host (A/B of the device sort)
     else if (!strcmp(key, "eval_threads")) r->eval_threads = (unsigned int)value;
+    else if (!strcmp(key, "seq_warps")) r->seq_warps = (int)value;   // sequential chains: 1 (plain loop), 2 or 4 warps per chain; 0 = automatic
     else if (!strcmp(key, "schedule")) {   // 0 / 1: windowed relaxation (pass-synchronous / asynchronous); 2: sequential chains; -1: automatic
         const int v = (int)value;
         if (v < -1 || v > 2) return fail(ZZB_E_ARG, "schedule must be -1, 0, 1 or 2");
@@ -919,10 +921,22 @@ static int32_t execute_seq(zzb_run_s* r, double T, float* device_ms)
     if (!(T < (double)INFINITY)) return fail(ZZB_E_ARG, "the sequential-chain schedule needs a finite end time");
     if (r->executed && !(r->hc.ctl.F < T)) return ZZB_OK;   // `while t' < T` (sfact.jl:199): the last event is already at or after T
     ZzSeq Q = pb->sq;
-    const unsigned dyn = (Q.orig ? 80u : 76u) * (unsigned)Q.ncmax + 8u + 8u * (72u + 2u * ((unsigned)Q.colmax + 8u));   // state + scratch (zz_seq.cuh)
-    if (dyn > 220u * 1024u) return fail(ZZB_E_ARG, "the sequential-chain schedule needs %u bytes of shared memory per chain", dyn);
+    // warps per chain (speculative thinning, zz_seq.cuh): 4 when the chains are few (latency of the single chain), 2 when many
+    // chains share the SMs (registers: six chains of two warps fit), unless zzb_run_set("seq_warps") says otherwise
+    auto smem_for = [&](int w) { return (Q.orig ? 80u : 76u) * (unsigned)Q.ncmax + 8u + (unsigned)w * 8u * (72u + 2u * ((unsigned)Q.colmax + 8u)); };   // state + scratch per warp
     CUfunction f = pb->logit ? G.f_seq_logit : G.f_seq;
-    if (dyn > 48u * 1024u) CU(cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)dyn));
+    CU(cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max(smem_for(4), 48u * 1024u)));
+    int nw = r->seq_warps;
+    if (nw != 1 && nw != 2 && nw != 4) {   // automatic: the most warps per chain with which all chains are resident at once
+        nw = 1;
+        for (int w = 4; w >= 2; w >>= 1) {
+            int per_sm = 0;
+            CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, 32 * w, smem_for(w)));
+            if ((long long)Q.ncomp <= (long long)per_sm * G.sm_count) { nw = w; break; }
+        }
+    }
+    const unsigned dyn = smem_for(nw);
+    if (dyn > 220u * 1024u) return fail(ZZB_E_ARG, "the sequential-chain schedule needs %u bytes of shared memory per chain", dyn);
     if (P.record_trace && r->trace_cap < (unsigned long long)ZZ_SEQ_RES_HOST * (unsigned long long)Q.ncomp)
         return fail(ZZB_E_TRACE, "trace buffer (%llu records) too small for %d chains (%u records reserved at a time)", r->trace_cap, Q.ncomp, ZZ_SEQ_RES_HOST);
     if (r->dev_sorted && r->n_sorted) {   // events of an earlier execute that are still on the device (sorted) join the host vector first
@@ -940,7 +954,7 @@ static int32_t execute_seq(zzb_run_s* r, double T, float* device_ms)
         Q.phase = phase;
         void* args[] = { &P, &Q };
         CU(cuEventRecord(G.ev0, G.stream));
-        CU(cuLaunchKernel(f, (unsigned)Q.ncomp, 1, 1, 32, 1, 1, dyn, G.stream, args, nullptr));
+        CU(cuLaunchKernel(f, (unsigned)Q.ncomp, 1, 1, 32u * (unsigned)nw, 1, 1, dyn, G.stream, args, nullptr));
         CU(cuEventRecord(G.ev1, G.stream));
         CU(cuStreamSynchronize(G.stream));
         r->launches++;
