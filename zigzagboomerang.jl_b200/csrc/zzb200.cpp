@@ -935,6 +935,8 @@ static int32_t execute_seq(zzb_run_s* r, double T, float* device_ms)
             if ((long long)Q.ncomp <= (long long)per_sm * G.sm_count) { nw = w; break; }
         }
     }
+    while (nw > 1 && P.record_trace && r->trace_cap < (unsigned long long)ZZ_SEQ_RES_HOST * (unsigned long long)Q.ncomp * (unsigned long long)nw)
+        nw >>= 1;   // (every warp of every chain may hold one reservation of trace records)
     const unsigned dyn = smem_for(nw);
     if (dyn > 220u * 1024u) return fail(ZZB_E_ARG, "the sequential-chain schedule needs %u bytes of shared memory per chain", dyn);
     if (P.record_trace && r->trace_cap < (unsigned long long)ZZ_SEQ_RES_HOST * (unsigned long long)Q.ncomp)
