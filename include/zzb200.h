@@ -130,6 +130,13 @@ int32_t zzb_spdmp_boomerang_run(zzb_problem_t p, double t0, const double* x0, co
 int32_t zzb_sspdmp3_run(zzb_problem_t p, const double* x0, const double* theta0, double T, double c, double kappa, int32_t rule,
                         const uint64_t* seed, uint32_t flags, zzb_run_t* out);
 
+/* sspdmp4 / asynchzz (src/asynchzz.jl:250-265,80-147): the same strong-bound sticky process with a bound constant c[i] and a thaw
+ * rate kappa[i] PER coordinate (StrongUpperBounds :2-7,20-28; StickyBarriers :258), start time t0; coordinates with x0 == 0 start
+ * frozen and continue, once thawed, with theta0 (rule :sticky of :206-213).  adapt = false only.  The reference's parallel schedule
+ * (local minima of a PartialQueue, :150-245) is replaced by the device's own; the run ends after the first event at or after T. */
+int32_t zzb_sspdmp4_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, const double* c,
+                        const double* kappa, const uint64_t* seed, uint32_t flags, zzb_run_t* out);
+
 /* spdmp / pdmp with Z = ZigZag(Gamma, mu, sigma; lambdaref > 0): velocity refreshments theta_i <- sigma_i * (+-1) at total rate
  * lambdaref (hasrefresh src/fact_samplers.jl:19; refresh branch src/sfact.jl:78-114, clock :188-190).  Refreshments are trace events
  * but not acceptances.  Per-coordinate clocks of rate lambdaref / d (superposition of the reference's single clock). */

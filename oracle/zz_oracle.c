@@ -1005,15 +1005,24 @@ zzo_run *zzo_sparsestickyzz(int64_t d, const int64_t *g_colptr, const int64_t *g
  *   * adapt is refused (the adapted bound is ONE global c, :336,383: its value depends on the global event order).
  * A reflection still reschedules nobody but the reflecting coordinate: in the windowed scheme of the device the timeline of
  * a coordinate then has OWN items only, and neighbours enter through the positions read at those items. */
-zzo_run *zzo_sparsestickyzz_ctr(int64_t d, const int64_t *g_colptr, const int64_t *g_rowval, const double *g_nzval, const double *h,
-                                const double *x0, const double *th0, double T, double c, double kappa, int rule,
-                                const uint64_t *seed)
+/* The same contract with a bound constant c[i] and a thaw rate kappa[i] PER coordinate, a start time t0 and rule 2 = "a thawed
+ * coordinate continues with the velocity it had when it froze" -- the process of asynchzz / sspdmp4 (src/asynchzz.jl:20-37,
+ * 150-245: StrongUpperBounds ab :20-28 with per-coordinate c, queue_time! :42-52 = min(bound expiry, proposal at rate
+ * 0.01 + a^+, hitting time of 0), thaw clock per coordinate :188, rule :sticky :206-213, accepted reflection :217-231, renewal
+ * :192-203), whose law does not depend on its schedule (local minima of a PartialQueue processed by threads); only
+ * adapt = false.  The reference's own end of a run depends on that schedule (it finishes the round in which the earliest time
+ * passes T, :138-147); the contract ends like sspdmp3: after the first event at or after T.
+ * Rules 0 / 1 with all c, all kappa equal and t0 = 0 are zzo_sparsestickyzz_ctr. */
+zzo_run *zzo_strongsticky_ctr(int64_t d, const int64_t *g_colptr, const int64_t *g_rowval, const double *g_nzval, const double *h,
+                              double t0, const double *x0, const double *th0, double T, const double *cv, const double *kv, int rule,
+                              const uint64_t *seed)
 {
     zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run));
     csc G = { g_colptr, g_rowval, g_nzval };
     size_t nb = (size_t)d * sizeof(double);
-    r->d = d;
-    char *active = (char *)calloc((size_t)d, 1), *psign = (char *)malloc((size_t)d), *action = (char *)calloc((size_t)d, 1);
+    r->d = d; r->t0 = t0;
+    char *active = (char *)calloc((size_t)d, 1), *action = (char *)calloc((size_t)d, 1);
+    double *psign = (double *)malloc(nb);   /* rules 0 / 1: remembered sign as +-1; rule 2: the velocity to continue with */
     double *tf = (double *)calloc((size_t)d, 8), *xf = (double *)calloc((size_t)d, 8), *th = (double *)calloc((size_t)d, 8);
     double *bt = (double *)calloc((size_t)d, 8), *ba = (double *)calloc((size_t)d, 8), *bexp = (double *)calloc((size_t)d, 8);
     uint32_t *kc = (uint32_t *)calloc((size_t)d, sizeof(uint32_t));
@@ -1032,7 +1041,7 @@ zzo_run *zzo_sparsestickyzz_ctr(int64_t d, const int64_t *g_colptr, const int64_
         (out) = h ? acc_ - h[(i) - 1] : acc_; } while (0)
     /* ab (:136-142) at time s, then queue_time! (:144-172) */
 #define SC_QUEUE(i, s, gi) do { \
-        ba[(i) - 1] = c + (gi) * th[(i) - 1]; bt[(i) - 1] = (s); bexp[(i) - 1] = (s) + 1.0 / c; \
+        ba[(i) - 1] = cv[(i) - 1] + (gi) * th[(i) - 1]; bt[(i) - 1] = (s); bexp[(i) - 1] = (s) + 1.0 / cv[(i) - 1]; \
         double xs_ = SC_POS((i), (s)); \
         double trefl_ = (s) + zzo_poisson_time3(ba[(i) - 1], 0.0, 0.01, SC_U(i)); \
         double thit_ = (th[(i) - 1] * xs_ >= 0) ? INFINITY : (s) - xs_ / th[(i) - 1]; \
@@ -1041,21 +1050,22 @@ zzo_run *zzo_sparsestickyzz_ctr(int64_t d, const int64_t *g_colptr, const int64_
         action[(i) - 1] = (thit_ == tau_) ? C_HIT : (trefl_ == tau_) ? C_REFLECT : C_RENEW; \
         if (Q.index[(i)]) h_set(&Q, (i), tau_); else h_enqueue(&Q, (i), tau_); } while (0)
     for (int64_t k = 0; k < d; ++k) {
-        psign[k] = 1;
-        if (x0[k] != 0) { active[k] = 1; xf[k] = x0[k]; th[k] = th0[k]; psign[k] = th0[k] > 0; }
+        psign[k] = rule == 2 ? th0[k] : 1.0;
+        tf[k] = t0;
+        if (x0[k] != 0) { active[k] = 1; xf[k] = x0[k]; th[k] = th0[k]; psign[k] = rule == 2 ? th0[k] : (th0[k] > 0 ? 1.0 : -1.0); }
     }
     for (int64_t i = 1; i <= d; ++i) {
-        if (active[i - 1]) { double gi; SC_GRAD(i, 0.0, gi); SC_QUEUE(i, 0.0, gi); }
-        else { action[i - 1] = C_THAW; h_enqueue(&Q, i, 0.0 - zz_log(SC_U(i)) / kappa); }
+        if (active[i - 1]) { double gi; SC_GRAD(i, t0, gi); SC_QUEUE(i, t0, gi); }
+        else { action[i - 1] = C_THAW; h_enqueue(&Q, i, t0 - zz_log(SC_U(i)) / kv[i - 1]); }
     }
-    double tp = 0.0; int64_t num = 0;
+    double tp = t0; int64_t num = 0;
     const double tl0 = now_s();
     while (tp < T && r->status == ZZO_OK) {
         for (;;) {
             int64_t i = Q.key[1]; tp = Q.val[1];
             double gi;
             if (action[i - 1] == C_THAW) {
-                double vi = rule == 1 ? (SC_U(i) < 0.5 ? -1.0 : 1.0) : -1.0 + 2.0 * (double)psign[i - 1];
+                double vi = rule == 1 ? (SC_U(i) < 0.5 ? -1.0 : 1.0) : psign[i - 1];
                 active[i - 1] = 1; tf[i - 1] = tp; th[i - 1] = vi;   /* xf stays the (signed) zero of the hit / of x0 */
                 SC_GRAD(i, tp, gi); SC_QUEUE(i, tp, gi);
                 push_event(r, tp, i, xf[i - 1], vi);
@@ -1067,7 +1077,7 @@ zzo_run *zzo_sparsestickyzz_ctr(int64_t d, const int64_t *g_colptr, const int64_
                    reference's record of a deleted coordinate is (t', 0.0, 0.0) (:20-26): equal up to the sign of zero */
                 active[i - 1] = 0; tf[i - 1] = tp; xf[i - 1] = -0.0 * th[i - 1]; th[i - 1] = 0.0;
                 action[i - 1] = C_THAW;
-                h_set(&Q, i, tp - zz_log(SC_U(i)) / kappa);
+                h_set(&Q, i, tp - zz_log(SC_U(i)) / kv[i - 1]);
                 push_event(r, tp, i, xf[i - 1], 0.0);
                 break;
             }
@@ -1083,7 +1093,8 @@ zzo_run *zzo_sparsestickyzz_ctr(int64_t d, const int64_t *g_colptr, const int64_
                 r->acc[i - 1]++;
                 if (l > lb) { r->status = ZZO_E_BOUND; r->err_i = i; r->err_t = tp; r->err_l = l; r->err_lb = lb; break; }
                 xf[i - 1] = SC_POS(i, tp); tf[i - 1] = tp; th[i - 1] = -th[i - 1];
-                if (rule == 0) psign[i - 1] = th[i - 1] > 0;
+                if (rule == 0) psign[i - 1] = th[i - 1] > 0 ? 1.0 : -1.0;
+                else if (rule == 2) psign[i - 1] = th[i - 1];
                 SC_GRAD(i, tp, gi); SC_QUEUE(i, tp, gi);
                 push_event(r, tp, i, xf[i - 1], th[i - 1]);
                 break;
@@ -1097,10 +1108,21 @@ zzo_run *zzo_sparsestickyzz_ctr(int64_t d, const int64_t *g_colptr, const int64_
 #undef SC_QUEUE
     r->loop_seconds = now_s() - tl0;
     r->num = num;
-    for (int64_t k = 0; k < d; ++k) r->c[k] = c;
+    for (int64_t k = 0; k < d; ++k) r->c[k] = cv[k];
     r->t = tf; r->x = xf; r->th = th;
     free(active); free(psign); free(action); free(bt); free(ba); free(bexp); free(kc);
     free(Q.key); free(Q.val); free(Q.index);
+    return r;
+}
+
+zzo_run *zzo_sparsestickyzz_ctr(int64_t d, const int64_t *g_colptr, const int64_t *g_rowval, const double *g_nzval, const double *h,
+                                const double *x0, const double *th0, double T, double c, double kappa, int rule,
+                                const uint64_t *seed)
+{
+    double *cv = (double *)malloc((size_t)d * 8), *kv = (double *)malloc((size_t)d * 8);
+    for (int64_t k = 0; k < d; ++k) { cv[k] = c; kv[k] = kappa; }
+    zzo_run *r = zzo_strongsticky_ctr(d, g_colptr, g_rowval, g_nzval, h, 0.0, x0, th0, T, cv, kv, rule, seed);
+    free(cv); free(kv);
     return r;
 }
 

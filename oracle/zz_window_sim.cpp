@@ -114,6 +114,20 @@ zzw_run* zzw_sparsesticky(int64_t d, const int64_t* gcp, const int64_t* grv, con
                     tag_limit | 0x80000000u, 0, kap.data(), nullptr, 0.0, 0.0, nullptr, &st);
 }
 
+// the same with a bound constant and a thaw rate PER coordinate, a start time and rule 2 = "continue with the velocity saved at the
+// freeze" (asynchzz / sspdmp4; contract: zzo_strongsticky_ctr).  th0 is passed as given: the record set-up below freezes the
+// coordinates that start at 0 and keeps their velocity, like zz_setup_kernel.
+zzw_run* zzw_strongsticky(int64_t d, const int64_t* gcp, const int64_t* grv, const double* gnz, const double* h, double t0,
+                          const double* x0, const double* th0, double T, const double* c, const double* kappa, int rule,
+                          const uint64_t* seed, double delta0, double target_frac, uint32_t tag_limit)
+{
+    ZzStrong st; st.c = c[0]; st.kappa = kappa[0]; st.rule = rule; st.pad = 0;
+    std::vector<double> th(th0, th0 + d), zero((size_t)d, 0.0);
+    if (rule != 2) for (int64_t j = 0; j < d; ++j) if (x0[j] == 0.0) th[j] = 0.0;
+    return zzw_impl(d, gcp, grv, gnz, h, gcp, grv, gnz, zero.data(), t0, x0, th.data(), T, c, seed, 0, 1.0, delta0, target_frac,
+                    tag_limit | 0x80000000u, 0, kappa, nullptr, 0.0, 0.0, nullptr, &st);
+}
+
 }  // extern "C"
 
 static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, const double* tnz, const double* h,
@@ -169,6 +183,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
     for (int64_t j = 0; j < d; ++j) {
         kin[j].theta = th0[j]; kin[j].tf = t0; kin[j].xf = x0[j]; kin[j].hdr[0] = kin[j].hdr[1] = 0;
         priv[j].c = c_in[j];
+        if (st && st->rule == 2 && x0[j] == 0.0) { priv[j].told = th0[j]; kin[j].theta = 0.0; }   // (as zz_setup_kernel)
     }
     double F0 = ZZ_INF;
     for (int64_t j = 0; j < d; ++j) {

@@ -58,6 +58,9 @@ def lib():
                                         C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]
         L.zzo_sparsestickyzz_ctr.restype = C.c_void_p
         L.zzo_sparsestickyzz_ctr.argtypes = [C.c_int64] + [C.c_void_p] * 6 + [C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
+        L.zzo_strongsticky_ctr.restype = C.c_void_p
+        L.zzo_strongsticky_ctr.argtypes = [C.c_int64] + [C.c_void_p] * 4 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                           C.c_int, C.c_void_p]
         L.zzo_queue_script.restype = None
         L.zzo_queue_script.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_int64, C.c_void_p, C.c_void_p]
@@ -227,6 +230,27 @@ def sparsestickyzz(G, x0, theta0, T, c, kappa, *, h=None, rule="sticky", adapt=F
         L.zzo_free(r)
 
 
+STRONG_RULES = {"sticky": 0, "reversible": 1, "keep": 2}
+
+
+def strongsticky(G, t0, x0, theta0, T, c, kappa, *, h=None, rule="keep", seed=(1, 2)):
+    """The strong-bound sticky ZigZag with a bound constant ``c[i]`` and a thaw rate ``kappa[i]`` per coordinate, start time ``t0``
+    (oracle/zz_oracle.c:zzo_strongsticky_ctr) -- with ``rule="keep"`` the process of ``asynchzz`` / ``sspdmp4``
+    (src/asynchzz.jl): a thawed coordinate continues with the velocity it had when it froze."""
+    L = lib()
+    d = G.n
+    f8 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    x0c, th0c, cv, kv = f8(x0), f8(theta0), f8(c), f8(kappa)
+    hc = None if h is None else f8(h)
+    sd = np.array(seed, dtype=np.uint64)
+    r = L.zzo_strongsticky_ctr(d, _p(G.colptr), _p(G.rowval), _p(G.nzval), _p(hc), float(t0), _p(x0c), _p(th0c), float(T), _p(cv), _p(kv),
+                               STRONG_RULES[rule], _p(sd))
+    try:
+        return _collect(L, r, d, t0, x0c, th0c)
+    finally:
+        L.zzo_free(r)
+
+
 # ---------------------------------------------------------------------------------------------------
 # Host emulation of the GPU schedule (oracle/zz_window_sim.cpp) -- test-only, see its header.
 _wlib = None
@@ -291,6 +315,13 @@ def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1,
                                 C.c_double(float(t0)), _p(x0), _p(theta0), C.c_double(float(T)), _p(c), _p(sd), C.c_int(int(adapt)), C.c_double(float(factor)),
                                 C.c_double(float(delta0)), C.c_double(float(target_frac)), C.c_uint32(int(tag_limit)))
         r = C.c_void_p(r)
+    elif strong == "keep":   # asynchzz / sspdmp4: per-coordinate c and kappa, start time, velocity kept over a freeze
+        L.zzw_strongsticky.restype = C.c_void_p
+        L.zzw_strongsticky.argtypes = [C.c_int64] + [C.c_void_p] * 4 + [C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_uint32]
+        kv = f8(kappa)
+        r = L.zzw_strongsticky(d, _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(h), float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(kv),
+                               2, _p(sd), float(delta0), float(target_frac), int(tag_limit))
     elif strong is not None:
         r = L.zzw_sparsesticky(d, _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(h), _p(x0), _p(theta0), float(T), float(c[0]),
                                float(kappa), {"sticky": 0, "reversible": 1}[strong], _p(sd), float(delta0), float(target_frac), int(tag_limit))

@@ -74,3 +74,37 @@ def test_sspdmp3_api_matches_the_contract(gpu):
     for f in ("t", "x", "theta"):
         assert np.array_equal(Xi.events[f].view(np.uint64), ref.events[f].view(np.uint64))
     assert np.array_equal(x.view(np.uint64), ref.x.view(np.uint64))
+
+
+def test_sspdmp4_asynchzz_process_bit_exact(gpu):
+    """`sspdmp4` (src/asynchzz.jl:250-265) on the device: per-coordinate c and kappa, shifted start, non-unit speeds, velocity kept
+    over a freeze -- bit for bit against the contract zzo_strongsticky_ctr; with equal constants and unit speeds it is sspdmp3."""
+    import oracle_lib as O
+    from test_sparse_sticky import chain_precision
+    rng = np.random.default_rng(11)
+    for case in range(6):
+        G = chain_precision(gpu, int(rng.integers(20, 400))) if case % 2 else gpu.grid_precision(int(rng.integers(4, 20)), int(rng.integers(4, 20)), shift=0.1)
+        p = G.n
+        x0 = np.where(rng.random(p) < 0.5, rng.standard_normal(p), 0.0)
+        th0 = rng.choice(np.array([-1.5, -1.0, 0.5, 1.0]), p)
+        h = 0.5 * rng.standard_normal(p) if case % 3 == 0 else None
+        t0 = float(rng.choice([0.0, -2.0, 5.0]))
+        T = t0 + 20.0
+        base = 3.0 + 4.0 * float(np.abs(G.nzval).max()) + (0.0 if h is None else float(np.abs(h).max()))
+        c = base * rng.uniform(1.0, 2.0, p)
+        kappa = rng.choice(np.array([0.2, 1.0, 3.0]), p)
+        ref = O.strongsticky(G, t0, x0, th0, T, c, kappa, h=h, seed=(7, 8 + case))
+        Xi, (acc, num) = gpu.sspdmp4(None, gpu.GaussianPotential(G, h), t0, x0, th0, T, c, None, gpu.ZigZag(G, np.zeros(p)), kappa, seed=(7, 8 + case))
+        assert num == ref.num and acc == int(ref.acc.sum()) and np.array_equal(Xi.acc_per_coordinate, ref.acc)
+        assert len(Xi.events) == len(ref.events) and np.array_equal(Xi.events["i"], ref.events["i"])
+        for f in ("t", "x", "theta"):
+            assert np.array_equal(Xi.events[f].view(np.uint64), ref.events[f].view(np.uint64)), f
+        t, x, th = Xi.final
+        assert np.array_equal(x.view(np.uint64), ref.x.view(np.uint64)) and np.array_equal(th.view(np.uint64), ref.theta.view(np.uint64))
+    # equal constants, unit speeds, t0 = 0: the :sticky process of sspdmp3
+    G = chain_precision(gpu, 300)
+    x0 = np.where(rng.random(300) < 0.5, rng.standard_normal(300), 0.0)
+    th0 = np.where(x0 != 0.0, rng.choice(np.array([-1.0, 1.0]), 300), 1.0)
+    X3, _, _ = gpu.sspdmp3(gpu.GaussianPotential(G), (x0, th0), 30.0, 6.0, None, gpu.ZigZag(G, np.zeros(300)), 0.5, rule="sticky", seed=(1, 2))
+    X4, _ = gpu.sspdmp4(None, gpu.GaussianPotential(G), 0.0, x0, th0, 30.0, 6.0, None, gpu.ZigZag(G, np.zeros(300)), 0.5, seed=(1, 2))
+    assert np.array_equal(X3.events, X4.events)

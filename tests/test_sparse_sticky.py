@@ -154,3 +154,59 @@ def test_windowed_schedule_with_the_strong_bound_timeline_equals_its_contract(zz
             O.assert_same_run(ref, sim)
             max_iters = max(max_iters, sim.stats["max_iters"])
     assert 2 <= max_iters <= 8
+
+
+def test_asynchzz_process_contract_and_schedule_emulation(zzb):
+    """asynchzz / sspdmp4 (src/asynchzz.jl): the strong-bound sticky process with c[i], kappa[i] per coordinate, a start time and
+    the velocity kept over a freeze.  (1) With equal constants, unit speeds and t0 = 0 it is sspdmp3's :sticky process, bit for
+    bit; (2) the device timeline inside the host emulation of both schedules equals the contract on random problems (per-coordinate
+    constants, non-unit speeds, shifted start); (3) a coordinate continues with exactly the velocity it froze with."""
+    rng = np.random.default_rng(5)
+    p = 40
+    G = chain_precision(zzb, p)
+    x0 = np.where(rng.random(p) < 0.5, rng.standard_normal(p), 0.0)
+    th0 = rng.choice(np.array([-1.0, 1.0]), p)
+    a = O.sparsestickyzz(G, x0, th0, 40.0, 6.0, 0.5, rule="sticky", seed=(3, 4), ctr=True)
+    th0a = np.where(x0 != 0.0, th0, 1.0)    # sspdmp3 re-enters a coordinate that starts frozen with +1
+    b = O.strongsticky(G, 0.0, x0, th0a, 40.0, np.full(p, 6.0), np.full(p, 0.5), rule="keep", seed=(3, 4))
+    O.assert_same_run(a, b)
+    for case in range(24):
+        if rng.random() < 0.5:
+            G = chain_precision(zzb, int(rng.integers(2, 90)))
+        else:
+            G = zzb.grid_precision(int(rng.integers(2, 8)), int(rng.integers(2, 8)), shift=0.1)
+        p = G.n
+        x0 = np.where(rng.random(p) < rng.choice([0.0, 0.4, 1.0]), rng.standard_normal(p), 0.0)
+        th0 = rng.choice(np.array([-1.5, -1.0, -0.5, 0.5, 1.0, 2.0]), p)
+        h = 0.5 * rng.standard_normal(p) if rng.random() < 0.3 else None
+        t0 = float(rng.choice([0.0, -3.0, 7.5]))
+        T = t0 + float(rng.uniform(5, 40))
+        base = 3.0 + 4.0 * float(np.abs(G.nzval).max()) + (0.0 if h is None else float(np.abs(h).max()))
+        c = base * rng.uniform(1.0, 2.0, p)
+        kappa = rng.choice(np.array([0.1, 0.5, 3.0]), p)
+        sd = (int(rng.integers(1 << 40)), int(rng.integers(1 << 40)))
+        kw = dict(delta0=float(10 ** rng.uniform(-3, 0.3)), target_frac=float(10 ** rng.uniform(-1.3, 0.7)))
+        if case % 2:
+            kw.update(async_tiles=int(rng.integers(1, 6)), order_seed=int(rng.integers(1, 1 << 30)))
+        try:
+            ref = O.strongsticky(G, t0, x0, th0, T, c, kappa, h=h, seed=sd)
+        except O.BoundError:
+            ref = None
+        try:
+            sim = O.window_sim(None, G, t0, x0, th0, T, c, h=h, kappa=kappa, strong="keep", seed=sd, **kw)
+        except O.BoundError:
+            sim = None
+        assert (ref is None) == (sim is None), case
+        if ref is None:
+            continue
+        O.assert_same_run(ref, sim)
+        # velocity before a freeze == velocity after the following thaw, per coordinate
+        vel = {j + 1: (th0[j] if x0[j] != 0.0 else 0.0) for j in range(p)}
+        saved = {j + 1: th0[j] for j in range(p)}
+        for t, i, x, th in ref.events:
+            i = int(i)
+            if th == 0.0:
+                saved[i] = vel[i]
+            elif vel[i] == 0.0:
+                assert th == saved[i], (case, i)
+            vel[i] = th

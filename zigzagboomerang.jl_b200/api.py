@@ -642,6 +642,47 @@ def sspdmp3(grad, u0, T, c, G, Z, kappa, *args, rule="reversible", adapt=False, 
             prob.close()
 
 
+def sspdmp4(coloring, grad, t0, x0, v0, T, c, G, Z, kappa, *args, adapt=False, factor=1.5, seed=None, record_trace=True, tune=None):
+    """``sspdmp4(Coloring, grad, t, x0, v0, T, c, nothing, Z, kappa, args...; adapt=false, factor=1.5)`` = ``trace, acc``
+    (src/asynchzz.jl:250-265): the strong-bound sticky ZigZag of ``asynchzz`` -- a bound constant ``c[i]`` per coordinate, valid
+    for ``1/c[i]`` and then renewed (``StrongUpperBounds``, :2-7,20-28), a reflection reschedules nobody else, coordinates stick at
+    0 and thaw at rate ``kappa[i]``, continuing with the velocity they had (rule ``:sticky``, :206-213); coordinates with
+    ``x0 == 0`` start frozen (:112-116).  The reference runs this process with its own thread schedule (local minima of a
+    ``PartialQueue`` over regions coloured by `Coloring`, :150-245); the device uses its windowed relaxation, so `coloring` is
+    accepted and ignored -- the law does not depend on the schedule.  Returns ``trace, (acc, num)``; ``trace.final`` holds
+    ``(t, x, theta)``.  Not on the device path: ``adapt``."""
+    if adapt:
+        raise NotImplementedError("sspdmp4(...; adapt=true) is not implemented on the device path")
+    if not isinstance(Z, ZigZag):
+        raise TypeError("sspdmp4: Z must be a ZigZag (its Gamma gives the dependency structure, src/asynchzz.jl:252-256)")
+    prob, own = _as_problem(grad, Z)
+    if seed is None:
+        seed = (secrets.randbits(64), secrets.randbits(64))
+    d = prob.d
+    cv = np.full(d, float(c)) if np.isscalar(c) else f8(c)
+    kv = np.full(d, float(kappa)) if np.isscalar(kappa) else f8(kappa)
+    if not ((cv > 0).all() and (kv > 0).all()):
+        raise ValueError("sspdmp4 needs c[i] > 0 and kappa[i] > 0")
+    run = Run(prob, record_trace=record_trace, kappa=kv)
+    try:
+        run.set(strong_c=float(cv[0]), strong_rule=2, **(tune or {}))
+        run.upload(t0, x0, v0, cv, seed=seed)
+        run.execute(T)
+        t, x, th, _ = run.final_state()
+        acc, num = run.counts()
+        ev = run.events() if record_trace else np.empty(0, dtype=EVENT_DTYPE)
+        Xi = FactTrace(Z, t0, f8(x0), np.where(f8(x0) != 0.0, f8(v0), 0.0), ev)
+        Xi.stats = run.stats()
+        Xi.device_ms = run.device_ms
+        Xi.acc_per_coordinate = acc
+        Xi.final = (t, x, th)
+        return Xi, (int(acc.sum()), num)
+    finally:
+        run.close()
+        if own:
+            prob.close()
+
+
 class FactSampler:
     """``FactSampler(grad, u0, c, [G,] F; factor=1.8, adapt=false, seed)`` with ``u0 = (t0, (x0, theta0))`` -- the pull-style
     interface of src/sfactiter.jl:5-64.  Iterating yields ``(t, (t, i, x_i, theta_i))`` pairs, one per accepted event, in

@@ -564,8 +564,11 @@ zz_setup_kernel(const ZzParams P, const double* __restrict__ x0, const double* _
 {
     for (int32_t j = P.setup_lo + blockIdx.x * blockDim.x + threadIdx.x; j < P.setup_hi; j += gridDim.x * blockDim.x) {
         ZzKin k; k.theta = th0[j]; k.tf = P.t0; k.xf = x0[j]; k.hdr[0] = 0; k.hdr[1] = 0;
-        P.v.kin[j] = k;
         ZzPriv p; p.a = 0.0; p.b = 0.0; p.told = P.t0; p.c = c0[j];
+        // strong-bound sampler, rule 2 (asynchzz, src/asynchzz.jl:112-116): a coordinate that starts at 0 starts frozen and
+        // remembers the velocity it will continue with
+        if (P.st.c > 0.0 && P.st.rule == 2 && k.xf == 0.0) { p.told = k.theta; k.theta = 0.0; }
+        P.v.kin[j] = k;
         P.v.priv[j] = p;
         P.dstamp[j] = 0; P.acc[j] = 0; P.s1[j] = 0.0; P.s2[j] = 0.0;
         if (P.s3) P.s3[j] = 0.0;

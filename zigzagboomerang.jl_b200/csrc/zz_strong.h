@@ -16,9 +16,12 @@
 #include "zz_core.h"
 
 struct ZzStrong {
-    double c;        // the ONE bound constant of SparseStickyUpperBounds (:127-134)
-    double kappa;    // thaw rate per frozen coordinate (StickyBarriers.kappa, stickyzz.jl:19-23)
-    int32_t rule;    // 0 = :sticky (re-enter with the remembered sign), 1 = :reversible (random sign)
+    double c;        // > 0: this run uses the strong-bound sampler.  The bound constant itself is read PER COORDINATE from the private
+                     // record (sspdmp3: the one constant of SparseStickyUpperBounds, :127-134, in every record; sspdmp4 / asynchzz:
+                     // the vector c of StrongUpperBounds, src/asynchzz.jl:2-7,20-28)
+    double kappa;    // (unused: the thaw rate of coordinate j is ZzView::kappa[j] -- StickyBarriers.kappa, stickyzz.jl:19-23)
+    int32_t rule;    // 0 = :sticky of sparsestickyzz (re-enter with the remembered sign), 1 = :reversible (random sign),
+                     // 2 = :sticky of asynchzz (src/asynchzz.jl:206-213: continue with the velocity saved when it froze)
     int32_t pad;
 };
 
@@ -31,11 +34,11 @@ struct ZzStrong {
 
 // ab (:136-142, adapt = false) at time s followed by queue_time! (:144-172): the earliest of bound expiry, proposed
 // reflection (rate 0.01 + a^+, poissontime.jl:86-92 with b = 0) and reaching 0 (:119-126)
-ZZ_HD void zz_strong_queue(const ZzView& v, const ZzStrong& S, int32_t j, double s, double xs, double th, double gi,
+ZZ_HD void zz_strong_queue(const ZzView& v, double cj, int32_t j, double s, double xs, double th, double gi,
                            uint32_t& k, double& ba, double& bexp, double& tau, uint32_t& act)
 {
-    ba = S.c + gi * th;
-    bexp = s + 1.0 / S.c;
+    ba = cj + gi * th;
+    bexp = s + 1.0 / cj;
     const double trefl = s + zz_poisson_time3(ba, 0.0, 0.01, zz_u01(v.seed0, v.seed1, (uint64_t)j, k++));
     const double thit = (th * xs >= 0.0) ? ZZ_INF : s - xs / th;
     double t = bexp < trefl ? bexp : trefl;
@@ -90,7 +93,7 @@ ZZ_HD void zz_timeline_strong(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w
             nev++;
             tf = s; th = vi;
             const double xs = xf + th * (s - tf);
-            zz_strong_queue(v, S, j, s, xs, th, zz_strong_grad<NB>(hd, g, j, s, xs, th), k, ba, bexp, tau, act);
+            zz_strong_queue(v, w.c, j, s, xs, th, zz_strong_grad<NB>(hd, g, j, s, xs, th), k, ba, bexp, tau, act);
             continue;
         }
         const double xs = xf + th * (s - tf);
@@ -102,14 +105,14 @@ ZZ_HD void zz_timeline_strong(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w
             nev++;
             xf = -0.0 * th; tf = s; th = 0.0;
             act = ZZ_SA_THAW;
-            tau = s - zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, k++)) / S.kappa;
+            tau = s - zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, k++)) / v.kappa[j];
             continue;
         }
         const double gi = zz_strong_grad<NB>(hd, g, j, s, xs, th);
         const double l = zz_pos(gi * th), lb = zz_pos(ba);          // lambda, :129-134 (b = 0)
         if (act == ZZ_SA_RENEW) {                                  // :330-340
             if (l > lb && !(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
-            zz_strong_queue(v, S, j, s, xs, th, gi, k, ba, bexp, tau, act);
+            zz_strong_queue(v, w.c, j, s, xs, th, gi, k, ba, bexp, tau, act);
             continue;
         }
         nprop++;                                                   // :372-399
@@ -121,10 +124,11 @@ ZZ_HD void zz_timeline_strong(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w
             nev++;
             xf = xs; tf = s; th = -th;
             if (S.rule == 0) psign = th > 0.0 ? 1.0 : -1.0;
+            else if (S.rule == 2) psign = th;
             const double xn = xf + th * (s - tf);
-            zz_strong_queue(v, S, j, s, xn, th, zz_strong_grad<NB>(hd, g, j, s, xn, th), k, ba, bexp, tau, act);
+            zz_strong_queue(v, w.c, j, s, xn, th, zz_strong_grad<NB>(hd, g, j, s, xn, th), k, ba, bexp, tau, act);
         } else {
-            zz_strong_queue(v, S, j, s, xs, th, gi, k, ba, bexp, tau, act);
+            zz_strong_queue(v, w.c, j, s, xs, th, gi, k, ba, bexp, tau, act);
         }
     }
     o.a = ba; o.b = bexp; o.told = psign; o.tau = tau; o.c = w.c;
@@ -154,13 +158,14 @@ ZZ_HD bool zz_init_node_strong(const ZzGraph& g, const ZzView& v, const ZzStrong
     uint32_t k = 0, act;
     double tau;
     if (th == 0.0) {
-        pr.a = 0.0; pr.b = 0.0; pr.told = 1.0;
+        pr.a = 0.0; pr.b = 0.0;
+        if (S.rule != 2) pr.told = 1.0;   // (rule 2: zz_setup_kernel has left the velocity to continue with in the record)
         act = ZZ_SA_THAW;
-        tau = t0 - zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, k++)) / S.kappa;
+        tau = t0 - zz_log(zz_u01(v.seed0, v.seed1, (uint64_t)j, k++)) / v.kappa[j];
     } else {
-        pr.told = th > 0.0 ? 1.0 : -1.0;
+        pr.told = S.rule == 2 ? th : (th > 0.0 ? 1.0 : -1.0);
         const double xs = xf + th * (t0 - tf);
-        zz_strong_queue(v, S, j, t0, xs, th, zz_strong_grad<ZZ_NB>(hd, g, j, t0, xs, th), k, pr.a, pr.b, tau, act);
+        zz_strong_queue(v, pr.c, j, t0, xs, th, zz_strong_grad<ZZ_NB>(hd, g, j, t0, xs, th), k, pr.a, pr.b, tau, act);
     }
     v.priv[j] = pr;
     v.tau[j] = tau;

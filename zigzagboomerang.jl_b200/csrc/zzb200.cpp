@@ -836,7 +836,7 @@ int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* t
             so = (size_t)r->setup_lo * 8; nb = (size_t)(r->setup_hi - r->setup_lo) * 8;
         }
         CU(cuMemcpyHtoDAsync(r->in_x.p + so, x0 + so / 8, nb, G.stream));
-        if (r->strong) {   // sparsestickystate (sparsestickyzz.jl:10-12): x0 == 0 starts frozen = velocity 0 in its record
+        if (r->strong && r->strong_rule != 2) {   // sparsestickystate (sparsestickyzz.jl:10-12): x0 == 0 starts frozen = velocity 0 in its record (rule 2: zz_setup_kernel keeps the velocity)
             std::vector<double> th(theta0, theta0 + r->d);
             for (int32_t j = 0; j < r->d; ++j) if (x0[j] == 0.0) th[j] = 0.0;
             CU(cuMemcpyHtoD(r->in_th.p, th.data(), nb));
@@ -1219,6 +1219,32 @@ int32_t zzb_sspdmp3_run(zzb_problem_t p, const double* x0, const double* theta0,
     if (!st) st = zzb_run_set(r, "strong_c", c);
     if (!st) st = zzb_run_set(r, "strong_rule", (double)rule);
     if (!st) st = zzb_run_upload(r, 0.0, x0, theta0, cv.data(), seed, 0, 1.0);
+    if (!st) st = zzb_run_execute(r, T, nullptr);
+    if (st) { zzb_run_free(r); return st; }
+    int32_t st2 = fetch_state(r);
+    if (st2) { zzb_run_free(r); return st2; }
+    *out = r;
+    return ZZB_OK;
+}
+
+// sspdmp4 / asynchzz (src/asynchzz.jl:250-265,80-147): the strong-bound sticky ZigZag with a bound constant c[i] and a thaw rate
+// kappa[i] per coordinate (StrongUpperBounds :2-7,20-28; StickyBarriers((0,0), (:sticky,:sticky), (kappa_i,kappa_i)) :258), start
+// time t0; coordinates with x0 == 0 start frozen and continue, once thawed, with theta0 (:112-116,206-213).  The reference runs
+// this process with its own parallel schedule (local minima of a PartialQueue, regions coloured for Threads.@threads, :150-245);
+// the device runs it with the windowed relaxation like sspdmp3 -- the law is the same, the schedule is not part of it.
+int32_t zzb_sspdmp4_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, const double* c,
+                        const double* kappa, const uint64_t* seed, uint32_t flags, zzb_run_t* out)
+{
+    if (!out || !p || !x0 || !theta0 || !c || !kappa || !seed) return fail(ZZB_E_ARG, "null argument");
+    zzb_run_t r = nullptr;
+    int32_t st = zzb_run_create(p, flags | ZZB_FLAG_STICKY, 0, &r);
+    if (st) return st;
+    for (int32_t j = 0; j < r->d; ++j)
+        if (!(c[j] > 0.0) || !(kappa[j] > 0.0)) { zzb_run_free(r); return fail(ZZB_E_ARG, "sspdmp4 needs c[i] > 0 and kappa[i] > 0"); }
+    st = zzb_run_upload_kappa(r, kappa);
+    if (!st) st = zzb_run_set(r, "strong_c", c[0]);
+    if (!st) st = zzb_run_set(r, "strong_rule", 2.0);
+    if (!st) st = zzb_run_upload(r, t0, x0, theta0, c, seed, 0, 1.0);
     if (!st) st = zzb_run_execute(r, T, nullptr);
     if (st) { zzb_run_free(r); return st; }
     int32_t st2 = fetch_state(r);

@@ -12,7 +12,7 @@ module ZigZagBoomerangB200
 using ZigZagBoomerang
 using ZigZagBoomerang: ZigZag, FactBoomerang, LocalBound, FactTrace, Trace, Seed
 using SparseArrays
-import ZigZagBoomerang: spdmp, pdmp, sspdmp, sspdmp3
+import ZigZagBoomerang: spdmp, pdmp, sspdmp, sspdmp3, sspdmp4
 
 const libzzb200 = get(ENV, "ZZB200_LIB", joinpath(@__DIR__, "..", "libzzb200.so"))
 const cubin = get(ENV, "ZZB200_CUBIN", joinpath(@__DIR__, "..", "zzb200_kernels.cubin"))
@@ -270,6 +270,50 @@ function sspdmp3(∇ϕ::GaussianPotential, u0, T, c, ::Nothing, Z::ZigZag, κ, a
         acc = Vector{Int}(undef, d); num = Ref{Int64}(0)
         check(ccall((:zzb_run_counts, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ref{Int64}), run[], acc, num))
         return Ξ, (sum(acc), num[]), (t, x, θ)
+    finally
+        ccall((:zzb_run_free, libzzb200), Int32, (Ptr{Cvoid},), run[])
+        ccall((:zzb_problem_free, libzzb200), Int32, (Ptr{Cvoid},), prob[])
+    end
+end
+
+# sspdmp4(Coloring, ∇ϕ, t, x0, v0, T, c, nothing, Z, κ; adapt, factor) (src/asynchzz.jl:250-265): the strong-bound sticky ZigZag of
+# `asynchzz` with a bound constant c[i] and a thaw rate κ[i] per coordinate; coordinates with x0 == 0 start frozen and continue with
+# v0 once thawed.  The reference's thread schedule (and its `Coloring`) is replaced by the device's own; same law.  Returns
+# trace, (acc, num) -- the reference returns (trace, acc::AcceptanceDiagnostics).
+function sspdmp4(Coloring, ∇ϕ::GaussianPotential, t, x0, v0, T, c, ::Nothing, Z::ZigZag, κ, args...; progress = false, adapt = false,
+                 factor = 1.5, seed = Seed())
+    adapt && error("sspdmp4(...; adapt = true) is not implemented on the device path")
+    init()
+    d = length(x0)
+    x0v, θ0v = Vector{Float64}(x0), Vector{Float64}(v0)
+    cv = c isa Number ? fill(Float64(c), d) : Vector{Float64}(c)
+    κv = κ isa Number ? fill(Float64(κ), d) : Vector{Float64}(κ)
+    Γ = ∇ϕ.Γ
+    prob = Ref{Ptr{Cvoid}}(C_NULL); run = Ref{Ptr{Cvoid}}(C_NULL)
+    h = ∇ϕ.h === nothing ? Ptr{Float64}(C_NULL) : pointer(∇ϕ.h)
+    sd = UInt64[seed[1], seed[2]]
+    GC.@preserve Γ x0v θ0v cv κv sd ∇ϕ begin
+        check(ccall((:zzb_problem_create_gaussian, libzzb200), Int32,
+                    (Ref{Ptr{Cvoid}}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
+                    prob, d, Γ.colptr, Γ.rowval, Γ.nzval, h, C_NULL, C_NULL, C_NULL, C_NULL))
+        st = ccall((:zzb_sspdmp4_run, libzzb200), Int32,
+                   (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{UInt64}, UInt32, Ref{Ptr{Cvoid}}),
+                   prob[], Float64(t), x0v, θ0v, T, cv, κv, sd, UInt32(0), run)
+        if st != 0
+            run[] != C_NULL && ccall((:zzb_run_free, libzzb200), Int32, (Ptr{Cvoid},), run[])
+            ccall((:zzb_problem_free, libzzb200), Int32, (Ptr{Cvoid},), prob[])
+            check(st)
+        end
+    end
+    try
+        n = Ref{Int64}(0)
+        check(ccall((:zzb_trace_len, libzzb200), Int32, (Ptr{Cvoid}, Ref{Int64}), run[], n))
+        θstart = [x0v[i] == 0 ? 0.0 : θ0v[i] for i in 1:d]
+        Ξ = ZigZagBoomerang.FactTrace(Z, Float64(t), x0v, θstart, Vector{Tuple{Float64,Int,Float64,Float64}}(undef, n[]))
+        check(ccall((:zzb_trace_copy, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64), run[], Ξ.events, 0, n[]))
+        acc = Vector{Int}(undef, d); num = Ref{Int64}(0)
+        check(ccall((:zzb_run_counts, libzzb200), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ref{Int64}), run[], acc, num))
+        return Ξ, (sum(acc), num[])
     finally
         ccall((:zzb_run_free, libzzb200), Int32, (Ptr{Cvoid},), run[])
         ccall((:zzb_problem_free, libzzb200), Int32, (Ptr{Cvoid},), prob[])
