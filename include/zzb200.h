@@ -61,6 +61,9 @@ extern "C" {
 #define ZZB_FLAG_STICKY 4u      /* sticky ZigZag sspdmp (src/ss_fact.jl): coordinates freeze at 0, thaw after Exp(kappa_i) */
 #define ZZB_FLAG_STICKY_REVERSIBLE 16u /* sspdmp(...; reversible = true): a thawing coordinate re-enters with a random sign, ss_fact.jl:111-113 */
 #define ZZB_FLAG_STICKY_STRONG_UB 32u  /* sspdmp(...; strong_upperbounds = true): a freeze reschedules nobody, ss_fact.jl:97-107 */
+#define ZZB_FLAG_STICKY_ZZ 128u  /* with ZZB_FLAG_STICKY: the dense sticky sampler stickyzz / sspdmp2 (src/stickyzz.jl:176-338) -- the sspdmp loop with
+                                   proposal times at rate 0.01 + (a + b t)^+ (queue_time! :144-165, poissontime.jl:93-99) and coordinates that
+                                   start at 0 starting frozen (:198-206) */
 #define ZZB_FLAG_REFRESH 64u    /* ZigZag with velocity refreshments (Z.lambdaref > 0): src/sfact.jl:78-114,188-190; zzb_run_upload_refresh */
 #define ZZB_FLAG_BOOMERANG 8u   /* factorised Boomerang (F::FactBoomerang): rotation around Z.mu, velocity refreshments */
 

@@ -63,6 +63,10 @@
 #define ZZO_LOCAL_BOUND 8 /* spdmp(..., C::LocalBound, ...) of src/local.jl:95-149 */
 #define ZZO_STICKY_REVERSIBLE 16 /* sspdmp(...; reversible = true): a thawing coordinate re-enters with a random sign, ss_fact.jl:111-113 */
 #define ZZO_STICKY_STRONG_UB 32  /* sspdmp(...; strong_upperbounds = true): a freeze reschedules nobody, ss_fact.jl:97-107 */
+#define ZZO_STICKYZZ 64          /* the dense sticky sampler stickyzz / sspdmp2 (src/stickyzz.jl:176-338): the same loop with (i) proposal
+                                    times drawn at rate 0.01 + (a + b t)^+ ("guarantee minimum rate", poissontime.jl:93-99 through
+                                    queue_time! stickyzz.jl:144-165) and (ii) coordinates that start AT 0 start frozen with a thaw clock
+                                    (:198-206) instead of being queued */
 
 #define ZZO_OK 0
 #define ZZO_E_BOUND 3 /* "Tuning parameter `c` too small." sfact.jl:124 */
@@ -620,7 +624,8 @@ typedef struct { ctx *z; heapq *Q; char *f; } sctx;
 static void s_queue_time(sctx *S, int64_t j, double tj, double xj)
 { /* queue_time!(rng, Q, t, x, th, i, b, f, Z), ss_fact.jl:54-66 */
     ctx *z = S->z;
-    double trefl = o_poisson_time(z->ba[j - 1], z->bb[j - 1], draw(z, j));
+    double trefl = (z->mode & ZZO_STICKYZZ) ? zzo_poisson_time3(z->ba[j - 1], z->bb[j - 1], 0.01, draw(z, j))
+                                            : o_poisson_time(z->ba[j - 1], z->bb[j - 1], draw(z, j));
     double tfreeze = freezing_time(xj, z->th[j - 1]);
     if (tfreeze <= trefl) { S->f[j - 1] = 1; h_set(S->Q, j, tj + tfreeze); }
     else { S->f[j - 1] = 0; h_set(S->Q, j, tj + trefl); }
@@ -670,9 +675,13 @@ zzo_run *zzo_sspdmp(int64_t d,
     Q.index = (int64_t *)malloc(((size_t)d + 2) * sizeof(int64_t));
     sctx S = { z, &Q, f };
     /* ss_fact.jl:177-188 */
+    if (mode & ZZO_STICKYZZ)   /* stickyzz.jl:198-206: a coordinate that starts at 0 starts frozen and keeps its speed for the thaw */
+        for (int64_t k = 0; k < d; ++k) if (x0[k] == 0.0) { thf[k] = z->th[k]; z->th[k] = 0.0; }
     for (int64_t i = 1; i <= d; ++i) ab_zigzag(z, i, t0);
     for (int64_t i = 1; i <= d; ++i) {
-        double trefl = o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i));
+        if ((mode & ZZO_STICKYZZ) && x0[i - 1] == 0.0) { f[i - 1] = 0; h_enqueue(&Q, i, t0 - zz_log(draw(z, i)) / kappa[i - 1]); continue; }
+        double trefl = (mode & ZZO_STICKYZZ) ? zzo_poisson_time3(z->ba[i - 1], z->bb[i - 1], 0.01, draw(z, i))
+                                             : o_poisson_time(z->ba[i - 1], z->bb[i - 1], draw(z, i));
         double tfreez = freezing_time(x0[i - 1], th0[i - 1]);
         if (trefl > tfreez) { f[i - 1] = 1; h_enqueue(&Q, i, t0 + tfreez); }
         else { f[i - 1] = 0; h_enqueue(&Q, i, t0 + trefl); }

@@ -139,7 +139,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
 {
     zzw_run* r = new zzw_run();
     r->d = d;
-    const int sticky_opts = local_bound & (ZZ_STICKY_REVERSIBLE | ZZ_STICKY_STRONG_UB);   // (the sspdmp option bits travel in `local_bound`)
+    const int sticky_opts = local_bound & (ZZ_STICKY_REVERSIBLE | ZZ_STICKY_STRONG_UB | ZZ_STICKY_ZZ);   // (the sspdmp option bits travel in `local_bound`)
     local_bound &= 1;
     ZzHostGraph G;
     std::vector<double> zero_mu((size_t)d, 0.0);
@@ -184,6 +184,7 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
         kin[j].theta = th0[j]; kin[j].tf = t0; kin[j].xf = x0[j]; kin[j].hdr[0] = kin[j].hdr[1] = 0;
         priv[j].c = c_in[j];
         if (st && st->rule == 2 && x0[j] == 0.0) { priv[j].told = th0[j]; kin[j].theta = 0.0; }   // (as zz_setup_kernel)
+        if (kappa && !st && (sticky_opts & ZZ_STICKY_ZZ) && x0[j] == 0.0) { priv[j].a = th0[j]; kin[j].theta = 0.0; }
     }
     double F0 = ZZ_INF;
     for (int64_t j = 0; j < d; ++j) {

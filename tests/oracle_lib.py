@@ -15,6 +15,7 @@ ARITH_INPLACE, ARITH_LAZY = 0, 2
 GRAPH_ALL = 4
 LOCAL_BOUND = 8
 STICKY_REVERSIBLE, STICKY_STRONG_UB = 16, 32   # sspdmp(...; reversible / strong_upperbounds), src/ss_fact.jl:97,111
+STICKYZZ = 64                                  # the dense sticky sampler stickyzz / sspdmp2 (src/stickyzz.jl): rate floor, frozen start
 PARITY_MODE = RNG_CTR | ARITH_LAZY  # what the GPU must reproduce bit for bit
 
 EVENT_DTYPE = np.dtype([("t", "<f8"), ("i", "<i8"), ("x", "<f8"), ("theta", "<f8")])  # trace.jl:38
@@ -293,7 +294,7 @@ def wlib():
 
 def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), adapt=False, factor=1.8,
                delta0=0.01, target_frac=0.4, tag_limit=0x0F000000, local_bound=False, kappa=None, boom=None, logistic=None,
-               strong=None, async_tiles=0, order_seed=1, reversible=False, strong_upperbounds=False, refresh=None):
+               strong=None, async_tiles=0, order_seed=1, reversible=False, strong_upperbounds=False, refresh=None, stickyzz=False):
     """``strong = rule`` ("sticky" / "reversible"): the strong-bound sparse sticky timeline (zz_strong.h) with scalar ``c`` and
     ``kappa``, target = ``bound``; contract: :func:`sparsestickyzz` with ``ctr=True``."""
     L = wlib()
@@ -338,7 +339,7 @@ def window_sim(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1,
         r = L.zzw_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
                         _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
                         float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor),
-                        float(delta0), float(target_frac), int(tag_limit), int(bool(local_bound)) | (2 if reversible else 0) | (4 if strong_upperbounds else 0),
+                        float(delta0), float(target_frac), int(tag_limit), int(bool(local_bound)) | (2 if reversible else 0) | (4 if strong_upperbounds else 0) | (8 if stickyzz else 0),
                         _p(None if kappa is None else f8(kappa)),
                         _p(None if boom is None else f8(boom[0])), 0.0 if boom is None else float(boom[1]), 0.0 if boom is None else float(boom[2]))
     try:

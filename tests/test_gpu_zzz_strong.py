@@ -108,3 +108,26 @@ def test_sspdmp4_asynchzz_process_bit_exact(gpu):
     X3, _, _ = gpu.sspdmp3(gpu.GaussianPotential(G), (x0, th0), 30.0, 6.0, None, gpu.ZigZag(G, np.zeros(300)), 0.5, rule="sticky", seed=(1, 2))
     X4, _ = gpu.sspdmp4(None, gpu.GaussianPotential(G), 0.0, x0, th0, 30.0, 6.0, None, gpu.ZigZag(G, np.zeros(300)), 0.5, seed=(1, 2))
     assert np.array_equal(X3.events, X4.events)
+
+
+@pytest.mark.parametrize("strong", [False, True])
+def test_sspdmp2_dense_sticky_on_device(gpu, strong):
+    """`sspdmp2` / stickyzz (src/stickyzz.jl:322-338) on the device: the sticky kernels with ZZB_FLAG_STICKY_ZZ (rate floor 0.01,
+    coordinates at 0 start frozen), lattice and general sparse graph, bit for bit against the oracle (ZZO_STICKYZZ)."""
+    import oracle_lib as O
+    rng = np.random.default_rng(21)
+    for G in (gpu.grid_precision(14, 11, shift=0.5), gpu.random_sparse_spd(150, deg=2, seed=2)):   # (columns of at most 8 entries: the cap of the sticky kernels)
+        d = G.n
+        x0 = np.where(rng.random(d) < 0.6, rng.standard_normal(d), 0.0)
+        th0 = rng.choice(np.array([-1.5, -1.0, 1.0, 0.5]), d)
+        c, kap = 6.0 * G.colnorms(), rng.choice(np.array([0.3, 0.8, 2.0]), d)
+        mode = O.PARITY_MODE | O.STICKYZZ | (O.STICKY_STRONG_UB if strong else 0)
+        ref = O.spdmp(G, G, 0.0, x0, th0, 8.0, c, kappa=kap, mode=mode)
+        Xi, (acc, num) = gpu.sspdmp2(gpu.GaussianPotential(G), 0.0, x0, th0, 8.0, c, None, gpu.ZigZag(G, np.zeros(d)), kap,
+                                     strong_upperbounds=strong, seed=(1, 2))
+        assert num == ref.num and np.array_equal(Xi.acc_per_coordinate, ref.acc)
+        assert len(Xi.events) == len(ref.events) and np.array_equal(Xi.events["i"], ref.events["i"])
+        for f in ("t", "x", "theta"):
+            assert np.array_equal(Xi.events[f].view(np.uint64), ref.events[f].view(np.uint64)), f
+        t, x, th = Xi.final
+        assert np.array_equal(x.view(np.uint64), ref.x.view(np.uint64)) and np.array_equal(th.view(np.uint64), ref.theta.view(np.uint64))

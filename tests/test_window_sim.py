@@ -212,6 +212,34 @@ def test_sticky_options_reversible_and_strong_upperbounds(zzb, reversible, stron
         O.assert_same_run(ref, got)
 
 
+@pytest.mark.parametrize("strong", [False, True])
+def test_dense_sticky_sampler_stickyzz(zzb, strong):
+    """stickyzz / sspdmp2 (src/stickyzz.jl:176-338): the sspdmp loop with proposal times at rate 0.01 + (a + b t)^+ and coordinates
+    that start at 0 starting frozen -- the device's sticky timeline with ZZ_STICKY_ZZ against the oracle (ZZO_STICKYZZ), under both
+    schedules of the emulation; the floor and the frozen start both change the run."""
+    G = zzb.grid_precision(8, 7, shift=0.5)
+    rng = np.random.default_rng(9)
+    d = G.n
+    x0 = np.where(rng.random(d) < 0.6, rng.standard_normal(d), 0.0)
+    th0 = rng.choice(np.array([-1.5, -1.0, 1.0, 0.5]), d)
+    c, kap = 6.0 * G.colnorms(), rng.choice(np.array([0.3, 0.8, 2.0]), d)
+    mode = O.PARITY_MODE | O.STICKYZZ | (O.STICKY_STRONG_UB if strong else 0)
+    ref = O.spdmp(G, G, 0.0, x0, th0, 8.0, c, kappa=kap, mode=mode)
+    assert len(ref.events) > 200
+    started = {int(i) for i in ref.events["i"][ref.events["t"] < 1e-9]}
+    first = {}
+    for t, i, x, th in ref.events:
+        first.setdefault(int(i), (t, x, th))
+    frozen0 = [j + 1 for j in range(d) if x0[j] == 0.0 and (j + 1) in first]
+    assert frozen0 and all(first[i][1] == 0.0 and first[i][2] == th0[i - 1] for i in frozen0)   # first event = thaw at 0 with the kept velocity
+    xs = np.where(x0 == 0.0, 1e-300, x0)   # (no coordinate AT 0: the plain sspdmp start, for comparison)
+    plain = O.spdmp(G, G, 0.0, xs, th0, 8.0, c, kappa=kap, mode=O.PARITY_MODE | (O.STICKY_STRONG_UB if strong else 0))
+    assert not np.array_equal(ref.events["t"][:50], plain.events["t"][:50])
+    for tiles in (0, 5):
+        got = O.window_sim(G, G, 0.0, x0, th0, 8.0, c, kappa=kap, strong_upperbounds=strong, stickyzz=True, async_tiles=tiles)
+        O.assert_same_run(ref, got)
+
+
 @pytest.mark.parametrize("lattice,tiles", [(True, 0), (True, 5), (False, 0), (False, 4)])
 def test_zigzag_refreshments(zzb, lattice, tiles):
     """ZigZag with velocity refreshments (Z.lambdaref > 0: src/sfact.jl:78-114,188-190): the device timeline

@@ -19,6 +19,7 @@ ZZB_FLAG_STICKY = 4
 ZZB_FLAG_BOOMERANG = 8
 ZZB_FLAG_STICKY_REVERSIBLE = 16
 ZZB_FLAG_STICKY_STRONG_UB = 32
+ZZB_FLAG_STICKY_ZZ = 128
 ZZB_FLAG_REFRESH = 64
 
 EVENT_DTYPE = np.dtype([("t", "<f8"), ("i", "<i8"), ("x", "<f8"), ("theta", "<f8")])  # src/trace.jl:38

@@ -316,7 +316,7 @@ class Run:
     """One sampler run on the device (staged form of the C-ABI)."""
 
     def __init__(self, problem: Problem, *, record_trace: bool = True, trace_capacity: int = 0, local_bound: bool = False,
-                 kappa=None, boomerang=None, reversible: bool = False, strong_upperbounds: bool = False, refresh=None):
+                 kappa=None, boomerang=None, reversible: bool = False, strong_upperbounds: bool = False, refresh=None, stickyzz: bool = False):
         self.problem = problem
         self.d = problem.d
         self._h = C.c_void_p()
@@ -324,6 +324,7 @@ class Run:
             | (_capi.ZZB_FLAG_STICKY if kappa is not None else 0) | (_capi.ZZB_FLAG_BOOMERANG if boomerang is not None else 0) \
             | (_capi.ZZB_FLAG_STICKY_REVERSIBLE if (kappa is not None and reversible) else 0) \
             | (_capi.ZZB_FLAG_STICKY_STRONG_UB if (kappa is not None and strong_upperbounds) else 0) \
+            | (_capi.ZZB_FLAG_STICKY_ZZ if (kappa is not None and stickyzz) else 0) \
             | (_capi.ZZB_FLAG_REFRESH if refresh is not None else 0)
         self.record_trace = record_trace
         check(_capi.lib().zzb_run_create(problem._h, flags, int(trace_capacity), C.byref(self._h)))
@@ -636,6 +637,43 @@ def sspdmp3(grad, u0, T, c, G, Z, kappa, *args, rule="reversible", adapt=False, 
         Xi.device_ms = run.device_ms
         Xi.acc_per_coordinate = acc
         return Xi, (int(acc.sum()), num), (t, x, th)
+    finally:
+        run.close()
+        if own:
+            prob.close()
+
+
+def sspdmp2(grad, t0, x0, v0, T, c, G, Z, kappa, *args, strong_upperbounds=False, adapt=False, factor=1.5, seed=None, record_trace=True,
+            tune=None):
+    """``sspdmp2(grad, t, x0, v0, T, c, nothing, Z, kappa, args...; strong_upperbounds=false, adapt=false, factor=1.5)`` =
+    ``trace, acc`` (src/stickyzz.jl:322-338): the dense sticky ZigZag ``stickyzz`` -- the loop of ``sspdmp`` (affine bounds, a
+    reflection reschedules its neighbourhood, coordinates stick at 0 and thaw at rate ``kappa[i]`` with the velocity they had)
+    with proposal times drawn at rate ``0.01 + (a + b t)^+`` (``queue_time!``, :144-165) and coordinates that start at 0 starting
+    frozen (:198-206).  Returns ``trace, (acc, num)``; ``trace.final`` holds ``(t, x, theta)``.  Not on the device path: ``adapt``."""
+    if adapt:
+        raise NotImplementedError("sspdmp2(...; adapt=true) is not implemented on the device path")
+    if not isinstance(Z, ZigZag):
+        raise TypeError("sspdmp2: Z must be a ZigZag (src/stickyzz.jl:323-331)")
+    prob, own = _as_problem(grad, Z)
+    if seed is None:
+        seed = (secrets.randbits(64), secrets.randbits(64))
+    d = prob.d
+    kv = np.full(d, float(kappa)) if np.isscalar(kappa) else f8(kappa)
+    run = Run(prob, record_trace=record_trace, kappa=kv, strong_upperbounds=strong_upperbounds, stickyzz=True)
+    try:
+        if tune:
+            run.set(**tune)
+        run.upload(t0, x0, v0, c, seed=seed)
+        run.execute(T)
+        t, x, th, _ = run.final_state()
+        acc, num = run.counts()
+        ev = run.events() if record_trace else np.empty(0, dtype=EVENT_DTYPE)
+        Xi = FactTrace(Z, t0, f8(x0), np.where(f8(x0) != 0.0, f8(v0), 0.0), ev)
+        Xi.stats = run.stats()
+        Xi.device_ms = run.device_ms
+        Xi.acc_per_coordinate = acc
+        Xi.final = (t, x, th)
+        return Xi, (int(acc.sum()), num)
     finally:
         run.close()
         if own:

@@ -31,6 +31,8 @@
 #define ZZ_F_STICKY_ERR 4u  // a freezing coordinate was not at 0 (ss_fact.jl:89-91)
 #define ZZ_STICKY_REVERSIBLE 2   // bits of ZzView::sticky (bit 0: sticky sampler): sspdmp options reversible / strong_upperbounds
 #define ZZ_STICKY_STRONG_UB 4
+#define ZZ_STICKY_ZZ 8            // the dense sticky sampler stickyzz / sspdmp2 (src/stickyzz.jl): proposal times at rate 0.01 + (a + b t)^+,
+                                 // coordinates that start at 0 start frozen
 #define ZZ_RENEW_BIT 0x80000000u  // in the draw counter: the queued time is a bound expiry, not a proposal (local.jl:34)
 
 // Kinematic record of one coordinate, read by its neighbours: 32 B = one DRAM/L2 sector.
@@ -401,15 +403,21 @@ ZZ_HD void zz_init_node(const ZzGraph& g, const ZzView& v, int32_t j, double t0)
     double gt, gx, gp, gm;
     zz_eval(g, v, j, t0, j, xf + th * (t0 - tf), th, 1u, 1u, gt, gx, gp, gm);
     ZzPriv pr;
-    pr.c = zz_ld_priv(v.priv + j).c;
+    const ZzPriv pr0 = zz_ld_priv(v.priv + j);
+    pr.c = pr0.c;
     const bool lbm = v.local_bound != 0;
+    const bool zzmode = v.sticky && (v.sticky & ZZ_STICKY_ZZ);   // stickyzz / sspdmp2
     pr.a = pr.c + (lbm ? gt : gx - g.gmu[j]) * th;
     pr.b = pr.c / 100 + th * gp;
     pr.told = t0;
+    if (zzmode && th == 0.0) pr.a = pr0.a;   // starts frozen: zz_setup_kernel has left the velocity to continue with in the `a` slot
     v.priv[j] = pr;
-    const double dt = zz_poisson_time(pr.a, pr.b, zz_u01(v.seed0, v.seed1, (uint64_t)j, 0));
+    const double u0 = zz_u01(v.seed0, v.seed1, (uint64_t)j, 0);
+    const double dt = zzmode ? zz_poisson_time3(pr.a, pr.b, 0.01, u0) : zz_poisson_time(pr.a, pr.b, u0);   // (floor: poissontime.jl:93-99)
     bool renew = false;
-    if (v.sticky) {   // ss_fact.jl:178-188: the earlier of the first proposal and the hitting time of 0, from t0
+    if (zzmode && th == 0.0) {   // stickyzz.jl:198-206: thaw clock only
+        v.tau[j] = t0 - zz_log(u0) / v.kappa[j];
+    } else if (v.sticky) {   // ss_fact.jl:178-188: the earlier of the first proposal and the hitting time of 0, from t0
         const double x0 = xf + th * (t0 - tf);
         const double tfreez = (th * x0 >= 0.0) ? ZZ_INF : -x0 / th;
         renew = dt > tfreez;

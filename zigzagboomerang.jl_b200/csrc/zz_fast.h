@@ -407,7 +407,8 @@ ZZ_HD void zz_timeline_sticky(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w
         b = c100 + th * gth;                         // fact_samplers.jl:52
         told = s;
         // queue_time! (:54-66): the earlier of the proposed reflection and the hitting time of 0
-        const double trefl = zz_poisson_time(a, b, zz_u01(v.seed0, v.seed1, (uint64_t)j, k++));
+        const double ur = zz_u01(v.seed0, v.seed1, (uint64_t)j, k++);
+        const double trefl = (v.sticky & ZZ_STICKY_ZZ) ? zz_poisson_time3(a, b, 0.01, ur) : zz_poisson_time(a, b, ur);   // stickyzz.jl:144-147
         const double tfreeze = zz_freezing_time(xnow, th);
         if (tfreeze <= trefl) { fbit = true; tau = s + tfreeze; }
         else { fbit = false; tau = s + trefl; }

@@ -568,6 +568,8 @@ zz_setup_kernel(const ZzParams P, const double* __restrict__ x0, const double* _
         // strong-bound sampler, rule 2 (asynchzz, src/asynchzz.jl:112-116): a coordinate that starts at 0 starts frozen and
         // remembers the velocity it will continue with
         if (P.st.c > 0.0 && P.st.rule == 2 && k.xf == 0.0) { p.told = k.theta; k.theta = 0.0; }
+        // stickyzz / sspdmp2 (src/stickyzz.jl:198-206): the same, the velocity travels in the `a` slot like that of every frozen coordinate
+        if (P.v.sticky && (P.v.sticky & ZZ_STICKY_ZZ) && k.xf == 0.0) { p.a = k.theta; k.theta = 0.0; }
         P.v.kin[j] = k;
         P.v.priv[j] = p;
         P.dstamp[j] = 0; P.acc[j] = 0; P.s1[j] = 0.0; P.s2[j] = 0.0;

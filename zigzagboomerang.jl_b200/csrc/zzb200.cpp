@@ -606,7 +606,8 @@ static void fill_params(zzb_run_s* r)
     P.grid = r->grid_n ? r->gridbuf.as<double>() : nullptr; P.grid_dt = r->grid_dt; P.grid_n = r->grid_n;
     P.v.local_bound = (r->flags & ZZB_FLAG_LOCAL_BOUND) ? 1 : 0;
     P.v.sticky = (r->flags & ZZB_FLAG_STICKY) ? (1 | ((r->flags & ZZB_FLAG_STICKY_REVERSIBLE) ? ZZ_STICKY_REVERSIBLE : 0) |
-                                                 ((r->flags & ZZB_FLAG_STICKY_STRONG_UB) ? ZZ_STICKY_STRONG_UB : 0)) : 0;
+                                                 ((r->flags & ZZB_FLAG_STICKY_STRONG_UB) ? ZZ_STICKY_STRONG_UB : 0) |
+                                                 ((r->flags & ZZB_FLAG_STICKY_ZZ) ? ZZ_STICKY_ZZ : 0)) : 0;
     P.v.boom = (r->flags & ZZB_FLAG_BOOMERANG) ? 1 : 0;
     P.v.refresh = (r->flags & ZZB_FLAG_REFRESH) ? 1 : 0;
     P.v.fth = (P.v.sticky || P.v.boom || P.v.refresh) ? r->dfth.as<double>() : nullptr;

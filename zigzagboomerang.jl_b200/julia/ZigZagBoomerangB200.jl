@@ -12,7 +12,7 @@ module ZigZagBoomerangB200
 using ZigZagBoomerang
 using ZigZagBoomerang: ZigZag, FactBoomerang, LocalBound, FactTrace, Trace, Seed
 using SparseArrays
-import ZigZagBoomerang: spdmp, pdmp, sspdmp, sspdmp3, sspdmp4
+import ZigZagBoomerang: spdmp, pdmp, sspdmp, sspdmp2, sspdmp3, sspdmp4
 
 const libzzb200 = get(ENV, "ZZB200_LIB", joinpath(@__DIR__, "..", "libzzb200.so"))
 const cubin = get(ENV, "ZZB200_CUBIN", joinpath(@__DIR__, "..", "zzb200_kernels.cubin"))
@@ -20,6 +20,9 @@ const cubin = get(ENV, "ZZB200_CUBIN", joinpath(@__DIR__, "..", "zzb200_kernels.
 const ZZB_E_BOUND = Int32(3)
 const ZZB_FLAG_NO_TRACE = UInt32(1)
 const ZZB_FLAG_LOCAL_BOUND = UInt32(2)
+const ZZB_FLAG_STICKY_REVERSIBLE = UInt32(16)
+const ZZB_FLAG_STICKY_STRONG_UB = UInt32(32)
+const ZZB_FLAG_STICKY_ZZ = UInt32(128)
 
 """
     GaussianPotential(Γ, h = nothing)
@@ -225,9 +228,21 @@ pdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, C::LocalBound, F::FactBoomerang, 
 # sspdmp(∇ϕ, t0, x0, θ0, T, c, [G,] F::ZigZag, κ, ...) (src/ss_fact.jl:159-217); acc is the scalar count of reflections
 function sspdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G, F::ZigZag, κ, args...;
                 strong_upperbounds = false, factor = 1.5, adapt = false, reversible = false, seed = Seed())
-    (strong_upperbounds || adapt || reversible) && error("sspdmp options strong_upperbounds / adapt / reversible are not implemented on the device path")
-    Ξ, u, (acc, num), cv = device_run(:sticky, ∇ϕ, t0, x0, θ0, T, c, F; κ = κ, seed = seed)
+    adapt && error("sspdmp(...; adapt = true) is not implemented on the device path")
+    flags = (reversible ? ZZB_FLAG_STICKY_REVERSIBLE : UInt32(0)) | (strong_upperbounds ? ZZB_FLAG_STICKY_STRONG_UB : UInt32(0))
+    Ξ, u, (acc, num), cv = device_run(:sticky, ∇ϕ, t0, x0, θ0, T, c, F; κ = κ, seed = seed, flags = flags)
     Ξ, u, (sum(acc), num), c
+end
+
+# sspdmp2(∇ϕ, t, x0, v0, T, c, nothing, Z, κ; strong_upperbounds, adapt, factor) (src/stickyzz.jl:322-338): the dense sticky ZigZag
+# `stickyzz` = the loop of sspdmp with proposal times at rate 0.01 + (a + b t)^+ and coordinates that start at 0 starting frozen.
+# Returns trace, (acc, num) -- the reference returns (trace, acc::AcceptanceDiagnostics).
+function sspdmp2(∇ϕ::GaussianPotential, t, x0, v0, T, c, ::Nothing, Z::ZigZag, κ, args...; strong_upperbounds = false, progress = false,
+                 adapt = false, factor = 1.5, seed = Seed())
+    adapt && error("sspdmp2(...; adapt = true) is not implemented on the device path")
+    flags = ZZB_FLAG_STICKY_ZZ | (strong_upperbounds ? ZZB_FLAG_STICKY_STRONG_UB : UInt32(0))
+    Ξ, u, (acc, num), cv = device_run(:sticky, ∇ϕ, t, x0, v0, T, c, Z; κ = κ, seed = seed, flags = flags)
+    Ξ, (sum(acc), num)
 end
 sspdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F::ZigZag, κ, args...; kargs...) = sspdmp(∇ϕ, t0, x0, θ0, T, c, nothing, F, κ, args...; kargs...)
 
