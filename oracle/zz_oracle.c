@@ -639,11 +639,36 @@ static void s_move_nbhd(ctx *z, const int64_t *idx, int64_t n, double tp)
     }
 }
 
+/* sspdmp(...; adapt = true, factor) (ss_fact.jl:132-136): an accepted proposal with l > lb multiplies c[i] by `factor` instead of
+ * raising the error.  The reference also resets its two diagnostic counters (acc = num = 0, :134) at that moment, so what it
+ * returns counts the proposals since the LAST adaptation in global event order; the contract returns the totals (the dynamics do
+ * not depend on the counters). */
+static zzo_run *sspdmp_impl(int64_t d,
+                    const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
+                    const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
+                    double t0, const double *x0, const double *th0, double T, const double *c_in, const double *kappa,
+                    const uint64_t *seed, int mode, int adapt, double factor);
 zzo_run *zzo_sspdmp(int64_t d,
                     const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
                     const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
                     double t0, const double *x0, const double *th0, double T, const double *c_in, const double *kappa,
                     const uint64_t *seed, int mode)
+{
+    return sspdmp_impl(d, tg_colptr, tg_rowval, tg_nzval, h, bd_colptr, bd_rowval, bd_nzval, mu, t0, x0, th0, T, c_in, kappa, seed, mode, 0, 1.0);
+}
+zzo_run *zzo_sspdmp_adapt(int64_t d,
+                    const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
+                    const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
+                    double t0, const double *x0, const double *th0, double T, const double *c_in, const double *kappa,
+                    const uint64_t *seed, int mode, int adapt, double factor)
+{
+    return sspdmp_impl(d, tg_colptr, tg_rowval, tg_nzval, h, bd_colptr, bd_rowval, bd_nzval, mu, t0, x0, th0, T, c_in, kappa, seed, mode, adapt, factor);
+}
+static zzo_run *sspdmp_impl(int64_t d,
+                    const int64_t *tg_colptr, const int64_t *tg_rowval, const double *tg_nzval, const double *h,
+                    const int64_t *bd_colptr, const int64_t *bd_rowval, const double *bd_nzval, const double *mu,
+                    double t0, const double *x0, const double *th0, double T, const double *c_in, const double *kappa,
+                    const uint64_t *seed, int mode, int adapt, double factor)
 {
     zzo_run *r = (zzo_run *)calloc(1, sizeof(zzo_run));
     ctx zs; ctx *z = &zs; memset(z, 0, sizeof(ctx));
@@ -741,7 +766,10 @@ zzo_run *zzo_sspdmp(int64_t d,
                 num += 1;
                 if (draw(z, i) * lb < l) {
                     r->acc[i - 1] += 1;
-                    if (l > lb) { r->status = ZZO_E_BOUND; r->err_i = i; r->err_t = tp; r->err_l = l; r->err_lb = lb; break; }
+                    if (l > lb) {                                           /* :132-136 */
+                        if (!adapt) { r->status = ZZO_E_BOUND; r->err_i = i; r->err_t = tp; r->err_l = l; r->err_lb = lb; break; }
+                        z->c[i - 1] *= factor;
+                    }
                     if (!lazy) s_move_nbhd(z, g2, ng2, tp);
                     if (lazy) { z->xf[i - 1] = pos_at(z, i, tp); z->tf[i - 1] = tp; }
                     z->th[i - 1] = -z->th[i - 1];

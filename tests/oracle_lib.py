@@ -149,9 +149,11 @@ def spdmp(target, bound, t0, x0, theta0, T, c, *, h=None, mu=None, seed=(1, 2), 
                              float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(sd), int(adapt), float(factor), int(mode))
     elif kappa is not None:
         kappa = f8(kappa)
-        r = L.zzo_sspdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
+        L.zzo_sspdmp_adapt.restype = C.c_void_p
+        L.zzo_sspdmp_adapt.argtypes = L.zzo_sspdmp.argtypes + [C.c_int, C.c_double]
+        r = L.zzo_sspdmp_adapt(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
                          _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),
-                         float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(kappa), _p(sd), int(mode))
+                         float(t0), _p(x0), _p(theta0), float(T), _p(c), _p(kappa), _p(sd), int(mode), int(adapt), float(factor))
     else:
         r = L.zzo_spdmp(d, _p(target.colptr), _p(target.rowval), _p(target.nzval), _p(h),
                         _p(bound.colptr), _p(bound.rowval), _p(bound.nzval), _p(mu),

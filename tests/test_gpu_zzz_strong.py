@@ -131,3 +131,28 @@ def test_sspdmp2_dense_sticky_on_device(gpu, strong):
             assert np.array_equal(Xi.events[f].view(np.uint64), ref.events[f].view(np.uint64)), f
         t, x, th = Xi.final
         assert np.array_equal(x.view(np.uint64), ref.x.view(np.uint64)) and np.array_equal(th.view(np.uint64), ref.theta.view(np.uint64))
+
+
+def test_sticky_adapt_on_device(gpu):
+    """sspdmp / sspdmp2 with adapt = true (src/ss_fact.jl:132-136, src/stickyzz.jl:305-309): c[i] grows by `factor` at an accepted
+    proposal with l > lb; bit for bit against the oracle, adapted bounds included."""
+    import oracle_lib as O
+    G = gpu.grid_precision(12, 13, shift=0.5)
+    Gb = G.scaled(0.5)
+    rng = np.random.default_rng(12)
+    d = G.n
+    x0, th0 = rng.standard_normal(d), rng.choice(np.array([-1.0, 1.0]), d)
+    c, kap = 0.05 * G.colnorms(), np.full(d, 0.8)
+    for stickyzz in (False, True):
+        ref = O.spdmp(G, Gb, 0.0, x0, th0, 8.0, c, kappa=kap, mode=O.PARITY_MODE | (O.STICKYZZ if stickyzz else 0), adapt=True, factor=1.5)
+        if stickyzz:
+            Xi, (acc, num) = gpu.sspdmp2(gpu.GaussianPotential(G), 0.0, x0, th0, 8.0, c, None, gpu.ZigZag(Gb, np.zeros(d)), kap, adapt=True, factor=1.5, seed=(1, 2))
+            cc = Xi.c
+        else:
+            Xi, _, (acc, num), cc = gpu.sspdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 8.0, c, gpu.ZigZag(Gb, np.zeros(d)), kap, adapt=True, factor=1.5, seed=(1, 2))
+        assert (ref.c != c).sum() > 5 and np.array_equal(cc.view(np.uint64), ref.c.view(np.uint64))
+        assert num == ref.num and acc == int(ref.acc.sum()) and len(Xi.events) == len(ref.events)
+        for f in ("t", "x", "theta"):
+            assert np.array_equal(Xi.events[f].view(np.uint64), ref.events[f].view(np.uint64)), f
+    with pytest.raises(gpu.BoundError):
+        gpu.sspdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 8.0, c, gpu.ZigZag(Gb, np.zeros(d)), kap, seed=(1, 2))

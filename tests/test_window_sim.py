@@ -212,6 +212,25 @@ def test_sticky_options_reversible_and_strong_upperbounds(zzb, reversible, stron
         O.assert_same_run(ref, got)
 
 
+@pytest.mark.parametrize("stickyzz", [False, True])
+def test_sticky_adaptation_of_the_bounds(zzb, stickyzz):
+    """sspdmp / sspdmp2 (...; adapt = true, factor) (src/ss_fact.jl:132-136, src/stickyzz.jl:305-309): too small a c is multiplied by
+    `factor` when a proposal is accepted with l > lb; device timeline against the oracle under both schedules."""
+    G = zzb.grid_precision(7, 8, shift=0.5)
+    rng = np.random.default_rng(12)
+    d = G.n
+    x0, th0 = rng.standard_normal(d), rng.choice(np.array([-1.0, 1.0]), d)
+    c, kap = 0.05 * G.colnorms(), np.full(d, 0.8)
+    mode = O.PARITY_MODE | (O.STICKYZZ if stickyzz else 0)
+    with pytest.raises(O.BoundError):
+        O.spdmp(G, G.scaled(0.5), 0.0, x0, th0, 8.0, c, kappa=kap, mode=mode)
+    ref = O.spdmp(G, G.scaled(0.5), 0.0, x0, th0, 8.0, c, kappa=kap, mode=mode, adapt=True, factor=1.5)
+    assert (ref.c != c).sum() > 5 and len(ref.events) > 200
+    for tiles in (0, 4):
+        got = O.window_sim(G, G.scaled(0.5), 0.0, x0, th0, 8.0, c, kappa=kap, stickyzz=stickyzz, adapt=True, factor=1.5, async_tiles=tiles)
+        O.assert_same_run(ref, got)
+
+
 @pytest.mark.parametrize("strong", [False, True])
 def test_dense_sticky_sampler_stickyzz(zzb, strong):
     """stickyzz / sspdmp2 (src/stickyzz.jl:176-338): the sspdmp loop with proposal times at rate 0.01 + (a + b t)^+ and coordinates

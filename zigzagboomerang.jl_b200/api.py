@@ -564,16 +564,13 @@ def pdmp(grad, t0, x0, theta0, T, c, F, *args, **kw):
 
 
 def sspdmp(grad, t0, x0, theta0, T, c, *rest, seed=None, record_trace=True, tune=None, reversible=False, strong_upperbounds=False,
-           **unsupported):
+           adapt=False, factor=1.5, **unsupported):
     """``sspdmp(grad, t0, x0, theta0, T, c, [G,] F::ZigZag, kappa, args...; reversible=false, strong_upperbounds=false)`` =
     ``Xi, (t, x, theta), (acc, num), c`` (src/ss_fact.jl:159-217): sticky ZigZag -- coordinates freeze when they hit 0 and thaw
     after an Exp(kappa_i) time.  ``reversible``: a thawing coordinate re-enters with a random sign (:111-113);
     ``strong_upperbounds``: a freeze reschedules nobody (:97-107).  `acc` is the number of accepted reflections (a scalar, like
-    the reference).  ``adapt=true`` is not available on the device path (the reference then also RESETS acc and num at every
-    adaptation, :133-135) and raises."""
-    for k, v in unsupported.items():
-        if v not in (False, None) and k in ("adapt",):
-            raise NotImplementedError(f"sspdmp(...; {k}=true) is not implemented on the device path")
+    the reference).  ``adapt=true``: an accepted proposal with ``l > lb`` multiplies ``c[i]`` by ``factor`` instead of raising
+    (:132-136); the reference then also RESETS its diagnostic counters acc and num (:134) -- the device returns the totals."""
     rest = list(rest)
     if rest and (rest[0] is None or isinstance(rest[0], (All, Matched))):
         rest.pop(0)
@@ -588,7 +585,7 @@ def sspdmp(grad, t0, x0, theta0, T, c, *rest, seed=None, record_trace=True, tune
     try:
         if tune:
             run.set(**tune)
-        run.upload(t0, x0, theta0, c, seed=seed)
+        run.upload(t0, x0, theta0, c, seed=seed, adapt=bool(adapt), factor=float(factor))
         run.execute(T)
         t, x, th, cc = run.final_state()
         acc, num = run.counts()
@@ -644,14 +641,13 @@ def sspdmp3(grad, u0, T, c, G, Z, kappa, *args, rule="reversible", adapt=False, 
 
 
 def sspdmp2(grad, t0, x0, v0, T, c, G, Z, kappa, *args, strong_upperbounds=False, adapt=False, factor=1.5, seed=None, record_trace=True,
-            tune=None):
+            tune=None):  # noqa: D401
     """``sspdmp2(grad, t, x0, v0, T, c, nothing, Z, kappa, args...; strong_upperbounds=false, adapt=false, factor=1.5)`` =
     ``trace, acc`` (src/stickyzz.jl:322-338): the dense sticky ZigZag ``stickyzz`` -- the loop of ``sspdmp`` (affine bounds, a
     reflection reschedules its neighbourhood, coordinates stick at 0 and thaw at rate ``kappa[i]`` with the velocity they had)
     with proposal times drawn at rate ``0.01 + (a + b t)^+`` (``queue_time!``, :144-165) and coordinates that start at 0 starting
-    frozen (:198-206).  Returns ``trace, (acc, num)``; ``trace.final`` holds ``(t, x, theta)``.  Not on the device path: ``adapt``."""
-    if adapt:
-        raise NotImplementedError("sspdmp2(...; adapt=true) is not implemented on the device path")
+    frozen (:198-206).  ``adapt=true`` multiplies ``c[i]`` by ``factor`` when a proposal is accepted with ``l > lb`` (:305-309).
+    Returns ``trace, (acc, num)``; ``trace.final`` holds ``(t, x, theta)``, ``trace.c`` the (adapted) bounds."""
     if not isinstance(Z, ZigZag):
         raise TypeError("sspdmp2: Z must be a ZigZag (src/stickyzz.jl:323-331)")
     prob, own = _as_problem(grad, Z)
@@ -663,9 +659,9 @@ def sspdmp2(grad, t0, x0, v0, T, c, G, Z, kappa, *args, strong_upperbounds=False
     try:
         if tune:
             run.set(**tune)
-        run.upload(t0, x0, v0, c, seed=seed)
+        run.upload(t0, x0, v0, c, seed=seed, adapt=bool(adapt), factor=float(factor))
         run.execute(T)
-        t, x, th, _ = run.final_state()
+        t, x, th, cc = run.final_state()
         acc, num = run.counts()
         ev = run.events() if record_trace else np.empty(0, dtype=EVENT_DTYPE)
         Xi = FactTrace(Z, t0, f8(x0), np.where(f8(x0) != 0.0, f8(v0), 0.0), ev)
@@ -673,6 +669,7 @@ def sspdmp2(grad, t0, x0, v0, T, c, G, Z, kappa, *args, strong_upperbounds=False
         Xi.device_ms = run.device_ms
         Xi.acc_per_coordinate = acc
         Xi.final = (t, x, th)
+        Xi.c = cc
         return Xi, (int(acc.sum()), num)
     finally:
         run.close()

@@ -323,7 +323,7 @@ ZZ_HD void zz_timeline_sticky(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w
 {
     double th = w.th, tf = w.tf, xf = w.xf;
     double a = w.a, b = w.b, told = w.told, c = w.c;
-    const double c100 = c / 100;
+    double c100 = c / 100;
     double tau = w.tau;
     bool fbit = (w.k & ZZ_RENEW_BIT) != 0;
     uint32_t k = w.k & ~ZZ_RENEW_BIT;
@@ -394,7 +394,10 @@ ZZ_HD void zz_timeline_sticky(ZzHood<NB>& hd, const ZzPool& pool, const ZzOwn& w
             const double u1 = zz_u01(v.seed0, v.seed1, (uint64_t)j, k++);
             nprop++;
             if (u1 * lb < l) {                       // :130
-                if (l > lb && !(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }  // :132-133
+                if (l > lb) {                        // :132-136
+                    if (v.adapt) { c *= v.factor; c100 = c / 100; }
+                    else if (!(flags & ZZ_F_VIOL)) { flags |= ZZ_F_VIOL; o.viol_t = s; o.viol_l = l; o.viol_lb = lb; }
+                }
                 if (nev == ZZ_MAXFLIP) { flags |= ZZ_F_OVERFLOW; break; }
 #pragma unroll
                 for (int m = 0; m < ZZ_MAXFLIP; ++m) if (m == (int)nev) { o.fl[m] = s; o.fth[m] = -th; }

@@ -787,7 +787,7 @@ int32_t zzb_run_reset(zzb_run_t r)
     if ((r->flags & ZZB_FLAG_BOOMERANG) && !r->have_boom) return fail(ZZB_E_ARG, "zzb_run_upload_boomerang must precede zzb_run_upload for a Boomerang run");
     if ((r->flags & ZZB_FLAG_REFRESH) && !r->have_refresh) return fail(ZZB_E_ARG, "zzb_run_upload_refresh must precede zzb_run_upload for a run with ZZB_FLAG_REFRESH");
     if ((r->flags & ZZB_FLAG_REFRESH) && r->nranks > 1) return fail(ZZB_E_ARG, "ZigZag refreshments are not sharded yet");
-    if ((r->flags & ZZB_FLAG_STICKY) && r->adapt) return fail(ZZB_E_ARG, "adapt is not supported by the sticky sampler on the device path");
+    if (r->strong && r->adapt) return fail(ZZB_E_ARG, "adapt is not supported by the strong-bound sticky samplers on the device path");
     for (int q = 0; q < r->nranks; ++q)
         if (q != r->rank && !r->peer_open[q]) return fail(ZZB_E_ARG, "peer %d of a sharded run has not been imported", q);
     fill_params(r);
