@@ -126,6 +126,12 @@ int32_t zzb_spdmp_boomerang_run(zzb_problem_t p, double t0, const double* x0, co
                                 const double* sigma, double lambdaref, double rho, const uint64_t* seed, int32_t adapt,
                                 double factor, uint32_t flags, zzb_run_t* out);
 
+/* sspdmp(...; adapt = true, factor = 1.5) (src/ss_fact.jl:132-136,159): as zzb_sspdmp_run, but an accepted proposal with l > lb
+ * multiplies c[i] by factor instead of ending the run with ZZB_E_BOUND; c is in/out (the adapted bounds).  The reference also resets
+ * its diagnostic counters (acc, num) at every adaptation (:134); zzb_run_counts returns the totals. */
+int32_t zzb_sspdmp_adapt_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, double* c,
+                             const double* kappa, const uint64_t* seed, int32_t adapt, double factor, uint32_t flags, zzb_run_t* out);
+
 /* sspdmp3 / sparsestickyzz (src/sparsestickyzz.jl:405-422,192-257): the strong-bound sparse sticky ZigZag of BASELINE config 4.
  * One bound constant c (SparseStickyUpperBounds :127-142, adapt = false), one thaw rate kappa (StickyBarriers), rule 0 = :sticky,
  * 1 = :reversible.  Coordinates with x0 == 0 start frozen (sparsestickystate :10-12); theta0 = velocities of the others; time

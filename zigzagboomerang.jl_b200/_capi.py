@@ -27,7 +27,7 @@ EVENT_DTYPE = np.dtype([("t", "<f8"), ("i", "<i8"), ("x", "<f8"), ("theta", "<f8
 # every symbol include/zzb200.h declares
 SYMBOLS = [
     "zzb_init", "zzb_shutdown", "zzb_last_error", "zzb_device_info", "zzb_event_record", "zzb_event_elapsed_ms", "zzb_problem_create_gaussian", "zzb_problem_create_logistic", "zzb_problem_free",
-    "zzb_spdmp_run", "zzb_sspdmp_run", "zzb_sspdmp3_run", "zzb_sspdmp4_run", "zzb_spdmp_boomerang_run", "zzb_spdmp_refresh_run", "zzb_run_upload_boomerang", "zzb_run_create", "zzb_run_shard", "zzb_run_ipc_export", "zzb_run_ipc_import", "zzb_run_range", "zzb_run_upload", "zzb_run_upload_kappa", "zzb_run_reset", "zzb_run_execute", "zzb_run_set", "zzb_run_stats",
+    "zzb_spdmp_run", "zzb_sspdmp_run", "zzb_sspdmp_adapt_run", "zzb_sspdmp3_run", "zzb_sspdmp4_run", "zzb_spdmp_boomerang_run", "zzb_spdmp_refresh_run", "zzb_run_upload_boomerang", "zzb_run_create", "zzb_run_shard", "zzb_run_ipc_export", "zzb_run_ipc_import", "zzb_run_range", "zzb_run_upload", "zzb_run_upload_kappa", "zzb_run_reset", "zzb_run_execute", "zzb_run_set", "zzb_run_stats",
     "zzb_run_fetch", "zzb_run_counts", "zzb_run_final_state", "zzb_trace_len", "zzb_trace_copy", "zzb_trace_clear", "zzb_trace_moments", "zzb_trace_sums",
     "zzb_run_discretize", "zzb_run_grid", "zzb_run_error_info", "zzb_run_free", "zzb_math_probe", "zzb_run_trace_filter", "zzb_trace_inclusion", "zzb_run_upload_refresh",
 ]
@@ -66,6 +66,7 @@ def lib():
             "zzb_problem_free": [vp],
             "zzb_spdmp_run": [vp, f64, vp, vp, f64, vp, vp, i32, f64, u32, vp],
             "zzb_sspdmp_run": [vp, f64, vp, vp, f64, vp, vp, vp, u32, vp],
+            "zzb_sspdmp_adapt_run": [vp, f64, vp, vp, f64, vp, vp, vp, i32, f64, u32, vp],
             "zzb_sspdmp3_run": [vp, vp, vp, f64, f64, f64, i32, vp, u32, vp],
             "zzb_sspdmp4_run": [vp, f64, vp, vp, f64, vp, vp, vp, u32, vp],
             "zzb_spdmp_refresh_run": [vp, f64, vp, vp, f64, vp, vp, f64, vp, i32, f64, u32, vp],

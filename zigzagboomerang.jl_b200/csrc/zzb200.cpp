@@ -1201,6 +1201,25 @@ int32_t zzb_sspdmp_run(zzb_problem_t p, double t0, const double* x0, const doubl
     return st;
 }
 
+// sspdmp(...; adapt = true, factor) (src/ss_fact.jl:132-136,159): zzb_sspdmp_run with the adaptation of the bounds; c is in/out
+int32_t zzb_sspdmp_adapt_run(zzb_problem_t p, double t0, const double* x0, const double* theta0, double T, double* c,
+                             const double* kappa, const uint64_t* seed, int32_t adapt, double factor, uint32_t flags, zzb_run_t* out)
+{
+    if (!out || !c || !kappa) return fail(ZZB_E_ARG, "null argument");
+    zzb_run_t r = nullptr;
+    int32_t st = zzb_run_create(p, flags | ZZB_FLAG_STICKY, 0, &r);
+    if (st) return st;
+    st = zzb_run_upload_kappa(r, kappa);
+    if (!st) st = zzb_run_upload(r, t0, x0, theta0, c, seed, adapt, factor);
+    if (!st) st = zzb_run_execute(r, T, nullptr);
+    if (st && st != ZZB_E_BOUND) { zzb_run_free(r); return st; }
+    int32_t st2 = fetch_state(r);
+    if (st2) { zzb_run_free(r); return st2; }
+    memcpy(c, r->fc.data(), (size_t)r->d * 8);
+    *out = r;
+    return st;
+}
+
 // sspdmp3 / sparsestickyzz (src/sparsestickyzz.jl:405-422,192-257): the strong-bound sparse sticky ZigZag as the reference runs
 // BASELINE config 4 -- one scalar bound constant c (SparseStickyUpperBounds, :127-142, adapt = false), one thaw rate kappa
 // (StickyBarriers), rule 0 = :sticky / 1 = :reversible; coordinates with x0 == 0 start frozen (sparsestickystate, :10-12),

@@ -139,10 +139,10 @@ function device_run(kind::Symbol, ∇ϕ::Union{GaussianPotential,LogisticSubsamp
                          Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}),
                         prob, d, Γt.colptr, Γt.rowval, Γt.nzval, h, Γb.colptr, Γb.rowval, Γb.nzval, μ))
         end
-        st = if kind === :sticky          # sspdmp, src/ss_fact.jl:159-217
-            ccall((:zzb_sspdmp_run, libzzb200), Int32,
-                  (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{UInt64}, UInt32,
-                   Ref{Ptr{Cvoid}}), prob[], t0, x0v, θ0v, T, cv, κv, sd, flags, run)
+        st = if kind === :sticky          # sspdmp, src/ss_fact.jl:159-217 (with adapt: :132-136)
+            ccall((:zzb_sspdmp_adapt_run, libzzb200), Int32,
+                  (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{UInt64}, Int32, Float64, UInt32,
+                   Ref{Ptr{Cvoid}}), prob[], t0, x0v, θ0v, T, cv, κv, sd, adapt, factor, flags, run)
         elseif kind === :refresh          # spdmp with Z.λref > 0 (hasrefresh, src/fact_samplers.jl:19): refresh branch src/sfact.jl:78-114
             ccall((:zzb_spdmp_refresh_run, libzzb200), Int32,
                   (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Float64, Ptr{Float64}, Ptr{Float64}, Float64,
@@ -228,10 +228,9 @@ pdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, C::LocalBound, F::FactBoomerang, 
 # sspdmp(∇ϕ, t0, x0, θ0, T, c, [G,] F::ZigZag, κ, ...) (src/ss_fact.jl:159-217); acc is the scalar count of reflections
 function sspdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, G, F::ZigZag, κ, args...;
                 strong_upperbounds = false, factor = 1.5, adapt = false, reversible = false, seed = Seed())
-    adapt && error("sspdmp(...; adapt = true) is not implemented on the device path")
     flags = (reversible ? ZZB_FLAG_STICKY_REVERSIBLE : UInt32(0)) | (strong_upperbounds ? ZZB_FLAG_STICKY_STRONG_UB : UInt32(0))
-    Ξ, u, (acc, num), cv = device_run(:sticky, ∇ϕ, t0, x0, θ0, T, c, F; κ = κ, seed = seed, flags = flags)
-    Ξ, u, (sum(acc), num), c
+    Ξ, u, (acc, num), cv = device_run(:sticky, ∇ϕ, t0, x0, θ0, T, c, F; κ = κ, seed = seed, flags = flags, adapt = adapt, factor = factor)
+    Ξ, u, (sum(acc), num), cv    # (adapt: the reference resets acc and num at every adaptation, src/ss_fact.jl:134; these are the totals)
 end
 
 # sspdmp2(∇ϕ, t, x0, v0, T, c, nothing, Z, κ; strong_upperbounds, adapt, factor) (src/stickyzz.jl:322-338): the dense sticky ZigZag
@@ -239,9 +238,8 @@ end
 # Returns trace, (acc, num) -- the reference returns (trace, acc::AcceptanceDiagnostics).
 function sspdmp2(∇ϕ::GaussianPotential, t, x0, v0, T, c, ::Nothing, Z::ZigZag, κ, args...; strong_upperbounds = false, progress = false,
                  adapt = false, factor = 1.5, seed = Seed())
-    adapt && error("sspdmp2(...; adapt = true) is not implemented on the device path")
     flags = ZZB_FLAG_STICKY_ZZ | (strong_upperbounds ? ZZB_FLAG_STICKY_STRONG_UB : UInt32(0))
-    Ξ, u, (acc, num), cv = device_run(:sticky, ∇ϕ, t, x0, v0, T, c, Z; κ = κ, seed = seed, flags = flags)
+    Ξ, u, (acc, num), cv = device_run(:sticky, ∇ϕ, t, x0, v0, T, c, Z; κ = κ, seed = seed, flags = flags, adapt = adapt, factor = factor)
     Ξ, (sum(acc), num)
 end
 sspdmp(∇ϕ::GaussianPotential, t0, x0, θ0, T, c, F::ZigZag, κ, args...; kargs...) = sspdmp(∇ϕ, t0, x0, θ0, T, c, nothing, F, κ, args...; kargs...)
