@@ -156,3 +156,47 @@ def test_sticky_adapt_on_device(gpu):
             assert np.array_equal(Xi.events[f].view(np.uint64), ref.events[f].view(np.uint64)), f
     with pytest.raises(gpu.BoundError):
         gpu.sspdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 8.0, c, gpu.ZigZag(Gb, np.zeros(d)), kap, seed=(1, 2))
+
+
+def test_one_call_entries_of_the_sticky_family(gpu):
+    """zzb_sspdmp_adapt_run and zzb_sspdmp4_run called the way a Julia `ccall` would (one call, raw pointers): same trace as the
+    staged Python path."""
+    import ctypes as C
+    from zzb200 import _capi
+    from zzb200.api import EVENT_DTYPE, Problem
+    L = _capi.lib()
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    G = gpu.grid_precision(9, 10, shift=0.5)
+    Gb = G.scaled(0.5)
+    rng = np.random.default_rng(3)
+    d = G.n
+    x0, th0 = rng.standard_normal(d), rng.choice(np.array([-1.0, 1.0]), d)
+    kap, sd = np.full(d, 0.8), np.array([1, 2], dtype=np.uint64)
+
+    def events_of(run):
+        n = C.c_int64()
+        _capi.check(L.zzb_trace_len(run, C.byref(n)))
+        ev = np.empty(n.value, dtype=EVENT_DTYPE)
+        _capi.check(L.zzb_trace_copy(run, ptr(ev), 0, n.value))
+        L.zzb_run_free(run)
+        return ev
+
+    prob = Problem(gpu.GaussianPotential(G), gpu.ZigZag(Gb, np.zeros(d)))
+    c = 0.05 * G.colnorms()
+    cio = c.copy()
+    run = C.c_void_p()
+    _capi.check(L.zzb_sspdmp_adapt_run(prob._h, 0.0, ptr(x0), ptr(th0), 6.0, ptr(cio), ptr(kap), ptr(sd), 1, 1.5, 0, C.byref(run)))
+    ev = events_of(run)
+    Xi, _, _, cc = gpu.sspdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 6.0, c, gpu.ZigZag(Gb, np.zeros(d)), kap, adapt=True, factor=1.5, seed=(1, 2))
+    assert np.array_equal(ev, Xi.events) and np.array_equal(cio, cc) and (cio != c).any()
+    prob.close()
+
+    prob = Problem(gpu.GaussianPotential(G), gpu.ZigZag(G, np.zeros(d)))
+    c4, k4 = 8.0 * G.colnorms() * rng.uniform(1, 2, d), rng.choice(np.array([0.3, 1.0]), d)
+    x4 = np.where(rng.random(d) < 0.5, x0, 0.0)
+    run = C.c_void_p()
+    _capi.check(L.zzb_sspdmp4_run(prob._h, -1.0, ptr(x4), ptr(th0), 9.0, ptr(c4), ptr(k4), ptr(sd), 0, C.byref(run)))
+    ev = events_of(run)
+    X4, _ = gpu.sspdmp4(None, gpu.GaussianPotential(G), -1.0, x4, th0, 9.0, c4, None, gpu.ZigZag(G, np.zeros(d)), k4, seed=(1, 2))
+    assert len(ev) > 100 and np.array_equal(ev, X4.events)
+    prob.close()
