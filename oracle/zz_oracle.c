@@ -1030,7 +1030,7 @@ zzo_run *zzo_sparsestickyzz(int64_t d, const int64_t *g_colptr, const int64_t *g
 }
 
 /* ---- the same sampler in the parity arithmetic (mode ctr|lazy): the contract a device kernel for the strong-bound sticky
- * sampler has to reproduce bit for bit (none exists yet; config 4 runs on the ss_fact.jl kernel).  Differences to the
+ * sampler reproduces bit for bit (zz_run_kernel_csr_strong, since round 2).  Differences to the
  * faithful restatement above, all equal in law:
  *   * per-coordinate counter streams u(i, k) (zz_math.h): coordinate i draws, in the order of ITS OWN events, the thaw
  *     waiting time when it freezes (and at t = 0 if it starts frozen), [rule :reversible: the sign at a thaw], the time of

@@ -1,8 +1,8 @@
 // zz_strong.h -- per-coordinate timeline of the STRONG-BOUND sparse sticky ZigZag (src/sparsestickyzz.jl, BASELINE config 4 as
-// the reference runs it) in the windowed scheme.  HOST-SIDE ONLY in this round: it is exercised by the schedule emulation
-// (oracle/zz_window_sim.cpp) against its contract oracle/zz_oracle.c:zzo_sparsestickyzz_ctr; no kernel of the image
-// instantiates it yet (config 4 runs on the sticky kernel of src/ss_fact.jl, same law).  It is written against the shared
-// structures of zz_fast.h so that a kernel instantiation only needs a mode constant.
+// the reference runs it) in the windowed scheme, and of its per-coordinate generalisation asynchzz / sspdmp4 (src/asynchzz.jl).
+// Kernel: zz_run_kernel_csr_strong (entries zzb_sspdmp3_run / zzb_sspdmp4_run); the same header runs inside the schedule emulation
+// (oracle/zz_window_sim.cpp); contracts oracle/zz_oracle.c:zzo_sparsestickyzz_ctr / zzo_strongsticky_ctr.  It is written against
+// the shared structures of zz_fast.h: the kernel instantiation is a mode constant.
 //
 // What is different from every other mode: a reflection reschedules NOBODY but the reflecting coordinate (constant bound
 // a = c + grad_i theta_i valid for 1/c, then renewed; sparsestickyzz.jl:136-142,330-340,372-399).  The timeline of j therefore
