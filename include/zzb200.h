@@ -187,6 +187,10 @@ int32_t zzb_trace_sums(zzb_run_t r, double* s1, double* s2);        /* the unsca
 /* subtrace at the source (src/trace.jl:275-290): only the events of the coordinates J (1-based, strictly ascending) are recorded,
  * renumbered to their position in J; nJ = 0 lifts the filter.  Before zzb_run_upload. */
 int32_t zzb_run_trace_filter(zzb_run_t r, const int64_t* J, int64_t nJ);
+/* cummean(trace) (src/trace.jl:203-225): per coordinate the running time average after each of its events, CSR-shaped -- the values
+ * of coordinate k (0-based) are entries offsets[k] .. offsets[k+1]-1 of times[] / values[] (sizes d + 1, zzb_trace_len, zzb_trace_len);
+ * the reference's leading pair (t0, x0_k) is left to the caller.  Computed on the device while the trace is still in HBM. */
+int32_t zzb_trace_cummean(zzb_run_t r, int64_t* offsets, double* times, double* values);
 /* inclusion_prob(trace) (src/trace.jl:161-178) of a sticky run from a device accumulator (no trace needed) */
 int32_t zzb_trace_inclusion(zzb_run_t r, double* p);
 /* Device-side discretisation.  zzb_run_discretize (before zzb_run_upload) asks for the n_rows grid times t0 + k dt,

@@ -119,3 +119,29 @@ def test_subtrace_filter_and_inclusion_prob_on_device(gpu):
         assert n == ref.num and a == int(ref.acc.sum()) and np.array_equal(Xo.events["i"], ref.events["i"])
         for f in ("t", "x", "theta"):
             assert np.array_equal(Xo.events[f].view(np.uint64), ref.events[f].view(np.uint64))
+
+
+def test_cummean_on_the_device(gpu):
+    """cummean(trace) (src/trace.jl:203-225) computed on the device from the trace in HBM (zzb_trace_cummean: grouping by
+    coordinate with the bucket kernels of the trace sort + one thread per coordinate) against the host routine on the copied
+    trace, bit for bit; the host fallback (trace drained to the host, many events per coordinate) gives the same."""
+    G, x0, th0, c = gpu.gmrf_config(40)
+    prob = gpu.Problem(gpu.GaussianPotential(G), gpu.ZigZag(G, np.zeros(G.n)))
+    for T, host_sort in ((3.0, 0), (3.0, 1), (150.0, 0)):   # device path; trace ordered on the host; > 64 events per coordinate (host walk)
+        run = gpu.Run(prob, record_trace=True)
+        run.set(host_sort=host_sort)
+        run.upload(0.5, x0, th0, c, seed=(3, 4))
+        run.execute(0.5 + T)
+        launches0 = run.stats()["launches"]
+        off, times, values = run.cummean()
+        kernels = run.stats()["launches"] - launches0
+        ev = run.events()
+        assert off[-1] == len(ev) == len(times)
+        ref = gpu.cummean(gpu.FactTrace(None, 0.5, x0, th0, ev))
+        got = gpu.cummean_lists(0.5, x0, off, times, values)
+        for k in range(0, G.n, 7):
+            assert np.array_equal(ref[k][0].view(np.uint64), got[k][0].view(np.uint64)), k
+            assert np.array_equal(ref[k][1].view(np.uint64), got[k][1].view(np.uint64)), k
+        assert kernels == (0 if host_sort else 4), (T, host_sort, kernels)   # (T = 150: the device tries, a coordinate overflows, the host walks)
+        run.close()
+    prob.close()

@@ -29,7 +29,7 @@ SYMBOLS = [
     "zzb_init", "zzb_shutdown", "zzb_last_error", "zzb_device_info", "zzb_event_record", "zzb_event_elapsed_ms", "zzb_problem_create_gaussian", "zzb_problem_create_logistic", "zzb_problem_free",
     "zzb_spdmp_run", "zzb_sspdmp_run", "zzb_sspdmp_adapt_run", "zzb_sspdmp3_run", "zzb_sspdmp4_run", "zzb_spdmp_boomerang_run", "zzb_spdmp_refresh_run", "zzb_run_upload_boomerang", "zzb_run_create", "zzb_run_shard", "zzb_run_ipc_export", "zzb_run_ipc_import", "zzb_run_range", "zzb_run_upload", "zzb_run_upload_kappa", "zzb_run_reset", "zzb_run_execute", "zzb_run_set", "zzb_run_stats",
     "zzb_run_fetch", "zzb_run_counts", "zzb_run_final_state", "zzb_trace_len", "zzb_trace_copy", "zzb_trace_clear", "zzb_trace_moments", "zzb_trace_sums",
-    "zzb_run_discretize", "zzb_run_grid", "zzb_run_error_info", "zzb_run_free", "zzb_math_probe", "zzb_run_trace_filter", "zzb_trace_inclusion", "zzb_run_upload_refresh",
+    "zzb_run_discretize", "zzb_run_grid", "zzb_run_error_info", "zzb_run_free", "zzb_math_probe", "zzb_run_trace_filter", "zzb_trace_inclusion", "zzb_trace_cummean", "zzb_run_upload_refresh",
 ]
 
 
@@ -98,6 +98,7 @@ def lib():
             "zzb_run_trace_filter": [vp, vp, i64],
             "zzb_run_upload_refresh": [vp, vp, f64],
             "zzb_trace_inclusion": [vp, vp],
+            "zzb_trace_cummean": [vp, vp, vp, vp],
             "zzb_run_free": [vp],
         }
         for name, args in sig.items():

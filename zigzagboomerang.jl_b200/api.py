@@ -393,6 +393,18 @@ class Run:
         check(_capi.lib().zzb_run_trace_filter(self._h, ptr(J), len(J)))
         return self
 
+    def cummean(self):
+        """``cummean(trace)`` (src/trace.jl:203-225) of this run, computed on the device while the trace is still in HBM:
+        ``(offsets, times, values)`` -- the running time averages of coordinate ``k`` (0-based) after each of its events are
+        ``values[offsets[k]:offsets[k+1]]`` at ``times[...]``; :func:`cummean_lists` turns this into the reference's list of pairs
+        (with the leading ``(t0, x0_k)``)."""
+        n = C.c_int64()
+        check(_capi.lib().zzb_trace_len(self._h, C.byref(n)))
+        off = np.empty(self.d + 1, dtype=np.int64)
+        times, values = np.empty(max(n.value, 1)), np.empty(max(n.value, 1))
+        check(_capi.lib().zzb_trace_cummean(self._h, ptr(off), ptr(times), ptr(values)))
+        return off, times[:n.value], values[:n.value]
+
     def inclusion_prob(self):
         """``inclusion_prob(trace)`` (src/trace.jl:161-178) of a sticky run, from a device accumulator (no trace needed)."""
         p = np.empty(self.d)
@@ -806,6 +818,12 @@ def cummean(tr: FactTrace):
         run = np.cumsum(term[sel])              # sequential partial sums, as the reference's y[i] += ...
         out.append((np.r_[tr.t0, tt], np.r_[tr.x0[k], run / (2 * tt)]))
     return out
+
+
+def cummean_lists(t0, x0, offsets, times, values):
+    """The reference's shape of ``cummean`` from the CSR triple of :meth:`Run.cummean`: per coordinate ``(times, values)`` starting
+    with ``(t0, x0_k)`` (views and one concatenation per coordinate, no arithmetic)."""
+    return [(np.r_[t0, times[offsets[k]:offsets[k + 1]]], np.r_[x0[k], values[offsets[k]:offsets[k + 1]]]) for k in range(len(x0))]
 
 
 def inclusion_prob(tr: FactTrace):

@@ -659,13 +659,15 @@ struct ZzTsort {
     unsigned long long n;       // records in `in` (events + markers)
     double tmin, scale;         // bucket = min(nb - 1, (t - tmin) * scale)
     unsigned int nb;
+    unsigned int mode;          // 0: buckets on the time axis; 1: bucket = coordinate (i - 1), nb = d (grouping for cummean)
     unsigned int* cnt;          // [nb]     events per bucket
     unsigned int* base;         // [nb + 1] exclusive prefix sum
     unsigned int* fill;         // [nb]     scatter cursors
     unsigned int* ovf;          // [1]
 };
-__device__ __forceinline__ unsigned int zz_tsort_bucket(const ZzTsort& Q, double t)
+__device__ __forceinline__ unsigned int zz_tsort_bucket(const ZzTsort& Q, double t, long long i)
 {
+    if (Q.mode == 1u) return (unsigned int)(i - 1);
     const double u = (t - Q.tmin) * Q.scale;
     if (!(u > 0.0)) return 0u;
     return u >= (double)(Q.nb - 1u) ? Q.nb - 1u : (unsigned int)u;
@@ -673,7 +675,7 @@ __device__ __forceinline__ unsigned int zz_tsort_bucket(const ZzTsort& Q, double
 extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_tsort_hist_kernel(const ZzTsort Q)
 {
     for (unsigned long long e = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; e < Q.n; e += (unsigned long long)gridDim.x * blockDim.x)
-        if (Q.in[e].i != 0) atomicAdd(Q.cnt + zz_tsort_bucket(Q, Q.in[e].t), 1u);
+        if (Q.in[e].i != 0) atomicAdd(Q.cnt + zz_tsort_bucket(Q, Q.in[e].t, Q.in[e].i), 1u);
 }
 extern "C" __global__ void __launch_bounds__(1024) zz_tsort_scan_kernel(const ZzTsort Q)
 {   // one CTA: exclusive prefix sum of the bucket counts (chunks of 1024 with a running carry)
@@ -706,7 +708,7 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_tsort_scatter_kernel(c
         const double2* src = reinterpret_cast<const double2*>(Q.in + e);
         const double2 a = src[0], b = src[1];
         if (__double_as_longlong(a.y) == 0LL) continue;   // window-end marker
-        const unsigned int bk = zz_tsort_bucket(Q, a.x);
+        const unsigned int bk = zz_tsort_bucket(Q, a.x, __double_as_longlong(a.y));
         const unsigned int pos = Q.base[bk] + atomicAdd(Q.fill + bk, 1u);
         double2* dst = reinterpret_cast<double2*>(Q.out + pos);
         dst[0] = a; dst[1] = b;
@@ -757,6 +759,45 @@ extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_tsort_sort_kernel(cons
         for (int q = 0; q < 4; ++q) {
             const unsigned int e = threadIdx.x + (unsigned int)q * blockDim.x;
             if (e < n) { double2* dst = reinterpret_cast<double2*>(ev + e); dst[0] = ra[q]; dst[1] = rb[q]; }
+        }
+    }
+}
+
+// cummean(trace) (src/trace.jl:203-225) on the device.  Input: the records grouped by coordinate (zz_tsort_hist / scan / scatter
+// with mode 1; inside a group in arbitrary order).  One thread per coordinate puts its (few) records into time order and walks
+// them: y += (x_prev + x)(t - t_prev), value = y / (2 t), exactly the reference's running sum.  A coordinate with more than
+// ZZ_CM_MAX events raises `ovf` (the host then does the whole thing itself).
+#define ZZ_CM_MAX 64u
+struct ZzCummean {
+    ZzEvent* ev;                // records grouped by coordinate (sorted in place)
+    const unsigned int* base;   // [d + 1]
+    const double* x0;
+    double t0;
+    int32_t d, pad;
+    double* times;              // [n] out, grouped like ev
+    double* values;             // [n] out
+    unsigned int* ovf;
+};
+extern "C" __global__ void __launch_bounds__(ZZ_BLOCK) zz_cummean_kernel(const ZzCummean Q)
+{
+    for (int32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < Q.d; k += gridDim.x * blockDim.x) {
+        const unsigned int b0 = Q.base[k], n = Q.base[k + 1] - b0;
+        if (n == 0u) continue;
+        if (n > ZZ_CM_MAX) { *Q.ovf = 1u; continue; }
+        ZzEvent* ev = Q.ev + b0;
+        for (unsigned int a = 1; a < n; ++a) {   // insertion sort by time (a coordinate has one event at a time)
+            const ZzEvent x = ev[a];
+            unsigned int p = a;
+            while (p > 0u && ev[p - 1].t > x.t) { ev[p] = ev[p - 1]; --p; }
+            ev[p] = x;
+        }
+        double y = 0.0, tp = Q.t0, xp = Q.x0[k];
+        for (unsigned int a = 0; a < n; ++a) {
+            const double t = ev[a].t, x = ev[a].x;
+            y += (xp + x) * (t - tp);            // trace.jl:217
+            tp = t; xp = x;
+            Q.times[b0 + a] = t;
+            Q.values[b0 + a] = y / (2 * t);      // trace.jl:222
         }
     }
 }

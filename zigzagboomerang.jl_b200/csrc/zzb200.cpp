@@ -97,6 +97,7 @@ struct Global {
     CUfunction f_init_strong = nullptr;
     CUfunction f_math_probe = nullptr;
     CUfunction f_seq = nullptr, f_seq_logit = nullptr;
+    CUfunction f_cummean = nullptr;
     CUfunction f_ts_hist = nullptr, f_ts_scan = nullptr, f_ts_scatter = nullptr, f_ts_sort = nullptr;
     CUfunction f_setup = nullptr, f_init = nullptr, f_init_boom = nullptr, f_run[ZZ_NKERN] = {}, f_export = nullptr, f_grid_tail = nullptr;
     CUstream stream = nullptr;
@@ -200,6 +201,7 @@ struct zzb_run_s {
     int tile_per = 0; unsigned int eval_threads = 0; int inbox_nr = 0;
     int seq_warps = 0;                 // sequential chains: warps per chain (0 = automatic)
     // device-side ordering of the trace (zz_tsort_*): the events of the last execute, sorted, still in HBM
+    DevBuf cm_work, cm_out;            // cummean on the device (zzb_trace_cummean)
     DevBuf trace_sorted, ts_work; bool dev_sorted = false; unsigned long long n_sorted = 0; bool host_sort_only = false;
     DevBuf trace_map, s3; bool have_map = false;   // subtrace filter / inclusion-time accumulator (sticky)
     int setup_lo = 0, setup_hi = 0;    // coordinates whose records this rank sets up (sharded lattice: slab + halo; otherwise all)
@@ -287,6 +289,7 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
     CU(cuModuleGetFunction(&G.f_grid_tail, G.mod, "zz_grid_tail_kernel"));
     CU(cuModuleGetFunction(&G.f_math_probe, G.mod, "zz_math_probe_kernel"));
+    CU(cuModuleGetFunction(&G.f_cummean, G.mod, "zz_cummean_kernel"));
     CU(cuModuleGetFunction(&G.f_seq, G.mod, "zz_seq_kernel"));
     CU(cuModuleGetFunction(&G.f_seq_logit, G.mod, "zz_seq_kernel_logit"));
     CU(cuModuleGetFunction(&G.f_ts_hist, G.mod, "zz_tsort_hist_kernel"));
@@ -850,7 +853,7 @@ int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* t
 }
 
 struct ZzTsortHost {   // same layout as ZzTsort in zz_kernels.cu
-    CUdeviceptr in, out; unsigned long long n; double tmin, scale; unsigned int nb; unsigned int pad;
+    CUdeviceptr in, out; unsigned long long n; double tmin, scale; unsigned int nb; unsigned int mode;
     CUdeviceptr cnt, base, fill, ovf;
 };
 
@@ -868,7 +871,7 @@ static int32_t device_sort_trace(zzb_run_s* r, unsigned long long n, double tmin
     CU(cuMemsetD8Async(r->ts_work.p, 0, wbytes, G.stream));
     ZzTsortHost Q;
     Q.in = r->trace.p; Q.out = r->trace_sorted.p; Q.n = n; Q.tmin = tmin;
-    Q.scale = (tmax > tmin) ? (double)nb / (tmax - tmin) : 0.0; Q.nb = nb; Q.pad = 0;
+    Q.scale = (tmax > tmin) ? (double)nb / (tmax - tmin) : 0.0; Q.nb = nb; Q.mode = 0;
     Q.cnt = r->ts_work.p; Q.base = r->ts_work.p + (size_t)nb * 4; Q.fill = r->ts_work.p + ((size_t)2 * nb + 1) * 4; Q.ovf = r->ts_work.p + ((size_t)3 * nb + 1) * 4;
     void* a[] = { &Q };
     const unsigned grid = (unsigned)std::min<unsigned long long>((n + ZZ_BLOCK - 1) / ZZ_BLOCK, (unsigned long long)G.sm_count * 16);
@@ -1484,6 +1487,85 @@ int32_t zzb_trace_inclusion(zzb_run_t r, double* p)
     CU(cuMemcpyDtoH(p, r->s3.p, (size_t)r->d * 8));
     const double Tl = r->hc.ctl.F;
     for (int32_t j = 0; j < r->d; ++j) p[j] = p[j] / Tl;
+    return ZZB_OK;
+}
+
+// cummean(trace) (src/trace.jl:203-225): per coordinate the running time average y_i / (2 t) after each of its events, y_i the
+// running sum of (x_prev + x)(t - t_prev).  CSR-shaped output: the values of coordinate k (0-based) are entries
+// offsets[k] .. offsets[k+1]-1 of times[] / values[] (the reference's leading pair (t0, x0_k) is left to the caller).  When the
+// trace is still in HBM (ordered there by the last execute) everything happens on the device: the records are grouped by
+// coordinate with the bucket kernels of the trace sort (bucket = coordinate), one thread per coordinate orders and walks its
+// records (zz_cummean_kernel); otherwise, or when a coordinate has more than 64 events, the host walks the trace.
+struct ZzCummeanHost { CUdeviceptr ev, base, x0; double t0; int32_t d, pad; CUdeviceptr times, values, ovf; };   // = ZzCummean (zz_kernels.cu)
+int32_t zzb_trace_cummean(zzb_run_t r, int64_t* offsets, double* times, double* values)
+{
+    if (!r || !offsets) return fail(ZZB_E_ARG, "null argument");
+    if (r->flags & ZZB_FLAG_NO_TRACE) return fail(ZZB_E_ARG, "the run does not record a trace");
+    if (r->flags & ZZB_FLAG_BOOMERANG) return fail(ZZB_E_ARG, "cummean assumes piecewise linear paths (not the Boomerang flow)");
+    if (r->have_map) return fail(ZZB_E_ARG, "cummean is not available together with a trace filter");
+    if (!r->executed) return fail(ZZB_E_ARG, "zzb_run_execute must precede zzb_trace_cummean");
+    CtxGuard cg;
+    const size_t d = (size_t)r->d;
+    const unsigned long long nd = r->dev_sorted ? r->n_sorted : 0ULL;
+    const size_t n = r->events.size() + (size_t)nd;
+    if (n && (!times || !values)) return fail(ZZB_E_ARG, "null argument");
+    bool done = false;
+    if (nd && r->events.empty() && nd < 0xfffffff0ULL) {
+        const unsigned int nb = (unsigned int)d;
+        const size_t wbytes = ((size_t)3 * nb + 2) * 4;
+        int32_t st = ZZB_OK;
+        if (r->cm_work.n < wbytes) st = r->cm_work.alloc(wbytes + 4096);
+        if (!st && r->cm_out.n < (size_t)nd * 16) st = r->cm_out.alloc((size_t)nd * 16);
+        if (!st) {
+            CU(cuMemsetD8Async(r->cm_work.p, 0, wbytes, G.stream));
+            ZzTsortHost Q;
+            Q.in = r->trace_sorted.p; Q.out = r->trace.p; Q.n = nd; Q.tmin = 0.0; Q.scale = 0.0; Q.nb = nb; Q.mode = 1;
+            Q.cnt = r->cm_work.p; Q.base = r->cm_work.p + (size_t)nb * 4; Q.fill = r->cm_work.p + ((size_t)2 * nb + 1) * 4; Q.ovf = r->cm_work.p + ((size_t)3 * nb + 1) * 4;
+            void* a[] = { &Q };
+            const unsigned grid = (unsigned)std::min<unsigned long long>((nd + ZZ_BLOCK - 1) / ZZ_BLOCK, (unsigned long long)G.sm_count * 16);
+            CU(cuLaunchKernel(G.f_ts_hist, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a, nullptr));
+            CU(cuLaunchKernel(G.f_ts_scan, 1, 1, 1, 1024, 1, 1, 0, G.stream, a, nullptr));
+            CU(cuLaunchKernel(G.f_ts_scatter, grid, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, a, nullptr));
+            ZzCummeanHost Cm;
+            Cm.ev = r->trace.p; Cm.base = Q.base; Cm.x0 = r->in_x.p; Cm.t0 = r->t0; Cm.d = (int32_t)d; Cm.pad = 0;
+            Cm.times = r->cm_out.p; Cm.values = r->cm_out.p + (size_t)nd * 8; Cm.ovf = Q.ovf;
+            void* b[] = { &Cm };
+            const unsigned gridc = (unsigned)std::min<size_t>((d + ZZ_BLOCK - 1) / ZZ_BLOCK, (size_t)G.sm_count * 16);
+            CU(cuLaunchKernel(G.f_cummean, gridc, 1, 1, ZZ_BLOCK, 1, 1, 0, G.stream, b, nullptr));
+            r->launches += 4;
+            std::vector<unsigned int> base(d + 1);
+            unsigned int ovf = 0;
+            CU(cuMemcpyDtoHAsync(base.data(), Q.base, (d + 1) * 4, G.stream));
+            CU(cuMemcpyDtoHAsync(&ovf, Q.ovf, 4, G.stream));
+            CU(cuStreamSynchronize(G.stream));
+            if (!ovf && base[d] == nd) {
+                CU(cuMemcpyDtoH(times, Cm.times, (size_t)nd * 8));
+                CU(cuMemcpyDtoH(values, Cm.values, (size_t)nd * 8));
+                for (size_t k = 0; k <= d; ++k) offsets[k] = (int64_t)base[k];
+                done = true;
+            }
+        }
+    }
+    if (!done) {   // host: the trace in time order, one pass
+        std::vector<zzb_event> ev(n);
+        if (!r->events.empty()) memcpy(ev.data(), r->events.data(), r->events.size() * sizeof(zzb_event));
+        if (nd) CU(cuMemcpyDtoH(ev.data() + r->events.size(), r->trace_sorted.p, (size_t)nd * sizeof(zzb_event)));
+        std::vector<double> x0(d);
+        CU(cuMemcpyDtoH(x0.data(), r->in_x.p, d * 8));
+        std::vector<int64_t> cnt(d + 1, 0);
+        for (const zzb_event& e : ev) cnt[(size_t)e.i]++;                  // (1-based ids land one slot up: exclusive scan below)
+        offsets[0] = 0;
+        for (size_t k = 0; k < d; ++k) offsets[k + 1] = offsets[k] + cnt[k + 1];
+        std::vector<int64_t> fill(offsets, offsets + d);
+        std::vector<double> y(d, 0.0), tp(d, r->t0), xp(x0);
+        for (const zzb_event& e : ev) {
+            const size_t k = (size_t)e.i - 1;
+            y[k] += (xp[k] + e.x) * (e.t - tp[k]);                         // trace.jl:217
+            tp[k] = e.t; xp[k] = e.x;
+            const int64_t pos = fill[k]++;
+            times[pos] = e.t; values[pos] = y[k] / (2 * e.t);              // trace.jl:222
+        }
+    }
     return ZZB_OK;
 }
 
