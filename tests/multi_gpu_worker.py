@@ -83,6 +83,45 @@ def main():
             if case % 5 == 0:
                 print(f"random case {case}: d={d} T={T} cs={cs} tune={tune}: {len(ref.events)} events bit-exact", flush=True)
         dist.barrier()
+    # sticky ZigZag (src/ss_fact.jl) and factorised Boomerang sharded: the lists of these samplers carry the velocity after each
+    # event, pushed into the neighbour ranks' replicas together with the event times
+    def compare(name, ref, res, stats, ms, check_sums=True):
+        class R3:
+            pass
+        got = R3()
+        got.events, got.num, got.acc = res["events"], res["num"], res["acc"]
+        got.t, got.x, got.theta, got.c = res["t"], res["x"], res["theta"], res["c"]
+        if check_sums:
+            got.s1, got.s2 = res["s1"], res["s2"]
+        else:
+            for f in ("s1", "s2"):
+                if hasattr(ref, f):
+                    delattr(ref, f)
+        O.assert_same_run(ref, got)
+        print(f"case {name}: world {world}, {len(ref.events)} events bit-exact, {stats['windows']} windows, {ms:.2f} ms", flush=True)
+
+    srng = np.random.default_rng(17)
+    for name, Gs in (("sticky grid 20x14", zzb.grid_precision(20, 14, shift=0.5)), ("sticky sparse 80", zzb.random_sparse_spd(80, deg=2, seed=10))):
+        d = Gs.n
+        x0_, th0_ = srng.standard_normal(d), srng.choice(np.array([-1.0, 1.0]), d)
+        c_, kap = 4.0 * Gs.colnorms(), srng.choice(np.array([0.3, 0.8, 2.0]), d)
+        for opts in (dict(), dict(reversible=True, strong_upperbounds=True)):
+            res, stats, ms = zzb.spdmp_sharded(zzb, zzb.GaussianPotential(Gs), zzb.ZigZag(Gs, np.zeros(d)), 0.0, x0_, th0_, 6.0, c_, seed=(3, 4),
+                                               run_kwargs=dict(kappa=kap, **opts))
+            if rank == 0:
+                mode = O.PARITY_MODE | (O.STICKY_REVERSIBLE if opts else 0) | (O.STICKY_STRONG_UB if opts else 0)
+                compare(name + (" reversible strong_ub" if opts else ""), O.spdmp(Gs, Gs, 0.0, x0_, th0_, 6.0, c_, kappa=kap, seed=(3, 4), mode=mode),
+                        res, stats, ms, check_sums=False)
+            dist.barrier()
+    from test_boomerang import boom_inputs
+    for name, Gb2 in (("boomerang grid 18x16", zzb.grid_precision(18, 16)), ("boomerang sparse 80", zzb.random_sparse_spd(80, deg=2, seed=5))):
+        Zg, sigma, x0_, th0_, c_ = boom_inputs(zzb, Gb2, 1.0, srng)
+        F = zzb.FactBoomerang(Zg, np.zeros(Gb2.n), 20.0, sigma, rho=0.2)
+        res, stats, ms = zzb.spdmp_sharded(zzb, zzb.GaussianPotential(Gb2), F, 0.0, x0_, th0_, 3.0, c_, seed=(5, 6), run_kwargs=dict(boomerang=F))
+        if rank == 0:
+            compare(name, O.spdmp(Gb2, Zg, 0.0, x0_, th0_, 3.0, c_, seed=(5, 6), mode=O.PARITY_MODE, boom=(sigma, 20.0, 0.2)), res, stats, ms,
+                    check_sums=False)
+        dist.barrier()
     if rank == 0:
         print("MULTI_OK", flush=True)
     dist.destroy_process_group()

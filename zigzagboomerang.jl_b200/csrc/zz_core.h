@@ -120,6 +120,7 @@ struct ZzView {
     int32_t lo, hi;                 // owned range
     ZzKin* kin_peer[ZZ_MAXRANKS];
     double* flips_peer[ZZ_MAXRANKS];
+    double* fth_peer[ZZ_MAXRANKS];   // (samplers whose lists carry the velocity after each event: sticky, Boomerang)
     // Factorised Boomerang (F::FactBoomerang in src/sfact.jl): rotation around bmu, velocity refreshment
     // theta <- brho theta + brhobar bsig N(0,1) at rate bref_rate = lambda_ref / d per coordinate; lists carry
     // (time, velocity after) like the sticky ones (fth)

@@ -1429,6 +1429,12 @@ __device__ __forceinline__ void zz_publish_async(const ZzParams& P, ZzAsyncSh& S
 #pragma unroll
                     for (int m = 0; m < ZZ_MAXFLIP; ++m)
                         if (m < (int)o.nflip) flr[m] = o.fl[m];
+                    if (ZZ_MODE_HAS_VEL(MODE)) {
+                        double* ftr = P.v.fth_peer[rr] + ((size_t)j * 2 + wsl) * ZZ_MAXFLIP;
+#pragma unroll
+                        for (int m = 0; m < ZZ_MAXFLIP; ++m)
+                            if (m < (int)o.nflip) ftr[m] = o.fth[m];
+                    }
                     reinterpret_cast<volatile uint32_t*>(P.v.kin_peer[rr] + j)[6 + wsl] = (newtag << 4) | o.nflip;
                 }
             }
@@ -1974,6 +1980,10 @@ ZZ_RUN_KERNEL(zz_run_kernel_csr_logit, ZZ_KIND_CSR, false, ZZ_MODE_LOGIT, ZZ_ASY
 ZZ_RUN_KERNEL(zz_run_kernel_csr_strong, ZZ_KIND_CSR, false, ZZ_MODE_STRONG, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_grid_refresh, ZZ_KIND_GRID, false, ZZ_MODE_REFRESH, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_refresh, ZZ_KIND_CSR, false, ZZ_MODE_REFRESH, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_sticky_multi, ZZ_KIND_GRID, true, ZZ_MODE_STICKY, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_sticky_multi, ZZ_KIND_CSR, true, ZZ_MODE_STICKY, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_grid_boom_multi, ZZ_KIND_GRID, true, ZZ_MODE_BOOM, ZZ_ASYNC)
+ZZ_RUN_KERNEL(zz_run_kernel_csr_boom_multi, ZZ_KIND_CSR, true, ZZ_MODE_BOOM, ZZ_ASYNC)
 ZZ_RUN_KERNEL(zz_run_kernel_grid_sync, ZZ_KIND_GRID, false, ZZ_MODE_PLAIN, 0)
 ZZ_RUN_KERNEL(zz_run_kernel_csr_sync, ZZ_KIND_CSR, false, ZZ_MODE_PLAIN, 0)
 

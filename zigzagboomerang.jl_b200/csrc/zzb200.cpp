@@ -85,7 +85,7 @@ static int32_t cu_fail(CUresult r, const char* what)
     } while (0)
 
 // --------------------------------------------------------------------------------------------- global state
-#define ZZ_NKERN 18   // event-loop kernels in the image (see zzb_init)
+#define ZZ_NKERN 22   // event-loop kernels in the image (see zzb_init)
 #define ZZ_KERN_BLOCK_IDX(k) ((k) == 12 || (k) == 13 ? 1 : ((k) & 1))
 #define ZZ_RUN_BLOCK_OF(r) ZZ_KERN_BLOCK_IDX((r)->kidx())      // the logistic / strong kernels are general-sparse kernels on any graph
 #define ZZ_KERN_ASYNC(k) ((k) < 14 || (k) >= 16)   // asynchronous tile-local relaxation (zz_run_body_async)
@@ -211,8 +211,8 @@ struct zzb_run_s {
         if (strong) return 13;
         if (prob && prob->logit) return 12;
         if (flags & ZZB_FLAG_REFRESH) return 16 + kind;
-        if (flags & ZZB_FLAG_BOOMERANG) return 10 + kind;
-        if (flags & ZZB_FLAG_STICKY) return 8 + kind;
+        if (flags & ZZB_FLAG_BOOMERANG) return (nranks > 1 ? 20 : 10) + kind;
+        if (flags & ZZB_FLAG_STICKY) return (nranks > 1 ? 18 : 8) + kind;
         if (!sched() && nranks <= 1 && !(flags & ZZB_FLAG_LOCAL_BOUND)) return 14 + kind;
         return kind + (nranks > 1 ? 2 : 0) + ((flags & ZZB_FLAG_LOCAL_BOUND) ? 4 : 0);
     }
@@ -283,7 +283,9 @@ int32_t zzb_init(int32_t ndev, const int32_t* dev_ids, const char* cubin_path)
                                          "zz_run_kernel_grid_sticky", "zz_run_kernel_csr_sticky", "zz_run_kernel_grid_boom", "zz_run_kernel_csr_boom",
                                          "zz_run_kernel_csr_logit", "zz_run_kernel_csr_strong",
                                          "zz_run_kernel_grid_sync", "zz_run_kernel_csr_sync",      // 14, 15: round-1 schedule (A/B reference)
-                                         "zz_run_kernel_grid_refresh", "zz_run_kernel_csr_refresh" };   // 16, 17: ZigZag with refreshments
+                                         "zz_run_kernel_grid_refresh", "zz_run_kernel_csr_refresh",     // 16, 17: ZigZag with refreshments
+                                         "zz_run_kernel_grid_sticky_multi", "zz_run_kernel_csr_sticky_multi",   // 18, 19: sticky, sharded
+                                         "zz_run_kernel_grid_boom_multi", "zz_run_kernel_csr_boom_multi" };     // 20, 21: Boomerang, sharded
     CU(cuModuleGetFunction(&G.f_init_strong, G.mod, "zz_init_kernel_strong"));
     for (int k = 0; k < ZZ_NKERN; ++k) CU(cuModuleGetFunction(&G.f_run[k], G.mod, run_names[k]));
     CU(cuModuleGetFunction(&G.f_export, G.mod, "zz_export_kernel"));
@@ -630,6 +632,7 @@ static void fill_params(zzb_run_s* r)
             const bool me = (q == r->rank);
             P.v.kin_peer[q] = me ? P.v.kin : reinterpret_cast<ZzKin*>(r->peer[q][0]);
             P.v.flips_peer[q] = me ? P.v.flips : reinterpret_cast<double*>(r->peer[q][1]);
+            P.v.fth_peer[q] = me ? P.v.fth : reinterpret_cast<double*>(r->peer[q][5]);
             P.inbox_peer[q] = me ? P.inbox : reinterpret_cast<unsigned long long*>(r->peer[q][3]);
             P.inbox_cnt_peer[q] = me ? P.inbox_cnt : reinterpret_cast<unsigned int*>(r->peer[q][4]);
             P.dstamp_peer[q] = me ? P.dstamp : reinterpret_cast<unsigned int*>(r->peer[q][2]);
@@ -644,7 +647,7 @@ static CUdeviceptr shared_buf(zzb_run_s* r, int k)
 {
     switch (k) {
     case 0: return r->kin.p; case 1: return r->flips.p; case 2: return r->dstamp.p;
-    case 3: return r->inbox.p; case 4: return r->inbox_cnt.p; case 5: return r->wl[2].p;
+    case 3: return r->inbox.p; case 4: return r->inbox_cnt.p; case 5: return r->dfth.p ? r->dfth.p : r->wl[2].p;   // (velocity lists of the sticky / Boomerang samplers)
     case 6: return r->touched.p; default: return r->ctl.p;
     }
 }
@@ -656,7 +659,7 @@ int32_t zzb_run_shard(zzb_run_t r, int32_t rank, int32_t nranks)
 {
     if (!r) return fail(ZZB_E_ARG, "null argument");
     if (nranks < 1 || nranks > ZZ_MAXRANKS || rank < 0 || rank >= nranks) return fail(ZZB_E_ARG, "bad rank %d of %d", rank, nranks);
-    if (nranks > 1 && (r->flags & (ZZB_FLAG_STICKY | ZZB_FLAG_BOOMERANG))) return fail(ZZB_E_ARG, "the sticky and Boomerang samplers are not sharded yet");
+    if (nranks > 1 && r->strong) return fail(ZZB_E_ARG, "the strong-bound sticky samplers are not sharded");
     if (nranks > 1 && r->prob->logit) return fail(ZZB_E_ARG, "the logistic target is not sharded (its dependency graph is complete: replicas only)");
     const int64_t d = r->d;
     int64_t shard = (d + nranks - 1) / nranks;
@@ -670,7 +673,7 @@ int32_t zzb_run_shard(zzb_run_t r, int32_t rank, int32_t nranks)
     return setup_tiles(r);   // (the inboxes are exported to the peers: allocate them now)
 }
 
-// 8 IPC handles (kin, flips, dstamp, inbox, inbox counters, [unused work list], touched list, control block) of this rank.
+// 8 IPC handles (kin, flips, dstamp, inbox, inbox counters, velocity lists [or an unused work list], touched list, control block) of this rank.
 int32_t zzb_run_ipc_export(zzb_run_t r, void* buf, int64_t cap, int64_t* len)
 {
     if (!r || !buf || !len) return fail(ZZB_E_ARG, "null argument");
@@ -790,6 +793,7 @@ int32_t zzb_run_reset(zzb_run_t r)
     if ((r->flags & ZZB_FLAG_BOOMERANG) && !r->have_boom) return fail(ZZB_E_ARG, "zzb_run_upload_boomerang must precede zzb_run_upload for a Boomerang run");
     if ((r->flags & ZZB_FLAG_REFRESH) && !r->have_refresh) return fail(ZZB_E_ARG, "zzb_run_upload_refresh must precede zzb_run_upload for a run with ZZB_FLAG_REFRESH");
     if ((r->flags & ZZB_FLAG_REFRESH) && r->nranks > 1) return fail(ZZB_E_ARG, "ZigZag refreshments are not sharded yet");
+    if (r->strong && r->nranks > 1) return fail(ZZB_E_ARG, "the strong-bound sticky samplers are not sharded");
     if (r->strong && r->adapt) return fail(ZZB_E_ARG, "adapt is not supported by the strong-bound sticky samplers on the device path");
     for (int q = 0; q < r->nranks; ++q)
         if (q != r->rank && !r->peer_open[q]) return fail(ZZB_E_ARG, "peer %d of a sharded run has not been imported", q);

@@ -46,14 +46,14 @@ def merge_shards(parts, d: int):
 
 
 def spdmp_sharded(zzb, target, Z, t0, x0, theta0, T, c, *, seed=(1, 2), adapt=False, factor=1.8, record_trace=True,
-                  tune=None, group=None, gather=True):
+                  tune=None, group=None, gather=True, run_kwargs=None):
     """Sharded `spdmp`: returns (result dict, run statistics, kernel milliseconds of this rank).  Must be called by every
     rank of `group` (default: the world), each after `zzb.init(local_rank)`."""
     import torch.distributed as dist
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     prob = zzb.Problem(target, Z)
-    run = zzb.Run(prob, record_trace=record_trace)
+    run = zzb.Run(prob, record_trace=record_trace, **(run_kwargs or {}))   # run_kwargs: kappa=... (sticky), boomerang=F (FactBoomerang)
     try:
         if tune:
             run.set(**tune)
