@@ -160,7 +160,8 @@ int32_t zzb_run_upload(zzb_run_t r, double t0, const double* x0, const double* t
 /* Coordinate sharding over the GPUs of one node (one process per GPU): rank r owns a contiguous block of coordinates;
  * halo records are read, and remote coordinates queued, through CUDA-IPC peer mappings over NVLink.  Order: zzb_run_create,
  * zzb_run_shard, exchange zzb_run_ipc_export blobs (e.g. torch.distributed all_gather), zzb_run_ipc_import for every peer,
- * zzb_run_upload on every rank, a host barrier, zzb_run_execute on every rank.  Results cover the owned range. */
+ * zzb_run_upload on every rank, a host barrier, zzb_run_execute on every rank.  Results cover the owned range.  Plain ZigZag,
+ * LocalBound, sticky (sspdmp / sspdmp2) and Boomerang runs shard; refreshments, strong bounds and the logistic target do not. */
 int32_t zzb_run_shard(zzb_run_t r, int32_t rank, int32_t nranks);
 int32_t zzb_run_ipc_export(zzb_run_t r, void* buf, int64_t cap, int64_t* len);
 int32_t zzb_run_ipc_import(zzb_run_t r, int32_t peer_rank, const void* buf, int64_t len);
