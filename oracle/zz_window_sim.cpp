@@ -174,11 +174,11 @@ static zzw_run* zzw_impl(int64_t d, const int64_t* tcp, const int64_t* trv, cons
     std::vector<double> rst((size_t)d * 2, 0.0), rspec((size_t)d * 2, 0.0);
     v.refresh = refresh_sigma ? 1 : 0; v.rsig = refresh_sigma; v.rlam1 = refresh_lambdaref / (double)d; v.rst = rst.data(); v.rspec = rspec.data();
     if (refresh_sigma) v.fth = fth.data();
-    if (refresh_sigma && !g.grid_m && G.maxdeg > ZZ_NB) { r->status = 1; r->msg = "column too long"; return r; }
+    if (refresh_sigma && !g.grid_m && G.maxdeg > ZZ_NB_WIDE) { r->status = 1; r->msg = "column too long"; return r; }
     const bool vel = kappa || boom_sigma || refresh_sigma;   // lists carry the velocity after each event
     v.boom = boom_sigma ? 1 : 0; v.bmu = mu; v.bsig = boom_sigma; v.bref_rate = boom_lambdaref / (double)d; v.brho = boom_rho;
     v.brhobar = sqrt(1 - boom_rho * boom_rho);
-    if (boom_sigma && !g.grid_m && G.maxdeg > ZZ_NB) { r->status = 1; r->msg = "column too long"; return r; }
+    if (boom_sigma && !g.grid_m && G.maxdeg > ZZ_NB_WIDE) { r->status = 1; r->msg = "column too long"; return r; }
 
     for (int64_t j = 0; j < d; ++j) {
         kin[j].theta = th0[j]; kin[j].tf = t0; kin[j].xf = x0[j]; kin[j].hdr[0] = kin[j].hdr[1] = 0;

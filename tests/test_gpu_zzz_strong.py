@@ -200,3 +200,36 @@ def test_one_call_entries_of_the_sticky_family(gpu):
     X4, _ = gpu.sspdmp4(None, gpu.GaussianPotential(G), -1.0, x4, th0, 9.0, c4, None, gpu.ZigZag(G, np.zeros(d)), k4, seed=(1, 2))
     assert len(ev) > 100 and np.array_equal(ev, X4.events)
     prob.close()
+
+
+def test_wide_columns_on_device(gpu):
+    """Sticky, refreshment and Boomerang samplers on a graph with columns of 9 .. 32 entries (the out-of-line wide instantiation,
+    zz_process_node_wide; round 1 refused more than 8): bit for bit against the oracle."""
+    import oracle_lib as O
+    from test_boomerang import boom_inputs
+    G = gpu.random_sparse_spd(300, deg=5, seed=2)
+    d = G.n
+    assert 8 < np.diff(G.colptr).max() <= 32
+    rng = np.random.default_rng(31)
+    x0, th0 = rng.standard_normal(d), rng.choice(np.array([-1.0, 1.0]), d)
+    c, kap = 4.0 * G.colnorms(), rng.choice(np.array([0.3, 0.8, 2.0]), d)
+    Z = gpu.ZigZag(G, np.zeros(d))
+    ref = O.spdmp(G, G, 0.0, x0, th0, 5.0, c, kappa=kap, seed=(1, 2))
+    Xi, (t, x, th), (acc, num), cc = gpu.sspdmp(gpu.GaussianPotential(G), 0.0, x0, th0, 5.0, c, Z, kap, seed=(1, 2))
+    assert num == ref.num and np.array_equal(Xi.events, ref.events) and np.array_equal(x.view(np.uint64), ref.x.view(np.uint64))
+    sigma = 0.5 + rng.random(d)
+    ths = sigma * rng.choice(np.array([-1.0, 1.0]), d)
+    cr = 3.0 * G.colnorms() * sigma.max()
+    ref = O.spdmp(G, G, 0.0, x0, ths, 4.0, cr, seed=(5, 7), refresh=(sigma, 0.8 * d), adapt=True)
+    Xi, (t, x, th), (acc, num), cc = gpu.spdmp(gpu.GaussianPotential(G), 0.0, x0, ths, 4.0, cr, gpu.ZigZag(G, np.zeros(d), sigma, lambdaref=0.8 * d),
+                                               seed=(5, 7), adapt=True)
+    assert num == ref.num and np.array_equal(Xi.events, ref.events) and np.array_equal(cc.view(np.uint64), ref.c.view(np.uint64))
+    Zg, bsig, xb, thb, cb = boom_inputs(gpu, G, 1.0, rng)
+    ref = O.spdmp(G, Zg, 0.0, xb, thb, 3.0, cb, seed=(5, 6), boom=(bsig, 20.0, 0.2))
+    F = gpu.FactBoomerang(Zg, np.zeros(d), 20.0, bsig, rho=0.2)
+    Xi, (t, x, th), (acc, num), cc = gpu.spdmp(gpu.GaussianPotential(G), 0.0, xb, thb, 3.0, cb, F, seed=(5, 6))
+    assert num == ref.num and np.array_equal(Xi.events, ref.events) and np.array_equal(x.view(np.uint64), ref.x.view(np.uint64))
+    big = gpu.random_sparse_spd(200, deg=20, seed=1)      # columns over 32 entries are still refused
+    assert np.diff(big.colptr).max() > 32
+    with pytest.raises(gpu.ZZBError, match="at most 32"):
+        gpu.sspdmp(gpu.GaussianPotential(big), 0.0, np.ones(200), np.ones(200), 1.0, big.colnorms(), gpu.ZigZag(big, np.zeros(200)), np.ones(200), seed=(1, 2))

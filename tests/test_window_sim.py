@@ -279,3 +279,31 @@ def test_zigzag_refreshments(zzb, lattice, tiles):
     assert nrefresh > 0.5 * 0.8 * d * 6.0 * 0.5 and int(ref.acc.sum()) > 50          # both kinds of event occur
     got = O.window_sim(G, Gb, 0.0, x0, th0, 6.0, c, h=h, mu=mu, seed=(5, 7), refresh=(sigma, 0.8 * d), adapt=True, async_tiles=tiles)
     O.assert_same_run(ref, got)
+
+
+@pytest.mark.parametrize("tiles", [0, 4])
+def test_wide_columns_of_the_velocity_list_samplers(zzb, tiles):
+    """Columns of 9 .. 32 entries for the samplers without a list-walking fallback (sticky, Boomerang, refreshments): the wider
+    out-of-line instantiation of gather + timeline (zz_process_node_wide) against the oracle, both schedules."""
+    from test_boomerang import boom_inputs
+    G = zzb.random_sparse_spd(70, deg=5, seed=2)
+    d = G.n
+    assert 8 < np.diff(G.colptr).max() <= 32
+    rng = np.random.default_rng(31)
+    x0, th0 = rng.standard_normal(d), rng.choice(np.array([-1.0, 1.0]), d)
+    c, kap = 4.0 * G.colnorms(), rng.choice(np.array([0.3, 0.8, 2.0]), d)
+    ref = O.spdmp(G, G, 0.0, x0, th0, 5.0, c, kappa=kap)
+    got = O.window_sim(G, G, 0.0, x0, th0, 5.0, c, kappa=kap, async_tiles=tiles)
+    O.assert_same_run(ref, got)
+    assert len(ref.events) > 150
+    sigma = 0.5 + rng.random(d)
+    ths = sigma * rng.choice(np.array([-1.0, 1.0]), d)
+    cr = 3.0 * G.colnorms() * sigma.max()
+    ref = O.spdmp(G, G, 0.0, x0, ths, 4.0, cr, seed=(5, 7), refresh=(sigma, 0.8 * d), adapt=True)
+    got = O.window_sim(G, G, 0.0, x0, ths, 4.0, cr, seed=(5, 7), refresh=(sigma, 0.8 * d), adapt=True, async_tiles=tiles)
+    O.assert_same_run(ref, got)
+    Zg, bsig, xb, thb, cb = boom_inputs(zzb, G, 1.0, rng)
+    ref = O.spdmp(G, Zg, 0.0, xb, thb, 3.0, cb, seed=(5, 6), boom=(bsig, 20.0, 0.2))
+    got = O.window_sim(G, Zg, 0.0, xb, thb, 3.0, cb, seed=(5, 6), boom=(bsig, 20.0, 0.2), async_tiles=tiles)
+    O.assert_same_run(ref, got)
+    assert len(ref.events) > 50

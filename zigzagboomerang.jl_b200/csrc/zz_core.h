@@ -392,7 +392,13 @@ ZZ_HD void zz_init_node_boom(const ZzGraph& g, const ZzView& v, int32_t j, doubl
     if (g.grid_m) { ZzHood<5> hd; ZzHoodMu<5> hm; zz_gather_grid<false, true>(g, v, j, 1u, 1u, true, hd, pool, fl, &hm); zz_boom_init<5>(hd, hm, g, v, j, t0); }
     else {
         ZzHood<ZZ_NB> hd; ZzHoodMu<ZZ_NB> hm;
-        if (!zz_gather_csr<ZZ_NB, false, true>(g, v, j, 1u, 1u, true, hd, pool, fl, &hm)) return;   // (longer columns are refused by the host)
+        if (g.nptr[j + 1] - g.nptr[j] > ZZ_NB) {   // columns of 9 .. ZZ_NB_WIDE entries (longer ones are refused by the host)
+            ZzHood<ZZ_NB_WIDE> hdw; ZzHoodMu<ZZ_NB_WIDE> hmw;
+            if (!zz_gather_csr<ZZ_NB_WIDE, false, true>(g, v, j, 1u, 1u, true, hdw, pool, fl, &hmw)) return;
+            zz_boom_init<ZZ_NB_WIDE>(hdw, hmw, g, v, j, t0);
+            return;
+        }
+        if (!zz_gather_csr<ZZ_NB, false, true>(g, v, j, 1u, 1u, true, hd, pool, fl, &hm)) return;
         zz_boom_init<ZZ_NB>(hd, hm, g, v, j, t0);
     }
 }

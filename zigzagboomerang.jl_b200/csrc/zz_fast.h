@@ -20,6 +20,7 @@ __device__ int zz_dbg_on;     // segments are accumulated only while set (ZZ_PRO
 #endif
 
 #define ZZ_NB 8     // neighbourhood capacity of the gathered path (entries of column j, j included)
+#define ZZ_NB_WIDE 32   // sticky / Boomerang / refreshment samplers: columns of 9 .. 32 entries take a second, out-of-line instantiation
 #define ZZ_POOL 16  // neighbour flips merged per coordinate and window
 
 // frontier state of the coordinate being evaluated (loaded before the neighbourhood so that all loads overlap)
@@ -771,6 +772,28 @@ ZZ_HD void zz_process_interior(const ZzGraph& g, const ZzView& v, int32_t j, dou
 #define ZZ_MODE_STRONG 5   // strong-bound sparse sticky ZigZag (zz_strong.h); only in -DZZ_ENABLE_STRONG builds of the image
 #define ZZ_MODE_REFRESH 6  // ZigZag with velocity refreshments (Z.lambdaref > 0, src/sfact.jl:78-114)
 #define ZZ_MODE_HAS_VEL(M) ((M) == ZZ_MODE_STICKY || (M) == ZZ_MODE_BOOM || (M) == ZZ_MODE_STRONG || (M) == ZZ_MODE_REFRESH)   // flip lists carry the velocity after each event
+// Columns of ZZ_NB + 1 .. ZZ_NB_WIDE entries for the samplers that have no list-walking fallback (sticky, Boomerang,
+// refreshments): the same gather + timeline with a wider neighbourhood.  Out of line (its arrays live in local memory): the
+// register allocation of the common path is untouched, long columns are merely slower.
+template <int MODE, bool MG>
+ZZ_HD_NOINLINE void zz_process_node_wide(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
+                                         uint32_t cur, bool first_iter, ZzNodeOut& o)
+{
+    ZzPool pool; uint32_t flags = 0;
+    ZzOwn w;
+    ZzHood<ZZ_NB_WIDE> hd;
+    zz_load_own(v, j, w);
+    if (MODE == ZZ_MODE_BOOM) {
+        ZzHoodMu<ZZ_NB_WIDE> hm;
+        zz_gather_csr<ZZ_NB_WIDE, MG, true>(g, v, j, w0, cur, first_iter, hd, pool, flags, &hm);
+        zz_timeline_boom<ZZ_NB_WIDE>(hd, hm, pool, w, g, v, j, H, incl, flags, o);
+        return;
+    }
+    zz_gather_csr<ZZ_NB_WIDE, MG, true>(g, v, j, w0, cur, first_iter, hd, pool, flags);
+    if (MODE == ZZ_MODE_REFRESH) zz_timeline_refresh<ZZ_NB_WIDE>(hd, pool, w, g, v, j, H, incl, flags, o);
+    else zz_timeline_sticky<ZZ_NB_WIDE>(hd, pool, w, g, v, j, H, incl, flags, o);
+}
+
 template <int KIND, int MODE, bool MG = true>
 ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, double H, int incl, uint32_t w0,
                              uint32_t cur, bool first_iter, ZzNodeOut& o)
@@ -814,6 +837,12 @@ ZZ_HD void zz_process_node_k(const ZzGraph& g, const ZzView& v, int32_t j, doubl
         if (MODE == ZZ_MODE_REFRESH) zz_timeline_refresh<ZZ_NB>(hd, pool, w, g, v, j, H, incl, flags, o);
         else if (MODE == ZZ_MODE_STICKY) zz_timeline_sticky<ZZ_NB>(hd, pool, w, g, v, j, H, incl, flags, o);
         else zz_timeline<ZZ_NB, MODE == ZZ_MODE_LB>(hd, pool, w, g, v, j, H, incl, flags, o);
+        return;
+    }
+    if (MODE == ZZ_MODE_STICKY || MODE == ZZ_MODE_BOOM || MODE == ZZ_MODE_REFRESH) {   // (the host refuses columns over ZZ_NB_WIDE)
+        o.interior = 0u;
+        zz_process_node_wide<(MODE == ZZ_MODE_STICKY || MODE == ZZ_MODE_BOOM || MODE == ZZ_MODE_REFRESH) ? MODE : ZZ_MODE_STICKY, MG>(
+            g, v, j, H, incl, w0, cur, first_iter, o);
         return;
     }
     zz_process_node_slow(g, v, j, H, incl, w0, cur, first_iter, o);

@@ -19,8 +19,10 @@
 
 #if defined(__CUDACC__)
 #define ZZ_HD __host__ __device__ __forceinline__
+#define ZZ_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define ZZ_HD static inline
+#define ZZ_HD_NOINLINE static inline
 #endif
 
 #if defined(__CUDA_ARCH__)

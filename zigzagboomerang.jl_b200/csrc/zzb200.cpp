@@ -508,15 +508,15 @@ int32_t zzb_run_create(zzb_problem_t p, uint32_t flags, int64_t trace_capacity_e
     if (p->logit && (flags & (ZZB_FLAG_STICKY | ZZB_FLAG_LOCAL_BOUND | ZZB_FLAG_BOOMERANG)))
         return fail(ZZB_E_ARG, "the logistic target runs with the plain ZigZag sampler only (no sticky / LocalBound / Boomerang)");
     if ((flags & ZZB_FLAG_STICKY) && (flags & ZZB_FLAG_LOCAL_BOUND)) return fail(ZZB_E_ARG, "sticky and LocalBound cannot be combined");
-    if ((flags & ZZB_FLAG_STICKY) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB)
-        return fail(ZZB_E_ARG, "the sticky kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB, p->hg.maxdeg);
+    if ((flags & ZZB_FLAG_STICKY) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB_WIDE)
+        return fail(ZZB_E_ARG, "the sticky kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB_WIDE, p->hg.maxdeg);
     if ((flags & ZZB_FLAG_BOOMERANG) && (flags & (ZZB_FLAG_STICKY | ZZB_FLAG_LOCAL_BOUND))) return fail(ZZB_E_ARG, "Boomerang cannot be combined with sticky / LocalBound");
     if ((flags & ZZB_FLAG_REFRESH) && (flags & (ZZB_FLAG_STICKY | ZZB_FLAG_LOCAL_BOUND | ZZB_FLAG_BOOMERANG))) return fail(ZZB_E_ARG, "ZigZag refreshments cannot be combined with sticky / LocalBound / Boomerang");
     if ((flags & ZZB_FLAG_REFRESH) && p->logit) return fail(ZZB_E_ARG, "ZigZag refreshments are not available with the logistic target");
-    if ((flags & ZZB_FLAG_REFRESH) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB)
-        return fail(ZZB_E_ARG, "the refreshment kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB, p->hg.maxdeg);
-    if ((flags & ZZB_FLAG_BOOMERANG) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB)
-        return fail(ZZB_E_ARG, "the Boomerang kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB, p->hg.maxdeg);
+    if ((flags & ZZB_FLAG_REFRESH) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB_WIDE)
+        return fail(ZZB_E_ARG, "the refreshment kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB_WIDE, p->hg.maxdeg);
+    if ((flags & ZZB_FLAG_BOOMERANG) && !p->g.grid_m && p->hg.maxdeg > ZZ_NB_WIDE)
+        return fail(ZZB_E_ARG, "the Boomerang kernels handle columns of at most %d entries (this matrix has %d)", ZZ_NB_WIDE, p->hg.maxdeg);
     if ((flags & ZZB_FLAG_LOCAL_BOUND) && !p->hg.bnd_eq_tgt)
         return fail(ZZB_E_ARG, "LocalBound builds its bound from the target: create the problem with the sampler matrix equal to the target (bnd_* = NULL) and Z.mu = 0");
     CtxGuard cg;
@@ -730,6 +730,7 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     // kappa[0] of zzb_run_upload_kappa is the thaw rate; coordinates with x0 == 0 start frozen.  Before zzb_run_upload.
     else if (!strcmp(key, "strong_c")) {
         if (!(r->flags & ZZB_FLAG_STICKY) || !(value > 0.0)) return fail(ZZB_E_ARG, "strong_c needs a sticky run and c > 0");
+        if (r->prob->hg.maxdeg > ZZ_NB) return fail(ZZB_E_ARG, "the strong-bound kernel handles columns of at most %d entries (this matrix has %d)", ZZ_NB, r->prob->hg.maxdeg);
         r->strong = true; r->strong_c = value; r->grid = G.sm_count * G.blocks_per_sm[r->kidx()];
     }
     else if (!strcmp(key, "strong_rule")) r->strong_rule = (int)value;
