@@ -7,9 +7,11 @@ import numpy as np
 import oracle_lib as O
 
 
-def run_cases(z, ncases, seed, verbose=False, sim=False, async_sim=False):
+def run_cases(z, ncases, seed, verbose=False, sim=False, async_sim=False, seq=False):
     """Returns (failures, bound_errors); prints failing cases.  sim = True: instead of the CUDA path, the host emulation of the
-    device schedule (oracle/zz_window_sim.cpp: the kernels' own per-coordinate code) is compared with the oracle -- no GPU."""
+    device schedule (oracle/zz_window_sim.cpp: the kernels' own per-coordinate code) is compared with the oracle -- no GPU.
+    seq = True: the sequential-chain schedule of the device (zz_seq.cuh: plain ZigZag, components of at most 2700 coordinates,
+    1 / 2 / 4 warps per chain, block-diagonal problems with scattered components among the cases)."""
     rng = np.random.default_rng(seed)
     nb = [0]
     class R:
@@ -29,8 +31,10 @@ def run_cases(z, ncases, seed, verbose=False, sim=False, async_sim=False):
     bad = 0
     for case in range(ncases):
         kind = rng.choice(["zigzag", "zigzag", "localbound", "sticky", "boomerang"])
+        if seq:
+            kind = "zigzag"
         if rng.random() < 0.5:
-            big = rng.random() < 0.1
+            big = rng.random() < 0.1 and not seq
             m, n = (int(rng.integers(60, 200)), int(rng.integers(60, 200))) if big else (int(rng.integers(2, 40)), int(rng.integers(2, 40)))
             G = z.grid_precision(m, n, shift=float(rng.choice([0.01, 0.5])))
             Zg = G
@@ -45,6 +49,16 @@ def run_cases(z, ncases, seed, verbose=False, sim=False, async_sim=False):
         T = float(rng.choice([0.5, 2.0, 6.0]))
         sd = (int(rng.integers(1 << 40)), int(rng.integers(1 << 40)))
         tune = rand_tune()
+        if seq:
+            tune = dict(schedule=2, seq_warps=int(rng.choice([0, 1, 2, 4])))
+            if rng.random() < 0.4 and d >= 6:   # several chains: drop the couplings between K chunks, then scatter the coordinates
+                from zzb200.problems import CSC
+                K = int(rng.integers(2, 5))
+                perm = rng.permutation(d)
+                dense = O.block_diagonal(G, K).to_scipy().toarray() if d % K == 0 else None
+                if dense is not None:
+                    G = CSC.from_dense(dense[np.ix_(perm, perm)])
+                    Zg = G
         adapt = bool(rng.random() < 0.6)
         cs = float(rng.choice([1e-6, 0.3, 1.0, 3.0])) if adapt else float(rng.choice([0.5, 2.0, 4.0]))   # 0.5: provokes bound errors
         c = cs * G.colnorms()
