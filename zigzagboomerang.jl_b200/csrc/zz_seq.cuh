@@ -126,6 +126,8 @@ struct ZzSeqStep {
     int idx[ZZ_SEQ_MAXW];         // local index of the item the warp took (-1: none)
     int verdict[ZZ_SEQ_MAXW];     // 0 nothing / invalidates what follows, 1 rejected, 2 accepted
     int stop;                     // the chain ends after this step (trace buffer full, bound violation, look-ahead hit)
+    int acc_li;                   // local index of the coordinate that flipped in this step (-1: none) and the time of the flip
+    double acc_tp;
 };
 
 // SPECULATIVE THINNING.  87 % of the proposals of config 3 are rejected, and a rejection changes nothing another coordinate
@@ -363,6 +365,7 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
         if (lane == 0) {
             V.idx[wid] = li; V.verdict[wid] = verdict; V.newtau[wid] = rtau;
             if (have && !room) V.stop = 1;
+            if (wid == 0) V.acc_li = -1;
         }
         __syncthreads();
         // does this warp's entry stand?  every earlier entry was rejected and re-queued after (tp, li)
@@ -375,70 +378,82 @@ __device__ __forceinline__ void zz_seq_body(const ZzParams& P, const ZzSeq& Q)
         if (valid && verdict == 1) {
             if (lane == 0) { S.a[li] = ra; S.b[li] = rb; S.told[li] = tp; S.tau[li] = rtau; S.kc[li] = kc + 1u; }
         }
-        ZZ_SP_TOC(2);
-        __syncthreads();   // the rejections of this step are applied before the (one) accepted flip reschedules its neighbourhood
-        ZZ_SP_TIC();
+        // The (at most one) accepted flip of the step: its own coordinate is updated now -- nobody else touches it --, the
+        // rescheduling of its neighbourhood is shared by all warps after the next barrier.
         if (valid && verdict == 2) {
             if (phase == 1) {   // look-ahead only: report the time, leave no trace
                 if (lane == 0) { atomicMin(&C->smin_key[0], zz_key(tp)); V.stop = 1; }
-                continue;
-            }
-            if (lane == 0) atomicAdd(P.acc + jg, 1u);                        // :122
-            if (l >= lb) {                                                   // :123-128
-                if (P.v.adapt) c *= P.v.factor;
-                else {
-                    if (lane == 0) {
-                        if (atomicExch(&C->viol, 1u) == 0u) { C->viol_i = jg + 1; C->viol_t = tp; C->viol_l = l; C->viol_lb = lb; }
-                        V.stop = 1;
+            } else if (l >= lb && !P.v.adapt) {                              // sfact.jl:123-124
+                if (lane == 0) {
+                    atomicAdd(P.acc + jg, 1u);
+                    if (atomicExch(&C->viol, 1u) == 0u) { C->viol_i = jg + 1; C->viol_t = tp; C->viol_l = l; C->viol_lb = lb; }
+                    V.stop = 1;
+                }
+            } else {
+                if (l >= lb) c *= P.v.factor;                                // :125-127
+                nflip++;
+                const int32_t tid = P.trace_map ? __ldg(P.trace_map + jg) : jg + 1;   // id in the trace (0: filtered out, src/trace.jl:275-290)
+                if (lane == 0) {
+                    atomicAdd(P.acc + jg, 1u);                               // :122
+                    // moment sums of the segment that ends here (trace.jl:194), the event (sfact.jl:50-52,143), the flip (:130)
+                    atomicAdd(P.s1 + jg, (xf_i + xi) * (tp - tf_i));
+                    atomicAdd(P.s2 + jg, (tp - tf_i) * (xf_i * xf_i + xf_i * xi + xi * xi));
+                    if (rec && tid != 0) {
+                        double2* e = reinterpret_cast<double2*>(P.trace + tr_pos);
+                        e[0] = make_double2(tp, __longlong_as_double((long long)tid));
+                        e[1] = make_double2(xi, -th_i);
                     }
-                    continue;
+                    S.xf[li] = xi; S.tf[li] = tp; S.th[li] = -th_i; S.c[li] = c; S.kc[li] = kc;
+                    V.acc_li = li; V.acc_tp = tp;
                 }
+                if (rec && tid != 0) tr_pos++;
             }
-            nflip++;
-            const int32_t tid = P.trace_map ? __ldg(P.trace_map + jg) : jg + 1;   // id in the trace (0: filtered out, src/trace.jl:275-290)
-            __syncwarp();
-            if (lane == 0) {
-                // moment sums of the segment that ends here (trace.jl:194), the event (sfact.jl:50-52,143), the flip (:130)
-                atomicAdd(P.s1 + jg, (xf_i + xi) * (tp - tf_i));
-                atomicAdd(P.s2 + jg, (tp - tf_i) * (xf_i * xf_i + xf_i * xi + xi * xi));
-                if (rec && tid != 0) {
-                    double2* e = reinterpret_cast<double2*>(P.trace + tr_pos);
-                    e[0] = make_double2(tp, __longlong_as_double((long long)tid));
-                    e[1] = make_double2(xi, -th_i);
-                }
-                S.xf[li] = xi; S.tf[li] = tp; S.th[li] = -th_i; S.c[li] = c; S.kc[li] = kc;
-            }
-            if (rec && tid != 0) tr_pos++;
-            __syncwarp();
-            // reschedule G1[i] = rows of column i of Z.Gamma (i among them), one neighbour per lane (:131-135); neighbours with a
-            // long column are then served one after the other by the whole warp
-            for (int32_t base = be0; base < be1; base += 32) {
+        }
+        ZZ_SP_TOC(2);
+        __syncthreads();   // the rejections of this step and the flip itself are applied
+        ZZ_SP_TIC();
+        const int ali = V.acc_li;
+        if (ali >= 0) {
+            // reschedule G1[i] = rows of column i of Z.Gamma (i among them; sfact.jl:131-135): warp 0 takes one neighbour per lane,
+            // neighbours with a long column are served cooperatively by the other warps, one each at a time (by warp 0 too when
+            // the chain has a single warp).  Every warp reads the column, so no hand-over is needed.
+            const double atp = V.acc_tp;
+            const int32_t an = lo + ali;
+            const int32_t ae0 = __ldg(Q.bcp + an), ae1 = __ldg(Q.bcp + an + 1);
+            for (int32_t base = ae0; base < ae1; base += 32) {
                 const int32_t e = base + lane;
-                const bool vld = e < be1;
-                int32_t jj = 0, lj = 0, f0 = 0, f1 = 0; double gmu_j = 0.0, Lj = 0.0; uint32_t kj = 0;
+                const bool vld = e < ae1;
+                int32_t jj = 0, lj = 0, f0 = 0, f1 = 0;
                 if (vld) {
                     const int32_t jc = __ldg(Q.brow + e);   // chain-order id of the neighbour
                     lj = jc - lo; jj = S.og ? S.og[lj] : jc;
                     f0 = __ldg(Q.bcp + jc); f1 = __ldg(Q.bcp + jc + 1);
+                }
+                const bool islong = vld && (f1 - f0 > ZZ_SEQ_LONG);
+                const unsigned int lm = __ballot_sync(0xffffffffu, islong);
+                const bool mine_short = vld && !islong && wid == 0;
+                const int nth = islong ? __popc(lm & ((1u << lane) - 1u)) : -1;            // rank among the long neighbours of the chunk
+                const bool mine_long = islong && (nw == 1 ? true : (1 + nth % (nw - 1)) == wid);
+                double gmu_j = 0.0, Lj = 0.0; uint32_t kj = 0;
+                if (mine_short || mine_long) {
                     gmu_j = __ldg(P.g.gmu + jj);
                     kj = S.kc[lj];
                     Lj = zz_log(zz_u01(seed0, seed1, (uint64_t)jj, (uint64_t)(kj++)));
                 }
-                const bool islong = vld && (f1 - f0 > ZZ_SEQ_LONG);
                 double sxj = 0.0, stj = 0.0;
-                if (vld && !islong) zz_seq_col_serial(S, Q.brow, Q.bval, f0, f1, tp, sxj, stj);
-                for (unsigned int lm = __ballot_sync(0xffffffffu, islong); lm; lm &= lm - 1u) {
-                    const int src = __ffs((int)lm) - 1;
+                if (mine_short) zz_seq_col_serial(S, Q.brow, Q.bval, f0, f1, atp, sxj, stj);
+                for (unsigned int ml = __ballot_sync(0xffffffffu, mine_long); ml; ml &= ml - 1u) {
+                    const int src = __ffs((int)ml) - 1;
                     double cx, ct;
-                    zz_seq_col_coop(S, Q.brow, Q.bval, __shfl_sync(0xffffffffu, f0, src), __shfl_sync(0xffffffffu, f1, src), tp, lane, cx, ct);
+                    zz_seq_col_coop(S, Q.brow, Q.bval, __shfl_sync(0xffffffffu, f0, src), __shfl_sync(0xffffffffu, f1, src), atp, lane, cx, ct);
                     if (lane == src) { sxj = cx; stj = ct; }
                 }
-                if (vld) {
+                if (mine_short || mine_long) {
                     const double cj = S.c[lj], thj = S.th[lj];
                     const double aj = cj + (sxj - gmu_j) * thj;               // fact_samplers.jl:51-52
                     const double bj = cj / 100 + thj * stj;
-                    const double tj = tp + zz_poisson_time_L(aj, bj, Lj);
-                    S.a[lj] = aj; S.b[lj] = bj; S.told[lj] = tp; S.tau[lj] = tj; S.kc[lj] = kj;
+                    const double tj = atp + zz_poisson_time_L(aj, bj, Lj);
+                    S.a[lj] = aj; S.b[lj] = bj; S.told[lj] = atp; S.tau[lj] = tj; S.kc[lj] = kj;
                 }
             }
             ZZ_SP_TOC(3);
