@@ -171,7 +171,7 @@ int32_t zzb_run_upload_boomerang(zzb_run_t r, const double* sigma, double lambda
 int32_t zzb_run_upload_refresh(zzb_run_t r, const double* sigma, double lambdaref);   /* ZZB_FLAG_REFRESH runs: before zzb_run_upload */
 int32_t zzb_run_reset(zzb_run_t r);                                  /* re-initialise from the inputs resident in HBM */
 int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms);   /* device_ms: CUDA-event time of the kernel(s) */
-int32_t zzb_run_set(zzb_run_t r, const char* key, double value);    /* "delta0", "target_frac" / "target_flip_frac" (proposals / accepted flips per window over d), "tag_limit", "max_windows", "grid", "host_sort", "strong_c" / "strong_rule" (sparsestickyzz), "seq_warps" (sequential chains: 1, 2 or 4 warps per chain thinning speculatively; 0 = automatic), "schedule": -1 automatic (default: sequential chains for the logistic target and for chains of at most 64 coordinates or densely coupled ones, else 1), 2 sequential chains -- one warp per connected component runs spdmp_inner! (src/sfact.jl:73-145) as written; plain ZigZag, components of at most 2700 coordinates --, 1 windowed asynchronous relaxation, 0 its pass-synchronous predecessor */
+int32_t zzb_run_set(zzb_run_t r, const char* key, double value);    /* "delta0", "target_frac" / "target_flip_frac" (proposals / accepted flips per window over d), "tag_limit", "max_windows", "grid", "host_sort", "strong_c" / "strong_rule" (sparsestickyzz), "seq_warps" (sequential chains: 1, 2, 4 or 8 warps per chain thinning speculatively; 0 = automatic), "schedule": -1 automatic (default: sequential chains for the logistic target and for chains of at most 64 coordinates or densely coupled ones, else 1), 2 sequential chains -- one warp per connected component runs spdmp_inner! (src/sfact.jl:73-145) as written; plain ZigZag, components of at most 2700 coordinates --, 1 windowed asynchronous relaxation, 0 its pass-synchronous predecessor */
 int32_t zzb_run_stats(zzb_run_t r, int64_t* out, int32_t n);        /* windows, retries, passes, node evaluations, rebases,
                                                                        kernel launches, grid size, block size */
 

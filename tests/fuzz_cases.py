@@ -50,7 +50,7 @@ def run_cases(z, ncases, seed, verbose=False, sim=False, async_sim=False, seq=Fa
         sd = (int(rng.integers(1 << 40)), int(rng.integers(1 << 40)))
         tune = rand_tune()
         if seq:
-            tune = dict(schedule=2, seq_warps=int(rng.choice([0, 1, 2, 4])))
+            tune = dict(schedule=2, seq_warps=int(rng.choice([0, 1, 2, 4, 8])))
             if rng.random() < 0.4 and d >= 6:   # several chains: drop the couplings between K chunks, then scatter the coordinates
                 from zzb200.problems import CSC
                 K = int(rng.integers(2, 5))

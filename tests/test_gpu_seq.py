@@ -40,7 +40,7 @@ def test_general_sparse_with_mu_h_adapt(gpu, seed):
     assert (got.c != c).any()
 
 
-@pytest.mark.parametrize("warps", [1, 2, 4])
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
 def test_speculative_thinning_any_number_of_warps(gpu, warps):
     """The warps of a chain take the earliest queue entries side by side; an entry counts only if every earlier one of the step
     was rejected and re-queued later.  Same bits for 1, 2 and 4 warps: Gaussian chains (several components, tight and loose

@@ -79,7 +79,7 @@ static inline void zz_build_seq(ZzHostSeq& S, int64_t d, const int64_t* bcp, con
     int64_t cm = 32;
     for (int64_t j = 0; j < d; ++j) { cm = std::max(cm, bcp[j + 1] - bcp[j]); if (tcp) cm = std::max(cm, tcp[j + 1] - tcp[j]); }
     S.colmax = (int32_t)((cm + 1) & ~(int64_t)1);
-    if (80 * (int64_t)S.ncmax + 8 + 4 * 8 * (72 + 2 * ((int64_t)S.colmax + 8)) > 220 * 1024) {   // (state + the scratch of four warps)
+    if (80 * (int64_t)S.ncmax + 8 + 8 * 8 * (72 + 2 * ((int64_t)S.colmax + 8)) > 220 * 1024) {   // (state + the scratch of eight warps)
         S.why = "the largest component (" + std::to_string(nmax) + " coordinates, longest column " + std::to_string(cm) + ") does not fit into the shared memory of an SM";
         return;
     }

@@ -118,7 +118,7 @@ __device__ __forceinline__ void zz_seq_argmin(double bt, int bi, double& tp, int
     tp = zz_unkey(((unsigned long long)mh << 32) | (unsigned long long)ml);
 }
 
-#define ZZ_SEQ_MAXW 4   // warps per chain
+#define ZZ_SEQ_MAXW 8   // warps per chain
 
 // Verdicts of one step, one per warp (shared memory)
 struct ZzSeqStep {

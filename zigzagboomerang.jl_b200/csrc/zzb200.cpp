@@ -717,7 +717,7 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
     else if (!strcmp(key, "host_sort")) r->host_sort_only = value != 0.0;   // order the trace on the host (A/B of the device sort)
     else if (!strcmp(key, "eval_threads")) r->eval_threads = (unsigned int)value;
-    else if (!strcmp(key, "seq_warps")) r->seq_warps = (int)value;   // sequential chains: 1 (plain loop), 2 or 4 warps per chain; 0 = automatic
+    else if (!strcmp(key, "seq_warps")) r->seq_warps = (int)value;   // sequential chains: 1 (plain loop), 2, 4 or 8 warps per chain; 0 = automatic
     else if (!strcmp(key, "schedule")) {   // 0 / 1: windowed relaxation (pass-synchronous / asynchronous); 2: sequential chains; -1: automatic
         const int v = (int)value;
         if (v < -1 || v > 2) return fail(ZZB_E_ARG, "schedule must be -1, 0, 1 or 2");
@@ -934,11 +934,11 @@ static int32_t execute_seq(zzb_run_s* r, double T, float* device_ms)
     // chains share the SMs (registers: six chains of two warps fit), unless zzb_run_set("seq_warps") says otherwise
     auto smem_for = [&](int w) { return (Q.orig ? 80u : 76u) * (unsigned)Q.ncmax + 8u + (unsigned)w * 8u * (72u + 2u * ((unsigned)Q.colmax + 8u)); };   // state + scratch per warp
     CUfunction f = pb->logit ? G.f_seq_logit : G.f_seq;
-    CU(cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::max(smem_for(4), 48u * 1024u)));
+    CU(cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::min(std::max(smem_for(8), 48u * 1024u), 227u * 1024u)));
     int nw = r->seq_warps;
-    if (nw != 1 && nw != 2 && nw != 4) {   // automatic: the most warps per chain with which all chains are resident at once
+    if (nw != 1 && nw != 2 && nw != 4 && nw != 8) {   // automatic: the most warps per chain with which all chains are resident at once
         nw = 1;
-        for (int w = 4; w >= 2; w >>= 1) {
+        for (int w = 8; w >= 2; w >>= 1) {
             int per_sm = 0;
             CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, 32 * w, smem_for(w)));
             if ((long long)Q.ncomp <= (long long)per_sm * G.sm_count) { nw = w; break; }
