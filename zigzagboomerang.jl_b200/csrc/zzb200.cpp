@@ -936,13 +936,11 @@ static int32_t execute_seq(zzb_run_s* r, double T, float* device_ms)
     CUfunction f = pb->logit ? G.f_seq_logit : G.f_seq;
     CU(cuFuncSetAttribute(f, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)std::min(std::max(smem_for(8), 48u * 1024u), 227u * 1024u)));
     int nw = r->seq_warps;
-    if (nw != 1 && nw != 2 && nw != 4 && nw != 8) {   // automatic: the most warps per chain with which all chains are resident at once
-        nw = 1;
-        for (int w = 8; w >= 2; w >>= 1) {
-            int per_sm = 0;
-            CU(cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, 32 * w, smem_for(w)));
-            if ((long long)Q.ncomp <= (long long)per_sm * G.sm_count) { nw = w; break; }
-        }
+    if (nw != 1 && nw != 2 && nw != 4 && nw != 8) {
+        // automatic: eight warps per chain while every chain has an SM of its own (latency of the single chain), else four --
+        // measured (profiles/r02_logit_seq.log): with many chains four warps each give the best throughput even in several
+        // waves (888 chains: 1.4e7 events/s with 4 warps in two waves, 1.2e7 with 1 warp each and all resident)
+        nw = (Q.ncomp <= G.sm_count) ? 8 : 4;
     }
     while (nw > 1 && P.record_trace && r->trace_cap < (unsigned long long)ZZ_SEQ_RES_HOST * (unsigned long long)Q.ncomp * (unsigned long long)nw)
         nw >>= 1;   // (every warp of every chain may hold one reservation of trace records)
