@@ -200,6 +200,7 @@ struct zzb_run_s {
     DevBuf dbgbuf; std::vector<unsigned long long> dbghost;
     int tile_per = 0; unsigned int eval_threads = 0; int inbox_nr = 0;
     int seq_warps = 0;                 // sequential chains: warps per chain (0 = automatic)
+    bool window_policy_set = false;    // target_frac / target_flip_frac were set by the caller
     // device-side ordering of the trace (zz_tsort_*): the events of the last execute, sorted, still in HBM
     DevBuf cm_work, cm_out;            // cummean on the device (zzb_trace_cummean)
     DevBuf trace_sorted, ts_work; bool dev_sorted = false; unsigned long long n_sorted = 0; bool host_sort_only = false;
@@ -711,8 +712,8 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
 {
     if (!r || !key) return fail(ZZB_E_ARG, "null argument");
     if (!strcmp(key, "delta0")) r->delta0 = value;
-    else if (!strcmp(key, "target_frac")) r->target_frac = value;
-    else if (!strcmp(key, "target_flip_frac")) r->target_flip_frac = value;
+    else if (!strcmp(key, "target_frac")) { r->target_frac = value; r->window_policy_set = true; }
+    else if (!strcmp(key, "target_flip_frac")) { r->target_flip_frac = value; r->window_policy_set = true; }
     else if (!strcmp(key, "tag_limit")) r->tag_limit = (unsigned int)value;
     else if (!strcmp(key, "max_windows")) r->max_windows = (unsigned int)value;
     else if (!strcmp(key, "host_sort")) r->host_sort_only = value != 0.0;   // order the trace on the host (A/B of the device sort)
@@ -1042,8 +1043,13 @@ int32_t zzb_run_execute(zzb_run_t r, double T, float* device_ms)
     P.T = T;
     double span = T - r->t0;
     P.delta0 = r->delta0 > 0 ? r->delta0 : std::max(1e-12, 1e-2 * std::min(1.0, span > 0 ? span : 1.0));
-    P.target = std::max(r->target_frac * (double)r->d, 4.0);              // proposals per window
-    P.target_flips = std::max(r->target_flip_frac * (double)r->d, 2.0);   // cap on accepted flips per window
+    // window length policy: proposals per window (and a cap on the accepted flips) as fractions of d.  Defaults measured on a B200:
+    // 0.25 / 0.045 at d = 10^6 (longer windows lengthen the wait for the slowest tile); small problems -- a tile of a few dozen
+    // coordinates per SM -- want windows four times longer (d = 10^4: 9.3e6 -> 1.27e7 switches/s)
+    double tfrac = r->target_frac, ffrac = r->target_flip_frac;
+    if (!r->window_policy_set && r->d <= 30000) { tfrac = 1.0; ffrac = 0.18; }
+    P.target = std::max(tfrac * (double)r->d, 4.0);              // proposals per window
+    P.target_flips = std::max(ffrac * (double)r->d, 2.0);        // cap on accepted flips per window
     P.tag_limit = r->tag_limit; P.max_windows = r->max_windows;
     float total_ms = 0.f;
     if (device_ms) *device_ms = 0.f;
