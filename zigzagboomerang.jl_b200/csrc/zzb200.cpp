@@ -722,6 +722,7 @@ int32_t zzb_run_set(zzb_run_t r, const char* key, double value)
     else if (!strcmp(key, "schedule")) {   // 0 / 1: windowed relaxation (pass-synchronous / asynchronous); 2: sequential chains; -1: automatic
         const int v = (int)value;
         if (v < -1 || v > 2) return fail(ZZB_E_ARG, "schedule must be -1, 0, 1 or 2");
+        if (r->executed) return fail(ZZB_E_ARG, "the schedule of a run is chosen before its first zzb_run_execute (zzb_run_reset starts over)");
         if (v == 2 && !r->seq_capable())
             return fail(ZZB_E_ARG, "the sequential-chain schedule is not available for this run (%s)",
                         r->prob->hs.ok ? "plain ZigZag on one GPU only, no device-side discretisation" : r->prob->hs.why.c_str());
