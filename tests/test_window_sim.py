@@ -307,3 +307,50 @@ def test_wide_columns_of_the_velocity_list_samplers(zzb, tiles):
     got = O.window_sim(G, Zg, 0.0, xb, thb, 3.0, cb, seed=(5, 6), boom=(bsig, 20.0, 0.2), async_tiles=tiles)
     O.assert_same_run(ref, got)
     assert len(ref.events) > 50
+
+
+def test_sticky_family_randomised_campaign(zzb):
+    """Random sticky problems through the device timeline inside the schedule emulation against the oracle: sspdmp and sspdmp2
+    (stickyzz: rate floor, frozen starts), with and without reversible / strong_upperbounds / adapt, per-coordinate thaw rates,
+    non-unit speeds, linear term, lattices and general sparse graphs with columns up to 32 entries, both schedules."""
+    rng = np.random.default_rng(77)
+    nbound = 0
+    for case in range(36):
+        if rng.random() < 0.5:
+            G = zzb.grid_precision(int(rng.integers(2, 12)), int(rng.integers(2, 12)), shift=float(rng.choice([0.1, 0.5])))
+        else:
+            G = zzb.random_sparse_spd(int(rng.integers(4, 90)), deg=int(rng.integers(1, 6)), seed=int(rng.integers(1 << 30)))
+            if np.diff(G.colptr).max() > 32:
+                continue
+        d = G.n
+        stickyzz = bool(rng.random() < 0.5)
+        x0 = np.where(rng.random(d) < (0.7 if stickyzz else 1.0), rng.standard_normal(d), 0.0 if stickyzz else 1e-3)
+        th0 = rng.choice(np.array([-1.5, -1.0, -0.5, 0.5, 1.0, 1.5]), d)
+        h = 0.3 * rng.standard_normal(d) if rng.random() < 0.3 else None
+        adapt = bool(rng.random() < 0.5)
+        cs = float(rng.choice([0.05, 0.5, 3.0])) if adapt else float(rng.choice([0.5, 3.0, 6.0]))
+        c = cs * G.colnorms() + (np.abs(h) if h is not None else 0.0)
+        kap = rng.choice(np.array([0.2, 0.8, 3.0]), d)
+        rev, sub = bool(rng.random() < 0.3), bool(rng.random() < 0.3)
+        mode = O.PARITY_MODE | (O.STICKYZZ if stickyzz else 0) | (O.STICKY_REVERSIBLE if rev else 0) | (O.STICKY_STRONG_UB if sub else 0)
+        T = float(rng.choice([1.0, 4.0, 9.0]))
+        sd = (int(rng.integers(1 << 40)), int(rng.integers(1 << 40)))
+        Gb = G.scaled(float(rng.choice([0.7, 1.0, 1.2]))) if rng.random() < 0.5 else G
+        kw = dict(delta0=float(10 ** rng.uniform(-3, 0.3)), target_frac=float(10 ** rng.uniform(-1.3, 0.7)))
+        if case % 2:
+            kw.update(async_tiles=int(rng.integers(1, 7)), order_seed=int(rng.integers(1, 1 << 30)))
+        try:
+            ref = O.spdmp(G, Gb, 0.0, x0, th0, T, c, h=h, kappa=kap, mode=mode, adapt=adapt, factor=1.5, seed=sd)
+        except O.BoundError:
+            ref = None
+        try:
+            got = O.window_sim(G, Gb, 0.0, x0, th0, T, c, h=h, kappa=kap, stickyzz=stickyzz, reversible=rev, strong_upperbounds=sub,
+                               adapt=adapt, factor=1.5, seed=sd, **kw)
+        except O.BoundError:
+            got = None
+        assert (ref is None) == (got is None), case
+        if ref is None:
+            nbound += 1
+        else:
+            O.assert_same_run(ref, got)
+    assert nbound < 30
